@@ -1,0 +1,202 @@
+/*
+ * m3b200.h -- C ABI of libm3b200.so: the B200-native (sm_100a) per-MCMC-step likelihood hot path
+ * of MaCh3:  event-by-event TSpline3 / TF1 response evaluation -> per-event total weight ->
+ * histogram fill -> Poisson / Barlow-Beeston -lnL, fused on the device.
+ *
+ * The reference (mach3-software/MaCh3 v2.4.2) has no FFI for this path; its seam is C++ virtual
+ * dispatch plus ONE class that isolates CUDA from host code, `SMonolithGPU`
+ * (Splines/gpuSplineUtils.cuh:63-218).  Every entry point below names the reference interface it
+ * replaces (file:line relative to the MaCh3 tree).  INTEGRATION.md shows the reference-side
+ * bindings (a drop-in SMonolithGPU, a SampleHandlerFD::Reweight/GetLikelihood override, ctypes).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer; the library copies on
+ *     upload and never returns pointers into its own host memory (device pointers are returned
+ *     only by the explicit *_device_ptr calls used to wire collectives).
+ *   - every function returns an m3b_status; m3b_last_error() gives the message.  Unlike the
+ *     reference's CudaCheckError (a no-op in release builds, Manager/gpuUtils.cu:18-35) every CUDA
+ *     call is checked.  There is NO CPU fallback: without a usable sm_100 device m3b_create fails.
+ *   - one handle = one SampleHandlerFD (+ its SMonolith).  Not thread-safe per handle, like the
+ *     reference (one host thread drives the chain).
+ *   - m3b_step* are asynchronous on the handle's stream; m3b_llh / m3b_read_* synchronise, which is
+ *     the contract of SplineBase::Evaluate + SynchroniseMemTransfer (Splines/SplineBase.h:35,50).
+ *   - types follow the reference's _LOW_MEMORY_STRUCTS_ build (float weights/coefficients, short
+ *     segments, double histograms and likelihood; Manager/Core.h:27-35).
+ */
+#ifndef M3B200_H
+#define M3B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define M3B_API __attribute__((visibility("default")))
+#else
+#define M3B_API
+#endif
+
+typedef struct m3b_handle m3b_handle;
+
+typedef enum {
+  M3B_OK = 0,
+  M3B_ERR_INVALID = 1,   /* bad argument / inconsistent arrays                                     */
+  M3B_ERR_CUDA = 2,      /* a CUDA runtime call or kernel failed                                   */
+  M3B_ERR_STATE = 3,     /* call order violated (e.g. step before upload)                          */
+  M3B_ERR_KNOTS = 4,     /* a spline's knot count differs from its parameter's (reference assumes  */
+                         /* identical knots per parameter, Splines/SplineMonolith.cpp:102-104)     */
+  M3B_ERR_NOMEM = 5,
+  M3B_ERR_NODEVICE = 6,  /* no sm_100 device: the product path has no CPU fallback                 */
+  M3B_ERR_PEER = 7       /* peer (multi-GPU) exchange failed or timed out                          */
+} m3b_status;
+
+/* Samples/SampleStructs.h:105-112 (same numeric values as enum TestStatistic) */
+typedef enum {
+  M3B_POISSON = 0, M3B_BARLOW_BEESTON = 1, M3B_ICECUBE = 2, M3B_PEARSON = 3, M3B_DEMBINSKI_ABDELMOTTELEB = 4
+} m3b_test_statistic;
+
+enum {
+  M3B_FLAG_KEEP_EVENT_WEIGHTS = 1, /* write per-event spline + total weights every step (+8 B/event)   */
+  M3B_FLAG_KEEP_KINEMATICS    = 2, /* keep kinematic variables on the device so bins can be recomputed */
+  M3B_FLAG_NO_FUSED_LLH       = 4  /* never fuse the LLH into the fill kernel (multi-GPU callers)      */
+};
+
+typedef struct {
+  int32_t device;          /* CUDA ordinal                                                          */
+  int32_t test_statistic;  /* m3b_test_statistic; LikelihoodOptions:TestStatistic (Manager.cpp:98-127)*/
+  int32_t update_w2;       /* LikelihoodOptions:UpdateW2 (Samples/SampleHandlerFD.cpp:64)            */
+  int32_t tile_events;     /* events per tile = threads per block: 0 (=256), 128, 256, 512           */
+  int32_t flags;           /* M3B_FLAG_*                                                            */
+  int32_t reserved[11];
+} m3b_config;
+
+/* ---- lifetime --------------------------------------------------------------------------------
+ * replaces SMonolithGPU::SMonolithGPU / InitGPU_* / Cleanup* (Splines/gpuSplineUtils.cu:80-190,
+ * 520-557) and the device-side half of SampleHandlerFD's arrays (SampleHandlerFD.cpp:749-754).   */
+M3B_API int m3b_create(const m3b_config* cfg, m3b_handle** out);
+M3B_API void m3b_destroy(m3b_handle* h);
+M3B_API const char* m3b_last_error(const m3b_handle* h);   /* h may be NULL: last global error      */
+M3B_API int m3b_abi_version(void);
+/* run everything on this cudaStream_t (e.g. the caller's current stream); default: own stream    */
+M3B_API int m3b_set_stream(m3b_handle* h, void* cuda_stream);
+
+/* ---- spline monolith -------------------------------------------------------------------------
+ * replaces SMonolithGPU::InitGPU_SplineMonolith + CopyToGPU_SplineMonolith
+ * (Splines/gpuSplineUtils.cu:103-168, 193-330).  Arrays are the reference's own
+ * (SplineMonoStruct, Splines/SplineCommon.h:30-50; SMonolith members, SplineMonolith.h:96-137):
+ *   coeff_x[n_params*max_knots]  knot x per parameter          n_pts[n_params] knots per parameter
+ *                                                              (FastSplineInfo::nPts, 0 = none)
+ * then, per chunk of events (any chunking; offsets relative to the chunk):
+ *   nParamPerEvent[2n]     {count,start} of TSpline3 responses (start is recomputed from counts)
+ *   paramNo_arr[tot_c]     parameter of each response          nKnots_arr[tot_c] first-knot offset
+ *   coeff_many[total_knots*4]  AoS {y,b,c,d}
+ *   nParamPerEvent_tf1[2n], paramNo_tf1[tot_l], coeff_tf1[tot_l*2] {a,b}   (TF1: a*x+b)
+ * The library re-tiles into its own SoA layout on the device.                                      */
+M3B_API int m3b_splines_begin(m3b_handle* h, int32_t n_params, int32_t max_knots,
+                              const float* coeff_x, const int16_t* n_pts, int64_t n_events_total);
+M3B_API int m3b_splines_append(m3b_handle* h, int64_t n_events,
+                               const uint32_t* nParamPerEvent, const int16_t* paramNo_arr,
+                               const uint64_t* nKnots_arr, uint64_t total_knots, const float* coeff_many,
+                               const uint32_t* nParamPerEvent_tf1, const int16_t* paramNo_tf1,
+                               const float* coeff_tf1);
+M3B_API int m3b_splines_end(m3b_handle* h);
+/* one-shot form with exactly the reference's types (unsigned int knot offsets) */
+M3B_API int m3b_upload_spline_monolith(m3b_handle* h, int32_t n_params, int32_t max_knots,
+                                       const float* coeff_x, const int16_t* n_pts, int64_t n_events,
+                                       const uint32_t* nParamPerEvent, const int16_t* paramNo_arr,
+                                       const uint32_t* nKnots_arr, uint32_t total_knots, const float* coeff_many,
+                                       const uint32_t* nParamPerEvent_tf1, const int16_t* paramNo_tf1,
+                                       const float* coeff_tf1);
+
+/* ---- binning, events, data -------------------------------------------------------------------
+ * m3b_upload_binning: BinningHandler's uniform binning (Samples/BinningHandler.cpp:341-355,
+ *   SampleBinningInfo Samples/SampleStructs.h:232-676): per sample n_dim[s] axes, nbins[s*4+d],
+ *   edges concatenated sample-major, dim-major.  Global bin = sum bin_d*stride_d + GlobalOffset.
+ * m3b_upload_events: what SampleHandlerFD::Initialise wires per event (SampleHandlerFD.cpp:169-202)
+ *   sample_id[E]          EventInfo::NominalSample
+ *   kin[d*E+e]            *EventInfo::KinVar[d]   (bins are found on the device with
+ *                         FindGlobalBin semantics, BinningHandler.cpp:257-277 -> SampleStructs.h:577-613)
+ *   norm_idx[e*npe+j]     index into the per-step norm value array (EventInfo::norm_pointers as
+ *                         offsets from ParameterHandlerBase::_fPropVal), <0 = none
+ *   osc_idx[E]            index into the per-step oscillation weight array (osc_w_pointer as an
+ *                         offset), NULL = event e reads osc[e]; use_osc=0: no osc weight at all
+ *   static_w[E]           product of the event's constant extra weights, NULL = none
+ * Events must come in the same order as the spline monolith's events.                              */
+M3B_API int m3b_upload_binning(m3b_handle* h, int32_t n_samples, const int32_t* n_dim,
+                               const int32_t* nbins /*[n_samples*4]*/, const double* edges);
+M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sample_id, const double* kin,
+                              int32_t n_norm_per_event, const int16_t* norm_idx, int32_t n_norm_values,
+                              int32_t use_osc, const int32_t* osc_idx, int64_t n_osc_values,
+                              const float* static_w);
+/* SampleHandlerFD::AddData (Samples/SampleHandlerFD.cpp:955-1044), array form */
+M3B_API int m3b_upload_data(m3b_handle* h, const double* data, int32_t n_bins);
+/* oscillation weights computed elsewhere (NuOscillator) and already valid for the next steps    */
+M3B_API int m3b_upload_osc(m3b_handle* h, const float* osc_w, int64_t n);
+/* pin the caller's persistent oscillation-weight array so per-step copies are true DMA           */
+M3B_API int m3b_register_host_buffer(m3b_handle* h, void* ptr, uint64_t bytes);
+M3B_API int m3b_set_test_statistic(m3b_handle* h, int32_t test_statistic);   /* SampleHandlerBase.h:185 */
+M3B_API int m3b_reset_w2(m3b_handle* h);   /* FirstTimeW2 = true again                              */
+
+/* ---- the step --------------------------------------------------------------------------------
+ * m3b_step = SampleHandlerFD::Reweight (Samples/SampleHandlerFD.cpp:316-343):
+ *   ResetHistograms -> SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-109, on the host,
+ *   with the reference's cached-segment history) -> CalcSplineWeights + CalcTotalEventWeight
+ *   (Splines/SplineMonolith.cpp:727-830) -> FillArray_MP (SampleHandlerFD.cpp:390-448) -> the
+ *   GetLikelihood reduction (SampleHandlerFD.cpp:1284-1300), all in one device pass.
+ *   spline_pars[n_params]   the doubles behind FastSplineInfo::splineParsPointer
+ *   norm_pars[n_norm_values] the doubles behind EventInfo::norm_pointers
+ *   osc_w                   host array of this step's oscillation weights (copied H2D inside the
+ *                           call), or NULL to keep the weights already on the device
+ * m3b_step_segments = SMonolithGPU::RunGPU_SplineMonolith's contract
+ *   (Splines/gpuSplineUtils.cu:444-512): the caller already ran FindSplineSegment and passes
+ *   ParamValues (float) and SplineSegments (short).
+ * m3b_llh = SampleHandlerFD::GetLikelihood / GetSampleLikelihood: blocks, returns -lnL (NOT -2lnL).  */
+M3B_API int m3b_step(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w);
+M3B_API int m3b_step_segments(m3b_handle* h, const float* param_values, const int16_t* segments,
+                              const double* norm_pars, const float* osc_w);
+M3B_API int m3b_llh(m3b_handle* h, double* total, double* per_sample /* [n_samples] or NULL */);
+/* SplineBase::FindSplineSegment alone (host, history-dependent); outputs are optional            */
+M3B_API int m3b_find_segments(m3b_handle* h, const double* spline_pars, int16_t* segments, float* param_values);
+M3B_API int m3b_synchronize(m3b_handle* h);   /* SplineBase::SynchroniseMemTransfer                 */
+
+/* ---- read-back (lazy host mirrors) -----------------------------------------------------------
+ * m3b_read_hist           SampleHandlerFD_array / _array_w2 (SampleHandlerFD.h:337-341)
+ * m3b_read_event_weights  spline_w[e] = *SMonolith::retPointer(e) (Splines/SplineMonolith.h:40);
+ *                         total_w[e] = CalcWeightTotal (SampleHandlerFD.cpp:568-594); either may be NULL
+ * m3b_read_event_bins     FindGlobalBin per event (-1 = under/overflow)                              */
+M3B_API int m3b_read_hist(m3b_handle* h, double* mc, double* w2);
+M3B_API int m3b_read_event_weights(m3b_handle* h, float* spline_w, float* total_w);
+M3B_API int m3b_read_event_bins(m3b_handle* h, int32_t* bins);
+
+/* ---- multi-GPU: one process per GPU, events sharded, partial histograms summed ---------------
+ * (new capability: the reference supports one GPU, Manager/gpuUtils.cu:71.)
+ * m3b_step_fill           like m3b_step but stops after the partial histogram (no LLH)
+ * m3b_hist_device_ptr     device address of {mc[n_bins], w2[n_bins]} (contiguous, 2*n_bins doubles)
+ *                         so the caller can all-reduce it in place (NCCL through torch.distributed)
+ * m3b_llh_from_hist       enqueue the LLH reduction over the (now global) histogram
+ * m3b_peer_*              the library's own exchange over NVLink peer memory: every rank pushes its
+ *                         partial histogram into each peer's inbox from inside the fill kernel's
+ *                         last block; the LLH kernel waits for the N arrivals and sums in rank order. */
+M3B_API int m3b_step_fill(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w);
+M3B_API int m3b_hist_device_ptr(m3b_handle* h, void** dev_ptr, int32_t* n_bins, int32_t* w2_live);
+M3B_API int m3b_llh_from_hist(m3b_handle* h);
+M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ipc_handle_64B);
+M3B_API int m3b_peer_import(m3b_handle* h, int32_t peer_rank, const void* ipc_handle_64B);
+M3B_API int m3b_step_peer(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_events, n_tiles;
+  int32_t n_params, n_bins, n_samples, n_signatures;
+  int32_t tile_events, grid_blocks, smem_bytes, hist_in_smem;
+  uint64_t device_bytes;          /* HBM held by the handle                                       */
+  uint64_t active_bytes_per_step; /* coefficient + event-table bytes one step actually loads       */
+  uint64_t steps, kernel_launches;
+} m3b_info;
+M3B_API int m3b_get_info(m3b_handle* h, m3b_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

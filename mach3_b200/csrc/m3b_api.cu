@@ -1,0 +1,978 @@
+// m3b_api.cu -- host side of libm3b200.so: the C ABI declared in include/m3b200.h.
+// Owns all device state; re-tiles the reference's AoS monolith into the tiled SoA layout;
+// mirrors SplineBase::FindSplineSegment on the host (O(nParams), history-dependent); enqueues one
+// fused kernel per step.  No CPU fallback: every compute entry point needs the sm_100 device.
+#include "m3b200.h"
+#include "m3b_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace m3b;
+
+static thread_local std::string g_last_error;
+
+struct m3b_handle {
+  m3b_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // ---- spline parameters (FastSplineInfo, Splines/SplineStructs.h:21-44)
+  int P = 0, Kmax = 0;
+  std::vector<float> coeff_x;
+  std::vector<int16_t> n_pts;
+  std::vector<int16_t> curr_segment;     // FastSplineInfo::CurrSegment
+  std::vector<int16_t> segments;         // SplineBase::SplineSegments
+  std::vector<float> param_values;       // SplineBase::ParamValues
+  std::vector<int16_t> nseg;             // stored segments per parameter (n_pts-1)
+  bool splines_open = false, splines_done = false;
+  int64_t n_events_total = 0, n_events_loaded = 0;
+  int T = 256;
+
+  // ---- signatures and tiles
+  std::map<std::vector<int16_t>, int> sig_index;   // key: cubic params, -1, linear params
+  std::vector<SigDesc> sigs;
+  std::vector<int32_t> sig_pool;
+  std::vector<int16_t> sig_slot_of_param;          // [n_sigs*P]
+  std::vector<int32_t> sig_segbase_of_param;       // [n_sigs*P]
+  std::vector<TileDesc> tiles;
+  std::vector<void*> allocs;
+  uint64_t device_bytes = 0;
+  uint64_t active_coef_bytes = 0;
+  int max_nc = 0, max_nl = 0;
+  TileDesc* d_tiles = nullptr;
+  SigDesc* d_sigs = nullptr;
+  int32_t* d_sig_pool = nullptr;
+  bool tiles_dirty = true;
+
+  // ---- binning
+  int n_samples = 0, n_bins = 0;
+  std::vector<int32_t> b_ndim, b_nbins, b_edge_off, b_stride, b_goff, sample_start;
+  std::vector<double> b_edges;
+  int32_t *d_ndim = nullptr, *d_nbins = nullptr, *d_edge_off = nullptr, *d_stride = nullptr, *d_goff = nullptr,
+          *d_sample_start = nullptr;
+  double* d_edges = nullptr;
+
+  // ---- events
+  int64_t n_events = 0, e_pad = 0, n_tiles = 0;
+  int32_t* d_bin = nullptr;
+  int32_t* d_osc_idx = nullptr;
+  float* d_osc = nullptr;
+  int64_t n_osc = 0;
+  bool use_osc = false;
+  float* d_static = nullptr;
+  int16_t* d_norm_idx = nullptr;
+  int norm_slots = 0, n_norm_values = 0;
+  double* d_kin = nullptr;
+  int32_t* d_sample_id = nullptr;
+  float *d_evt_spline_w = nullptr, *d_evt_total_w = nullptr;
+  bool evt_weights_valid = false;
+
+  // ---- histograms, likelihood
+  double* d_hw[2] = {nullptr, nullptr};   // each {mc[n_bins], w2[n_bins]}
+  bool mc_zero[2] = {false, false}, w2_zero[2] = {false, false};
+  int cur = 0;                            // buffer of the last step
+  double* d_w2_frozen = nullptr;
+  double* d_data = nullptr;
+  unsigned int* d_ticket = nullptr;
+  double* d_llh = nullptr;
+  double* h_llh = nullptr;                // mapped pinned
+  double* h_llh_dev = nullptr;            // device alias of h_llh
+  int test_stat = 0;
+  bool first_time_w2 = true;
+  bool last_w2_live = false;
+
+  // ---- per-step staging
+  StepLayout step{};
+  static constexpr int kRing = 4;
+  unsigned char* h_step[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t step_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned char* d_step[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  int ring = 0;
+  std::vector<unsigned char> last_step_table;
+  bool have_step = false;
+
+  // ---- launch configuration
+  int grid = 0, smem = 0;
+  bool hist_in_smem = true;
+  bool launch_ready = false;
+  bool launch_w2_live = false;
+
+  // ---- peer exchange
+  int peer_world = 0, peer_rank = 0;
+  double* d_inbox[2] = {nullptr, nullptr};       // own inboxes (two epochs' parity), [world*2*n_bins]
+  unsigned int* d_flags[2] = {nullptr, nullptr}; // [world]
+  double* peer_inbox[2][8] = {};
+  unsigned int* peer_flag[2][8] = {};
+  unsigned int peer_epoch = 0;
+  int32_t* d_status = nullptr;
+  std::vector<void*> ipc_opened;
+  std::vector<void*> registered;
+
+  uint64_t steps = 0, launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+static int fail(m3b_handle* h, int code, const std::string& msg) {
+  g_last_error = msg;
+  if (h) h->err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      char b__[512];                                                                               \
+      snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return fail(h, M3B_ERR_CUDA, b__);                                                           \
+    }                                                                                              \
+  } while (0)
+#define REQUIRE(cond, code, msg)                                                                   \
+  do { if (!(cond)) return fail(h, code, std::string(msg)); } while (0)
+
+template <class Tp>
+static cudaError_t dev_alloc(m3b_handle* h, Tp** p, size_t n) {
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(Tp));
+  if (e == cudaSuccess) { h->allocs.push_back(*p); h->device_bytes += n * sizeof(Tp); }
+  return e;
+}
+template <class Tp>
+static cudaError_t dev_upload(m3b_handle* h, Tp** p, const std::vector<Tp>& v) {
+  cudaError_t e = dev_alloc(h, p, v.size());
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpy(*p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice);
+  return e;
+}
+
+extern "C" {
+
+M3B_API int m3b_abi_version(void) { return 1; }
+
+M3B_API const char* m3b_last_error(const m3b_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+M3B_API int m3b_create(const m3b_config* cfg, m3b_handle** out) {
+  m3b_handle* h = nullptr;
+  if (!cfg || !out) return fail(nullptr, M3B_ERR_INVALID, "m3b_create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, M3B_ERR_NODEVICE, std::string("m3b_create: no CUDA device (") + cudaGetErrorString(e) +
+                                               "); libm3b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, M3B_ERR_INVALID, "m3b_create: bad device ordinal");
+  cudaDeviceProp prop{};
+  e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, M3B_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, M3B_ERR_NODEVICE, std::string("m3b_create: device '") + prop.name +
+                                               "' is not sm_100 (kernels are built for sm_100a only)");
+  const int T = cfg->tile_events == 0 ? 256 : cfg->tile_events;
+  if (T != 128 && T != 256 && T != 512) return fail(nullptr, M3B_ERR_INVALID, "m3b_create: tile_events must be 128, 256 or 512");
+  h = new m3b_handle();
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  h->sm_count = prop.multiProcessorCount;
+  h->T = T;
+  h->test_stat = cfg->test_statistic;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  CK(dev_alloc(h, &h->d_ticket, 1));
+  CK(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
+  CK(dev_alloc(h, &h->d_status, 1));
+  CK(cudaMemset(h->d_status, 0, sizeof(int32_t)));
+  for (int i = 0; i < m3b_handle::kRing; ++i) CK(cudaEventCreateWithFlags(&h->step_ev[i], cudaEventDisableTiming));
+  *out = h;
+  return M3B_OK;
+}
+
+M3B_API void m3b_destroy(m3b_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  for (void* p : h->registered) cudaHostUnregister(p);
+  for (void* p : h->allocs) cudaFree(p);
+  for (int i = 0; i < m3b_handle::kRing; ++i) {
+    if (h->h_step[i]) cudaFreeHost(h->h_step[i]);
+    if (h->step_ev[i]) cudaEventDestroy(h->step_ev[i]);
+  }
+  if (h->h_llh) cudaFreeHost(h->h_llh);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+M3B_API int m3b_set_stream(m3b_handle* h, void* s) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  h->stream = static_cast<cudaStream_t>(s);
+  return M3B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// splines
+// ------------------------------------------------------------------------------------------------
+M3B_API int m3b_splines_begin(m3b_handle* h, int32_t n_params, int32_t max_knots, const float* coeff_x,
+                              const int16_t* n_pts, int64_t n_events_total) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(!h->splines_open && !h->splines_done, M3B_ERR_STATE, "m3b_splines_begin: monolith already uploaded");
+  REQUIRE(n_params > 0 && n_params <= kMaxParams, M3B_ERR_INVALID, "m3b_splines_begin: n_params out of range");
+  REQUIRE(max_knots >= 0 && coeff_x && n_pts && n_events_total >= 0, M3B_ERR_INVALID, "m3b_splines_begin: bad argument");
+  h->P = n_params; h->Kmax = max_knots;
+  h->coeff_x.assign(coeff_x, coeff_x + static_cast<size_t>(n_params) * max_knots);
+  h->n_pts.assign(n_pts, n_pts + n_params);
+  h->nseg.resize(n_params);
+  for (int p = 0; p < n_params; ++p) {
+    REQUIRE(n_pts[p] >= 0 && n_pts[p] <= max_knots, M3B_ERR_INVALID, "m3b_splines_begin: n_pts[p] > max_knots");
+    h->nseg[p] = static_cast<int16_t>(n_pts[p] > 1 ? n_pts[p] - 1 : (n_pts[p] == 1 ? 1 : 0));
+  }
+  h->curr_segment.assign(n_params, 0);
+  h->segments.assign(n_params, 0);                 // Splines/SplineMonolith.cpp:91-95
+  h->param_values.assign(n_params, -999.f);
+  h->n_events_total = n_events_total;
+  h->n_events_loaded = 0;
+  h->splines_open = true;
+  return M3B_OK;
+}
+
+static int signature_of(m3b_handle* h, const std::vector<int16_t>& cub, const std::vector<int16_t>& lin) {
+  std::vector<int16_t> key(cub);
+  key.push_back(-1);
+  key.insert(key.end(), lin.begin(), lin.end());
+  auto it = h->sig_index.find(key);
+  if (it != h->sig_index.end()) return it->second;
+  const int id = static_cast<int>(h->sigs.size());
+  SigDesc sd{};
+  sd.nc = static_cast<int32_t>(cub.size());
+  sd.nl = static_cast<int32_t>(lin.size());
+  sd.off = static_cast<int32_t>(h->sig_pool.size());
+  h->sig_slot_of_param.resize(static_cast<size_t>(id + 1) * h->P, -1);
+  h->sig_segbase_of_param.resize(static_cast<size_t>(id + 1) * h->P, 0);
+  for (int16_t p : cub) h->sig_pool.push_back(p);
+  int rows = 0;
+  for (size_t s = 0; s < cub.size(); ++s) {
+    h->sig_pool.push_back(rows);
+    h->sig_slot_of_param[static_cast<size_t>(id) * h->P + cub[s]] = static_cast<int16_t>(s);
+    h->sig_segbase_of_param[static_cast<size_t>(id) * h->P + cub[s]] = rows;
+    rows += h->nseg[cub[s]];
+  }
+  for (size_t s = 0; s < lin.size(); ++s) {
+    h->sig_pool.push_back(lin[s]);
+    h->sig_slot_of_param[static_cast<size_t>(id) * h->P + lin[s]] = static_cast<int16_t>(s);
+  }
+  sd.rows = rows;
+  h->sigs.push_back(sd);
+  h->sig_index.emplace(std::move(key), id);
+  h->max_nc = std::max(h->max_nc, sd.nc);
+  h->max_nl = std::max(h->max_nl, sd.nl);
+  return id;
+}
+
+// one internal chunk: events [0,n) whose first event sits on a tile boundary
+static int append_chunk(m3b_handle* h, int64_t n, const uint32_t* cnt_c, const int16_t* paramNo,
+                        const uint64_t* knot_off, uint64_t total_knots, const float* coeff_many,
+                        const uint32_t* cnt_l, const int16_t* paramNo_l, const float* coeff_l) {
+  const int T = h->T, P = h->P;
+  std::vector<uint64_t> start_c(n + 1), start_l(n + 1);
+  start_c[0] = 0; start_l[0] = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    start_c[i + 1] = start_c[i] + cnt_c[2 * i];
+    start_l[i + 1] = start_l[i] + cnt_l[2 * i];
+  }
+  const uint64_t tot_c = start_c[n], tot_l = start_l[n];
+  // validate: parameter ids, knot counts (the reference assumes one knot set per parameter)
+  for (uint64_t s = 0; s < tot_c; ++s) {
+    const int p = paramNo[s];
+    REQUIRE(p >= 0 && p < P, M3B_ERR_INVALID, "m3b_splines_append: paramNo_arr out of range");
+    const uint64_t nk = (s + 1 < tot_c ? knot_off[s + 1] : total_knots) - knot_off[s];
+    if (nk != static_cast<uint64_t>(h->n_pts[p])) {
+      char b[256];
+      snprintf(b, sizeof b, "m3b_splines_append: response %llu of parameter %d has %llu knots, parameter has %d",
+               (unsigned long long)s, p, (unsigned long long)nk, (int)h->n_pts[p]);
+      return fail(h, M3B_ERR_KNOTS, b);
+    }
+  }
+  for (uint64_t s = 0; s < tot_l; ++s)
+    REQUIRE(paramNo_l[s] >= 0 && paramNo_l[s] < P, M3B_ERR_INVALID, "m3b_splines_append: paramNo_tf1 out of range");
+
+  // signatures: union of the parameters of each tile's events
+  const int64_t ntile = (n + T - 1) / T;
+  std::vector<int32_t> tile_sig(ntile);
+  std::vector<uint64_t> tile_cub_off(ntile), tile_lin_off(ntile);
+  std::vector<unsigned char> seen(P);
+  uint64_t cub_total = 0, lin_total = 0;
+  bool all_full = true;
+  std::vector<int16_t> cub, lin;
+  for (int64_t t = 0; t < ntile; ++t) {
+    const int64_t e0 = t * T, e1 = std::min<int64_t>(n, e0 + T);
+    std::fill(seen.begin(), seen.end(), 0);
+    for (uint64_t s = start_c[e0]; s < start_c[e1]; ++s) seen[paramNo[s]] |= 1;
+    for (uint64_t s = start_l[e0]; s < start_l[e1]; ++s) seen[paramNo_l[s]] |= 2;
+    cub.clear(); lin.clear();
+    for (int p = 0; p < P; ++p) {
+      REQUIRE(seen[p] != 3, M3B_ERR_INVALID, "m3b_splines_append: parameter used both as TSpline3 and TF1");
+      if (seen[p] & 1) cub.push_back(static_cast<int16_t>(p));
+      if (seen[p] & 2) lin.push_back(static_cast<int16_t>(p));
+    }
+    const int sig = signature_of(h, cub, lin);
+    tile_sig[t] = sig;
+    tile_cub_off[t] = cub_total;
+    tile_lin_off[t] = lin_total;
+    cub_total += static_cast<uint64_t>(h->sigs[sig].rows) * T;
+    lin_total += static_cast<uint64_t>(h->sigs[sig].nl) * T;
+    const uint64_t full_c = static_cast<uint64_t>(cub.size()) * T, full_l = static_cast<uint64_t>(lin.size()) * T;
+    if (e1 - e0 != T || start_c[e1] - start_c[e0] != full_c || start_l[e1] - start_l[e0] != full_l) all_full = false;
+    h->active_coef_bytes += (16ull * cub.size() + 8ull * lin.size()) * T;
+  }
+
+  // device pools for this chunk + staging copies of the AoS arrays
+  float4* d_cub = nullptr; float2* d_lin = nullptr;
+  CK(dev_alloc(h, &d_cub, cub_total));
+  CK(dev_alloc(h, &d_lin, lin_total));
+  uint64_t *d_start_c = nullptr, *d_start_l = nullptr, *d_knot_off = nullptr, *d_tco = nullptr, *d_tlo = nullptr;
+  int16_t *d_paramNo = nullptr, *d_paramNo_l = nullptr, *d_slot_of = nullptr, *d_nseg = nullptr;
+  int32_t *d_tile_sig = nullptr, *d_segbase_of = nullptr;
+  float4* d_many = nullptr; float2* d_cl = nullptr;
+  std::vector<void*> tmp;
+  auto talloc = [&](void** p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes ? bytes : 16); if (e == cudaSuccess) tmp.push_back(*p); return e; };
+  auto tfree = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
+#define TCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { tfree(); char b__[512]; \
+    snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(h, M3B_ERR_CUDA, b__); } } while (0)
+#define TUP(dptr, hptr, count, type) do { TCK(talloc(reinterpret_cast<void**>(&dptr), (count) * sizeof(type))); \
+    if ((count) > 0) TCK(cudaMemcpyAsync(dptr, hptr, (count) * sizeof(type), cudaMemcpyHostToDevice, h->stream)); } while (0)
+  TUP(d_start_c, start_c.data(), static_cast<size_t>(n + 1), uint64_t);
+  TUP(d_start_l, start_l.data(), static_cast<size_t>(n + 1), uint64_t);
+  TUP(d_paramNo, paramNo, tot_c, int16_t);
+  TUP(d_knot_off, knot_off, tot_c, uint64_t);
+  TUP(d_many, coeff_many, total_knots, float4);
+  TUP(d_paramNo_l, paramNo_l, tot_l, int16_t);
+  TUP(d_cl, coeff_l, tot_l, float2);
+  TUP(d_tile_sig, tile_sig.data(), static_cast<size_t>(ntile), int32_t);
+  TUP(d_slot_of, h->sig_slot_of_param.data(), h->sig_slot_of_param.size(), int16_t);
+  TUP(d_segbase_of, h->sig_segbase_of_param.data(), h->sig_segbase_of_param.size(), int32_t);
+  TUP(d_nseg, h->nseg.data(), static_cast<size_t>(P), int16_t);
+  TUP(d_tco, tile_cub_off.data(), static_cast<size_t>(ntile), uint64_t);
+  TUP(d_tlo, tile_lin_off.data(), static_cast<size_t>(ntile), uint64_t);
+  RetileArgs ra{};
+  ra.n = n; ra.tile0_event = h->n_events_loaded; ra.T = T; ra.P = P;
+  ra.start_c = d_start_c; ra.paramNo = d_paramNo; ra.knot_off = d_knot_off; ra.coeff_many = d_many;
+  ra.start_l = d_start_l; ra.paramNo_l = d_paramNo_l; ra.coeff_l = d_cl;
+  ra.tile_sig = d_tile_sig; ra.slot_of_param = d_slot_of; ra.segbase_of_param = d_segbase_of; ra.nseg = d_nseg;
+  ra.tile_cub_off = d_tco; ra.tile_lin_off = d_tlo; ra.cub_pool = d_cub; ra.lin_pool = d_lin;
+  TCK(launch_retile(ra, all_full ? 0 : static_cast<int64_t>(cub_total), all_full ? 0 : static_cast<int64_t>(lin_total), h->stream));
+  TCK(cudaStreamSynchronize(h->stream));
+  tfree();
+#undef TUP
+#undef TCK
+  for (int64_t t = 0; t < ntile; ++t) {
+    TileDesc td{};
+    td.cub = d_cub + tile_cub_off[t];
+    td.lin = d_lin + tile_lin_off[t];
+    td.sig = tile_sig[t];
+    h->tiles.push_back(td);
+  }
+  h->n_events_loaded += n;
+  h->tiles_dirty = true;
+  return M3B_OK;
+}
+
+M3B_API int m3b_splines_append(m3b_handle* h, int64_t n, const uint32_t* nParamPerEvent, const int16_t* paramNo_arr,
+                               const uint64_t* nKnots_arr, uint64_t total_knots, const float* coeff_many,
+                               const uint32_t* nParamPerEvent_tf1, const int16_t* paramNo_tf1, const float* coeff_tf1) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->splines_open, M3B_ERR_STATE, "m3b_splines_append: call m3b_splines_begin first");
+  REQUIRE(n >= 0 && nParamPerEvent && nParamPerEvent_tf1, M3B_ERR_INVALID, "m3b_splines_append: bad argument");
+  REQUIRE(h->n_events_loaded % h->T == 0, M3B_ERR_STATE,
+          "m3b_splines_append: every chunk but the last must hold a multiple of tile_events events");
+  REQUIRE(h->n_events_loaded + n <= h->n_events_total, M3B_ERR_INVALID, "m3b_splines_append: more events than announced");
+  CK(cudaSetDevice(h->device));
+  // internal sub-chunks bound the staging memory
+  const int64_t sub = 32768 / h->T * h->T;
+  uint64_t tot_c_all = 0;
+  for (int64_t i = 0; i < n; ++i) tot_c_all += nParamPerEvent[2 * i];
+  REQUIRE(tot_c_all == 0 || (paramNo_arr && nKnots_arr && coeff_many), M3B_ERR_INVALID, "m3b_splines_append: null TSpline3 arrays");
+  uint64_t oc = 0, ol = 0;
+  std::vector<uint64_t> rel;
+  for (int64_t e0 = 0; e0 < n; e0 += sub) {
+    const int64_t m = std::min<int64_t>(sub, n - e0);
+    uint64_t nc = 0, nl = 0;
+    for (int64_t i = 0; i < m; ++i) { nc += nParamPerEvent[2 * (e0 + i)]; nl += nParamPerEvent_tf1[2 * (e0 + i)]; }
+    // knots of this sub-chunk's responses [oc, oc+nc): contiguous in the monolith
+    const uint64_t k0 = nc ? nKnots_arr[oc] : 0;
+    const uint64_t k1 = nc ? (oc + nc < tot_c_all ? nKnots_arr[oc + nc] : total_knots) : 0;
+    REQUIRE(k1 >= k0 && k1 <= total_knots, M3B_ERR_INVALID, "m3b_splines_append: nKnots_arr is not increasing");
+    rel.resize(nc);
+    for (uint64_t s = 0; s < nc; ++s) rel[s] = nKnots_arr[oc + s] - k0;
+    int rc = append_chunk(h, m, nParamPerEvent + 2 * e0, nc ? paramNo_arr + oc : nullptr, rel.data(), k1 - k0,
+                          nc ? coeff_many + 4 * k0 : nullptr, nParamPerEvent_tf1 + 2 * e0,
+                          nl ? paramNo_tf1 + ol : nullptr, nl ? coeff_tf1 + 2 * ol : nullptr);
+    if (rc != M3B_OK) return rc;
+    oc += nc; ol += nl;
+  }
+  return M3B_OK;
+}
+
+M3B_API int m3b_splines_end(m3b_handle* h) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->splines_open, M3B_ERR_STATE, "m3b_splines_end: no upload in progress");
+  REQUIRE(h->n_events_loaded == h->n_events_total, M3B_ERR_STATE, "m3b_splines_end: fewer events appended than announced");
+  h->splines_open = false;
+  h->splines_done = true;
+  h->launch_ready = false;
+  return M3B_OK;
+}
+
+M3B_API int m3b_upload_spline_monolith(m3b_handle* h, int32_t n_params, int32_t max_knots, const float* coeff_x,
+                                       const int16_t* n_pts, int64_t n_events, const uint32_t* nParamPerEvent,
+                                       const int16_t* paramNo_arr, const uint32_t* nKnots_arr, uint32_t total_knots,
+                                       const float* coeff_many, const uint32_t* nParamPerEvent_tf1,
+                                       const int16_t* paramNo_tf1, const float* coeff_tf1) {
+  int rc = m3b_splines_begin(h, n_params, max_knots, coeff_x, n_pts, n_events);
+  if (rc != M3B_OK) return rc;
+  uint64_t tot_c = 0;
+  for (int64_t i = 0; i < n_events; ++i) tot_c += nParamPerEvent[2 * i];
+  std::vector<uint64_t> k64(tot_c);
+  for (uint64_t s = 0; s < tot_c; ++s) k64[s] = nKnots_arr[s];
+  rc = m3b_splines_append(h, n_events, nParamPerEvent, paramNo_arr, k64.data(), total_knots, coeff_many,
+                          nParamPerEvent_tf1, paramNo_tf1, coeff_tf1);
+  if (rc != M3B_OK) return rc;
+  return m3b_splines_end(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// binning, events, data
+// ------------------------------------------------------------------------------------------------
+M3B_API int m3b_upload_binning(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* nbins,
+                               const double* edges) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(n_samples > 0 && n_samples <= 64 && n_dim && nbins && edges, M3B_ERR_INVALID, "m3b_upload_binning: bad argument (1..64 samples)");
+  REQUIRE(h->n_samples == 0, M3B_ERR_STATE, "m3b_upload_binning: binning already uploaded");
+  CK(cudaSetDevice(h->device));
+  h->n_samples = n_samples;
+  h->b_ndim.assign(n_dim, n_dim + n_samples);
+  h->b_nbins.assign(nbins, nbins + static_cast<size_t>(n_samples) * kMaxDim);
+  h->b_edge_off.assign(static_cast<size_t>(n_samples) * kMaxDim, 0);
+  h->b_stride.assign(static_cast<size_t>(n_samples) * kMaxDim, 0);
+  h->b_goff.assign(n_samples, 0);
+  h->sample_start.assign(n_samples + 1, 0);
+  int eoff = 0, goff = 0;
+  for (int s = 0; s < n_samples; ++s) {
+    REQUIRE(n_dim[s] >= 1 && n_dim[s] <= kMaxDim, M3B_ERR_INVALID, "m3b_upload_binning: 1..4 dimensions per sample");
+    int stride = 1;                                   // SampleStructs.h:656-664, x fastest
+    for (int d = 0; d < n_dim[s]; ++d) {
+      const int nb = nbins[s * kMaxDim + d];
+      REQUIRE(nb >= 1, M3B_ERR_INVALID, "m3b_upload_binning: empty axis");
+      for (int i = 0; i < nb; ++i)
+        REQUIRE(edges[eoff + i] < edges[eoff + i + 1], M3B_ERR_INVALID, "m3b_upload_binning: edges must increase strictly");
+      h->b_edge_off[s * kMaxDim + d] = eoff;
+      h->b_stride[s * kMaxDim + d] = stride;
+      stride *= nb;
+      eoff += nb + 1;
+    }
+    h->b_goff[s] = goff;                              // BinningHandler.cpp:341-355
+    h->sample_start[s] = goff;
+    goff += stride;
+  }
+  h->sample_start[n_samples] = goff;
+  h->n_bins = goff;
+  h->b_edges.assign(edges, edges + eoff);
+  CK(dev_upload(h, &h->d_ndim, h->b_ndim));
+  CK(dev_upload(h, &h->d_nbins, h->b_nbins));
+  CK(dev_upload(h, &h->d_edge_off, h->b_edge_off));
+  CK(dev_upload(h, &h->d_stride, h->b_stride));
+  CK(dev_upload(h, &h->d_goff, h->b_goff));
+  CK(dev_upload(h, &h->d_sample_start, h->sample_start));
+  CK(dev_upload(h, &h->d_edges, h->b_edges));
+  for (int k = 0; k < 2; ++k) {
+    CK(dev_alloc(h, &h->d_hw[k], static_cast<size_t>(2) * h->n_bins));
+    CK(cudaMemset(h->d_hw[k], 0, sizeof(double) * 2 * h->n_bins));
+    h->mc_zero[k] = h->w2_zero[k] = true;
+  }
+  h->d_w2_frozen = h->d_hw[0] + h->n_bins;
+  CK(dev_alloc(h, &h->d_data, static_cast<size_t>(h->n_bins)));
+  CK(cudaMemset(h->d_data, 0, sizeof(double) * h->n_bins));
+  CK(dev_alloc(h, &h->d_llh, static_cast<size_t>(1 + n_samples)));
+  CK(cudaMemset(h->d_llh, 0, sizeof(double) * (1 + n_samples)));
+  CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_llh), sizeof(double) * (1 + n_samples), cudaHostAllocMapped));
+  memset(h->h_llh, 0, sizeof(double) * (1 + n_samples));
+  CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_llh_dev), h->h_llh, 0));
+  h->launch_ready = false;
+  return M3B_OK;
+}
+
+M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sample_id, const double* kin,
+                              int32_t n_norm_per_event, const int16_t* norm_idx, int32_t n_norm_values,
+                              int32_t use_osc, const int32_t* osc_idx, int64_t n_osc_values, const float* static_w) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->n_samples > 0, M3B_ERR_STATE, "m3b_upload_events: upload the binning first");
+  REQUIRE(h->n_events == 0, M3B_ERR_STATE, "m3b_upload_events: events already uploaded");
+  REQUIRE(n_events > 0 && sample_id && kin, M3B_ERR_INVALID, "m3b_upload_events: bad argument");
+  REQUIRE(n_norm_per_event >= 0 && n_norm_per_event <= kMaxNormSlots, M3B_ERR_INVALID, "m3b_upload_events: at most 16 norm pointers per event");
+  REQUIRE(!h->splines_done || h->n_events_total == n_events, M3B_ERR_INVALID, "m3b_upload_events: event count differs from the spline monolith's");
+  CK(cudaSetDevice(h->device));
+  const int T = h->T;
+  h->n_events = n_events;
+  h->n_tiles = (n_events + T - 1) / T;
+  h->e_pad = h->n_tiles * T;
+  const int64_t E = n_events, EP = h->e_pad;
+  int max_dim = 0;
+  for (int64_t e = 0; e < E; ++e) {
+    REQUIRE(sample_id[e] >= 0 && sample_id[e] < h->n_samples, M3B_ERR_INVALID, "m3b_upload_events: sample_id out of range");
+    max_dim = std::max(max_dim, h->b_ndim[sample_id[e]]);
+  }
+  // bins on the device
+  CK(dev_alloc(h, &h->d_bin, static_cast<size_t>(EP)));
+  {
+    int32_t* d_sid = nullptr; double* d_kin = nullptr;
+    const bool keep = (h->cfg.flags & M3B_FLAG_KEEP_KINEMATICS) != 0;
+    if (keep) { CK(dev_alloc(h, &d_sid, static_cast<size_t>(E))); CK(dev_alloc(h, &d_kin, static_cast<size_t>(E) * max_dim)); }
+    else { CK(cudaMalloc(&d_sid, sizeof(int32_t) * E)); CK(cudaMalloc(&d_kin, sizeof(double) * E * max_dim)); }
+    CK(cudaMemcpyAsync(d_sid, sample_id, sizeof(int32_t) * E, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_kin, kin, sizeof(double) * E * max_dim, cudaMemcpyHostToDevice, h->stream));
+    BinArgs ba{};
+    ba.n_events = E; ba.e_pad = EP; ba.sample_id = d_sid; ba.kin = d_kin; ba.n_samples = h->n_samples;
+    ba.n_dim = h->d_ndim; ba.nbins = h->d_nbins; ba.edge_off = h->d_edge_off; ba.stride = h->d_stride;
+    ba.global_off = h->d_goff; ba.edges = h->d_edges; ba.bin = h->d_bin;
+    CK(launch_bins(ba, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (keep) { h->d_sample_id = d_sid; h->d_kin = d_kin; } else { cudaFree(d_sid); cudaFree(d_kin); }
+  }
+  // norm bindings, transposed to [slot][event] and padded
+  h->norm_slots = norm_idx ? n_norm_per_event : 0;
+  h->n_norm_values = n_norm_values;
+  if (h->norm_slots > 0) {
+    std::vector<int16_t> tr(static_cast<size_t>(h->norm_slots) * EP, -1);
+    for (int64_t e = 0; e < E; ++e)
+      for (int j = 0; j < h->norm_slots; ++j) {
+        const int16_t v = norm_idx[e * n_norm_per_event + j];
+        REQUIRE(v < n_norm_values, M3B_ERR_INVALID, "m3b_upload_events: norm_idx out of range");
+        tr[static_cast<size_t>(j) * EP + e] = v;
+      }
+    CK(dev_upload(h, &h->d_norm_idx, tr));
+  }
+  h->use_osc = use_osc != 0;
+  if (h->use_osc) {
+    h->n_osc = osc_idx ? n_osc_values : E;
+    REQUIRE(h->n_osc > 0, M3B_ERR_INVALID, "m3b_upload_events: n_osc_values must be > 0 with osc_idx");
+    if (osc_idx) {
+      std::vector<int32_t> oi(static_cast<size_t>(EP), 0);
+      for (int64_t e = 0; e < E; ++e) {
+        REQUIRE(osc_idx[e] >= 0 && osc_idx[e] < n_osc_values, M3B_ERR_INVALID, "m3b_upload_events: osc_idx out of range");
+        oi[e] = osc_idx[e];
+      }
+      CK(dev_upload(h, &h->d_osc_idx, oi));
+    }
+    CK(dev_alloc(h, &h->d_osc, static_cast<size_t>(h->n_osc)));
+    std::vector<float> ones(static_cast<size_t>(h->n_osc), 1.f);
+    CK(cudaMemcpy(h->d_osc, ones.data(), sizeof(float) * h->n_osc, cudaMemcpyHostToDevice));
+  }
+  if (static_w) {
+    std::vector<float> sw(static_cast<size_t>(EP), 1.f);
+    std::copy(static_w, static_w + E, sw.begin());
+    CK(dev_upload(h, &h->d_static, sw));
+  }
+  if (h->cfg.flags & M3B_FLAG_KEEP_EVENT_WEIGHTS) {
+    CK(dev_alloc(h, &h->d_evt_spline_w, static_cast<size_t>(EP)));
+    CK(dev_alloc(h, &h->d_evt_total_w, static_cast<size_t>(EP)));
+  }
+  h->launch_ready = false;
+  return M3B_OK;
+}
+
+M3B_API int m3b_upload_data(m3b_handle* h, const double* data, int32_t n_bins) {
+  REQUIRE(h && data, M3B_ERR_INVALID, "m3b_upload_data: null argument");
+  REQUIRE(h->n_bins > 0 && n_bins == h->n_bins, M3B_ERR_INVALID, "m3b_upload_data: n_bins differs from the binning's");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_data, data, sizeof(double) * n_bins, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return M3B_OK;
+}
+
+M3B_API int m3b_upload_osc(m3b_handle* h, const float* osc_w, int64_t n) {
+  REQUIRE(h && osc_w, M3B_ERR_INVALID, "m3b_upload_osc: null argument");
+  REQUIRE(h->use_osc && n == h->n_osc, M3B_ERR_INVALID, "m3b_upload_osc: length differs from the oscillation-weight array's");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_osc, osc_w, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  return M3B_OK;
+}
+
+M3B_API int m3b_register_host_buffer(m3b_handle* h, void* ptr, uint64_t bytes) {
+  REQUIRE(h && ptr && bytes, M3B_ERR_INVALID, "m3b_register_host_buffer: bad argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  h->registered.push_back(ptr);
+  return M3B_OK;
+}
+
+M3B_API int m3b_set_test_statistic(m3b_handle* h, int32_t ts) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(ts >= 0 && ts <= 4, M3B_ERR_INVALID, "m3b_set_test_statistic: unknown test statistic");
+  h->test_stat = ts;
+  return M3B_OK;
+}
+
+M3B_API int m3b_reset_w2(m3b_handle* h) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  h->first_time_w2 = true;
+  return M3B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step
+// ------------------------------------------------------------------------------------------------
+// SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-109), same decisions in the same order
+static void find_segments(m3b_handle* h, const double* pars) {
+  for (int i = 0; i < h->P; ++i) {
+    const int nPoints = h->n_pts[i];
+    const float* x = h->coeff_x.data() + static_cast<size_t>(i) * h->Kmax;
+    const float xvar = static_cast<float>(pars[i]);
+    h->param_values[i] = xvar;
+    if (nPoints == 0) continue;
+    int segment = 0, hi = nPoints - 1;
+    const int prev = h->curr_segment[i];
+    if (xvar <= x[0]) segment = 0;
+    else if (xvar >= x[nPoints - 1]) segment = hi;
+    else if (x[prev + 1] > xvar && xvar >= x[prev]) segment = prev;
+    else {
+      while (hi - segment > 1) {
+        const int half = (segment + hi) / 2;
+        if (xvar > x[half]) segment = half; else hi = half;
+      }
+    }
+    if (segment >= nPoints - 1 && nPoints > 1) segment = nPoints - 2;
+    h->curr_segment[i] = static_cast<int16_t>(segment);
+    h->segments[i] = static_cast<int16_t>(segment);
+  }
+}
+
+M3B_API int m3b_find_segments(m3b_handle* h, const double* spline_pars, int16_t* segments, float* param_values) {
+  REQUIRE(h && spline_pars, M3B_ERR_INVALID, "m3b_find_segments: null argument");
+  REQUIRE(h->P > 0, M3B_ERR_STATE, "m3b_find_segments: no spline monolith");
+  find_segments(h, spline_pars);
+  if (segments) std::copy(h->segments.begin(), h->segments.end(), segments);
+  if (param_values) std::copy(h->param_values.begin(), h->param_values.end(), param_values);
+  return M3B_OK;
+}
+
+static int prepare_launch(m3b_handle* h, bool w2_live) {
+  CK(cudaSetDevice(h->device));
+  if (h->tiles_dirty || !h->d_tiles) {
+    REQUIRE(!h->splines_open, M3B_ERR_STATE, "step: spline upload still open (call m3b_splines_end)");
+    if (!h->splines_done) {
+      // no response functions at all: tiles with an empty signature
+      h->P = std::max(h->P, 0);
+      std::vector<int16_t> none;
+      const int sig = signature_of(h, none, none);
+      h->tiles.assign(static_cast<size_t>(h->n_tiles), TileDesc{nullptr, nullptr, sig, 0});
+    }
+    REQUIRE(static_cast<int64_t>(h->tiles.size()) == h->n_tiles, M3B_ERR_STATE, "step: spline monolith and event table disagree on the number of events");
+    CK(dev_upload(h, &h->d_tiles, h->tiles));
+    CK(dev_upload(h, &h->d_sigs, h->sigs));
+    CK(dev_upload(h, &h->d_sig_pool, h->sig_pool));
+    h->tiles_dirty = false;
+    h->launch_ready = false;
+  }
+  if (!h->h_step[0] || h->step.P != h->P || h->step.Nn != h->n_norm_values) {
+    h->step = make_step_layout(h->P, h->n_norm_values);
+    for (int i = 0; i < m3b_handle::kRing; ++i) {
+      if (h->h_step[i]) cudaFreeHost(h->h_step[i]);
+      CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_step[i]), h->step.bytes, cudaHostAllocDefault));
+      CK(dev_alloc(h, &h->d_step[i], static_cast<size_t>(h->step.bytes)));
+    }
+    h->launch_ready = false;
+  }
+  if (!h->launch_ready || h->launch_w2_live != w2_live) {
+    FillArgs a{};
+    a.step = h->step; a.max_nc = h->max_nc; a.max_nl = h->max_nl; a.n_bins = h->n_bins; a.n_samples = h->n_samples;
+    int smem = fill_smem_bytes(a, true, w2_live);
+    h->hist_in_smem = smem <= 200 * 1024;
+    if (!h->hist_in_smem) smem = fill_smem_bytes(a, false, w2_live);
+    CK(fill_set_smem(h->T, smem));
+    int bps = 0;
+    CK(fill_occupancy(h->T, smem, &bps));
+    REQUIRE(bps > 0, M3B_ERR_CUDA, "step: fill kernel does not fit on an SM");
+    h->smem = smem;
+    h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(bps) * h->sm_count));
+    const char* g = getenv("M3B_GRID_BLOCKS_PER_SM");
+    if (g && atoi(g) > 0) h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(std::min(atoi(g), bps)) * h->sm_count));
+    h->launch_ready = true;
+    h->launch_w2_live = w2_live;
+  }
+  return M3B_OK;
+}
+
+enum StepMode { kFused = 0, kFillOnly = 1, kPeer = 2, kWeightsOnly = 3 };
+
+static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, const double* norm_pars,
+                        const float* osc_w, StepMode mode) {
+  REQUIRE(h->n_events > 0 && h->n_bins > 0, M3B_ERR_STATE, "step: upload binning and events first");
+  REQUIRE(h->n_norm_values == 0 || norm_pars, M3B_ERR_INVALID, "step: norm_pars is NULL but events carry norm pointers");
+  const bool w2_live = h->first_time_w2;      // Samples/SampleHandlerFD.cpp:445,460
+  int rc = prepare_launch(h, w2_live);
+  if (rc != M3B_OK) return rc;
+
+  // per-step table {segment, dx, value, norm}
+  const int slot = h->ring;
+  h->ring = (h->ring + 1) % m3b_handle::kRing;
+  CK(cudaEventSynchronize(h->step_ev[slot]));
+  unsigned char* st = h->h_step[slot];
+  int32_t* seg = reinterpret_cast<int32_t*>(st + h->step.off_seg);
+  float* dx = reinterpret_cast<float*>(st + h->step.off_dx);
+  float* val = reinterpret_cast<float*>(st + h->step.off_val);
+  float* norm = reinterpret_cast<float*>(st + h->step.off_norm);
+  for (int p = 0; p < h->P; ++p) {
+    seg[p] = segs[p];
+    val[p] = vals[p];
+    // dx = ParamValues[Param] - coeff_x[Param*_max_knots+segment]  (Splines/SplineMonolith.cpp:759), in float
+    dx[p] = h->n_pts[p] > 0 ? vals[p] - h->coeff_x[static_cast<size_t>(p) * h->Kmax + segs[p]] : 0.f;
+  }
+  for (int j = 0; j < h->n_norm_values; ++j) norm[j] = static_cast<float>(norm_pars[j]);   // SampleHandlerFD.cpp:580
+  CK(cudaMemcpyAsync(h->d_step[slot], st, h->step.bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->step_ev[slot], h->stream));
+  if (osc_w) {
+    REQUIRE(h->use_osc, M3B_ERR_INVALID, "step: osc_w given but events were uploaded with use_osc=0");
+    CK(cudaMemcpyAsync(h->d_osc, osc_w, sizeof(float) * h->n_osc, cudaMemcpyHostToDevice, h->stream));
+  }
+
+  // fused mode alternates two buffers (the last block zeroes the other one for the next step);
+  // the multi-GPU modes keep one buffer so its address is stable for the collective
+  const int nxt = mode == kFused ? (h->cur ^ 1) : h->cur;
+  double* mc = h->d_hw[nxt];
+  double* w2 = h->d_hw[nxt] + h->n_bins;
+  if (!h->mc_zero[nxt]) CK(cudaMemsetAsync(mc, 0, sizeof(double) * h->n_bins, h->stream));
+  if (w2_live && !h->w2_zero[nxt]) CK(cudaMemsetAsync(w2, 0, sizeof(double) * h->n_bins, h->stream));
+  h->mc_zero[nxt] = false;
+  if (w2_live) { h->w2_zero[nxt] = false; h->d_w2_frozen = w2; }
+
+  FillArgs a{};
+  a.tiles = h->d_tiles; a.sigs = h->d_sigs; a.sig_pool = h->d_sig_pool;
+  a.n_tiles = static_cast<int32_t>(h->n_tiles); a.T = h->T; a.max_nc = h->max_nc; a.max_nl = h->max_nl;
+  a.step_table = h->d_step[slot]; a.step = h->step;
+  a.bin = h->d_bin; a.osc = h->use_osc ? h->d_osc : nullptr; a.osc_idx = h->d_osc_idx; a.static_w = h->d_static;
+  a.norm_idx = h->d_norm_idx; a.norm_slots = h->norm_slots; a.e_pad = h->e_pad; a.n_events = h->n_events;
+  a.hist = mc; a.w2 = w2_live ? w2 : nullptr;
+  a.n_bins = h->n_bins; a.hist_in_smem = h->hist_in_smem ? 1 : 0;
+  a.fuse_llh = (mode == kFused) ? 1 : 0;
+  a.test_stat = h->test_stat; a.n_samples = h->n_samples;
+  a.data = h->d_data; a.w2_frozen = h->d_w2_frozen; a.sample_start = h->d_sample_start;
+  a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->h_llh_dev;
+  a.evt_spline_w = h->d_evt_spline_w; a.evt_total_w = h->d_evt_total_w;
+  if (mode == kFused) {
+    // the last block zeroes the other buffer for the next step
+    const int other = nxt ^ 1;
+    a.hist_next = h->d_hw[other];
+    h->mc_zero[other] = true;
+    const bool next_live = h->cfg.update_w2 != 0;
+    if (next_live && (h->d_hw[other] + h->n_bins) != h->d_w2_frozen) { a.w2_next = h->d_hw[other] + h->n_bins; h->w2_zero[other] = true; }
+  }
+  if (mode == kPeer) {
+    REQUIRE(h->peer_world > 0, M3B_ERR_STATE, "m3b_step_peer: call m3b_peer_export/import first");
+    ++h->peer_epoch;
+    const int par = h->peer_epoch & 1;
+    a.peer_world = h->peer_world; a.peer_rank = h->peer_rank; a.peer_epoch = h->peer_epoch;
+    for (int r = 0; r < h->peer_world; ++r) { a.peer_inbox[r] = h->peer_inbox[par][r]; a.peer_flag[r] = h->peer_flag[par][r]; }
+  }
+  CK(launch_fill(a, h->grid, h->smem, h->stream));
+  ++h->launches;
+  if (mode == kPeer) {
+    const int par = h->peer_epoch & 1;
+    LlhArgs l{};
+    l.data = h->d_data; l.sample_start = h->d_sample_start; l.n_bins = h->n_bins; l.n_samples = h->n_samples;
+    l.test_stat = h->test_stat; l.llh_dev = h->d_llh; l.llh_host = h->h_llh_dev;
+    l.peer_world = h->peer_world; l.inbox = h->d_inbox[par]; l.flags = h->d_flags[par]; l.epoch = h->peer_epoch;
+    l.hist_out = mc; l.w2_out = w2; l.w2_live = w2_live ? 1 : 0; l.status = h->d_status;
+    l.hist = mc; l.w2 = h->d_w2_frozen;
+    if (!w2_live) l.w2_out = nullptr;
+    CK(launch_llh(l, h->stream));
+    ++h->launches;
+  }
+  h->cur = nxt;
+  h->last_w2_live = w2_live;
+  if (!h->cfg.update_w2) h->first_time_w2 = false;     // Samples/SampleHandlerFD.cpp:342
+  h->evt_weights_valid = h->d_evt_spline_w != nullptr;
+  ++h->steps;
+  return M3B_OK;
+}
+
+static int step_common(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w, StepMode mode) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  if (h->P > 0) {
+    REQUIRE(spline_pars, M3B_ERR_INVALID, "step: spline_pars is NULL");
+    find_segments(h, spline_pars);
+  }
+  return enqueue_step(h, h->param_values.data(), h->segments.data(), norm_pars, osc_w, mode);
+}
+
+M3B_API int m3b_step(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  return step_common(h, spline_pars, norm_pars, osc_w, (h->cfg.flags & M3B_FLAG_NO_FUSED_LLH) ? kFillOnly : kFused);
+}
+
+M3B_API int m3b_step_segments(m3b_handle* h, const float* param_values, const int16_t* segments,
+                              const double* norm_pars, const float* osc_w) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->P == 0 || (param_values && segments), M3B_ERR_INVALID, "m3b_step_segments: null argument");
+  for (int p = 0; p < h->P; ++p) {
+    REQUIRE(segments[p] >= 0 && segments[p] < std::max<int>(1, h->nseg[p]), M3B_ERR_INVALID, "m3b_step_segments: segment out of range");
+    h->segments[p] = segments[p]; h->curr_segment[p] = segments[p]; h->param_values[p] = param_values[p];
+  }
+  return enqueue_step(h, h->param_values.data(), h->segments.data(), norm_pars, osc_w,
+                      (h->cfg.flags & M3B_FLAG_NO_FUSED_LLH) ? kFillOnly : kFused);
+}
+
+M3B_API int m3b_step_fill(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w) {
+  return step_common(h, spline_pars, norm_pars, osc_w, kFillOnly);
+}
+
+M3B_API int m3b_step_peer(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w) {
+  return step_common(h, spline_pars, norm_pars, osc_w, kPeer);
+}
+
+M3B_API int m3b_hist_device_ptr(m3b_handle* h, void** dev_ptr, int32_t* n_bins, int32_t* w2_live) {
+  REQUIRE(h && dev_ptr, M3B_ERR_INVALID, "m3b_hist_device_ptr: null argument");
+  REQUIRE(h->n_bins > 0, M3B_ERR_STATE, "m3b_hist_device_ptr: no binning");
+  *dev_ptr = h->d_hw[h->cur];
+  if (n_bins) *n_bins = h->n_bins;
+  if (w2_live) *w2_live = h->last_w2_live ? 1 : 0;
+  return M3B_OK;
+}
+
+M3B_API int m3b_llh_from_hist(m3b_handle* h) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->steps > 0, M3B_ERR_STATE, "m3b_llh_from_hist: no step yet");
+  CK(cudaSetDevice(h->device));
+  LlhArgs l{};
+  l.hist = h->d_hw[h->cur]; l.w2 = h->d_w2_frozen; l.data = h->d_data; l.sample_start = h->d_sample_start;
+  l.n_bins = h->n_bins; l.n_samples = h->n_samples; l.test_stat = h->test_stat;
+  l.llh_dev = h->d_llh; l.llh_host = h->h_llh_dev; l.status = h->d_status;
+  CK(launch_llh(l, h->stream));
+  ++h->launches;
+  return M3B_OK;
+}
+
+M3B_API int m3b_synchronize(m3b_handle* h) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return M3B_OK;
+}
+
+M3B_API int m3b_llh(m3b_handle* h, double* total, double* per_sample) {
+  REQUIRE(h && total, M3B_ERR_INVALID, "m3b_llh: null argument");
+  REQUIRE(h->steps > 0, M3B_ERR_STATE, "m3b_llh: no step yet");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->peer_world > 0 && h->h_llh[0] != h->h_llh[0]) {     // NaN: look at the exchange status
+    int32_t st = 0;
+    CK(cudaMemcpy(&st, h->d_status, sizeof st, cudaMemcpyDeviceToHost));
+    if (st != 0) return fail(h, M3B_ERR_PEER, "m3b_llh: peer histogram exchange timed out");
+  }
+  *total = h->h_llh[0];
+  if (per_sample) for (int s = 0; s < h->n_samples; ++s) per_sample[s] = h->h_llh[1 + s];
+  return M3B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// read-back
+// ------------------------------------------------------------------------------------------------
+M3B_API int m3b_read_hist(m3b_handle* h, double* mc, double* w2) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->n_bins > 0, M3B_ERR_STATE, "m3b_read_hist: no binning");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (mc) CK(cudaMemcpy(mc, h->d_hw[h->cur], sizeof(double) * h->n_bins, cudaMemcpyDeviceToHost));
+  if (w2) CK(cudaMemcpy(w2, h->d_w2_frozen, sizeof(double) * h->n_bins, cudaMemcpyDeviceToHost));
+  return M3B_OK;
+}
+
+M3B_API int m3b_read_event_bins(m3b_handle* h, int32_t* bins) {
+  REQUIRE(h && bins, M3B_ERR_INVALID, "m3b_read_event_bins: null argument");
+  REQUIRE(h->n_events > 0, M3B_ERR_STATE, "m3b_read_event_bins: no events");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(bins, h->d_bin, sizeof(int32_t) * h->n_events, cudaMemcpyDeviceToHost));
+  return M3B_OK;
+}
+
+M3B_API int m3b_read_event_weights(m3b_handle* h, float* spline_w, float* total_w) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->steps > 0, M3B_ERR_STATE, "m3b_read_event_weights: no step yet");
+  REQUIRE(h->d_evt_spline_w, M3B_ERR_STATE, "m3b_read_event_weights: create the handle with M3B_FLAG_KEEP_EVENT_WEIGHTS");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (spline_w) CK(cudaMemcpy(spline_w, h->d_evt_spline_w, sizeof(float) * h->n_events, cudaMemcpyDeviceToHost));
+  if (total_w) CK(cudaMemcpy(total_w, h->d_evt_total_w, sizeof(float) * h->n_events, cudaMemcpyDeviceToHost));
+  return M3B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer exchange wiring (CUDA IPC between the per-GPU processes)
+// ------------------------------------------------------------------------------------------------
+M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ipc_handle_64B) {
+  REQUIRE(h && ipc_handle_64B, M3B_ERR_INVALID, "m3b_peer_export: null argument");
+  REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, M3B_ERR_INVALID, "m3b_peer_export: 1..8 ranks");
+  REQUIRE(h->n_bins > 0, M3B_ERR_STATE, "m3b_peer_export: upload the binning first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  CK(cudaSetDevice(h->device));
+  if (!h->d_inbox[0]) {
+    // one allocation: [2 parities][world * 2*n_bins doubles] then [2][world] flags (as doubles' worth of space)
+    const size_t inbox_d = static_cast<size_t>(world) * 2 * h->n_bins;
+    const size_t total_d = 2 * inbox_d + 2 * 8;   // 2*8 doubles = 128 B for 2x8 u32 flags (+slack)
+    double* base = nullptr;
+    CK(dev_alloc(h, &base, total_d));
+    CK(cudaMemset(base, 0, total_d * sizeof(double)));
+    h->d_inbox[0] = base; h->d_inbox[1] = base + inbox_d;
+    h->d_flags[0] = reinterpret_cast<unsigned int*>(base + 2 * inbox_d);
+    h->d_flags[1] = h->d_flags[0] + 8;
+  }
+  h->peer_world = world; h->peer_rank = rank;
+  for (int par = 0; par < 2; ++par) { h->peer_inbox[par][rank] = h->d_inbox[par]; h->peer_flag[par][rank] = h->d_flags[par]; }
+  cudaIpcMemHandle_t mh;
+  CK(cudaIpcGetMemHandle(&mh, h->d_inbox[0]));
+  memcpy(ipc_handle_64B, &mh, 64);
+  return M3B_OK;
+}
+
+M3B_API int m3b_peer_import(m3b_handle* h, int32_t peer_rank, const void* ipc_handle_64B) {
+  REQUIRE(h && ipc_handle_64B, M3B_ERR_INVALID, "m3b_peer_import: null argument");
+  REQUIRE(h->peer_world > 0 && peer_rank >= 0 && peer_rank < h->peer_world, M3B_ERR_STATE, "m3b_peer_import: export first / bad rank");
+  if (peer_rank == h->peer_rank) return M3B_OK;
+  CK(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, ipc_handle_64B, 64);
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->ipc_opened.push_back(p);
+  double* base = static_cast<double*>(p);
+  const size_t inbox_d = static_cast<size_t>(h->peer_world) * 2 * h->n_bins;
+  h->peer_inbox[0][peer_rank] = base; h->peer_inbox[1][peer_rank] = base + inbox_d;
+  h->peer_flag[0][peer_rank] = reinterpret_cast<unsigned int*>(base + 2 * inbox_d);
+  h->peer_flag[1][peer_rank] = h->peer_flag[0][peer_rank] + 8;
+  return M3B_OK;
+}
+
+M3B_API int m3b_get_info(m3b_handle* h, m3b_info* out) {
+  REQUIRE(h && out, M3B_ERR_INVALID, "m3b_get_info: null argument");
+  memset(out, 0, sizeof *out);
+  out->n_events = h->n_events; out->n_tiles = h->n_tiles; out->n_params = h->P; out->n_bins = h->n_bins;
+  out->n_samples = h->n_samples; out->n_signatures = static_cast<int32_t>(h->sigs.size());
+  out->tile_events = h->T; out->grid_blocks = h->grid; out->smem_bytes = h->smem; out->hist_in_smem = h->hist_in_smem ? 1 : 0;
+  out->device_bytes = h->device_bytes;
+  uint64_t per_evt = 4;   // bin id
+  if (h->use_osc) per_evt += 4 + (h->d_osc_idx ? 4 : 0);
+  if (h->d_static) per_evt += 4;
+  per_evt += 2ull * h->norm_slots;
+  out->active_bytes_per_step = h->active_coef_bytes + per_evt * static_cast<uint64_t>(h->e_pad);
+  out->steps = h->steps; out->kernel_launches = h->launches;
+  return M3B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// m3b_internal.h -- structures shared by the host API (m3b_api.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace m3b {
+
+constexpr int kMaxDim = 4;          // kinematic dimensions per sample (matches the C ABI's nbins[s*4+d])
+constexpr int kMaxParams = 2048;    // spline parameters per handle (step table lives in shared memory)
+constexpr int kMaxNormSlots = 16;   // norm pointers per event
+
+// One tile = T consecutive events.  Cubic coefficients of the tile are stored
+//   cub[(segbase(slot) + segment) * T + lane]   float4 {y,b,c,d}
+// so that, the active segment being uniform per parameter per step, every warp reads 512
+// contiguous bytes per response.  Linear coefficients: lin[slot * T + lane] float2 {a,b}.
+struct TileDesc {
+  const float4* cub;
+  const float2* lin;
+  int32_t sig;       // signature: which parameters the tile's slots refer to
+  int32_t pad;
+};
+
+// Signature = the (sorted) union of parameters of the tile's events.  pool layout at `off`:
+//   cparam[nc] | segbase[nc] | lparam[nl]       (int32 each)
+struct SigDesc {
+  int32_t nc, nl, off, rows;   // rows = total segment rows of the tile's cubic block
+};
+
+// Per-step table, built on the host (SplineBase::FindSplineSegment), copied H2D once per step and
+// staged into shared memory by every block with one bulk (TMA) copy:
+//   int32 seg[P] | float dx[P] | float val[P] | float norm[Nn]    (padded to 16 B)
+struct StepLayout {
+  int32_t P, Nn;
+  int32_t off_seg, off_dx, off_val, off_norm, bytes;
+};
+inline StepLayout make_step_layout(int P, int Nn) {
+  StepLayout L;
+  L.P = P; L.Nn = Nn;
+  L.off_seg = 0;
+  L.off_dx = L.off_seg + 4 * P;
+  L.off_val = L.off_dx + 4 * P;
+  L.off_norm = L.off_val + 4 * P;
+  L.bytes = (L.off_norm + 4 * Nn + 15) & ~15;
+  if (L.bytes == 0) L.bytes = 16;
+  return L;
+}
+
+struct FillArgs {
+  // tiles
+  const TileDesc* tiles;
+  const SigDesc* sigs;
+  const int32_t* sig_pool;
+  int32_t n_tiles, T, max_nc, max_nl;
+  // per-step table
+  const unsigned char* step_table;
+  StepLayout step;
+  // event table (flat, padded to n_tiles*T)
+  const int32_t* bin;
+  const float* osc;
+  const int32_t* osc_idx;
+  const float* static_w;
+  const int16_t* norm_idx;     // [slot * e_pad + e]
+  int32_t norm_slots;
+  int64_t e_pad, n_events;
+  // histograms
+  double* hist;                // [n_bins] mc, this step
+  double* w2;                  // [n_bins] or nullptr when W2 is frozen
+  double* hist_next;           // zeroed by the last block for the next step (nullptr = caller memsets)
+  double* w2_next;
+  int32_t n_bins, hist_in_smem;
+  // fused likelihood (last block)
+  int32_t fuse_llh, test_stat, n_samples;
+  const double* data;
+  const double* w2_frozen;     // w2 histogram to use in the LLH (== w2 when live)
+  const int32_t* sample_start; // [n_samples+1] global bin offsets
+  unsigned int* ticket;
+  double* llh_dev;             // [1+n_samples]
+  double* llh_host;            // mapped pinned mirror (nullptr = none)
+  // optional per-event outputs
+  float* evt_spline_w;
+  float* evt_total_w;
+  // peer exchange (multi-GPU, own collective): push partial hist into every rank's inbox
+  int32_t peer_world, peer_rank;
+  double* peer_inbox[8];       // peer_inbox[r] = rank r's inbox base; slot for us at [peer_rank * 2*n_bins]
+  unsigned int* peer_flag[8];  // peer_flag[r][peer_rank] <- epoch
+  unsigned int peer_epoch;
+};
+
+struct LlhArgs {
+  const double* hist; const double* w2; const double* data;
+  const int32_t* sample_start;
+  int32_t n_bins, n_samples, test_stat;
+  double* llh_dev; double* llh_host;
+  // peer mode: sum inbox slots in rank order instead of reading hist
+  int32_t peer_world; const double* inbox; const unsigned int* flags; unsigned int epoch;
+  double* hist_out; double* w2_out; int32_t w2_live;
+  int32_t* status;   // set to 1 on peer timeout
+};
+
+struct BinArgs {
+  int64_t n_events, e_pad;
+  const int32_t* sample_id;
+  const double* kin;           // [d * n_events + e]
+  int32_t n_samples;
+  const int32_t* n_dim;        // [n_samples]
+  const int32_t* nbins;        // [n_samples*kMaxDim]
+  const int32_t* edge_off;     // [n_samples*kMaxDim] offset into edges
+  const int32_t* stride;       // [n_samples*kMaxDim]
+  const int32_t* global_off;   // [n_samples]
+  const double* edges;
+  int32_t* bin;                // [e_pad]
+};
+
+struct RetileArgs {
+  int64_t n;                   // events in chunk
+  int64_t tile0_event;         // chunk's first event is the first lane of a tile
+  int32_t T, P;
+  const uint64_t* start_c;     // [n+1]
+  const int16_t* paramNo;
+  const uint64_t* knot_off;
+  const float4* coeff_many;
+  const uint64_t* start_l;     // [n+1]
+  const int16_t* paramNo_l;
+  const float2* coeff_l;
+  const int32_t* tile_sig;     // [tiles in chunk]
+  const int16_t* slot_of_param;// [n_sigs * P]  slot (cubic or linear numbering) or -1
+  const int32_t* segbase_of_param; // [n_sigs * P] first segment row of the parameter's slot
+  const int16_t* nseg;         // [P] segments stored per parameter (n_pts-1)
+  const uint64_t* tile_cub_off;// [tiles] float4 offset of tile's cubic block in chunk pool
+  const uint64_t* tile_lin_off;// [tiles] float2 offset
+  float4* cub_pool;
+  float2* lin_pool;
+};
+
+// launchers (m3b_kernels.cu)
+cudaError_t launch_fill(const FillArgs& a, int grid, int smem_bytes, cudaStream_t s);
+cudaError_t launch_llh(const LlhArgs& a, cudaStream_t s);
+cudaError_t launch_bins(const BinArgs& a, cudaStream_t s);
+cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s);
+cudaError_t fill_occupancy(int T, int smem_bytes, int* blocks_per_sm);
+cudaError_t fill_set_smem(int T, int smem_bytes);
+int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
+
+}  // namespace m3b

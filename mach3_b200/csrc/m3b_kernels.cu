@@ -1,0 +1,522 @@
+// m3b_kernels.cu -- hand-written sm_100a kernels of the MaCh3 per-step likelihood hot path.
+//
+//   fill_kernel   fused   SMonolith::CalcSplineWeights + CalcTotalEventWeight
+//                         (Splines/SplineMonolith.cpp:727-830)
+//                       + SampleHandlerFD::CalcWeightTotal + FillArray_MP
+//                         (Samples/SampleHandlerFD.cpp:390-448, 568-594)
+//                       + SampleHandlerFD::GetLikelihood / SampleHandlerBase::GetTestStatLLH
+//                         (Samples/SampleHandlerFD.cpp:1284-1300, Samples/SampleHandlerBase.cpp:17-192)
+//                 one launch per MCMC step: HBM-bound coefficient stream -> registers -> per-event
+//                 product -> shared-memory privatised histogram -> global f64 reduction -> the last
+//                 block to finish reduces the likelihood (block-then-grid) and returns one scalar.
+//   llh_kernel    the likelihood reduction alone (after a multi-GPU histogram exchange)
+//   bin_kernel    BinningHandler::FindGlobalBin (Samples/BinningHandler.cpp:257-277) per event
+//   retile_*      AoS reference monolith -> tiled SoA device layout (setup time)
+//
+// No tensor cores: the path is a bandwidth-bound gather/evaluate/scatter.
+#include "m3b_internal.h"
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace m3b {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers: mbarrier + 1-D bulk (TMA) global->shared copy, streaming vector loads
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+// coefficient rows are read once per step: keep them out of L1, default L2 policy (small
+// workloads stay L2-resident between steps, large ones stream)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {
+  float2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// test statistics, SampleHandlerBase::GetTestStatLLH (Samples/SampleHandlerBase.cpp:35-192), f64
+// ------------------------------------------------------------------------------------------------
+constexpr double kLowMcBound = .00001;   // M3::_LOW_MC_BOUND_ (Manager/Core.h:83)
+
+__device__ __forceinline__ double poisson_llh(double data, double mc) {      // :17-31
+  if (data == 0) return mc;
+  if (mc < kLowMcBound) {
+    if (data > kLowMcBound) return (kLowMcBound - data + data * log(data / kLowMcBound));
+    else if (data >= mc) return 0.;
+  }
+  return (mc - data + data * log(data / mc));
+}
+
+__device__ double test_stat_llh(int ts, double data, double mc, double w2) {
+  switch (ts) {
+    case 1: {   // kBarlowBeeston :46-88
+      double newmc = mc;
+      if (mc < kLowMcBound) {
+        if (data > kLowMcBound) newmc = kLowMcBound;
+        else if (data >= mc) return 0.;
+      }
+      const double fractional = sqrt(w2) / newmc;
+      const double fractional2 = fractional * fractional;
+      const double temp = newmc * fractional2 - 1;
+      const double temp2 = temp * temp + 4 * data * fractional2;
+      if (temp2 < 0) return nan("");          // the reference throws here
+      const double beta = (-1 * temp + sqrt(temp2)) / 2.;
+      double stat = mc * beta;
+      if (data > 0) {
+        newmc *= beta;
+        stat = newmc - data + data * log(data / newmc);
+      }
+      double penalty = 0;
+      if (fractional > 0) penalty = (beta - 1) * (beta - 1) / (2 * fractional2);
+      return stat + penalty;
+    }
+    case 4: {   // kDembinskiAbdelmotteleb :90-126
+      if (w2 == 0) return poisson_llh(data, mc);
+      double newmc = mc;
+      if (mc < kLowMcBound) {
+        if (data > kLowMcBound) newmc = kLowMcBound;
+        else if (data >= mc) return 0.;
+      }
+      const double k = newmc * newmc / w2;
+      const double beta = (data + k) / (newmc + k);
+      newmc *= beta;
+      const double penalty = k * beta - k + k * log(k / (k * beta));
+      double stat = newmc;
+      if (data > 0) stat = newmc - data + data * log(data / newmc);
+      return stat + penalty;
+    }
+    case 2: {   // kIceCube :133-160 (the reference evaluates in long double; f64 here)
+      if (w2 == 0) return poisson_llh(data, mc);
+      const double b = mc / w2;
+      const double a = mc * b + 1;
+      const double stat = -1 * (a * log(b) + lgamma(data + a) - lgamma(data + 1) - ((data + a) * log1p(b)) - lgamma(a));
+      if (mc <= data) {
+        if (data <= kLowMcBound) return 0.;
+        const double poisson = poisson_llh(data, kLowMcBound);
+        if (stat > poisson) return poisson;
+      }
+      return stat;
+    }
+    case 3: {   // kPearson :162-177
+      if (data == 0) return mc / 2.;
+      if (mc < kLowMcBound) {
+        if (data > kLowMcBound) return (data - kLowMcBound) * (data - kLowMcBound) / (2. * kLowMcBound);
+        else if (data >= mc) return 0.;
+      }
+      return (data - mc) * (data - mc) / (2 * mc);
+    }
+    default:    // kPoisson :178-184
+      return poisson_llh(data, mc);
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-level likelihood.  For every sample all threads stride over the sample's bins
+// [start,end), then shuffle-tree per warp; thread s finally adds the warps' partial sums of
+// sample s in warp order and thread 0 adds the samples in sample order.  The summation shape
+// is fixed, so the result is a deterministic function of the histogram.
+// scratch: n_samples * 32 doubles of shared memory.
+constexpr int kMaxSamples = 64;
+
+__device__ void block_llh(const double* __restrict__ hist, const double* __restrict__ w2,
+                          const double* __restrict__ data, const int32_t* __restrict__ sample_start,
+                          int n_samples, int ts, double* llh_dev, double* llh_host, double* scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int s = 0; s < n_samples; ++s) {
+    const int b0 = sample_start[s], b1 = sample_start[s + 1];
+    double acc = 0.;
+    for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x)
+      acc += test_stat_llh(ts, data[b], __ldcg(hist + b), w2 ? __ldcg(w2 + b) : 0.);
+    acc = warp_sum(acc);
+    if (lane == 0) scratch[s * 32 + warp] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_samples) {
+    double tot = 0.;
+    for (int w = 0; w < nwarps; ++w) tot += scratch[threadIdx.x * 32 + w];
+    scratch[threadIdx.x * 32] = tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.;
+    for (int s = 0; s < n_samples; ++s) {
+      const double v = scratch[s * 32];
+      tot += v;
+      llh_dev[1 + s] = v;
+      if (llh_host) llh_host[1 + s] = v;
+    }
+    llh_dev[0] = tot;
+    if (llh_host) { llh_host[0] = tot; __threadfence_system(); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused per-step kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kBatch = 8;
+
+template <int T>
+__global__ void __launch_bounds__(T) fill_kernel(const __grid_constant__ FillArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x;
+  unsigned char* st = smem;
+  int32_t* s_row = reinterpret_cast<int32_t*>(smem + a.step.bytes);
+  float* s_dx = reinterpret_cast<float*>(s_row + a.max_nc);
+  float* s_lv = s_dx + a.max_nc;
+  double* s_hist = reinterpret_cast<double*>(
+      smem + ((a.step.bytes + 4 * (2 * a.max_nc + a.max_nl) + 15) & ~15));
+  double* s_w2 = s_hist + a.n_bins;
+  const bool w2_live = a.w2 != nullptr;
+  const bool smem_hist = a.hist_in_smem != 0;
+
+  // stage the per-step {segment, dx, value, norm} table with one bulk (TMA) copy
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, static_cast<uint32_t>(a.step.bytes));
+    bulk_g2s(st, a.step_table, static_cast<uint32_t>(a.step.bytes), &bar);
+  }
+  if (smem_hist) {
+    for (int i = tid; i < a.n_bins; i += T) s_hist[i] = 0.;
+    if (w2_live) for (int i = tid; i < a.n_bins; i += T) s_w2[i] = 0.;
+  }
+  mbar_wait(&bar, 0);
+  __syncthreads();
+
+  const int32_t* seg = reinterpret_cast<const int32_t*>(st + a.step.off_seg);
+  const float* dxp = reinterpret_cast<const float*>(st + a.step.off_dx);
+  const float* val = reinterpret_cast<const float*>(st + a.step.off_val);
+  const float* norm = reinterpret_cast<const float*>(st + a.step.off_norm);
+
+  int cur_sig = -1, nc = 0, nl = 0;
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const TileDesc td = a.tiles[t];
+    if (td.sig != cur_sig) {            // block-uniform
+      __syncthreads();
+      const SigDesc sd = a.sigs[td.sig];
+      nc = sd.nc; nl = sd.nl;
+      const int32_t* pool = a.sig_pool + sd.off;
+      for (int s = tid; s < nc; s += T) {
+        const int p = pool[s];
+        s_row[s] = (pool[nc + s] + seg[p]) * T;
+        s_dx[s] = dxp[p];
+      }
+      for (int s = tid; s < nl; s += T) s_lv[s] = val[pool[2 * nc + s]];
+      cur_sig = td.sig;
+      __syncthreads();
+    }
+    const int64_t e = static_cast<int64_t>(t) * T + tid;
+
+    // event-table loads first so they fly together with the coefficient stream
+    const int bin = a.bin[e];
+    float w_osc = 1.f, w_static = 1.f;
+    if (a.osc) {
+      const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
+      w_osc = a.osc[oi];
+    }
+    if (a.static_w) w_static = a.static_w[e];
+    // CalcWeightTotal, first factor: norms (double -> float on the host), reference order
+    float w = 1.0f;
+    #pragma unroll 4
+    for (int j = 0; j < a.norm_slots; ++j) {
+      const int i = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + e];
+      w *= (i >= 0 ? norm[i] : 1.0f);
+    }
+
+    // CalcSplineWeights + CalcTotalEventWeight: cubic responses in slot (= parameter) order, then
+    // TF1.  Loads are issued kBatch at a time so every thread keeps kBatch*16 B in flight.
+    float w_spl = 1.0f;
+    const float4* cub = td.cub + tid;
+    for (int s0 = 0; s0 < nc; s0 += kBatch) {
+      float4 c[kBatch];
+      #pragma unroll
+      for (int j = 0; j < kBatch; ++j)
+        if (s0 + j < nc) c[j] = ldg_stream(cub + s_row[s0 + j]);
+      #pragma unroll
+      for (int j = 0; j < kBatch; ++j)
+        if (s0 + j < nc) {
+          const float dx = s_dx[s0 + j];
+          w_spl *= fmaf(dx, fmaf(dx, fmaf(dx, c[j].w, c[j].z), c[j].y), c[j].x);
+        }
+    }
+    const float2* lin = td.lin + tid;
+    for (int s0 = 0; s0 < nl; s0 += kBatch) {
+      float2 c[kBatch];
+      #pragma unroll
+      for (int j = 0; j < kBatch; ++j)
+        if (s0 + j < nl) c[j] = ldg_stream(lin + (s0 + j) * T);
+      #pragma unroll
+      for (int j = 0; j < kBatch; ++j)
+        if (s0 + j < nl) w_spl *= fmaf(c[j].x, s_lv[s0 + j], c[j].y);
+    }
+
+    // then osc, spline, extra -- the push order of total_weight_pointers
+    w *= w_osc;
+    w *= w_spl;
+    w *= w_static;
+
+    if (a.evt_spline_w && e < a.n_events) { a.evt_spline_w[e] = w_spl; a.evt_total_w[e] = w; }
+
+    // FillArray_MP: skip w<=0 and under/overflow; mc += w; w2 += w*w (float product)
+    if (w > 0.f && bin >= 0) {
+      if (smem_hist) {
+        atomicAdd(s_hist + bin, static_cast<double>(w));
+        if (w2_live) atomicAdd(s_w2 + bin, static_cast<double>(w * w));
+      } else {
+        atomicAdd(a.hist + bin, static_cast<double>(w));
+        if (w2_live) atomicAdd(a.w2 + bin, static_cast<double>(w * w));
+      }
+    }
+  }
+
+  // block -> grid: flush the privatised histogram
+  if (smem_hist) {
+    __syncthreads();
+    for (int i = tid; i < a.n_bins; i += T) {
+      const double v = s_hist[i];
+      if (v != 0.) atomicAdd(a.hist + i, v);
+    }
+    if (w2_live)
+      for (int i = tid; i < a.n_bins; i += T) {
+        const double v = s_w2[i];
+        if (v != 0.) atomicAdd(a.w2 + i, v);
+      }
+  }
+  if (!a.fuse_llh && a.peer_world == 0) return;
+
+  // last-block-done ticket
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int tk = atomicAdd(a.ticket, 1u);
+    s_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  if (a.peer_world > 0) {
+    // push the finished partial histogram into every rank's inbox over NVLink peer memory
+    const int nb2 = a.n_bins * (w2_live ? 2 : 1);
+    for (int r = 0; r < a.peer_world; ++r) {
+      double* dst = a.peer_inbox[r] + static_cast<int64_t>(a.peer_rank) * 2 * a.n_bins;
+      for (int i = tid; i < nb2; i += T) dst[i] = __ldcg((i < a.n_bins ? a.hist : a.w2 - a.n_bins) + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < a.peer_world) {
+      unsigned int* f = a.peer_flag[tid] + a.peer_rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.peer_epoch) : "memory");
+    }
+    if (tid == 0) *a.ticket = 0u;
+    return;
+  }
+
+  block_llh(a.hist, a.w2_frozen, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host,
+            reinterpret_cast<double*>(smem));
+  // prepare the next step: zero its histogram(s), re-arm the ticket
+  if (a.hist_next) for (int i = tid; i < a.n_bins; i += T) a.hist_next[i] = 0.;
+  if (a.w2_next) for (int i = tid; i < a.n_bins; i += T) a.w2_next[i] = 0.;
+  if (tid == 0) *a.ticket = 0u;
+}
+
+int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
+  int b = (a.step.bytes + 4 * (2 * a.max_nc + a.max_nl) + 15) & ~15;
+  if (hist_in_smem) b += 8 * a.n_bins * (w2_live ? 2 : 1);
+  const int llh_scratch = a.n_samples * 32 * 8;   // block_llh reuses the dynamic region
+  return b > llh_scratch ? b : llh_scratch;
+}
+
+template <int T>
+static cudaError_t launch_fill_t(const FillArgs& a, int grid, int smem, cudaStream_t s) {
+  fill_kernel<T><<<grid, T, smem, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_fill(const FillArgs& a, int grid, int smem, cudaStream_t s) {
+  switch (a.T) {
+    case 128: return launch_fill_t<128>(a, grid, smem, s);
+    case 256: return launch_fill_t<256>(a, grid, smem, s);
+    case 512: return launch_fill_t<512>(a, grid, smem, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+cudaError_t fill_set_smem(int T, int smem) {
+  const int cap = smem > 48 * 1024 ? smem : 48 * 1024;
+  switch (T) {
+    case 128: return cudaFuncSetAttribute(fill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    case 256: return cudaFuncSetAttribute(fill_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    case 512: return cudaFuncSetAttribute(fill_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    default: return cudaErrorInvalidValue;
+  }
+}
+cudaError_t fill_occupancy(int T, int smem, int* bps) {
+  switch (T) {
+    case 128: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, fill_kernel<128>, 128, smem);
+    case 256: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, fill_kernel<256>, 256, smem);
+    case 512: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, fill_kernel<512>, 512, smem);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// likelihood alone (after an external all-reduce, or after the peer push: sums inbox slots)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) llh_kernel(const __grid_constant__ LlhArgs a) {
+  __shared__ double s_part[kMaxSamples * 32];
+  __shared__ int s_ok;
+  const double* hist = a.hist;
+  const double* w2 = a.w2;
+  if (a.peer_world > 0) {
+    // wait (bounded) until every rank's partial histogram of this epoch has landed in our inbox
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (threadIdx.x < a.peer_world) {
+      const unsigned int* f = a.flags + threadIdx.x;
+      unsigned int v = 0;
+      const long long t0 = clock64();
+      while (true) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v == a.epoch) break;
+        if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }   // ~2 s: give up, report
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+    if (!s_ok) { if (threadIdx.x == 0) { *a.status = 1; a.llh_dev[0] = nan(""); if (a.llh_host) a.llh_host[0] = nan(""); } return; }
+    // fixed rank order => every rank computes the bit-identical global histogram
+    const int nb2 = a.n_bins * (a.w2_live ? 2 : 1);
+    for (int i = threadIdx.x; i < nb2; i += blockDim.x) {
+      double acc = 0.;
+      for (int r = 0; r < a.peer_world; ++r) acc += __ldcg(a.inbox + static_cast<int64_t>(r) * 2 * a.n_bins + i);
+      if (i < a.n_bins) a.hist_out[i] = acc; else a.w2_out[i - a.n_bins] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    hist = a.hist_out;
+    if (a.w2_live) w2 = a.w2_out;
+  }
+  block_llh(hist, w2, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, s_part);
+}
+cudaError_t launch_llh(const LlhArgs& a, cudaStream_t s) {
+  llh_kernel<<<1, 1024, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// BinningHandler::FindGlobalBin, uniform arm.  SampleBinningInfo::FindBin's nominal-bin and
+// adjacent-bin shortcuts (Samples/SampleStructs.h:588-609) return exactly upper_bound(edges,x)-1
+// whenever they fire, so the stateless form below is bit-identical to the reference.
+// ------------------------------------------------------------------------------------------------
+__global__ void bin_kernel(const __grid_constant__ BinArgs a) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= a.e_pad) return;
+  if (e >= a.n_events) { a.bin[e] = -1; return; }
+  const int s = a.sample_id[e];
+  const int nd = a.n_dim[s];
+  int g = 0;
+  bool ok = true;
+  for (int d = 0; d < nd; ++d) {
+    const double x = a.kin[static_cast<int64_t>(d) * a.n_events + e];
+    const int nb = a.nbins[s * kMaxDim + d];
+    const double* ed = a.edges + a.edge_off[s * kMaxDim + d];
+    if (x < ed[0] || x >= ed[nb]) { ok = false; break; }       // SampleStructs.h:584
+    int lo = 0, len = nb + 1;                                    // std::upper_bound
+    while (len > 0) {
+      const int half = len >> 1;
+      if (!(x < ed[lo + half])) { lo += half + 1; len -= half + 1; } else len = half;
+    }
+    g += (lo - 1) * a.stride[s * kMaxDim + d];
+  }
+  a.bin[e] = ok ? g + a.global_off[s] : -1;
+}
+cudaError_t launch_bins(const BinArgs& a, cudaStream_t s) {
+  const int threads = 256;
+  const int64_t blocks = (a.e_pad + threads - 1) / threads;
+  bin_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup: AoS monolith -> tiled SoA.  identity rows first ({1,0,0,0} / {0,1}: a response that
+// multiplies by exactly 1.0f), then every event scatters its own responses.
+// ------------------------------------------------------------------------------------------------
+__global__ void identity_kernel(float4* cub, int64_t n_cub, float2* lin, int64_t n_lin) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = i; k < n_cub; k += stride) cub[k] = make_float4(1.f, 0.f, 0.f, 0.f);
+  for (int64_t k = i; k < n_lin; k += stride) lin[k] = make_float2(0.f, 1.f);
+}
+
+__global__ void retile_kernel(const __grid_constant__ RetileArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const int64_t tile = i / a.T;
+  const int lane = static_cast<int>(i - tile * a.T);
+  const int sig = a.tile_sig[tile];
+  const int16_t* slot_of = a.slot_of_param + static_cast<int64_t>(sig) * a.P;
+  const int32_t* segbase_of = a.segbase_of_param + static_cast<int64_t>(sig) * a.P;
+  float4* cub = a.cub_pool + a.tile_cub_off[tile] + lane;
+  float2* lin = a.lin_pool + a.tile_lin_off[tile] + lane;
+  for (uint64_t s = a.start_c[i]; s < a.start_c[i + 1]; ++s) {
+    const int p = a.paramNo[s];
+    const int nseg = a.nseg[p];
+    const float4* src = a.coeff_many + a.knot_off[s];
+    float4* dst = cub + static_cast<int64_t>(segbase_of[p]) * a.T;
+    for (int k = 0; k < nseg; ++k) dst[static_cast<int64_t>(k) * a.T] = src[k];
+  }
+  for (uint64_t s = a.start_l[i]; s < a.start_l[i + 1]; ++s) {
+    const int p = a.paramNo_l[s];
+    lin[static_cast<int64_t>(slot_of[p]) * a.T] = a.coeff_l[s];
+  }
+}
+
+cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s) {
+  if (n_identity_cub > 0 || n_identity_lin > 0) {
+    identity_kernel<<<148 * 8, 256, 0, s>>>(a.cub_pool, n_identity_cub, a.lin_pool, n_identity_lin);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (a.n > 0) {
+    const int threads = 128;
+    retile_kernel<<<static_cast<unsigned>((a.n + threads - 1) / threads), threads, 0, s>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace m3b

@@ -1,0 +1,252 @@
+"""ctypes binding of libm3b200.so (include/m3b200.h).  Fails loudly when the CUDA library is
+missing or cannot create a device context: there is no CPU fallback in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libm3b200.so")
+
+OK = 0
+POISSON, BARLOW_BEESTON, ICECUBE, PEARSON, DEMBINSKI_ABDELMOTTELEB = range(5)
+FLAG_KEEP_EVENT_WEIGHTS = 1
+FLAG_KEEP_KINEMATICS = 2
+FLAG_NO_FUSED_LLH = 4
+
+#: every symbol include/m3b200.h declares
+EXPORTS = (
+    "m3b_create", "m3b_destroy", "m3b_last_error", "m3b_abi_version", "m3b_set_stream",
+    "m3b_splines_begin", "m3b_splines_append", "m3b_splines_end", "m3b_upload_spline_monolith",
+    "m3b_upload_binning", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer",
+    "m3b_set_test_statistic", "m3b_reset_w2",
+    "m3b_step", "m3b_step_segments", "m3b_llh", "m3b_find_segments", "m3b_synchronize",
+    "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
+    "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
+    "m3b_get_info",
+)
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("test_statistic", C.c_int32), ("update_w2", C.c_int32),
+                ("tile_events", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 11)]
+
+
+class Info(C.Structure):
+    _fields_ = [("n_events", C.c_int64), ("n_tiles", C.c_int64), ("n_params", C.c_int32), ("n_bins", C.c_int32),
+                ("n_samples", C.c_int32), ("n_signatures", C.c_int32), ("tile_events", C.c_int32),
+                ("grid_blocks", C.c_int32), ("smem_bytes", C.c_int32), ("hist_in_smem", C.c_int32),
+                ("device_bytes", C.c_uint64), ("active_bytes_per_step", C.c_uint64), ("steps", C.c_uint64),
+                ("kernel_launches", C.c_uint64)]
+
+
+class M3BError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libm3b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libm3b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                               "mach3_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.m3b_last_error.restype = C.c_char_p
+        L.m3b_last_error.argtypes = [C.c_void_p]
+        L.m3b_destroy.restype = None
+        L.m3b_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype)
+
+
+class Handle:
+    """One device context = one sample handler + its spline monolith."""
+
+    def __init__(self, device=0, test_statistic=POISSON, update_w2=False, tile_events=0, flags=0):
+        self.L = load()
+        cfg = Config(device=device, test_statistic=test_statistic, update_w2=int(update_w2),
+                     tile_events=tile_events, flags=flags)
+        self.h = C.c_void_p()
+        rc = self.L.m3b_create(C.byref(cfg), C.byref(self.h))
+        if rc != OK:
+            raise M3BError(rc, (self.L.m3b_last_error(None) or b"").decode())
+        self.n_samples = 0
+        self.n_bins = 0
+        self.n_events = 0
+        self.n_params = 0
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise M3BError(rc, (self.L.m3b_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.L.m3b_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.m3b_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    # ---- splines
+    def splines_begin(self, n_params, max_knots, coeff_x, n_pts, n_events_total):
+        cx, npt = _c(coeff_x, np.float32), _c(n_pts, np.int16)
+        self.n_params = int(n_params)
+        self._ck(self.L.m3b_splines_begin(self.h, C.c_int32(n_params), C.c_int32(max_knots), _p(cx), _p(npt),
+                                          C.c_int64(n_events_total)))
+
+    def splines_append(self, spl):
+        a = [_c(spl["nParamPerEvent"], np.uint32), _c(spl["paramNo_arr"], np.int16), _c(spl["nKnots_arr"], np.uint64),
+             _c(spl["coeff_many"], np.float32), _c(spl["nParamPerEvent_tf1"], np.uint32),
+             _c(spl["paramNo_tf1"], np.int16), _c(spl["coeff_tf1"], np.float32)]
+        n = a[0].size // 2
+        self._ck(self.L.m3b_splines_append(self.h, C.c_int64(n), _p(a[0]), _p(a[1]), _p(a[2]),
+                                           C.c_uint64(a[3].size // 4), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6])))
+
+    def splines_end(self):
+        self._ck(self.L.m3b_splines_end(self.h))
+
+    def upload_spline_monolith(self, n_params, max_knots, coeff_x, n_pts, spl):
+        """One-shot upload with the reference's own types (unsigned int knot offsets)."""
+        cx, npt = _c(coeff_x, np.float32), _c(n_pts, np.int16)
+        a = [_c(spl["nParamPerEvent"], np.uint32), _c(spl["paramNo_arr"], np.int16), _c(spl["nKnots_arr"], np.uint32),
+             _c(spl["coeff_many"], np.float32), _c(spl["nParamPerEvent_tf1"], np.uint32),
+             _c(spl["paramNo_tf1"], np.int16), _c(spl["coeff_tf1"], np.float32)]
+        self.n_params = int(n_params)
+        self._ck(self.L.m3b_upload_spline_monolith(
+            self.h, C.c_int32(n_params), C.c_int32(max_knots), _p(cx), _p(npt), C.c_int64(a[0].size // 2),
+            _p(a[0]), _p(a[1]), _p(a[2]), C.c_uint32(a[3].size // 4), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6])))
+
+    # ---- binning / events / data
+    def upload_binning(self, edges):
+        """edges: list over samples of list over dims of edge arrays."""
+        ns = len(edges)
+        ndim = np.array([len(e) for e in edges], np.int32)
+        nbins = np.zeros(ns * 4, np.int32)
+        flat = []
+        for s, dims in enumerate(edges):
+            for d, e in enumerate(dims):
+                nbins[s * 4 + d] = len(e) - 1
+                flat.append(np.asarray(e, np.float64))
+        flat = np.ascontiguousarray(np.concatenate(flat))
+        self._ck(self.L.m3b_upload_binning(self.h, C.c_int32(ns), _p(ndim), _p(nbins), _p(flat)))
+        self.n_samples = ns
+        self.n_bins = int(sum(int(np.prod([len(e) - 1 for e in dims])) for dims in edges))
+
+    def upload_events(self, sample_id, kin, norm_idx=None, n_norm_per_event=0, n_norm_values=0, use_osc=False,
+                      osc_idx=None, n_osc_values=0, static_w=None):
+        sid, k = _c(sample_id, np.int32), _c(kin, np.float64)
+        ni, oi, sw = _c(norm_idx, np.int16), _c(osc_idx, np.int32), _c(static_w, np.float32)
+        self.n_events = sid.size
+        self._ck(self.L.m3b_upload_events(self.h, C.c_int64(sid.size), _p(sid), _p(k), C.c_int32(n_norm_per_event),
+                                          _p(ni), C.c_int32(n_norm_values), C.c_int32(int(use_osc)), _p(oi),
+                                          C.c_int64(n_osc_values), _p(sw)))
+
+    def upload_data(self, data):
+        d = _c(data, np.float64)
+        self._ck(self.L.m3b_upload_data(self.h, _p(d), C.c_int32(d.size)))
+
+    def upload_osc(self, osc_w):
+        o = _c(osc_w, np.float32)
+        self._ck(self.L.m3b_upload_osc(self.h, _p(o), C.c_int64(o.size)))
+
+    def register_host_buffer(self, arr):
+        self._ck(self.L.m3b_register_host_buffer(self.h, _p(arr), C.c_uint64(arr.nbytes)))
+
+    def set_test_statistic(self, ts):
+        self._ck(self.L.m3b_set_test_statistic(self.h, C.c_int32(ts)))
+
+    def reset_w2(self):
+        self._ck(self.L.m3b_reset_w2(self.h))
+
+    # ---- step
+    def step(self, spline_pars, norm_pars=None, osc_w=None, mode="fused"):
+        """Asynchronous.  Arrays must stay alive until the next synchronising call."""
+        sp = _c(spline_pars, np.float64)
+        nm = _c(norm_pars, np.float64)
+        if osc_w is not None:
+            assert osc_w.dtype == np.float32 and osc_w.flags.c_contiguous
+        self._keep = (sp, nm, osc_w)
+        fn = {"fused": self.L.m3b_step, "fill": self.L.m3b_step_fill, "peer": self.L.m3b_step_peer}[mode]
+        self._ck(fn(self.h, _p(sp), _p(nm), _p(osc_w)))
+
+    def step_segments(self, param_values, segments, norm_pars=None, osc_w=None):
+        pv, sg, nm = _c(param_values, np.float32), _c(segments, np.int16), _c(norm_pars, np.float64)
+        self._keep = (pv, sg, nm, osc_w)
+        self._ck(self.L.m3b_step_segments(self.h, _p(pv), _p(sg), _p(nm), _p(osc_w)))
+
+    def llh(self, per_sample=False):
+        tot = C.c_double(0)
+        ps = np.zeros(max(self.n_samples, 1), np.float64)
+        self._ck(self.L.m3b_llh(self.h, C.byref(tot), _p(ps)))
+        return (tot.value, ps[:self.n_samples]) if per_sample else tot.value
+
+    def find_segments(self, spline_pars):
+        sp = _c(spline_pars, np.float64)
+        seg = np.zeros(self.n_params, np.int16)
+        val = np.zeros(self.n_params, np.float32)
+        self._ck(self.L.m3b_find_segments(self.h, _p(sp), _p(seg), _p(val)))
+        return seg, val
+
+    def synchronize(self):
+        self._ck(self.L.m3b_synchronize(self.h))
+
+    # ---- read-back
+    def read_hist(self):
+        mc, w2 = np.zeros(self.n_bins, np.float64), np.zeros(self.n_bins, np.float64)
+        self._ck(self.L.m3b_read_hist(self.h, _p(mc), _p(w2)))
+        return mc, w2
+
+    def read_event_weights(self):
+        sw, tw = np.zeros(self.n_events, np.float32), np.zeros(self.n_events, np.float32)
+        self._ck(self.L.m3b_read_event_weights(self.h, _p(sw), _p(tw)))
+        return sw, tw
+
+    def read_event_bins(self):
+        b = np.zeros(self.n_events, np.int32)
+        self._ck(self.L.m3b_read_event_bins(self.h, _p(b)))
+        return b
+
+    # ---- multi-GPU
+    def hist_device_ptr(self):
+        ptr, nb, live = C.c_void_p(), C.c_int32(), C.c_int32()
+        self._ck(self.L.m3b_hist_device_ptr(self.h, C.byref(ptr), C.byref(nb), C.byref(live)))
+        return ptr.value, nb.value, bool(live.value)
+
+    def llh_from_hist(self):
+        self._ck(self.L.m3b_llh_from_hist(self.h))
+
+    def peer_export(self, rank, world):
+        buf = (C.c_ubyte * 64)()
+        self._ck(self.L.m3b_peer_export(self.h, C.c_int32(rank), C.c_int32(world), buf))
+        return bytes(buf)
+
+    def peer_import(self, peer_rank, handle_bytes):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle_bytes)
+        self._ck(self.L.m3b_peer_import(self.h, C.c_int32(peer_rank), buf))
+
+    def info(self) -> Info:
+        i = Info()
+        self._ck(self.L.m3b_get_info(self.h, C.byref(i)))
+        return i

@@ -1,0 +1,664 @@
+/*
+ * m3_oracle.c -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of the reference's per-MCMC-step likelihood path, function by
+ * function, each citing the reference file:line it follows (paths relative to the
+ * mach3-software/MaCh3 tree, v2.4.2).  Types are those of the reference's
+ * _LOW_MEMORY_STRUCTS_ build (M3::float_t = float, M3::int_t = short; Manager/Core.h:27-35),
+ * the only build in which SMonolith is wired into SampleHandlerFD
+ * (Samples/SampleHandlerFD.cpp:1244-1254).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library, and only as the checker or the timed CPU baseline.  The product
+ * (mach3_b200/) never links, imports or calls it.
+ *
+ * PARITY PIN STATUS: the reference ships no tests, fixtures or golden vectors for this path
+ *  and its host code cannot be built here (needs ROOT, yaml-cpp, spdlog).  The
+ * spline-evaluation part (CalcSplineWeights + CalcTotalEventWeight) is pinned against the
+ * reference's OWN CUDA kernels (Splines/gpuSplineUtils.cu compiled from /root/reference into
+ * oracle/_ref, run on a B200; vectors committed under tests/golden/).  FindSplineSegment,
+ * FillArray, FindBin and the test statistics are "parity unpinned": checked only against
+ * known-answer tests derived from the formulas.
+ *
+ * The data layout deliberately mirrors the reference (AoS {y,b,c,d} knots, {count,start}
+ * CSR, one heap-allocated pointer vector per event) so that timing it is a fair stand-in
+ * for the reference's multithreaded CPU path.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define M3O_API __attribute__((visibility("default")))
+
+/* Manager/Core.h:83,91 */
+static const double LOW_MC_BOUND = .00001;
+enum { UnderOverFlowBin = -1 };
+/* Splines/SplineCommon.h:13,15 */
+enum { nCoeff = 4, nTF1Coeff = 2 };
+/* Samples/SampleStructs.h:105-112 */
+enum TestStatistic { kPoisson, kBarlowBeeston, kIceCube, kPearson, kDembinskiAbdelmotteleb, kNTestStatistics };
+
+/* ============================================================================================
+ * Splines: FastSplineInfo (Splines/SplineStructs.h:21-44) + SplineBase + SMonolith state
+ * ========================================================================================== */
+typedef struct {
+  short nPts;
+  const float* xPts;              /* knot positions (first spline seen for the parameter) */
+  int   n_x;                      /* xPts.size() */
+  short CurrSegment;
+  const double* splineParsPointer;
+} FastSplineInfo;
+
+typedef struct {
+  /* SplineBase (Splines/SplineBase.h:77-81) */
+  short nParams;
+  FastSplineInfo* SplineInfoArray;
+  short* SplineSegments;
+  float* ParamValues;
+  /* SplineMonoStruct (Splines/SplineCommon.h:30-50); knot offsets widened to 64 bit */
+  const float* coeff_x;
+  const float* coeff_many;
+  const uint64_t* nKnots_arr;
+  const short* paramNo_arr;
+  /* SMonolith (Splines/SplineMonolith.h:96-137) */
+  unsigned int NEvents;
+  short _max_knots;
+  uint64_t NSplines_valid, NTF1_valid;
+  const uint32_t* cpu_nParamPerEvent;
+  const uint32_t* cpu_nParamPerEvent_tf1;
+  const float* cpu_coeff_TF1_many;
+  const short* cpu_paramNo_TF1_arr;
+  float* cpu_weights_spline_var;
+  float* cpu_weights_tf1_var;
+  float* cpu_total_weights;
+  /* 64-bit {start} of every event: the reference's unsigned start index overflows beyond
+   * 2^32 responses; recomputed here from the counts */
+  uint64_t* start_c;
+  uint64_t* start_l;
+} SMonolith;
+
+M3O_API SMonolith* m3o_monolith_create(int nParams, int max_knots, const float* coeff_x, const short* n_pts,
+                                       unsigned int NEvents,
+                                       const uint32_t* nParamPerEvent, const short* paramNo_arr,
+                                       const uint64_t* nKnots_arr, const float* coeff_many,
+                                       const uint32_t* nParamPerEvent_tf1, const short* paramNo_tf1,
+                                       const float* coeff_tf1) {
+  SMonolith* m = (SMonolith*)calloc(1, sizeof(SMonolith));
+  m->nParams = (short)nParams;
+  m->_max_knots = (short)max_knots;
+  m->coeff_x = coeff_x; m->coeff_many = coeff_many; m->nKnots_arr = nKnots_arr; m->paramNo_arr = paramNo_arr;
+  m->NEvents = NEvents;
+  m->cpu_nParamPerEvent = nParamPerEvent; m->cpu_nParamPerEvent_tf1 = nParamPerEvent_tf1;
+  m->cpu_coeff_TF1_many = coeff_tf1; m->cpu_paramNo_TF1_arr = paramNo_tf1;
+  m->SplineInfoArray = (FastSplineInfo*)calloc((size_t)nParams, sizeof(FastSplineInfo));
+  /* Splines/SplineMonolith.cpp:85-95: segments 0, values -999 */
+  m->SplineSegments = (short*)calloc((size_t)nParams, sizeof(short));
+  m->ParamValues = (float*)malloc(sizeof(float) * (size_t)nParams);
+  for (int j = 0; j < nParams; ++j) {
+    m->ParamValues[j] = -999;
+    m->SplineInfoArray[j].nPts = n_pts[j];
+    m->SplineInfoArray[j].n_x = n_pts[j] > 0 ? n_pts[j] : 0;
+    m->SplineInfoArray[j].xPts = coeff_x + (size_t)j * (size_t)max_knots;
+    m->SplineInfoArray[j].CurrSegment = 0;
+    m->SplineInfoArray[j].splineParsPointer = NULL;
+  }
+  m->start_c = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)NEvents + 1));
+  m->start_l = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)NEvents + 1));
+  m->start_c[0] = 0; m->start_l[0] = 0;
+  for (unsigned int e = 0; e < NEvents; ++e) {
+    m->start_c[e + 1] = m->start_c[e] + nParamPerEvent[2 * e];
+    m->start_l[e + 1] = m->start_l[e] + nParamPerEvent_tf1[2 * e];
+  }
+  m->NSplines_valid = m->start_c[NEvents];
+  m->NTF1_valid = m->start_l[NEvents];
+  /* Splines/SplineMonolith.cpp:241-245 */
+  m->cpu_total_weights = (float*)calloc((size_t)NEvents + 1, sizeof(float));
+  m->cpu_weights_spline_var = (float*)calloc((size_t)m->NSplines_valid + 1, sizeof(float));
+  m->cpu_weights_tf1_var = (float*)calloc((size_t)m->NTF1_valid + 1, sizeof(float));
+  return m;
+}
+
+M3O_API void m3o_monolith_destroy(SMonolith* m) {
+  if (!m) return;
+  free(m->SplineInfoArray); free(m->SplineSegments); free(m->ParamValues);
+  free(m->cpu_total_weights); free(m->cpu_weights_spline_var); free(m->cpu_weights_tf1_var);
+  free(m->start_c); free(m->start_l);
+  free(m);
+}
+
+/* SMonolith::setSplinePointers (Splines/SplineMonolith.h:44-46); here param i -> &base[i] */
+M3O_API void m3o_set_spline_pointers(SMonolith* m, const double* base) {
+  for (short i = 0; i < m->nParams; ++i) m->SplineInfoArray[i].splineParsPointer = base + i;
+}
+
+/* SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-109) */
+M3O_API void m3o_find_spline_segment(SMonolith* m) {
+  for (short i = 0; i < m->nParams; ++i) {
+    const short nPoints = m->SplineInfoArray[i].nPts;
+    const float* xArray = m->SplineInfoArray[i].xPts;
+
+    /* :54-55 the variation is narrowed to float, stored for every parameter */
+    const float xvar = (float)(*m->SplineInfoArray[i].splineParsPointer);
+    m->ParamValues[i] = xvar;
+
+    /* :60 parameters without any spline are skipped */
+    if (m->SplineInfoArray[i].n_x == 0) continue;
+
+    short segment = 0;
+    short kHigh = (short)(nPoints - 1);
+    const short PreviousSegment = m->SplineInfoArray[i].CurrSegment;
+
+    if (xvar <= xArray[0]) {                                   /* :69 */
+      segment = 0;
+    } else if (xvar >= xArray[nPoints - 1]) {                  /* :72 */
+      segment = kHigh;
+    } else if (xArray[PreviousSegment + 1] > xvar && xvar >= xArray[PreviousSegment]) { /* :76 */
+      segment = PreviousSegment;
+    } else {                                                   /* :79-95 binary search */
+      short kHalf = 0;
+      while (kHigh - segment > 1) {
+        kHalf = (short)((segment + kHigh) / 2);
+        if (xvar > xArray[kHalf]) segment = kHalf;
+        else kHigh = kHalf;
+      }
+    }
+    if (segment >= nPoints - 1 && nPoints > 1) segment = (short)(nPoints - 2);   /* :97 */
+
+    m->SplineInfoArray[i].CurrSegment = segment;               /* :102-103 */
+    m->SplineSegments[i] = (short)m->SplineInfoArray[i].CurrSegment;
+  }
+}
+
+/* SMonolith::CalcSplineWeights (Splines/SplineMonolith.cpp:727-788) */
+M3O_API void m3o_calc_spline_weights(SMonolith* m) {
+  #pragma omp parallel
+  {
+    #pragma omp for simd nowait
+    for (uint64_t splineNum = 0; splineNum < m->NSplines_valid; ++splineNum) {
+      const short Param = m->paramNo_arr[splineNum];                              /* :741 */
+      const short segment = m->SplineSegments[Param];                             /* :744 */
+      const short segment_X = (short)(Param * m->_max_knots + segment);           /* :747 */
+      const uint64_t CurrentKnotPos = m->nKnots_arr[splineNum] * nCoeff + (uint64_t)(segment * nCoeff); /* :750 */
+      const float fY = m->coeff_many[CurrentKnotPos];
+      const float fB = m->coeff_many[CurrentKnotPos + 1];
+      const float fC = m->coeff_many[CurrentKnotPos + 2];
+      const float fD = m->coeff_many[CurrentKnotPos + 3];
+      const float dx = m->ParamValues[Param] - m->coeff_x[segment_X];             /* :759 */
+      m->cpu_weights_spline_var[splineNum] = fmaf(dx, fmaf(dx, fmaf(dx, fD, fC), fB), fY); /* :762 */
+    }
+    #pragma omp for simd
+    for (uint64_t tf1Num = 0; tf1Num < m->NTF1_valid; ++tf1Num) {
+      const float x = m->ParamValues[m->cpu_paramNo_TF1_arr[tf1Num]];             /* :773 */
+      const uint64_t TF1_Index = tf1Num * nTF1Coeff;
+      const float a = m->cpu_coeff_TF1_many[TF1_Index];
+      const float b = m->cpu_coeff_TF1_many[TF1_Index + 1];
+      m->cpu_weights_tf1_var[tf1Num] = fmaf(a, x, b);                             /* :780 */
+    }
+  }
+}
+
+/* SMonolith::CalcTotalEventWeight (Splines/SplineMonolith.cpp:792-830) */
+M3O_API void m3o_calc_total_event_weight(SMonolith* m) {
+  #pragma omp parallel for
+  for (unsigned int EventNum = 0; EventNum < m->NEvents; ++EventNum) {
+    float totalWeight = 1.0f;
+    const unsigned int Offset = 2 * EventNum;
+    const uint64_t startIndex = m->start_c[EventNum];
+    const unsigned int numParams = m->cpu_nParamPerEvent[Offset];
+    #pragma omp simd reduction(*:totalWeight)
+    for (unsigned int id = 0; id < numParams; ++id) totalWeight *= m->cpu_weights_spline_var[startIndex + id];
+    const uint64_t startIndex_tf1 = m->start_l[EventNum];
+    const unsigned int numParams_tf1 = m->cpu_nParamPerEvent_tf1[Offset];
+    #pragma omp simd reduction(*:totalWeight)
+    for (unsigned int id = 0; id < numParams_tf1; ++id) totalWeight *= m->cpu_weights_tf1_var[startIndex_tf1 + id];
+    m->cpu_total_weights[EventNum] = totalWeight;
+  }
+}
+
+/* SMonolith::Evaluate, CPU build (Splines/SplineMonolith.cpp:712-723) */
+M3O_API void m3o_evaluate(SMonolith* m) {
+  m3o_find_spline_segment(m);
+  m3o_calc_spline_weights(m);
+  m3o_calc_total_event_weight(m);
+}
+
+M3O_API const short* m3o_segments(const SMonolith* m) { return m->SplineSegments; }
+M3O_API const float* m3o_param_values(const SMonolith* m) { return m->ParamValues; }
+M3O_API const float* m3o_total_weights(const SMonolith* m) { return m->cpu_total_weights; }       /* retPointer(0) */
+M3O_API const float* m3o_spline_weights(const SMonolith* m) { return m->cpu_weights_spline_var; }
+M3O_API const float* m3o_tf1_weights(const SMonolith* m) { return m->cpu_weights_tf1_var; }
+M3O_API uint64_t m3o_n_splines_valid(const SMonolith* m) { return m->NSplines_valid; }
+M3O_API uint64_t m3o_n_tf1_valid(const SMonolith* m) { return m->NTF1_valid; }
+/* let tests force the cached segment (history dependence of SplineBase.cpp:76) */
+M3O_API void m3o_set_curr_segment(SMonolith* m, int p, int seg) { m->SplineInfoArray[p].CurrSegment = (short)seg; }
+
+/* ============================================================================================
+ * Binning: SampleBinningInfo (Samples/SampleStructs.h:232-676) + BinningHandler
+ * ========================================================================================== */
+typedef struct {        /* Samples/SampleStructs.h:172-183 */
+  double lower_binedge, upper_binedge, lower_lower_binedge, upper_upper_binedge;
+} BinShiftLookup;
+
+#define M3O_MAX_DIM 4
+typedef struct {
+  int nDim;
+  int AxisNBins[M3O_MAX_DIM];
+  double* BinEdges[M3O_MAX_DIM];
+  BinShiftLookup* BinLookup[M3O_MAX_DIM];
+  int Strides[M3O_MAX_DIM];
+  int nBins;
+  int GlobalOffset;
+} SampleBinningInfo;
+
+/* SampleBinningInfo::InitialiseLookUpSingleDimension (Samples/SampleStructs.h:618-647) */
+static void InitialiseLookUpSingleDimension(BinShiftLookup* Bin_Lookup, const double* Bin_Edges, const int TotBins) {
+  for (int bin_i = 0; bin_i < TotBins; bin_i++) {
+    double low_lower_edge = -999999.123456;      /* M3::_DEFAULT_RETURN_VAL_ */
+    double low_edge = Bin_Edges[bin_i];
+    double upper_edge = Bin_Edges[bin_i + 1];
+    double upper_upper_edge = -999999.123456;
+    if (bin_i == 0) low_lower_edge = Bin_Edges[0];
+    else low_lower_edge = Bin_Edges[bin_i - 1];
+    if (bin_i + 2 < TotBins) upper_upper_edge = Bin_Edges[bin_i + 2];
+    else if (bin_i + 1 < TotBins) upper_upper_edge = Bin_Edges[bin_i + 1];
+    Bin_Lookup[bin_i].lower_binedge = low_edge;
+    Bin_Lookup[bin_i].upper_binedge = upper_edge;
+    Bin_Lookup[bin_i].lower_lower_binedge = low_lower_edge;
+    Bin_Lookup[bin_i].upper_upper_binedge = upper_upper_edge;
+  }
+}
+
+/* std::upper_bound over doubles */
+static int upper_bound_d(const double* a, int n, double v) {
+  int lo = 0, len = n;
+  while (len > 0) {
+    int half = len >> 1;
+    if (!(v < a[lo + half])) { lo += half + 1; len -= half + 1; }
+    else len = half;
+  }
+  return lo;
+}
+
+/* SampleBinningInfo::FindBin (Samples/SampleStructs.h:577-613) */
+static int FindBin(const double KinVar, const int NomBin, const int N_Bins,
+                   const double* Bin_Edges, const BinShiftLookup* Bin_Lookup) {
+  if (KinVar < Bin_Edges[0] || KinVar >= Bin_Edges[N_Bins]) return UnderOverFlowBin;   /* :584 */
+  if (NomBin > UnderOverFlowBin) {                                                     /* :588 */
+    const BinShiftLookup* Bin = &Bin_Lookup[NomBin];
+    const double lower = Bin->lower_binedge, upper = Bin->upper_binedge;
+    const double lower_lower = Bin->lower_lower_binedge, upper_upper = Bin->upper_upper_binedge;
+    if (KinVar < upper && KinVar >= lower) return NomBin;                              /* :597 */
+    if (KinVar < lower && KinVar >= lower_lower) return NomBin - 1;                    /* :602 */
+    if (KinVar < upper_upper && KinVar >= upper) return NomBin + 1;                    /* :606 */
+  }
+  return upper_bound_d(Bin_Edges, N_Bins + 1, KinVar) - 1;                             /* :612 */
+}
+
+/* BinningHandler::FindNominalBin (Samples/BinningHandler.cpp:294-307) */
+static int FindNominalBin(const SampleBinningInfo* info, const int iDim, const double Var) {
+  const double* edges = info->BinEdges[iDim];
+  const int ne = info->AxisNBins[iDim] + 1;
+  if (Var < edges[0] || Var >= edges[ne - 1]) return UnderOverFlowBin;
+  return upper_bound_d(edges, ne, Var) - 1;
+}
+
+/* ============================================================================================
+ * Samples: EventInfo (Samples/FarDetectorCoreInfoStruct.h:82-126) + SampleHandlerFD state
+ * ========================================================================================== */
+typedef struct {
+  const double** norm_pointers;         int n_norm;      /* std::vector<const double*>        */
+  const float**  total_weight_pointers; int n_tw;        /* std::vector<const M3::float_t*>   */
+  const double** KinVar;                                 /* std::vector<const double*>        */
+  int*           NomBin;                int n_dim;       /* std::vector<int>                  */
+  int NominalSample;
+} EventInfo;
+
+typedef struct {
+  unsigned int nEvents;
+  int nSamples;
+  SampleBinningInfo* SampleBinning;
+  int TotalBins;
+  EventInfo* MCSamples;
+  double* SampleHandlerFD_array;
+  double* SampleHandlerFD_array_w2;
+  double* SampleHandlerFD_data;
+  int fTestStatistic;
+  int FirstTimeW2;   /* Samples/SampleHandlerFD.h: FirstTimeW2 = true initially */
+  int UpdateW2;      /* LikelihoodOptions:UpdateW2 (Samples/SampleHandlerFD.cpp:64) */
+  SMonolith* SplineHandler;
+} SampleHandlerFD;
+
+/* binning description: for each sample, nDim then per dim nbins; edges concatenated */
+M3O_API SampleHandlerFD* m3o_sample_create(unsigned int nEvents, int nSamples, const int* nDim,
+                                           const int* nbins /*[nSamples*M3O_MAX_DIM]*/,
+                                           const double* edges /*concatenated per sample per dim*/,
+                                           int test_statistic, int update_w2) {
+  SampleHandlerFD* s = (SampleHandlerFD*)calloc(1, sizeof(SampleHandlerFD));
+  s->nEvents = nEvents; s->nSamples = nSamples;
+  s->SampleBinning = (SampleBinningInfo*)calloc((size_t)nSamples, sizeof(SampleBinningInfo));
+  const double* ep = edges;
+  int GlobalOffsetCounter = 0;                         /* BinningHandler::SetGlobalBinNumbers (:341-355) */
+  for (int i = 0; i < nSamples; ++i) {
+    SampleBinningInfo* b = &s->SampleBinning[i];
+    b->nDim = nDim[i];
+    int stride = 1, tot = 1;
+    for (int d = 0; d < b->nDim; ++d) {
+      const int nb = nbins[i * M3O_MAX_DIM + d];
+      b->AxisNBins[d] = nb;
+      b->BinEdges[d] = (double*)malloc(sizeof(double) * (size_t)(nb + 1));
+      memcpy(b->BinEdges[d], ep, sizeof(double) * (size_t)(nb + 1));
+      ep += nb + 1;
+      b->BinLookup[d] = (BinShiftLookup*)malloc(sizeof(BinShiftLookup) * (size_t)nb);
+      InitialiseLookUpSingleDimension(b->BinLookup[d], b->BinEdges[d], nb);
+      b->Strides[d] = stride;                          /* InitialiseStrides (SampleStructs.h:656-664) */
+      stride *= nb; tot *= nb;
+    }
+    b->nBins = tot;
+    b->GlobalOffset = GlobalOffsetCounter;
+    GlobalOffsetCounter += tot;
+  }
+  s->TotalBins = GlobalOffsetCounter;
+  /* SampleHandlerFD::SetupReweightArrays (Samples/SampleHandlerFD.cpp:749-754) */
+  s->SampleHandlerFD_array = (double*)calloc((size_t)s->TotalBins, sizeof(double));
+  s->SampleHandlerFD_array_w2 = (double*)calloc((size_t)s->TotalBins, sizeof(double));
+  s->SampleHandlerFD_data = (double*)calloc((size_t)s->TotalBins, sizeof(double));
+  s->MCSamples = (EventInfo*)calloc((size_t)nEvents, sizeof(EventInfo));
+  s->fTestStatistic = test_statistic;
+  s->FirstTimeW2 = 1;
+  s->UpdateW2 = update_w2;
+  return s;
+}
+
+M3O_API void m3o_sample_destroy(SampleHandlerFD* s) {
+  if (!s) return;
+  for (unsigned int e = 0; e < s->nEvents; ++e) {
+    free(s->MCSamples[e].norm_pointers); free(s->MCSamples[e].total_weight_pointers);
+    free(s->MCSamples[e].KinVar); free(s->MCSamples[e].NomBin);
+  }
+  free(s->MCSamples);
+  for (int i = 0; i < s->nSamples; ++i)
+    for (int d = 0; d < s->SampleBinning[i].nDim; ++d) { free(s->SampleBinning[i].BinEdges[d]); free(s->SampleBinning[i].BinLookup[d]); }
+  free(s->SampleBinning);
+  free(s->SampleHandlerFD_array); free(s->SampleHandlerFD_array_w2); free(s->SampleHandlerFD_data);
+  free(s);
+}
+
+/* Wires the per-event pointer vectors the way SampleHandlerFD::Initialise does
+ * (Samples/SampleHandlerFD.cpp:169-202):
+ *   KinVar/NomBin    FindNominalBinAndEdges (:858-887)
+ *   norm_pointers    SetupNormParameters    (:637-663)   -> &norm_base[idx]
+ *   total_weight_pointers, in push order:
+ *       oscillation weight  SetupNuOscillatorPointers (:1108-1122) -> &osc_base[osc_idx or e]
+ *       spline weight       SetSplinePointers         (:1244-1249) -> SMonolith::retPointer(e)
+ *       extra weight        AddAdditionalWeightPointers (experiment) -> &static_w[e]
+ * kin is dim-major: kin[d*nEvents + e].  norm_idx holds n_norm_per_event entries per event,
+ * a negative entry = no pointer.  Any base may be NULL = that weight is absent. */
+M3O_API void m3o_sample_set_events(SampleHandlerFD* s, const int* sample_id, const double* kin,
+                                   int n_norm_per_event, const short* norm_idx, const double* norm_base,
+                                   const float* osc_base, const int* osc_idx,
+                                   SMonolith* spline, const float* static_w) {
+  s->SplineHandler = spline;
+  for (unsigned int e = 0; e < s->nEvents; ++e) {
+    EventInfo* ev = &s->MCSamples[e];
+    ev->NominalSample = sample_id[e];
+    const SampleBinningInfo* b = &s->SampleBinning[ev->NominalSample];
+    ev->n_dim = b->nDim;
+    ev->KinVar = (const double**)malloc(sizeof(double*) * (size_t)b->nDim);
+    ev->NomBin = (int*)malloc(sizeof(int) * (size_t)b->nDim);
+    for (int d = 0; d < b->nDim; ++d) {
+      ev->KinVar[d] = &kin[(size_t)d * s->nEvents + e];
+      const int bin = FindNominalBin(b, d, *ev->KinVar[d]);
+      ev->NomBin[d] = (bin >= 0 && bin < b->AxisNBins[d]) ? bin : UnderOverFlowBin;
+    }
+    int nn = 0;
+    for (int j = 0; j < n_norm_per_event; ++j) if (norm_base && norm_idx[(size_t)e * n_norm_per_event + j] >= 0) ++nn;
+    ev->n_norm = nn;
+    ev->norm_pointers = (const double**)malloc(sizeof(double*) * (size_t)(nn > 0 ? nn : 1));
+    nn = 0;
+    for (int j = 0; j < n_norm_per_event; ++j) {
+      if (!norm_base) break;
+      const short idx = norm_idx[(size_t)e * n_norm_per_event + j];
+      if (idx >= 0) ev->norm_pointers[nn++] = &norm_base[idx];
+    }
+    int nt = (osc_base ? 1 : 0) + (spline ? 1 : 0) + (static_w ? 1 : 0);
+    ev->n_tw = nt;
+    ev->total_weight_pointers = (const float**)malloc(sizeof(float*) * (size_t)(nt > 0 ? nt : 1));
+    nt = 0;
+    if (osc_base) ev->total_weight_pointers[nt++] = &osc_base[osc_idx ? (size_t)osc_idx[e] : (size_t)e];
+    if (spline)   ev->total_weight_pointers[nt++] = &spline->cpu_total_weights[e];
+    if (static_w) ev->total_weight_pointers[nt++] = &static_w[e];
+  }
+}
+
+/* SampleHandlerFD::CalcWeightTotal (Samples/SampleHandlerFD.cpp:568-594) */
+static inline float CalcWeightTotal(const EventInfo* restrict MCEvent) {
+  float TotalWeight = 1.0;
+  const int nNorms = MCEvent->n_norm;
+  #pragma omp simd reduction(*:TotalWeight)
+  for (int iParam = 0; iParam < nNorms; ++iParam) TotalWeight *= (float)(*(MCEvent->norm_pointers[iParam]));
+  const int TotalWeights = MCEvent->n_tw;
+  #pragma omp simd reduction(*:TotalWeight)
+  for (int iWeight = 0; iWeight < TotalWeights; ++iWeight) TotalWeight *= *(MCEvent->total_weight_pointers[iWeight]);
+  return TotalWeight;
+}
+
+/* BinningHandler::FindGlobalBin, uniform binning arm (Samples/BinningHandler.cpp:257-277) */
+static inline int FindGlobalBin(const SampleHandlerFD* s, const int NomSample, const double* const* KinVar, const int* NomBin, int Dim) {
+  const SampleBinningInfo* restrict Binning = &s->SampleBinning[NomSample];
+  int GlobalBin = 0;
+  for (int i = 0; i < Dim; ++i) {
+    const double Var = *KinVar[i];
+    const int Bin = FindBin(Var, NomBin[i], Binning->AxisNBins[i], Binning->BinEdges[i], Binning->BinLookup[i]);
+    if (Bin < 0) return UnderOverFlowBin;
+    GlobalBin += Bin * Binning->Strides[i];
+  }
+  GlobalBin += Binning->GlobalOffset;
+  return GlobalBin;
+}
+
+/* SampleHandlerFD::ResetHistograms (Samples/SampleHandlerFD.cpp:454-463) */
+static void ResetHistograms(SampleHandlerFD* s) {
+  for (int i = 0; i < s->TotalBins; ++i) s->SampleHandlerFD_array[i] = 0.0;
+  if (s->FirstTimeW2) for (int i = 0; i < s->TotalBins; ++i) s->SampleHandlerFD_array_w2[i] = 0.0;
+}
+
+/* SampleHandlerFD::FillArray_MP (Samples/SampleHandlerFD.cpp:390-448); no functional shifts,
+ * no selection cuts, no CalcWeightFunc (defaults, Samples/SampleHandlerFD.h:241,289) */
+static void FillArray_MP(SampleHandlerFD* s) {
+  const int TotalBins = s->TotalBins;
+  const unsigned int NumberOfEvents = s->nEvents;
+  double* MC_Array_for_reduction = s->SampleHandlerFD_array;
+  double* W2_array_for_reduction = s->SampleHandlerFD_array_w2;
+  const int FirstTimeW2 = s->FirstTimeW2;
+  #pragma omp parallel for reduction(+:MC_Array_for_reduction[:TotalBins], W2_array_for_reduction[:TotalBins])
+  for (unsigned int iEvent = 0; iEvent < NumberOfEvents; ++iEvent) {
+    const EventInfo* restrict MCEvent = &s->MCSamples[iEvent];
+    const float totalweight = CalcWeightTotal(MCEvent);
+    if (totalweight <= 0.) continue;                                                      /* :432 */
+    const int GlobalBin = FindGlobalBin(s, MCEvent->NominalSample, MCEvent->KinVar, MCEvent->NomBin, MCEvent->n_dim);
+    if (GlobalBin > UnderOverFlowBin) {                                                   /* :443 */
+      MC_Array_for_reduction[GlobalBin] += totalweight;
+      if (FirstTimeW2) W2_array_for_reduction[GlobalBin] += totalweight * totalweight;    /* float product, :445 */
+    }
+  }
+}
+
+/* SampleHandlerFD::Reweight (Samples/SampleHandlerFD.cpp:316-343).  The oscillator is an
+ * input array here (north_star), so Oscillator->Evaluate() is the caller's job. */
+M3O_API void m3o_reweight(SampleHandlerFD* s) {
+  ResetHistograms(s);
+  if (s->SplineHandler) m3o_evaluate(s->SplineHandler);
+  FillArray_MP(s);
+  if (!s->UpdateW2) s->FirstTimeW2 = 0;
+}
+/* FillArray part alone (spline weights already evaluated) -- for DragRace-style split timing */
+M3O_API void m3o_fill_only(SampleHandlerFD* s) {
+  ResetHistograms(s);
+  FillArray_MP(s);
+  if (!s->UpdateW2) s->FirstTimeW2 = 0;
+}
+
+/* SampleHandlerBase::GetPoissonLLH (Samples/SampleHandlerBase.cpp:17-31) */
+static double GetPoissonLLH(const double data, const double mc) {
+  if (data == 0) return mc;
+  if (mc < LOW_MC_BOUND) {
+    if (data > LOW_MC_BOUND) return (LOW_MC_BOUND - data + data * log(data / LOW_MC_BOUND));
+    else if (data >= mc) return 0.;
+  }
+  return (mc - data + data * log(data / mc));
+}
+
+/* SampleHandlerBase::GetTestStatLLH (Samples/SampleHandlerBase.cpp:35-192) */
+static double GetTestStatLLH(const int fTestStatistic, const double data, const double mc, const double w2) {
+  switch (fTestStatistic) {
+    case kBarlowBeeston: {                                                  /* :46-88 */
+      double newmc = mc;
+      if (mc < LOW_MC_BOUND) {
+        if (data > LOW_MC_BOUND) newmc = LOW_MC_BOUND;
+        else if (data >= mc) return 0.;
+      }
+      const double fractional = sqrt(w2) / newmc;
+      const double fractional2 = fractional * fractional;
+      const double temp = newmc * fractional2 - 1;
+      const double temp2 = temp * temp + 4 * data * fractional2;
+      if (temp2 < 0) return NAN;            /* the reference throws here (:65-68) */
+      const double beta = (-1 * temp + sqrt(temp2)) / 2.;
+      double stat = mc * beta;
+      if (data > 0) {
+        newmc *= beta;
+        stat = newmc - data + data * log(data / newmc);
+      }
+      double penalty = 0;
+      if (fractional > 0) penalty = (beta - 1) * (beta - 1) / (2 * fractional2);
+      return stat + penalty;
+    }
+    case kDembinskiAbdelmotteleb: {                                         /* :90-126 */
+      if (w2 == 0) return GetPoissonLLH(data, mc);
+      double newmc = mc;
+      if (mc < LOW_MC_BOUND) {
+        if (data > LOW_MC_BOUND) newmc = LOW_MC_BOUND;
+        else if (data >= mc) return 0.;
+      }
+      const double k = newmc * newmc / w2;
+      const double beta = (data + k) / (newmc + k);
+      newmc *= beta;
+      const double penalty = k * beta - k + k * log(k / (k * beta));
+      double stat = newmc;
+      if (data > 0) stat = newmc - data + data * log(data / newmc);
+      return stat + penalty;
+    }
+    case kIceCube: {                                                        /* :133-160 */
+      if (w2 == 0) return GetPoissonLLH(data, mc);
+      const long double b = mc / w2;
+      const long double a = mc * b + 1;
+      const double stat = (double)(-1 * (a * logl(b) + lgammal(data + a) - lgammal(data + 1) - ((data + a) * log1pl(b)) - lgammal(a)));
+      if (mc <= data) {
+        if (data <= LOW_MC_BOUND) return 0.;
+        const double poisson = GetPoissonLLH(data, LOW_MC_BOUND);
+        if (stat > poisson) return poisson;
+      }
+      return stat;
+    }
+    case kPearson: {                                                        /* :162-177 */
+      if (data == 0) return mc / 2.;
+      if (mc < LOW_MC_BOUND) {
+        if (data > LOW_MC_BOUND) return (data - LOW_MC_BOUND) * (data - LOW_MC_BOUND) / (2. * LOW_MC_BOUND);
+        else if (data >= mc) return 0.;
+      }
+      return (data - mc) * (data - mc) / (2 * mc);
+    }
+    case kPoisson:                                                          /* :178-184 */
+      return GetPoissonLLH(data, mc);
+    default:
+      return NAN;
+  }
+}
+M3O_API double m3o_test_stat_llh(int test_statistic, double data, double mc, double w2) {
+  return GetTestStatLLH(test_statistic, data, mc, w2);
+}
+
+/* SampleHandlerFD::GetLikelihood (Samples/SampleHandlerFD.cpp:1284-1300) */
+M3O_API double m3o_get_likelihood(const SampleHandlerFD* s) {
+  double negLogL = 0.;
+  #pragma omp parallel for reduction(+:negLogL)
+  for (int idx = 0; idx < s->TotalBins; ++idx)
+    negLogL += GetTestStatLLH(s->fTestStatistic, s->SampleHandlerFD_data[idx], s->SampleHandlerFD_array[idx], s->SampleHandlerFD_array_w2[idx]);
+  return negLogL;
+}
+/* SampleHandlerFD::GetSampleLikelihood (Samples/SampleHandlerFD.cpp:1262-1281) */
+M3O_API double m3o_get_sample_likelihood(const SampleHandlerFD* s, int isample) {
+  const int Start = s->SampleBinning[isample].GlobalOffset;
+  const int End = isample + 1 < s->nSamples ? s->SampleBinning[isample + 1].GlobalOffset : s->TotalBins;
+  double negLogL = 0.;
+  #pragma omp parallel for reduction(+:negLogL)
+  for (int idx = Start; idx < End; ++idx)
+    negLogL += GetTestStatLLH(s->fTestStatistic, s->SampleHandlerFD_data[idx], s->SampleHandlerFD_array[idx], s->SampleHandlerFD_array_w2[idx]);
+  return negLogL;
+}
+
+M3O_API int m3o_total_bins(const SampleHandlerFD* s) { return s->TotalBins; }
+M3O_API double* m3o_mc_array(SampleHandlerFD* s) { return s->SampleHandlerFD_array; }
+M3O_API double* m3o_w2_array(SampleHandlerFD* s) { return s->SampleHandlerFD_array_w2; }
+M3O_API double* m3o_data_array(SampleHandlerFD* s) { return s->SampleHandlerFD_data; }
+M3O_API void m3o_set_test_statistic(SampleHandlerFD* s, int t) { s->fTestStatistic = t; }
+M3O_API void m3o_set_first_time_w2(SampleHandlerFD* s, int v) { s->FirstTimeW2 = v; }
+/* SampleHandlerFD::AddData (Samples/SampleHandlerFD.cpp:955-1044), array form */
+M3O_API void m3o_add_data(SampleHandlerFD* s, const double* data) { memcpy(s->SampleHandlerFD_data, data, sizeof(double) * (size_t)s->TotalBins); }
+
+/* per-event views used by the bit-exact index parity tests */
+M3O_API void m3o_event_bins(const SampleHandlerFD* s, int* out) {
+  #pragma omp parallel for
+  for (unsigned int e = 0; e < s->nEvents; ++e) {
+    const EventInfo* ev = &s->MCSamples[e];
+    out[e] = FindGlobalBin(s, ev->NominalSample, ev->KinVar, ev->NomBin, ev->n_dim);
+  }
+}
+M3O_API void m3o_event_weights(const SampleHandlerFD* s, float* out) {
+  #pragma omp parallel for
+  for (unsigned int e = 0; e < s->nEvents; ++e) out[e] = CalcWeightTotal(&s->MCSamples[e]);
+}
+/* single-value bin lookup for the FindBin known-answer tests */
+M3O_API int m3o_find_bin(const SampleHandlerFD* s, int sample, int dim, double var, int nom_bin) {
+  const SampleBinningInfo* b = &s->SampleBinning[sample];
+  return FindBin(var, nom_bin, b->AxisNBins[dim], b->BinEdges[dim], b->BinLookup[dim]);
+}
+M3O_API int m3o_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ============================================================================================
+ * BinnedSplineHandler::CalcSplineWeights (Splines/BinnedSplineHandler.cpp:306-341), in the
+ * reference's default build (M3::float_t = double).  xvar is read un-narrowed through the
+ * parameter pointer (:327), x is stored per spline (:329), negative weights clamp to 0 (:337).
+ * ========================================================================================== */
+M3O_API void m3o_binned_calc_spline_weights(int64_t n_unique, const int* uniquecoeffindices,
+                                            const short* uniquesplinevec_Monolith, const short* SplineSegments,
+                                            const int* coeffindexvec, const double* manycoeff_arr,
+                                            const double* xcoeff_arr, const double* const* splineParsPointer,
+                                            double* weightvec_Monolith) {
+  #pragma omp parallel for simd
+  for (int64_t iCoeff = 0; iCoeff < n_unique; ++iCoeff) {
+    const int iSpline = uniquecoeffindices[iCoeff];
+    const short uniqueIndex = (short)uniquesplinevec_Monolith[iSpline];
+    const short currentsegment = (short)SplineSegments[uniqueIndex];
+    const int segCoeff = coeffindexvec[iSpline] + currentsegment;
+    const int coeffOffset = segCoeff * nCoeff;
+    const double y = manycoeff_arr[coeffOffset + 0];
+    const double b = manycoeff_arr[coeffOffset + 1];
+    const double c = manycoeff_arr[coeffOffset + 2];
+    const double d = manycoeff_arr[coeffOffset + 3];
+    const double xvar = *splineParsPointer[uniqueIndex];
+    const double dx = xvar - xcoeff_arr[segCoeff];
+    double weight = fma(dx, fma(dx, fma(dx, d, c), b), y);
+    if (weight < 0) weight = 0.;
+    weightvec_Monolith[iSpline] = weight;
+  }
+}
