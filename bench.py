@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- one reweight + fill + likelihood step of the MaCh3 hot path on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched through torchrun)
+    python bench.py --impl reference ...                      (the reference's CPU path, host cores)
+
+Workload (BASELINE.json): N=1 -> configs[1] "T2K-FD-like" 1M events x (40 TSpline3 K=7 + 10 TF1),
+60x15 bins, Poisson.  N>1 -> configs[2] "DUNE-FD-scale" 20M events x (48+12), 4 samples x 80x20 bins,
+events sharded contiguously over the ranks, partial histograms exchanged every step.
+Synthetic data (mach3_b200.synth), fresh proposal every step so the active spline segments change.
+
+Prints ONE JSON line (rank 0).  `value` = events/s with all inputs resident in HBM (only the
+<2 KB per-step parameter table crosses PCIe); `e2e` = the same through the C ABI with the
+oscillation-weight array copied from host memory inside every step and the -lnL read back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CHUNK = 131072          # events generated / uploaded per chunk (multiple of every tile size)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--events", type=int, default=0, help="override the total event count (debug)")
+    ap.add_argument("--exchange", default=os.environ.get("M3B_EXCHANGE", "nccl"), choices=["nccl", "peer"])
+    ap.add_argument("--tile", type=int, default=int(os.environ.get("M3B_TILE", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-events", type=int, default=200_000)
+    return ap.parse_args()
+
+
+def pick_workload(args):
+    from mach3_b200 import synth
+    name = args.workload
+    if name == "auto":
+        name = "cfg2" if args.gpus == 1 else "cfg3"
+    w = {"cfg1": synth.CFG1, "cfg2": synth.CFG2, "cfg3": synth.CFG3}[name]
+    if args.events:
+        w = w.scaled(args.events, name=w.name + f" [events overridden to {args.events}]")
+    return w
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.index)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's restatement of the reference's MULTITHREAD CPU path
+# (the reference itself cannot be built here: ROOT/yaml-cpp/spdlog are absent)
+# ---------------------------------------------------------------------------------------------
+def cpu_path(w, n_sample, steps, warmup, budget_s=None):
+    """Times SampleHandlerFD::Reweight (FindSplineSegment + CalcSplineWeights + CalcTotalEventWeight
+    + FillArray_MP) + GetLikelihood on a bounded sample of workload `w`, DragRace style
+    (Fitters/FitterBase.cpp:461-520).  Returns (events/s, ms/step, laps, cores, llh)."""
+    from mach3_b200 import synth
+    from oracle import binding as O          # the checker, here as the timed CPU baseline
+    O.set_multithread(True)
+    ws = w.scaled(min(n_sample, w.n_events))
+    mono, sh, d = O.build_from_workload(ws)
+    sp, nm = synth.proposal(ws, -1)
+    mono.set_params(sp); sh.norm_vals[:] = nm
+    sh.Reweight()
+    sh.AddData(np.random.default_rng(ws.seed).poisson(sh.mc).astype(np.float64))
+    for k in range(max(warmup, 1)):
+        sp, nm = synth.proposal(ws, k)
+        mono.set_params(sp); sh.norm_vals[:] = nm
+        sh.Reweight(); llh = sh.GetLikelihood()
+    t_all, laps = 0.0, 0
+    for k in range(steps):
+        sp, nm = synth.proposal(ws, warmup + k)
+        mono.set_params(sp); sh.norm_vals[:] = nm
+        t0 = time.perf_counter()
+        sh.Reweight()
+        llh = sh.GetLikelihood()
+        t_all += time.perf_counter() - t0
+        laps += 1
+        if budget_s is not None and t_all > budget_s and laps >= 3:
+            break
+    ms = 1e3 * t_all / laps
+    return ws.n_events / (ms * 1e-3), ms, laps, O.num_threads(), llh, ws
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mach3_b200 import build
+    build.build_synth(); build.build_oracle()
+    w = pick_workload(args)
+    evs, ms, laps, cores, llh, ws = cpu_path(w, args.cpu_sample_events, args.steps, min(args.warmup, 3), budget_s=120.0)
+    sample = (f"{ws.n_events} events of the {w.n_events}-event workload, {laps} timed steps, OpenMP {cores} threads, "
+              "oracle port of the reference's MULTITHREAD CPU path (flags -O3 -fopenmp -flto, no -march)")
+    line = {"impl": "reference", "metric": "reweighted events/s per MCMC step (reweight+fill+LLH)", "value": evs,
+            "unit": "events/s", "n_gpus": args.gpus, "steps": laps, "warmup": min(args.warmup, 3), "ms_per_step": ms,
+            "llh_evals_per_s": 1e3 / ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
+            "config": {"workload": w.name, "sample": sample},
+            "cpu_baseline": {"value": evs, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": evs, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+class _DevArray:
+    """torch view of a raw device pointer (plumbing for the NCCL all-reduce)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def main_b200(args):
+    import torch
+    from mach3_b200 import lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = pick_workload(args)
+    E = w.n_events
+    # contiguous, tile-aligned event shards
+    per = ((E + world - 1) // world + 511) // 512 * 512
+    e0, e1 = min(E, rank * per), min(E, (rank + 1) * per)
+    n_local = e1 - e0
+
+    flags = lib.FLAG_NO_FUSED_LLH if world > 1 else 0
+    h = lib.Handle(device=local, test_statistic=w.test_statistic, update_w2=False, tile_events=args.tile, flags=flags)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    t_setup = time.perf_counter()
+    typ, npts, cx = synth.param_layout(w)
+    h.splines_begin(w.n_params, w.n_knots, cx, npts, n_local)
+    for c0 in range(e0, e1, CHUNK):
+        h.splines_append(synth.make_splines(w, c0, min(e1, c0 + CHUNK)))
+    h.splines_end()
+    h.upload_binning(synth.bin_edges(w))
+    ev = synth.make_events(w, e0, e1)
+    h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0,
+                    ev["static_w"])
+    del ev
+    n_osc_bufs = 4
+    osc_bufs = [synth.make_osc(w, k, e0, e1) for k in range(n_osc_bufs)]
+    for b in osc_bufs:
+        h.register_host_buffer(b)          # the caller's persistent osc array: pinned once
+    h.upload_osc(osc_bufs[0])
+    t_setup = time.perf_counter() - t_setup
+
+    hist_t = None
+    if world > 1:
+        if args.exchange == "peer":
+            mine = h.peer_export(rank, world)
+            allh = [None] * world
+            dist.all_gather_object(allh, mine)
+            for r in range(world):
+                h.peer_import(r, allh[r])
+        ptr, nb, _ = h.hist_device_ptr()
+        hist_t = torch.as_tensor(_DevArray(ptr, 2 * nb), device=f"cuda:{local}")
+
+    def step(k, osc=None):
+        sp, nm = props[k]
+        if world == 1:
+            h.step(sp, nm, osc)
+        elif args.exchange == "peer":
+            h.step(sp, nm, osc, mode="peer")
+        else:
+            h.step(sp, nm, osc, mode="fill")
+            _, nb, live = h.hist_device_ptr()
+            dist.all_reduce(hist_t[: (2 * nb if live else nb)])
+            h.llh_from_hist()
+
+    W, K = args.warmup, args.steps
+    props = {k: synth.proposal(w, k) for k in range(-1, 2 * (W + K) + 16)}
+
+    # Asimov data at nominal, Poisson-fluctuated with a seed every rank shares
+    step(-1); h.llh()
+    mc, _ = h.read_hist()
+    data = np.random.default_rng(w.seed).poisson(mc).astype(np.float64)
+    h.upload_data(data)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM --------------------------------------------
+    for k in range(W):
+        step(k)
+    llh_w = h.llh()
+    clocks = ClockSampler(local)
+    clocks.start()
+    h.set_timing(True)
+    h.kernel_time()
+    launches0 = h.info().kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for k in range(W, W + K):
+        step(k)
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    kern_ms, kern_n = h.kernel_time()
+    h.set_timing(False)
+    launches = h.info().kernel_launches - launches0
+    llh_last = h.llh()
+
+    # ---------------- e2e: host buffers in, scalar out, every step -----------------------------
+    for k in range(min(W, 5)):
+        step(W + K + k, osc_bufs[k % n_osc_bufs]); h.llh()
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    t_host = time.perf_counter()
+    for k in range(K):
+        step(W + K + 5 + k, osc_bufs[k % n_osc_bufs])
+        llh_e2e = h.llh()
+    ev3.record(stream)
+    barrier()
+    t_host = time.perf_counter() - t_host
+    ms_e2e = max(ev2.elapsed_time(ev3), 1e3 * t_host)
+    clk = clocks.stop()
+
+    info = h.info()
+    if dist is not None:
+        t = torch.tensor([ms_total, ms_e2e, kern_ms / max(kern_n, 1)], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e, kern_avg = t.tolist()
+    else:
+        kern_avg = kern_ms / max(kern_n, 1)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ms_step = ms_total / K
+        alg_bytes_local = n_local * w.bytes_per_event        # SURVEY §8d per-event figure x events of one launch
+        achieved = alg_bytes_local / (kern_avg * 1e-3) / 1e9
+        step_bytes = 12 * w.n_params + 4 * w.n_norm_params
+        line = {
+            "metric": "reweighted events/s per MCMC step (reweight+fill+LLH)",
+            "value": E / (ms_step * 1e-3), "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "llh_evals_per_s": 1e3 / ms_step, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
+            "config": {"workload": w.name, "events": E, "events_per_gpu": n_local, "responses_per_event": w.n_params,
+                       "bins": w.n_bins, "tile_events": info.tile_events, "grid_blocks": info.grid_blocks,
+                       "smem_bytes": info.smem_bytes, "exchange": ("none" if world == 1 else args.exchange),
+                       "l2": "inputs larger than L2: %.0f MB of coefficient rows stream per step per GPU, fresh "
+                             "proposal (different segments) every step" % (info.active_bytes_per_step / 1e6),
+                       "device_bytes": info.device_bytes, "setup_s": round(t_setup, 2)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs_nominal": achieved / 8000.0,
+                         "kernel": "m3b::fill_kernel", "kernel_ms": kern_avg, "algorithmic_bytes_per_launch": alg_bytes_local,
+                         "loaded_bytes_per_launch": info.active_bytes_per_step, "traffic": None},
+            "e2e": {"value": E / (ms_e2e / K * 1e-3), "unit": "events/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": int(4 * n_local + step_bytes), "d2h_bytes_per_step": int(8 * (1 + w.n_samples)),
+                    "api": "m3b_step(host pars, host norms, host osc weights) + m3b_llh()"},
+            "gpu_launches": int(launches), "clocks": clk,
+            "llh": {"last_value_step": llh_last, "last_e2e_step": llh_e2e, "after_warmup": llh_w},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            evs, ms, laps, cores, _, ws = cpu_path(w, args.cpu_sample_events, 100, 2, budget_s=15.0)
+            line["cpu_baseline"] = {"value": evs, "unit": "events/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+                                    "sample": f"{ws.n_events} events of the same workload, {laps} DragRace laps of "
+                                              f"Reweight+GetLikelihood, OpenMP {cores} threads"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    h.close()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

@@ -195,6 +195,11 @@ typedef struct {
   uint64_t steps, kernel_launches;
 } m3b_info;
 M3B_API int m3b_get_info(m3b_handle* h, m3b_info* out);
+/* CUDA-event timing of the fill kernel alone, on the handle's stream (the reference has only a
+ * TStopwatch around the whole step, Fitters/MCMCBase.cpp:93).  m3b_kernel_time synchronises and
+ * returns the summed duration and the number of launches timed since the last call.              */
+M3B_API int m3b_set_timing(m3b_handle* h, int32_t enabled);
+M3B_API int m3b_kernel_time(m3b_handle* h, double* total_ms, int64_t* n_launches);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,11 @@ struct m3b_handle {
   std::vector<void*> registered;
 
   uint64_t steps = 0, launches = 0;
+
+  // ---- optional kernel timing
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;   // pairs
+  size_t tev_used = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -200,6 +205,7 @@ M3B_API void m3b_destroy(m3b_handle* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : h->registered) cudaHostUnregister(p);
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   for (int i = 0; i < m3b_handle::kRing; ++i) {
     if (h->h_step[i]) cudaFreeHost(h->h_step[i]);
     if (h->step_ev[i]) cudaEventDestroy(h->step_ev[i]);
@@ -781,7 +787,14 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     a.peer_world = h->peer_world; a.peer_rank = h->peer_rank; a.peer_epoch = h->peer_epoch;
     for (int r = 0; r < h->peer_world; ++r) { a.peer_inbox[r] = h->peer_inbox[par][r]; a.peer_flag[r] = h->peer_flag[par][r]; }
   }
+  if (h->timing) {
+    if (h->tev_used + 2 > h->tev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->tev.push_back(e); }
+    }
+    CK(cudaEventRecord(h->tev[h->tev_used], h->stream));
+  }
   CK(launch_fill(a, h->grid, h->smem, h->stream));
+  if (h->timing) { CK(cudaEventRecord(h->tev[h->tev_used + 1], h->stream)); h->tev_used += 2; }
   ++h->launches;
   if (mode == kPeer) {
     const int par = h->peer_epoch & 1;
@@ -956,6 +969,28 @@ M3B_API int m3b_peer_import(m3b_handle* h, int32_t peer_rank, const void* ipc_ha
   h->peer_inbox[0][peer_rank] = base; h->peer_inbox[1][peer_rank] = base + inbox_d;
   h->peer_flag[0][peer_rank] = reinterpret_cast<unsigned int*>(base + 2 * inbox_d);
   h->peer_flag[1][peer_rank] = h->peer_flag[0][peer_rank] + 8;
+  return M3B_OK;
+}
+
+M3B_API int m3b_set_timing(m3b_handle* h, int32_t enabled) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  h->timing = enabled != 0;
+  return M3B_OK;
+}
+
+M3B_API int m3b_kernel_time(m3b_handle* h, double* total_ms, int64_t* n_launches) {
+  REQUIRE(h && total_ms && n_launches, M3B_ERR_INVALID, "m3b_kernel_time: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  double tot = 0;
+  for (size_t i = 0; i + 1 < h->tev_used; i += 2) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *n_launches = static_cast<int64_t>(h->tev_used / 2);
+  h->tev_used = 0;
   return M3B_OK;
 }
 

@@ -25,7 +25,7 @@ EXPORTS = (
     "m3b_step", "m3b_step_segments", "m3b_llh", "m3b_find_segments", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
     "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
-    "m3b_get_info",
+    "m3b_get_info", "m3b_set_timing", "m3b_kernel_time",
 )
 
 
@@ -245,6 +245,15 @@ class Handle:
     def peer_import(self, peer_rank, handle_bytes):
         buf = (C.c_ubyte * 64).from_buffer_copy(handle_bytes)
         self._ck(self.L.m3b_peer_import(self.h, C.c_int32(peer_rank), buf))
+
+    def set_timing(self, on=True):
+        self._ck(self.L.m3b_set_timing(self.h, C.c_int32(int(on))))
+
+    def kernel_time(self):
+        """-> (summed fill-kernel ms, launches) since the last call; synchronises."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        self._ck(self.L.m3b_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def info(self) -> Info:
         i = Info()

@@ -26,6 +26,7 @@ class _Cfg(C.Structure):
         ("n_knots", C.c_int32), ("n_modes", C.c_int32), ("density", C.c_float), ("n_samples", C.c_int32),
         ("n_dims", C.c_int32), ("nbins_x", C.c_int32), ("nbins_y", C.c_int32), ("n_norm_params", C.c_int32),
         ("n_norm_per_event", C.c_int32), ("sample_start", C.c_int64 * (MAX_SAMPLES + 1)),
+        ("mode_block", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -66,6 +67,7 @@ class Workload:
     n_norm_params: int = 5
     n_norm_per_event: int = 2
     test_statistic: int = 0     # kPoisson
+    mode_block: int = 1         # events come in runs of this many sharing one interaction mode
 
     @property
     def n_params(self):
@@ -101,6 +103,7 @@ class Workload:
         c.n_samples, c.n_dims = self.n_samples, self.n_dims
         c.nbins_x, c.nbins_y = self.nbins_x, self.nbins_y
         c.n_norm_params, c.n_norm_per_event = self.n_norm_params, self.n_norm_per_event
+        c.mode_block = self.mode_block
         acc = 0.0
         for s in range(self.n_samples):
             c.sample_start[s] = int(round(acc * self.n_events))
@@ -123,6 +126,13 @@ CFG5 = Workload("cfg5: 5M ev x (48 TSpline3 K=7 + 12 TF1), 900 bins, 256 proposa
 SPARSE = Workload("sparse: 40k ev, 24 params (20+4), 6 modes, density 0.6, 3 samples", 777, 40_000, 20, 4, 6,
                   sample_fracs=(0.5, 0.3, 0.2), n_dims=2, nbins_x=20, nbins_y=8, n_modes=6, density=0.6,
                   test_statistic=1)
+
+
+# the same, with events grouped in runs of one mode (as after sorting by interaction mode):
+# tiles then carry different parameter signatures, and runs do not align with tile boundaries
+SPARSE_RUNS = Workload("sparse-runs: 40k ev, 24 params, 6 modes in runs of 700, density 0.5, 3 samples", 778, 40_000,
+                       20, 4, 6, sample_fracs=(0.5, 0.3, 0.2), n_dims=2, nbins_x=20, nbins_y=8, n_modes=6,
+                       density=0.5, test_statistic=1, mode_block=700)
 
 
 def param_layout(w: Workload):

@@ -38,7 +38,8 @@ static inline int param_is_linear(const m3s_config* c, int p) {
   return ((int64_t)(p + 1) * L / P) > ((int64_t)p * L / P);
 }
 static inline int event_mode(const m3s_config* c, int64_t e) {
-  return c->n_modes <= 1 ? 0 : (int)(h4(c->seed, TAG_MODE, (uint64_t)e, 0) % (uint64_t)c->n_modes);
+  const int64_t blk = c->mode_block > 1 ? c->mode_block : 1;
+  return c->n_modes <= 1 ? 0 : (int)(h4(c->seed, TAG_MODE, (uint64_t)(e / blk), 0) % (uint64_t)c->n_modes);
 }
 static inline int has_response(const m3s_config* c, int p, int mode) {
   if (c->density >= 1.0f) return 1;

@@ -34,6 +34,8 @@ typedef struct {
   int32_t  n_norm_params;     /* normalisation parameters                                   */
   int32_t  n_norm_per_event;  /* each event is bound to this many of them                   */
   int64_t  sample_start[M3S_MAX_SAMPLES + 1]; /* event index where each sample starts       */
+  int32_t  mode_block;        /* events come in runs of this many sharing one mode (>=1)    */
+  int32_t  reserved;
 } m3s_config;
 
 /* per-parameter layout: type[p] (0 = TSpline3, 1 = TF1), n_pts[p], coeff_x[p*K+j]          */

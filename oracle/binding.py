@@ -208,6 +208,12 @@ def test_stat_llh(test_statistic, data, mc, w2):
     return lib().m3o_test_stat_llh(int(test_statistic), float(data), float(mc), float(w2))
 
 
+def set_multithread(on: bool):
+    """True: the reference's MULTITHREAD build (OpenMP, reassociating simd reductions);
+    False: its serial build (strict left-to-right float products, FillArray)."""
+    lib().m3o_set_multithread(C.c_int(int(on)))
+
+
 def num_threads():
     return lib().m3o_num_threads()
 

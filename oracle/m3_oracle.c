@@ -34,6 +34,14 @@
 
 #define M3O_API __attribute__((visibility("default")))
 
+/* The reference has two builds of this path: MULTITHREAD (OpenMP pragmas; `omp simd
+ * reduction(*)` lets the compiler reassociate the per-event products) and the serial build
+ * (no pragmas; strictly left-to-right products, SampleHandlerFD::FillArray instead of
+ * FillArray_MP).  Both are restated; tests use the serial one where bit-exact weights matter. */
+static int g_multithread = 1;
+M3O_API void m3o_set_multithread(int on) { g_multithread = on; }
+M3O_API int m3o_get_multithread(void) { return g_multithread; }
+
 /* Manager/Core.h:83,91 */
 static const double LOW_MC_BOUND = .00001;
 enum { UnderOverFlowBin = -1 };
@@ -173,8 +181,30 @@ M3O_API void m3o_find_spline_segment(SMonolith* m) {
   }
 }
 
-/* SMonolith::CalcSplineWeights (Splines/SplineMonolith.cpp:727-788) */
+/* SMonolith::CalcSplineWeights (Splines/SplineMonolith.cpp:727-788), serial build */
+static void calc_spline_weights_serial(SMonolith* m) {
+  for (uint64_t splineNum = 0; splineNum < m->NSplines_valid; ++splineNum) {
+    const short Param = m->paramNo_arr[splineNum];
+    const short segment = m->SplineSegments[Param];
+    const short segment_X = (short)(Param * m->_max_knots + segment);
+    const uint64_t CurrentKnotPos = m->nKnots_arr[splineNum] * nCoeff + (uint64_t)(segment * nCoeff);
+    const float fY = m->coeff_many[CurrentKnotPos];
+    const float fB = m->coeff_many[CurrentKnotPos + 1];
+    const float fC = m->coeff_many[CurrentKnotPos + 2];
+    const float fD = m->coeff_many[CurrentKnotPos + 3];
+    const float dx = m->ParamValues[Param] - m->coeff_x[segment_X];
+    m->cpu_weights_spline_var[splineNum] = fmaf(dx, fmaf(dx, fmaf(dx, fD, fC), fB), fY);
+  }
+  for (uint64_t tf1Num = 0; tf1Num < m->NTF1_valid; ++tf1Num) {
+    const float x = m->ParamValues[m->cpu_paramNo_TF1_arr[tf1Num]];
+    const uint64_t TF1_Index = tf1Num * nTF1Coeff;
+    m->cpu_weights_tf1_var[tf1Num] = fmaf(m->cpu_coeff_TF1_many[TF1_Index], x, m->cpu_coeff_TF1_many[TF1_Index + 1]);
+  }
+}
+
+/* SMonolith::CalcSplineWeights (Splines/SplineMonolith.cpp:727-788), MULTITHREAD build */
 M3O_API void m3o_calc_spline_weights(SMonolith* m) {
+  if (!g_multithread) { calc_spline_weights_serial(m); return; }
   #pragma omp parallel
   {
     #pragma omp for simd nowait
@@ -201,8 +231,23 @@ M3O_API void m3o_calc_spline_weights(SMonolith* m) {
   }
 }
 
-/* SMonolith::CalcTotalEventWeight (Splines/SplineMonolith.cpp:792-830) */
+/* SMonolith::CalcTotalEventWeight (Splines/SplineMonolith.cpp:792-830), serial build */
+static void calc_total_event_weight_serial(SMonolith* m) {
+  for (unsigned int EventNum = 0; EventNum < m->NEvents; ++EventNum) {
+    float totalWeight = 1.0f;
+    const uint64_t startIndex = m->start_c[EventNum];
+    const unsigned int numParams = m->cpu_nParamPerEvent[2 * EventNum];
+    for (unsigned int id = 0; id < numParams; ++id) totalWeight *= m->cpu_weights_spline_var[startIndex + id];
+    const uint64_t startIndex_tf1 = m->start_l[EventNum];
+    const unsigned int numParams_tf1 = m->cpu_nParamPerEvent_tf1[2 * EventNum];
+    for (unsigned int id = 0; id < numParams_tf1; ++id) totalWeight *= m->cpu_weights_tf1_var[startIndex_tf1 + id];
+    m->cpu_total_weights[EventNum] = totalWeight;
+  }
+}
+
+/* SMonolith::CalcTotalEventWeight (Splines/SplineMonolith.cpp:792-830), MULTITHREAD build */
 M3O_API void m3o_calc_total_event_weight(SMonolith* m) {
+  if (!g_multithread) { calc_total_event_weight_serial(m); return; }
   #pragma omp parallel for
   for (unsigned int EventNum = 0; EventNum < m->NEvents; ++EventNum) {
     float totalWeight = 1.0f;
@@ -446,6 +491,14 @@ static inline float CalcWeightTotal(const EventInfo* restrict MCEvent) {
   return TotalWeight;
 }
 
+/* SampleHandlerFD::CalcWeightTotal, serial build (no omp simd) */
+static float CalcWeightTotal_serial(const EventInfo* restrict MCEvent) {
+  float TotalWeight = 1.0;
+  for (int iParam = 0; iParam < MCEvent->n_norm; ++iParam) TotalWeight *= (float)(*(MCEvent->norm_pointers[iParam]));
+  for (int iWeight = 0; iWeight < MCEvent->n_tw; ++iWeight) TotalWeight *= *(MCEvent->total_weight_pointers[iWeight]);
+  return TotalWeight;
+}
+
 /* BinningHandler::FindGlobalBin, uniform binning arm (Samples/BinningHandler.cpp:257-277) */
 static inline int FindGlobalBin(const SampleHandlerFD* s, const int NomSample, const double* const* KinVar, const int* NomBin, int Dim) {
   const SampleBinningInfo* restrict Binning = &s->SampleBinning[NomSample];
@@ -487,18 +540,32 @@ static void FillArray_MP(SampleHandlerFD* s) {
   }
 }
 
+/* SampleHandlerFD::FillArray (Samples/SampleHandlerFD.cpp:352-383), the serial build's fill */
+static void FillArray(SampleHandlerFD* s) {
+  for (unsigned int iEvent = 0; iEvent < s->nEvents; iEvent++) {
+    const EventInfo* restrict MCEvent = &s->MCSamples[iEvent];
+    const float totalweight = CalcWeightTotal_serial(MCEvent);
+    if (totalweight <= 0.) continue;
+    const int GlobalBin = FindGlobalBin(s, MCEvent->NominalSample, MCEvent->KinVar, MCEvent->NomBin, MCEvent->n_dim);
+    if (GlobalBin > UnderOverFlowBin) {
+      s->SampleHandlerFD_array[GlobalBin] += totalweight;
+      if (s->FirstTimeW2) s->SampleHandlerFD_array_w2[GlobalBin] += totalweight * totalweight;
+    }
+  }
+}
+
 /* SampleHandlerFD::Reweight (Samples/SampleHandlerFD.cpp:316-343).  The oscillator is an
  * input array here (north_star), so Oscillator->Evaluate() is the caller's job. */
 M3O_API void m3o_reweight(SampleHandlerFD* s) {
   ResetHistograms(s);
   if (s->SplineHandler) m3o_evaluate(s->SplineHandler);
-  FillArray_MP(s);
+  if (g_multithread) FillArray_MP(s); else FillArray(s);
   if (!s->UpdateW2) s->FirstTimeW2 = 0;
 }
 /* FillArray part alone (spline weights already evaluated) -- for DragRace-style split timing */
 M3O_API void m3o_fill_only(SampleHandlerFD* s) {
   ResetHistograms(s);
-  FillArray_MP(s);
+  if (g_multithread) FillArray_MP(s); else FillArray(s);
   if (!s->UpdateW2) s->FirstTimeW2 = 0;
 }
 
@@ -619,7 +686,8 @@ M3O_API void m3o_event_bins(const SampleHandlerFD* s, int* out) {
 }
 M3O_API void m3o_event_weights(const SampleHandlerFD* s, float* out) {
   #pragma omp parallel for
-  for (unsigned int e = 0; e < s->nEvents; ++e) out[e] = CalcWeightTotal(&s->MCSamples[e]);
+  for (unsigned int e = 0; e < s->nEvents; ++e)
+    out[e] = g_multithread ? CalcWeightTotal(&s->MCSamples[e]) : CalcWeightTotal_serial(&s->MCSamples[e]);
 }
 /* single-value bin lookup for the FindBin known-answer tests */
 M3O_API int m3o_find_bin(const SampleHandlerFD* s, int sample, int dim, double var, int nom_bin) {
