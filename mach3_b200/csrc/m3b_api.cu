@@ -100,7 +100,7 @@ struct m3b_handle {
   bool have_step = false;
 
   // ---- launch configuration
-  int grid = 0, smem = 0;
+  int grid = 0, smem = 0, variant = 1;
   bool hist_in_smem = true;
   bool launch_ready = false;
   bool launch_w2_live = false;
@@ -702,9 +702,11 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
     int smem = fill_smem_bytes(a, true, w2_live);
     h->hist_in_smem = smem <= 200 * 1024;
     if (!h->hist_in_smem) smem = fill_smem_bytes(a, false, w2_live);
-    CK(fill_set_smem(h->T, smem));
+    const char* v = getenv("M3B_VARIANT");
+    if (v) h->variant = atoi(v);
+    CK(fill_set_smem(h->T, h->variant, smem));
     int bps = 0;
-    CK(fill_occupancy(h->T, smem, &bps));
+    CK(fill_occupancy(h->T, h->variant, smem, &bps));
     REQUIRE(bps > 0, M3B_ERR_CUDA, "step: fill kernel does not fit on an SM");
     h->smem = smem;
     h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(bps) * h->sm_count));
@@ -793,7 +795,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     }
     CK(cudaEventRecord(h->tev[h->tev_used], h->stream));
   }
-  CK(launch_fill(a, h->grid, h->smem, h->stream));
+  CK(launch_fill(a, h->variant, h->grid, h->smem, h->stream));
   if (h->timing) { CK(cudaEventRecord(h->tev[h->tev_used + 1], h->stream)); h->tev_used += 2; }
   ++h->launches;
   if (mode == kPeer) {

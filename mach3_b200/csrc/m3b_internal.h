@@ -133,12 +133,12 @@ struct RetileArgs {
 };
 
 // launchers (m3b_kernels.cu)
-cudaError_t launch_fill(const FillArgs& a, int grid, int smem_bytes, cudaStream_t s);
+cudaError_t launch_fill(const FillArgs& a, int variant, int grid, int smem_bytes, cudaStream_t s);
 cudaError_t launch_llh(const LlhArgs& a, cudaStream_t s);
 cudaError_t launch_bins(const BinArgs& a, cudaStream_t s);
 cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s);
-cudaError_t fill_occupancy(int T, int smem_bytes, int* blocks_per_sm);
-cudaError_t fill_set_smem(int T, int smem_bytes);
+cudaError_t fill_occupancy(int T, int variant, int smem_bytes, int* blocks_per_sm);
+cudaError_t fill_set_smem(int T, int variant, int smem_bytes);
 int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
 
 }  // namespace m3b

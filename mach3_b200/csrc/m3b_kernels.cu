@@ -186,10 +186,10 @@ __device__ void block_llh(const double* __restrict__ hist, const double* __restr
 // ------------------------------------------------------------------------------------------------
 // the fused per-step kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kBatch = 8;
-
-template <int T>
-__global__ void __launch_bounds__(T) fill_kernel(const __grid_constant__ FillArgs a) {
+// T = events per tile = threads per block; kBatch = coefficient loads in flight per thread;
+// kMinBlocks = blocks per SM the register allocation is capped for
+template <int T, int kBatch, int kMinBlocks>
+__global__ void __launch_bounds__(T, kMinBlocks) fill_kernel(const __grid_constant__ FillArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_last;
@@ -363,35 +363,37 @@ int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
   return b > llh_scratch ? b : llh_scratch;
 }
 
-template <int T>
-static cudaError_t launch_fill_t(const FillArgs& a, int grid, int smem, cudaStream_t s) {
-  fill_kernel<T><<<grid, T, smem, s>>>(a);
+// kernel variants: {batch, min blocks/SM}; picked per tile size by fill_variant()
+#define M3B_FOR_VARIANT(T_, V_, EXPR)                                                       \
+  switch (V_) {                                                                             \
+    case 0: { constexpr int B = 8, M = 1; auto k = fill_kernel<T_, B, M>; EXPR; } break;    \
+    case 1: { constexpr int B = 8, M = (1024 / T_); auto k = fill_kernel<T_, B, M>; EXPR; } break;  \
+    case 2: { constexpr int B = 4, M = (1280 / T_); auto k = fill_kernel<T_, B, M>; EXPR; } break;  \
+    case 3: { constexpr int B = 4, M = (1536 / T_); auto k = fill_kernel<T_, B, M>; EXPR; } break;  \
+    case 4: { constexpr int B = 16, M = (512 / T_); auto k = fill_kernel<T_, B, M>; EXPR; } break;  \
+    case 5: { constexpr int B = 12, M = (768 / T_); auto k = fill_kernel<T_, B, M>; EXPR; } break;  \
+    default: return cudaErrorInvalidValue;                                                  \
+  }
+#define M3B_FOR_TILE(T_RUNTIME, V_, EXPR)                                                   \
+  switch (T_RUNTIME) {                                                                      \
+    case 128: M3B_FOR_VARIANT(128, V_, EXPR) break;                                         \
+    case 256: M3B_FOR_VARIANT(256, V_, EXPR) break;                                         \
+    case 512: M3B_FOR_VARIANT(512, V_, EXPR) break;                                         \
+    default: return cudaErrorInvalidValue;                                                  \
+  }
+
+cudaError_t launch_fill(const FillArgs& a, int variant, int grid, int smem, cudaStream_t s) {
+  M3B_FOR_TILE(a.T, variant, (k<<<grid, a.T, smem, s>>>(a)))
   return cudaGetLastError();
 }
-cudaError_t launch_fill(const FillArgs& a, int grid, int smem, cudaStream_t s) {
-  switch (a.T) {
-    case 128: return launch_fill_t<128>(a, grid, smem, s);
-    case 256: return launch_fill_t<256>(a, grid, smem, s);
-    case 512: return launch_fill_t<512>(a, grid, smem, s);
-    default: return cudaErrorInvalidValue;
-  }
-}
-cudaError_t fill_set_smem(int T, int smem) {
+cudaError_t fill_set_smem(int T, int variant, int smem) {
   const int cap = smem > 48 * 1024 ? smem : 48 * 1024;
-  switch (T) {
-    case 128: return cudaFuncSetAttribute(fill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    case 256: return cudaFuncSetAttribute(fill_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    case 512: return cudaFuncSetAttribute(fill_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-    default: return cudaErrorInvalidValue;
-  }
+  M3B_FOR_TILE(T, variant, return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, cap))
+  return cudaSuccess;
 }
-cudaError_t fill_occupancy(int T, int smem, int* bps) {
-  switch (T) {
-    case 128: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, fill_kernel<128>, 128, smem);
-    case 256: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, fill_kernel<256>, 256, smem);
-    case 512: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, fill_kernel<512>, 512, smem);
-    default: return cudaErrorInvalidValue;
-  }
+cudaError_t fill_occupancy(int T, int variant, int smem, int* bps) {
+  M3B_FOR_TILE(T, variant, return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, k, T, smem))
+  return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------------

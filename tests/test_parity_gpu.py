@@ -94,7 +94,7 @@ def test_cfg1_shape_parity(tile):
     # Asimov: the device LLH of the device histogram against its own copy is exactly zero
     gsh.AddData(gsh.GetMCArray())
     gsh.Reweight()
-    assert gsh.GetLikelihood() == 0.0
+    assert abs(gsh.GetLikelihood()) < 1e-10
     gsh.AddData(asimov)
     for step in range(6):
         _set(w, step, mono, osh, gsh, gd, osc_step=step)
@@ -250,7 +250,8 @@ def test_full_size_cfg2_properties():
     asimov = gsh.GetMCArray()
     gsh.AddData(asimov)
     gsh.Reweight()
-    assert gsh.GetLikelihood() == 0.0                     # Asimov: exactly zero
+    # Asimov: zero up to the f64 rounding of a differently-ordered atomic histogram sum
+    assert abs(gsh.GetLikelihood()) < 1e-9
     # histogram total == sum of positive in-range event weights, computed independently in numpy
     osc = gd["osc"].astype(np.float64)
     assert asimov.sum() > 0 and np.isfinite(asimov).all()
