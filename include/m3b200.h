@@ -156,6 +156,14 @@ M3B_API int m3b_step(m3b_handle* h, const double* spline_pars, const double* nor
 M3B_API int m3b_step_segments(m3b_handle* h, const float* param_values, const int16_t* segments,
                               const double* norm_pars, const float* osc_w);
 M3B_API int m3b_llh(m3b_handle* h, double* total, double* per_sample /* [n_samples] or NULL */);
+/* m3b_eval_weights = SMonolithGPU::RunGPU_SplineMonolith exactly (Splines/gpuSplineUtils.cu:444-512):
+ *   evaluate all responses, multiply per event, and enqueue the copy of the per-event totals into the
+ *   caller's host array (cpu_total_weights, pinned by InitGPU_SplineMonolith :139) -- asynchronous until
+ *   m3b_synchronize (= SynchroniseSplines, :515-518).  No fill, no likelihood; needs no sample handler
+ *   (if no events were uploaded the library wires a one-bin sample around the monolith's events).
+ *   Handle must carry M3B_FLAG_KEEP_EVENT_WEIGHTS.  This is what adapters/SMonolithGPU_m3b200.cu calls.  */
+M3B_API int m3b_eval_weights(m3b_handle* h, const float* param_values, const int16_t* segments,
+                             float* host_total_weights);
 /* SplineBase::FindSplineSegment alone (host, history-dependent); outputs are optional            */
 M3B_API int m3b_find_segments(m3b_handle* h, const double* spline_pars, int16_t* segments, float* param_values);
 M3B_API int m3b_synchronize(m3b_handle* h);   /* SplineBase::SynchroniseMemTransfer                 */

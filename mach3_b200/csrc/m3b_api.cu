@@ -100,7 +100,11 @@ struct m3b_handle {
   bool have_step = false;
 
   // ---- launch configuration
-  int grid = 0, smem = 0, variant = 1;
+  int grid = 0, smem = 0, variant = 1;   // LDG kernel variant (m3b_kernels.cu), used when use_tma is false
+  bool use_tma = true;                   // streaming TMA kernel (m3b_fill_tma.cu), the default
+  int tma_G = 8, tma_stages = 0;
+  TmaSmem tma{};
+  unsigned int* d_tile_counter = nullptr;
   bool hist_in_smem = true;
   bool launch_ready = false;
   bool launch_w2_live = false;
@@ -191,6 +195,8 @@ M3B_API int m3b_create(const m3b_config* cfg, m3b_handle** out) {
   h->own_stream = true;
   CK(dev_alloc(h, &h->d_ticket, 1));
   CK(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
+  CK(dev_alloc(h, &h->d_tile_counter, 1));
+  CK(cudaMemset(h->d_tile_counter, 0, sizeof(unsigned int)));
   CK(dev_alloc(h, &h->d_status, 1));
   CK(cudaMemset(h->d_status, 0, sizeof(int32_t)));
   for (int i = 0; i < m3b_handle::kRing; ++i) CK(cudaEventCreateWithFlags(&h->step_ev[i], cudaEventDisableTiming));
@@ -699,19 +705,56 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
   if (!h->launch_ready || h->launch_w2_live != w2_live) {
     FillArgs a{};
     a.step = h->step; a.max_nc = h->max_nc; a.max_nl = h->max_nl; a.n_bins = h->n_bins; a.n_samples = h->n_samples;
-    int smem = fill_smem_bytes(a, true, w2_live);
-    h->hist_in_smem = smem <= 200 * 1024;
-    if (!h->hist_in_smem) smem = fill_smem_bytes(a, false, w2_live);
+    // kernel choice: M3B_VARIANT=tma (default) | 0..5 (LDG register-streaming variants, m3b_kernels.cu)
     const char* v = getenv("M3B_VARIANT");
-    if (v) h->variant = atoi(v);
-    CK(fill_set_smem(h->T, h->variant, smem));
-    int bps = 0;
-    CK(fill_occupancy(h->T, h->variant, smem, &bps));
-    REQUIRE(bps > 0, M3B_ERR_CUDA, "step: fill kernel does not fit on an SM");
-    h->smem = smem;
-    h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(bps) * h->sm_count));
-    const char* g = getenv("M3B_GRID_BLOCKS_PER_SM");
-    if (g && atoi(g) > 0) h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(std::min(atoi(g), bps)) * h->sm_count));
+    h->use_tma = true;
+    if (v && v[0] >= '0' && v[0] <= '9') { h->use_tma = false; h->variant = atoi(v); }
+    const int llh_scratch = h->n_samples * 32 * 8;
+    if (h->use_tma) {
+      // ring of G-row stages in whatever shared memory the fixed tables (and the privatised
+      // histogram, if it fits next to >= 3 stages) leave of the 227 KB opt-in limit
+      const char* ge = getenv("M3B_TMA_G");
+      h->tma_G = ge ? atoi(ge) : (h->T == 512 ? 4 : 8);
+      const char* be = getenv("M3B_TMA_BLOCKS_PER_SM");
+      const int want_bps = be && atoi(be) > 1 ? atoi(be) : 1;
+      const int budget = (232448 - 1024 * want_bps) / want_bps - 1024;     // static barriers + per-block reserve
+      auto stages_for = [&](bool hist) {
+        const TmaSmem L0 = tma_smem_layout(h->step, h->max_nc, h->max_nl, h->n_bins, hist, w2_live, h->T, h->tma_G, 0);
+        return std::min(32, (budget - L0.off_ring) / L0.stage_bytes);
+      };
+      h->hist_in_smem = true;
+      int ns = stages_for(true);
+      if (ns < 3) { h->hist_in_smem = false; ns = stages_for(false); }
+      const char* se = getenv("M3B_TMA_STAGES");
+      if (se && atoi(se) > 0) ns = std::min(ns, atoi(se));
+      if (ns < 2) h->use_tma = false;          // tables alone overflow shared memory: register-streaming kernel
+      else {
+        h->tma_stages = ns;
+        h->tma = tma_smem_layout(h->step, h->max_nc, h->max_nl, h->n_bins, h->hist_in_smem, w2_live, h->T, h->tma_G, ns);
+        int smem = std::max(h->tma.total, llh_scratch);
+        cudaError_t e = fill_tma_set_smem(h->T, h->tma_G, smem);
+        if (e == cudaErrorInvalidValue) return fail(h, M3B_ERR_INVALID, "step: unsupported M3B_TMA_G for this tile size");
+        CK(e);
+        int bps = 0;
+        CK(fill_tma_occupancy(h->T, h->tma_G, smem, &bps));
+        REQUIRE(bps > 0, M3B_ERR_CUDA, "step: TMA fill kernel does not fit on an SM");
+        h->smem = smem;
+        h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(std::min(bps, want_bps)) * h->sm_count));
+      }
+    }
+    if (!h->use_tma) {
+      int smem = fill_smem_bytes(a, true, w2_live);
+      h->hist_in_smem = smem <= 200 * 1024;
+      if (!h->hist_in_smem) smem = fill_smem_bytes(a, false, w2_live);
+      CK(fill_set_smem(h->T, h->variant, smem));
+      int bps = 0;
+      CK(fill_occupancy(h->T, h->variant, smem, &bps));
+      REQUIRE(bps > 0, M3B_ERR_CUDA, "step: fill kernel does not fit on an SM");
+      h->smem = smem;
+      h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(bps) * h->sm_count));
+      const char* g = getenv("M3B_GRID_BLOCKS_PER_SM");
+      if (g && atoi(g) > 0) h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(std::min(atoi(g), bps)) * h->sm_count));
+    }
     h->launch_ready = true;
     h->launch_w2_live = w2_live;
   }
@@ -756,10 +799,12 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   const int nxt = mode == kFused ? (h->cur ^ 1) : h->cur;
   double* mc = h->d_hw[nxt];
   double* w2 = h->d_hw[nxt] + h->n_bins;
-  if (!h->mc_zero[nxt]) CK(cudaMemsetAsync(mc, 0, sizeof(double) * h->n_bins, h->stream));
-  if (w2_live && !h->w2_zero[nxt]) CK(cudaMemsetAsync(w2, 0, sizeof(double) * h->n_bins, h->stream));
-  h->mc_zero[nxt] = false;
-  if (w2_live) { h->w2_zero[nxt] = false; h->d_w2_frozen = w2; }
+  if (mode != kWeightsOnly) {
+    if (!h->mc_zero[nxt]) CK(cudaMemsetAsync(mc, 0, sizeof(double) * h->n_bins, h->stream));
+    if (w2_live && !h->w2_zero[nxt]) CK(cudaMemsetAsync(w2, 0, sizeof(double) * h->n_bins, h->stream));
+    h->mc_zero[nxt] = false;
+    if (w2_live) { h->w2_zero[nxt] = false; h->d_w2_frozen = w2; }
+  }
 
   FillArgs a{};
   a.tiles = h->d_tiles; a.sigs = h->d_sigs; a.sig_pool = h->d_sig_pool;
@@ -770,8 +815,11 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   a.hist = mc; a.w2 = w2_live ? w2 : nullptr;
   a.n_bins = h->n_bins; a.hist_in_smem = h->hist_in_smem ? 1 : 0;
   a.fuse_llh = (mode == kFused) ? 1 : 0;
+  a.weights_only = (mode == kWeightsOnly) ? 1 : 0;
   a.test_stat = h->test_stat; a.n_samples = h->n_samples;
   a.data = h->d_data; a.w2_frozen = h->d_w2_frozen; a.sample_start = h->d_sample_start;
+  a.tile_begin = 0;
+  if (h->use_tma) { a.tile_counter = h->d_tile_counter; a.n_stages = h->tma_stages; a.tma = h->tma; }
   a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->h_llh_dev;
   a.evt_spline_w = h->d_evt_spline_w; a.evt_total_w = h->d_evt_total_w;
   if (mode == kFused) {
@@ -795,7 +843,8 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     }
     CK(cudaEventRecord(h->tev[h->tev_used], h->stream));
   }
-  CK(launch_fill(a, h->variant, h->grid, h->smem, h->stream));
+  if (h->use_tma) CK(launch_fill_tma(a, h->tma_G, h->grid, h->smem, h->stream));
+  else CK(launch_fill(a, h->variant, h->grid, h->smem, h->stream));
   if (h->timing) { CK(cudaEventRecord(h->tev[h->tev_used + 1], h->stream)); h->tev_used += 2; }
   ++h->launches;
   if (mode == kPeer) {
@@ -810,10 +859,11 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     CK(launch_llh(l, h->stream));
     ++h->launches;
   }
+  h->evt_weights_valid = h->d_evt_spline_w != nullptr;
+  if (mode == kWeightsOnly) return M3B_OK;             // histograms, W2 state and step count untouched
   h->cur = nxt;
   h->last_w2_live = w2_live;
   if (!h->cfg.update_w2) h->first_time_w2 = false;     // Samples/SampleHandlerFD.cpp:342
-  h->evt_weights_valid = h->d_evt_spline_w != nullptr;
   ++h->steps;
   return M3B_OK;
 }
@@ -842,6 +892,53 @@ M3B_API int m3b_step_segments(m3b_handle* h, const float* param_values, const in
   }
   return enqueue_step(h, h->param_values.data(), h->segments.data(), norm_pars, osc_w,
                       (h->cfg.flags & M3B_FLAG_NO_FUSED_LLH) ? kFillOnly : kFused);
+}
+
+// SMonolithGPU::RunGPU_SplineMonolith (Splines/gpuSplineUtils.cu:444-512): evaluate every response,
+// multiply per event, copy the per-event totals to the caller's (pinned) host array -- asynchronously;
+// SynchroniseSplines() = m3b_synchronize.  Works without a sample handler: if no events were uploaded
+// the library wires a trivial one-bin sample around the monolith's events.
+static int ensure_standalone_events(m3b_handle* h) {
+  if (h->n_events > 0) return M3B_OK;
+  REQUIRE(h->splines_done, M3B_ERR_STATE, "m3b_eval_weights: upload the spline monolith first");
+  if (h->n_samples == 0) {
+    const int32_t nd = 1, nb[kMaxDim] = {1, 0, 0, 0};
+    const double ed[2] = {0., 1.};
+    int rc = m3b_upload_binning(h, 1, &nd, nb, ed);
+    if (rc != M3B_OK) return rc;
+  }
+  CK(cudaSetDevice(h->device));
+  const int T = h->T;
+  h->n_events = h->n_events_total;
+  h->n_tiles = (h->n_events + T - 1) / T;
+  h->e_pad = h->n_tiles * T;
+  CK(dev_alloc(h, &h->d_bin, static_cast<size_t>(h->e_pad)));
+  CK(cudaMemset(h->d_bin, 0xFF, sizeof(int32_t) * h->e_pad));       // bin -1: nothing is ever filled
+  if (!h->d_evt_spline_w) {
+    CK(dev_alloc(h, &h->d_evt_spline_w, static_cast<size_t>(h->e_pad)));
+    CK(dev_alloc(h, &h->d_evt_total_w, static_cast<size_t>(h->e_pad)));
+  }
+  h->launch_ready = false;
+  return M3B_OK;
+}
+
+M3B_API int m3b_eval_weights(m3b_handle* h, const float* param_values, const int16_t* segments,
+                             float* host_total_weights) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->P > 0 && param_values && segments, M3B_ERR_INVALID, "m3b_eval_weights: null argument / no monolith");
+  int rc = ensure_standalone_events(h);
+  if (rc != M3B_OK) return rc;
+  REQUIRE(h->d_evt_spline_w, M3B_ERR_STATE, "m3b_eval_weights: create the handle with M3B_FLAG_KEEP_EVENT_WEIGHTS");
+  for (int p = 0; p < h->P; ++p) {
+    REQUIRE(segments[p] >= 0 && segments[p] < std::max<int>(1, h->nseg[p]), M3B_ERR_INVALID, "m3b_eval_weights: segment out of range");
+    h->segments[p] = segments[p]; h->curr_segment[p] = segments[p]; h->param_values[p] = param_values[p];
+  }
+  std::vector<double> ones(static_cast<size_t>(std::max(h->n_norm_values, 1)), 1.0);
+  rc = enqueue_step(h, h->param_values.data(), h->segments.data(), ones.data(), nullptr, kWeightsOnly);
+  if (rc != M3B_OK) return rc;
+  if (host_total_weights)
+    CK(cudaMemcpyAsync(host_total_weights, h->d_evt_spline_w, sizeof(float) * h->n_events, cudaMemcpyDeviceToHost, h->stream));
+  return M3B_OK;
 }
 
 M3B_API int m3b_step_fill(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w) {

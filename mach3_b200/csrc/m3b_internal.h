@@ -45,12 +45,19 @@ inline StepLayout make_step_layout(int P, int Nn) {
   return L;
 }
 
+// Shared-memory map of the TMA fill kernel (m3b_fill_tma.cu); computed on the host, passed by value.
+//   [step table][dx[max_nc]][lv[max_nl]][row[max_nc]][stage descriptors][hist (+w2)][ring: n_stages x stage_bytes]
+struct TmaSmem {
+  int32_t off_dx, off_lv, off_row, off_desc, off_hist, off_ring, stage_bytes, total;
+};
+
 struct FillArgs {
-  // tiles
+  // tiles: this launch covers [tile_begin, n_tiles)
   const TileDesc* tiles;
   const SigDesc* sigs;
   const int32_t* sig_pool;
-  int32_t n_tiles, T, max_nc, max_nl;
+  int32_t tile_begin, n_tiles, T, max_nc, max_nl;
+  TmaSmem tma;
   // per-step table
   const unsigned char* step_table;
   StepLayout step;
@@ -68,12 +75,15 @@ struct FillArgs {
   double* hist_next;           // zeroed by the last block for the next step (nullptr = caller memsets)
   double* w2_next;
   int32_t n_bins, hist_in_smem;
+  int32_t weights_only;        // 1: stop after the per-event weights (no fill, no likelihood)
   // fused likelihood (last block)
   int32_t fuse_llh, test_stat, n_samples;
   const double* data;
   const double* w2_frozen;     // w2 histogram to use in the LLH (== w2 when live)
   const int32_t* sample_start; // [n_samples+1] global bin offsets
   unsigned int* ticket;
+  unsigned int* tile_counter;  // dynamic tile scheduler of the TMA kernel (nullptr: static interleave)
+  int32_t n_stages;            // TMA kernel: stages of the shared-memory coefficient ring
   double* llh_dev;             // [1+n_samples]
   double* llh_host;            // mapped pinned mirror (nullptr = none)
   // optional per-event outputs
@@ -139,6 +149,12 @@ cudaError_t launch_bins(const BinArgs& a, cudaStream_t s);
 cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s);
 cudaError_t fill_occupancy(int T, int variant, int smem_bytes, int* blocks_per_sm);
 cudaError_t fill_set_smem(int T, int variant, int smem_bytes);
+// TMA streaming kernel (m3b_fill_tma.cu): G = coefficient rows per shared-memory stage
+TmaSmem tma_smem_layout(const StepLayout& step, int max_nc, int max_nl, int n_bins, bool hist_in_smem, bool w2_live,
+                        int T, int G, int n_stages);
+cudaError_t launch_fill_tma(const FillArgs& a, int G, int grid, int smem_bytes, cudaStream_t s);
+cudaError_t fill_tma_set_smem(int T, int G, int smem_bytes);
+cudaError_t fill_tma_occupancy(int T, int G, int smem_bytes, int* blocks_per_sm);
 int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
 
 }  // namespace m3b

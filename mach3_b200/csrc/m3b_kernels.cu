@@ -14,174 +14,9 @@
 //   retile_*      AoS reference monolith -> tiled SoA device layout (setup time)
 //
 // No tensor cores: the path is a bandwidth-bound gather/evaluate/scatter.
-#include "m3b_internal.h"
-#include <cuda_runtime.h>
-#include <math.h>
+#include "m3b_device.cuh"
 
 namespace m3b {
-
-// ------------------------------------------------------------------------------------------------
-// small PTX helpers: mbarrier + 1-D bulk (TMA) global->shared copy, streaming vector loads
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-// coefficient rows are read once per step: keep them out of L1, default L2 policy (small
-// workloads stay L2-resident between steps, large ones stream)
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float2 ldg_stream(const float2* p) {
-  float2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-}
-
-// ------------------------------------------------------------------------------------------------
-// test statistics, SampleHandlerBase::GetTestStatLLH (Samples/SampleHandlerBase.cpp:35-192), f64
-// ------------------------------------------------------------------------------------------------
-constexpr double kLowMcBound = .00001;   // M3::_LOW_MC_BOUND_ (Manager/Core.h:83)
-
-__device__ __forceinline__ double poisson_llh(double data, double mc) {      // :17-31
-  if (data == 0) return mc;
-  if (mc < kLowMcBound) {
-    if (data > kLowMcBound) return (kLowMcBound - data + data * log(data / kLowMcBound));
-    else if (data >= mc) return 0.;
-  }
-  return (mc - data + data * log(data / mc));
-}
-
-__device__ double test_stat_llh(int ts, double data, double mc, double w2) {
-  switch (ts) {
-    case 1: {   // kBarlowBeeston :46-88
-      double newmc = mc;
-      if (mc < kLowMcBound) {
-        if (data > kLowMcBound) newmc = kLowMcBound;
-        else if (data >= mc) return 0.;
-      }
-      const double fractional = sqrt(w2) / newmc;
-      const double fractional2 = fractional * fractional;
-      const double temp = newmc * fractional2 - 1;
-      const double temp2 = temp * temp + 4 * data * fractional2;
-      if (temp2 < 0) return nan("");          // the reference throws here
-      const double beta = (-1 * temp + sqrt(temp2)) / 2.;
-      double stat = mc * beta;
-      if (data > 0) {
-        newmc *= beta;
-        stat = newmc - data + data * log(data / newmc);
-      }
-      double penalty = 0;
-      if (fractional > 0) penalty = (beta - 1) * (beta - 1) / (2 * fractional2);
-      return stat + penalty;
-    }
-    case 4: {   // kDembinskiAbdelmotteleb :90-126
-      if (w2 == 0) return poisson_llh(data, mc);
-      double newmc = mc;
-      if (mc < kLowMcBound) {
-        if (data > kLowMcBound) newmc = kLowMcBound;
-        else if (data >= mc) return 0.;
-      }
-      const double k = newmc * newmc / w2;
-      const double beta = (data + k) / (newmc + k);
-      newmc *= beta;
-      const double penalty = k * beta - k + k * log(k / (k * beta));
-      double stat = newmc;
-      if (data > 0) stat = newmc - data + data * log(data / newmc);
-      return stat + penalty;
-    }
-    case 2: {   // kIceCube :133-160 (the reference evaluates in long double; f64 here)
-      if (w2 == 0) return poisson_llh(data, mc);
-      const double b = mc / w2;
-      const double a = mc * b + 1;
-      const double stat = -1 * (a * log(b) + lgamma(data + a) - lgamma(data + 1) - ((data + a) * log1p(b)) - lgamma(a));
-      if (mc <= data) {
-        if (data <= kLowMcBound) return 0.;
-        const double poisson = poisson_llh(data, kLowMcBound);
-        if (stat > poisson) return poisson;
-      }
-      return stat;
-    }
-    case 3: {   // kPearson :162-177
-      if (data == 0) return mc / 2.;
-      if (mc < kLowMcBound) {
-        if (data > kLowMcBound) return (data - kLowMcBound) * (data - kLowMcBound) / (2. * kLowMcBound);
-        else if (data >= mc) return 0.;
-      }
-      return (data - mc) * (data - mc) / (2 * mc);
-    }
-    default:    // kPoisson :178-184
-      return poisson_llh(data, mc);
-  }
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-  #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// Block-level likelihood.  For every sample all threads stride over the sample's bins
-// [start,end), then shuffle-tree per warp; thread s finally adds the warps' partial sums of
-// sample s in warp order and thread 0 adds the samples in sample order.  The summation shape
-// is fixed, so the result is a deterministic function of the histogram.
-// scratch: n_samples * 32 doubles of shared memory.
-constexpr int kMaxSamples = 64;
-
-__device__ void block_llh(const double* __restrict__ hist, const double* __restrict__ w2,
-                          const double* __restrict__ data, const int32_t* __restrict__ sample_start,
-                          int n_samples, int ts, double* llh_dev, double* llh_host, double* scratch) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int s = 0; s < n_samples; ++s) {
-    const int b0 = sample_start[s], b1 = sample_start[s + 1];
-    double acc = 0.;
-    for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x)
-      acc += test_stat_llh(ts, data[b], __ldcg(hist + b), w2 ? __ldcg(w2 + b) : 0.);
-    acc = warp_sum(acc);
-    if (lane == 0) scratch[s * 32 + warp] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < n_samples) {
-    double tot = 0.;
-    for (int w = 0; w < nwarps; ++w) tot += scratch[threadIdx.x * 32 + w];
-    scratch[threadIdx.x * 32] = tot;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot = 0.;
-    for (int s = 0; s < n_samples; ++s) {
-      const double v = scratch[s * 32];
-      tot += v;
-      llh_dev[1 + s] = v;
-      if (llh_host) llh_host[1 + s] = v;
-    }
-    llh_dev[0] = tot;
-    if (llh_host) { llh_host[0] = tot; __threadfence_system(); }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // the fused per-step kernel
@@ -212,7 +47,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) fill_kernel(const __grid_consta
     mbar_expect_tx(&bar, static_cast<uint32_t>(a.step.bytes));
     bulk_g2s(st, a.step_table, static_cast<uint32_t>(a.step.bytes), &bar);
   }
-  if (smem_hist) {
+  if (smem_hist && !a.weights_only) {
     for (int i = tid; i < a.n_bins; i += T) s_hist[i] = 0.;
     if (w2_live) for (int i = tid; i < a.n_bins; i += T) s_w2[i] = 0.;
   }
@@ -225,7 +60,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) fill_kernel(const __grid_consta
   const float* norm = reinterpret_cast<const float*>(st + a.step.off_norm);
 
   int cur_sig = -1, nc = 0, nl = 0;
-  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+  for (int t = a.tile_begin + blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const TileDesc td = a.tiles[t];
     if (td.sig != cur_sig) {            // block-uniform
       __syncthreads();
@@ -294,7 +129,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) fill_kernel(const __grid_consta
     if (a.evt_spline_w && e < a.n_events) { a.evt_spline_w[e] = w_spl; a.evt_total_w[e] = w; }
 
     // FillArray_MP: skip w<=0 and under/overflow; mc += w; w2 += w*w (float product)
-    if (w > 0.f && bin >= 0) {
+    if (w > 0.f && bin >= 0 && !a.weights_only) {
       if (smem_hist) {
         atomicAdd(s_hist + bin, static_cast<double>(w));
         if (w2_live) atomicAdd(s_w2 + bin, static_cast<double>(w * w));
@@ -305,55 +140,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) fill_kernel(const __grid_consta
     }
   }
 
-  // block -> grid: flush the privatised histogram
-  if (smem_hist) {
-    __syncthreads();
-    for (int i = tid; i < a.n_bins; i += T) {
-      const double v = s_hist[i];
-      if (v != 0.) atomicAdd(a.hist + i, v);
-    }
-    if (w2_live)
-      for (int i = tid; i < a.n_bins; i += T) {
-        const double v = s_w2[i];
-        if (v != 0.) atomicAdd(a.w2 + i, v);
-      }
-  }
-  if (!a.fuse_llh && a.peer_world == 0) return;
-
-  // last-block-done ticket
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int tk = atomicAdd(a.ticket, 1u);
-    s_last = (tk == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-
-  if (a.peer_world > 0) {
-    // push the finished partial histogram into every rank's inbox over NVLink peer memory
-    const int nb2 = a.n_bins * (w2_live ? 2 : 1);
-    for (int r = 0; r < a.peer_world; ++r) {
-      double* dst = a.peer_inbox[r] + static_cast<int64_t>(a.peer_rank) * 2 * a.n_bins;
-      for (int i = tid; i < nb2; i += T) dst[i] = __ldcg((i < a.n_bins ? a.hist : a.w2 - a.n_bins) + i);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < a.peer_world) {
-      unsigned int* f = a.peer_flag[tid] + a.peer_rank;
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.peer_epoch) : "memory");
-    }
-    if (tid == 0) *a.ticket = 0u;
-    return;
-  }
-
-  block_llh(a.hist, a.w2_frozen, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host,
-            reinterpret_cast<double*>(smem));
-  // prepare the next step: zero its histogram(s), re-arm the ticket
-  if (a.hist_next) for (int i = tid; i < a.n_bins; i += T) a.hist_next[i] = 0.;
-  if (a.w2_next) for (int i = tid; i < a.n_bins; i += T) a.w2_next[i] = 0.;
-  if (tid == 0) *a.ticket = 0u;
+  finish_block(a, s_hist, s_w2, reinterpret_cast<double*>(smem), &s_last);
 }
 
 int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {

@@ -22,7 +22,7 @@ EXPORTS = (
     "m3b_splines_begin", "m3b_splines_append", "m3b_splines_end", "m3b_upload_spline_monolith",
     "m3b_upload_binning", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer",
     "m3b_set_test_statistic", "m3b_reset_w2",
-    "m3b_step", "m3b_step_segments", "m3b_llh", "m3b_find_segments", "m3b_synchronize",
+    "m3b_step", "m3b_step_segments", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
     "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
     "m3b_get_info", "m3b_set_timing", "m3b_kernel_time",
@@ -195,6 +195,15 @@ class Handle:
         pv, sg, nm = _c(param_values, np.float32), _c(segments, np.int16), _c(norm_pars, np.float64)
         self._keep = (pv, sg, nm, osc_w)
         self._ck(self.L.m3b_step_segments(self.h, _p(pv), _p(sg), _p(nm), _p(osc_w)))
+
+    def eval_weights(self, param_values, segments, host_out):
+        """SMonolithGPU::RunGPU_SplineMonolith: asynchronous; host_out valid after synchronize()."""
+        pv, sg = _c(param_values, np.float32), _c(segments, np.int16)
+        assert host_out.dtype == np.float32 and host_out.flags.c_contiguous
+        self._keep = (pv, sg, host_out)
+        self._ck(self.L.m3b_eval_weights(self.h, _p(pv), _p(sg), _p(host_out)))
+        if self.n_events == 0:
+            self.n_events = host_out.size
 
     def llh(self, per_sample=False):
         tot = C.c_double(0)
