@@ -184,6 +184,7 @@ def main_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    numa = lib.bind_to_gpu_cpus(local)     # pinned host buffers (osc weights, -lnL mirror) land on the GPU's socket
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -193,7 +194,7 @@ def main_b200(args):
     w = pick_workload(args)
     E = w.n_events
     # contiguous, tile-aligned event shards
-    per = ((E + world - 1) // world + 511) // 512 * 512
+    per = ((E + world - 1) // world + 1023) // 1024 * 1024
     e0, e1 = min(E, rank * per), min(E, (rank + 1) * per)
     n_local = e1 - e0
 
@@ -325,7 +326,7 @@ def main_b200(args):
                        "smem_bytes": info.smem_bytes, "exchange": ("none" if world == 1 else args.exchange),
                        "l2": "inputs larger than L2: %.0f MB of coefficient rows stream per step per GPU, fresh "
                              "proposal (different segments) every step" % (info.active_bytes_per_step / 1e6),
-                       "device_bytes": info.device_bytes, "setup_s": round(t_setup, 2)},
+                       "device_bytes": info.device_bytes, "setup_s": round(t_setup, 2), "host_cpu_affinity": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs_nominal": achieved / 8000.0,
@@ -333,7 +334,8 @@ def main_b200(args):
                          "loaded_bytes_per_launch": info.active_bytes_per_step, "traffic": None},
             "e2e": {"value": E / (ms_e2e / K * 1e-3), "unit": "events/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(4 * n_local + step_bytes), "d2h_bytes_per_step": int(8 * (1 + w.n_samples)),
-                    "api": "m3b_step(host pars, host norms, host osc weights) + m3b_llh()"},
+                    "api": "m3b_step(host pars, host norms, host osc weights in pinned memory) + m3b_llh(); the osc weights "
+                           "are streamed over PCIe by the fill kernel's own bulk copies (no separate H2D pass)"},
             "gpu_launches": int(launches), "clocks": clk,
             "llh": {"last_value_step": llh_last, "last_e2e_step": llh_e2e, "after_warmup": llh_w},
         }

@@ -66,7 +66,7 @@ typedef struct {
   int32_t device;          /* CUDA ordinal                                                          */
   int32_t test_statistic;  /* m3b_test_statistic; LikelihoodOptions:TestStatistic (Manager.cpp:98-127)*/
   int32_t update_w2;       /* LikelihoodOptions:UpdateW2 (Samples/SampleHandlerFD.cpp:64)            */
-  int32_t tile_events;     /* events per tile = threads per block: 0 (=256), 128, 256, 512           */
+  int32_t tile_events;     /* events per tile row of the device layout: 0 (=1024), 128, 256, 512, 1024 */
   int32_t flags;           /* M3B_FLAG_*                                                            */
   int32_t reserved[11];
 } m3b_config;
@@ -208,6 +208,10 @@ M3B_API int m3b_get_info(m3b_handle* h, m3b_info* out);
  * returns the summed duration and the number of launches timed since the last call.              */
 M3B_API int m3b_set_timing(m3b_handle* h, int32_t enabled);
 M3B_API int m3b_kernel_time(m3b_handle* h, double* total_ms, int64_t* n_launches);
+/* per-block timeline of the fill kernel (globaltimer ns; 8 u64 per block: start, tables staged, first
+ * stage consumed, producer out of work, consumers done, histogram flushed, block end, units done).
+ * Call once with out == NULL to switch tracing on, then after a step with out = u64[grid*8].       */
+M3B_API int m3b_block_trace(m3b_handle* h, uint64_t* out, int32_t* grid);
 
 #ifdef __cplusplus
 }

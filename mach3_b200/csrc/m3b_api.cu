@@ -91,6 +91,7 @@ struct m3b_handle {
 
   // ---- per-step staging
   StepLayout step{};
+  int step_sigs = -1;
   static constexpr int kRing = 4;
   unsigned char* h_step[kRing] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t step_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
@@ -102,9 +103,13 @@ struct m3b_handle {
   // ---- launch configuration
   int grid = 0, smem = 0, variant = 1;   // LDG kernel variant (m3b_kernels.cu), used when use_tma is false
   bool use_tma = true;                   // streaming TMA kernel (m3b_fill_tma.cu), the default
-  int tma_G = 8, tma_stages = 0;
+  int tma_stages = 0;
   TmaSmem tma{};
   unsigned int* d_tile_counter = nullptr;
+  bool zc_slots = false;                   // shared-memory slots for zero-copy oscillation weights
+  std::map<const void*, const float*> zc_ptr;   // pinned host array -> its device alias (or nullptr)
+  unsigned long long* d_trace = nullptr;   // m3b_block_trace
+  int trace_grid = 0;
   bool hist_in_smem = true;
   bool launch_ready = false;
   bool launch_w2_live = false;
@@ -182,8 +187,9 @@ M3B_API int m3b_create(const m3b_config* cfg, m3b_handle** out) {
   if (prop.major != 10)
     return fail(nullptr, M3B_ERR_NODEVICE, std::string("m3b_create: device '") + prop.name +
                                                "' is not sm_100 (kernels are built for sm_100a only)");
-  const int T = cfg->tile_events == 0 ? 256 : cfg->tile_events;
-  if (T != 128 && T != 256 && T != 512) return fail(nullptr, M3B_ERR_INVALID, "m3b_create: tile_events must be 128, 256 or 512");
+  const int T = cfg->tile_events == 0 ? 1024 : cfg->tile_events;
+  if (T != 128 && T != 256 && T != 512 && T != 1024)
+    return fail(nullptr, M3B_ERR_INVALID, "m3b_create: tile_events must be 128, 256, 512 or 1024");
   h = new m3b_handle();
   h->cfg = *cfg;
   h->device = cfg->device;
@@ -390,6 +396,7 @@ static int append_chunk(m3b_handle* h, int64_t n, const uint32_t* cnt_c, const i
     td.cub = d_cub + tile_cub_off[t];
     td.lin = d_lin + tile_lin_off[t];
     td.sig = tile_sig[t];
+    td.ncnl = h->sigs[td.sig].nc | (h->sigs[td.sig].nl << 16);
     h->tiles.push_back(td);
   }
   h->n_events_loaded += n;
@@ -693,8 +700,9 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
     h->tiles_dirty = false;
     h->launch_ready = false;
   }
-  if (!h->h_step[0] || h->step.P != h->P || h->step.Nn != h->n_norm_values) {
-    h->step = make_step_layout(h->P, h->n_norm_values);
+  if (!h->h_step[0] || h->step.P != h->P || h->step.Nn != h->n_norm_values || h->step_sigs != static_cast<int>(h->sigs.size())) {
+    h->step_sigs = static_cast<int>(h->sigs.size());
+    h->step = make_step_layout(h->P, h->n_norm_values, h->step_sigs, h->max_nc, h->max_nl);
     for (int i = 0; i < m3b_handle::kRing; ++i) {
       if (h->h_step[i]) cudaFreeHost(h->h_step[i]);
       CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_step[i]), h->step.bytes, cudaHostAllocDefault));
@@ -707,40 +715,36 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
     a.step = h->step; a.max_nc = h->max_nc; a.max_nl = h->max_nl; a.n_bins = h->n_bins; a.n_samples = h->n_samples;
     // kernel choice: M3B_VARIANT=tma (default) | 0..5 (LDG register-streaming variants, m3b_kernels.cu)
     const char* v = getenv("M3B_VARIANT");
-    h->use_tma = true;
+    h->use_tma = h->T % 256 == 0;
     if (v && v[0] >= '0' && v[0] <= '9') { h->use_tma = false; h->variant = atoi(v); }
+    REQUIRE(h->use_tma || h->T <= 512, M3B_ERR_INVALID, "step: the register-streaming kernel variants need tile_events <= 512");
     const int llh_scratch = h->n_samples * 32 * 8;
     if (h->use_tma) {
-      // ring of G-row stages in whatever shared memory the fixed tables (and the privatised
+      // ring of 32 KB stages in whatever shared memory the fixed tables (and the privatised
       // histogram, if it fits next to >= 3 stages) leave of the 227 KB opt-in limit
-      const char* ge = getenv("M3B_TMA_G");
-      h->tma_G = ge ? atoi(ge) : (h->T == 512 ? 4 : 8);
       const char* be = getenv("M3B_TMA_BLOCKS_PER_SM");
       const int want_bps = be && atoi(be) > 1 ? atoi(be) : 1;
       const int budget = (232448 - 1024 * want_bps) / want_bps - 1024;     // static barriers + per-block reserve
       auto stages_for = [&](bool hist) {
-        const TmaSmem L0 = tma_smem_layout(h->step, h->max_nc, h->max_nl, h->n_bins, hist, w2_live, h->T, h->tma_G, 0);
-        return std::min(32, (budget - L0.off_ring) / L0.stage_bytes);
+        const TmaSmem L0 = tma_smem_layout(h->step, h->max_nc, h->max_nl, h->n_bins, hist, w2_live, h->zc_slots, 0);
+        return std::min(32, (budget - L0.off_ring) / (L0.stage_bytes + (h->zc_slots ? 4096 : 0)));
       };
       h->hist_in_smem = true;
       int ns = stages_for(true);
       if (ns < 3) { h->hist_in_smem = false; ns = stages_for(false); }
       const char* se = getenv("M3B_TMA_STAGES");
       if (se && atoi(se) > 0) ns = std::min(ns, atoi(se));
-      if (ns < 2) h->use_tma = false;          // tables alone overflow shared memory: register-streaming kernel
-      else {
-        h->tma_stages = ns;
-        h->tma = tma_smem_layout(h->step, h->max_nc, h->max_nl, h->n_bins, h->hist_in_smem, w2_live, h->T, h->tma_G, ns);
-        int smem = std::max(h->tma.total, llh_scratch);
-        cudaError_t e = fill_tma_set_smem(h->T, h->tma_G, smem);
-        if (e == cudaErrorInvalidValue) return fail(h, M3B_ERR_INVALID, "step: unsupported M3B_TMA_G for this tile size");
-        CK(e);
-        int bps = 0;
-        CK(fill_tma_occupancy(h->T, h->tma_G, smem, &bps));
-        REQUIRE(bps > 0, M3B_ERR_CUDA, "step: TMA fill kernel does not fit on an SM");
-        h->smem = smem;
-        h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(std::min(bps, want_bps)) * h->sm_count));
-      }
+      REQUIRE(ns >= 2, M3B_ERR_NOMEM, "step: per-step tables leave no room for the coefficient ring in shared memory");
+      h->tma_stages = ns;
+      h->tma = tma_smem_layout(h->step, h->max_nc, h->max_nl, h->n_bins, h->hist_in_smem, w2_live, h->zc_slots, ns);
+      int smem = std::max(h->tma.total, llh_scratch);
+      CK(fill_tma_set_smem(smem));
+      int bps = 0;
+      CK(fill_tma_occupancy(smem, &bps));
+      REQUIRE(bps > 0, M3B_ERR_CUDA, "step: TMA fill kernel does not fit on an SM");
+      h->smem = smem;
+      const int64_t units = h->n_tiles * (h->T / 256);
+      h->grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(std::min(bps, want_bps)) * h->sm_count));
     }
     if (!h->use_tma) {
       int smem = fill_smem_bytes(a, true, w2_live);
@@ -768,14 +772,38 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   REQUIRE(h->n_events > 0 && h->n_bins > 0, M3B_ERR_STATE, "step: upload binning and events first");
   REQUIRE(h->n_norm_values == 0 || norm_pars, M3B_ERR_INVALID, "step: norm_pars is NULL but events carry norm pointers");
   const bool w2_live = h->first_time_w2;      // Samples/SampleHandlerFD.cpp:445,460
+  // Oscillation weights handed over in pinned (registered) host memory are not copied: the TMA
+  // kernel's producers stream them over PCIe while the coefficients stream from HBM.
+  const float* osc_zc = nullptr;
+  if (osc_w && h->use_osc && !h->d_osc_idx && h->T % 256 == 0) {
+    auto it = h->zc_ptr.find(osc_w);
+    if (it == h->zc_ptr.end()) {
+      const float* dev = nullptr;
+      const char* z = getenv("M3B_OSC_ZEROCOPY");
+      cudaPointerAttributes at{};
+      if (!(z && z[0] == '0') && cudaPointerGetAttributes(&at, osc_w) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+          at.devicePointer && (reinterpret_cast<uintptr_t>(at.devicePointer) & 15) == 0)
+        dev = static_cast<const float*>(at.devicePointer);
+      cudaGetLastError();
+      it = h->zc_ptr.emplace(osc_w, dev).first;
+    }
+    osc_zc = it->second;
+    if (osc_zc && !h->zc_slots) { h->zc_slots = true; h->launch_ready = false; }
+  }
   int rc = prepare_launch(h, w2_live);
   if (rc != M3B_OK) return rc;
+  if (!h->use_tma) osc_zc = nullptr;
 
   // per-step table {segment, dx, value, norm}
+  const bool inline_step = h->step.bytes <= kStepInlineMax && !getenv("M3B_NO_INLINE_STEP");
+  FillArgs a{};
   const int slot = h->ring;
-  h->ring = (h->ring + 1) % m3b_handle::kRing;
-  CK(cudaEventSynchronize(h->step_ev[slot]));
-  unsigned char* st = h->h_step[slot];
+  unsigned char* st = a.step_inline;
+  if (!inline_step) {
+    h->ring = (h->ring + 1) % m3b_handle::kRing;
+    CK(cudaEventSynchronize(h->step_ev[slot]));
+    st = h->h_step[slot];
+  }
   int32_t* seg = reinterpret_cast<int32_t*>(st + h->step.off_seg);
   float* dx = reinterpret_cast<float*>(st + h->step.off_dx);
   float* val = reinterpret_cast<float*>(st + h->step.off_val);
@@ -787,11 +815,27 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     dx[p] = h->n_pts[p] > 0 ? vals[p] - h->coeff_x[static_cast<size_t>(p) * h->Kmax + segs[p]] : 0.f;
   }
   for (int j = 0; j < h->n_norm_values; ++j) norm[j] = static_cast<float>(norm_pars[j]);   // SampleHandlerFD.cpp:580
-  CK(cudaMemcpyAsync(h->d_step[slot], st, h->step.bytes, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaEventRecord(h->step_ev[slot], h->stream));
+  if (h->step.n_sigs_x) {     // per-signature slot tables: no indirection left for the device
+    int32_t* rowx = reinterpret_cast<int32_t*>(st + h->step.off_rowx);
+    float* dxx = reinterpret_cast<float*>(st + h->step.off_dxx);
+    float* lvx = reinterpret_cast<float*>(st + h->step.off_lvx);
+    for (size_t g = 0; g < h->sigs.size(); ++g) {
+      const SigDesc& sd = h->sigs[g];
+      const int32_t* pool = h->sig_pool.data() + sd.off;
+      for (int c = 0; c < sd.nc; ++c) {
+        rowx[g * h->max_nc + c] = pool[sd.nc + c] + seg[pool[c]];
+        dxx[g * h->max_nc + c] = dx[pool[c]];
+      }
+      for (int l = 0; l < sd.nl; ++l) lvx[g * h->max_nl + l] = val[pool[2 * sd.nc + l]];
+    }
+  }
+  if (!inline_step) {
+    CK(cudaMemcpyAsync(h->d_step[slot], st, h->step.bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->step_ev[slot], h->stream));
+  }
   if (osc_w) {
     REQUIRE(h->use_osc, M3B_ERR_INVALID, "step: osc_w given but events were uploaded with use_osc=0");
-    CK(cudaMemcpyAsync(h->d_osc, osc_w, sizeof(float) * h->n_osc, cudaMemcpyHostToDevice, h->stream));
+    if (!osc_zc) CK(cudaMemcpyAsync(h->d_osc, osc_w, sizeof(float) * h->n_osc, cudaMemcpyHostToDevice, h->stream));
   }
 
   // fused mode alternates two buffers (the last block zeroes the other one for the next step);
@@ -806,7 +850,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     if (w2_live) { h->w2_zero[nxt] = false; h->d_w2_frozen = w2; }
   }
 
-  FillArgs a{};
+  a.step_inline_bytes = inline_step ? h->step.bytes : 0;
   a.tiles = h->d_tiles; a.sigs = h->d_sigs; a.sig_pool = h->d_sig_pool;
   a.n_tiles = static_cast<int32_t>(h->n_tiles); a.T = h->T; a.max_nc = h->max_nc; a.max_nl = h->max_nl;
   a.step_table = h->d_step[slot]; a.step = h->step;
@@ -818,10 +862,13 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   a.weights_only = (mode == kWeightsOnly) ? 1 : 0;
   a.test_stat = h->test_stat; a.n_samples = h->n_samples;
   a.data = h->d_data; a.w2_frozen = h->d_w2_frozen; a.sample_start = h->d_sample_start;
+  for (int i = 0; i <= h->n_samples; ++i) a.sample_start_inline[i] = h->sample_start[i];
   a.tile_begin = 0;
+  a.osc_host = osc_zc; a.osc_store = h->d_osc;
   if (h->use_tma) { a.tile_counter = h->d_tile_counter; a.n_stages = h->tma_stages; a.tma = h->tma; }
   a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->h_llh_dev;
   a.evt_spline_w = h->d_evt_spline_w; a.evt_total_w = h->d_evt_total_w;
+  a.trace = h->d_trace;
   if (mode == kFused) {
     // the last block zeroes the other buffer for the next step
     const int other = nxt ^ 1;
@@ -843,7 +890,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     }
     CK(cudaEventRecord(h->tev[h->tev_used], h->stream));
   }
-  if (h->use_tma) CK(launch_fill_tma(a, h->tma_G, h->grid, h->smem, h->stream));
+  if (h->use_tma) CK(launch_fill_tma(a, h->grid, h->smem, h->stream));
   else CK(launch_fill(a, h->variant, h->grid, h->smem, h->stream));
   if (h->timing) { CK(cudaEventRecord(h->tev[h->tev_used + 1], h->stream)); h->tev_used += 2; }
   ++h->launches;
@@ -1090,6 +1137,31 @@ M3B_API int m3b_kernel_time(m3b_handle* h, double* total_ms, int64_t* n_launches
   *total_ms = tot;
   *n_launches = static_cast<int64_t>(h->tev_used / 2);
   h->tev_used = 0;
+  return M3B_OK;
+}
+
+// per-block timeline of the NEXT/LAST fill launch (debug aid for the tail/ramp analysis in DESIGN.md):
+// enable with out == NULL (allocates), then after a step call again with out = u64[grid*8].
+M3B_API int m3b_block_trace(m3b_handle* h, uint64_t* out, int32_t* grid) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  CK(cudaSetDevice(h->device));
+  if (!h->d_trace) {
+    CK(dev_alloc(h, &h->d_trace, static_cast<size_t>(8) * 4096));
+    CK(cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * 8 * 4096));
+  }
+  if (grid) *grid = h->grid;
+  if (out) {
+    CK(cudaStreamSynchronize(h->stream));
+    REQUIRE(h->grid <= 4096, M3B_ERR_INVALID, "m3b_block_trace: grid too large");
+    CK(cudaMemcpy(out, h->d_trace, sizeof(unsigned long long) * 8 * h->grid, cudaMemcpyDeviceToHost));
+    if (getenv("M3B_TRACE_LAST")) {
+      unsigned long long last[2];
+      CK(cudaMemcpy(last, h->d_trace + 8 * 4000, sizeof last, cudaMemcpyDeviceToHost));
+      unsigned long long t0 = ~0ull;
+      for (int b = 0; b < h->grid; ++b) t0 = std::min<unsigned long long>(t0, out[8 * b]);
+      fprintf(stderr, "m3b trace: last block won the ticket at %.2f us, wrote -lnL at %.2f us\n", (last[0] - t0) / 1e3, (last[1] - t0) / 1e3);
+    }
+  }
   return M3B_OK;
 }
 

@@ -37,6 +37,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // coefficient rows are read once per step: keep them out of L1, default L2 policy (small
 // workloads stay L2-resident between steps, large ones stream)
+// Stage the per-step table into shared memory: from the kernel parameters (constant bank) when the
+// host inlined it, else with one bulk copy from device memory.  Every thread calls it; `bar` must be
+// initialised (count 1) and visible.  Returns after the table is readable by the whole block.
+__device__ __forceinline__ void stage_step_table(const FillArgs& a, unsigned char* st, uint64_t* bar) {
+  if (a.step_inline_bytes > 0) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.step_inline);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(st);
+    for (int i = threadIdx.x; i < a.step_inline_bytes / 4; i += blockDim.x) dst[i] = src[i];
+  } else {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, static_cast<uint32_t>(a.step.bytes));
+      bulk_g2s(st, a.step_table, static_cast<uint32_t>(a.step.bytes), bar);
+    }
+    mbar_wait(bar, 0);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// trace slots: 0 block start, 1 tables staged, 2 first stage consumed, 3 producer out of work,
+//              4 consumers done, 5 histogram flushed, 6 block end, 7 units processed by the block
+__device__ __forceinline__ void trace_mark(const FillArgs& a, int slot) {
+  if (a.trace) a.trace[static_cast<size_t>(blockIdx.x) * 8 + slot] = globaltimer_ns();
+}
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 v;
   asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -146,8 +173,23 @@ static __device__ void block_llh(const double* __restrict__ hist, const double* 
   for (int s = 0; s < n_samples; ++s) {
     const int b0 = sample_start[s], b1 = sample_start[s + 1];
     double acc = 0.;
-    for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x)
-      acc += test_stat_llh(ts, data[b], __ldcg(hist + b), w2 ? __ldcg(w2 + b) : 0.);
+    // loads of four strides first, then the arithmetic: one memory latency per batch instead of one
+    // per bin (data[] has been flushed out of L2 by the coefficient stream); same summation order
+    const int NT = blockDim.x;
+    for (int b = b0 + threadIdx.x; b < b1; b += 4 * NT) {
+      double d[4], m[4], v[4];
+      #pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int bb = b + k * NT;
+        const bool ok = bb < b1;
+        d[k] = ok ? data[bb] : 0.;
+        m[k] = ok ? __ldcg(hist + bb) : 0.;
+        v[k] = (ok && w2) ? __ldcg(w2 + bb) : 0.;
+      }
+      #pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (b + k * NT < b1) acc += test_stat_llh(ts, d[k], m[k], v[k]);
+    }
     acc = warp_sum(acc);
     if (lane == 0) scratch[s * 32 + warp] = acc;
   }
@@ -167,7 +209,7 @@ static __device__ void block_llh(const double* __restrict__ hist, const double* 
       if (llh_host) llh_host[1 + s] = v;
     }
     llh_dev[0] = tot;
-    if (llh_host) { llh_host[0] = tot; __threadfence_system(); }
+    if (llh_host) llh_host[0] = tot;     // mapped host memory; visible to the host when the kernel has completed
   }
 }
 
@@ -182,6 +224,16 @@ __device__ __forceinline__ void finish_block(const FillArgs& a, const double* s_
                                              double* scratch, int* s_last) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const bool w2_live = a.w2 != nullptr;
+  if (a.fuse_llh) {
+    // the last block will need data[] (and a frozen w2[]) which the coefficient stream has pushed out
+    // of L2 by now: every block pulls its slice back in while it flushes
+    const int lines = (a.n_bins * 8 + 127) / 128;
+    for (int l = blockIdx.x * NT + tid; l < lines; l += gridDim.x * NT) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.data) + 128 * l));
+      if (a.w2_frozen && a.w2_frozen != a.w2)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.w2_frozen) + 128 * l));
+    }
+  }
   if (a.hist_in_smem && !a.weights_only) {
     __syncthreads();
     for (int i = tid; i < a.n_bins; i += NT) {
@@ -194,6 +246,7 @@ __device__ __forceinline__ void finish_block(const FillArgs& a, const double* s_
         if (v != 0.) atomicAdd(a.w2 + i, v);
       }
   }
+  if (tid == 0) trace_mark(a, 5);
   // (weights_only: SMonolithGPU::RunGPU_SplineMonolith contract -- the weights are the output)
   if ((a.weights_only || (!a.fuse_llh && a.peer_world == 0)) && !a.tile_counter) return;
 
@@ -228,7 +281,9 @@ __device__ __forceinline__ void finish_block(const FillArgs& a, const double* s_
   }
   if (!a.fuse_llh) { if (tid == 0) *a.ticket = 0u; return; }
 
-  block_llh(a.hist, a.w2_frozen, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, scratch);
+  if (tid == 0 && a.trace) a.trace[8 * 4000 + 0] = globaltimer_ns();      // last block: ticket won
+  block_llh(a.hist, a.w2_frozen, a.data, a.sample_start_inline, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, scratch);
+  if (tid == 0 && a.trace) a.trace[8 * 4000 + 1] = globaltimer_ns();      // last block: -lnL written
   // prepare the next step: zero its histogram(s), re-arm the ticket
   if (a.hist_next) for (int i = tid; i < a.n_bins; i += NT) a.hist_next[i] = 0.;
   if (a.w2_next) for (int i = tid; i < a.n_bins; i += NT) a.w2_next[i] = 0.;

@@ -6,24 +6,24 @@
 // (Samples/SampleHandlerFD.cpp:1284-1300), but the coefficient stream no longer goes through
 // registers.  One persistent block per SM:
 //
-//   producer warp   takes tiles from a global counter (dynamic schedule: no tail imbalance between
-//                   SMs) and, for each tile, issues one 1-D bulk copy (cp.async.bulk, SASS UBLKCP)
-//                   per active coefficient row -- T*16 B, fully contiguous because the active segment
-//                   is uniform per parameter per step -- into a ring of shared-memory stages of G
-//                   rows each, completion counted by an mbarrier per stage;
-//   T consumer      one event per thread: wait for a stage, read its own float4/float2 from every
-//   threads         row (conflict-free LDS.128), Horner fmaf, sequential float product in the
-//                   reference's order, release the stage; at the tile's last stage: norms x osc x
+//   producer warp   takes work from a global counter (guided self-scheduling: whole tile rows while
+//                   plenty is left, single 256-event units at the end, so the SMs finish together) and
+//                   issues one 1-D bulk copy (cp.async.bulk, SASS UBLKCP) per active coefficient row
+//                   -- up to T*16 B, fully contiguous because the active segment is uniform per
+//                   parameter per step -- into a ring of 32 KB shared-memory stages, completion
+//                   counted by an mbarrier per stage;
+//   256 consumer    g (1,2,4) events per thread: wait for a stage, read their own float4/float2 from
+//   threads         every row (conflict-free LDS.128), Horner fmaf, sequential float product in the
+//                   reference's order, release the stage; at the grab's last stage: norms x osc x
 //                   spline x static, w<=0 / overflow skip, shared-memory privatised f64 histogram.
 //
-// Bytes in flight are bounded by the ring (up to ~200 KB per SM), not by registers x occupancy, and
-// only T events per SM are in flight, so the end-of-grid tail is ~1/26 of the old kernel's for cfg2.
+// Bytes in flight are bounded by the ring (up to ~200 KB per SM), not by registers x occupancy.
 #include "m3b_device.cuh"
 
 namespace m3b {
 
 constexpr int kMaxStages = 32;
-constexpr int kFlagLinear = 1, kFlagFirst = 2, kFlagLast = 4;
+constexpr int kFlagLinear = 1, kFlagFirst = 2, kFlagLast = 4, kFlagOscDirect = 8;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -33,7 +33,7 @@ __device__ __forceinline__ void consumer_sync(int n_threads) {     // named barr
 }
 
 TmaSmem tma_smem_layout(const StepLayout& step, int max_nc, int max_nl, int n_bins, bool hist_in_smem, bool w2_live,
-                        int T, int G, int n_stages) {
+                        bool osc_slots, int n_stages) {
   TmaSmem L;
   L.off_dx = step.bytes;
   L.off_lv = L.off_dx + 4 * ((max_nc + 3) & ~3);
@@ -41,24 +41,73 @@ TmaSmem tma_smem_layout(const StepLayout& step, int max_nc, int max_nl, int n_bi
   L.off_desc = (L.off_row + 4 * max_nc + 15) & ~15;
   L.off_hist = (L.off_desc + 16 * kMaxStages + 15) & ~15;
   const int hist_bytes = hist_in_smem ? 8 * n_bins * (w2_live ? 2 : 1) : 0;
-  L.off_ring = (L.off_hist + hist_bytes + 127) & ~127;
-  L.stage_bytes = G * T * 16;
+  L.off_osc = (L.off_hist + hist_bytes + 127) & ~127;              // per stage: kMaxG units x 256 floats
+  L.off_ring = L.off_osc + (osc_slots ? n_stages * 4 * 256 * 4 : 0);
+  L.stage_bytes = 8 * 256 * 16;
   L.total = L.off_ring + n_stages * L.stage_bytes;
   return L;
 }
 
-template <int T, int G>
-__global__ void __launch_bounds__(T + 32, 1) fill_tma_kernel(const __grid_constant__ FillArgs a) {
+// One work unit = kUnit consecutive lanes of a tile row (kUnit consumer threads, one event each).
+// A tile row holds T = q_max*kUnit events; the producer grabs g in {1,2,4,...,q_max} aligned units
+// at a time -- whole rows while plenty of work is left (g*kUnit*16 B contiguous per copy: DRAM likes
+// long bursts, scripts/hbm_probe.cu), single units near the end of the grid so the SMs finish
+// together (guided self-scheduling).  A consumer thread then carries g events.
+constexpr int kUnit = 256;
+constexpr int kStageBytes = 8 * kUnit * 16;      // 32 KB: 8/g cubic rows or 16/g linear rows of g units
+constexpr int kMaxG = 4;
+
+template <int GQ>
+__device__ __forceinline__ void consume_cubic(const float4* rows, int n, const float* dx, float (&w)[kMaxG]) {
+  constexpr int kRows = 8 / GQ;
+  if (n == kRows) {
+    float4 c[kRows][GQ];
+    #pragma unroll
+    for (int j = 0; j < kRows; ++j)
+      #pragma unroll
+      for (int q = 0; q < GQ; ++q) c[j][q] = rows[(j * GQ + q) * kUnit];
+    #pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+      const float d = dx[j];
+      #pragma unroll
+      for (int q = 0; q < GQ; ++q) w[q] *= fmaf(d, fmaf(d, fmaf(d, c[j][q].w, c[j][q].z), c[j][q].y), c[j][q].x);
+    }
+  } else {
+    for (int j = 0; j < n; ++j) {
+      const float d = dx[j];
+      #pragma unroll
+      for (int q = 0; q < GQ; ++q) {
+        const float4 c = rows[(j * GQ + q) * kUnit];
+        w[q] *= fmaf(d, fmaf(d, fmaf(d, c.w, c.z), c.y), c.x);
+      }
+    }
+  }
+}
+template <int GQ>
+__device__ __forceinline__ void consume_linear(const float2* rows, int n, const float* lv, float (&w)[kMaxG]) {
+  #pragma unroll 2
+  for (int j = 0; j < n; ++j) {
+    const float v = lv[j];
+    #pragma unroll
+    for (int q = 0; q < GQ; ++q) {
+      const float2 c = rows[(j * GQ + q) * kUnit];
+      w[q] *= fmaf(c.x, v, c.y);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_constant__ FillArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t step_bar;
   __shared__ int s_last;
 
-  constexpr int kConsumerWarps = T / 32;
-  constexpr int kStageBytes = G * T * 16;
+  constexpr int kConsumerWarps = kUnit / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NS = a.n_stages;
+  const int T = a.T;                       // events per tile row
+  const int qmax = T / kUnit;              // units per tile
   const bool w2_live = a.w2 != nullptr;
   const bool smem_hist = a.hist_in_smem != 0;
 
@@ -71,23 +120,31 @@ __global__ void __launch_bounds__(T + 32, 1) fill_tma_kernel(const __grid_consta
   double* s_hist = reinterpret_cast<double*>(smem + L.off_hist);
   double* s_w2 = s_hist + a.n_bins;
   unsigned char* ring = smem + L.off_ring;
+  float* s_osc = reinterpret_cast<float*>(smem + L.off_osc);
 
+  if (tid == 0) trace_mark(a, 0);
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
     mbar_init(&step_bar, 1);
   }
   __syncthreads();
-  // stage the per-step {segment, dx, value, norm} table with one bulk copy
-  if (tid == 0) {
-    mbar_expect_tx(&step_bar, static_cast<uint32_t>(a.step.bytes));
-    bulk_g2s(st, a.step_table, static_cast<uint32_t>(a.step.bytes), &step_bar);
-  }
   if (smem_hist && !a.weights_only) {
-    for (int i = tid; i < a.n_bins; i += T + 32) s_hist[i] = 0.;
-    if (w2_live) for (int i = tid; i < a.n_bins; i += T + 32) s_w2[i] = 0.;
+    for (int i = tid; i < a.n_bins; i += kUnit + 32) s_hist[i] = 0.;
+    if (w2_live) for (int i = tid; i < a.n_bins; i += kUnit + 32) s_w2[i] = 0.;
   }
-  mbar_wait(&step_bar, 0);
-  __syncthreads();
+  // the producer's first grab and its tile descriptor overlap the table staging (shortens the ramp)
+  const unsigned int unit_begin = static_cast<unsigned int>(a.tile_begin) * qmax;
+  const unsigned int unit_end = static_cast<unsigned int>(a.n_tiles) * qmax;
+  const unsigned int guard = 2u * gridDim.x;
+  unsigned int c_first = 0; int want_first = 0;
+  if (warp == kConsumerWarps && lane == 0) {
+    want_first = qmax;
+    while (want_first > 1 && unit_end - unit_begin < guard * want_first) want_first >>= 1;
+    c_first = atomicAdd(a.tile_counter, static_cast<unsigned int>(want_first));
+  }
+  // stage the per-step {segment, dx, value, norm, per-signature slot} tables
+  stage_step_table(a, st, &step_bar);
+  if (tid == 0) trace_mark(a, 1);
 
   const int32_t* seg = reinterpret_cast<const int32_t*>(st + a.step.off_seg);
   const float* dxp = reinterpret_cast<const float*>(st + a.step.off_dx);
@@ -99,61 +156,121 @@ __global__ void __launch_bounds__(T + 32, 1) fill_tma_kernel(const __grid_consta
     int stage = 0, prod_sig = -1;
     uint32_t phase = 1;       // a fresh mbarrier passes a wait on the "previous" phase
     auto advance = [&]() { if (++stage == NS) { stage = 0; phase ^= 1u; } };
+    const unsigned int c0 = __shfl_sync(0xffffffffu, c_first, 0);
+    const int w0 = __shfl_sync(0xffffffffu, want_first, 0);
+    unsigned int seen = c0 + w0;    // last counter value this producer saw: estimates the work left
+    unsigned int u = unit_begin + c0;   // units [u, u_end) grabbed and not yet issued
+    unsigned int u_end = u + w0 < unit_end ? u + w0 : unit_end;
+    unsigned long long n_units = 0;
+    const bool expanded = a.step.n_sigs_x > 0;
+    const int32_t* rowx = reinterpret_cast<const int32_t*>(st + a.step.off_rowx);
+    bool fresh = true;
     while (true) {
-      int t = 0;
-      if (lane == 0) t = a.tile_begin + static_cast<int>(atomicAdd(a.tile_counter, 1u));
-      t = __shfl_sync(0xffffffffu, t, 0);
-      if (t >= a.n_tiles) break;
-      const TileDesc td = a.tiles[t];
-      const SigDesc sd = a.sigs[td.sig];
-      const int nc = sd.nc, nl = sd.nl;
-      if (td.sig != prod_sig) {      // first active row of every cubic slot, this step's segments
-        const int32_t* pool = a.sig_pool + sd.off;
-        __syncwarp();
-        for (int s = lane; s < nc; s += 32) s_row[s] = pool[nc + s] + seg[pool[s]];
-        __syncwarp();
-        prod_sig = td.sig;
-      }
-      const int ncs = (nc + G - 1) / G, nls = (nl + 2 * G - 1) / (2 * G);
-      const int total = ncs + nls > 0 ? ncs + nls : 1;
-      int k = 0;
-      for (int s0 = 0; s0 < nc; s0 += G, ++k) {
-        const int n = nc - s0 < G ? nc - s0 : G;
-        mbar_wait(&empty_bar[stage], phase);
+      if (fresh) { fresh = false; if (u >= unit_end) break; }
+      else if (u >= u_end) {
+        // guided grab: one atomicAdd (never retries, no CAS storms); the size comes from the
+        // work left as of this producer's previous grab
+        unsigned int c = 0; int want = 0;
         if (lane == 0) {
-          s_desc[stage] = make_int4(t, s0, n, (k == 0 ? kFlagFirst : 0) | (k == total - 1 ? kFlagLast : 0) | (td.sig << 8));
-          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(n) * T * 16u);
+          const unsigned int left = unit_begin + seen < unit_end ? unit_end - unit_begin - seen : 0u;
+          want = qmax;
+          while (want > 1 && left < guard * want) want >>= 1;
+          c = atomicAdd(a.tile_counter, static_cast<unsigned int>(want));
+        }
+        want = __shfl_sync(0xffffffffu, want, 0);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        seen = c + want;
+        u = unit_begin + c;
+        if (u >= unit_end) break;
+        u_end = u + want < unit_end ? u + want : unit_end;
+      }
+      // largest aligned power-of-two piece of [u, u_end): stays inside one tile row
+      int g = qmax;
+      while (g > 1 && ((u & (g - 1)) != 0 || u + g > u_end)) g >>= 1;
+      const int t = static_cast<int>(u / qmax);
+      const int lane0 = static_cast<int>(u % qmax) * kUnit;       // first lane of the grab within the tile row
+      const TileDesc td = a.tiles[t];
+      const int nc = td.ncnl & 0xffff, nl = td.ncnl >> 16;
+      // zero-copy oscillation weights: g*1 KB straight from pinned host memory, riding on the grab's
+      // last stage (they are needed only when the event's total weight is formed)
+      const int64_t e_first = static_cast<int64_t>(t) * T + lane0;
+      // (the grab holding the ragged end of the event list reads its few weights with plain loads)
+      const bool osc_tail = a.osc_host && e_first + static_cast<int64_t>(g) * kUnit > a.n_events;
+      const uint32_t osc_bytes = (a.osc_host && !osc_tail) ? static_cast<uint32_t>(g) * kUnit * 4u : 0u;
+      const int xflags = (td.sig << 8) | (osc_tail ? kFlagOscDirect : 0);
+      const int32_t* rowp = rowx + td.sig * a.step.max_nc;     // first active row of every cubic slot
+      if (!expanded) {
+        if (td.sig != prod_sig) {    // too many signatures for the host-expanded tables: build it here
+          const int32_t* pool = a.sig_pool + a.sigs[td.sig].off;
+          __syncwarp();
+          for (int s = lane; s < nc; s += 32) s_row[s] = pool[nc + s] + seg[pool[s]];
+          __syncwarp();
+          prod_sig = td.sig;
+        }
+        rowp = s_row;
+      }
+      const int rc = 8 / g, rl = 16 / g;                           // rows per stage
+      const int ncs = (nc + rc - 1) / rc, nls = (nl + rl - 1) / rl;
+      const int total = ncs + nls > 0 ? ncs + nls : 1;
+      const int where = t | (lane0 / kUnit) << 24;                 // tile (24 bits) | first unit
+      int k = 0;
+      for (int s0 = 0; s0 < nc; s0 += rc, ++k) {
+        const int n = nc - s0 < rc ? nc - s0 : rc;
+        const uint32_t row_bytes = static_cast<uint32_t>(g) * kUnit * 16u;
+        mbar_wait(&empty_bar[stage], phase);
+        const bool last = k == total - 1;
+        if (lane == 0) {
+          s_desc[stage] = make_int4(where, s0 | n << 16, g, (k == 0 ? kFlagFirst : 0) | (last ? kFlagLast : 0) | xflags);
+          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(n) * row_bytes + (last ? osc_bytes : 0u));
         }
         __syncwarp();
-        if (lane < n) {
-          const int64_t row = static_cast<int64_t>(s_row[s0 + lane]) * T;
-          bulk_g2s(ring + static_cast<size_t>(stage) * kStageBytes + static_cast<size_t>(lane) * T * 16, td.cub + row,
-                   T * 16u, &full_bar[stage]);
-        }
+        if (lane < n)
+          bulk_g2s(ring + static_cast<size_t>(stage) * kStageBytes + static_cast<size_t>(lane) * row_bytes,
+                   td.cub + static_cast<int64_t>(rowp[s0 + lane]) * T + lane0, row_bytes, &full_bar[stage]);
+        if (last && osc_bytes && lane == 31)
+          bulk_g2s(s_osc + static_cast<size_t>(stage) * (kMaxG * kUnit), a.osc_host + e_first, osc_bytes, &full_bar[stage]);
         advance();
       }
-      for (int s0 = 0; s0 < nl; s0 += 2 * G, ++k) {
-        const int n = nl - s0 < 2 * G ? nl - s0 : 2 * G;
+      for (int s0 = 0; s0 < nl; s0 += rl, ++k) {
+        const int n = nl - s0 < rl ? nl - s0 : rl;
+        const uint32_t row_bytes = static_cast<uint32_t>(g) * kUnit * 8u;
         mbar_wait(&empty_bar[stage], phase);
+        const bool last = k == total - 1;
         if (lane == 0) {
-          s_desc[stage] = make_int4(t, s0, n, kFlagLinear | (k == 0 ? kFlagFirst : 0) | (k == total - 1 ? kFlagLast : 0) | (td.sig << 8));
-          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(n) * T * 8u);
-          bulk_g2s(ring + static_cast<size_t>(stage) * kStageBytes, td.lin + static_cast<int64_t>(s0) * T,
-                   static_cast<uint32_t>(n) * T * 8u, &full_bar[stage]);
+          s_desc[stage] = make_int4(where, s0 | n << 16, g, kFlagLinear | (k == 0 ? kFlagFirst : 0) | (last ? kFlagLast : 0) | xflags);
+          mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(n) * row_bytes + (last ? osc_bytes : 0u));
         }
         __syncwarp();
+        if (last && osc_bytes && lane == 31)
+          bulk_g2s(s_osc + static_cast<size_t>(stage) * (kMaxG * kUnit), a.osc_host + e_first, osc_bytes, &full_bar[stage]);
+        if (g == qmax) {       // whole rows: the slots are contiguous, one copy
+          if (lane == 0)
+            bulk_g2s(ring + static_cast<size_t>(stage) * kStageBytes, td.lin + static_cast<int64_t>(s0) * T,
+                     static_cast<uint32_t>(n) * row_bytes, &full_bar[stage]);
+        } else if (lane < n) {
+          bulk_g2s(ring + static_cast<size_t>(stage) * kStageBytes + static_cast<size_t>(lane) * row_bytes,
+                   td.lin + static_cast<int64_t>(s0 + lane) * T + lane0, row_bytes, &full_bar[stage]);
+        }
         advance();
       }
       if (k == 0) {   // a tile without response functions still has events to weight and fill
         mbar_wait(&empty_bar[stage], phase);
         if (lane == 0) {
-          s_desc[stage] = make_int4(t, 0, 0, kFlagFirst | kFlagLast | (td.sig << 8));
-          mbar_arrive(&full_bar[stage]);
+          s_desc[stage] = make_int4(where, 0, g, kFlagFirst | kFlagLast | xflags);
+          if (osc_bytes) {
+            mbar_expect_tx(&full_bar[stage], osc_bytes);
+            bulk_g2s(s_osc + static_cast<size_t>(stage) * (kMaxG * kUnit), a.osc_host + e_first, osc_bytes, &full_bar[stage]);
+          } else {
+            mbar_arrive(&full_bar[stage]);
+          }
         }
         __syncwarp();
         advance();
       }
+      u += g;
+      n_units += g;
     }
+    if (lane == 0) { trace_mark(a, 3); if (a.trace) a.trace[static_cast<size_t>(blockIdx.x) * 8 + 7] = n_units; }
     // terminal stage
     mbar_wait(&empty_bar[stage], phase);
     if (lane == 0) {
@@ -162,118 +279,128 @@ __global__ void __launch_bounds__(T + 32, 1) fill_tma_kernel(const __grid_consta
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ consumers: one event per thread
+    // ------------------------------------------------------------------ consumers: g events per thread
     int stage = 0;
     uint32_t phase = 0;
     int cur_sig = -1;
-    float w_spl = 1.0f, w_osc = 1.f, w_static = 1.f;
-    int bin = -1;
-    int64_t e = 0;
+    float w_spl[kMaxG], w_osc[kMaxG], w_static[kMaxG];
+    int bin[kMaxG];
+    #pragma unroll
+    for (int q = 0; q < kMaxG; ++q) { w_spl[q] = 1.f; w_osc[q] = 1.f; w_static[q] = 1.f; bin[q] = -1; }
+    int64_t e0 = 0;
+    const float* c_dx = s_dx;
+    const float* c_lv = s_lv;
+    bool first = true;
     while (true) {
       mbar_wait(&full_bar[stage], phase);
       const int4 d = s_desc[stage];
       if (d.x < 0) break;
-      const int s0 = d.y, n = d.z, flags = d.w & 0xff;
+      if (first) { first = false; if (tid == 0) trace_mark(a, 2); }
+      const int s0 = d.y & 0xffff, n = d.y >> 16, g = d.z, flags = d.w & 0xff;
       if (flags & kFlagFirst) {
         const int sig = d.w >> 8;
         if (sig != cur_sig) {          // uniform over the consumers: they all walk the same stage sequence
-          consumer_sync(T);
-          const SigDesc sd = a.sigs[sig];
-          const int32_t* pool = a.sig_pool + sd.off;
-          for (int s = tid; s < sd.nc; s += T) s_dx[s] = dxp[pool[s]];
-          for (int s = tid; s < sd.nl; s += T) s_lv[s] = val[pool[2 * sd.nc + s]];
+          if (a.step.n_sigs_x > 0) {
+            c_dx = reinterpret_cast<const float*>(st + a.step.off_dxx) + sig * a.step.max_nc;
+            c_lv = reinterpret_cast<const float*>(st + a.step.off_lvx) + sig * a.step.max_nl;
+          } else {
+            consumer_sync(kUnit);
+            const SigDesc sd = a.sigs[sig];
+            const int32_t* pool = a.sig_pool + sd.off;
+            for (int s = tid; s < sd.nc; s += kUnit) s_dx[s] = dxp[pool[s]];
+            for (int s = tid; s < sd.nl; s += kUnit) s_lv[s] = val[pool[2 * sd.nc + s]];
+            consumer_sync(kUnit);
+          }
           cur_sig = sig;
-          consumer_sync(T);
         }
-        e = static_cast<int64_t>(d.x) * T + tid;
+        e0 = static_cast<int64_t>(d.x & 0xffffff) * T + (d.x >> 24) * kUnit + tid;
         // event-table loads fly while the tile's stages are consumed
-        bin = a.bin[e];
-        w_osc = 1.f; w_static = 1.f;
-        if (a.osc) {
-          const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
-          w_osc = a.osc[oi];
+        #pragma unroll
+        for (int q = 0; q < kMaxG; ++q) {
+          if (q < g) {
+            const int64_t e = e0 + q * kUnit;
+            bin[q] = a.bin[e];
+            w_osc[q] = 1.f; w_static[q] = 1.f;
+            if (a.osc && !a.osc_host) {
+              const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
+              w_osc[q] = a.osc[oi];
+            }
+            if (a.static_w) w_static[q] = a.static_w[e];
+            w_spl[q] = 1.0f;
+          }
         }
-        if (a.static_w) w_static = a.static_w[e];
-        w_spl = 1.0f;
       }
       const unsigned char* sb = ring + static_cast<size_t>(stage) * kStageBytes;
       if (!(flags & kFlagLinear)) {
         const float4* rows = reinterpret_cast<const float4*>(sb) + tid;
-        if (n == G) {
-          float4 c[G];
-          #pragma unroll
-          for (int j = 0; j < G; ++j) c[j] = rows[j * T];
-          #pragma unroll
-          for (int j = 0; j < G; ++j) {
-            const float dx = s_dx[s0 + j];
-            w_spl *= fmaf(dx, fmaf(dx, fmaf(dx, c[j].w, c[j].z), c[j].y), c[j].x);
-          }
-        } else {
-          for (int j = 0; j < n; ++j) {
-            const float4 c = rows[j * T];
-            const float dx = s_dx[s0 + j];
-            w_spl *= fmaf(dx, fmaf(dx, fmaf(dx, c.w, c.z), c.y), c.x);
-          }
-        }
+        if (g == 4) consume_cubic<4>(rows, n, c_dx + s0, w_spl);
+        else if (g == 2) consume_cubic<2>(rows, n, c_dx + s0, w_spl);
+        else consume_cubic<1>(rows, n, c_dx + s0, w_spl);
       } else {
         const float2* rows = reinterpret_cast<const float2*>(sb) + tid;
-        #pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-          const float2 c = rows[j * T];
-          w_spl *= fmaf(c.x, s_lv[s0 + j], c.y);
-        }
+        if (g == 4) consume_linear<4>(rows, n, c_lv + s0, w_spl);
+        else if (g == 2) consume_linear<2>(rows, n, c_lv + s0, w_spl);
+        else consume_linear<1>(rows, n, c_lv + s0, w_spl);
+      }
+      if ((flags & kFlagLast) && a.osc_host) {
+        #pragma unroll
+        for (int q = 0; q < kMaxG; ++q)
+          if (q < g) {
+            const int64_t e = e0 + q * kUnit;
+            if (flags & kFlagOscDirect) w_osc[q] = e < a.n_events ? a.osc_host[e] : 1.f;
+            else w_osc[q] = s_osc[stage * (kMaxG * kUnit) + q * kUnit + tid];
+            if (e < a.n_events) a.osc_store[e] = w_osc[q];
+          }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);       // stage may be refilled
       if (++stage == NS) { stage = 0; phase ^= 1u; }
 
       if (flags & kFlagLast) {
-        // CalcWeightTotal: norms (double -> float on the host) in pointer order, then osc, spline, extras
-        float w = 1.0f;
-        for (int j = 0; j < a.norm_slots; ++j) {
-          const int i = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + e];
-          w *= (i >= 0 ? norm[i] : 1.0f);
-        }
-        w *= w_osc;
-        w *= w_spl;
-        w *= w_static;
-        if (a.evt_spline_w && e < a.n_events) { a.evt_spline_w[e] = w_spl; a.evt_total_w[e] = w; }
-        // FillArray_MP: skip w<=0 and under/overflow; mc += w; w2 += w*w (float product)
-        if (w > 0.f && bin >= 0 && !a.weights_only) {
-          if (smem_hist) {
-            atomicAdd(s_hist + bin, static_cast<double>(w));
-            if (w2_live) atomicAdd(s_w2 + bin, static_cast<double>(w * w));
-          } else {
-            atomicAdd(a.hist + bin, static_cast<double>(w));
-            if (w2_live) atomicAdd(a.w2 + bin, static_cast<double>(w * w));
+        #pragma unroll
+        for (int q = 0; q < kMaxG; ++q) {
+          if (q < g) {
+            const int64_t e = e0 + q * kUnit;
+            // CalcWeightTotal: norms (double -> float on the host) in pointer order, then osc, spline, extras
+            float w = 1.0f;
+            for (int j = 0; j < a.norm_slots; ++j) {
+              const int i = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + e];
+              w *= (i >= 0 ? norm[i] : 1.0f);
+            }
+            w *= w_osc[q];
+            w *= w_spl[q];
+            w *= w_static[q];
+            if (a.evt_spline_w && e < a.n_events) { a.evt_spline_w[e] = w_spl[q]; a.evt_total_w[e] = w; }
+            // FillArray_MP: skip w<=0 and under/overflow; mc += w; w2 += w*w (float product)
+            if (w > 0.f && bin[q] >= 0 && !a.weights_only) {
+              if (smem_hist) {
+                atomicAdd(s_hist + bin[q], static_cast<double>(w));
+                if (w2_live) atomicAdd(s_w2 + bin[q], static_cast<double>(w * w));
+              } else {
+                atomicAdd(a.hist + bin[q], static_cast<double>(w));
+                if (w2_live) atomicAdd(a.w2 + bin[q], static_cast<double>(w * w));
+              }
+            }
           }
         }
       }
     }
   }
+  if (tid == 0) trace_mark(a, 4);
   finish_block(a, s_hist, s_w2, reinterpret_cast<double*>(smem), &s_last);
+  if (tid == 0) trace_mark(a, 6);
 }
 
-#define M3B_TMA_DISPATCH(T_RUNTIME, G_RUNTIME, EXPR)                                          \
-  if (T_RUNTIME == 256 && G_RUNTIME == 8) { auto k = fill_tma_kernel<256, 8>; EXPR; }         \
-  else if (T_RUNTIME == 256 && G_RUNTIME == 4) { auto k = fill_tma_kernel<256, 4>; EXPR; }    \
-  else if (T_RUNTIME == 128 && G_RUNTIME == 8) { auto k = fill_tma_kernel<128, 8>; EXPR; }    \
-  else if (T_RUNTIME == 128 && G_RUNTIME == 16) { auto k = fill_tma_kernel<128, 16>; EXPR; }  \
-  else if (T_RUNTIME == 512 && G_RUNTIME == 4) { auto k = fill_tma_kernel<512, 4>; EXPR; }    \
-  else if (T_RUNTIME == 512 && G_RUNTIME == 8) { auto k = fill_tma_kernel<512, 8>; EXPR; }    \
-  else return cudaErrorInvalidValue;
-
-cudaError_t launch_fill_tma(const FillArgs& a, int G, int grid, int smem, cudaStream_t s) {
-  M3B_TMA_DISPATCH(a.T, G, (k<<<grid, a.T + 32, smem, s>>>(a)))
+cudaError_t launch_fill_tma(const FillArgs& a, int grid, int smem, cudaStream_t s) {
+  if (a.T % kUnit != 0 || a.T / kUnit > kMaxG || (a.T / kUnit & (a.T / kUnit - 1)) != 0) return cudaErrorInvalidValue;
+  fill_tma_kernel<<<grid, kUnit + 32, smem, s>>>(a);
   return cudaGetLastError();
 }
-cudaError_t fill_tma_set_smem(int T, int G, int smem) {
-  M3B_TMA_DISPATCH(T, G, return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
-  return cudaSuccess;
+cudaError_t fill_tma_set_smem(int smem) {
+  return cudaFuncSetAttribute(fill_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
-cudaError_t fill_tma_occupancy(int T, int G, int smem, int* bps) {
-  M3B_TMA_DISPATCH(T, G, return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, k, T + 32, smem))
-  return cudaSuccess;
+cudaError_t fill_tma_occupancy(int smem, int* bps) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, fill_tma_kernel, kUnit + 32, smem);
 }
 
 }  // namespace m3b

@@ -17,7 +17,7 @@ struct TileDesc {
   const float4* cub;
   const float2* lin;
   int32_t sig;       // signature: which parameters the tile's slots refer to
-  int32_t pad;
+  int32_t ncnl;      // the signature's slot counts, nc | nl << 16 (saves the producer a dependent load)
 };
 
 // Signature = the (sorted) union of parameters of the tile's events.  pool layout at `off`:
@@ -28,19 +28,39 @@ struct SigDesc {
 
 // Per-step table, built on the host (SplineBase::FindSplineSegment), copied H2D once per step and
 // staged into shared memory by every block with one bulk (TMA) copy:
-//   int32 seg[P] | float dx[P] | float val[P] | float norm[Nn]    (padded to 16 B)
+//   int32 seg[P] | float dx[P] | float val[P] | float norm[Nn]
+// and, when the signatures are few enough (n_sigs_x > 0), the same expanded per signature slot so
+// the kernels index by slot with no indirection through the signature pool:
+//   int32 rowx[n_sigs][max_nc]  first active coefficient row of the slot = segbase + segment
+//   float dxx [n_sigs][max_nc]  dx of the slot's parameter
+//   float lvx [n_sigs][max_nl]  value of the TF1 slot's parameter
+// (padded to 16 B)
 struct StepLayout {
   int32_t P, Nn;
   int32_t off_seg, off_dx, off_val, off_norm, bytes;
+  int32_t n_sigs_x, max_nc, max_nl, off_rowx, off_dxx, off_lvx;
 };
-inline StepLayout make_step_layout(int P, int Nn) {
+constexpr int kMaxExpandedStepBytes = 16384;
+constexpr int kStepInlineMax = 3072;      // kernel parameters stay below the classic 4 KB limit
+inline StepLayout make_step_layout(int P, int Nn, int n_sigs, int max_nc, int max_nl) {
   StepLayout L;
   L.P = P; L.Nn = Nn;
   L.off_seg = 0;
   L.off_dx = L.off_seg + 4 * P;
   L.off_val = L.off_dx + 4 * P;
   L.off_norm = L.off_val + 4 * P;
-  L.bytes = (L.off_norm + 4 * Nn + 15) & ~15;
+  int end = L.off_norm + 4 * Nn;
+  L.max_nc = max_nc; L.max_nl = max_nl;
+  const long long x = 4ll * n_sigs * (2 * max_nc + max_nl);
+  L.n_sigs_x = (n_sigs > 0 && x > 0 && x <= kMaxExpandedStepBytes) ? n_sigs : 0;
+  L.off_rowx = L.off_dxx = L.off_lvx = 0;
+  if (L.n_sigs_x) {
+    L.off_rowx = (end + 15) & ~15;
+    L.off_dxx = L.off_rowx + 4 * n_sigs * max_nc;
+    L.off_lvx = L.off_dxx + 4 * n_sigs * max_nc;
+    end = L.off_lvx + 4 * n_sigs * max_nl;
+  }
+  L.bytes = (end + 15) & ~15;
   if (L.bytes == 0) L.bytes = 16;
   return L;
 }
@@ -48,7 +68,7 @@ inline StepLayout make_step_layout(int P, int Nn) {
 // Shared-memory map of the TMA fill kernel (m3b_fill_tma.cu); computed on the host, passed by value.
 //   [step table][dx[max_nc]][lv[max_nl]][row[max_nc]][stage descriptors][hist (+w2)][ring: n_stages x stage_bytes]
 struct TmaSmem {
-  int32_t off_dx, off_lv, off_row, off_desc, off_hist, off_ring, stage_bytes, total;
+  int32_t off_dx, off_lv, off_row, off_desc, off_hist, off_osc, off_ring, stage_bytes, total;
 };
 
 struct FillArgs {
@@ -58,12 +78,17 @@ struct FillArgs {
   const int32_t* sig_pool;
   int32_t tile_begin, n_tiles, T, max_nc, max_nl;
   TmaSmem tma;
-  // per-step table
+  // per-step table: in device memory (step_table, one H2D copy per step) or, when it is small
+  // enough (the usual case), inside the kernel parameters themselves (step_inline): no copy at all
   const unsigned char* step_table;
   StepLayout step;
+  int32_t step_inline_bytes;
   // event table (flat, padded to n_tiles*T)
   const int32_t* bin;
   const float* osc;
+  const float* osc_host;       // TMA kernel, zero-copy: this step's weights in pinned host memory, streamed
+                               // over PCIe by the producer's bulk copies (no separate H2D pass); the
+  float* osc_store;            // consumers also store them here so later steps find them on the device
   const int32_t* osc_idx;
   const float* static_w;
   const int16_t* norm_idx;     // [slot * e_pad + e]
@@ -81,6 +106,7 @@ struct FillArgs {
   const double* data;
   const double* w2_frozen;     // w2 histogram to use in the LLH (== w2 when live)
   const int32_t* sample_start; // [n_samples+1] global bin offsets
+  int32_t sample_start_inline[65];   // the same, in the kernel parameters (saves the last block a DRAM round trip)
   unsigned int* ticket;
   unsigned int* tile_counter;  // dynamic tile scheduler of the TMA kernel (nullptr: static interleave)
   int32_t n_stages;            // TMA kernel: stages of the shared-memory coefficient ring
@@ -89,6 +115,9 @@ struct FillArgs {
   // optional per-event outputs
   float* evt_spline_w;
   float* evt_total_w;
+  // optional per-block timeline (m3b_block_trace): 8 x u64 globaltimer ns per block
+  unsigned long long* trace;
+  alignas(16) unsigned char step_inline[kStepInlineMax];
   // peer exchange (multi-GPU, own collective): push partial hist into every rank's inbox
   int32_t peer_world, peer_rank;
   double* peer_inbox[8];       // peer_inbox[r] = rank r's inbox base; slot for us at [peer_rank * 2*n_bins]
@@ -149,12 +178,12 @@ cudaError_t launch_bins(const BinArgs& a, cudaStream_t s);
 cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s);
 cudaError_t fill_occupancy(int T, int variant, int smem_bytes, int* blocks_per_sm);
 cudaError_t fill_set_smem(int T, int variant, int smem_bytes);
-// TMA streaming kernel (m3b_fill_tma.cu): G = coefficient rows per shared-memory stage
+// TMA streaming kernel (m3b_fill_tma.cu): tile rows of T = 256, 512 or 1024 events
 TmaSmem tma_smem_layout(const StepLayout& step, int max_nc, int max_nl, int n_bins, bool hist_in_smem, bool w2_live,
-                        int T, int G, int n_stages);
-cudaError_t launch_fill_tma(const FillArgs& a, int G, int grid, int smem_bytes, cudaStream_t s);
-cudaError_t fill_tma_set_smem(int T, int G, int smem_bytes);
-cudaError_t fill_tma_occupancy(int T, int G, int smem_bytes, int* blocks_per_sm);
+                        bool osc_slots, int n_stages);
+cudaError_t launch_fill_tma(const FillArgs& a, int grid, int smem_bytes, cudaStream_t s);
+cudaError_t fill_tma_set_smem(int smem_bytes);
+cudaError_t fill_tma_occupancy(int smem_bytes, int* blocks_per_sm);
 int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
 
 }  // namespace m3b

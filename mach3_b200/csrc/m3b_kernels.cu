@@ -43,16 +43,11 @@ __global__ void __launch_bounds__(T, kMinBlocks) fill_kernel(const __grid_consta
   // stage the per-step {segment, dx, value, norm} table with one bulk (TMA) copy
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bar, static_cast<uint32_t>(a.step.bytes));
-    bulk_g2s(st, a.step_table, static_cast<uint32_t>(a.step.bytes), &bar);
-  }
   if (smem_hist && !a.weights_only) {
     for (int i = tid; i < a.n_bins; i += T) s_hist[i] = 0.;
     if (w2_live) for (int i = tid; i < a.n_bins; i += T) s_w2[i] = 0.;
   }
-  mbar_wait(&bar, 0);
-  __syncthreads();
+  stage_step_table(a, st, &bar);
 
   const int32_t* seg = reinterpret_cast<const int32_t*>(st + a.step.off_seg);
   const float* dxp = reinterpret_cast<const float*>(st + a.step.off_dx);

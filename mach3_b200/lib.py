@@ -25,7 +25,7 @@ EXPORTS = (
     "m3b_step", "m3b_step_segments", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
     "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
-    "m3b_get_info", "m3b_set_timing", "m3b_kernel_time",
+    "m3b_get_info", "m3b_set_timing", "m3b_kernel_time", "m3b_block_trace",
 )
 
 
@@ -65,6 +65,25 @@ def load():
         L.m3b_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+def bind_to_gpu_cpus(device=0):
+    """Pin the calling process to the CPUs NVML reports as local to `device` so that pinned host
+    buffers are first-touched on the GPU's socket (zero-copy osc weights cross PCIe once, not UPI +
+    PCIe).  Host-side placement only; returns a short description or None when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(device)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cpus local to gpu {device}"
+    except Exception as e:       # noqa: BLE001 - best effort
+        return None
 
 
 def _p(a):
@@ -263,6 +282,16 @@ class Handle:
         ms, n = C.c_double(0), C.c_int64(0)
         self._ck(self.L.m3b_kernel_time(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def block_trace(self, read=True):
+        """Per-block timeline of the last fill launch: array [grid, 8] of globaltimer ns (see m3b200.h)."""
+        g = C.c_int32(0)
+        self._ck(self.L.m3b_block_trace(self.h, None, C.byref(g)))
+        if not read:
+            return None
+        out = np.zeros((max(g.value, 1), 8), np.uint64)
+        self._ck(self.L.m3b_block_trace(self.h, _p(out), C.byref(g)))
+        return out[:g.value]
 
     def info(self) -> Info:
         i = Info()

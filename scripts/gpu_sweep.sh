@@ -2,7 +2,7 @@ mkdir -p gpurun_out
 
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -15 gpurun_out/pytest_gpu.log
 B="timeout 300 python bench.py --no-cpu-baseline --steps 100 --warmup 10"
-for cfg in "M3B_VARIANT=tma" "M3B_VARIANT=1" "M3B_VARIANT=tma M3B_TMA_G=4" "M3B_VARIANT=tma M3B_TILE=128 M3B_TMA_G=8" "M3B_VARIANT=tma M3B_TILE=128 M3B_TMA_G=16" "M3B_VARIANT=tma M3B_TILE=128 M3B_TMA_G=8 M3B_TMA_BLOCKS_PER_SM=2" "M3B_VARIANT=tma M3B_TILE=512 M3B_TMA_G=4" "M3B_VARIANT=tma M3B_TMA_STAGES=3" "M3B_VARIANT=tma M3B_TMA_STAGES=4"; do
+for cfg in "M3B_VARIANT=tma" "M3B_VARIANT=tma M3B_TILE=512" "M3B_VARIANT=tma M3B_TILE=256" "M3B_VARIANT=1 M3B_TILE=256" "M3B_VARIANT=tma M3B_TMA_STAGES=4" "M3B_VARIANT=tma M3B_TMA_STAGES=3"; do
   echo "== $cfg" >> gpurun_out/sweep.log
   env $cfg $B 2>&1 | python -c "
 import sys, json

@@ -80,7 +80,7 @@ def _check_step(w, mono, osh, gsh, check_weights=True):
     return o_llh, g_llh
 
 
-@pytest.mark.parametrize("tile", [128, 256, 512])
+@pytest.mark.parametrize("tile", [128, 256, 512, 1024])
 def test_cfg1_shape_parity(tile):
     """BASELINE config 1 shape (10 TSpline3 K=5 + 2 TF1, 1-D 50 bins, Poisson), reduced to 30k events."""
     w = synth.CFG1.scaled(30_011)          # ragged last tile
@@ -275,3 +275,40 @@ def test_full_size_cfg2_properties():
     gsd["pars"][:] = gd["pars"]; gsd["norm"][:] = nm
     gsub.Reweight(); gsub.GetLikelihood()
     np.testing.assert_allclose(gsub.GetMCArray(), osh.mc, rtol=ORDER_RTOL if _exact() else HIST_RTOL, atol=1e-12)
+
+
+def test_zero_copy_oscillation_weights_match_the_copied_path(oracle_build):
+    """Oscillation weights in pinned host memory are streamed by the kernel's bulk copies (no H2D pass);
+    the result must be identical to the cudaMemcpy path, also for the ragged last tile, and the
+    weights must stay on the device for later steps that pass no array."""
+    if oracle_build != "serial":
+        pytest.skip("device-vs-device comparison: one oracle build is enough")
+    w = synth.CFG1.scaled(70_001)
+    typ, npts, cx = synth.param_layout(w)
+    spl, ev = synth.make_splines(w, 0, w.n_events), synth.make_events(w, 0, w.n_events)
+    out = []
+    for pinned in (False, True):
+        h = lib.Handle(update_w2=True, flags=lib.FLAG_KEEP_EVENT_WEIGHTS)
+        h.upload_spline_monolith(w.n_params, w.n_knots, cx, npts, spl)
+        h.upload_binning(synth.bin_edges(w))
+        h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0,
+                        ev["static_w"])
+        res, keep = [], []
+        for step in range(3):
+            osc = synth.make_osc(w, step)
+            keep.append(osc)                    # registered memory must outlive the handle
+            if pinned:
+                h.register_host_buffer(osc)
+            sp, nm = synth.proposal(w, step)
+            h.step(sp, nm, osc)
+            llh = h.llh()
+            res.append((llh, h.read_hist()[0].copy(), h.read_event_weights()[1].copy()))
+            sp2, nm2 = synth.proposal(w, step + 10)
+            h.step(sp2, nm2, None)              # keeps the weights of the previous call
+            res.append((h.llh(), h.read_hist()[0].copy(), h.read_event_weights()[1].copy()))
+        out.append(res)
+        h.close()
+    for (l0, m0, w0), (l1, m1, w1) in zip(*out):
+        np.testing.assert_array_equal(w0, w1)
+        np.testing.assert_allclose(m0, m1, rtol=ORDER_RTOL, atol=1e-13)
+        assert l0 == pytest.approx(l1, rel=1e-10, abs=1e-9)
