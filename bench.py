@@ -164,13 +164,6 @@ def main_reference(args):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
-class _DevArray:
-    """torch view of a raw device pointer (plumbing for the NCCL all-reduce)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-
 def main_b200(args):
     import torch
     from mach3_b200 import lib, synth
@@ -194,8 +187,8 @@ def main_b200(args):
     w = pick_workload(args)
     E = w.n_events
     # contiguous, tile-aligned event shards
-    per = ((E + world - 1) // world + 1023) // 1024 * 1024
-    e0, e1 = min(E, rank * per), min(E, (rank + 1) * per)
+    from mach3_b200 import sharding
+    e0, e1 = sharding.shard_range(E, world, rank)
     n_local = e1 - e0
 
     flags = lib.FLAG_NO_FUSED_LLH if world > 1 else 0
@@ -220,28 +213,14 @@ def main_b200(args):
     h.upload_osc(osc_bufs[0])
     t_setup = time.perf_counter() - t_setup
 
-    hist_t = None
-    if world > 1:
-        if args.exchange == "peer":
-            mine = h.peer_export(rank, world)
-            allh = [None] * world
-            dist.all_gather_object(allh, mine)
-            for r in range(world):
-                h.peer_import(r, allh[r])
-        ptr, nb, _ = h.hist_device_ptr()
-        hist_t = torch.as_tensor(_DevArray(ptr, 2 * nb), device=f"cuda:{local}")
+    sh = sharding.ShardedSampleHandler(h, dist, args.exchange, device=f"cuda:{local}") if world > 1 else None
 
     def step(k, osc=None):
         sp, nm = props[k]
         if world == 1:
             h.step(sp, nm, osc)
-        elif args.exchange == "peer":
-            h.step(sp, nm, osc, mode="peer")
         else:
-            h.step(sp, nm, osc, mode="fill")
-            _, nb, live = h.hist_device_ptr()
-            dist.all_reduce(hist_t[: (2 * nb if live else nb)])
-            h.llh_from_hist()
+            sh.Reweight(sp, nm, osc)
 
     W, K = args.warmup, args.steps
     props = {k: synth.proposal(w, k) for k in range(-1, 2 * (W + K) + 16)}
@@ -315,6 +294,21 @@ def main_b200(args):
         alg_bytes_local = n_local * w.bytes_per_event        # SURVEY §8d per-event figure x events of one launch
         achieved = alg_bytes_local / (kern_avg * 1e-3) / 1e9
         step_bytes = 12 * w.n_params + 4 * w.n_norm_params
+        kname = "m3b::fill_tma_kernel" if info.kernel_variant < 0 else f"m3b::fill_kernel<{info.tile_events},variant {info.kernel_variant}>"
+        # DRAM traffic per launch from the committed `ncu --set full` capture of this same command
+        traffic, traffic_src = None, None
+        prof = os.path.join(ROOT, "profiles", "r01_ncu_full_fill_tma_cfg2.json")
+        if world == 1 and w is synth.CFG2 and info.kernel_variant < 0 and os.path.exists(prof):
+            try:
+                pj = json.load(open(prof))
+                rd = [float(x) for x in pj["dram__bytes_read.sum"]["per_launch"]]
+                wr = [float(x) for x in pj["dram__bytes_write.sum"]["per_launch"]]
+                scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+                traffic = (sum(rd) / len(rd)) * scale[pj["dram__bytes_read.sum"]["unit"]] + \
+                          (sum(wr) / len(wr)) * scale[pj["dram__bytes_write.sum"]["unit"]]
+                traffic_src = "profiles/r01_ncu_full_fill_tma_cfg2.json (dram__bytes_read.sum + dram__bytes_write.sum, mean of 3 launches)"
+            except Exception:
+                traffic = None
         line = {
             "metric": "reweighted events/s per MCMC step (reweight+fill+LLH)",
             "value": E / (ms_step * 1e-3), "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -323,15 +317,15 @@ def main_b200(args):
             "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
             "config": {"workload": w.name, "events": E, "events_per_gpu": n_local, "responses_per_event": w.n_params,
                        "bins": w.n_bins, "tile_events": info.tile_events, "grid_blocks": info.grid_blocks,
-                       "smem_bytes": info.smem_bytes, "exchange": ("none" if world == 1 else args.exchange),
+                       "smem_bytes": info.smem_bytes, "tma_stages": info.tma_stages, "exchange": ("none" if world == 1 else args.exchange),
                        "l2": "inputs larger than L2: %.0f MB of coefficient rows stream per step per GPU, fresh "
                              "proposal (different segments) every step" % (info.active_bytes_per_step / 1e6),
                        "device_bytes": info.device_bytes, "setup_s": round(t_setup, 2), "host_cpu_affinity": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "kernel": "m3b::fill_kernel", "kernel_ms": kern_avg, "algorithmic_bytes_per_launch": alg_bytes_local,
-                         "loaded_bytes_per_launch": info.active_bytes_per_step, "traffic": None},
+                         "kernel": kname, "kernel_ms": kern_avg, "algorithmic_bytes_per_launch": alg_bytes_local,
+                         "loaded_bytes_per_launch": info.active_bytes_per_step, "traffic": traffic, "traffic_source": traffic_src},
             "e2e": {"value": E / (ms_e2e / K * 1e-3), "unit": "events/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(4 * n_local + step_bytes), "d2h_bytes_per_step": int(8 * (1 + w.n_samples)),
                     "api": "m3b_step(host pars, host norms, host osc weights in pinned memory) + m3b_llh(); the osc weights "

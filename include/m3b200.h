@@ -201,6 +201,8 @@ typedef struct {
   uint64_t device_bytes;          /* HBM held by the handle                                       */
   uint64_t active_bytes_per_step; /* coefficient + event-table bytes one step actually loads       */
   uint64_t steps, kernel_launches;
+  int32_t kernel_variant;         /* -1: streaming TMA kernel (default); 0..5: register-streaming variants */
+  int32_t tma_stages;             /* 32 KB shared-memory stages of the coefficient ring                    */
 } m3b_info;
 M3B_API int m3b_get_info(m3b_handle* h, m3b_info* out);
 /* CUDA-event timing of the fill kernel alone, on the handle's stream (the reference has only a

@@ -1178,6 +1178,7 @@ M3B_API int m3b_get_info(m3b_handle* h, m3b_info* out) {
   per_evt += 2ull * h->norm_slots;
   out->active_bytes_per_step = h->active_coef_bytes + per_evt * static_cast<uint64_t>(h->e_pad);
   out->steps = h->steps; out->kernel_launches = h->launches;
+  out->kernel_variant = h->use_tma ? -1 : h->variant; out->tma_stages = h->use_tma ? h->tma_stages : 0;
   return M3B_OK;
 }
 

@@ -39,7 +39,7 @@ class Info(C.Structure):
                 ("n_samples", C.c_int32), ("n_signatures", C.c_int32), ("tile_events", C.c_int32),
                 ("grid_blocks", C.c_int32), ("smem_bytes", C.c_int32), ("hist_in_smem", C.c_int32),
                 ("device_bytes", C.c_uint64), ("active_bytes_per_step", C.c_uint64), ("steps", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("kernel_variant", C.c_int32), ("tma_stages", C.c_int32)]
 
 
 class M3BError(RuntimeError):

@@ -1,0 +1,99 @@
+"""Launched by torchrun (one process per GPU): event-sharded fill + histogram exchange + -lnL on the
+B200s against the single-process CPU oracle on the same seeded workload.  Both exchanges
+(NCCL all-reduce on the library's buffer; the library's own peer-memory push) must give every rank
+the same -lnL, equal to the oracle's within the north_star tolerance (1e-6 relative).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multigpu/parity_ranks.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from mach3_b200 import lib, sharding, synth  # noqa: E402
+from oracle import binding as O              # noqa: E402  (the checker)
+
+LLH_RTOL = 1e-6
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_events = int(os.environ.get("M3B_PARITY_EVENTS", "150001"))
+    w = synth.CFG3.scaled(n_events)
+    e0, e1 = sharding.shard_range(w.n_events, world, rank)
+    typ, npts, cx = synth.param_layout(w)
+    steps = [-1, 0, 1, 2, 3]
+
+    # oracle, whole workload, rank 0 only
+    ref = None
+    if rank == 0:
+        O.set_multithread(False)
+        mono, osh, _ = O.build_from_workload(w, update_w2=True, test_statistic=lib.BARLOW_BEESTON)
+        sp, nm = synth.proposal(w, -1)
+        mono.set_params(sp); osh.norm_vals[:] = nm
+        osh.Reweight()
+        data = np.random.default_rng(11).poisson(osh.mc).astype(np.float64)
+        osh.AddData(data)
+        ref = []
+        for s in steps:
+            sp, nm = synth.proposal(w, s)
+            mono.set_params(sp); osh.norm_vals[:] = nm
+            osh.Reweight()
+            ref.append((osh.GetLikelihood(), osh.mc.copy(), osh.w2.copy()))
+    box = [data if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    data = box[0]
+
+    ok = True
+    for exchange in ("nccl", "peer"):
+        h = lib.Handle(device=local, test_statistic=lib.BARLOW_BEESTON, update_w2=True, flags=lib.FLAG_NO_FUSED_LLH)
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        h.splines_begin(w.n_params, w.n_knots, cx, npts, e1 - e0)
+        if e1 > e0:
+            h.splines_append(synth.make_splines(w, e0, e1))
+        h.splines_end()
+        h.upload_binning(synth.bin_edges(w))
+        ev = synth.make_events(w, e0, e1)
+        h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0,
+                        ev["static_w"])
+        h.upload_osc(synth.make_osc(w, 0, e0, e1))
+        h.upload_data(data)
+        sh = sharding.ShardedSampleHandler(h, dist, exchange, device=f"cuda:{local}")
+        for i, s in enumerate(steps):
+            sp, nm = synth.proposal(w, s)
+            sh.Reweight(sp, nm)
+            llh = sh.GetLikelihood()
+            mc, w2 = h.read_hist()
+            t = torch.tensor([llh], dtype=torch.float64, device=f"cuda:{local}")
+            allv = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allv, t)
+            vals = [float(v.item()) for v in allv]
+            if rank == 0:
+                r_llh, r_mc, r_w2 = ref[i]
+                same = all(v == vals[0] for v in vals) if exchange == "peer" else all(abs(v - vals[0]) <= 1e-12 * abs(vals[0]) for v in vals)
+                good = abs(llh - r_llh) <= LLH_RTOL * abs(r_llh) + 1e-9 and np.allclose(mc, r_mc, rtol=1e-10, atol=1e-10) \
+                    and np.allclose(w2, r_w2, rtol=1e-10, atol=1e-10) and same
+                ok &= bool(good)
+                print(f"[{exchange}] step {s:2d}: -lnL gpu {llh:.9f} oracle {r_llh:.9f} rel {abs(llh - r_llh) / max(abs(r_llh), 1e-300):.2e} "
+                      f"ranks agree {same} -> {'OK' if good else 'FAIL'}", flush=True)
+        dist.barrier()
+        h.close()
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    if not int(flag.item()):
+        raise SystemExit(1)
+    if rank == 0:
+        print("MULTI-GPU PARITY OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()
