@@ -1,0 +1,227 @@
+// SampleHandlerB200.h -- the fused B200 path behind MaCh3's SampleHandlerBase virtuals.
+//
+//   template <class FDBase> class SampleHandlerB200 : public FDBase
+//
+// FDBase is the experiment's concrete SampleHandlerFD subclass (the class that implements SetupSplines,
+// SetupFDMC, ... -- Samples/SampleHandlerFD.h:189-304).  The adapter overrides exactly the three
+// virtuals every fitter calls (Samples/SampleHandlerBase.h:37-90; Fitters/MR2T2.cpp:62-74):
+//
+//     void   Reweight()                       Samples/SampleHandlerFD.cpp:316-343
+//     double GetLikelihood() const            :1284-1300     (returns -lnL, like the reference)
+//     double GetSampleLikelihood(int) const   :1262-1281
+//
+// and turns the per-event pointer soup the reference builds in Initialise()
+// (Samples/SampleHandlerFD.cpp:169-202; EventInfo, Samples/FarDetectorCoreInfoStruct.h:82-126) into the
+// flat index tables of libm3b200 (include/m3b200.h) ONCE, in MoveToB200():
+//
+//     EventInfo::norm_pointers[j]          -> norm_idx = ptr - <base of ParameterHandlerBase::_fPropVal>
+//     EventInfo::total_weight_pointers[k]  -> classified by address:
+//           inside SMonolith::cpu_total_weights       the event's spline weight: produced on the device, dropped
+//           inside the oscillator's weight array      osc_idx = ptr - base          (SampleHandlerFD.cpp:1108-1122)
+//           &M3::Zero / &M3::Unity                    static factor 0 / 1           (:1128-1131)
+//           anything else                             read now, folded into the event's static weight
+//     EventInfo::KinVar[d]                 -> kin[d][e] = *ptr  (bins are found on the device; functional
+//                                             "shift" parameters, :545-564, are NOT supported by this adapter)
+//     EventInfo::NominalSample             -> sample_id
+//     BinningHandler (GetNDim/GetBinEdges) -> m3b_upload_binning            (uniform binning only)
+//     SplineMonoStruct + SMonolith arrays  -> m3b_upload_spline_monolith    (pass them through SetMonolith())
+//
+// Per step Reweight() = [Oscillator->Evaluate()] + ONE m3b_step call: FindSplineSegment (host, the
+// reference's own history-dependent rule) -> fused evaluate/product/fill/-lnL kernel.  Nothing but
+// the -lnL scalar comes back; SampleHandlerFD_array / _array_w2 are refreshed lazily by SyncHostArrays()
+// (call it before GetMCArray()/PrintRates()/plotting).
+//
+// The template keeps this header compilable against the real MaCh3 (needs ROOT; not available in this
+// repository's build image) and against the mock in tests/adapters/mock_mach3.h, which the repository's
+// own test builds and runs on the B200 (tests/test_adapter_gpu.py).
+#pragma once
+#include "m3b200.h"
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace m3b200 {
+
+// What the adapter needs from the experiment side that SampleHandlerFD keeps private or spreads over
+// several objects.  All pointers are the reference's own arrays; the library copies on upload.
+struct MonolithArrays {               // Splines/SplineCommon.h:30-50, Splines/SplineMonolith.h:96-137
+  int n_params = 0, max_knots = 0;
+  const float* coeff_x = nullptr;             // SplineMonoStruct::coeff_x           [n_params*max_knots]
+  const int16_t* n_pts = nullptr;             // FastSplineInfo::nPts per parameter  [n_params]
+  const uint32_t* nParamPerEvent = nullptr;   // SMonolith::cpu_nParamPerEvent       [2*n_events]
+  const int16_t* paramNo_arr = nullptr;       // SplineMonoStruct::paramNo_arr
+  const uint32_t* nKnots_arr = nullptr;       // SplineMonoStruct::nKnots_arr
+  uint32_t total_knots = 0;
+  const float* coeff_many = nullptr;          // SplineMonoStruct::coeff_many        [total_knots*4]
+  const uint32_t* nParamPerEvent_tf1 = nullptr;
+  const int16_t* paramNo_tf1 = nullptr;       // SMonolith::cpu_paramNo_TF1_arr
+  const float* coeff_tf1 = nullptr;           // SMonolith::cpu_coeff_TF1_many       [n_tf1*2]
+  std::vector<const double*> spline_par_pointers;   // what SMonolith::setSplinePointers receives
+  const float* cpu_total_weights = nullptr;   // SMonolith::cpu_total_weights (address range only; never read)
+};
+
+struct PointerBases {
+  const double* norm_base = nullptr;  int n_norm = 0;        // ParameterHandlerBase::_fPropVal.data(), size
+  const float* osc_base = nullptr;    int64_t n_osc = 0;     // the oscillator's weight array (may be null)
+  const float* zero = nullptr;                               // &M3::Zero
+  const float* unity = nullptr;                              // &M3::Unity
+};
+
+template <class FDBase>
+class SampleHandlerB200 : public FDBase {
+ public:
+  using FDBase::FDBase;
+  ~SampleHandlerB200() override { if (h_) m3b_destroy(h_); }
+
+  // Call once after the base class finished Initialise() (events, binning, splines, pointers wired).
+  void MoveToB200(const MonolithArrays& mono, const PointerBases& bases, int cuda_device = 0) {
+    m3b_config cfg{};
+    cfg.device = cuda_device;
+    cfg.test_statistic = static_cast<int32_t>(this->fTestStatistic);   // enum TestStatistic == m3b_test_statistic
+    cfg.update_w2 = this->UpdateW2 ? 1 : 0;
+    check(m3b_create(&cfg, &h_), "m3b_create");
+    const int64_t E = static_cast<int64_t>(this->GetNEvents());
+    bases_ = bases;
+    spline_ptrs_ = mono.spline_par_pointers;
+    spline_vals_.assign(spline_ptrs_.size(), 0.0);
+
+    // --- spline monolith: the reference's arrays, as they are
+    if (mono.n_params > 0)
+      check(m3b_upload_spline_monolith(h_, mono.n_params, mono.max_knots, mono.coeff_x, mono.n_pts, E,
+                                       mono.nParamPerEvent, mono.paramNo_arr, mono.nKnots_arr, mono.total_knots,
+                                       mono.coeff_many, mono.nParamPerEvent_tf1, mono.paramNo_tf1, mono.coeff_tf1),
+            "m3b_upload_spline_monolith");
+
+    // --- binning (BinningHandler: uniform arm, Samples/BinningHandler.cpp:257-277)
+    const int nS = static_cast<int>(this->GetNsamples());
+    std::vector<int32_t> ndim(nS), nbins(static_cast<size_t>(nS) * 4, 0);
+    std::vector<double> edges;
+    int max_dim = 0;
+    for (int s = 0; s < nS; ++s) {
+      ndim[s] = this->GetBinningHandler()->GetNDim(s);
+      if (ndim[s] < 1 || ndim[s] > 4) throw std::runtime_error("SampleHandlerB200: 1..4 binning dimensions per sample");
+      max_dim = ndim[s] > max_dim ? ndim[s] : max_dim;
+      for (int d = 0; d < ndim[s]; ++d) {
+        const std::vector<double> e = this->GetBinningHandler()->GetBinEdges(s, d);
+        nbins[static_cast<size_t>(s) * 4 + d] = static_cast<int32_t>(e.size()) - 1;
+        edges.insert(edges.end(), e.begin(), e.end());
+      }
+    }
+    check(m3b_upload_binning(h_, nS, ndim.data(), nbins.data(), edges.data()), "m3b_upload_binning");
+    n_bins_ = this->GetBinningHandler()->GetNBins();
+
+    // --- events: pointers -> indices
+    size_t max_norm = 0;
+    for (int64_t e = 0; e < E; ++e) max_norm = std::max(max_norm, this->MCSamples[e].norm_pointers.size());
+    if (max_norm > 16) throw std::runtime_error("SampleHandlerB200: more than 16 norm pointers on one event");
+    std::vector<int32_t> sample_id(E), osc_idx(E, 0);
+    std::vector<double> kin(static_cast<size_t>(max_dim) * E, 0.0);
+    std::vector<int16_t> norm_idx(static_cast<size_t>(max_norm) * E, -1);
+    std::vector<float> static_w(E, 1.0f);
+    bool any_osc = false, all_osc = true;
+    for (int64_t e = 0; e < E; ++e) {
+      const auto& ev = this->MCSamples[e];
+      sample_id[e] = ev.NominalSample;
+      for (size_t d = 0; d < ev.KinVar.size() && d < static_cast<size_t>(max_dim); ++d) kin[d * E + e] = *ev.KinVar[d];
+      for (size_t j = 0; j < ev.norm_pointers.size(); ++j) {
+        const std::ptrdiff_t off = ev.norm_pointers[j] - bases.norm_base;
+        if (off < 0 || off >= bases.n_norm) throw std::runtime_error("SampleHandlerB200: norm pointer outside the parameter array");
+        norm_idx[e * max_norm + j] = static_cast<int16_t>(off);
+      }
+      bool has_osc = false;
+      for (const auto* p : ev.total_weight_pointers) {
+        if (mono.cpu_total_weights && p >= mono.cpu_total_weights && p < mono.cpu_total_weights + E) {
+          if (p - mono.cpu_total_weights != e) throw std::runtime_error("SampleHandlerB200: event points at another event's spline weight");
+        } else if (bases.osc_base && p >= bases.osc_base && p < bases.osc_base + bases.n_osc) {
+          if (has_osc) throw std::runtime_error("SampleHandlerB200: two oscillation weights on one event");
+          osc_idx[e] = static_cast<int32_t>(p - bases.osc_base);
+          has_osc = true;
+        } else if (p == bases.zero) {
+          static_w[e] = 0.0f;                 // NC event with flavour change (SampleHandlerFD.cpp:1128-1131)
+        } else if (p != bases.unity) {
+          static_w[e] *= static_cast<float>(*p);    // experiment-specific constant weight
+        }
+      }
+      any_osc |= has_osc;
+      all_osc &= has_osc;
+    }
+    if (any_osc && !all_osc) {
+      // events without an oscillation weight read a slot that always holds 1.0f
+      extra_unity_slot_ = true;
+      for (int64_t e = 0; e < E; ++e) {
+        bool has = false;
+        for (const auto* p : this->MCSamples[e].total_weight_pointers)
+          has |= (bases.osc_base && p >= bases.osc_base && p < bases.osc_base + bases.n_osc);
+        if (!has) osc_idx[e] = static_cast<int32_t>(bases.n_osc);
+      }
+    }
+    n_osc_dev_ = any_osc ? bases.n_osc + (extra_unity_slot_ ? 1 : 0) : 0;
+    check(m3b_upload_events(h_, E, sample_id.data(), kin.data(), static_cast<int32_t>(max_norm),
+                            max_norm ? norm_idx.data() : nullptr, bases.n_norm, any_osc ? 1 : 0,
+                            any_osc ? osc_idx.data() : nullptr, n_osc_dev_, static_w.data()),
+          "m3b_upload_events");
+    if (any_osc) osc_stage_.assign(static_cast<size_t>(n_osc_dev_), 1.0f);
+    check(m3b_upload_data(h_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_upload_data");
+    ready_ = true;
+  }
+
+  // SampleHandlerFD::AddData (Samples/SampleHandlerFD.cpp:955-1044) changed SampleHandlerFD_data
+  void DataChanged() { check(m3b_upload_data(h_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_upload_data"); }
+
+  // ---- the three virtuals the fitters call -------------------------------------------------------
+  void Reweight() override {
+    if (!ready_) { FDBase::Reweight(); return; }           // before MoveToB200: the reference's own path
+    if (this->Oscillator) this->Oscillator->Evaluate();    // NuOscillator stays where it is (input array)
+    for (size_t p = 0; p < spline_ptrs_.size(); ++p) spline_vals_[p] = *spline_ptrs_[p];
+    const float* osc = nullptr;
+    if (n_osc_dev_ > 0) {
+      std::copy(bases_.osc_base, bases_.osc_base + bases_.n_osc, osc_stage_.begin());
+      osc = osc_stage_.data();
+    }
+    check(m3b_step(h_, spline_vals_.empty() ? nullptr : spline_vals_.data(), bases_.norm_base, osc), "m3b_step");
+    host_arrays_stale_ = true;
+    if (!this->UpdateW2) this->FirstTimeW2 = false;        // Samples/SampleHandlerFD.cpp:342
+  }
+
+  double GetLikelihood() const override {
+    if (!ready_) return FDBase::GetLikelihood();
+    double total = 0;
+    check(m3b_llh(h_, &total, nullptr), "m3b_llh");
+    return total;
+  }
+
+  double GetSampleLikelihood(const int isample) const override {
+    if (!ready_) return FDBase::GetSampleLikelihood(isample);
+    std::vector<double> per(static_cast<size_t>(const_cast<SampleHandlerB200*>(this)->GetNsamples()));
+    double total = 0;
+    check(m3b_llh(h_, &total, per.data()), "m3b_llh");
+    return per.at(static_cast<size_t>(isample));
+  }
+
+  // Lazy host mirrors of SampleHandlerFD_array / _array_w2 (Samples/SampleHandlerFD.h:337-341).
+  void SyncHostArrays() {
+    if (!ready_ || !host_arrays_stale_) return;
+    check(m3b_read_hist(h_, this->SampleHandlerFD_array.data(), this->SampleHandlerFD_array_w2.data()), "m3b_read_hist");
+    host_arrays_stale_ = false;
+  }
+
+  m3b_handle* handle() const { return h_; }
+
+ private:
+  void check(int rc, const char* what) const {
+    if (rc != M3B_OK) throw std::runtime_error(std::string("SampleHandlerB200: ") + what + ": " + m3b_last_error(h_));
+  }
+  m3b_handle* h_ = nullptr;
+  bool ready_ = false, host_arrays_stale_ = false, extra_unity_slot_ = false;
+  int n_bins_ = 0;
+  int64_t n_osc_dev_ = 0;
+  PointerBases bases_{};
+  std::vector<const double*> spline_ptrs_;
+  std::vector<double> spline_vals_;
+  std::vector<float> osc_stage_;
+};
+
+}  // namespace m3b200

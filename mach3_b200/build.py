@@ -86,6 +86,10 @@ def build_reference_gpu(force=False, verbose=False):
     if not os.path.isdir(REFERENCE) or not os.path.exists(mk):
         return None
     _run(["make", "-C", os.path.dirname(mk), "-B" if force else "-s"], verbose)
+    # the drop-in SMonolithGPU adapter, compiled against the reference's own header + the same harness
+    amk = os.path.join(ROOT, "adapters", "Makefile")
+    if os.path.exists(amk):
+        _run(["make", "-C", os.path.dirname(amk), "-B" if force else "-s"], verbose)
     return os.path.join(ORACLE, "_ref")
 
 

@@ -934,8 +934,9 @@ M3B_API int m3b_step_segments(m3b_handle* h, const float* param_values, const in
   REQUIRE(h, M3B_ERR_INVALID, "null handle");
   REQUIRE(h->P == 0 || (param_values && segments), M3B_ERR_INVALID, "m3b_step_segments: null argument");
   for (int p = 0; p < h->P; ++p) {
-    REQUIRE(segments[p] >= 0 && segments[p] < std::max<int>(1, h->nseg[p]), M3B_ERR_INVALID, "m3b_step_segments: segment out of range");
-    h->segments[p] = segments[p]; h->curr_segment[p] = segments[p]; h->param_values[p] = param_values[p];
+    const int16_t sg = h->nseg[p] > 0 ? segments[p] : 0;
+    REQUIRE(sg >= 0 && sg < std::max<int>(1, h->nseg[p]), M3B_ERR_INVALID, "m3b_step_segments: segment out of range");
+    h->segments[p] = sg; h->curr_segment[p] = sg; h->param_values[p] = param_values[p];
   }
   return enqueue_step(h, h->param_values.data(), h->segments.data(), norm_pars, osc_w,
                       (h->cfg.flags & M3B_FLAG_NO_FUSED_LLH) ? kFillOnly : kFused);
@@ -977,8 +978,10 @@ M3B_API int m3b_eval_weights(m3b_handle* h, const float* param_values, const int
   if (rc != M3B_OK) return rc;
   REQUIRE(h->d_evt_spline_w, M3B_ERR_STATE, "m3b_eval_weights: create the handle with M3B_FLAG_KEEP_EVENT_WEIGHTS");
   for (int p = 0; p < h->P; ++p) {
-    REQUIRE(segments[p] >= 0 && segments[p] < std::max<int>(1, h->nseg[p]), M3B_ERR_INVALID, "m3b_eval_weights: segment out of range");
-    h->segments[p] = segments[p]; h->curr_segment[p] = segments[p]; h->param_values[p] = param_values[p];
+    // a parameter without any TSpline3 response has no knots here; whatever the caller's segment is, it is unused
+    const int16_t sg = h->nseg[p] > 0 ? segments[p] : 0;
+    REQUIRE(sg >= 0 && sg < std::max<int>(1, h->nseg[p]), M3B_ERR_INVALID, "m3b_eval_weights: segment out of range");
+    h->segments[p] = sg; h->curr_segment[p] = sg; h->param_values[p] = param_values[p];
   }
   std::vector<double> ones(static_cast<size_t>(std::max(h->n_norm_values, 1)), 1.0);
   rc = enqueue_step(h, h->param_values.data(), h->segments.data(), ones.data(), nullptr, kWeightsOnly);

@@ -25,13 +25,19 @@ struct RefMono {
 
 extern "C" {
 
+#ifdef M3REF_ANY_NPARAMS   /* harness linked against adapters/SMonolithGPU_m3b200.cu: no compile-time limit */
+__attribute__((visibility("default"))) int m3ref_compiled_nparams(void) { return -1; }
+#else
 __attribute__((visibility("default"))) int m3ref_compiled_nparams(void) { return NSplines_GPU; }
+#endif
 
 __attribute__((visibility("default"))) void* m3ref_create(
     int n_params, int max_knots, const float* coeff_x, unsigned n_events, const unsigned* nParamPerEvent,
     const short* paramNo_arr, const unsigned* nKnots_arr, unsigned total_knots, const float* coeff_many,
     const unsigned* nParamPerEvent_tf1, const short* paramNo_tf1, const float* coeff_tf1) {
+#ifndef M3REF_ANY_NPARAMS
   if (n_params != NSplines_GPU) return nullptr;      // the reference would `throw;` (gpuSplineUtils.cu:211-216)
+#endif
   RefMono* r = new RefMono();
   r->n_params = n_params; r->n_events = n_events;
   unsigned ns = 0, nt = 0;

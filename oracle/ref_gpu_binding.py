@@ -19,6 +19,11 @@ def available(n_params):
     return os.path.exists(lib_path(n_params))
 
 
+def adapter_path():
+    """adapters/SMonolithGPU_m3b200.cu (the drop-in class on top of libm3b200) + the same harness."""
+    return os.path.join(_HERE, "_ref", "libm3adapter_gpu.so")
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -26,8 +31,8 @@ def _p(a):
 class RefSMonolithGPU:
     """The reference's SMonolithGPU driven like SMonolith does (MoveToGPU / Evaluate)."""
 
-    def __init__(self, n_params, max_knots, coeff_x, spl):
-        L = C.CDLL(lib_path(n_params))
+    def __init__(self, n_params, max_knots, coeff_x, spl, adapter=False):
+        L = C.CDLL(adapter_path() if adapter else lib_path(n_params))
         L.m3ref_create.restype = C.c_void_p
         L.m3ref_total_weights.restype = C.c_void_p
         L.m3ref_time_ms.restype = C.c_double
@@ -35,7 +40,7 @@ class RefSMonolithGPU:
         L.m3ref_time_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.m3ref_total_weights.argtypes = [C.c_void_p]
         L.m3ref_destroy.argtypes = [C.c_void_p]
-        assert L.m3ref_compiled_nparams() == n_params
+        assert L.m3ref_compiled_nparams() == (-1 if adapter else n_params)
         self.L = L
         self.n_events = int(spl["n_events"])
         self.n_params = n_params
