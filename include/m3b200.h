@@ -109,6 +109,27 @@ M3B_API int m3b_upload_spline_monolith(m3b_handle* h, int32_t n_params, int32_t 
                                        const uint32_t* nParamPerEvent_tf1, const int16_t* paramNo_tf1,
                                        const float* coeff_tf1);
 
+/* ---- binned splines --------------------------------------------------------------------------
+ * The other SplineBase implementation, BinnedSplineHandler (Splines/BinnedSplineHandler.h:110-135,
+ * Evaluate/CalcSplineWeights .cpp:295-341), _LOW_MEMORY_STRUCTS_ build (M3::float_t = float).  Either this
+ * or the event-by-event monolith above, per handle.  Arrays are the reference's own:
+ *   knot_x[n_params*max_knots], n_pts[n_params]   FastSplineInfo::xPts / nPts per spline parameter
+ *   uniquesplinevec_Monolith[n_slots]             parameter of every weightvec_Monolith slot
+ *   coeffindexvec[n_slots]                        first knot of the slot's spline in the coefficient arrays
+ *   uniquecoeffindices[n_unique]                  the non-flat slots (the only ones evaluated, .cpp:311)
+ *   manycoeff_arr[n_coeff*4] {y,b,c,d}, xcoeff_arr[n_coeff]   per knot per spline (x is per spline, .cpp:329)
+ * m3b_upload_event_binned_splines (after m3b_upload_events): the event's pointers into weightvec_Monolith
+ *   (BinnedSplineHandler::retPointer, wired at Samples/SampleHandlerFD.cpp:1196-1242) as slot indices, in
+ *   pointer order; they are multiplied after the oscillation weight and before the static weight.
+ * m3b_read_binned_weights: lazy host mirror of weightvec_Monolith (1.0 for flat slots).                   */
+M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t max_knots, const float* knot_x,
+                                      const int16_t* n_pts, int64_t n_slots, const int32_t* uniquesplinevec_Monolith,
+                                      const int32_t* coeffindexvec, int64_t n_unique, const int32_t* uniquecoeffindices,
+                                      int64_t n_coeff, const float* manycoeff_arr, const float* xcoeff_arr);
+M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, const uint32_t* n_per_event,
+                                            const int32_t* spline_index);
+M3B_API int m3b_read_binned_weights(m3b_handle* h, float* weightvec_Monolith /* [n_slots] */);
+
 /* ---- binning, events, data -------------------------------------------------------------------
  * m3b_upload_binning: BinningHandler's uniform binning (Samples/BinningHandler.cpp:341-355,
  *   SampleBinningInfo Samples/SampleStructs.h:232-676): per sample n_dim[s] axes, nbins[s*4+d],
@@ -201,7 +222,8 @@ typedef struct {
   uint64_t device_bytes;          /* HBM held by the handle                                       */
   uint64_t active_bytes_per_step; /* coefficient + event-table bytes one step actually loads       */
   uint64_t steps, kernel_launches;
-  int32_t kernel_variant;         /* -1: streaming TMA kernel (default); 0..5: register-streaming variants */
+  int32_t kernel_variant;         /* -1: streaming TMA kernel (default); 0..5: register-streaming variants;  */
+                                  /* -2: binned-spline kernels                                               */
   int32_t tma_stages;             /* 32 KB shared-memory stages of the coefficient ring                    */
 } m3b_info;
 M3B_API int m3b_get_info(m3b_handle* h, m3b_info* out);

@@ -2,169 +2,10 @@
 // Owns all device state; re-tiles the reference's AoS monolith into the tiled SoA layout;
 // mirrors SplineBase::FindSplineSegment on the host (O(nParams), history-dependent); enqueues one
 // fused kernel per step.  No CPU fallback: every compute entry point needs the sm_100 device.
-#include "m3b200.h"
-#include "m3b_internal.h"
-
-#include <algorithm>
-#include <cstdio>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
-
-using namespace m3b;
+#include "m3b_handle.h"
 
 static thread_local std::string g_last_error;
-
-struct m3b_handle {
-  m3b_config cfg{};
-  int device = 0;
-  int sm_count = 148;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  std::string err;
-
-  // ---- spline parameters (FastSplineInfo, Splines/SplineStructs.h:21-44)
-  int P = 0, Kmax = 0;
-  std::vector<float> coeff_x;
-  std::vector<int16_t> n_pts;
-  std::vector<int16_t> curr_segment;     // FastSplineInfo::CurrSegment
-  std::vector<int16_t> segments;         // SplineBase::SplineSegments
-  std::vector<float> param_values;       // SplineBase::ParamValues
-  std::vector<int16_t> nseg;             // stored segments per parameter (n_pts-1)
-  bool splines_open = false, splines_done = false;
-  int64_t n_events_total = 0, n_events_loaded = 0;
-  int T = 256;
-
-  // ---- signatures and tiles
-  std::map<std::vector<int16_t>, int> sig_index;   // key: cubic params, -1, linear params
-  std::vector<SigDesc> sigs;
-  std::vector<int32_t> sig_pool;
-  std::vector<int16_t> sig_slot_of_param;          // [n_sigs*P]
-  std::vector<int32_t> sig_segbase_of_param;       // [n_sigs*P]
-  std::vector<TileDesc> tiles;
-  std::vector<void*> allocs;
-  uint64_t device_bytes = 0;
-  uint64_t active_coef_bytes = 0;
-  int max_nc = 0, max_nl = 0;
-  TileDesc* d_tiles = nullptr;
-  SigDesc* d_sigs = nullptr;
-  int32_t* d_sig_pool = nullptr;
-  bool tiles_dirty = true;
-
-  // ---- binning
-  int n_samples = 0, n_bins = 0;
-  std::vector<int32_t> b_ndim, b_nbins, b_edge_off, b_stride, b_goff, sample_start;
-  std::vector<double> b_edges;
-  int32_t *d_ndim = nullptr, *d_nbins = nullptr, *d_edge_off = nullptr, *d_stride = nullptr, *d_goff = nullptr,
-          *d_sample_start = nullptr;
-  double* d_edges = nullptr;
-
-  // ---- events
-  int64_t n_events = 0, e_pad = 0, n_tiles = 0;
-  int32_t* d_bin = nullptr;
-  int32_t* d_osc_idx = nullptr;
-  float* d_osc = nullptr;
-  int64_t n_osc = 0;
-  bool use_osc = false;
-  float* d_static = nullptr;
-  int16_t* d_norm_idx = nullptr;
-  int norm_slots = 0, n_norm_values = 0;
-  double* d_kin = nullptr;
-  int32_t* d_sample_id = nullptr;
-  float *d_evt_spline_w = nullptr, *d_evt_total_w = nullptr;
-  bool evt_weights_valid = false;
-
-  // ---- histograms, likelihood
-  double* d_hw[2] = {nullptr, nullptr};   // each {mc[n_bins], w2[n_bins]}
-  bool mc_zero[2] = {false, false}, w2_zero[2] = {false, false};
-  int cur = 0;                            // buffer of the last step
-  double* d_w2_frozen = nullptr;
-  double* d_data = nullptr;
-  unsigned int* d_ticket = nullptr;
-  double* d_llh = nullptr;
-  double* h_llh = nullptr;                // mapped pinned
-  double* h_llh_dev = nullptr;            // device alias of h_llh
-  int test_stat = 0;
-  bool first_time_w2 = true;
-  bool last_w2_live = false;
-
-  // ---- per-step staging
-  StepLayout step{};
-  int step_sigs = -1;
-  static constexpr int kRing = 4;
-  unsigned char* h_step[kRing] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t step_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
-  unsigned char* d_step[kRing] = {nullptr, nullptr, nullptr, nullptr};
-  int ring = 0;
-  std::vector<unsigned char> last_step_table;
-  bool have_step = false;
-
-  // ---- launch configuration
-  int grid = 0, smem = 0, variant = 1;   // LDG kernel variant (m3b_kernels.cu), used when use_tma is false
-  bool use_tma = true;                   // streaming TMA kernel (m3b_fill_tma.cu), the default
-  int tma_stages = 0;
-  TmaSmem tma{};
-  unsigned int* d_tile_counter = nullptr;
-  bool zc_slots = false;                   // shared-memory slots for zero-copy oscillation weights
-  std::map<const void*, const float*> zc_ptr;   // pinned host array -> its device alias (or nullptr)
-  unsigned long long* d_trace = nullptr;   // m3b_block_trace
-  int trace_grid = 0;
-  bool hist_in_smem = true;
-  bool launch_ready = false;
-  bool launch_w2_live = false;
-
-  // ---- peer exchange
-  int peer_world = 0, peer_rank = 0;
-  double* d_inbox[2] = {nullptr, nullptr};       // own inboxes (two epochs' parity), [world*2*n_bins]
-  unsigned int* d_flags[2] = {nullptr, nullptr}; // [world]
-  double* peer_inbox[2][8] = {};
-  unsigned int* peer_flag[2][8] = {};
-  unsigned int peer_epoch = 0;
-  int32_t* d_status = nullptr;
-  std::vector<void*> ipc_opened;
-  std::vector<void*> registered;
-
-  uint64_t steps = 0, launches = 0;
-
-  // ---- optional kernel timing
-  bool timing = false;
-  std::vector<cudaEvent_t> tev;   // pairs
-  size_t tev_used = 0;
-};
-
-// ------------------------------------------------------------------------------------------------
-static int fail(m3b_handle* h, int code, const std::string& msg) {
-  g_last_error = msg;
-  if (h) h->err = msg;
-  return code;
-}
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e__ = (call);                                                                      \
-    if (e__ != cudaSuccess) {                                                                      \
-      char b__[512];                                                                               \
-      snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-      return fail(h, M3B_ERR_CUDA, b__);                                                           \
-    }                                                                                              \
-  } while (0)
-#define REQUIRE(cond, code, msg)                                                                   \
-  do { if (!(cond)) return fail(h, code, std::string(msg)); } while (0)
-
-template <class Tp>
-static cudaError_t dev_alloc(m3b_handle* h, Tp** p, size_t n) {
-  if (n == 0) n = 1;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(Tp));
-  if (e == cudaSuccess) { h->allocs.push_back(*p); h->device_bytes += n * sizeof(Tp); }
-  return e;
-}
-template <class Tp>
-static cudaError_t dev_upload(m3b_handle* h, Tp** p, const std::vector<Tp>& v) {
-  cudaError_t e = dev_alloc(h, p, v.size());
-  if (e != cudaSuccess) return e;
-  if (!v.empty()) e = cudaMemcpy(*p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice);
-  return e;
-}
+std::string& m3b_last_error_slot() { return g_last_error; }
 
 extern "C" {
 
@@ -684,7 +525,8 @@ M3B_API int m3b_find_segments(m3b_handle* h, const double* spline_pars, int16_t*
 
 static int prepare_launch(m3b_handle* h, bool w2_live) {
   CK(cudaSetDevice(h->device));
-  if (h->tiles_dirty || !h->d_tiles) {
+  if (h->binned) REQUIRE(h->d_wtiles, M3B_ERR_STATE, "step: call m3b_upload_event_binned_splines first");
+  if (!h->binned && (h->tiles_dirty || !h->d_tiles)) {
     REQUIRE(!h->splines_open, M3B_ERR_STATE, "step: spline upload still open (call m3b_splines_end)");
     if (!h->splines_done) {
       // no response functions at all: tiles with an empty signature
@@ -700,8 +542,8 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
     h->tiles_dirty = false;
     h->launch_ready = false;
   }
-  if (!h->h_step[0] || h->step.P != h->P || h->step.Nn != h->n_norm_values || h->step_sigs != static_cast<int>(h->sigs.size())) {
-    h->step_sigs = static_cast<int>(h->sigs.size());
+  if (!h->h_step[0] || h->step.P != h->P || h->step.Nn != h->n_norm_values || h->step_sigs != (h->binned ? 0 : static_cast<int>(h->sigs.size()))) {
+    h->step_sigs = h->binned ? 0 : static_cast<int>(h->sigs.size());
     h->step = make_step_layout(h->P, h->n_norm_values, h->step_sigs, h->max_nc, h->max_nl);
     for (int i = 0; i < m3b_handle::kRing; ++i) {
       if (h->h_step[i]) cudaFreeHost(h->h_step[i]);
@@ -715,8 +557,24 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
     a.step = h->step; a.max_nc = h->max_nc; a.max_nl = h->max_nl; a.n_bins = h->n_bins; a.n_samples = h->n_samples;
     // kernel choice: M3B_VARIANT=tma (default) | 0..5 (LDG register-streaming variants, m3b_kernels.cu)
     const char* v = getenv("M3B_VARIANT");
-    h->use_tma = h->T % 256 == 0;
+    h->use_tma = h->T % 256 == 0 && !h->binned;
     if (v && v[0] >= '0' && v[0] <= '9') { h->use_tma = false; h->variant = atoi(v); }
+    if (h->binned) {
+      // BinnedSplineHandler path: evaluate the non-flat splines, then gather/fill (m3b_binned.cu)
+      int smem = binned_fill_smem_bytes(a, true, w2_live);
+      h->hist_in_smem = smem <= 200 * 1024;
+      if (!h->hist_in_smem) smem = binned_fill_smem_bytes(a, false, w2_live);
+      CK(binned_fill_set_smem(smem));
+      int bps = 0;
+      CK(binned_fill_occupancy(smem, &bps));
+      REQUIRE(bps > 0, M3B_ERR_CUDA, "step: binned fill kernel does not fit on an SM");
+      h->smem = smem;
+      h->grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_wtiles + 7) / 8, static_cast<int64_t>(bps) * h->sm_count)));
+      h->binned_eval_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_btiles + 3) / 4, 8ll * h->sm_count)));
+      h->launch_ready = true;
+      h->launch_w2_live = w2_live;
+      return M3B_OK;
+    }
     REQUIRE(h->use_tma || h->T <= 512, M3B_ERR_INVALID, "step: the register-streaming kernel variants need tile_events <= 512");
     const int llh_scratch = h->n_samples * 32 * 8;
     if (h->use_tma) {
@@ -890,7 +748,12 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     }
     CK(cudaEventRecord(h->tev[h->tev_used], h->stream));
   }
-  if (h->use_tma) CK(launch_fill_tma(a, h->grid, h->smem, h->stream));
+  if (h->binned) {
+    a.btiles = h->d_btiles; a.n_btiles = h->n_btiles; a.bcoef = h->d_bcoef; a.bx = h->d_bx; a.bw = h->d_bw;
+    a.ell = h->d_ell; a.wtiles = h->d_wtiles; a.n_wtiles = h->n_wtiles;
+    if (h->n_btiles > 0) { CK(launch_binned_eval(a, h->binned_eval_grid, h->stream)); ++h->launches; }
+    CK(launch_binned_fill(a, h->grid, h->smem, h->stream));
+  } else if (h->use_tma) CK(launch_fill_tma(a, h->grid, h->smem, h->stream));
   else CK(launch_fill(a, h->variant, h->grid, h->smem, h->stream));
   if (h->timing) { CK(cudaEventRecord(h->tev[h->tev_used + 1], h->stream)); h->tev_used += 2; }
   ++h->launches;
@@ -974,6 +837,7 @@ M3B_API int m3b_eval_weights(m3b_handle* h, const float* param_values, const int
                              float* host_total_weights) {
   REQUIRE(h, M3B_ERR_INVALID, "null handle");
   REQUIRE(h->P > 0 && param_values && segments, M3B_ERR_INVALID, "m3b_eval_weights: null argument / no monolith");
+  REQUIRE(!h->binned, M3B_ERR_STATE, "m3b_eval_weights: event-by-event monolith only (use m3b_step + m3b_read_binned_weights)");
   int rc = ensure_standalone_events(h);
   if (rc != M3B_OK) return rc;
   REQUIRE(h->d_evt_spline_w, M3B_ERR_STATE, "m3b_eval_weights: create the handle with M3B_FLAG_KEEP_EVENT_WEIGHTS");
@@ -1181,7 +1045,7 @@ M3B_API int m3b_get_info(m3b_handle* h, m3b_info* out) {
   per_evt += 2ull * h->norm_slots;
   out->active_bytes_per_step = h->active_coef_bytes + per_evt * static_cast<uint64_t>(h->e_pad);
   out->steps = h->steps; out->kernel_launches = h->launches;
-  out->kernel_variant = h->use_tma ? -1 : h->variant; out->tma_stages = h->use_tma ? h->tma_stages : 0;
+  out->kernel_variant = h->binned ? -2 : (h->use_tma ? -1 : h->variant); out->tma_stages = h->use_tma ? h->tma_stages : 0;
   return M3B_OK;
 }
 

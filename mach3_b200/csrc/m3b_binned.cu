@@ -1,0 +1,280 @@
+// m3b_binned.cu -- the BinnedSplineHandler form of the hot path (BASELINE config 4).
+//
+//   binned_eval_kernel   BinnedSplineHandler::CalcSplineWeights (Splines/BinnedSplineHandler.cpp:306-341):
+//                        one weight per non-flat binned spline, fmaf Horner on the active segment,
+//                        negative weights clamped to 0 (:337); flat splines are never evaluated and
+//                        stay at 1.0 (:236,283) -- here they are simply not stored.
+//   binned_fill_kernel   SampleHandlerFD::CalcWeightTotal over the event's N weight pointers
+//                        (Samples/SampleHandlerFD.cpp:568-594, pointers wired at :1196-1242) + FillArray_MP
+//                        (:390-448) + the likelihood (the common epilogue, m3b_device.cuh).
+//   host                 m3b_upload_binned_splines / m3b_upload_event_binned_splines / m3b_read_binned_weights
+//
+// _LOW_MEMORY_STRUCTS_ build of the reference (M3::float_t = float), like the SMonolith path.
+#include "m3b_device.cuh"
+#include "m3b_handle.h"
+
+namespace m3b {
+
+__global__ void __launch_bounds__(256) binned_eval_kernel(const __grid_constant__ FillArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  stage_step_table(a, smem, &bar);
+  const int32_t* seg = reinterpret_cast<const int32_t*>(smem + a.step.off_seg);
+  const float* val = reinterpret_cast<const float*>(smem + a.step.off_val);
+  constexpr int U = 4;          // tiles in flight per block: 4 x (16+4) B per thread before the first use
+  for (int t0 = blockIdx.x * U; t0 < a.n_btiles; t0 += gridDim.x * U) {
+    float4 c[U]; float x[U]; float xv[U]; int out[U];
+    #pragma unroll
+    for (int u = 0; u < U; ++u) {
+      out[u] = -1;
+      if (t0 + u < a.n_btiles) {
+        const BTile bt = a.btiles[t0 + u];
+        const int64_t i = bt.coef_off + static_cast<int64_t>(seg[bt.param]) * bt.n_pad + bt.k0 + threadIdx.x;
+        c[u] = ldg_stream(a.bcoef + i);
+        x[u] = __ldcs(a.bx + i);
+        xv[u] = val[bt.param];                 // M3::float_t(*splineParsPointer), :327
+        out[u] = bt.out0 + threadIdx.x;
+      }
+    }
+    #pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (out[u] >= 0) {
+        const float dx = xv[u] - x[u];                                               // :329
+        float w = fmaf(dx, fmaf(dx, fmaf(dx, c[u].w, c[u].z), c[u].y), c[u].x);       // :332
+        if (w < 0) w = 0.f;                                                           // :337
+        a.bw[out[u]] = w;
+      }
+    }
+  }
+}
+
+int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
+  int b = (a.step.bytes + 15) & ~15;
+  if (hist_in_smem) b += 8 * a.n_bins * (w2_live ? 2 : 1);
+  const int llh_scratch = a.n_samples * 32 * 8;
+  return b > llh_scratch ? b : llh_scratch;
+}
+
+__global__ void __launch_bounds__(256) binned_fill_kernel(const __grid_constant__ FillArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double* s_hist = reinterpret_cast<double*>(smem + ((a.step.bytes + 15) & ~15));
+  double* s_w2 = s_hist + a.n_bins;
+  const bool w2_live = a.w2 != nullptr;
+  const bool smem_hist = a.hist_in_smem != 0;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (smem_hist && !a.weights_only) {
+    for (int i = tid; i < a.n_bins; i += 256) s_hist[i] = 0.;
+    if (w2_live) for (int i = tid; i < a.n_bins; i += 256) s_w2[i] = 0.;
+  }
+  stage_step_table(a, smem, &bar);
+  const float* norm = reinterpret_cast<const float*>(smem + a.step.off_norm);
+
+  for (int64_t wt = static_cast<int64_t>(blockIdx.x) * 8 + warp; wt < a.n_wtiles; wt += static_cast<int64_t>(gridDim.x) * 8) {
+    const WTile d = a.wtiles[wt];
+    const int64_t e = wt * 32 + lane;
+    const int bin = a.bin[e];
+    float w_osc = 1.f, w_static = 1.f;
+    if (a.osc) {
+      const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
+      w_osc = a.osc[oi];
+    }
+    if (a.static_w) w_static = a.static_w[e];
+    // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras
+    float w = 1.0f;
+    for (int j = 0; j < a.norm_slots; ++j) {
+      const int i = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + e];
+      w *= (i >= 0 ? norm[i] : 1.0f);
+    }
+    w *= w_osc;
+    float w_spl = 1.0f;        // product of the binned weights alone (m3b_read_event_weights)
+    const int32_t* col = a.ell + d.off + lane;
+    for (int j0 = 0; j0 < d.max_n; j0 += 8) {
+      int idx[8]; float g[8];
+      #pragma unroll
+      for (int j = 0; j < 8; ++j) idx[j] = (j0 + j < d.max_n) ? __ldcs(col + (j0 + j) * 32) : -1;
+      #pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = idx[j] >= 0 ? __ldg(a.bw + idx[j]) : 1.0f;
+      #pragma unroll
+      for (int j = 0; j < 8; ++j) if (idx[j] >= 0) { w *= g[j]; w_spl *= g[j]; }
+    }
+    w *= w_static;
+    if (a.evt_spline_w && e < a.n_events) { a.evt_spline_w[e] = w_spl; a.evt_total_w[e] = w; }
+    if (w > 0.f && bin >= 0 && !a.weights_only) {
+      if (smem_hist) {
+        atomicAdd(s_hist + bin, static_cast<double>(w));
+        if (w2_live) atomicAdd(s_w2 + bin, static_cast<double>(w * w));
+      } else {
+        atomicAdd(a.hist + bin, static_cast<double>(w));
+        if (w2_live) atomicAdd(a.w2 + bin, static_cast<double>(w * w));
+      }
+    }
+  }
+  finish_block(a, s_hist, s_w2, reinterpret_cast<double*>(smem), &s_last);
+}
+
+cudaError_t launch_binned_eval(const FillArgs& a, int grid, cudaStream_t s) {
+  binned_eval_kernel<<<grid, 256, (a.step.bytes + 15) & ~15, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_binned_fill(const FillArgs& a, int grid, int smem, cudaStream_t s) {
+  binned_fill_kernel<<<grid, 256, smem, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t binned_fill_set_smem(int smem) {
+  const int cap = smem > 48 * 1024 ? smem : 48 * 1024;
+  return cudaFuncSetAttribute(binned_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+}
+cudaError_t binned_fill_occupancy(int smem, int* bps) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel, 256, smem);
+}
+
+}  // namespace m3b
+
+// ------------------------------------------------------------------------------------------------
+// host: uploads
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t max_knots, const float* knot_x,
+                                      const int16_t* n_pts, int64_t n_slots, const int32_t* uniquesplinevec_Monolith,
+                                      const int32_t* coeffindexvec, int64_t n_unique, const int32_t* uniquecoeffindices,
+                                      int64_t n_coeff, const float* manycoeff_arr, const float* xcoeff_arr) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(!h->splines_open && !h->splines_done && !h->binned, M3B_ERR_STATE, "m3b_upload_binned_splines: a spline handler is already uploaded");
+  REQUIRE(n_params > 0 && n_params <= kMaxParams && max_knots >= 2 && knot_x && n_pts, M3B_ERR_INVALID, "m3b_upload_binned_splines: bad parameter layout");
+  REQUIRE(n_slots > 0 && n_slots < (1ll << 31) && uniquesplinevec_Monolith && coeffindexvec, M3B_ERR_INVALID, "m3b_upload_binned_splines: bad slot arrays");
+  REQUIRE(n_unique >= 0 && (n_unique == 0 || (uniquecoeffindices && manycoeff_arr && xcoeff_arr)), M3B_ERR_INVALID, "m3b_upload_binned_splines: null coefficient arrays");
+  CK(cudaSetDevice(h->device));
+  h->P = n_params; h->Kmax = max_knots;
+  h->coeff_x.assign(knot_x, knot_x + static_cast<size_t>(n_params) * max_knots);
+  h->n_pts.assign(n_pts, n_pts + n_params);
+  h->nseg.resize(n_params);
+  for (int p = 0; p < n_params; ++p) {
+    REQUIRE(n_pts[p] >= 0 && n_pts[p] <= max_knots, M3B_ERR_INVALID, "m3b_upload_binned_splines: n_pts[p] > max_knots");
+    h->nseg[p] = static_cast<int16_t>(n_pts[p] > 1 ? n_pts[p] - 1 : 0);
+  }
+  h->curr_segment.assign(n_params, 0);
+  h->segments.assign(n_params, 0);
+  h->param_values.assign(n_params, -999.f);
+
+  // group the non-flat splines by parameter (stable: ascending slot inside a parameter), pad to 256
+  std::vector<int64_t> count(n_params + 1, 0);
+  for (int64_t k = 0; k < n_unique; ++k) {
+    const int32_t s = uniquecoeffindices[k];
+    REQUIRE(s >= 0 && s < n_slots, M3B_ERR_INVALID, "m3b_upload_binned_splines: uniquecoeffindices out of range");
+    const int32_t p = uniquesplinevec_Monolith[s];
+    REQUIRE(p >= 0 && p < n_params, M3B_ERR_INVALID, "m3b_upload_binned_splines: uniquesplinevec_Monolith out of range");
+    REQUIRE(h->nseg[p] > 0, M3B_ERR_KNOTS, "m3b_upload_binned_splines: non-flat spline on a parameter without knots");
+    REQUIRE(coeffindexvec[s] >= 0 && static_cast<int64_t>(coeffindexvec[s]) + n_pts[p] <= n_coeff, M3B_ERR_KNOTS,
+            "m3b_upload_binned_splines: a spline's knots run past the coefficient arrays (knot count differs from its parameter's)");
+    ++count[p + 1];
+  }
+  std::vector<int64_t> out_base(n_params + 1, 0), coef_base(n_params + 1, 0), npad(n_params, 0);
+  for (int p = 0; p < n_params; ++p) {
+    npad[p] = (count[p + 1] + 255) / 256 * 256;
+    out_base[p + 1] = out_base[p] + npad[p];
+    coef_base[p + 1] = coef_base[p] + npad[p] * h->nseg[p];
+  }
+  const int64_t n_act_pad = out_base[n_params], n_coef_dev = coef_base[n_params];
+  h->b_slot2compact.assign(static_cast<size_t>(n_slots), -1);
+  h->b_compact2slot.assign(static_cast<size_t>(n_act_pad), -1);
+  std::vector<float4> coef(static_cast<size_t>(n_coef_dev), make_float4(1.f, 0.f, 0.f, 0.f));
+  std::vector<float> xs(static_cast<size_t>(n_coef_dev), 0.f);
+  std::vector<int64_t> fill(n_params, 0);
+  for (int64_t k = 0; k < n_unique; ++k) {
+    const int32_t s = uniquecoeffindices[k];
+    const int32_t p = uniquesplinevec_Monolith[s];
+    const int64_t j = fill[p]++;
+    REQUIRE(h->b_slot2compact[s] < 0, M3B_ERR_INVALID, "m3b_upload_binned_splines: slot listed twice in uniquecoeffindices");
+    h->b_slot2compact[s] = static_cast<int32_t>(out_base[p] + j);
+    h->b_compact2slot[out_base[p] + j] = s;
+    const float4* src = reinterpret_cast<const float4*>(manycoeff_arr) + coeffindexvec[s];
+    for (int g = 0; g < h->nseg[p]; ++g) {
+      coef[coef_base[p] + g * npad[p] + j] = src[g];
+      xs[coef_base[p] + g * npad[p] + j] = xcoeff_arr[coeffindexvec[s] + g];
+    }
+  }
+  std::vector<BTile> tiles;
+  for (int p = 0; p < n_params; ++p)
+    for (int64_t k0 = 0; k0 < npad[p]; k0 += 256)
+      tiles.push_back(BTile{coef_base[p], static_cast<int32_t>(npad[p]), p, static_cast<int32_t>(k0), static_cast<int32_t>(out_base[p] + k0)});
+  CK(dev_upload(h, &h->d_bcoef, coef));
+  CK(dev_upload(h, &h->d_bx, xs));
+  CK(dev_upload(h, &h->d_btiles, tiles));
+  CK(dev_alloc(h, &h->d_bw, static_cast<size_t>(n_act_pad)));
+  h->n_btiles = static_cast<int32_t>(tiles.size());
+  h->b_n_slots = n_slots; h->b_n_act = n_unique; h->b_n_act_pad = n_act_pad;
+  h->binned = true;
+  h->launch_ready = false;
+  return M3B_OK;
+}
+
+M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, const uint32_t* n_per_event,
+                                            const int32_t* spline_index) {
+  REQUIRE(h && n_per_event, M3B_ERR_INVALID, "m3b_upload_event_binned_splines: null argument");
+  REQUIRE(h->binned, M3B_ERR_STATE, "m3b_upload_event_binned_splines: upload the binned splines first");
+  REQUIRE(h->n_events > 0 && n_events == h->n_events, M3B_ERR_STATE, "m3b_upload_event_binned_splines: upload the events first (same count)");
+  REQUIRE(!h->d_wtiles, M3B_ERR_STATE, "m3b_upload_event_binned_splines: already uploaded");
+  CK(cudaSetDevice(h->device));
+  const int64_t n_wt = h->e_pad / 32;
+  std::vector<WTile> wt(static_cast<size_t>(n_wt));
+  // first pass: non-flat pointers per event, ELL width per 32 events
+  std::vector<uint32_t> keep(static_cast<size_t>(n_events), 0);
+  uint64_t off = 0;
+  for (int64_t e = 0; e < n_events; ++e) {
+    uint32_t k = 0;
+    for (uint32_t j = 0; j < n_per_event[e]; ++j) {
+      const int32_t s = spline_index[off + j];
+      REQUIRE(s >= 0 && s < h->b_n_slots, M3B_ERR_INVALID, "m3b_upload_event_binned_splines: spline_index out of range");
+      if (h->b_slot2compact[s] >= 0) ++k;        // flat splines hold exactly 1.0f: multiplying by them changes nothing
+    }
+    keep[e] = k;
+    off += n_per_event[e];
+  }
+  int64_t total = 0;
+  for (int64_t t = 0; t < n_wt; ++t) {
+    uint32_t mx = 0;
+    for (int64_t e = t * 32; e < std::min<int64_t>(n_events, t * 32 + 32); ++e) mx = std::max(mx, keep[e]);
+    wt[t].off = total; wt[t].max_n = static_cast<int32_t>(mx); wt[t].pad = 0;
+    total += static_cast<int64_t>(mx) * 32;
+  }
+  std::vector<int32_t> ell(static_cast<size_t>(std::max<int64_t>(total, 1)), -1);
+  off = 0;
+  for (int64_t e = 0; e < n_events; ++e) {
+    const WTile& d = wt[e / 32];
+    int64_t k = 0;
+    for (uint32_t j = 0; j < n_per_event[e]; ++j) {
+      const int32_t c = h->b_slot2compact[spline_index[off + j]];
+      if (c >= 0) ell[d.off + (k++) * 32 + (e & 31)] = c;       // pointer order kept: the product is sequential
+    }
+    off += n_per_event[e];
+  }
+  CK(dev_upload(h, &h->d_ell, ell));
+  CK(dev_upload(h, &h->d_wtiles, wt));
+  h->n_wtiles = n_wt;
+  h->b_gather_per_step = static_cast<uint64_t>(total);
+  h->launch_ready = false;
+  return M3B_OK;
+}
+
+// BinnedSplineHandler::weightvec_Monolith as the host sees it (retPointer targets): 1.0 for flat slots
+M3B_API int m3b_read_binned_weights(m3b_handle* h, float* weightvec_Monolith) {
+  REQUIRE(h && weightvec_Monolith, M3B_ERR_INVALID, "m3b_read_binned_weights: null argument");
+  REQUIRE(h->binned && h->steps > 0, M3B_ERR_STATE, "m3b_read_binned_weights: no binned step yet");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<float> bw(static_cast<size_t>(h->b_n_act_pad));
+  CK(cudaMemcpy(bw.data(), h->d_bw, sizeof(float) * bw.size(), cudaMemcpyDeviceToHost));
+  for (int64_t s = 0; s < h->b_n_slots; ++s) weightvec_Monolith[s] = 1.0f;
+  for (int64_t c = 0; c < h->b_n_act_pad; ++c)
+    if (h->b_compact2slot[c] >= 0) weightvec_Monolith[h->b_compact2slot[c]] = bw[c];
+  return M3B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// m3b_handle.h -- the handle behind the C ABI and the small host helpers shared by the .cu files
+// that implement it (m3b_api.cu: monolith path; m3b_binned.cu: BinnedSplineHandler path).
+#pragma once
+#include "m3b200.h"
+#include "m3b_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace m3b;
+
+std::string& m3b_last_error_slot();     // thread-local last error (defined in m3b_api.cu)
+
+struct m3b_handle {
+  m3b_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // ---- spline parameters (FastSplineInfo, Splines/SplineStructs.h:21-44)
+  int P = 0, Kmax = 0;
+  std::vector<float> coeff_x;
+  std::vector<int16_t> n_pts;
+  std::vector<int16_t> curr_segment;     // FastSplineInfo::CurrSegment
+  std::vector<int16_t> segments;         // SplineBase::SplineSegments
+  std::vector<float> param_values;       // SplineBase::ParamValues
+  std::vector<int16_t> nseg;             // stored segments per parameter (n_pts-1)
+  bool splines_open = false, splines_done = false;
+  int64_t n_events_total = 0, n_events_loaded = 0;
+  int T = 256;
+
+  // ---- signatures and tiles
+  std::map<std::vector<int16_t>, int> sig_index;   // key: cubic params, -1, linear params
+  std::vector<SigDesc> sigs;
+  std::vector<int32_t> sig_pool;
+  std::vector<int16_t> sig_slot_of_param;          // [n_sigs*P]
+  std::vector<int32_t> sig_segbase_of_param;       // [n_sigs*P]
+  std::vector<TileDesc> tiles;
+  std::vector<void*> allocs;
+  uint64_t device_bytes = 0;
+  uint64_t active_coef_bytes = 0;
+  int max_nc = 0, max_nl = 0;
+  TileDesc* d_tiles = nullptr;
+  SigDesc* d_sigs = nullptr;
+  int32_t* d_sig_pool = nullptr;
+  bool tiles_dirty = true;
+
+  // ---- binning
+  int n_samples = 0, n_bins = 0;
+  std::vector<int32_t> b_ndim, b_nbins, b_edge_off, b_stride, b_goff, sample_start;
+  std::vector<double> b_edges;
+  int32_t *d_ndim = nullptr, *d_nbins = nullptr, *d_edge_off = nullptr, *d_stride = nullptr, *d_goff = nullptr,
+          *d_sample_start = nullptr;
+  double* d_edges = nullptr;
+
+  // ---- events
+  int64_t n_events = 0, e_pad = 0, n_tiles = 0;
+  int32_t* d_bin = nullptr;
+  int32_t* d_osc_idx = nullptr;
+  float* d_osc = nullptr;
+  int64_t n_osc = 0;
+  bool use_osc = false;
+  float* d_static = nullptr;
+  int16_t* d_norm_idx = nullptr;
+  int norm_slots = 0, n_norm_values = 0;
+  double* d_kin = nullptr;
+  int32_t* d_sample_id = nullptr;
+  float *d_evt_spline_w = nullptr, *d_evt_total_w = nullptr;
+  bool evt_weights_valid = false;
+
+  // ---- histograms, likelihood
+  double* d_hw[2] = {nullptr, nullptr};   // each {mc[n_bins], w2[n_bins]}
+  bool mc_zero[2] = {false, false}, w2_zero[2] = {false, false};
+  int cur = 0;                            // buffer of the last step
+  double* d_w2_frozen = nullptr;
+  double* d_data = nullptr;
+  unsigned int* d_ticket = nullptr;
+  double* d_llh = nullptr;
+  double* h_llh = nullptr;                // mapped pinned
+  double* h_llh_dev = nullptr;            // device alias of h_llh
+  int test_stat = 0;
+  bool first_time_w2 = true;
+  bool last_w2_live = false;
+
+  // ---- per-step staging
+  StepLayout step{};
+  int step_sigs = -1;
+  static constexpr int kRing = 4;
+  unsigned char* h_step[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t step_ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned char* d_step[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  int ring = 0;
+  std::vector<unsigned char> last_step_table;
+  bool have_step = false;
+
+  // ---- launch configuration
+  int grid = 0, smem = 0, variant = 1;   // LDG kernel variant (m3b_kernels.cu), used when use_tma is false
+  bool use_tma = true;                   // streaming TMA kernel (m3b_fill_tma.cu), the default
+  int tma_stages = 0;
+  TmaSmem tma{};
+  unsigned int* d_tile_counter = nullptr;
+  bool zc_slots = false;                   // shared-memory slots for zero-copy oscillation weights
+  std::map<const void*, const float*> zc_ptr;   // pinned host array -> its device alias (or nullptr)
+  unsigned long long* d_trace = nullptr;   // m3b_block_trace
+  int trace_grid = 0;
+  bool hist_in_smem = true;
+  bool launch_ready = false;
+  bool launch_w2_live = false;
+
+  // ---- peer exchange
+  int peer_world = 0, peer_rank = 0;
+  double* d_inbox[2] = {nullptr, nullptr};       // own inboxes (two epochs' parity), [world*2*n_bins]
+  unsigned int* d_flags[2] = {nullptr, nullptr}; // [world]
+  double* peer_inbox[2][8] = {};
+  unsigned int* peer_flag[2][8] = {};
+  unsigned int peer_epoch = 0;
+  int32_t* d_status = nullptr;
+  std::vector<void*> ipc_opened;
+  std::vector<void*> registered;
+
+  // ---- BinnedSplineHandler path (m3b_binned.cu)
+  bool binned = false;
+  int64_t b_n_slots = 0, b_n_act = 0, b_n_act_pad = 0, n_wtiles = 0;
+  int32_t n_btiles = 0;
+  std::vector<int32_t> b_slot2compact, b_compact2slot;
+  float4* d_bcoef = nullptr; float* d_bx = nullptr; float* d_bw = nullptr;
+  BTile* d_btiles = nullptr; WTile* d_wtiles = nullptr; int32_t* d_ell = nullptr;
+  uint64_t b_gather_per_step = 0;
+  int binned_eval_grid = 0;
+
+  uint64_t steps = 0, launches = 0;
+
+  // ---- optional kernel timing
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;   // pairs
+  size_t tev_used = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+static inline int fail(m3b_handle* h, int code, const std::string& msg) {
+  m3b_last_error_slot() = msg;
+  if (h) h->err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      char b__[512];                                                                               \
+      snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return fail(h, M3B_ERR_CUDA, b__);                                                           \
+    }                                                                                              \
+  } while (0)
+#define REQUIRE(cond, code, msg)                                                                   \
+  do { if (!(cond)) return fail(h, code, std::string(msg)); } while (0)
+
+template <class Tp>
+static inline cudaError_t dev_alloc(m3b_handle* h, Tp** p, size_t n) {
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(Tp));
+  if (e == cudaSuccess) { h->allocs.push_back(*p); h->device_bytes += n * sizeof(Tp); }
+  return e;
+}
+template <class Tp>
+static inline cudaError_t dev_upload(m3b_handle* h, Tp** p, const std::vector<Tp>& v) {
+  cudaError_t e = dev_alloc(h, p, v.size());
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpy(*p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice);
+  return e;
+}
+

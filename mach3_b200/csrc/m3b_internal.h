@@ -65,6 +65,19 @@ inline StepLayout make_step_layout(int P, int Nn, int n_sigs, int max_nc, int ma
   return L;
 }
 
+// ---- BinnedSplineHandler path (m3b_binned.cu) ------------------------------------------------------
+// Active (non-flat) binned splines are grouped by parameter and padded to 256 per parameter:
+//   bcoef[coef_off + segment * n_pad + k]  float4 {y,b,c,d}     bx[same index]  knot x of that segment
+// so one step reads, per parameter, ONE contiguous row of coefficients and one of x.
+struct BTile {                 // 256 consecutive active splines of one parameter
+  int64_t coef_off;            // first element of the parameter's [nseg][n_pad] block
+  int32_t n_pad, param, k0, out0;   // row length, parameter, first spline of the tile in the row, first compact weight
+};
+struct WTile {                 // 32 consecutive events: their binned-spline pointers as ELL columns
+  int64_t off;                 // ell[off + j*32 + lane] = compact weight index of the lane's j-th pointer, -1 = none
+  int32_t max_n, pad;
+};
+
 // Shared-memory map of the TMA fill kernel (m3b_fill_tma.cu); computed on the host, passed by value.
 //   [step table][dx[max_nc]][lv[max_nl]][row[max_nc]][stage descriptors][hist (+w2)][ring: n_stages x stage_bytes]
 struct TmaSmem {
@@ -115,6 +128,10 @@ struct FillArgs {
   // optional per-event outputs
   float* evt_spline_w;
   float* evt_total_w;
+  // BinnedSplineHandler path
+  const BTile* btiles; int32_t n_btiles;
+  const float4* bcoef; const float* bx; float* bw;
+  const int32_t* ell; const WTile* wtiles; int64_t n_wtiles;
   // optional per-block timeline (m3b_block_trace): 8 x u64 globaltimer ns per block
   unsigned long long* trace;
   alignas(16) unsigned char step_inline[kStepInlineMax];
@@ -185,5 +202,11 @@ cudaError_t launch_fill_tma(const FillArgs& a, int grid, int smem_bytes, cudaStr
 cudaError_t fill_tma_set_smem(int smem_bytes);
 cudaError_t fill_tma_occupancy(int smem_bytes, int* blocks_per_sm);
 int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
+// BinnedSplineHandler path (m3b_binned.cu)
+cudaError_t launch_binned_eval(const FillArgs& a, int grid, cudaStream_t s);
+cudaError_t launch_binned_fill(const FillArgs& a, int grid, int smem_bytes, cudaStream_t s);
+cudaError_t binned_fill_set_smem(int smem_bytes);
+cudaError_t binned_fill_occupancy(int smem_bytes, int* blocks_per_sm);
+int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
 
 }  // namespace m3b

@@ -80,6 +80,34 @@ class SMonolith:
         return self.handle.find_segments(self._pars if pars is None else pars)
 
 
+class BinnedSplineHandler:
+    """The binned SplineBase implementation (Splines/BinnedSplineHandler.h) on the B200, always attached
+    to a :class:`SampleHandlerFD`: its evaluation runs inside ``Reweight()``; ``weightvec_Monolith`` is a
+    lazy host mirror."""
+
+    def __init__(self, spl, handle):
+        self.handle = handle
+        self.n_params = int(spl["n_params"])
+        handle.upload_binned_splines(spl)
+
+    def GetName(self):
+        return "BinnedSplineHandler"
+
+    def GetNParams(self):
+        return self.n_params
+
+    def setSplinePointers(self, spline_pars_array):
+        assert spline_pars_array.dtype == np.float64 and spline_pars_array.size == self.n_params
+        self._pars = spline_pars_array
+
+    @property
+    def weightvec_Monolith(self):
+        return self.handle.read_binned_weights()
+
+    def FindSplineSegment(self, pars=None):
+        return self.handle.find_segments(self._pars if pars is None else pars)
+
+
 def slice_monolith(spl, e0, e1):
     """Events [e0,e1) of a reference-layout monolith, offsets rebased to the chunk."""
     cnt = np.asarray(spl["nParamPerEvent"]).reshape(-1, 2)[:, 0].astype(np.int64)
@@ -128,6 +156,14 @@ class SampleHandlerFD:
         self.SplineHandler = SMonolith(n_params, max_knots, coeff_x, n_pts, spl, handle=self.handle,
                                        chunk_events=chunk_events)
         return self.SplineHandler
+
+    def SetupBinnedSplines(self, spl):
+        self.SplineHandler = BinnedSplineHandler(spl, self.handle)
+        return self.SplineHandler
+
+    def SetBinnedSplinePointers(self, n_per_event, spline_index):
+        """SampleHandlerFD::SetSplinePointers, binned arm (Samples/SampleHandlerFD.cpp:1196-1242); after SetupEvents."""
+        self.handle.upload_event_binned_splines(n_per_event, spline_index)
 
     def SetupEvents(self, sample_id, kin, norm_idx=None, n_norm_per_event=0, norm_pars=None, osc_w=None,
                     osc_idx=None, static_w=None):
@@ -205,3 +241,20 @@ def build_from_workload(w, e0=0, e1=None, with_osc=True, update_w2=False, test_s
                    osc, None, ev["static_w"])
     sh.SetSplinePointers(pars)
     return sh, dict(typ=typ, npts=npts, coeff_x=cx, spl=spl, ev=ev, pars=pars, norm=norm, osc=osc)
+
+
+def build_binned_from_workload(w, update_w2=True, test_statistic=None, device=0, keep_event_weights=False, fused_llh=True):
+    """B200 SampleHandlerFD + BinnedSplineHandler wired on a synthetic binned-spline workload."""
+    from .synth import binned as B
+    spl = B.make_binned_splines(w)
+    ev = B.make_binned_events(w)
+    sh = SampleHandlerFD(B.bin_edges(w), w.test_statistic if test_statistic is None else test_statistic, update_w2, device,
+                         0, keep_event_weights, fused_llh)
+    sh.SetupBinnedSplines(spl)
+    pars = np.zeros(w.n_systs, np.float64)
+    norm = np.ones(w.n_norm_params, np.float64)
+    osc = B.make_osc(w, 0)
+    sh.SetupEvents(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, norm, osc, None, ev["static_w"])
+    sh.SetBinnedSplinePointers(ev["n_per_event"], ev["spline_index"])
+    sh.SetSplinePointers(pars)
+    return sh, dict(spl=spl, ev=ev, pars=pars, norm=norm, osc=osc)

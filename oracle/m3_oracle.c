@@ -351,6 +351,85 @@ static int FindNominalBin(const SampleBinningInfo* info, const int iDim, const d
   return upper_bound_d(edges, ne, Var) - 1;
 }
 
+
+/* ============================================================================================
+ * BinnedSplineHandler (Splines/BinnedSplineHandler.h:110-135, .cpp:295-341), _LOW_MEMORY_STRUCTS_
+ * build (M3::float_t = float, like the SMonolith path above; the default build holds the same
+ * arrays in double -- see m3o_binned_calc_spline_weights at the end of this file).
+ *   weightvec_Monolith[n_slots]         one weight per (sample,osc,syst,mode,bin) slot, 1.0 for flat
+ *   uniquesplinevec_Monolith[iSpline]   spline parameter of the slot
+ *   coeffindexvec[iSpline]              first knot of the slot's spline in manycoeff_arr / xcoeff_arr
+ *   uniquecoeffindices[]                the non-flat slots: only these are evaluated (:311-340)
+ * Segments come from SplineBase::FindSplineSegment on the parameter's xPts (first spline seen).
+ * ========================================================================================== */
+typedef struct BinnedSplineHandler_ {
+  SMonolith base;                       /* SplineBase part only: nParams, SplineInfoArray, SplineSegments, ParamValues */
+  int64_t n_slots, n_unique;
+  const int* uniquesplinevec_Monolith;
+  const int* coeffindexvec;
+  const int* uniquecoeffindices;
+  const float* manycoeff_arr;
+  const float* xcoeff_arr;
+  float* weightvec_Monolith;
+} BinnedSplineHandler;
+
+M3O_API BinnedSplineHandler* m3o_binned_create(int nParams, int max_knots, const float* knot_x, const short* n_pts,
+                                               int64_t n_slots, const int* uniquesplinevec_Monolith, const int* coeffindexvec,
+                                               int64_t n_unique, const int* uniquecoeffindices,
+                                               const float* manycoeff_arr, const float* xcoeff_arr) {
+  BinnedSplineHandler* b = (BinnedSplineHandler*)calloc(1, sizeof(BinnedSplineHandler));
+  b->base.nParams = (short)nParams;
+  b->base.SplineInfoArray = (FastSplineInfo*)calloc((size_t)nParams, sizeof(FastSplineInfo));
+  b->base.SplineSegments = (short*)calloc((size_t)nParams, sizeof(short));
+  b->base.ParamValues = (float*)calloc((size_t)nParams, sizeof(float));
+  for (int j = 0; j < nParams; ++j) {
+    b->base.SplineInfoArray[j].nPts = n_pts[j];
+    b->base.SplineInfoArray[j].n_x = n_pts[j] > 0 ? n_pts[j] : 0;
+    b->base.SplineInfoArray[j].xPts = knot_x + (size_t)j * (size_t)max_knots;
+  }
+  b->n_slots = n_slots; b->n_unique = n_unique;
+  b->uniquesplinevec_Monolith = uniquesplinevec_Monolith; b->coeffindexvec = coeffindexvec;
+  b->uniquecoeffindices = uniquecoeffindices; b->manycoeff_arr = manycoeff_arr; b->xcoeff_arr = xcoeff_arr;
+  b->weightvec_Monolith = (float*)malloc(sizeof(float) * (size_t)(n_slots > 0 ? n_slots : 1));
+  for (int64_t i = 0; i < n_slots; ++i) b->weightvec_Monolith[i] = 1.0f;     /* flat splines stay at 1 (.cpp:236,283) */
+  return b;
+}
+M3O_API void m3o_binned_destroy(BinnedSplineHandler* b) {
+  if (!b) return;
+  free(b->base.SplineInfoArray); free(b->base.SplineSegments); free(b->base.ParamValues); free(b->weightvec_Monolith);
+  free(b);
+}
+M3O_API void m3o_binned_set_pointers(BinnedSplineHandler* b, const double* pars) { m3o_set_spline_pointers(&b->base, pars); }
+
+/* BinnedSplineHandler::CalcSplineWeights (Splines/BinnedSplineHandler.cpp:306-341) */
+static void binned_calc_spline_weights(BinnedSplineHandler* h) {
+  const int64_t n = h->n_unique;
+  #pragma omp parallel for simd if (g_multithread)
+  for (int64_t iCoeff = 0; iCoeff < n; ++iCoeff) {
+    const int iSpline = h->uniquecoeffindices[iCoeff];
+    const short uniqueIndex = (short)h->uniquesplinevec_Monolith[iSpline];
+    const short currentsegment = (short)h->base.SplineSegments[uniqueIndex];
+    const int segCoeff = h->coeffindexvec[iSpline] + currentsegment;
+    const int coeffOffset = segCoeff * nCoeff;
+    const float y = h->manycoeff_arr[coeffOffset + 0];
+    const float b = h->manycoeff_arr[coeffOffset + 1];
+    const float c = h->manycoeff_arr[coeffOffset + 2];
+    const float d = h->manycoeff_arr[coeffOffset + 3];
+    const float xvar = (float)(*h->base.SplineInfoArray[uniqueIndex].splineParsPointer);   /* :327, M3::float_t */
+    const float dx = xvar - h->xcoeff_arr[segCoeff];                                       /* :329 */
+    float weight = fmaf(dx, fmaf(dx, fmaf(dx, d, c), b), y);                               /* :332 */
+    if (weight < 0) weight = 0.;                                                           /* :337 */
+    h->weightvec_Monolith[iSpline] = weight;
+  }
+}
+/* BinnedSplineHandler::Evaluate (:295-303) */
+M3O_API void m3o_binned_evaluate(BinnedSplineHandler* b) {
+  m3o_find_spline_segment(&b->base);
+  binned_calc_spline_weights(b);
+}
+M3O_API const float* m3o_binned_weights(const BinnedSplineHandler* b) { return b->weightvec_Monolith; }
+M3O_API const short* m3o_binned_segments(const BinnedSplineHandler* b) { return b->base.SplineSegments; }
+
 /* ============================================================================================
  * Samples: EventInfo (Samples/FarDetectorCoreInfoStruct.h:82-126) + SampleHandlerFD state
  * ========================================================================================== */
@@ -375,6 +454,7 @@ typedef struct {
   int FirstTimeW2;   /* Samples/SampleHandlerFD.h: FirstTimeW2 = true initially */
   int UpdateW2;      /* LikelihoodOptions:UpdateW2 (Samples/SampleHandlerFD.cpp:64) */
   SMonolith* SplineHandler;
+  struct BinnedSplineHandler_* BinnedHandler;   /* the other SplineBase implementation (either/or) */
 } SampleHandlerFD;
 
 /* binning description: for each sample, nDim then per dim nbins; edges concatenated */
@@ -479,6 +559,34 @@ M3O_API void m3o_sample_set_events(SampleHandlerFD* s, const int* sample_id, con
   }
 }
 
+
+/* The same wiring with a BinnedSplineHandler (Samples/SampleHandlerFD.cpp:1196-1242): after the
+ * oscillation pointer every event gets one pointer per binned spline that applies to it --
+ * BinnedSplineHandler::retPointer(...) = &weightvec_Monolith[index] -- in the order GetEventSplines
+ * returned them; then the experiment's extra weights.  n_per_event[e] pointers, indices concatenated. */
+M3O_API void m3o_sample_set_events_binned(SampleHandlerFD* s, const int* sample_id, const double* kin,
+                                          int n_norm_per_event, const short* norm_idx, const double* norm_base,
+                                          const float* osc_base, const int* osc_idx,
+                                          BinnedSplineHandler* binned, const uint32_t* n_per_event, const int* spline_index,
+                                          const float* static_w) {
+  m3o_sample_set_events(s, sample_id, kin, n_norm_per_event, norm_idx, norm_base, osc_base, osc_idx, NULL, static_w);
+  s->BinnedHandler = binned;
+  uint64_t off = 0;
+  for (unsigned int e = 0; e < s->nEvents; ++e) {
+    EventInfo* ev = &s->MCSamples[e];
+    const int n_old = ev->n_tw, n_b = (int)n_per_event[e];
+    const float** tw = (const float**)malloc(sizeof(float*) * (size_t)(n_old + n_b > 0 ? n_old + n_b : 1));
+    int nt = 0, k = 0;
+    if (osc_base) tw[nt++] = ev->total_weight_pointers[k++];
+    for (int j = 0; j < n_b; ++j) tw[nt++] = &binned->weightvec_Monolith[spline_index[off + (uint64_t)j]];
+    while (k < n_old) tw[nt++] = ev->total_weight_pointers[k++];
+    free(ev->total_weight_pointers);
+    ev->total_weight_pointers = tw;
+    ev->n_tw = nt;
+    off += (uint64_t)n_b;
+  }
+}
+
 /* SampleHandlerFD::CalcWeightTotal (Samples/SampleHandlerFD.cpp:568-594) */
 static inline float CalcWeightTotal(const EventInfo* restrict MCEvent) {
   float TotalWeight = 1.0;
@@ -559,6 +667,7 @@ static void FillArray(SampleHandlerFD* s) {
 M3O_API void m3o_reweight(SampleHandlerFD* s) {
   ResetHistograms(s);
   if (s->SplineHandler) m3o_evaluate(s->SplineHandler);
+  if (s->BinnedHandler) m3o_binned_evaluate(s->BinnedHandler);
   if (g_multithread) FillArray_MP(s); else FillArray(s);
   if (!s->UpdateW2) s->FirstTimeW2 = 0;
 }

@@ -1,0 +1,78 @@
+"""BASELINE config 4 shape: BinnedSplineHandler evaluation + N weight pointers per event + Barlow-Beeston
+with live W2, B200 path (C ABI) against the CPU oracle.  Bars: segments and bins bit-exact, binned-spline
+weights and per-event weights bit-exact against the serial oracle build (same fmaf nesting, same product
+order), -lnL <= 1e-6 relative (north_star)."""
+import numpy as np
+import pytest
+
+from mach3_b200 import handlers, lib
+from mach3_b200.synth import binned as B
+from oracle import binding as O
+
+pytestmark = pytest.mark.gpu
+LLH_RTOL = 1e-6
+
+
+@pytest.fixture(autouse=True, params=["serial", "multithread"])
+def oracle_build(request):
+    O.set_multithread(request.param == "multithread")
+    yield request.param
+    O.set_multithread(True)
+
+
+def _set(w, step, bsh, osh, gsh, gd, osc_step=None):
+    sp, nm = B.proposal(w, step)
+    bsh.set_params(sp); osh.norm_vals[:] = nm
+    gd["pars"][:] = sp; gd["norm"][:] = nm
+    if osc_step is not None:
+        osc = B.make_osc(w, osc_step)
+        osh.osc_w[:] = osc; gd["osc"][:] = osc
+        gsh.OscillatorEvaluated()
+
+
+@pytest.mark.parametrize("ts", [lib.BARLOW_BEESTON, lib.POISSON])
+def test_binned_spline_path_matches_oracle(oracle_build, ts):
+    w = B.CFG4_SMALL
+    exact = oracle_build == "serial"
+    bsh, osh, od = O.build_binned_from_workload(w, update_w2=True, test_statistic=ts)
+    gsh, gd = handlers.build_binned_from_workload(w, update_w2=True, test_statistic=ts, keep_event_weights=True)
+    np.testing.assert_array_equal(gsh.GetEventBins(), osh.event_bins())
+    data = None
+    for i, step in enumerate((-1, 0, 1, -2, 2, -3, -4, 3)):
+        _set(w, step, bsh, osh, gsh, gd, osc_step=i)
+        osh.Reweight(); gsh.Reweight()
+        if data is None:
+            data = np.random.default_rng(3).poisson(osh.mc).astype(np.float64)
+            osh.AddData(data); gsh.AddData(data)
+            osh.Reweight(); gsh.Reweight()      # W2 is live: same state on both sides
+        o, g = osh.GetLikelihood(), gsh.GetLikelihood()
+        seg, _ = gsh.SplineHandler.FindSplineSegment()
+        np.testing.assert_array_equal(seg, bsh.segments)
+        wv = gsh.SplineHandler.weightvec_Monolith
+        np.testing.assert_array_equal(wv, bsh.weights)            # same fmaf nesting, same clamp: bit-exact
+        assert (wv >= 0).all()
+        sw, tw = gsh.GetEventWeight()
+        if exact:
+            np.testing.assert_array_equal(tw, osh.event_weights())
+        else:
+            np.testing.assert_allclose(tw, osh.event_weights(), rtol=1e-5, atol=0)
+        mc, w2 = gsh.GetMCArray(), gsh.GetW2Array()
+        np.testing.assert_allclose(mc, osh.mc, rtol=1e-12 if exact else 1e-6, atol=1e-12)
+        np.testing.assert_allclose(w2, osh.w2, rtol=1e-12 if exact else 1e-6, atol=1e-12)
+        assert g == pytest.approx(o, rel=1e-10 if exact else LLH_RTOL, abs=1e-9)
+    assert (bsh.weights == 0).any(), "the workload should exercise the negative-weight clamp"
+
+
+def test_binned_rejects_inconsistent_input():
+    w = B.CFG4_SMALL
+    spl = B.make_binned_splines(w)
+    h = lib.Handle()
+    bad = dict(spl); bad["uniquecoeffindices"] = np.array([w.n_slots + 5], np.int32)
+    with pytest.raises(lib.M3BError):
+        h.upload_binned_splines(bad)
+    h.close()
+    h = lib.Handle()
+    h.upload_binned_splines(spl)
+    with pytest.raises(lib.M3BError):       # events first
+        h.upload_event_binned_splines(np.zeros(4, np.uint32), np.zeros(0, np.int32))
+    h.close()
