@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--events", type=int, default=0, help="override the total event count (debug)")
     ap.add_argument("--exchange", default=os.environ.get("M3B_EXCHANGE", "nccl"), choices=["nccl", "peer"])
     ap.add_argument("--tile", type=int, default=int(os.environ.get("M3B_TILE", "0")))
@@ -345,9 +345,75 @@ def main_b200(args):
     h.close()
 
 
+def main_cfg4(args):
+    """BASELINE config 4 (BinnedSplineHandler workload), single GPU, optional bench line:
+    python bench.py --workload cfg4 [--events N]   (not the default; the headline stays cfg2)."""
+    import torch
+    from mach3_b200 import handlers, lib
+    from mach3_b200.synth import binned as B
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; no CPU fallback")
+    w = B.CFG4 if not args.events else B.CFG4.scaled(n_events=args.events, n_grid=max(1000, int(B.CFG4.n_grid * args.events / B.CFG4.n_events)))
+    t0 = time.perf_counter()
+    sh, d = handlers.build_binned_from_workload(w, update_w2=True)
+    h = sh.handle
+    t_setup = time.perf_counter() - t0
+    W, K = args.warmup, args.steps
+    props = {k: B.proposal(w, k) for k in range(-1, W + K + 2)}
+
+    def step(k):
+        d["pars"][:], d["norm"][:] = props[k]
+        sh.Reweight()
+
+    step(-1); sh.GetLikelihood()
+    sh.AddData(np.random.default_rng(w.seed).poisson(sh.GetMCArray()).astype(np.float64))
+    for k in range(W):
+        step(k)
+    sh.GetLikelihood()
+    h.set_timing(True); h.kernel_time()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for k in range(W, W + K):
+        step(k)
+    llh = sh.GetLikelihood()
+    t_async = time.perf_counter() - t1
+    kern_ms, kern_n = h.kernel_time()
+    t1 = time.perf_counter()
+    for k in range(K):
+        step(W + (k % K)); llh_e = sh.GetLikelihood()
+    t_e2e = time.perf_counter() - t1
+    n_act = int(d["spl"]["uniquecoeffindices"].size)
+    n_ptr = int(d["ev"]["spline_index"].size)
+    alg = n_act * (16 + 4 + 4) + w.n_events * 8 + n_ptr * 4 * 2       # eval: {y,b,c,d}+x read, weight write; fill: index + gather
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kms = kern_ms / max(kern_n, 1)
+    line = {"metric": "reweighted events/s per MCMC step (binned-spline eval + fill + Barlow-Beeston LLH)",
+            "value": w.n_events / (t_async / K), "unit": "events/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_async / K, "binned_spline_evals_per_s": n_act / (t_async / K), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
+            "config": {"workload": w.name, "events": w.n_events, "active_binned_splines": n_act, "weight_pointers": n_ptr,
+                       "slots": w.n_slots, "bins": w.n_bins, "setup_s": round(t_setup, 1),
+                       "l2": "coefficient rows (%.0f MB/step) stream from HBM; the compact weight array (%.0f MB) is gathered through L2"
+                             % (n_act * 20 / 1e6, n_act * 4 / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (kms * 1e-3) / 1e9 / peak, "kernel": "m3b::binned_eval_kernel + m3b::binned_fill_kernel",
+                         "kernel_ms": kms, "algorithmic_bytes_per_launch": alg, "traffic": None},
+            "e2e": {"value": w.n_events / (t_e2e / K), "unit": "events/s", "ms_per_step": 1e3 * t_e2e / K,
+                    "h2d_bytes_per_step": 12 * w.n_systs + 4 * w.n_norm_params, "d2h_bytes_per_step": 16},
+            "gpu_launches": int(2 * K), "llh": {"last": llh, "last_e2e": llh_e}}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "cfg4":
+        main_cfg4(a)
+    elif a.impl == "reference":
         main_reference(a)
     else:
         main_b200(a)

@@ -177,6 +177,13 @@ M3B_API int m3b_step(m3b_handle* h, const double* spline_pars, const double* nor
 M3B_API int m3b_step_segments(m3b_handle* h, const float* param_values, const int16_t* segments,
                               const double* norm_pars, const float* osc_w);
 M3B_API int m3b_llh(m3b_handle* h, double* total, double* per_sample /* [n_samples] or NULL */);
+/* m3b_step_batch: n_sets proposals against the same events (parallel chains, DelayedMR2T2 stages
+ *   Fitters/DelayedMR2T2.cpp:110-157, RunLLHScan Fitters/FitterBase.cpp:742-798).  spline_pars[n_sets*n_params],
+ *   norm_pars[n_sets*n_norm_values] row-major; sets are evaluated in order with the reference's sequential
+ *   semantics (cached segments, W2 freeze); ONE host synchronisation; llh_total[n_sets] (-lnL each),
+ *   llh_per_sample[n_sets*n_samples] or NULL.  osc_w (or NULL) applies to the whole batch.                 */
+M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars,
+                           const float* osc_w, double* llh_total, double* llh_per_sample);
 /* m3b_eval_weights = SMonolithGPU::RunGPU_SplineMonolith exactly (Splines/gpuSplineUtils.cu:444-512):
  *   evaluate all responses, multiply per event, and enqueue the copy of the per-event totals into the
  *   caller's host array (cpu_total_weights, pinned by InitGPU_SplineMonolith :139) -- asynchronous until

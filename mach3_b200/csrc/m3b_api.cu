@@ -64,6 +64,7 @@ M3B_API void m3b_destroy(m3b_handle* h) {
     if (h->step_ev[i]) cudaEventDestroy(h->step_ev[i]);
   }
   if (h->h_llh) cudaFreeHost(h->h_llh);
+  if (h->h_batch) cudaFreeHost(h->h_batch);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -724,7 +725,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   a.tile_begin = 0;
   a.osc_host = osc_zc; a.osc_store = h->d_osc;
   if (h->use_tma) { a.tile_counter = h->d_tile_counter; a.n_stages = h->tma_stages; a.tma = h->tma; }
-  a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->h_llh_dev;
+  a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->llh_host_override ? h->llh_host_override : h->h_llh_dev;
   a.evt_spline_w = h->d_evt_spline_w; a.evt_total_w = h->d_evt_total_w;
   a.trace = h->d_trace;
   if (mode == kFused) {
@@ -852,6 +853,44 @@ M3B_API int m3b_eval_weights(m3b_handle* h, const float* param_values, const int
   if (rc != M3B_OK) return rc;
   if (host_total_weights)
     CK(cudaMemcpyAsync(host_total_weights, h->d_evt_spline_w, sizeof(float) * h->n_events, cudaMemcpyDeviceToHost, h->stream));
+  return M3B_OK;
+}
+
+// Batched proposals (BASELINE config 5: parallel chains, DelayedMR2T2 stages, LLH scans): n_sets parameter
+// vectors against the same events.  Sets are evaluated in order with the reference's sequential semantics
+// (cached segments of SplineBase::FindSplineSegment, W2 freeze), all launches are enqueued back to back and
+// the host synchronises ONCE; every set's -lnL lands in its own slot of a mapped host array.
+M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars,
+                           const float* osc_w, double* llh_total, double* llh_per_sample) {
+  REQUIRE(h && llh_total, M3B_ERR_INVALID, "m3b_step_batch: null argument");
+  REQUIRE(n_sets > 0, M3B_ERR_INVALID, "m3b_step_batch: n_sets must be positive");
+  REQUIRE(h->peer_world == 0 && !(h->cfg.flags & M3B_FLAG_NO_FUSED_LLH), M3B_ERR_STATE, "m3b_step_batch: single-GPU fused handles only");
+  REQUIRE(h->n_bins > 0, M3B_ERR_STATE, "m3b_step_batch: upload binning and events first");
+  CK(cudaSetDevice(h->device));
+  const size_t slot = static_cast<size_t>(1 + h->n_samples);
+  if (h->batch_cap < static_cast<size_t>(n_sets)) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_batch) cudaFreeHost(h->h_batch);
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_batch), sizeof(double) * slot * n_sets, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_batch_dev), h->h_batch, 0));
+    h->batch_cap = static_cast<size_t>(n_sets);
+  }
+  int rc = M3B_OK;
+  for (int32_t i = 0; i < n_sets && rc == M3B_OK; ++i) {
+    h->llh_host_override = h->h_batch_dev + slot * i;
+    rc = step_common(h, h->P > 0 ? spline_pars + static_cast<size_t>(i) * h->P : nullptr,
+                     h->n_norm_values > 0 ? norm_pars + static_cast<size_t>(i) * h->n_norm_values : nullptr,
+                     i == 0 ? osc_w : nullptr, kFused);
+  }
+  h->llh_host_override = nullptr;
+  if (rc != M3B_OK) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  for (int32_t i = 0; i < n_sets; ++i) {
+    llh_total[i] = h->h_batch[slot * i];
+    if (llh_per_sample) for (int s = 0; s < h->n_samples; ++s) llh_per_sample[static_cast<size_t>(i) * h->n_samples + s] = h->h_batch[slot * i + 1 + s];
+  }
+  // m3b_llh after a batch returns the last set's value
+  for (size_t k = 0; k < slot; ++k) h->h_llh[k] = h->h_batch[slot * (n_sets - 1) + k];
   return M3B_OK;
 }
 

@@ -134,6 +134,10 @@ struct m3b_handle {
   uint64_t b_gather_per_step = 0;
   int binned_eval_grid = 0;
 
+  // ---- batched proposals (m3b_step_batch): one -lnL slot per set in mapped host memory
+  double* h_batch = nullptr; double* h_batch_dev = nullptr; size_t batch_cap = 0;
+  double* llh_host_override = nullptr;
+
   uint64_t steps = 0, launches = 0;
 
   // ---- optional kernel timing

@@ -23,7 +23,7 @@ EXPORTS = (
     "m3b_upload_binned_splines", "m3b_upload_event_binned_splines", "m3b_read_binned_weights",
     "m3b_upload_binning", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer",
     "m3b_set_test_statistic", "m3b_reset_w2",
-    "m3b_step", "m3b_step_segments", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
+    "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
     "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
     "m3b_get_info", "m3b_set_timing", "m3b_kernel_time", "m3b_block_trace",
@@ -230,6 +230,16 @@ class Handle:
         self._keep = (sp, nm, osc_w)
         fn = {"fused": self.L.m3b_step, "fill": self.L.m3b_step_fill, "peer": self.L.m3b_step_peer}[mode]
         self._ck(fn(self.h, _p(sp), _p(nm), _p(osc_w)))
+
+    def step_batch(self, spline_pars, norm_pars=None, osc_w=None, per_sample=False):
+        """n_sets proposals (rows of spline_pars / norm_pars) in one call; returns -lnL per set."""
+        sp = _c(spline_pars, np.float64)
+        n_sets = sp.shape[0] if sp is not None else np.asarray(norm_pars).shape[0]
+        nm = _c(norm_pars, np.float64)
+        tot = np.zeros(n_sets, np.float64)
+        ps = np.zeros((n_sets, max(self.n_samples, 1)), np.float64) if per_sample else None
+        self._ck(self.L.m3b_step_batch(self.h, C.c_int32(n_sets), _p(sp), _p(nm), _p(osc_w), _p(tot), _p(ps)))
+        return (tot, ps[:, :self.n_samples]) if per_sample else tot
 
     def step_segments(self, param_values, segments, norm_pars=None, osc_w=None):
         pv, sg, nm = _c(param_values, np.float32), _c(segments, np.int16), _c(norm_pars, np.float64)

@@ -118,12 +118,12 @@ def make_binned_events(w: BinnedWorkload):
         spline_index = np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, np.int32)
     else:  # large workloads: a contiguous run of systematics starting at a random one (cheap to generate)
         start = rng.integers(0, P, E)
-        tot = int(n_per.sum())
-        ev = np.repeat(np.arange(E), n_per)
-        j = np.arange(tot) - np.repeat(np.cumsum(n_per) - n_per, n_per)
-        syst = (start[ev] + j) % P
-        syst2 = np.sort(np.stack([ev, syst], 1).view([("e", np.int64), ("s", np.int64)]).reshape(-1), order=["e", "s"])
-        spline_index = (syst2["s"] * G + grid_bin[syst2["e"]]).astype(np.int32)
+        npi = n_per.astype(np.int64)
+        tot = int(npi.sum())
+        ev = np.repeat(np.arange(E, dtype=np.int64), npi)
+        j = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(npi) - npi, npi)
+        key = np.sort(ev * P + (start[ev] + j) % P)              # ascending systematic inside each event
+        spline_index = ((key % P) * G + grid_bin[key // P]).astype(np.int32)
     kin = np.empty((2, E))
     kin[0] = rng.gamma(3.0, 0.3, E)
     kin[1] = rng.uniform(0, np.pi, E)

@@ -312,3 +312,31 @@ def test_zero_copy_oscillation_weights_match_the_copied_path(oracle_build):
         np.testing.assert_array_equal(w0, w1)
         np.testing.assert_allclose(m0, m1, rtol=ORDER_RTOL, atol=1e-13)
         assert l0 == pytest.approx(l1, rel=1e-10, abs=1e-9)
+
+
+def test_batched_proposals_match_sequential_oracle(oracle_build):
+    """BASELINE config 5 shape (reduced): a batch of parameter sets, perturbations around one point so only a few
+    segments per parameter are active, evaluated by m3b_step_batch; every set's -lnL against the oracle run
+    sequentially (same cached-segment history)."""
+    w = synth.CFG5.scaled(40_003)
+    mono, osh, od = O.build_from_workload(w)
+    gsh, gd = handlers.build_from_workload(w)
+    _set(w, -1, mono, osh, gsh, gd)
+    osh.Reweight(); gsh.Reweight(); gsh.GetLikelihood()
+    data = np.random.default_rng(9).poisson(osh.mc).astype(np.float64)
+    osh.AddData(data); gsh.AddData(data)
+    rng = np.random.default_rng(10)
+    n_sets = 48
+    sp0, nm0 = synth.proposal(w, 3)
+    sps = np.clip(sp0[None, :] + rng.normal(0, 0.3, (n_sets, w.n_params)), -2.9, 2.9)
+    nms = np.clip(nm0[None, :] + rng.normal(0, 0.05, (n_sets, w.n_norm_params)), 0.5, 1.5)
+    sps[5] = np.round(sps[5])            # a set sitting exactly on knots
+    tot, per = gsh.handle.step_batch(sps, nms, per_sample=True)
+    assert tot.shape == (n_sets,)
+    for i in range(n_sets):
+        mono.set_params(sps[i]); osh.norm_vals[:] = nms[i]
+        osh.Reweight()
+        o = osh.GetLikelihood()
+        assert tot[i] == pytest.approx(o, rel=1e-10 if _exact() else LLH_RTOL, abs=1e-9), i
+        assert per[i].sum() == pytest.approx(tot[i], rel=1e-12)
+    assert gsh.GetLikelihood() == tot[-1]
