@@ -6,6 +6,6 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 timeout 600 $TR --master-port 29511 tests/multigpu/parity_ranks.py > gpurun_out/multi_parity_$N.log 2>&1; echo "parity exit $?" >> gpurun_out/multi_parity_$N.log
 grep -v "^W\|^\[W\|warn" gpurun_out/multi_parity_$N.log | tail -14
 for ex in nccl peer; do
-  timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 100 --warmup 10 --exchange $ex > gpurun_out/bench_cfg3_${N}_$ex.json 2> gpurun_out/bench_cfg3_${N}_$ex.err; echo "bench $ex exit $?"
+  timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps ${STEPS:-100} --warmup 10 --exchange $ex > gpurun_out/bench_cfg3_${N}_$ex.json 2> gpurun_out/bench_cfg3_${N}_$ex.err; echo "bench $ex exit $?"
   tail -c 3000 gpurun_out/bench_cfg3_${N}_$ex.json; tail -5 gpurun_out/bench_cfg3_${N}_$ex.err
 done
