@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--events", type=int, default=0, help="override the total event count (debug)")
-    ap.add_argument("--exchange", default=os.environ.get("M3B_EXCHANGE", "nccl"), choices=["nccl", "peer"])
+    ap.add_argument("--exchange", default=os.environ.get("M3B_EXCHANGE", "auto"), choices=["auto", "nccl", "peer"],
+                    help="N>1 histogram exchange: the library's own peer-memory pull fused with the likelihood (peer), "
+                         "NCCL all-reduce + likelihood launch (nccl), or peer with NCCL as fallback (auto)")
     ap.add_argument("--tile", type=int, default=int(os.environ.get("M3B_TILE", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-events", type=int, default=200_000)
@@ -317,7 +319,7 @@ def main_b200(args):
             "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
             "config": {"workload": w.name, "events": E, "events_per_gpu": n_local, "responses_per_event": w.n_params,
                        "bins": w.n_bins, "tile_events": info.tile_events, "grid_blocks": info.grid_blocks,
-                       "smem_bytes": info.smem_bytes, "tma_stages": info.tma_stages, "exchange": ("none" if world == 1 else args.exchange),
+                       "smem_bytes": info.smem_bytes, "tma_stages": info.tma_stages, "exchange": ("none" if world == 1 else sh.exchange),
                        "l2": "inputs larger than L2: %.0f MB of coefficient rows stream per step per GPU, fresh "
                              "proposal (different segments) every step" % (info.active_bytes_per_step / 1e6),
                        "device_bytes": info.device_bytes, "setup_s": round(t_setup, 2), "host_cpu_affinity": numa},

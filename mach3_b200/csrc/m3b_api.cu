@@ -702,7 +702,15 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   const int nxt = mode == kFused ? (h->cur ^ 1) : h->cur;
   double* mc = h->d_hw[nxt];
   double* w2 = h->d_hw[nxt] + h->n_bins;
-  if (mode != kWeightsOnly) {
+  if (mode == kPeer) {
+    // the partial histogram goes into this rank's exported buffer (two parities); the reduced one is
+    // written to d_hw[cur] by the pull kernel
+    REQUIRE(h->peer_world > 0, M3B_ERR_STATE, "m3b_step_peer: call m3b_peer_export/import first");
+    ++h->peer_epoch;
+    double* part = h->d_inbox[h->peer_epoch & 1];
+    CK(cudaMemsetAsync(part, 0, sizeof(double) * h->n_bins * (w2_live ? 2 : 1), h->stream));
+    if (w2_live) h->d_w2_frozen = w2;
+  } else if (mode != kWeightsOnly) {
     if (!h->mc_zero[nxt]) CK(cudaMemsetAsync(mc, 0, sizeof(double) * h->n_bins, h->stream));
     if (w2_live && !h->w2_zero[nxt]) CK(cudaMemsetAsync(w2, 0, sizeof(double) * h->n_bins, h->stream));
     h->mc_zero[nxt] = false;
@@ -737,11 +745,10 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     if (next_live && (h->d_hw[other] + h->n_bins) != h->d_w2_frozen) { a.w2_next = h->d_hw[other] + h->n_bins; h->w2_zero[other] = true; }
   }
   if (mode == kPeer) {
-    REQUIRE(h->peer_world > 0, M3B_ERR_STATE, "m3b_step_peer: call m3b_peer_export/import first");
-    ++h->peer_epoch;
-    const int par = h->peer_epoch & 1;
+    double* part = h->d_inbox[h->peer_epoch & 1];
+    a.hist = part; a.w2 = w2_live ? part + h->n_bins : nullptr;
     a.peer_world = h->peer_world; a.peer_rank = h->peer_rank; a.peer_epoch = h->peer_epoch;
-    for (int r = 0; r < h->peer_world; ++r) { a.peer_inbox[r] = h->peer_inbox[par][r]; a.peer_flag[r] = h->peer_flag[par][r]; }
+    a.peer_flag_own = h->d_flags[0];
   }
   if (h->timing) {
     if (h->tev_used + 2 > h->tev.size()) {
@@ -761,14 +768,19 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   if (mode == kPeer) {
     const int par = h->peer_epoch & 1;
     LlhArgs l{};
-    l.data = h->d_data; l.sample_start = h->d_sample_start; l.n_bins = h->n_bins; l.n_samples = h->n_samples;
+    l.data = h->d_data; l.n_bins = h->n_bins; l.n_samples = h->n_samples;
     l.test_stat = h->test_stat; l.llh_dev = h->d_llh; l.llh_host = h->h_llh_dev;
-    l.peer_world = h->peer_world; l.inbox = h->d_inbox[par]; l.flags = h->d_flags[par]; l.epoch = h->peer_epoch;
+    l.peer_world = h->peer_world; l.epoch = h->peer_epoch;
+    for (int r = 0; r < h->peer_world; ++r) { l.peer_hist[r] = h->peer_inbox[par][r]; l.peer_flag[r] = h->peer_flag[0][r]; }
     l.hist_out = mc; l.w2_out = w2; l.w2_live = w2_live ? 1 : 0; l.status = h->d_status;
-    l.hist = mc; l.w2 = h->d_w2_frozen;
-    if (!w2_live) l.w2_out = nullptr;
-    CK(launch_llh(l, h->stream));
+    l.w2 = h->d_w2_frozen;
+    l.partial = h->d_llh_partial; l.ticket = h->d_llh_ticket;
+    for (int i = 0; i <= h->n_samples; ++i) l.sample_start_inline[i] = h->sample_start[i];
+    const int blocks = std::max(1, std::min(kLlhPullMaxBlocks, (h->n_bins + 511) / 512));
+    CK(launch_llh_pull(l, blocks, h->stream));
     ++h->launches;
+    h->mc_zero[nxt] = false;
+    if (w2_live) h->w2_zero[nxt] = false;
   }
   h->evt_weights_valid = h->d_evt_spline_w != nullptr;
   if (mode == kWeightsOnly) return M3B_OK;             // histograms, W2 state and step count untouched
@@ -988,15 +1000,18 @@ M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ip
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
   CK(cudaSetDevice(h->device));
   if (!h->d_inbox[0]) {
-    // one allocation: [2 parities][world * 2*n_bins doubles] then [2][world] flags (as doubles' worth of space)
-    const size_t inbox_d = static_cast<size_t>(world) * 2 * h->n_bins;
-    const size_t total_d = 2 * inbox_d + 2 * 8;   // 2*8 doubles = 128 B for 2x8 u32 flags (+slack)
+    // one exported allocation: [2 parities][mc[n_bins] | w2[n_bins]] then this rank's epoch flag
+    const size_t part_d = static_cast<size_t>(2) * h->n_bins;
+    const size_t total_d = 2 * part_d + 16;
     double* base = nullptr;
     CK(dev_alloc(h, &base, total_d));
     CK(cudaMemset(base, 0, total_d * sizeof(double)));
-    h->d_inbox[0] = base; h->d_inbox[1] = base + inbox_d;
-    h->d_flags[0] = reinterpret_cast<unsigned int*>(base + 2 * inbox_d);
-    h->d_flags[1] = h->d_flags[0] + 8;
+    h->d_inbox[0] = base; h->d_inbox[1] = base + part_d;
+    h->d_flags[0] = reinterpret_cast<unsigned int*>(base + 2 * part_d);
+    h->d_flags[1] = h->d_flags[0];
+    CK(dev_alloc(h, &h->d_llh_partial, static_cast<size_t>(kLlhPullMaxBlocks) * std::max(1, h->n_samples)));
+    CK(dev_alloc(h, &h->d_llh_ticket, 1));
+    CK(cudaMemset(h->d_llh_ticket, 0, sizeof(unsigned int)));
   }
   h->peer_world = world; h->peer_rank = rank;
   for (int par = 0; par < 2; ++par) { h->peer_inbox[par][rank] = h->d_inbox[par]; h->peer_flag[par][rank] = h->d_flags[par]; }
@@ -1017,10 +1032,10 @@ M3B_API int m3b_peer_import(m3b_handle* h, int32_t peer_rank, const void* ipc_ha
   CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
   h->ipc_opened.push_back(p);
   double* base = static_cast<double*>(p);
-  const size_t inbox_d = static_cast<size_t>(h->peer_world) * 2 * h->n_bins;
-  h->peer_inbox[0][peer_rank] = base; h->peer_inbox[1][peer_rank] = base + inbox_d;
-  h->peer_flag[0][peer_rank] = reinterpret_cast<unsigned int*>(base + 2 * inbox_d);
-  h->peer_flag[1][peer_rank] = h->peer_flag[0][peer_rank] + 8;
+  const size_t part_d = static_cast<size_t>(2) * h->n_bins;
+  h->peer_inbox[0][peer_rank] = base; h->peer_inbox[1][peer_rank] = base + part_d;
+  h->peer_flag[0][peer_rank] = reinterpret_cast<unsigned int*>(base + 2 * part_d);
+  h->peer_flag[1][peer_rank] = h->peer_flag[0][peer_rank];
   return M3B_OK;
 }
 

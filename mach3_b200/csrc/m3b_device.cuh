@@ -1,6 +1,6 @@
 // m3b_device.cuh -- device-side pieces shared by the fill kernels: PTX helpers (mbarrier, bulk/TMA
 // copies, streaming loads), the test statistics of SampleHandlerBase::GetTestStatLLH, the block-level
-// likelihood reduction and the common block epilogue (flush -> ticket -> peer push | fused -lnL).
+// likelihood reduction and the common block epilogue (flush -> ticket -> publish to peers | fused -lnL).
 #pragma once
 #include "m3b_internal.h"
 #include <cuda_runtime.h>
@@ -264,19 +264,12 @@ __device__ __forceinline__ void finish_block(const FillArgs& a, const double* s_
 
   if (a.weights_only) { if (tid == 0) *a.ticket = 0u; return; }
   if (a.peer_world > 0) {
-    // push the finished partial histogram into every rank's inbox over NVLink peer memory
-    const int nb2 = a.n_bins * (w2_live ? 2 : 1);
-    for (int r = 0; r < a.peer_world; ++r) {
-      double* dst = a.peer_inbox[r] + static_cast<int64_t>(a.peer_rank) * 2 * a.n_bins;
-      for (int i = tid; i < nb2; i += NT) dst[i] = __ldcg((i < a.n_bins ? a.hist : a.w2 - a.n_bins) + i);
+    // the whole grid has flushed into this rank's exported buffer: publish the epoch; the peers pull
+    if (tid == 0) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag_own), "r"(a.peer_epoch) : "memory");
+      *a.ticket = 0u;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < a.peer_world) {
-      unsigned int* f = a.peer_flag[tid] + a.peer_rank;
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.peer_epoch) : "memory");
-    }
-    if (tid == 0) *a.ticket = 0u;
     return;
   }
   if (!a.fuse_llh) { if (tid == 0) *a.ticket = 0u; return; }

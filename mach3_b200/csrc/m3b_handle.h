@@ -120,6 +120,7 @@ struct m3b_handle {
   double* peer_inbox[2][8] = {};
   unsigned int* peer_flag[2][8] = {};
   unsigned int peer_epoch = 0;
+  double* d_llh_partial = nullptr; unsigned int* d_llh_ticket = nullptr;
   int32_t* d_status = nullptr;
   std::vector<void*> ipc_opened;
   std::vector<void*> registered;

@@ -135,10 +135,11 @@ struct FillArgs {
   // optional per-block timeline (m3b_block_trace): 8 x u64 globaltimer ns per block
   unsigned long long* trace;
   alignas(16) unsigned char step_inline[kStepInlineMax];
-  // peer exchange (multi-GPU, own collective): push partial hist into every rank's inbox
+  // peer exchange (multi-GPU, own collective): in peer mode `hist`/`w2` point into this rank's exported
+  // partial-histogram buffer; when the whole grid has flushed, the last block publishes `peer_epoch` in
+  // this rank's flag and the peers PULL the buffer over NVLink (llh_pull_kernel)
   int32_t peer_world, peer_rank;
-  double* peer_inbox[8];       // peer_inbox[r] = rank r's inbox base; slot for us at [peer_rank * 2*n_bins]
-  unsigned int* peer_flag[8];  // peer_flag[r][peer_rank] <- epoch
+  unsigned int* peer_flag_own;
   unsigned int peer_epoch;
 };
 
@@ -147,9 +148,14 @@ struct LlhArgs {
   const int32_t* sample_start;
   int32_t n_bins, n_samples, test_stat;
   double* llh_dev; double* llh_host;
-  // peer mode: sum inbox slots in rank order instead of reading hist
-  int32_t peer_world; const double* inbox; const unsigned int* flags; unsigned int epoch;
+  // peer (pull) mode: every rank reads all ranks' partial histograms over NVLink peer memory, in rank order
+  int32_t peer_world; unsigned int epoch;
+  const double* peer_hist[8];        // rank r's exported partial {mc[n_bins], w2[n_bins]} of this epoch's parity
+  const unsigned int* peer_flag[8];  // rank r's epoch flag
   double* hist_out; double* w2_out; int32_t w2_live;
+  double* partial;                   // [blocks * n_samples] per-block per-sample sums
+  unsigned int* ticket;
+  int32_t sample_start_inline[65];
   int32_t* status;   // set to 1 on peer timeout
 };
 
@@ -191,6 +197,8 @@ struct RetileArgs {
 // launchers (m3b_kernels.cu)
 cudaError_t launch_fill(const FillArgs& a, int variant, int grid, int smem_bytes, cudaStream_t s);
 cudaError_t launch_llh(const LlhArgs& a, cudaStream_t s);
+cudaError_t launch_llh_pull(const LlhArgs& a, int blocks, cudaStream_t s);
+constexpr int kLlhPullMaxBlocks = 32;
 cudaError_t launch_bins(const BinArgs& a, cudaStream_t s);
 cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s);
 cudaError_t fill_occupancy(int T, int variant, int smem_bytes, int* blocks_per_sm);

@@ -179,43 +179,95 @@ cudaError_t fill_occupancy(int T, int variant, int smem, int* bps) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// likelihood alone (after an external all-reduce, or after the peer push: sums inbox slots)
+// likelihood alone (after an external all-reduce of the histogram)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) llh_kernel(const __grid_constant__ LlhArgs a) {
   __shared__ double s_part[kMaxSamples * 32];
-  __shared__ int s_ok;
-  const double* hist = a.hist;
-  const double* w2 = a.w2;
-  if (a.peer_world > 0) {
-    // wait (bounded) until every rank's partial histogram of this epoch has landed in our inbox
-    if (threadIdx.x == 0) s_ok = 1;
-    __syncthreads();
-    if (threadIdx.x < a.peer_world) {
-      const unsigned int* f = a.flags + threadIdx.x;
-      unsigned int v = 0;
-      const long long t0 = clock64();
-      while (true) {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        if (v == a.epoch) break;
-        if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }   // ~2 s: give up, report
-        __nanosleep(200);
-      }
+  block_llh(a.hist, a.w2, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, s_part);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The library's own histogram exchange + likelihood, fused (multi-GPU, one process per GPU):
+// every rank PULLS all ranks' partial histograms over NVLink peer memory (plain P2P loads on CUDA-IPC
+// mapped pointers), sums them in rank order -- so all ranks hold bit-identical totals -- and reduces
+// -lnL, block-then-grid: block b owns a contiguous slice of the bins, the last block to finish adds the
+// per-block per-sample sums in block order.  Replaces ncclAllReduce + a separate likelihood launch.
+// Waiting for the peers' epoch flags is bounded (~2 s); a timeout is reported, never a hang.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) llh_pull_kernel(const __grid_constant__ LlhArgs a) {
+  __shared__ double s_part[kMaxSamples * 16];
+  __shared__ int s_ok, s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
+  if (tid < a.peer_world) {
+    unsigned int v = 0;
+    const long long t0 = clock64();
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.peer_flag[tid]) : "memory");
+      if (static_cast<int>(v - a.epoch) >= 0) break;          // a peer may already be one step ahead
+      if (clock64() - t0 > 4000000000LL) { s_ok = 0; break; }
+      __nanosleep(100);
     }
-    __syncthreads();
-    if (!s_ok) { if (threadIdx.x == 0) { *a.status = 1; a.llh_dev[0] = nan(""); if (a.llh_host) a.llh_host[0] = nan(""); } return; }
-    // fixed rank order => every rank computes the bit-identical global histogram
-    const int nb2 = a.n_bins * (a.w2_live ? 2 : 1);
-    for (int i = threadIdx.x; i < nb2; i += blockDim.x) {
-      double acc = 0.;
-      for (int r = 0; r < a.peer_world; ++r) acc += __ldcg(a.inbox + static_cast<int64_t>(r) * 2 * a.n_bins + i);
-      if (i < a.n_bins) a.hist_out[i] = acc; else a.w2_out[i - a.n_bins] = acc;
-    }
-    __threadfence();
-    __syncthreads();
-    hist = a.hist_out;
-    if (a.w2_live) w2 = a.w2_out;
   }
-  block_llh(hist, w2, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, s_part);
+  __syncthreads();
+  if (!s_ok) {
+    if (tid == 0 && blockIdx.x == 0) { *a.status = 1; a.llh_dev[0] = nan(""); if (a.llh_host) a.llh_host[0] = nan(""); }
+    return;
+  }
+  const int per = (a.n_bins + gridDim.x - 1) / gridDim.x;
+  const int b0 = blockIdx.x * per, b1 = min(a.n_bins, b0 + per);
+  for (int s = 0; s < a.n_samples; ++s) {
+    const int lo = max(b0, a.sample_start_inline[s]), hi = min(b1, a.sample_start_inline[s + 1]);
+    double acc = 0.;
+    for (int b = lo + tid; b < hi; b += blockDim.x) {
+      double mc = 0., w2 = 0.;
+      for (int r = 0; r < a.peer_world; ++r) mc += __ldcv(a.peer_hist[r] + b);          // fixed rank order
+      a.hist_out[b] = mc;
+      if (a.w2_live) {
+        for (int r = 0; r < a.peer_world; ++r) w2 += __ldcv(a.peer_hist[r] + a.n_bins + b);
+        a.w2_out[b] = w2;
+      } else if (a.w2) {
+        w2 = a.w2[b];
+      }
+      acc += test_stat_llh(a.test_stat, a.data[b], mc, w2);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_part[s * 16 + warp] = acc;
+  }
+  __syncthreads();
+  if (tid < a.n_samples) {
+    double tot = 0.;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += s_part[tid * 16 + w];
+    a.partial[blockIdx.x * a.n_samples + tid] = tot;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < a.n_samples) {
+    double tot = 0.;
+    for (int b = 0; b < static_cast<int>(gridDim.x); ++b) tot += __ldcg(a.partial + b * a.n_samples + tid);
+    s_part[tid] = tot;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.;
+    for (int s = 0; s < a.n_samples; ++s) {
+      tot += s_part[s];
+      a.llh_dev[1 + s] = s_part[s];
+      if (a.llh_host) a.llh_host[1 + s] = s_part[s];
+    }
+    a.llh_dev[0] = tot;
+    if (a.llh_host) a.llh_host[0] = tot;
+    *a.ticket = 0u;
+  }
+}
+cudaError_t launch_llh_pull(const LlhArgs& a, int blocks, cudaStream_t s) {
+  llh_pull_kernel<<<blocks, 512, 0, s>>>(a);
+  return cudaGetLastError();
 }
 cudaError_t launch_llh(const LlhArgs& a, cudaStream_t s) {
   llh_kernel<<<1, 1024, 0, s>>>(a);

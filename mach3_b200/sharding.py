@@ -52,12 +52,33 @@ class ShardedSampleHandler:
         self.exchange = exchange if self.world > 1 else "none"
         self._hist = None
         if self.world > 1:
-            if exchange == "peer":
-                mine = handle.peer_export(self.rank, self.world)
+            if exchange in ("peer", "auto"):
+                # the library's own exchange: CUDA-IPC peer mappings of every rank's partial histogram.
+                # "auto" falls back to NCCL (on all ranks together) if the mappings cannot be made.
+                ok = 1
+                try:
+                    mine = handle.peer_export(self.rank, self.world)
+                except Exception:
+                    if exchange == "peer":
+                        raise
+                    mine, ok = None, 0
                 allh = [None] * self.world
                 dist.all_gather_object(allh, mine)
-                for r in range(self.world):
-                    handle.peer_import(r, allh[r])
+                if all(x is not None for x in allh):
+                    try:
+                        for r in range(self.world):
+                            handle.peer_import(r, allh[r])
+                    except Exception:
+                        if exchange == "peer":
+                            raise
+                        ok = 0
+                else:
+                    ok = 0
+                oks = [None] * self.world
+                dist.all_gather_object(oks, ok)
+                self.exchange = exchange = "peer" if all(oks) else "nccl"
+            if exchange == "peer":
+                pass
             elif exchange == "nccl":
                 import torch
                 ptr, nb, _ = handle.hist_device_ptr()
