@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--events", type=int, default=0, help="override the total event count (debug)")
     ap.add_argument("--exchange", default=os.environ.get("M3B_EXCHANGE", "auto"), choices=["auto", "nccl", "peer"],
                     help="N>1 histogram exchange: the library's own peer-memory pull fused with the likelihood (peer), "
@@ -411,10 +411,79 @@ def main_cfg4(args):
     print(json.dumps(line), flush=True)
 
 
+def main_cfg5(args):
+    """BASELINE config 5 (batched proposals), single GPU, optional bench line:
+    python bench.py --workload cfg5 [--events N] [--steps batches]   -- 256 parameter sets per batch."""
+    import torch
+    from mach3_b200 import lib, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; no CPU fallback")
+    w = synth.CFG5 if not args.events else synth.CFG5.scaled(args.events)
+    n_sets = 256
+    h = lib.Handle(test_statistic=w.test_statistic, update_w2=False, tile_events=args.tile)
+    t0 = time.perf_counter()
+    typ, npts, cx = synth.param_layout(w)
+    h.splines_begin(w.n_params, w.n_knots, cx, npts, w.n_events)
+    for c0 in range(0, w.n_events, CHUNK):
+        h.splines_append(synth.make_splines(w, c0, min(w.n_events, c0 + CHUNK)))
+    h.splines_end()
+    h.upload_binning(synth.bin_edges(w))
+    ev = synth.make_events(w, 0, w.n_events)
+    h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0, ev["static_w"])
+    del ev
+    h.upload_osc(synth.make_osc(w, 0, 0, w.n_events))
+    t_setup = time.perf_counter() - t0
+    sp, nm = synth.proposal(w, -1)
+    h.step(sp, nm); h.llh()
+    h.upload_data(np.random.default_rng(w.seed).poisson(h.read_hist()[0]).astype(np.float64))
+    # single-set reference point on the same handle
+    h.set_timing(True); h.kernel_time()
+    for k in range(10):
+        sp, nm = synth.proposal(w, k); h.step(sp, nm)
+    h.llh()
+    ms1, n1 = h.kernel_time()
+    rng = np.random.default_rng(w.seed + 7)
+
+    def batch(k):
+        sp0, nm0 = synth.proposal(w, k)
+        sps = np.clip(sp0[None, :] + rng.normal(0, 0.3, (n_sets, w.n_params)), -2.9, 2.9)
+        nms = np.clip(nm0[None, :] + rng.normal(0, 0.05, (n_sets, w.n_norm_params)), 0.5, 1.5)
+        return sps, nms
+
+    W, K = max(1, min(args.warmup, 2)), max(1, min(args.steps, 5))
+    bs = [batch(k) for k in range(W + K)]
+    for k in range(W):
+        h.step_batch(*bs[k])
+    h.kernel_time()
+    t1 = time.perf_counter()
+    for k in range(W, W + K):
+        tot = h.step_batch(*bs[k])
+    t_b = (time.perf_counter() - t1) / K
+    msb, nb = h.kernel_time()
+    kms = msb / max(nb, 1)
+    fp_instr = w.n_events * n_sets * (4 * (w.n_params - w.n_linear) + 2 * w.n_linear)     # FMA/MUL issue slots
+    peak_issue = 148 * 128 * 1.965e9
+    line = {"metric": "LLH evaluations/s over batched proposals (reweight+fill+LLH per parameter set)", "value": n_sets / t_b,
+            "unit": "LLH evals/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_b, "us_per_llh": 1e6 * t_b / n_sets,
+            "event_sets_per_s": w.n_events * n_sets / t_b, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
+            "config": {"workload": w.name, "events": w.n_events, "sets_per_batch": n_sets, "bins": w.n_bins, "setup_s": round(t_setup, 1),
+                       "single_set_kernel_ms": ms1 / max(n1, 1), "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / kms},
+            "roofline": {"bound": "fp32 issue (CUDA cores; no contraction, so no tensor cores)", "achieved": fp_instr / (kms * 1e-3) / 1e12,
+                         "peak": peak_issue / 1e12, "unit": "T FP32 instr/s", "frac": fp_instr / (kms * 1e-3) / peak_issue,
+                         "kernel": "m3b::fill_batch_kernel", "kernel_ms": kms, "traffic": None},
+            "e2e": {"value": n_sets / t_b, "unit": "LLH evals/s", "h2d_bytes_per_step": int(n_sets * (8 * w.n_params + 8 * w.n_norm_params)),
+                    "d2h_bytes_per_step": int(n_sets * 8 * (1 + w.n_samples))},
+            "gpu_launches": int(2 * K), "llh": {"first": float(tot[0]), "last": float(tot[-1])}}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.workload == "cfg4":
         main_cfg4(a)
+    elif a.workload == "cfg5":
+        main_cfg5(a)
     elif a.impl == "reference":
         main_reference(a)
     else:

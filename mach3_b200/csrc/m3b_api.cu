@@ -65,6 +65,7 @@ M3B_API void m3b_destroy(m3b_handle* h) {
   }
   if (h->h_llh) cudaFreeHost(h->h_llh);
   if (h->h_batch) cudaFreeHost(h->h_batch);
+  for (void* p : {h->bt_dx, h->bt_rowoff, h->bt_val, h->bt_rowlist, h->bt_norm, h->bt_sigs, h->bt_hist, h->bt_llh, h->bt_slot}) if (p) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -883,16 +884,29 @@ M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_p
   if (h->batch_cap < static_cast<size_t>(n_sets)) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_batch) cudaFreeHost(h->h_batch);
+  for (void* p : {h->bt_dx, h->bt_rowoff, h->bt_val, h->bt_rowlist, h->bt_norm, h->bt_sigs, h->bt_hist, h->bt_llh, h->bt_slot}) if (p) cudaFree(p);
     CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_batch), sizeof(double) * slot * n_sets, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_batch_dev), h->h_batch, 0));
     h->batch_cap = static_cast<size_t>(n_sets);
   }
   int rc = M3B_OK;
-  for (int32_t i = 0; i < n_sets && rc == M3B_OK; ++i) {
+  int32_t i0 = 0;
+  // the batched kernel (one pass over the coefficient rows for up to 256 sets) whenever the state allows it
+  while (i0 < n_sets) {
+    const int32_t n = std::min<int32_t>(256, n_sets - i0);
+    int done = 0;
+    rc = m3b_batch_try(h, n, h->P > 0 ? spline_pars + static_cast<size_t>(i0) * h->P : nullptr,
+                       h->n_norm_values > 0 ? norm_pars + static_cast<size_t>(i0) * h->n_norm_values : nullptr,
+                       i0 == 0 ? osc_w : nullptr, h->h_batch_dev + slot * i0, &done);
+    if (rc != M3B_OK) return rc;
+    if (!done) break;
+    i0 += n;
+  }
+  for (int32_t i = i0; i < n_sets && rc == M3B_OK; ++i) {
     h->llh_host_override = h->h_batch_dev + slot * i;
     rc = step_common(h, h->P > 0 ? spline_pars + static_cast<size_t>(i) * h->P : nullptr,
                      h->n_norm_values > 0 ? norm_pars + static_cast<size_t>(i) * h->n_norm_values : nullptr,
-                     i == 0 ? osc_w : nullptr, kFused);
+                     (i == 0 && i0 == 0) ? osc_w : nullptr, kFused);
   }
   h->llh_host_override = nullptr;
   if (rc != M3B_OK) return rc;

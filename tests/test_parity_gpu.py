@@ -314,11 +314,16 @@ def test_zero_copy_oscillation_weights_match_the_copied_path(oracle_build):
         assert l0 == pytest.approx(l1, rel=1e-10, abs=1e-9)
 
 
-def test_batched_proposals_match_sequential_oracle(oracle_build):
-    """BASELINE config 5 shape (reduced): a batch of parameter sets, perturbations around one point so only a few
-    segments per parameter are active, evaluated by m3b_step_batch; every set's -lnL against the oracle run
-    sequentially (same cached-segment history)."""
-    w = synth.CFG5.scaled(40_003)
+@pytest.mark.parametrize("wl,n_events,n_sets,kernel", [("CFG5", 40_003, 48, "batch"), ("CFG5", 20_000, 48, "sequential"),
+                                                       ("SPARSE_RUNS", 20_000, 70, "batch"), ("CFG1", 9_000, 300, "batch")])
+def test_batched_proposals_match_sequential_oracle(oracle_build, wl, n_events, n_sets, kernel, monkeypatch):
+    """BASELINE config 5 shape (reduced) and friends: a batch of parameter sets -- perturbations around one point so
+    only a few segments per parameter are active -- evaluated by m3b_step_batch in ONE pass over the coefficient
+    rows (or, forced, by sequential single-set launches); every set's -lnL against the oracle run sequentially
+    (same cached-segment history).  300 sets = two launches of the batched kernel."""
+    if kernel == "sequential":
+        monkeypatch.setenv("M3B_NO_BATCH_KERNEL", "1")
+    w = getattr(synth, wl).scaled(n_events)
     mono, osh, od = O.build_from_workload(w)
     gsh, gd = handlers.build_from_workload(w)
     _set(w, -1, mono, osh, gsh, gd)
@@ -326,17 +331,25 @@ def test_batched_proposals_match_sequential_oracle(oracle_build):
     data = np.random.default_rng(9).poisson(osh.mc).astype(np.float64)
     osh.AddData(data); gsh.AddData(data)
     rng = np.random.default_rng(10)
-    n_sets = 48
     sp0, nm0 = synth.proposal(w, 3)
     sps = np.clip(sp0[None, :] + rng.normal(0, 0.3, (n_sets, w.n_params)), -2.9, 2.9)
-    nms = np.clip(nm0[None, :] + rng.normal(0, 0.05, (n_sets, w.n_norm_params)), 0.5, 1.5)
+    nms = np.clip(nm0[None, :] + rng.normal(0, 0.05, (n_sets, max(w.n_norm_params, 1))), 0.5, 1.5)[:, :w.n_norm_params]
     sps[5] = np.round(sps[5])            # a set sitting exactly on knots
-    tot, per = gsh.handle.step_batch(sps, nms, per_sample=True)
+    launches0 = gsh.handle.info().kernel_launches
+    tot, per = gsh.handle.step_batch(sps, nms if w.n_norm_params else None, per_sample=True)
+    launches = gsh.handle.info().kernel_launches - launches0
+    assert launches == (n_sets if kernel == "sequential" else 2 * ((n_sets + 255) // 256))
     assert tot.shape == (n_sets,)
     for i in range(n_sets):
-        mono.set_params(sps[i]); osh.norm_vals[:] = nms[i]
+        mono.set_params(sps[i])
+        if w.n_norm_params:
+            osh.norm_vals[:] = nms[i]
         osh.Reweight()
         o = osh.GetLikelihood()
         assert tot[i] == pytest.approx(o, rel=1e-10 if _exact() else LLH_RTOL, abs=1e-9), i
         assert per[i].sum() == pytest.approx(tot[i], rel=1e-12)
     assert gsh.GetLikelihood() == tot[-1]
+    np.testing.assert_allclose(gsh.GetMCArray(), osh.mc, rtol=1e-12 if _exact() else HIST_RTOL, atol=1e-12)
+    # the handle keeps working like after a normal step
+    _set(w, 4, mono, osh, gsh, gd)
+    _check_step(w, mono, osh, gsh, check_weights=False)
