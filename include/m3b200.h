@@ -146,6 +146,15 @@ M3B_API int m3b_read_binned_weights(m3b_handle* h, float* weightvec_Monolith /* 
  * Events must come in the same order as the spline monolith's events.                              */
 M3B_API int m3b_upload_binning(m3b_handle* h, int32_t n_samples, const int32_t* n_dim,
                                const int32_t* nbins /*[n_samples*4]*/, const double* edges);
+/* m3b_upload_binning_ex: like m3b_upload_binning, but sample s may use the reference's NON-UNIFORM binning
+ *   (uniform[s] == 0; SampleBinningInfo::InitNonUniform, Samples/SampleStructs.h:468-528): its bins are boxes,
+ *   nbins[s*4+0] = number of boxes, and its part of `edges` holds boxes*n_dim[s] {lo,hi} pairs (BinInfo::Extent).
+ *   The library builds the same 10-per-dimension "mega bin" grid and box lists as InitialiseGridMapping
+ *   (:394-466); an event is in the first listed box with lo < x <= hi in every dimension
+ *   (BinInfo::IsEventInside :207-219; FindGlobalBin's non-uniform arm, Samples/BinningHandler.cpp:278-290).
+ *   All non-uniform samples of one handle must have the same dimensionality.                               */
+M3B_API int m3b_upload_binning_ex(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* uniform,
+                                  const int32_t* nbins /*[n_samples*4]*/, const double* edges);
 M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sample_id, const double* kin,
                               int32_t n_norm_per_event, const int16_t* norm_idx, int32_t n_norm_values,
                               int32_t use_osc, const int32_t* osc_idx, int64_t n_osc_values,

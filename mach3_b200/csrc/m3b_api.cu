@@ -313,40 +313,109 @@ M3B_API int m3b_upload_spline_monolith(m3b_handle* h, int32_t n_params, int32_t 
 // ------------------------------------------------------------------------------------------------
 // binning, events, data
 // ------------------------------------------------------------------------------------------------
-M3B_API int m3b_upload_binning(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* nbins,
-                               const double* edges) {
+static int upload_binning_impl(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* uniform,
+                               const int32_t* nbins, const double* edges) {
   REQUIRE(h, M3B_ERR_INVALID, "null handle");
   REQUIRE(n_samples > 0 && n_samples <= 64 && n_dim && nbins && edges, M3B_ERR_INVALID, "m3b_upload_binning: bad argument (1..64 samples)");
   REQUIRE(h->n_samples == 0, M3B_ERR_STATE, "m3b_upload_binning: binning already uploaded");
   CK(cudaSetDevice(h->device));
   h->n_samples = n_samples;
   h->b_ndim.assign(n_dim, n_dim + n_samples);
-  h->b_nbins.assign(nbins, nbins + static_cast<size_t>(n_samples) * kMaxDim);
+  h->b_nbins.assign(static_cast<size_t>(n_samples) * kMaxDim, 0);
   h->b_edge_off.assign(static_cast<size_t>(n_samples) * kMaxDim, 0);
   h->b_stride.assign(static_cast<size_t>(n_samples) * kMaxDim, 0);
   h->b_goff.assign(n_samples, 0);
   h->sample_start.assign(n_samples + 1, 0);
-  int eoff = 0, goff = 0;
+  h->b_uniform.assign(n_samples, 1); h->b_box_off.assign(n_samples, 0); h->b_grid_off.assign(n_samples, 0);
+  h->b_grid_start.assign(1, 0);
+  h->b_edges.clear();
+  const double* ep = edges;
+  int goff = 0;
+  bool any_nonuniform = false;
   for (int s = 0; s < n_samples; ++s) {
     REQUIRE(n_dim[s] >= 1 && n_dim[s] <= kMaxDim, M3B_ERR_INVALID, "m3b_upload_binning: 1..4 dimensions per sample");
+    const int nd = n_dim[s];
     int stride = 1;                                   // SampleStructs.h:656-664, x fastest
-    for (int d = 0; d < n_dim[s]; ++d) {
+    h->b_goff[s] = goff;                              // BinningHandler.cpp:341-355
+    h->sample_start[s] = goff;
+    if (uniform && !uniform[s]) {
+      // SampleBinningInfo::InitNonUniform + InitialiseGridMapping (Samples/SampleStructs.h:394-528)
+      any_nonuniform = true;
+      constexpr int kPerDim = 10;                     // BinsPerDimension
+      const int nb = nbins[s * kMaxDim];
+      REQUIRE(nb >= 1 && nd >= 2, M3B_ERR_INVALID, "m3b_upload_binning: a non-uniform sample needs >= 1 box and >= 2 dimensions");
+      h->b_uniform[s] = 0;
+      const size_t box0 = h->b_boxes.size();
+      h->b_boxes.insert(h->b_boxes.end(), ep, ep + static_cast<size_t>(nb) * nd * 2);
+      const double* ex = h->b_boxes.data() + box0;
+      std::vector<std::vector<double>> me(nd, std::vector<double>(kPerDim + 1));
+      int n_grid = 1;
+      for (int d = 0; d < nd; ++d) {
+        double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
+        for (int i = 0; i < nb; ++i) {
+          REQUIRE(ex[(static_cast<size_t>(i) * nd + d) * 2] < ex[(static_cast<size_t>(i) * nd + d) * 2 + 1], M3B_ERR_INVALID, "m3b_upload_binning: box with lo >= hi");
+          mn = std::min(mn, ex[(static_cast<size_t>(i) * nd + d) * 2]);
+          mx = std::max(mx, ex[(static_cast<size_t>(i) * nd + d) * 2 + 1]);
+        }
+        const double width = (mx - mn) / static_cast<double>(kPerDim);
+        for (int e = 0; e <= kPerDim; ++e) me[d][e] = mn + static_cast<double>(e) * width;
+        h->b_nbins[s * kMaxDim + d] = kPerDim;
+        h->b_edge_off[s * kMaxDim + d] = static_cast<int32_t>(h->b_edges.size());
+        h->b_edges.insert(h->b_edges.end(), me[d].begin(), me[d].end());
+        h->b_stride[s * kMaxDim + d] = stride;
+        stride *= kPerDim; n_grid *= kPerDim;
+      }
+      h->b_grid_off[s] = static_cast<int32_t>(h->b_grid_start.size()) - 1;
+      for (int g = 0; g < n_grid; ++g) {
+        int rem = g;
+        double cell[kMaxDim][2];
+        for (int d = 0; d < nd; ++d) { const int i = rem % kPerDim; rem /= kPerDim; cell[d][0] = me[d][i]; cell[d][1] = me[d][i + 1]; }
+        for (int i = 0; i < nb; ++i) {
+          bool overlap = true;
+          for (int d = 0; d < nd && overlap; ++d)
+            overlap = ex[(static_cast<size_t>(i) * nd + d) * 2 + 1] > cell[d][0] && ex[(static_cast<size_t>(i) * nd + d) * 2] < cell[d][1];
+          if (overlap) h->b_grid_idx.push_back(i);
+        }
+        h->b_grid_start.push_back(static_cast<int32_t>(h->b_grid_idx.size()));
+      }
+      ep += static_cast<size_t>(nb) * nd * 2;
+      goff += nb;
+      continue;
+    }
+    for (int d = 0; d < nd; ++d) {
       const int nb = nbins[s * kMaxDim + d];
       REQUIRE(nb >= 1, M3B_ERR_INVALID, "m3b_upload_binning: empty axis");
       for (int i = 0; i < nb; ++i)
-        REQUIRE(edges[eoff + i] < edges[eoff + i + 1], M3B_ERR_INVALID, "m3b_upload_binning: edges must increase strictly");
-      h->b_edge_off[s * kMaxDim + d] = eoff;
+        REQUIRE(ep[i] < ep[i + 1], M3B_ERR_INVALID, "m3b_upload_binning: edges must increase strictly");
+      h->b_nbins[s * kMaxDim + d] = nb;
+      h->b_edge_off[s * kMaxDim + d] = static_cast<int32_t>(h->b_edges.size());
+      h->b_edges.insert(h->b_edges.end(), ep, ep + nb + 1);
       h->b_stride[s * kMaxDim + d] = stride;
       stride *= nb;
-      eoff += nb + 1;
+      ep += nb + 1;
     }
-    h->b_goff[s] = goff;                              // BinningHandler.cpp:341-355
-    h->sample_start[s] = goff;
     goff += stride;
   }
   h->sample_start[n_samples] = goff;
   h->n_bins = goff;
-  h->b_edges.assign(edges, edges + eoff);
+  if (any_nonuniform) {
+    // first box of every non-uniform sample, in boxes (hence one dimensionality for all of them)
+    size_t doubles = 0;
+    for (int s = 0; s < n_samples; ++s) {
+      if (!h->b_uniform[s]) {
+        REQUIRE(doubles % (2 * static_cast<size_t>(n_dim[s])) == 0, M3B_ERR_INVALID, "m3b_upload_binning: non-uniform samples must share one dimensionality");
+        h->b_box_off[s] = static_cast<int32_t>(doubles / (2 * static_cast<size_t>(n_dim[s])));
+        doubles += static_cast<size_t>(nbins[s * kMaxDim]) * n_dim[s] * 2;
+      }
+    }
+    CK(dev_upload(h, &h->d_uniform, h->b_uniform));
+    CK(dev_upload(h, &h->d_box_off, h->b_box_off));
+    CK(dev_upload(h, &h->d_grid_off, h->b_grid_off));
+    CK(dev_upload(h, &h->d_boxes, h->b_boxes));
+    CK(dev_upload(h, &h->d_grid_start, h->b_grid_start));
+    if (h->b_grid_idx.empty()) h->b_grid_idx.push_back(0);
+    CK(dev_upload(h, &h->d_grid_idx, h->b_grid_idx));
+  }
   CK(dev_upload(h, &h->d_ndim, h->b_ndim));
   CK(dev_upload(h, &h->d_nbins, h->b_nbins));
   CK(dev_upload(h, &h->d_edge_off, h->b_edge_off));
@@ -369,6 +438,16 @@ M3B_API int m3b_upload_binning(m3b_handle* h, int32_t n_samples, const int32_t* 
   CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_llh_dev), h->h_llh, 0));
   h->launch_ready = false;
   return M3B_OK;
+}
+
+M3B_API int m3b_upload_binning(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* nbins,
+                               const double* edges) {
+  return upload_binning_impl(h, n_samples, n_dim, nullptr, nbins, edges);
+}
+
+M3B_API int m3b_upload_binning_ex(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* uniform,
+                                  const int32_t* nbins, const double* edges) {
+  return upload_binning_impl(h, n_samples, n_dim, uniform, nbins, edges);
 }
 
 M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sample_id, const double* kin,
@@ -404,6 +483,8 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
     ba.n_events = E; ba.e_pad = EP; ba.sample_id = d_sid; ba.kin = d_kin; ba.n_samples = h->n_samples;
     ba.n_dim = h->d_ndim; ba.nbins = h->d_nbins; ba.edge_off = h->d_edge_off; ba.stride = h->d_stride;
     ba.global_off = h->d_goff; ba.edges = h->d_edges; ba.bin = h->d_bin;
+    ba.uniform = h->d_uniform; ba.box_off = h->d_box_off; ba.grid_off = h->d_grid_off; ba.boxes = h->d_boxes;
+    ba.grid_start = h->d_grid_start; ba.grid_idx = h->d_grid_idx;
     CK(launch_bins(ba, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (keep) { h->d_sample_id = d_sid; h->d_kin = d_kin; } else { cudaFree(d_sid); cudaFree(d_kin); }

@@ -60,6 +60,11 @@ struct m3b_handle {
   int32_t *d_ndim = nullptr, *d_nbins = nullptr, *d_edge_off = nullptr, *d_stride = nullptr, *d_goff = nullptr,
           *d_sample_start = nullptr;
   double* d_edges = nullptr;
+  // non-uniform samples
+  std::vector<int32_t> b_uniform, b_box_off, b_grid_off, b_grid_start, b_grid_idx;
+  std::vector<double> b_boxes;
+  int32_t *d_uniform = nullptr, *d_box_off = nullptr, *d_grid_off = nullptr, *d_grid_start = nullptr, *d_grid_idx = nullptr;
+  double* d_boxes = nullptr;
 
   // ---- events
   int64_t n_events = 0, e_pad = 0, n_tiles = 0;

@@ -171,6 +171,14 @@ struct BinArgs {
   const int32_t* global_off;   // [n_samples]
   const double* edges;
   int32_t* bin;                // [e_pad]
+  // non-uniform samples (boxes behind a 10-per-dimension mega-bin grid, Samples/SampleStructs.h:394-528):
+  // for them nbins/edge_off/stride describe the mega grid
+  const int32_t* uniform;      // [n_samples] (nullptr = all uniform)
+  const int32_t* box_off;      // [n_samples] first box of the sample in `boxes` (in boxes)
+  const int32_t* grid_off;     // [n_samples] first mega bin of the sample in grid_start
+  const double* boxes;         // [box][dim][2] {lo, hi}
+  const int32_t* grid_start;   // CSR: boxes overlapping mega bin g are grid_idx[grid_start[g] .. grid_start[g+1])
+  const int32_t* grid_idx;
 };
 
 struct RetileArgs {

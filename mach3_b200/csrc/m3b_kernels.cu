@@ -299,6 +299,24 @@ __global__ void bin_kernel(const __grid_constant__ BinArgs a) {
     }
     g += (lo - 1) * a.stride[s * kMaxDim + d];
   }
+  if (ok && a.uniform && !a.uniform[s]) {
+    // non-uniform arm of FindGlobalBin (Samples/BinningHandler.cpp:278-290): g is the mega bin; scan its boxes in
+    // order, BinInfo::IsEventInside = (lo, hi] in every dimension (Samples/SampleStructs.h:207-219)
+    const int g0 = a.grid_off[s] + g;
+    int found = -1;
+    for (int k = a.grid_start[g0]; k < a.grid_start[g0 + 1] && found < 0; ++k) {
+      const int b = a.grid_idx[k];
+      const double* ex = a.boxes + (static_cast<int64_t>(a.box_off[s] + b) * nd) * 2;
+      bool inside = true;
+      for (int d = 0; d < nd; ++d) {
+        const double x = a.kin[static_cast<int64_t>(d) * a.n_events + e];
+        inside &= (x > ex[2 * d]) & (x <= ex[2 * d + 1]);
+      }
+      if (inside) found = b;
+    }
+    a.bin[e] = found >= 0 ? found + a.global_off[s] : -1;
+    return;
+  }
   a.bin[e] = ok ? g + a.global_off[s] : -1;
 }
 cudaError_t launch_bins(const BinArgs& a, cudaStream_t s) {

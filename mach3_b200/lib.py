@@ -21,7 +21,7 @@ EXPORTS = (
     "m3b_create", "m3b_destroy", "m3b_last_error", "m3b_abi_version", "m3b_set_stream",
     "m3b_splines_begin", "m3b_splines_append", "m3b_splines_end", "m3b_upload_spline_monolith",
     "m3b_upload_binned_splines", "m3b_upload_event_binned_splines", "m3b_read_binned_weights",
-    "m3b_upload_binning", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer",
+    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer",
     "m3b_set_test_statistic", "m3b_reset_w2",
     "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
@@ -180,19 +180,28 @@ class Handle:
         return out
 
     def upload_binning(self, edges):
-        """edges: list over samples of list over dims of edge arrays."""
+        """edges: list over samples; a uniform sample is a list over dims of edge arrays, a NON-UNIFORM sample
+        (Samples/SampleStructs.h:468-528) is a float array [n_boxes, n_dim, 2] of {lo, hi} box extents."""
         ns = len(edges)
-        ndim = np.array([len(e) for e in edges], np.int32)
-        nbins = np.zeros(ns * 4, np.int32)
-        flat = []
+        ndim, uniform, nbins, flat, total = np.zeros(ns, np.int32), np.ones(ns, np.int32), np.zeros(ns * 4, np.int32), [], 0
         for s, dims in enumerate(edges):
+            if isinstance(dims, np.ndarray) and dims.ndim == 3:
+                uniform[s], ndim[s], nbins[s * 4] = 0, dims.shape[1], dims.shape[0]
+                flat.append(np.asarray(dims, np.float64).reshape(-1))
+                total += dims.shape[0]
+                continue
+            ndim[s] = len(dims)
             for d, e in enumerate(dims):
                 nbins[s * 4 + d] = len(e) - 1
                 flat.append(np.asarray(e, np.float64))
+            total += int(np.prod([len(e) - 1 for e in dims]))
         flat = np.ascontiguousarray(np.concatenate(flat))
-        self._ck(self.L.m3b_upload_binning(self.h, C.c_int32(ns), _p(ndim), _p(nbins), _p(flat)))
+        if uniform.all():
+            self._ck(self.L.m3b_upload_binning(self.h, C.c_int32(ns), _p(ndim), _p(nbins), _p(flat)))
+        else:
+            self._ck(self.L.m3b_upload_binning_ex(self.h, C.c_int32(ns), _p(ndim), _p(uniform), _p(nbins), _p(flat)))
         self.n_samples = ns
-        self.n_bins = int(sum(int(np.prod([len(e) - 1 for e in dims])) for dims in edges))
+        self.n_bins = total
 
     def upload_events(self, sample_id, kin, norm_idx=None, n_norm_per_event=0, n_norm_values=0, use_osc=False,
                       osc_idx=None, n_osc_values=0, static_w=None):

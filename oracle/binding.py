@@ -27,6 +27,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.m3o_monolith_create.restype = C.c_void_p
         L.m3o_sample_create.restype = C.c_void_p
+        L.m3o_sample_create_ex.restype = C.c_void_p
         L.m3o_binned_create.restype = C.c_void_p
         L.m3o_binned_weights.restype = C.c_void_p
         L.m3o_binned_segments.restype = C.c_void_p
@@ -165,19 +166,24 @@ class SampleHandlerFD:
     """Oracle mirror of the reference's ``SampleHandlerFD`` reweight / likelihood path."""
 
     def __init__(self, n_events, edges, test_statistic=kPoisson, update_w2=False):
+        """edges: list over samples; uniform sample = list over dims of edge arrays, non-uniform sample = float
+        array [n_boxes, n_dim, 2] (BinInfo::Extent)."""
         n_samples = len(edges)
-        ndim = np.array([len(e) for e in edges], np.int32)
-        nbins = np.zeros(n_samples * MAX_DIM, np.int32)
-        flat = []
+        ndim, uniform, nbins, flat = np.zeros(n_samples, np.int32), np.ones(n_samples, np.int32), np.zeros(n_samples * MAX_DIM, np.int32), []
         for s, dims in enumerate(edges):
+            if isinstance(dims, np.ndarray) and dims.ndim == 3:
+                uniform[s], ndim[s], nbins[s * MAX_DIM] = 0, dims.shape[1], dims.shape[0]
+                flat.append(np.asarray(dims, np.float64).reshape(-1))
+                continue
+            ndim[s] = len(dims)
             for d, e in enumerate(dims):
                 nbins[s * MAX_DIM + d] = len(e) - 1
                 flat.append(np.asarray(e, np.float64))
         flat = np.concatenate(flat)
         self.n_events = int(n_events)
         self.n_samples = n_samples
-        self.h = C.c_void_p(lib().m3o_sample_create(C.c_uint(n_events), C.c_int(n_samples), _p(ndim), _p(nbins),
-                                                    _p(flat), C.c_int(test_statistic), C.c_int(int(update_w2))))
+        self.h = C.c_void_p(lib().m3o_sample_create_ex(C.c_uint(n_events), C.c_int(n_samples), _p(ndim), _p(uniform), _p(nbins),
+                                                       _p(flat), C.c_int(test_statistic), C.c_int(int(update_w2))))
         self.n_bins = lib().m3o_total_bins(self.h)
         self._keep = []
 

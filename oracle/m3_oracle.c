@@ -297,6 +297,12 @@ typedef struct {
   int Strides[M3O_MAX_DIM];
   int nBins;
   int GlobalOffset;
+  /* non-uniform binning (Samples/SampleStructs.h:186-220,249-252): boxes + the "mega bin" grid that maps to them */
+  int Uniform;
+  int nBoxes;
+  double* Extent;            /* [box][dim][2] = BinInfo::Extent */
+  int* GridStart;            /* CSR over mega bins: BinGridMapping[mega] = GridIdx[GridStart[mega] .. GridStart[mega+1]) */
+  int* GridIdx;
 } SampleBinningInfo;
 
 /* SampleBinningInfo::InitialiseLookUpSingleDimension (Samples/SampleStructs.h:618-647) */
@@ -457,11 +463,73 @@ typedef struct {
   struct BinnedSplineHandler_* BinnedHandler;   /* the other SplineBase implementation (either/or) */
 } SampleHandlerFD;
 
+
+/* SampleBinningInfo::InitNonUniform + InitialiseGridMapping (Samples/SampleStructs.h:394-528): the boxes are
+ * mapped through a regular grid of BinsPerDimension = 10 "mega bins" per dimension spanning their bounding
+ * box; every mega bin lists, in box order, the boxes that overlap it (a_hi > b_lo && a_lo < b_hi). */
+static void InitNonUniform(SampleBinningInfo* b, int nDim, int nBoxes, const double* extent) {
+  enum { BinsPerDimension = 10 };
+  b->Uniform = 0; b->nDim = nDim; b->nBoxes = nBoxes; b->nBins = nBoxes;
+  b->Extent = (double*)malloc(sizeof(double) * (size_t)nBoxes * (size_t)nDim * 2);
+  memcpy(b->Extent, extent, sizeof(double) * (size_t)nBoxes * (size_t)nDim * 2);
+  int NGridBins = 1, stride = 1;
+  for (int d = 0; d < nDim; ++d) {
+    double MinVal = 1.7976931348623157e308, MaxVal = -1.7976931348623157e308;
+    for (int i = 0; i < nBoxes; ++i) {
+      const double lo = extent[((size_t)i * nDim + d) * 2], hi = extent[((size_t)i * nDim + d) * 2 + 1];
+      if (lo < MinVal) MinVal = lo;
+      if (hi > MaxVal) MaxVal = hi;
+    }
+    b->AxisNBins[d] = BinsPerDimension;
+    b->BinEdges[d] = (double*)malloc(sizeof(double) * (BinsPerDimension + 1));
+    const double BinWidth = (MaxVal - MinVal) / (double)BinsPerDimension;
+    for (int e = 0; e <= BinsPerDimension; ++e) b->BinEdges[d][e] = MinVal + (double)e * BinWidth;     /* :518-521 */
+    b->BinLookup[d] = (BinShiftLookup*)malloc(sizeof(BinShiftLookup) * BinsPerDimension);
+    InitialiseLookUpSingleDimension(b->BinLookup[d], b->BinEdges[d], BinsPerDimension);
+    b->Strides[d] = stride; stride *= BinsPerDimension; NGridBins *= BinsPerDimension;
+  }
+  b->GridStart = (int*)calloc((size_t)NGridBins + 1, sizeof(int));
+  for (int pass = 0; pass < 2; ++pass) {
+    int total = 0;
+    for (int g = 0; g < NGridBins; ++g) {
+      if (pass == 1) b->GridStart[g] = total;
+      int rem = g;
+      double cell[M3O_MAX_DIM][2];
+      for (int d = 0; d < nDim; ++d) { const int i = rem % BinsPerDimension; rem /= BinsPerDimension; cell[d][0] = b->BinEdges[d][i]; cell[d][1] = b->BinEdges[d][i + 1]; }
+      for (int i = 0; i < nBoxes; ++i) {
+        int overlap = 1;
+        for (int d = 0; d < nDim; ++d) {
+          const double a_lo = extent[((size_t)i * nDim + d) * 2], a_hi = extent[((size_t)i * nDim + d) * 2 + 1];
+          if (!(a_hi > cell[d][0] && a_lo < cell[d][1])) { overlap = 0; break; }                       /* :425 */
+        }
+        if (overlap) { if (pass == 1) b->GridIdx[total] = i; ++total; }
+      }
+    }
+    if (pass == 0) b->GridIdx = (int*)malloc(sizeof(int) * (size_t)(total > 0 ? total : 1));
+    else b->GridStart[NGridBins] = total;
+  }
+}
+
+/* like m3o_sample_create, but sample i may be non-uniform (uniform[i] == 0): then nbins[i*M3O_MAX_DIM] is its
+ * number of boxes and its part of `edges` holds nBoxes*nDim {lo,hi} pairs */
+M3O_API void* m3o_sample_create_ex(unsigned int nEvents, int nSamples, const int* nDim, const int* uniform,
+                                   const int* nbins, const double* edges, int test_statistic, int update_w2);
+
 /* binning description: for each sample, nDim then per dim nbins; edges concatenated */
+static SampleHandlerFD* sample_create(unsigned int nEvents, int nSamples, const int* nDim, const int* uniform,
+                                      const int* nbins, const double* edges, int test_statistic, int update_w2);
 M3O_API SampleHandlerFD* m3o_sample_create(unsigned int nEvents, int nSamples, const int* nDim,
                                            const int* nbins /*[nSamples*M3O_MAX_DIM]*/,
                                            const double* edges /*concatenated per sample per dim*/,
                                            int test_statistic, int update_w2) {
+  return sample_create(nEvents, nSamples, nDim, NULL, nbins, edges, test_statistic, update_w2);
+}
+M3O_API void* m3o_sample_create_ex(unsigned int nEvents, int nSamples, const int* nDim, const int* uniform,
+                                   const int* nbins, const double* edges, int test_statistic, int update_w2) {
+  return sample_create(nEvents, nSamples, nDim, uniform, nbins, edges, test_statistic, update_w2);
+}
+static SampleHandlerFD* sample_create(unsigned int nEvents, int nSamples, const int* nDim, const int* uniform,
+                                      const int* nbins, const double* edges, int test_statistic, int update_w2) {
   SampleHandlerFD* s = (SampleHandlerFD*)calloc(1, sizeof(SampleHandlerFD));
   s->nEvents = nEvents; s->nSamples = nSamples;
   s->SampleBinning = (SampleBinningInfo*)calloc((size_t)nSamples, sizeof(SampleBinningInfo));
@@ -470,6 +538,15 @@ M3O_API SampleHandlerFD* m3o_sample_create(unsigned int nEvents, int nSamples, c
   for (int i = 0; i < nSamples; ++i) {
     SampleBinningInfo* b = &s->SampleBinning[i];
     b->nDim = nDim[i];
+    b->Uniform = 1;
+    if (uniform && !uniform[i]) {
+      const int nBoxes = nbins[i * M3O_MAX_DIM];
+      InitNonUniform(b, nDim[i], nBoxes, ep);
+      ep += (size_t)nBoxes * (size_t)nDim[i] * 2;
+      b->GlobalOffset = GlobalOffsetCounter;
+      GlobalOffsetCounter += nBoxes;
+      continue;
+    }
     int stride = 1, tot = 1;
     for (int d = 0; d < b->nDim; ++d) {
       const int nb = nbins[i * M3O_MAX_DIM + d];
@@ -506,7 +583,10 @@ M3O_API void m3o_sample_destroy(SampleHandlerFD* s) {
   }
   free(s->MCSamples);
   for (int i = 0; i < s->nSamples; ++i)
+  {
     for (int d = 0; d < s->SampleBinning[i].nDim; ++d) { free(s->SampleBinning[i].BinEdges[d]); free(s->SampleBinning[i].BinLookup[d]); }
+    free(s->SampleBinning[i].Extent); free(s->SampleBinning[i].GridStart); free(s->SampleBinning[i].GridIdx);
+  }
   free(s->SampleBinning);
   free(s->SampleHandlerFD_array); free(s->SampleHandlerFD_array_w2); free(s->SampleHandlerFD_data);
   free(s);
@@ -617,8 +697,23 @@ static inline int FindGlobalBin(const SampleHandlerFD* s, const int NomSample, c
     if (Bin < 0) return UnderOverFlowBin;
     GlobalBin += Bin * Binning->Strides[i];
   }
-  GlobalBin += Binning->GlobalOffset;
-  return GlobalBin;
+  if (Binning->Uniform) {
+    GlobalBin += Binning->GlobalOffset;
+    return GlobalBin;
+  }
+  /* non-uniform arm (Samples/BinningHandler.cpp:278-290): scan the mega bin's boxes in order; BinInfo::IsEventInside
+   * tests (lo, hi] in every dimension (Samples/SampleStructs.h:207-219) */
+  for (int k = Binning->GridStart[GlobalBin]; k < Binning->GridStart[GlobalBin + 1]; ++k) {
+    const int BinNumber = Binning->GridIdx[k];
+    int inside = 1;
+    for (int i = 0; i < Dim; ++i) {
+      const double Var = *KinVar[i];
+      const double lo = Binning->Extent[((size_t)BinNumber * Dim + i) * 2], hi = Binning->Extent[((size_t)BinNumber * Dim + i) * 2 + 1];
+      inside &= (Var > lo) & (Var <= hi);
+    }
+    if (inside) return BinNumber + Binning->GlobalOffset;
+  }
+  return UnderOverFlowBin;
 }
 
 /* SampleHandlerFD::ResetHistograms (Samples/SampleHandlerFD.cpp:454-463) */
