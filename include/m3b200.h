@@ -66,7 +66,7 @@ typedef struct {
   int32_t device;          /* CUDA ordinal                                                          */
   int32_t test_statistic;  /* m3b_test_statistic; LikelihoodOptions:TestStatistic (Manager.cpp:98-127)*/
   int32_t update_w2;       /* LikelihoodOptions:UpdateW2 (Samples/SampleHandlerFD.cpp:64)            */
-  int32_t tile_events;     /* events per tile row of the device layout: 0 (=1024), 128, 256, 512, 1024 */
+  int32_t tile_events;     /* events per tile row of the device layout: 0 (auto: 512 below 1.5M events, else 1024), 128..1024 */
   int32_t flags;           /* M3B_FLAG_*                                                            */
   int32_t reserved[11];
 } m3b_config;

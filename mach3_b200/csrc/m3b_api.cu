@@ -36,6 +36,7 @@ M3B_API int m3b_create(const m3b_config* cfg, m3b_handle** out) {
   h->device = cfg->device;
   h->sm_count = prop.multiProcessorCount;
   h->T = T;
+  h->T_auto = cfg->tile_events == 0;
   h->test_stat = cfg->test_statistic;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -88,6 +89,9 @@ M3B_API int m3b_splines_begin(m3b_handle* h, int32_t n_params, int32_t max_knots
   REQUIRE(!h->splines_open && !h->splines_done, M3B_ERR_STATE, "m3b_splines_begin: monolith already uploaded");
   REQUIRE(n_params > 0 && n_params <= kMaxParams, M3B_ERR_INVALID, "m3b_splines_begin: n_params out of range");
   REQUIRE(max_knots >= 0 && coeff_x && n_pts && n_events_total >= 0, M3B_ERR_INVALID, "m3b_splines_begin: bad argument");
+  // tile row length, when the caller left it open: 16 KB rows stream best, but with few tiles per SM
+  // the end-of-grid balance matters more and 8 KB rows win (measured at cfg2: 1 M events, 26 units per SM)
+  if (h->T_auto && h->n_events == 0) h->T = n_events_total >= 1500000 ? 1024 : 512;
   h->P = n_params; h->Kmax = max_knots;
   h->coeff_x.assign(coeff_x, coeff_x + static_cast<size_t>(n_params) * max_knots);
   h->n_pts.assign(n_pts, n_pts + n_params);
@@ -814,7 +818,11 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   for (int i = 0; i <= h->n_samples; ++i) a.sample_start_inline[i] = h->sample_start[i];
   a.tile_begin = 0;
   a.osc_host = osc_zc; a.osc_store = h->d_osc;
-  if (h->use_tma) { a.tile_counter = h->d_tile_counter; a.n_stages = h->tma_stages; a.tma = h->tma; }
+  if (h->use_tma) {
+    a.tile_counter = h->d_tile_counter; a.n_stages = h->tma_stages; a.tma = h->tma;
+    const char* ge = getenv("M3B_GUARD_X2");
+    a.guard_x2 = ge && atoi(ge) > 0 ? atoi(ge) : 6;
+  }
   a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->llh_host_override ? h->llh_host_override : h->h_llh_dev;
   a.evt_spline_w = h->d_evt_spline_w; a.evt_total_w = h->d_evt_total_w;
   a.trace = h->d_trace;

@@ -132,16 +132,17 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
     for (int i = tid; i < a.n_bins; i += kUnit + 32) s_hist[i] = 0.;
     if (w2_live) for (int i = tid; i < a.n_bins; i += kUnit + 32) s_w2[i] = 0.;
   }
-  // the producer's first grab and its tile descriptor overlap the table staging (shortens the ramp)
+  // Work scheduling.  First round: static (block b owns units [b*w0, (b+1)*w0)), so the producer can fetch its
+  // tile descriptor while the tables are staged; afterwards guided grabs from the global counter.
   const unsigned int unit_begin = static_cast<unsigned int>(a.tile_begin) * qmax;
   const unsigned int unit_end = static_cast<unsigned int>(a.n_tiles) * qmax;
-  const unsigned int guard = 2u * gridDim.x;
-  unsigned int c_first = 0; int want_first = 0;
-  if (warp == kConsumerWarps && lane == 0) {
-    want_first = qmax;
-    while (want_first > 1 && unit_end - unit_begin < guard * want_first) want_first >>= 1;
-    c_first = atomicAdd(a.tile_counter, static_cast<unsigned int>(want_first));
-  }
+  const unsigned int guard = (static_cast<unsigned int>(a.guard_x2) * gridDim.x) >> 1;
+  int w0 = qmax;
+  while (w0 > 1 && unit_end - unit_begin < guard * w0) w0 >>= 1;
+  const unsigned int static_units = gridDim.x * static_cast<unsigned int>(w0);
+  const unsigned int u_first = unit_begin + blockIdx.x * static_cast<unsigned int>(w0);
+  TileDesc td_pre{};
+  if (warp == kConsumerWarps && u_first < unit_end) td_pre = a.tiles[u_first / qmax];     // in flight during the staging
   // stage the per-step {segment, dx, value, norm, per-signature slot} tables
   stage_step_table(a, st, &step_bar);
   if (tid == 0) trace_mark(a, 1);
@@ -156,10 +157,8 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
     int stage = 0, prod_sig = -1;
     uint32_t phase = 1;       // a fresh mbarrier passes a wait on the "previous" phase
     auto advance = [&]() { if (++stage == NS) { stage = 0; phase ^= 1u; } };
-    const unsigned int c0 = __shfl_sync(0xffffffffu, c_first, 0);
-    const int w0 = __shfl_sync(0xffffffffu, want_first, 0);
-    unsigned int seen = c0 + w0;    // last counter value this producer saw: estimates the work left
-    unsigned int u = unit_begin + c0;   // units [u, u_end) grabbed and not yet issued
+    unsigned int seen = 0;          // last counter value this producer saw: estimates the work left
+    unsigned int u = u_first;       // units [u, u_end) grabbed and not yet issued
     unsigned int u_end = u + w0 < unit_end ? u + w0 : unit_end;
     unsigned long long n_units = 0;
     const bool expanded = a.step.n_sigs_x > 0;
@@ -172,7 +171,8 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
         // work left as of this producer's previous grab
         unsigned int c = 0; int want = 0;
         if (lane == 0) {
-          const unsigned int left = unit_begin + seen < unit_end ? unit_end - unit_begin - seen : 0u;
+          const unsigned int done = static_units + seen;
+          const unsigned int left = unit_begin + done < unit_end ? unit_end - unit_begin - done : 0u;
           want = qmax;
           while (want > 1 && left < guard * want) want >>= 1;
           c = atomicAdd(a.tile_counter, static_cast<unsigned int>(want));
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
         want = __shfl_sync(0xffffffffu, want, 0);
         c = __shfl_sync(0xffffffffu, c, 0);
         seen = c + want;
-        u = unit_begin + c;
+        u = unit_begin + static_units + c;
         if (u >= unit_end) break;
         u_end = u + want < unit_end ? u + want : unit_end;
       }
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
       while (g > 1 && ((u & (g - 1)) != 0 || u + g > u_end)) g >>= 1;
       const int t = static_cast<int>(u / qmax);
       const int lane0 = static_cast<int>(u % qmax) * kUnit;       // first lane of the grab within the tile row
-      const TileDesc td = a.tiles[t];
+      const TileDesc td = (u == u_first) ? td_pre : a.tiles[t];
       const int nc = td.ncnl & 0xffff, nl = td.ncnl >> 16;
       // zero-copy oscillation weights: g*1 KB straight from pinned host memory, riding on the grab's
       // last stage (they are needed only when the event's total weight is formed)

@@ -36,6 +36,7 @@ struct m3b_handle {
   bool splines_open = false, splines_done = false;
   int64_t n_events_total = 0, n_events_loaded = 0;
   int T = 256;
+  bool T_auto = false;                   // cfg.tile_events == 0: chosen from the event count at m3b_splines_begin
 
   // ---- signatures and tiles
   std::map<std::vector<int16_t>, int> sig_index;   // key: cubic params, -1, linear params

@@ -123,6 +123,7 @@ struct FillArgs {
   unsigned int* ticket;
   unsigned int* tile_counter;  // dynamic tile scheduler of the TMA kernel (nullptr: static interleave)
   int32_t n_stages;            // TMA kernel: stages of the shared-memory coefficient ring
+  int32_t guard_x2;            // TMA kernel: whole tile rows are grabbed while more than guard_x2/2 * grid * g units are left
   double* llh_dev;             // [1+n_samples]
   double* llh_host;            // mapped pinned mirror (nullptr = none)
   // optional per-event outputs
