@@ -167,6 +167,11 @@ def main_reference(args):
 # B200 arm
 # ---------------------------------------------------------------------------------------------
 def main_b200(args):
+    # torchrun exports OMP_NUM_THREADS=1; the synthetic-workload generator (host, OpenMP) would then build each
+    # rank's shard on one core.  Give every rank its share of the host cores BEFORE the generator library loads.
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_env > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world_env))
     import torch
     from mach3_b200 import lib, synth
 
