@@ -353,3 +353,31 @@ def test_batched_proposals_match_sequential_oracle(oracle_build, wl, n_events, n
     # the handle keeps working like after a normal step
     _set(w, 4, mono, osh, gsh, gd)
     _check_step(w, mono, osh, gsh, check_weights=False)
+
+
+def test_tiny_and_ragged_event_counts():
+    """Fewer events than one tile row, one event, and a count one past a tile boundary."""
+    for n in (1, 33, 513, 1025):
+        w = synth.CFG1.scaled(n)
+        O.set_multithread(False)
+        mono, osh, gsh, gd = _pair(w)
+        np.testing.assert_array_equal(gsh.GetEventBins(), osh.event_bins())
+        for step in (-1, 0, 1):
+            _set(w, step, mono, osh, gsh, gd)
+            _check_step(w, mono, osh, gsh)
+    O.set_multithread(True)
+
+
+def test_call_order_errors_are_reported():
+    h = lib.Handle()
+    with pytest.raises(lib.M3BError) as ei:
+        h.step(np.zeros(3))                      # nothing uploaded
+    assert ei.value.code == 3                    # M3B_ERR_STATE
+    h.upload_binning([[np.array([0.0, 1.0, 2.0])]])
+    with pytest.raises(lib.M3BError):
+        h.upload_binning([[np.array([0.0, 1.0])]])           # twice
+    with pytest.raises(lib.M3BError):
+        h.upload_data(np.zeros(5))                           # wrong bin count
+    with pytest.raises(lib.M3BError):
+        h.upload_events(np.array([3], np.int32), np.zeros(1))   # sample id out of range
+    h.close()
