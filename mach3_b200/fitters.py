@@ -1,0 +1,46 @@
+"""Batch consumers of the hot path: fitter-side loops of the reference that evaluate many
+parameter sets against the same events, rewritten on top of m3b_step_batch so that one pass over the coefficient
+rows serves the whole loop.
+
+    RunLLHScan     FitterBase::RunLLHScan (Fitters/FitterBase.cpp:620-798): for every scanned parameter, n_points
+                   values at the bin centres of [lower, upper], all other parameters at their central values,
+                   samples[i]->Reweight(); samples[i]->GetLikelihood() (+ GetSampleLikelihood when split by sample).
+                   Returns what the reference writes into hScanSam / hScanSamSplit: 2 x (-lnL).
+
+Only the sample-likelihood part is computed here; the systematic (prior) terms of the scan come from the
+ParameterHandler and are out of scope.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def scan_points(lower: float, upper: float, n_points: int) -> np.ndarray:
+    """TH1D(n_points, lower, upper)->GetBinCenter(j+1), j = 0..n_points-1 (Fitters/FitterBase.cpp:738)."""
+    width = (upper - lower) / n_points
+    return lower + (np.arange(n_points) + 0.5) * width
+
+
+def RunLLHScan(sample, central_spline_pars, central_norm_pars=None, spline_ranges=None, norm_ranges=None, n_points=100,
+               by_sample=False):
+    """`sample`: mach3_b200.handlers.SampleHandlerFD.  spline_ranges / norm_ranges: {parameter index: (lower, upper)}.
+    Returns {("spline"|"norm", index): {"x": points, "llh2": 2*(-lnL)[n_points], "llh2_by_sample": [n_points, n_samples]}}.
+    The handle is left at the central values (one extra Reweight), like the reference resets the parameter."""
+    h = sample.handle
+    c_sp = np.ascontiguousarray(central_spline_pars, np.float64)
+    c_nm = None if central_norm_pars is None else np.ascontiguousarray(central_norm_pars, np.float64)
+    out = {}
+    for kind, ranges in (("spline", spline_ranges or {}), ("norm", norm_ranges or {})):
+        for idx, (lo, hi) in ranges.items():
+            x = scan_points(lo, hi, n_points)
+            sps = np.tile(c_sp, (n_points, 1))
+            nms = None if c_nm is None else np.tile(c_nm, (n_points, 1))
+            if kind == "spline":
+                sps[:, idx] = x
+            else:
+                nms[:, idx] = x
+            tot, per = h.step_batch(sps, nms, per_sample=True)
+            out[(kind, idx)] = {"x": x, "llh2": 2.0 * tot, "llh2_by_sample": 2.0 * per if by_sample else None}
+    h.step(c_sp, c_nm)
+    h.llh()
+    return out

@@ -381,3 +381,33 @@ def test_call_order_errors_are_reported():
     with pytest.raises(lib.M3BError):
         h.upload_events(np.array([3], np.int32), np.zeros(1))   # sample id out of range
     h.close()
+
+
+def test_llh_scan_matches_the_reference_loop(oracle_build):
+    """FitterBase::RunLLHScan through m3b_step_batch against the reference's loop (set one parameter to the bin
+    centre, Reweight, GetLikelihood) run on the oracle."""
+    from mach3_b200 import fitters
+    w = synth.SPARSE.scaled(30_000)
+    mono, osh, od = O.build_from_workload(w)
+    gsh, gd = handlers.build_from_workload(w)
+    _set(w, -1, mono, osh, gsh, gd)
+    osh.Reweight(); gsh.Reweight(); gsh.GetLikelihood()
+    data = np.random.default_rng(12).poisson(osh.mc).astype(np.float64)
+    osh.AddData(data); gsh.AddData(data)
+    c_sp, c_nm = synth.proposal(w, 2)
+    res = fitters.RunLLHScan(gsh, c_sp, c_nm, spline_ranges={0: (-2.5, 2.5), w.n_params - 1: (-1.0, 1.0)},
+                             norm_ranges={1: (0.7, 1.3)}, n_points=40, by_sample=True)
+    for (kind, idx), r in res.items():
+        assert r["x"][0] < r["x"][-1] and r["llh2"].shape == (40,)
+        for j, x in enumerate(r["x"]):
+            sp, nm = c_sp.copy(), c_nm.copy()
+            (sp if kind == "spline" else nm)[idx] = x
+            mono.set_params(sp); osh.norm_vals[:] = nm
+            osh.Reweight()
+            assert r["llh2"][j] == pytest.approx(2 * osh.GetLikelihood(), rel=1e-9 if _exact() else LLH_RTOL, abs=1e-9)
+            for s in range(w.n_samples):
+                assert r["llh2_by_sample"][j, s] == pytest.approx(2 * osh.GetSampleLikelihood(s), rel=1e-8 if _exact() else 1e-5, abs=1e-8)
+    # the reference resets the scanned parameter without reweighting (FitterBase.cpp:795); RunLLHScan leaves the
+    # handle at the central values with one Reweight: same cached-segment history on both sides
+    mono.set_params(c_sp); osh.norm_vals[:] = c_nm; osh.Reweight()
+    assert gsh.GetLikelihood() == pytest.approx(osh.GetLikelihood(), rel=1e-9 if _exact() else LLH_RTOL)
