@@ -466,6 +466,16 @@ def main_cfg5(args):
     t_b = (time.perf_counter() - t1) / K
     msb, nb = h.kernel_time()
     kms = msb / max(nb, 1)
+    # LLH scan of one parameter (FitterBase::RunLLHScan): 256 points, every other parameter fixed -> one segment per slot
+    sp0, nm0 = synth.proposal(w, 1)
+    sc_sp = np.tile(sp0, (n_sets, 1)); sc_sp[:, 0] = np.linspace(-2.9, 2.9, n_sets)
+    sc_nm = np.tile(nm0, (n_sets, 1))
+    h.step_batch(sc_sp, sc_nm); h.kernel_time()
+    t2 = time.perf_counter()
+    for k in range(K):
+        h.step_batch(sc_sp, sc_nm)
+    t_scan = (time.perf_counter() - t2) / K
+    ms_scan, n_scan = h.kernel_time()
     fp_instr = w.n_events * n_sets * (4 * (w.n_params - w.n_linear) + 2 * w.n_linear)     # FMA/MUL issue slots
     peak_issue = 148 * 128 * 1.965e9
     line = {"metric": "LLH evaluations/s over batched proposals (reweight+fill+LLH per parameter set)", "value": n_sets / t_b,
@@ -473,7 +483,9 @@ def main_cfg5(args):
             "event_sets_per_s": w.n_events * n_sets / t_b, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
             "config": {"workload": w.name, "events": w.n_events, "sets_per_batch": n_sets, "bins": w.n_bins, "setup_s": round(t_setup, 1),
-                       "single_set_kernel_ms": ms1 / max(n1, 1), "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / kms},
+                       "single_set_kernel_ms": ms1 / max(n1, 1), "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / kms,
+                       "llh_scan_256_points": {"ms": 1e3 * t_scan, "us_per_llh": 1e6 * t_scan / n_sets, "kernel_ms": ms_scan / max(n_scan, 1),
+                                               "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / (ms_scan / max(n_scan, 1))}},
             "roofline": {"bound": "fp32 issue (CUDA cores; no contraction, so no tensor cores)", "achieved": fp_instr / (kms * 1e-3) / 1e12,
                          "peak": peak_issue / 1e12, "unit": "T FP32 instr/s", "frac": fp_instr / (kms * 1e-3) / peak_issue,
                          "kernel": "m3b::fill_batch_kernel", "kernel_ms": kms, "traffic": None},

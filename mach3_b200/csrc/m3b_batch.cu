@@ -7,11 +7,11 @@
 //     tile    = 32 consecutive events, whose coefficient rows -- for every segment that ANY set of the batch
 //               selects (1-3 per parameter for proposals around one point) -- a producer warp stages in
 //               shared memory with 1-D bulk copies (multi-buffered);
-//     thread  = one EVENT of the tile (lane) x 32 parameter SETS (warp w owns sets 32w..32w+31), so a
+//     thread  = one EVENT of the tile (lane) x 16 parameter SETS (warp w owns sets 16w..16w+15), so a
 //               coefficient row is read from shared memory ONCE per warp (conflict-free LDS.128) and re-used
-//               from registers for the warp's 32 sets; per (slot,set) a broadcast LDS.64 brings {dx, which
+//               from registers for the warp's 16 sets; per (slot,set) a broadcast LDS.64 brings {dx, which
 //               staged row}.  Slots whose sets use 1/2/3 distinct segments evaluate those 1/2/3 polynomials and
-//               select the result (warp-uniform); more fall back to a per-set LDS.128.  32 running products in
+//               select the result (warp-uniform); more fall back to a per-set LDS.128.  16 running products in
 //               registers, cubic slots in order, then TF1 slots: the reference's order
 //               (Splines/SplineMonolith.cpp:799-828), so every (event,set) weight is bit-identical to the
 //               single-set path;
@@ -27,7 +27,10 @@
 namespace m3b {
 
 constexpr int kBT = 32;            // events per batch tile
-constexpr int kBSets = 256;        // sets per launch = consumer threads
+constexpr int kBSets = 256;        // sets per launch
+constexpr int kSW = 16;            // sets per consumer warp: 16 warps x 16 sets (more warps per scheduler than 8 x 32)
+constexpr int kCW = kBSets / kSW;  // consumer warps
+constexpr int kCT = kCW * 32;      // consumer threads
 constexpr int kRowF4 = kBT + 1;    // staged cubic row stride in float4: +16 B of padding so that lanes whose sets select
                                    // different segments of a slot (rows r, r') hit different banks at the same event
 
@@ -57,7 +60,7 @@ __device__ __forceinline__ void mbar_arrive_b(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid_constant__ BatchArgs a) {
+__global__ void __launch_bounds__(kCT + 32, 1) fill_batch_kernel(const __grid_constant__ BatchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4];
   __shared__ int4 s_desc[4];       // {unit, sig, 0, 0}; unit < 0 = no more work
@@ -72,11 +75,11 @@ __global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid
   const int buf_bytes = a.max_rows * kRowF4 * 16 + a.max_nl * kBT * 8;
   unsigned char* bufs = smem + tables_bytes;
 
-  if (tid == 0) for (int b = 0; b < a.n_buf; ++b) { mbar_init(&full_bar[b], 1); mbar_init(&empty_bar[b], kBSets / 32); }
-  for (int i = tid; i < a.n_norm * kBSets; i += kBSets + 32) s_norm[(i % kBSets) * nnp + i / kBSets] = a.t_norm[i];
+  if (tid == 0) for (int b = 0; b < a.n_buf; ++b) { mbar_init(&full_bar[b], 1); mbar_init(&empty_bar[b], kCW); }
+  for (int i = tid; i < a.n_norm * kBSets; i += kCT + 32) s_norm[(i % kBSets) * nnp + i / kBSets] = a.t_norm[i];
   __syncthreads();
 
-  if (warp == kBSets / 32) {
+  if (warp == kCW) {
     // ---------------------------------------------------------------- producer warp
     int buf = 0; uint32_t phase = 1;
     while (true) {
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid
     }
   } else {
     // ---------------------------------------------------------------- consumers: lane = event, warp = 32 sets
-    const int set0 = warp * 32;
+    const int set0 = warp * kSW;
     int buf = 0; uint32_t phase = 0; int cur_sig = -1, nc = 0, nl = 0;
     auto H = [](const float4& k, float dx) { return fmaf(dx, fmaf(dx, fmaf(dx, k.w, k.z), k.y), k.x); };
     while (true) {
@@ -116,16 +119,15 @@ __global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid
       const int4 d = s_desc[buf];
       if (d.x < 0) break;
       if (d.y != cur_sig) {            // block-uniform: reload this signature's per-set tables
-        asm volatile("bar.sync 1, %0;" ::"r"(kBSets) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(kCT) : "memory");
         const BatchSig sg = a.sigs[d.y];
         nc = sg.nc; nl = sg.nl;
-        for (int c = 0; c < nc; ++c)
-          s_tab[c * kBSets + tid] = make_float2(a.t_dx[sg.off_dx + c * kBSets + tid],
-                                                __int_as_float(static_cast<int>(a.t_rowoff[sg.off_rowoff + c * kBSets + tid])));
-        for (int l = 0; l < nl; ++l) s_val[l * kBSets + tid] = a.t_val[sg.off_val + l * kBSets + tid];
-        for (int c = tid; c < nc; c += kBSets) s_slot[c] = make_int2(a.t_slot[sg.off_slot + 2 * c], a.t_slot[sg.off_slot + 2 * c + 1]);
+        for (int i = tid; i < nc * kBSets; i += kCT)
+          s_tab[i] = make_float2(a.t_dx[sg.off_dx + i], __int_as_float(static_cast<int>(a.t_rowoff[sg.off_rowoff + i])));
+        for (int i = tid; i < nl * kBSets; i += kCT) s_val[i] = a.t_val[sg.off_val + i];
+        for (int c = tid; c < nc; c += kCT) s_slot[c] = make_int2(a.t_slot[sg.off_slot + 2 * c], a.t_slot[sg.off_slot + 2 * c + 1]);
         cur_sig = d.y;
-        asm volatile("bar.sync 1, %0;" ::"r"(kBSets) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(kCT) : "memory");
       }
       const unsigned char* src = bufs + static_cast<size_t>(buf) * buf_bytes;
       const float4* cub = reinterpret_cast<const float4*>(src) + lane;
@@ -144,9 +146,9 @@ __global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid
       #pragma unroll
       for (int j = 0; j < 4; ++j) if (j < a.norm_slots) ni[j] = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + ev];
 
-      float W[32];
+      float W[kSW];
       #pragma unroll
-      for (int q = 0; q < 32; ++q) W[q] = 1.0f;
+      for (int q = 0; q < kSW; ++q) W[q] = 1.0f;
       const bool active = set0 < a.n_sets;              // warps whose 32 sets are all padding only keep the ring moving
       for (int c = 0; active && c < nc; ++c) {
         const int2 si = s_slot[c];                      // {first staged row, distinct segments}: block-uniform
@@ -155,13 +157,13 @@ __global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid
         if (si.y == 1) {
           const float4 k0 = rp[0];
           #pragma unroll
-          for (int q = 0; q < 32; ++q) W[q] *= H(k0, tab[q].x);
+          for (int q = 0; q < kSW; ++q) W[q] *= H(k0, tab[q].x);
         } else if (si.y <= 3) {
           // staged row 0 is the segment most sets of the batch select: evaluate it for every set and redo the
           // few sets that sit in a neighbouring segment (warp-uniform: the row rank depends on the set only)
           const float4 k0 = rp[0], k1 = rp[kRowF4], k2 = rp[(si.y - 1) * kRowF4];
           #pragma unroll
-          for (int q = 0; q < 32; ++q) {
+          for (int q = 0; q < kSW; ++q) {
             const float2 tq = tab[q];
             const int r = __float_as_int(tq.y);
             float h = H(k0, tq.x);
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid
           }
         } else {
           #pragma unroll
-          for (int q = 0; q < 32; ++q) {
+          for (int q = 0; q < kSW; ++q) {
             const float2 tq = tab[q];
             W[q] *= H(rp[__float_as_int(tq.y) * kRowF4], tq.x);
           }
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid
         const float2 k = lin[l * kBT];
         const float* vp = s_val + l * kBSets + set0;
         #pragma unroll
-        for (int q = 0; q < 32; ++q) W[q] *= fmaf(k.x, vp[q], k.y);
+        for (int q = 0; q < kSW; ++q) W[q] *= fmaf(k.x, vp[q], k.y);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_b(&empty_bar[buf]);
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(kBSets + 32, 1) fill_batch_kernel(const __grid
       // CalcWeightTotal + fill, per (event, set): norms (reference order), osc, spline, static
       if (!active) continue;
       #pragma unroll
-      for (int q = 0; q < 32; ++q) {
+      for (int q = 0; q < kSW; ++q) {
         const int set = set0 + q;
         const float* nv = s_norm + set * nnp;
         float w = 1.0f;
@@ -370,7 +372,7 @@ int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, cons
     if (h->tev_used + 2 > h->tev.size()) for (int i = 0; i < 2; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->tev.push_back(e); }
     CK(cudaEventRecord(h->tev[h->tev_used], h->stream));
   }
-  fill_batch_kernel<<<grid, kBSets + 32, smem, h->stream>>>(a);
+  fill_batch_kernel<<<grid, kCT + 32, smem, h->stream>>>(a);
   CK(cudaGetLastError());
   if (h->timing) { CK(cudaEventRecord(h->tev[h->tev_used + 1], h->stream)); h->tev_used += 2; }
   const int nxt = h->cur ^ 1;       // leave the handle as after the last set's step: its histogram becomes the current one
