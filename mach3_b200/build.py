@@ -86,6 +86,10 @@ def build_reference_gpu(force=False, verbose=False):
     if not os.path.isdir(REFERENCE) or not os.path.exists(mk):
         return None
     _run(["make", "-C", os.path.dirname(mk), "-B" if force else "-s"], verbose)
+    # the reference's own (header-only) binning code behind a C ABI: pins the oracle's FindBin / non-uniform binning
+    hmk = os.path.join(ORACLE, "ref_host", "Makefile")
+    if os.path.exists(hmk):
+        _run(["make", "-C", os.path.dirname(hmk), "-B" if force else "-s"], verbose)
     # the drop-in SMonolithGPU adapter, compiled against the reference's own header + the same harness
     amk = os.path.join(ROOT, "adapters", "Makefile")
     if os.path.exists(amk):

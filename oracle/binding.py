@@ -41,6 +41,11 @@ def lib():
         L.m3o_test_stat_llh.restype = C.c_double
         L.m3o_test_stat_llh.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
         L.m3o_find_bin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.m3o_bin_edge.restype = C.c_double
+        L.m3o_bin_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.m3o_grid_entry.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.m3o_grid_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.m3o_axis_nbins.argtypes = [C.c_void_p, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -259,6 +264,14 @@ class SampleHandlerFD:
 
     def find_bin(self, sample, dim, var, nom_bin):
         return lib().m3o_find_bin(self.h, sample, dim, float(var), int(nom_bin))
+
+    def axis_edges(self, sample, dim):
+        n = lib().m3o_axis_nbins(self.h, sample, dim)
+        return np.array([lib().m3o_bin_edge(self.h, sample, dim, i) for i in range(n + 1)])
+
+    def grid_mapping(self, sample, mega):
+        n = lib().m3o_grid_size(self.h, sample, mega)
+        return [lib().m3o_grid_entry(self.h, sample, mega, k) for k in range(n)]
 
     def __del__(self):
         try:

@@ -894,6 +894,17 @@ M3O_API void m3o_event_weights(const SampleHandlerFD* s, float* out) {
     out[e] = g_multithread ? CalcWeightTotal(&s->MCSamples[e]) : CalcWeightTotal_serial(&s->MCSamples[e]);
 }
 /* single-value bin lookup for the FindBin known-answer tests */
+/* accessors used to pin the binning restatement against the reference's own SampleBinningInfo (oracle/ref_host) */
+M3O_API double m3o_bin_edge(const SampleHandlerFD* s, int sample, int dim, int i) { return s->SampleBinning[sample].BinEdges[dim][i]; }
+M3O_API int m3o_axis_nbins(const SampleHandlerFD* s, int sample, int dim) { return s->SampleBinning[sample].AxisNBins[dim]; }
+M3O_API int m3o_grid_size(const SampleHandlerFD* s, int sample, int mega) {
+  const SampleBinningInfo* b = &s->SampleBinning[sample];
+  return b->Uniform ? 0 : b->GridStart[mega + 1] - b->GridStart[mega];
+}
+M3O_API int m3o_grid_entry(const SampleHandlerFD* s, int sample, int mega, int k) {
+  const SampleBinningInfo* b = &s->SampleBinning[sample];
+  return b->GridIdx[b->GridStart[mega] + k];
+}
 M3O_API int m3o_find_bin(const SampleHandlerFD* s, int sample, int dim, double var, int nom_bin) {
   const SampleBinningInfo* b = &s->SampleBinning[sample];
   return FindBin(var, nom_bin, b->AxisNBins[dim], b->BinEdges[dim], b->BinLookup[dim]);

@@ -1,0 +1,3 @@
+// stand-in for ROOT's TH1.h (ROOT is not installed in this image): deliberately empty.
+// The reference code compiled through oracle/ref_host uses nothing from it.
+#pragma once
