@@ -16,8 +16,11 @@
  *  and its host code cannot be built here (needs ROOT, yaml-cpp, spdlog).  The
  * spline-evaluation part (CalcSplineWeights + CalcTotalEventWeight) is pinned against the
  * reference's OWN CUDA kernels (Splines/gpuSplineUtils.cu compiled from /root/reference into
- * oracle/_ref, run on a B200; vectors committed under tests/golden/).  FindSplineSegment,
- * FillArray, FindBin and the test statistics are "parity unpinned": checked only against
+ * oracle/_ref, run on a B200; vectors committed under tests/golden/).  The binning part (FindBin,
+ * bin-migration look-up, strides, InitNonUniform, InitialiseGridMapping, IsEventInside) is pinned against the
+ * reference's OWN header Samples/SampleStructs.h compiled into oracle/_ref/libm3ref_host.so (oracle/ref_host,
+ * vectors tests/golden/ref_host_binning.npz).  FindSplineSegment, CalcWeightTotal, FillArray, the test
+ * statistics and BinnedSplineHandler::CalcSplineWeights are "parity unpinned": checked only against
  * known-answer tests derived from the formulas.
  *
  * The data layout deliberately mirrors the reference (AoS {y,b,c,d} knots, {count,start}
