@@ -391,7 +391,11 @@ def main_cfg4(args):
     t_e2e = time.perf_counter() - t1
     n_act = int(d["spl"]["uniquecoeffindices"].size)
     n_ptr = int(d["ev"]["spline_index"].size)
-    alg = n_act * (16 + 4 + 4) + w.n_events * 8 + n_ptr * 4 * 2       # eval: {y,b,c,d}+x read, weight write; fill: index + gather
+    mask = np.zeros(w.n_slots, bool); mask[d["spl"]["uniquecoeffindices"]] = True
+    n_nonflat = int(mask[d["ev"]["spline_index"]].sum())              # pointers at flat splines (exactly 1.0) are dropped at upload
+    del mask
+    # eval: {y,b,c,d}+x read, weight write per non-flat spline; fill: event table + (index + gathered weight) per non-flat pointer
+    alg = n_act * (16 + 4 + 4) + w.n_events * 8 + n_nonflat * 4 * 2
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -403,7 +407,7 @@ def main_cfg4(args):
             "value": w.n_events / (t_async / K), "unit": "events/s", "n_gpus": 1, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * t_async / K, "binned_spline_evals_per_s": n_act / (t_async / K), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
-            "config": {"workload": w.name, "events": w.n_events, "active_binned_splines": n_act, "weight_pointers": n_ptr,
+            "config": {"workload": w.name, "events": w.n_events, "active_binned_splines": n_act, "weight_pointers": n_ptr, "non_flat_weight_pointers": n_nonflat,
                        "slots": w.n_slots, "bins": w.n_bins, "setup_s": round(t_setup, 1),
                        "l2": "coefficient rows (%.0f MB/step) stream from HBM; the compact weight array (%.0f MB) is gathered through L2"
                              % (n_act * 20 / 1e6, n_act * 4 / 1e6)},

@@ -657,7 +657,7 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
       REQUIRE(bps > 0, M3B_ERR_CUDA, "step: binned fill kernel does not fit on an SM");
       h->smem = smem;
       h->grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_wtiles + 7) / 8, static_cast<int64_t>(bps) * h->sm_count)));
-      h->binned_eval_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_btiles + 3) / 4, 8ll * h->sm_count)));
+      h->binned_eval_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_btiles + 1) / 2, 8ll * h->sm_count)));
       h->launch_ready = true;
       h->launch_w2_live = w2_live;
       return M3B_OK;
@@ -721,18 +721,13 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   // kernel's producers stream them over PCIe while the coefficients stream from HBM.
   const float* osc_zc = nullptr;
   if (osc_w && h->use_osc && !h->d_osc_idx && h->T % 256 == 0) {
-    auto it = h->zc_ptr.find(osc_w);
-    if (it == h->zc_ptr.end()) {
-      const float* dev = nullptr;
-      const char* z = getenv("M3B_OSC_ZEROCOPY");
-      cudaPointerAttributes at{};
-      if (!(z && z[0] == '0') && cudaPointerGetAttributes(&at, osc_w) == cudaSuccess && at.type == cudaMemoryTypeHost &&
-          at.devicePointer && (reinterpret_cast<uintptr_t>(at.devicePointer) & 15) == 0)
-        dev = static_cast<const float*>(at.devicePointer);
-      cudaGetLastError();
-      it = h->zc_ptr.emplace(osc_w, dev).first;
-    }
-    osc_zc = it->second;
+    // asked every step (about a microsecond): the caller may have re-registered or re-allocated the array
+    static const bool zc_off = [] { const char* z = getenv("M3B_OSC_ZEROCOPY"); return z && z[0] == '0'; }();
+    cudaPointerAttributes at{};
+    if (!zc_off && cudaPointerGetAttributes(&at, osc_w) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
+        (reinterpret_cast<uintptr_t>(at.devicePointer) & 15) == 0)
+      osc_zc = static_cast<const float*>(at.devicePointer);
+    cudaGetLastError();
     if (osc_zc && !h->zc_slots) { h->zc_slots = true; h->launch_ready = false; }
   }
   int rc = prepare_launch(h, w2_live);

@@ -15,6 +15,8 @@
 
 namespace m3b {
 
+constexpr int kBTileSplines = 1024;     // splines per BTile: 4 per thread, so one descriptor load feeds 4 x 20 B of stream
+
 __global__ void __launch_bounds__(256) binned_eval_kernel(const __grid_constant__ FillArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -23,17 +25,17 @@ __global__ void __launch_bounds__(256) binned_eval_kernel(const __grid_constant_
   stage_step_table(a, smem, &bar);
   const int32_t* seg = reinterpret_cast<const int32_t*>(smem + a.step.off_seg);
   const float* val = reinterpret_cast<const float*>(smem + a.step.off_val);
-  constexpr int U = 4;          // tiles in flight per block: 4 x (16+4) B per thread before the first use
+  constexpr int U = 2, V = kBTileSplines / 256;      // tiles in flight per block x splines per thread per tile
   for (int t0 = blockIdx.x * U; t0 < a.n_btiles; t0 += gridDim.x * U) {
-    float4 c[U]; float x[U]; float xv[U]; int out[U];
+    float4 c[U][V]; float x[U][V]; float xv[U]; int out[U];
     #pragma unroll
     for (int u = 0; u < U; ++u) {
       out[u] = -1;
       if (t0 + u < a.n_btiles) {
         const BTile bt = a.btiles[t0 + u];
         const int64_t i = bt.coef_off + static_cast<int64_t>(seg[bt.param]) * bt.n_pad + bt.k0 + threadIdx.x;
-        c[u] = ldg_stream(a.bcoef + i);
-        x[u] = __ldcs(a.bx + i);
+        #pragma unroll
+        for (int v = 0; v < V; ++v) { c[u][v] = ldg_stream(a.bcoef + i + v * 256); x[u][v] = __ldcs(a.bx + i + v * 256); }
         xv[u] = val[bt.param];                 // M3::float_t(*splineParsPointer), :327
         out[u] = bt.out0 + threadIdx.x;
       }
@@ -41,10 +43,13 @@ __global__ void __launch_bounds__(256) binned_eval_kernel(const __grid_constant_
     #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (out[u] >= 0) {
-        const float dx = xv[u] - x[u];                                               // :329
-        float w = fmaf(dx, fmaf(dx, fmaf(dx, c[u].w, c[u].z), c[u].y), c[u].x);       // :332
-        if (w < 0) w = 0.f;                                                           // :337
-        a.bw[out[u]] = w;
+        #pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float dx = xv[u] - x[u][v];                                                          // :329
+          float w = fmaf(dx, fmaf(dx, fmaf(dx, c[u][v].w, c[u][v].z), c[u][v].y), c[u][v].x);         // :332
+          if (w < 0) w = 0.f;                                                                         // :337
+          a.bw[out[u] + v * 256] = w;
+        }
       }
     }
   }
@@ -177,7 +182,7 @@ M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t m
   }
   std::vector<int64_t> out_base(n_params + 1, 0), coef_base(n_params + 1, 0), npad(n_params, 0);
   for (int p = 0; p < n_params; ++p) {
-    npad[p] = (count[p + 1] + 255) / 256 * 256;
+    npad[p] = (count[p + 1] + kBTileSplines - 1) / kBTileSplines * kBTileSplines;
     out_base[p + 1] = out_base[p] + npad[p];
     coef_base[p + 1] = coef_base[p] + npad[p] * h->nseg[p];
   }
@@ -202,7 +207,7 @@ M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t m
   }
   std::vector<BTile> tiles;
   for (int p = 0; p < n_params; ++p)
-    for (int64_t k0 = 0; k0 < npad[p]; k0 += 256)
+    for (int64_t k0 = 0; k0 < npad[p]; k0 += kBTileSplines)
       tiles.push_back(BTile{coef_base[p], static_cast<int32_t>(npad[p]), p, static_cast<int32_t>(k0), static_cast<int32_t>(out_base[p] + k0)});
   CK(dev_upload(h, &h->d_bcoef, coef));
   CK(dev_upload(h, &h->d_bx, xs));

@@ -114,7 +114,6 @@ struct m3b_handle {
   TmaSmem tma{};
   unsigned int* d_tile_counter = nullptr;
   bool zc_slots = false;                   // shared-memory slots for zero-copy oscillation weights
-  std::map<const void*, const float*> zc_ptr;   // pinned host array -> its device alias (or nullptr)
   unsigned long long* d_trace = nullptr;   // m3b_block_trace
   int trace_grid = 0;
   bool hist_in_smem = true;

@@ -66,10 +66,10 @@ inline StepLayout make_step_layout(int P, int Nn, int n_sigs, int max_nc, int ma
 }
 
 // ---- BinnedSplineHandler path (m3b_binned.cu) ------------------------------------------------------
-// Active (non-flat) binned splines are grouped by parameter and padded to 256 per parameter:
+// Active (non-flat) binned splines are grouped by parameter and padded to 1024 per parameter:
 //   bcoef[coef_off + segment * n_pad + k]  float4 {y,b,c,d}     bx[same index]  knot x of that segment
 // so one step reads, per parameter, ONE contiguous row of coefficients and one of x.
-struct BTile {                 // 256 consecutive active splines of one parameter
+struct BTile {                 // 1024 consecutive active splines of one parameter
   int64_t coef_off;            // first element of the parameter's [nseg][n_pad] block
   int32_t n_pad, param, k0, out0;   // row length, parameter, first spline of the tile in the row, first compact weight
 };
