@@ -129,6 +129,21 @@ M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t m
 M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, const uint32_t* n_per_event,
                                             const int32_t* spline_index);
 M3B_API int m3b_read_binned_weights(m3b_handle* h, float* weightvec_Monolith /* [n_slots] */);
+/* The same path in the reference's DEFAULT build (M3::float_t = double, Manager/Core.h:27-51 -- the build in which
+ * BinnedSplineHandler is normally used): coefficients, knots, binned weights, oscillation and static weights and the
+ * per-event product are double, fma instead of fmaf, the parameter value is read un-narrowed by the evaluation
+ * (Splines/BinnedSplineHandler.cpp:327) but narrowed to float by FindSplineSegment (Splines/SplineBase.cpp:54).
+ * m3b_upload_binned_splines_f64 switches the handle to that build; oscillation weights then come through
+ * m3b_upload_osc_f64 (m3b_step's float osc_w must be NULL), static weights through m3b_upload_event_weights_f64
+ * (or widened from m3b_upload_events' floats), mirrors through the *_f64 readers.                                 */
+M3B_API int m3b_upload_binned_splines_f64(m3b_handle* h, int32_t n_params, int32_t max_knots, const double* knot_x,
+                                          const int16_t* n_pts, int64_t n_slots, const int32_t* uniquesplinevec_Monolith,
+                                          const int32_t* coeffindexvec, int64_t n_unique, const int32_t* uniquecoeffindices,
+                                          int64_t n_coeff, const double* manycoeff_arr, const double* xcoeff_arr);
+M3B_API int m3b_upload_event_weights_f64(m3b_handle* h, int64_t n_events, const double* static_w);
+M3B_API int m3b_upload_osc_f64(m3b_handle* h, const double* osc_w, int64_t n);
+M3B_API int m3b_read_binned_weights_f64(m3b_handle* h, double* weightvec_Monolith /* [n_slots] */);
+M3B_API int m3b_read_event_weights_f64(m3b_handle* h, double* spline_w, double* total_w);
 
 /* ---- binning, events, data -------------------------------------------------------------------
  * m3b_upload_binning: BinningHandler's uniform binning (Samples/BinningHandler.cpp:341-355,

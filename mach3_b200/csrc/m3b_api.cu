@@ -577,11 +577,13 @@ M3B_API int m3b_reset_w2(m3b_handle* h) {
 // the step
 // ------------------------------------------------------------------------------------------------
 // SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-109), same decisions in the same order
-static void find_segments(m3b_handle* h, const double* pars) {
+extern "C++" {
+template <class K>
+static void find_segments_t(m3b_handle* h, const double* pars, const K* knots) {
   for (int i = 0; i < h->P; ++i) {
     const int nPoints = h->n_pts[i];
-    const float* x = h->coeff_x.data() + static_cast<size_t>(i) * h->Kmax;
-    const float xvar = static_cast<float>(pars[i]);
+    const K* x = knots + static_cast<size_t>(i) * h->Kmax;      // FastSplineInfo::xPts (M3::float_t)
+    const float xvar = static_cast<float>(pars[i]);             // always narrowed to float, :54
     h->param_values[i] = xvar;
     if (nPoints == 0) continue;
     int segment = 0, hi = nPoints - 1;
@@ -599,6 +601,11 @@ static void find_segments(m3b_handle* h, const double* pars) {
     h->curr_segment[i] = static_cast<int16_t>(segment);
     h->segments[i] = static_cast<int16_t>(segment);
   }
+}
+}  // extern "C++"
+static void find_segments(m3b_handle* h, const double* pars) {
+  if (h->f64) find_segments_t(h, pars, h->coeff_x_d.data());
+  else find_segments_t(h, pars, h->coeff_x.data());
 }
 
 M3B_API int m3b_find_segments(m3b_handle* h, const double* spline_pars, int16_t* segments, float* param_values) {
@@ -631,7 +638,7 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
   }
   if (!h->h_step[0] || h->step.P != h->P || h->step.Nn != h->n_norm_values || h->step_sigs != (h->binned ? 0 : static_cast<int>(h->sigs.size()))) {
     h->step_sigs = h->binned ? 0 : static_cast<int>(h->sigs.size());
-    h->step = make_step_layout(h->P, h->n_norm_values, h->step_sigs, h->max_nc, h->max_nl);
+    h->step = make_step_layout(h->P, h->n_norm_values, h->step_sigs, h->max_nc, h->max_nl, h->f64);
     for (int i = 0; i < m3b_handle::kRing; ++i) {
       if (h->h_step[i]) cudaFreeHost(h->h_step[i]);
       CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_step[i]), h->step.bytes, cudaHostAllocDefault));
@@ -752,9 +759,15 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     seg[p] = segs[p];
     val[p] = vals[p];
     // dx = ParamValues[Param] - coeff_x[Param*_max_knots+segment]  (Splines/SplineMonolith.cpp:759), in float
-    dx[p] = h->n_pts[p] > 0 ? vals[p] - h->coeff_x[static_cast<size_t>(p) * h->Kmax + segs[p]] : 0.f;
+    dx[p] = (h->n_pts[p] > 0 && !h->f64) ? vals[p] - h->coeff_x[static_cast<size_t>(p) * h->Kmax + segs[p]] : 0.f;
   }
   for (int j = 0; j < h->n_norm_values; ++j) norm[j] = static_cast<float>(norm_pars[j]);   // SampleHandlerFD.cpp:580
+  if (h->f64) {      // default build: the binned eval reads the parameter un-narrowed (BinnedSplineHandler.cpp:327), norms stay double
+    double* vd = reinterpret_cast<double*>(st + h->step.off_val_d);
+    double* nd = reinterpret_cast<double*>(st + h->step.off_norm_d);
+    for (int p = 0; p < h->P; ++p) vd[p] = h->spline_pars_last.empty() ? static_cast<double>(vals[p]) : h->spline_pars_last[p];
+    for (int j = 0; j < h->n_norm_values; ++j) nd[j] = norm_pars[j];
+  }
   if (h->step.n_sigs_x) {     // per-signature slot tables: no indirection left for the device
     int32_t* rowx = reinterpret_cast<int32_t*>(st + h->step.off_rowx);
     float* dxx = reinterpret_cast<float*>(st + h->step.off_dxx);
@@ -775,6 +788,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   }
   if (osc_w) {
     REQUIRE(h->use_osc, M3B_ERR_INVALID, "step: osc_w given but events were uploaded with use_osc=0");
+    REQUIRE(!h->f64, M3B_ERR_INVALID, "step: this handle runs the double build; pass oscillation weights with m3b_upload_osc_f64");
     if (!osc_zc) CK(cudaMemcpyAsync(h->d_osc, osc_w, sizeof(float) * h->n_osc, cudaMemcpyHostToDevice, h->stream));
   }
 
@@ -844,6 +858,9 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   if (h->binned) {
     a.btiles = h->d_btiles; a.n_btiles = h->n_btiles; a.bcoef = h->d_bcoef; a.bx = h->d_bx; a.bw = h->d_bw;
     a.ell = h->d_ell; a.wtiles = h->d_wtiles; a.n_wtiles = h->n_wtiles;
+    a.real_f64 = h->f64 ? 1 : 0;
+    a.bcoef_d = h->d_bcoef_d; a.bx_d = h->d_bx_d; a.bw_d = h->d_bw_d; a.osc_d = h->d_osc_d; a.static_d = h->d_static_d;
+    a.evt_spline_d = h->d_evt_spline_d; a.evt_total_d = h->d_evt_total_d;
     if (h->n_btiles > 0) { CK(launch_binned_eval(a, h->binned_eval_grid, h->stream)); ++h->launches; }
     CK(launch_binned_fill(a, h->grid, h->smem, h->stream));
   } else if (h->use_tma) CK(launch_fill_tma(a, h->grid, h->smem, h->stream));
@@ -881,6 +898,7 @@ static int step_common(m3b_handle* h, const double* spline_pars, const double* n
   if (h->P > 0) {
     REQUIRE(spline_pars, M3B_ERR_INVALID, "step: spline_pars is NULL");
     find_segments(h, spline_pars);
+    if (h->f64) h->spline_pars_last.assign(spline_pars, spline_pars + h->P);
   }
   return enqueue_step(h, h->param_values.data(), h->segments.data(), norm_pars, osc_w, mode);
 }
@@ -899,6 +917,7 @@ M3B_API int m3b_step_segments(m3b_handle* h, const float* param_values, const in
     REQUIRE(sg >= 0 && sg < std::max<int>(1, h->nseg[p]), M3B_ERR_INVALID, "m3b_step_segments: segment out of range");
     h->segments[p] = sg; h->curr_segment[p] = sg; h->param_values[p] = param_values[p];
   }
+  h->spline_pars_last.clear();          // only the narrowed values are known on this entry point
   return enqueue_step(h, h->param_values.data(), h->segments.data(), norm_pars, osc_w,
                       (h->cfg.flags & M3B_FLAG_NO_FUSED_LLH) ? kFillOnly : kFused);
 }

@@ -12,6 +12,7 @@
 // _LOW_MEMORY_STRUCTS_ build of the reference (M3::float_t = float), like the SMonolith path.
 #include "m3b_device.cuh"
 #include "m3b_handle.h"
+#include <type_traits>
 
 namespace m3b {
 
@@ -55,6 +56,37 @@ __global__ void __launch_bounds__(256) binned_eval_kernel(const __grid_constant_
   }
 }
 
+// the same in the reference's default build: M3::float_t = double, fma instead of fmaf (Manager/Core.h:44-51), the
+// parameter value read un-narrowed (:327)
+__global__ void __launch_bounds__(256) binned_eval_kernel_f64(const __grid_constant__ FillArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  stage_step_table(a, smem, &bar);
+  const int32_t* seg = reinterpret_cast<const int32_t*>(smem + a.step.off_seg);
+  const double* val = reinterpret_cast<const double*>(smem + a.step.off_val_d);
+  constexpr int V = kBTileSplines / 256;
+  for (int t = blockIdx.x; t < a.n_btiles; t += gridDim.x) {
+    const BTile bt = a.btiles[t];
+    const int64_t i = bt.coef_off + static_cast<int64_t>(seg[bt.param]) * bt.n_pad + bt.k0 + threadIdx.x;
+    const double xv = val[bt.param];
+    double2 lo[V], hi[V]; double x[V];
+    #pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const double2* cp = reinterpret_cast<const double2*>(a.bcoef_d + 4 * (i + v * 256));
+      lo[v] = __ldcs(cp); hi[v] = __ldcs(cp + 1); x[v] = __ldcs(a.bx_d + i + v * 256);
+    }
+    #pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const double dx = xv - x[v];
+      double w = fma(dx, fma(dx, fma(dx, hi[v].y, hi[v].x), lo[v].y), lo[v].x);
+      if (w < 0) w = 0.;
+      a.bw_d[bt.out0 + threadIdx.x + v * 256] = w;
+    }
+  }
+}
+
 int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
   int b = (a.step.bytes + 15) & ~15;
   if (hist_in_smem) b += 8 * a.n_bins * (w2_live ? 2 : 1);
@@ -62,7 +94,9 @@ int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
   return b > llh_scratch ? b : llh_scratch;
 }
 
+template <bool F64>
 __global__ void __launch_bounds__(256) binned_fill_kernel(const __grid_constant__ FillArgs a) {
+  using R = typename std::conditional<F64, double, float>::type;      // M3::float_t of the build
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_last;
@@ -78,39 +112,45 @@ __global__ void __launch_bounds__(256) binned_fill_kernel(const __grid_constant_
     if (w2_live) for (int i = tid; i < a.n_bins; i += 256) s_w2[i] = 0.;
   }
   stage_step_table(a, smem, &bar);
-  const float* norm = reinterpret_cast<const float*>(smem + a.step.off_norm);
+  const R* norm = reinterpret_cast<const R*>(smem + (F64 ? a.step.off_norm_d : a.step.off_norm));
+  const R* bw = F64 ? reinterpret_cast<const R*>(a.bw_d) : reinterpret_cast<const R*>(a.bw);
+  const R* oscp = F64 ? reinterpret_cast<const R*>(a.osc_d) : reinterpret_cast<const R*>(a.osc);
+  const R* statp = F64 ? reinterpret_cast<const R*>(a.static_d) : reinterpret_cast<const R*>(a.static_w);
 
   for (int64_t wt = static_cast<int64_t>(blockIdx.x) * 8 + warp; wt < a.n_wtiles; wt += static_cast<int64_t>(gridDim.x) * 8) {
     const WTile d = a.wtiles[wt];
     const int64_t e = wt * 32 + lane;
     const int bin = a.bin[e];
-    float w_osc = 1.f, w_static = 1.f;
-    if (a.osc) {
+    R w_osc = 1, w_static = 1;
+    if (oscp) {
       const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
-      w_osc = a.osc[oi];
+      w_osc = oscp[oi];
     }
-    if (a.static_w) w_static = a.static_w[e];
+    if (statp) w_static = statp[e];
     // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras
-    float w = 1.0f;
+    R w = 1;
     for (int j = 0; j < a.norm_slots; ++j) {
       const int i = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + e];
-      w *= (i >= 0 ? norm[i] : 1.0f);
+      w *= (i >= 0 ? norm[i] : R(1));
     }
     w *= w_osc;
-    float w_spl = 1.0f;        // product of the binned weights alone (m3b_read_event_weights)
+    R w_spl = 1;               // product of the binned weights alone (m3b_read_event_weights)
     const int32_t* col = a.ell + d.off + lane;
     for (int j0 = 0; j0 < d.max_n; j0 += 8) {
-      int idx[8]; float g[8];
+      int idx[8]; R g[8];
       #pragma unroll
       for (int j = 0; j < 8; ++j) idx[j] = (j0 + j < d.max_n) ? __ldcs(col + (j0 + j) * 32) : -1;
       #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = idx[j] >= 0 ? __ldg(a.bw + idx[j]) : 1.0f;
+      for (int j = 0; j < 8; ++j) g[j] = idx[j] >= 0 ? __ldg(bw + idx[j]) : R(1);
       #pragma unroll
       for (int j = 0; j < 8; ++j) if (idx[j] >= 0) { w *= g[j]; w_spl *= g[j]; }
     }
     w *= w_static;
-    if (a.evt_spline_w && e < a.n_events) { a.evt_spline_w[e] = w_spl; a.evt_total_w[e] = w; }
-    if (w > 0.f && bin >= 0 && !a.weights_only) {
+    if (e < a.n_events) {
+      if (F64) { if (a.evt_spline_d) { a.evt_spline_d[e] = w_spl; a.evt_total_d[e] = w; } }
+      else if (a.evt_spline_w) { a.evt_spline_w[e] = static_cast<float>(w_spl); a.evt_total_w[e] = static_cast<float>(w); }
+    }
+    if (w > R(0) && bin >= 0 && !a.weights_only) {
       if (smem_hist) {
         atomicAdd(s_hist + bin, static_cast<double>(w));
         if (w2_live) atomicAdd(s_w2 + bin, static_cast<double>(w * w));
@@ -124,19 +164,23 @@ __global__ void __launch_bounds__(256) binned_fill_kernel(const __grid_constant_
 }
 
 cudaError_t launch_binned_eval(const FillArgs& a, int grid, cudaStream_t s) {
-  binned_eval_kernel<<<grid, 256, (a.step.bytes + 15) & ~15, s>>>(a);
+  if (a.real_f64) binned_eval_kernel_f64<<<grid, 256, (a.step.bytes + 15) & ~15, s>>>(a);
+  else binned_eval_kernel<<<grid, 256, (a.step.bytes + 15) & ~15, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_binned_fill(const FillArgs& a, int grid, int smem, cudaStream_t s) {
-  binned_fill_kernel<<<grid, 256, smem, s>>>(a);
+  if (a.real_f64) binned_fill_kernel<true><<<grid, 256, smem, s>>>(a);
+  else binned_fill_kernel<false><<<grid, 256, smem, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t binned_fill_set_smem(int smem) {
   const int cap = smem > 48 * 1024 ? smem : 48 * 1024;
-  return cudaFuncSetAttribute(binned_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  cudaError_t e = cudaFuncSetAttribute(binned_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(binned_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
 }
 cudaError_t binned_fill_occupancy(int smem, int* bps) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel, 256, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel<true>, 256, smem);
 }
 
 }  // namespace m3b
@@ -144,12 +188,12 @@ cudaError_t binned_fill_occupancy(int smem, int* bps) {
 // ------------------------------------------------------------------------------------------------
 // host: uploads
 // ------------------------------------------------------------------------------------------------
-extern "C" {
-
-M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t max_knots, const float* knot_x,
+template <class R>
+static int upload_binned_impl(m3b_handle* h, int32_t n_params, int32_t max_knots, const R* knot_x,
                                       const int16_t* n_pts, int64_t n_slots, const int32_t* uniquesplinevec_Monolith,
                                       const int32_t* coeffindexvec, int64_t n_unique, const int32_t* uniquecoeffindices,
-                                      int64_t n_coeff, const float* manycoeff_arr, const float* xcoeff_arr) {
+                                      int64_t n_coeff, const R* manycoeff_arr, const R* xcoeff_arr) {
+  constexpr bool F64 = std::is_same<R, double>::value;
   REQUIRE(h, M3B_ERR_INVALID, "null handle");
   REQUIRE(!h->splines_open && !h->splines_done && !h->binned, M3B_ERR_STATE, "m3b_upload_binned_splines: a spline handler is already uploaded");
   REQUIRE(n_params > 0 && n_params <= kMaxParams && max_knots >= 2 && knot_x && n_pts, M3B_ERR_INVALID, "m3b_upload_binned_splines: bad parameter layout");
@@ -157,7 +201,8 @@ M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t m
   REQUIRE(n_unique >= 0 && (n_unique == 0 || (uniquecoeffindices && manycoeff_arr && xcoeff_arr)), M3B_ERR_INVALID, "m3b_upload_binned_splines: null coefficient arrays");
   CK(cudaSetDevice(h->device));
   h->P = n_params; h->Kmax = max_knots;
-  h->coeff_x.assign(knot_x, knot_x + static_cast<size_t>(n_params) * max_knots);
+  if (F64) { h->coeff_x_d.assign(knot_x, knot_x + static_cast<size_t>(n_params) * max_knots); h->f64 = true; }
+  else h->coeff_x.assign(knot_x, knot_x + static_cast<size_t>(n_params) * max_knots);
   h->n_pts.assign(n_pts, n_pts + n_params);
   h->nseg.resize(n_params);
   for (int p = 0; p < n_params; ++p) {
@@ -189,8 +234,9 @@ M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t m
   const int64_t n_act_pad = out_base[n_params], n_coef_dev = coef_base[n_params];
   h->b_slot2compact.assign(static_cast<size_t>(n_slots), -1);
   h->b_compact2slot.assign(static_cast<size_t>(n_act_pad), -1);
-  std::vector<float4> coef(static_cast<size_t>(n_coef_dev), make_float4(1.f, 0.f, 0.f, 0.f));
-  std::vector<float> xs(static_cast<size_t>(n_coef_dev), 0.f);
+  std::vector<R> coef(static_cast<size_t>(n_coef_dev) * 4, R(0));       // {y,b,c,d} per element; padding = the constant 1
+  for (int64_t i = 0; i < n_coef_dev; ++i) coef[4 * i] = R(1);
+  std::vector<R> xs(static_cast<size_t>(n_coef_dev), R(0));
   std::vector<int64_t> fill(n_params, 0);
   for (int64_t k = 0; k < n_unique; ++k) {
     const int32_t s = uniquecoeffindices[k];
@@ -199,9 +245,9 @@ M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t m
     REQUIRE(h->b_slot2compact[s] < 0, M3B_ERR_INVALID, "m3b_upload_binned_splines: slot listed twice in uniquecoeffindices");
     h->b_slot2compact[s] = static_cast<int32_t>(out_base[p] + j);
     h->b_compact2slot[out_base[p] + j] = s;
-    const float4* src = reinterpret_cast<const float4*>(manycoeff_arr) + coeffindexvec[s];
+    const R* src = manycoeff_arr + 4 * static_cast<int64_t>(coeffindexvec[s]);
     for (int g = 0; g < h->nseg[p]; ++g) {
-      coef[coef_base[p] + g * npad[p] + j] = src[g];
+      for (int q = 0; q < 4; ++q) coef[4 * (coef_base[p] + g * npad[p] + j) + q] = src[4 * g + q];
       xs[coef_base[p] + g * npad[p] + j] = xcoeff_arr[coeffindexvec[s] + g];
     }
   }
@@ -209,15 +255,42 @@ M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t m
   for (int p = 0; p < n_params; ++p)
     for (int64_t k0 = 0; k0 < npad[p]; k0 += kBTileSplines)
       tiles.push_back(BTile{coef_base[p], static_cast<int32_t>(npad[p]), p, static_cast<int32_t>(k0), static_cast<int32_t>(out_base[p] + k0)});
-  CK(dev_upload(h, &h->d_bcoef, coef));
-  CK(dev_upload(h, &h->d_bx, xs));
+  if (F64) {
+    CK(dev_upload(h, &h->d_bcoef_d, reinterpret_cast<const std::vector<double>&>(coef)));
+    CK(dev_upload(h, &h->d_bx_d, reinterpret_cast<const std::vector<double>&>(xs)));
+    CK(dev_alloc(h, &h->d_bw_d, static_cast<size_t>(n_act_pad)));
+  } else {
+    float4* dc = nullptr;
+    CK(dev_alloc(h, &dc, static_cast<size_t>(n_coef_dev)));
+    CK(cudaMemcpy(dc, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
+    h->d_bcoef = dc;
+    CK(dev_upload(h, &h->d_bx, reinterpret_cast<const std::vector<float>&>(xs)));
+    CK(dev_alloc(h, &h->d_bw, static_cast<size_t>(n_act_pad)));
+  }
   CK(dev_upload(h, &h->d_btiles, tiles));
-  CK(dev_alloc(h, &h->d_bw, static_cast<size_t>(n_act_pad)));
   h->n_btiles = static_cast<int32_t>(tiles.size());
   h->b_n_slots = n_slots; h->b_n_act = n_unique; h->b_n_act_pad = n_act_pad;
   h->binned = true;
   h->launch_ready = false;
   return M3B_OK;
+}
+
+
+extern "C" {
+
+M3B_API int m3b_upload_binned_splines(m3b_handle* h, int32_t n_params, int32_t max_knots, const float* knot_x,
+                                      const int16_t* n_pts, int64_t n_slots, const int32_t* uniquesplinevec_Monolith,
+                                      const int32_t* coeffindexvec, int64_t n_unique, const int32_t* uniquecoeffindices,
+                                      int64_t n_coeff, const float* manycoeff_arr, const float* xcoeff_arr) {
+  return upload_binned_impl<float>(h, n_params, max_knots, knot_x, n_pts, n_slots, uniquesplinevec_Monolith, coeffindexvec, n_unique,
+                                   uniquecoeffindices, n_coeff, manycoeff_arr, xcoeff_arr);
+}
+M3B_API int m3b_upload_binned_splines_f64(m3b_handle* h, int32_t n_params, int32_t max_knots, const double* knot_x,
+                                          const int16_t* n_pts, int64_t n_slots, const int32_t* uniquesplinevec_Monolith,
+                                          const int32_t* coeffindexvec, int64_t n_unique, const int32_t* uniquecoeffindices,
+                                          int64_t n_coeff, const double* manycoeff_arr, const double* xcoeff_arr) {
+  return upload_binned_impl<double>(h, n_params, max_knots, knot_x, n_pts, n_slots, uniquesplinevec_Monolith, coeffindexvec, n_unique,
+                                    uniquecoeffindices, n_coeff, manycoeff_arr, xcoeff_arr);
 }
 
 M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, const uint32_t* n_per_event,
@@ -260,6 +333,24 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
     }
     off += n_per_event[e];
   }
+  if (h->f64) {
+    // default build: osc / static weights and the per-event outputs are M3::float_t = double.  Until the caller
+    // supplies doubles (m3b_upload_event_weights_f64 / m3b_upload_osc_f64) the float uploads are widened (exact).
+    if (h->d_static && !h->d_static_d) {
+      std::vector<float> f(static_cast<size_t>(h->e_pad));
+      CK(cudaMemcpy(f.data(), h->d_static, sizeof(float) * f.size(), cudaMemcpyDeviceToHost));
+      std::vector<double> dd(f.begin(), f.end());
+      CK(dev_upload(h, &h->d_static_d, dd));
+    }
+    if (h->use_osc && !h->d_osc_d) {
+      std::vector<double> ones(static_cast<size_t>(h->n_osc), 1.0);
+      CK(dev_upload(h, &h->d_osc_d, ones));
+    }
+    if ((h->cfg.flags & M3B_FLAG_KEEP_EVENT_WEIGHTS) && !h->d_evt_spline_d) {
+      CK(dev_alloc(h, &h->d_evt_spline_d, static_cast<size_t>(h->e_pad)));
+      CK(dev_alloc(h, &h->d_evt_total_d, static_cast<size_t>(h->e_pad)));
+    }
+  }
   CK(dev_upload(h, &h->d_ell, ell));
   CK(dev_upload(h, &h->d_wtiles, wt));
   h->n_wtiles = n_wt;
@@ -268,10 +359,54 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
   return M3B_OK;
 }
 
+// ---- default (double) build: inputs and mirrors in M3::float_t = double
+M3B_API int m3b_upload_event_weights_f64(m3b_handle* h, int64_t n_events, const double* static_w) {
+  REQUIRE(h && static_w, M3B_ERR_INVALID, "m3b_upload_event_weights_f64: null argument");
+  REQUIRE(h->f64, M3B_ERR_STATE, "m3b_upload_event_weights_f64: the handle does not run the double build (m3b_upload_binned_splines_f64)");
+  REQUIRE(h->n_events > 0 && n_events == h->n_events, M3B_ERR_STATE, "m3b_upload_event_weights_f64: upload the events first (same count)");
+  CK(cudaSetDevice(h->device));
+  std::vector<double> sw(static_cast<size_t>(h->e_pad), 1.0);
+  std::copy(static_w, static_w + n_events, sw.begin());
+  if (!h->d_static_d) CK(dev_alloc(h, &h->d_static_d, sw.size()));
+  CK(cudaMemcpy(h->d_static_d, sw.data(), sizeof(double) * sw.size(), cudaMemcpyHostToDevice));
+  return M3B_OK;
+}
+M3B_API int m3b_upload_osc_f64(m3b_handle* h, const double* osc_w, int64_t n) {
+  REQUIRE(h && osc_w, M3B_ERR_INVALID, "m3b_upload_osc_f64: null argument");
+  REQUIRE(h->f64, M3B_ERR_STATE, "m3b_upload_osc_f64: the handle does not run the double build");
+  REQUIRE(h->use_osc && n == h->n_osc, M3B_ERR_INVALID, "m3b_upload_osc_f64: length differs from the oscillation-weight array's");
+  CK(cudaSetDevice(h->device));
+  if (!h->d_osc_d) CK(dev_alloc(h, &h->d_osc_d, static_cast<size_t>(n)));
+  CK(cudaMemcpyAsync(h->d_osc_d, osc_w, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  return M3B_OK;
+}
+M3B_API int m3b_read_binned_weights_f64(m3b_handle* h, double* weightvec_Monolith) {
+  REQUIRE(h && weightvec_Monolith, M3B_ERR_INVALID, "m3b_read_binned_weights_f64: null argument");
+  REQUIRE(h->binned && h->f64 && h->steps > 0, M3B_ERR_STATE, "m3b_read_binned_weights_f64: no double-build binned step yet");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<double> bw(static_cast<size_t>(h->b_n_act_pad));
+  CK(cudaMemcpy(bw.data(), h->d_bw_d, sizeof(double) * bw.size(), cudaMemcpyDeviceToHost));
+  for (int64_t s = 0; s < h->b_n_slots; ++s) weightvec_Monolith[s] = 1.0;
+  for (int64_t c = 0; c < h->b_n_act_pad; ++c)
+    if (h->b_compact2slot[c] >= 0) weightvec_Monolith[h->b_compact2slot[c]] = bw[c];
+  return M3B_OK;
+}
+M3B_API int m3b_read_event_weights_f64(m3b_handle* h, double* spline_w, double* total_w) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->f64 && h->steps > 0 && h->d_evt_spline_d, M3B_ERR_STATE,
+          "m3b_read_event_weights_f64: needs the double build, M3B_FLAG_KEEP_EVENT_WEIGHTS and a step");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (spline_w) CK(cudaMemcpy(spline_w, h->d_evt_spline_d, sizeof(double) * h->n_events, cudaMemcpyDeviceToHost));
+  if (total_w) CK(cudaMemcpy(total_w, h->d_evt_total_d, sizeof(double) * h->n_events, cudaMemcpyDeviceToHost));
+  return M3B_OK;
+}
+
 // BinnedSplineHandler::weightvec_Monolith as the host sees it (retPointer targets): 1.0 for flat slots
 M3B_API int m3b_read_binned_weights(m3b_handle* h, float* weightvec_Monolith) {
   REQUIRE(h && weightvec_Monolith, M3B_ERR_INVALID, "m3b_read_binned_weights: null argument");
-  REQUIRE(h->binned && h->steps > 0, M3B_ERR_STATE, "m3b_read_binned_weights: no binned step yet");
+  REQUIRE(h->binned && !h->f64 && h->steps > 0, M3B_ERR_STATE, "m3b_read_binned_weights: no float-build binned step yet");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   std::vector<float> bw(static_cast<size_t>(h->b_n_act_pad));

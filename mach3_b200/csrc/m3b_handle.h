@@ -134,6 +134,11 @@ struct m3b_handle {
 
   // ---- BinnedSplineHandler path (m3b_binned.cu)
   bool binned = false;
+  bool f64 = false;                         // binned path in the reference's default build (M3::float_t = double)
+  std::vector<double> coeff_x_d;            // knots as the default build holds them
+  std::vector<double> spline_pars_last;     // the un-narrowed parameter values of the step being enqueued
+  double *d_bcoef_d = nullptr, *d_bx_d = nullptr, *d_bw_d = nullptr, *d_osc_d = nullptr, *d_static_d = nullptr,
+         *d_evt_spline_d = nullptr, *d_evt_total_d = nullptr;
   int64_t b_n_slots = 0, b_n_act = 0, b_n_act_pad = 0, n_wtiles = 0;
   int32_t n_btiles = 0;
   std::vector<int32_t> b_slot2compact, b_compact2slot;

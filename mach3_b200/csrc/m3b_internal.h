@@ -39,10 +39,11 @@ struct StepLayout {
   int32_t P, Nn;
   int32_t off_seg, off_dx, off_val, off_norm, bytes;
   int32_t n_sigs_x, max_nc, max_nl, off_rowx, off_dxx, off_lvx;
+  int32_t off_val_d, off_norm_d;   // f64 copies of val[P] / norm[Nn] (the reference's default build, M3::float_t = double)
 };
 constexpr int kMaxExpandedStepBytes = 16384;
 constexpr int kStepInlineMax = 3072;      // kernel parameters stay below the classic 4 KB limit
-inline StepLayout make_step_layout(int P, int Nn, int n_sigs, int max_nc, int max_nl) {
+inline StepLayout make_step_layout(int P, int Nn, int n_sigs, int max_nc, int max_nl, bool f64 = false) {
   StepLayout L;
   L.P = P; L.Nn = Nn;
   L.off_seg = 0;
@@ -59,6 +60,12 @@ inline StepLayout make_step_layout(int P, int Nn, int n_sigs, int max_nc, int ma
     L.off_dxx = L.off_rowx + 4 * n_sigs * max_nc;
     L.off_lvx = L.off_dxx + 4 * n_sigs * max_nc;
     end = L.off_lvx + 4 * n_sigs * max_nl;
+  }
+  L.off_val_d = L.off_norm_d = 0;
+  if (f64) {
+    L.off_val_d = (end + 7) & ~7;
+    L.off_norm_d = L.off_val_d + 8 * P;
+    end = L.off_norm_d + 8 * Nn;
   }
   L.bytes = (end + 15) & ~15;
   if (L.bytes == 0) L.bytes = 16;
@@ -132,6 +139,13 @@ struct FillArgs {
   // BinnedSplineHandler path
   const BTile* btiles; int32_t n_btiles;
   const float4* bcoef; const float* bx; float* bw;
+  // ... in the reference's default build (M3::float_t = double): coefficients, weights, osc/static weights and the
+  // per-event product are double
+  int32_t real_f64;
+  const double* bcoef_d;       // 4 doubles {y,b,c,d} per element
+  const double* bx_d; double* bw_d;
+  const double* osc_d; const double* static_d;
+  double* evt_spline_d; double* evt_total_d;
   const int32_t* ell; const WTile* wtiles; int64_t n_wtiles;
   // optional per-block timeline (m3b_block_trace): 8 x u64 globaltimer ns per block
   unsigned long long* trace;

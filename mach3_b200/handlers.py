@@ -85,10 +85,10 @@ class BinnedSplineHandler:
     to a :class:`SampleHandlerFD`: its evaluation runs inside ``Reweight()``; ``weightvec_Monolith`` is a
     lazy host mirror."""
 
-    def __init__(self, spl, handle):
+    def __init__(self, spl, handle, f64=False):
         self.handle = handle
         self.n_params = int(spl["n_params"])
-        handle.upload_binned_splines(spl)
+        handle.upload_binned_splines(spl, f64=f64)
 
     def GetName(self):
         return "BinnedSplineHandler"
@@ -157,8 +157,10 @@ class SampleHandlerFD:
                                        chunk_events=chunk_events)
         return self.SplineHandler
 
-    def SetupBinnedSplines(self, spl):
-        self.SplineHandler = BinnedSplineHandler(spl, self.handle)
+    def SetupBinnedSplines(self, spl, f64=False):
+        """f64: the reference's default build (M3::float_t = double); oscillation / static weights are then doubles."""
+        self.SplineHandler = BinnedSplineHandler(spl, self.handle, f64=f64)
+        self._f64 = bool(f64)
         return self.SplineHandler
 
     def SetBinnedSplinePointers(self, n_per_event, spline_index):
@@ -186,6 +188,12 @@ class SampleHandlerFD:
 
     # -- reference API -------------------------------------------------------------------------
     def Reweight(self):
+        if getattr(self, "_f64", False):
+            if self._osc_dirty and self._osc_w is not None:
+                self.handle.upload_osc_f64(self._osc_w)
+            self.handle.step(self._spline_pars, self._norm_pars, None, mode="fused" if self._fused else "fill")
+            self._osc_dirty = False
+            return
         osc = self._osc_w if self._osc_dirty else None
         self.handle.step(self._spline_pars, self._norm_pars, osc, mode="fused" if self._fused else "fill")
         self._osc_dirty = False
@@ -243,17 +251,27 @@ def build_from_workload(w, e0=0, e1=None, with_osc=True, update_w2=False, test_s
     return sh, dict(typ=typ, npts=npts, coeff_x=cx, spl=spl, ev=ev, pars=pars, norm=norm, osc=osc)
 
 
-def build_binned_from_workload(w, update_w2=True, test_statistic=None, device=0, keep_event_weights=False, fused_llh=True):
-    """B200 SampleHandlerFD + BinnedSplineHandler wired on a synthetic binned-spline workload."""
+def build_binned_from_workload(w, update_w2=True, test_statistic=None, device=0, keep_event_weights=False, fused_llh=True,
+                               f64=False):
+    """B200 SampleHandlerFD + BinnedSplineHandler wired on a synthetic binned-spline workload
+    (f64: the reference's default build, M3::float_t = double)."""
     from .synth import binned as B
-    spl = B.make_binned_splines(w)
-    ev = B.make_binned_events(w)
+    spl = B.make_binned_splines(w, f64=f64)
+    ev = B.make_binned_events(w, f64=f64)
     sh = SampleHandlerFD(B.bin_edges(w), w.test_statistic if test_statistic is None else test_statistic, update_w2, device,
                          0, keep_event_weights, fused_llh)
-    sh.SetupBinnedSplines(spl)
+    sh.SetupBinnedSplines(spl, f64=f64)
     pars = np.zeros(w.n_systs, np.float64)
     norm = np.ones(w.n_norm_params, np.float64)
-    osc = B.make_osc(w, 0)
+    osc = B.make_osc(w, 0, f64=f64)
+    if f64:
+        # the float entry points only fix the shapes here; the double arrays follow
+        sh.handle.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, norm.size, True, None, 0, None)
+        sh._norm_pars, sh._osc_w, sh._osc_dirty = norm, osc, True
+        sh.SetBinnedSplinePointers(ev["n_per_event"], ev["spline_index"])
+        sh.handle.upload_event_weights_f64(ev["static_w"])
+        sh.SetSplinePointers(pars)
+        return sh, dict(spl=spl, ev=ev, pars=pars, norm=norm, osc=osc)
     sh.SetupEvents(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, norm, osc, None, ev["static_w"])
     sh.SetBinnedSplinePointers(ev["n_per_event"], ev["spline_index"])
     sh.SetSplinePointers(pars)

@@ -21,6 +21,8 @@ EXPORTS = (
     "m3b_create", "m3b_destroy", "m3b_last_error", "m3b_abi_version", "m3b_set_stream",
     "m3b_splines_begin", "m3b_splines_append", "m3b_splines_end", "m3b_upload_spline_monolith",
     "m3b_upload_binned_splines", "m3b_upload_event_binned_splines", "m3b_read_binned_weights",
+    "m3b_upload_binned_splines_f64", "m3b_upload_event_weights_f64", "m3b_upload_osc_f64", "m3b_read_binned_weights_f64",
+    "m3b_read_event_weights_f64",
     "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer",
     "m3b_set_test_statistic", "m3b_reset_w2",
     "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
@@ -159,22 +161,39 @@ class Handle:
             _p(a[0]), _p(a[1]), _p(a[2]), C.c_uint32(a[3].size // 4), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6])))
 
     # ---- binning / events / data
-    def upload_binned_splines(self, spl):
-        """`spl`: the reference's BinnedSplineHandler arrays (see mach3_b200.synth.binned.make_binned_splines)."""
-        a = [_c(spl["knot_x"], np.float32), _c(spl["n_pts"], np.int16), _c(spl["uniquesplinevec_Monolith"], np.int32),
-             _c(spl["coeffindexvec"], np.int32), _c(spl["uniquecoeffindices"], np.int32), _c(spl["manycoeff_arr"], np.float32),
-             _c(spl["xcoeff_arr"], np.float32)]
-        self._ck(self.L.m3b_upload_binned_splines(self.h, C.c_int32(int(spl["n_params"])), C.c_int32(int(spl["max_knots"])),
-                                                  _p(a[0]), _p(a[1]), C.c_int64(int(spl["n_slots"])), _p(a[2]), _p(a[3]),
-                                                  C.c_int64(a[4].size), _p(a[4]), C.c_int64(a[6].size), _p(a[5]), _p(a[6])))
+    def upload_binned_splines(self, spl, f64=False):
+        """`spl`: the reference's BinnedSplineHandler arrays (see mach3_b200.synth.binned.make_binned_splines).
+        f64=True: the reference's default build (M3::float_t = double)."""
+        ft = np.float64 if f64 else np.float32
+        a = [_c(spl["knot_x"], ft), _c(spl["n_pts"], np.int16), _c(spl["uniquesplinevec_Monolith"], np.int32),
+             _c(spl["coeffindexvec"], np.int32), _c(spl["uniquecoeffindices"], np.int32), _c(spl["manycoeff_arr"], ft),
+             _c(spl["xcoeff_arr"], ft)]
+        fn = self.L.m3b_upload_binned_splines_f64 if f64 else self.L.m3b_upload_binned_splines
+        self._ck(fn(self.h, C.c_int32(int(spl["n_params"])), C.c_int32(int(spl["max_knots"])),
+                    _p(a[0]), _p(a[1]), C.c_int64(int(spl["n_slots"])), _p(a[2]), _p(a[3]),
+                    C.c_int64(a[4].size), _p(a[4]), C.c_int64(a[6].size), _p(a[5]), _p(a[6])))
         self.n_params = int(spl["n_params"])
         self.n_slots = int(spl["n_slots"])
+        self.f64 = bool(f64)
+
+    def upload_event_weights_f64(self, static_w):
+        sw = _c(static_w, np.float64)
+        self._ck(self.L.m3b_upload_event_weights_f64(self.h, C.c_int64(sw.size), _p(sw)))
+
+    def upload_osc_f64(self, osc_w):
+        o = _c(osc_w, np.float64)
+        self._keep_osc = o
+        self._ck(self.L.m3b_upload_osc_f64(self.h, _p(o), C.c_int64(o.size)))
 
     def upload_event_binned_splines(self, n_per_event, spline_index):
         n, si = _c(n_per_event, np.uint32), _c(spline_index, np.int32)
         self._ck(self.L.m3b_upload_event_binned_splines(self.h, C.c_int64(n.size), _p(n), _p(si)))
 
     def read_binned_weights(self):
+        if getattr(self, "f64", False):
+            out = np.zeros(self.n_slots, np.float64)
+            self._ck(self.L.m3b_read_binned_weights_f64(self.h, _p(out)))
+            return out
         out = np.zeros(self.n_slots, np.float32)
         self._ck(self.L.m3b_read_binned_weights(self.h, _p(out)))
         return out
@@ -287,6 +306,10 @@ class Handle:
         return mc, w2
 
     def read_event_weights(self):
+        if getattr(self, "f64", False):
+            sw, tw = np.zeros(self.n_events, np.float64), np.zeros(self.n_events, np.float64)
+            self._ck(self.L.m3b_read_event_weights_f64(self.h, _p(sw), _p(tw)))
+            return sw, tw
         sw, tw = np.zeros(self.n_events, np.float32), np.zeros(self.n_events, np.float32)
         self._ck(self.L.m3b_read_event_weights(self.h, _p(sw), _p(tw)))
         return sw, tw

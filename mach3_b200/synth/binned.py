@@ -76,11 +76,12 @@ def _natural_spline_coeffs(x, y):
     return out
 
 
-def make_binned_splines(w: BinnedWorkload):
+def make_binned_splines(w: BinnedWorkload, f64=False):
     rng = np.random.default_rng(w.seed)
     P, G, K = w.n_systs, w.n_grid, w.n_knots
     x = np.linspace(-3.0, 3.0, K)
-    knot_x = np.tile(x.astype(np.float32), P)                       # SplineInfoArray[p].xPts
+    ft = np.float64 if f64 else np.float32                         # M3::float_t of the build
+    knot_x = np.tile(x.astype(ft), P)                               # SplineInfoArray[p].xPts
     n_pts = np.full(P, K, np.int16)
     active = rng.random(P * G) < w.fill
     uniquecoeffindices = np.nonzero(active)[0].astype(np.int32)
@@ -88,21 +89,21 @@ def make_binned_splines(w: BinnedWorkload):
     uniquesplinevec = np.repeat(np.arange(P, dtype=np.int32), G)
     coeffindexvec = np.zeros(P * G, np.int32)
     coeffindexvec[uniquecoeffindices] = np.arange(n_act, dtype=np.int32) * K
-    many = np.zeros((n_act, K, 4), np.float32)
+    many = np.zeros((n_act, K, 4), ft)
     CH = 1 << 20
     for c0 in range(0, n_act, CH):
         n = min(CH, n_act - c0)
         a = rng.uniform(-0.25, 0.25, (n, 1))
         b = rng.uniform(-0.12, 0.03, (n, 1))
         y = 1 + a * x + b * x * x            # dips below zero at the edges for some splines: exercises the clamp
-        many[c0:c0 + n] = _natural_spline_coeffs(x, y).astype(np.float32)
-    xcoeff = np.tile(x.astype(np.float32), n_act)
+        many[c0:c0 + n] = _natural_spline_coeffs(x, y).astype(ft)
+    xcoeff = np.tile(x.astype(ft), n_act)
     return dict(n_params=P, max_knots=K, knot_x=knot_x, n_pts=n_pts, n_slots=P * G, uniquesplinevec_Monolith=uniquesplinevec,
                 coeffindexvec=coeffindexvec, uniquecoeffindices=uniquecoeffindices, manycoeff_arr=many.reshape(-1),
                 xcoeff_arr=xcoeff)
 
 
-def make_binned_events(w: BinnedWorkload):
+def make_binned_events(w: BinnedWorkload, f64=False):
     rng = np.random.default_rng(w.seed + 1)
     E, P, G = w.n_events, w.n_systs, w.n_grid
     grid_bin = rng.integers(0, G, E)
@@ -128,7 +129,7 @@ def make_binned_events(w: BinnedWorkload):
     kin[0] = rng.gamma(3.0, 0.3, E)
     kin[1] = rng.uniform(0, np.pi, E)
     norm_idx = rng.integers(0, w.n_norm_params, (E, w.n_norm_per_event)).astype(np.int16)
-    static_w = rng.uniform(0.5, 1.5, E).astype(np.float32)
+    static_w = rng.uniform(0.5, 1.5, E).astype(np.float64 if f64 else np.float32)
     return dict(sample_id=np.zeros(E, np.int32), kin=kin.reshape(-1), norm_idx=norm_idx.reshape(-1), static_w=static_w,
                 n_per_event=n_per, spline_index=spline_index)
 
@@ -137,9 +138,9 @@ def bin_edges(w: BinnedWorkload):
     return [[np.linspace(0.0, 3.0, w.nbins_x + 1), np.linspace(0.0, np.pi, w.nbins_y + 1)]]
 
 
-def make_osc(w: BinnedWorkload, step=0):
+def make_osc(w: BinnedWorkload, step=0, f64=False):
     rng = np.random.default_rng(w.seed + 100 + step)
-    o = rng.random(w.n_events).astype(np.float32)
+    o = rng.random(w.n_events).astype(np.float64 if f64 else np.float32)
     o[rng.integers(0, w.n_events, max(1, w.n_events // 997))] = 0.0
     return o
 

@@ -29,6 +29,9 @@ def lib():
         L.m3o_sample_create.restype = C.c_void_p
         L.m3o_sample_create_ex.restype = C.c_void_p
         L.m3o_binned_create.restype = C.c_void_p
+        L.m3o_binnedd_create.restype = C.c_void_p
+        L.m3o_binnedd_weights.restype = C.c_void_p
+        L.m3o_binnedd_segments.restype = C.c_void_p
         L.m3o_binned_weights.restype = C.c_void_p
         L.m3o_binned_segments.restype = C.c_void_p
         for n in ("m3o_segments", "m3o_param_values", "m3o_total_weights", "m3o_spline_weights", "m3o_tf1_weights",
@@ -167,6 +170,45 @@ class BinnedSplineHandler:
             pass
 
 
+class BinnedSplineHandlerD:
+    """The same in the reference's DEFAULT build (M3::float_t = double)."""
+
+    def __init__(self, spl):
+        k = dict(knot_x=np.ascontiguousarray(spl["knot_x"], np.float64), n_pts=np.ascontiguousarray(spl["n_pts"], np.int16),
+                 usv=np.ascontiguousarray(spl["uniquesplinevec_Monolith"], np.int32),
+                 civ=np.ascontiguousarray(spl["coeffindexvec"], np.int32),
+                 uci=np.ascontiguousarray(spl["uniquecoeffindices"], np.int32),
+                 many=np.ascontiguousarray(spl["manycoeff_arr"], np.float64), xc=np.ascontiguousarray(spl["xcoeff_arr"], np.float64))
+        self._keep = k
+        self.n_params = int(spl["n_params"])
+        self.n_slots = int(spl["n_slots"])
+        self.h = C.c_void_p(lib().m3o_binnedd_create(C.c_int(self.n_params), C.c_int(int(spl["max_knots"])), _p(k["knot_x"]),
+                                                     _p(k["n_pts"]), C.c_int64(self.n_slots), _p(k["usv"]), _p(k["civ"]),
+                                                     C.c_int64(k["uci"].size), _p(k["uci"]), _p(k["many"]), _p(k["xc"])))
+        self.pars = np.zeros(self.n_params, np.float64)
+        lib().m3o_binnedd_set_pointers(self.h, _p(self.pars))
+
+    def set_params(self, values):
+        self.pars[:] = values
+
+    def Evaluate(self):
+        lib().m3o_binnedd_evaluate(self.h)
+
+    @property
+    def weights(self):
+        return _view(lib().m3o_binnedd_weights(self.h), self.n_slots, np.float64)
+
+    @property
+    def segments(self):
+        return _view(lib().m3o_binnedd_segments(self.h), self.n_params, np.int16)
+
+    def __del__(self):
+        try:
+            lib().m3o_binnedd_destroy(self.h)
+        except Exception:
+            pass
+
+
 class SampleHandlerFD:
     """Oracle mirror of the reference's ``SampleHandlerFD`` reweight / likelihood path."""
 
@@ -220,8 +262,25 @@ class SampleHandlerFD:
                                            _p(k[2]), _p(self.norm_vals), _p(self.osc_w), None, binned.h, _p(k[4]), _p(k[5]),
                                            _p(k[3]))
 
+    def set_events_binned_d(self, sample_id, kin, norm_idx, n_norm_per_event, norm_vals, osc_w, binned: BinnedSplineHandlerD,
+                            n_per_event, spline_index, static_w):
+        """Default build: osc / static weights are double arrays."""
+        self.norm_vals = None if norm_vals is None else np.ascontiguousarray(norm_vals, np.float64)
+        self.osc_w = None if osc_w is None else np.ascontiguousarray(osc_w, np.float64)
+        k = [np.ascontiguousarray(sample_id, np.int32), np.ascontiguousarray(kin, np.float64),
+             None if norm_idx is None else np.ascontiguousarray(norm_idx, np.int16),
+             None if static_w is None else np.ascontiguousarray(static_w, np.float64),
+             np.ascontiguousarray(n_per_event, np.uint32), np.ascontiguousarray(spline_index, np.int32), binned]
+        self._keep = k
+        self._double_build = True
+        lib().m3o_sample_set_events_binned_d(self.h, _p(k[0]), _p(k[1]), C.c_int(n_norm_per_event if k[2] is not None else 0),
+                                             _p(k[2]), _p(self.norm_vals), _p(self.osc_w), binned.h, _p(k[4]), _p(k[5]), _p(k[3]))
+
     def Reweight(self):
-        lib().m3o_reweight(self.h)
+        if getattr(self, "_double_build", False):
+            lib().m3o_reweight_d(self.h)
+        else:
+            lib().m3o_reweight(self.h)
 
     def FillOnly(self):
         lib().m3o_fill_only(self.h)
@@ -258,6 +317,10 @@ class SampleHandlerFD:
         return out
 
     def event_weights(self):
+        if getattr(self, "_double_build", False):
+            out = np.zeros(self.n_events, np.float64)
+            lib().m3o_event_weights_d(self.h, _p(out))
+            return out
         out = np.zeros(self.n_events, np.float32)
         lib().m3o_event_weights(self.h, _p(out))
         return out
@@ -310,15 +373,21 @@ def build_from_workload(w, e0=0, e1=None, with_osc=True, update_w2=False, test_s
     return mono, sh, dict(typ=typ, npts=npts, coeff_x=cx, spl=spl, ev=ev)
 
 
-def build_binned_from_workload(w, update_w2=True, test_statistic=None, with_osc=True):
-    """Oracle BinnedSplineHandler + SampleHandlerFD wired on a synthetic binned-spline workload."""
+def build_binned_from_workload(w, update_w2=True, test_statistic=None, with_osc=True, f64=False):
+    """Oracle BinnedSplineHandler + SampleHandlerFD wired on a synthetic binned-spline workload
+    (f64: the reference's default build)."""
     from mach3_b200.synth import binned as B
-    spl = B.make_binned_splines(w)
-    ev = B.make_binned_events(w)
-    bsh = BinnedSplineHandler(spl)
+    spl = B.make_binned_splines(w, f64=f64)
+    ev = B.make_binned_events(w, f64=f64)
     sh = SampleHandlerFD(w.n_events, B.bin_edges(w), w.test_statistic if test_statistic is None else test_statistic, update_w2)
-    osc = B.make_osc(w, 0) if with_osc else None
+    osc = B.make_osc(w, 0, f64=f64) if with_osc else None
     norm_vals = np.ones(w.n_norm_params, np.float64)
-    sh.set_events_binned(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, norm_vals, osc, bsh,
-                         ev["n_per_event"], ev["spline_index"], ev["static_w"])
+    if f64:
+        bsh = BinnedSplineHandlerD(spl)
+        sh.set_events_binned_d(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, norm_vals, osc, bsh,
+                               ev["n_per_event"], ev["spline_index"], ev["static_w"])
+    else:
+        bsh = BinnedSplineHandler(spl)
+        sh.set_events_binned(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, norm_vals, osc, bsh,
+                             ev["n_per_event"], ev["spline_index"], ev["static_w"])
     return bsh, sh, dict(spl=spl, ev=ev)

@@ -439,6 +439,96 @@ M3O_API void m3o_binned_evaluate(BinnedSplineHandler* b) {
 M3O_API const float* m3o_binned_weights(const BinnedSplineHandler* b) { return b->weightvec_Monolith; }
 M3O_API const short* m3o_binned_segments(const BinnedSplineHandler* b) { return b->base.SplineSegments; }
 
+
+/* ============================================================================================
+ * The binned-spline path in the reference's DEFAULT build (M3::float_t = double, Manager/Core.h:27-51):
+ * FastSplineInfo::xPts, the coefficient arrays, weightvec_Monolith, the oscillation/extra weights and
+ * CalcWeightTotal's product are double; FindSplineSegment still narrows the parameter to float
+ * (Splines/SplineBase.cpp:54) while CalcSplineWeights reads it un-narrowed (BinnedSplineHandler.cpp:327);
+ * M3::fmaf_t is std::fma.
+ * ========================================================================================== */
+typedef struct BinnedSplineHandlerD_ {
+  int nParams, max_knots;
+  const double* knot_x; const short* n_pts;
+  short* CurrSegment; short* SplineSegments; float* ParamValues;
+  const double* pars;
+  int64_t n_slots, n_unique;
+  const int* uniquesplinevec_Monolith; const int* coeffindexvec; const int* uniquecoeffindices;
+  const double* manycoeff_arr; const double* xcoeff_arr;
+  double* weightvec_Monolith;
+} BinnedSplineHandlerD;
+
+M3O_API BinnedSplineHandlerD* m3o_binnedd_create(int nParams, int max_knots, const double* knot_x, const short* n_pts,
+                                                 int64_t n_slots, const int* uniquesplinevec_Monolith, const int* coeffindexvec,
+                                                 int64_t n_unique, const int* uniquecoeffindices,
+                                                 const double* manycoeff_arr, const double* xcoeff_arr) {
+  BinnedSplineHandlerD* b = (BinnedSplineHandlerD*)calloc(1, sizeof(BinnedSplineHandlerD));
+  b->nParams = nParams; b->max_knots = max_knots; b->knot_x = knot_x; b->n_pts = n_pts;
+  b->CurrSegment = (short*)calloc((size_t)nParams, sizeof(short));
+  b->SplineSegments = (short*)calloc((size_t)nParams, sizeof(short));
+  b->ParamValues = (float*)calloc((size_t)nParams, sizeof(float));
+  b->n_slots = n_slots; b->n_unique = n_unique;
+  b->uniquesplinevec_Monolith = uniquesplinevec_Monolith; b->coeffindexvec = coeffindexvec; b->uniquecoeffindices = uniquecoeffindices;
+  b->manycoeff_arr = manycoeff_arr; b->xcoeff_arr = xcoeff_arr;
+  b->weightvec_Monolith = (double*)malloc(sizeof(double) * (size_t)(n_slots > 0 ? n_slots : 1));
+  for (int64_t i = 0; i < n_slots; ++i) b->weightvec_Monolith[i] = 1.0;
+  return b;
+}
+M3O_API void m3o_binnedd_destroy(BinnedSplineHandlerD* b) {
+  if (!b) return;
+  free(b->CurrSegment); free(b->SplineSegments); free(b->ParamValues); free(b->weightvec_Monolith); free(b);
+}
+M3O_API void m3o_binnedd_set_pointers(BinnedSplineHandlerD* b, const double* pars) { b->pars = pars; }
+
+/* SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-109) with xPts in double */
+static void find_spline_segment_d(BinnedSplineHandlerD* m) {
+  for (int i = 0; i < m->nParams; ++i) {
+    const short nPoints = m->n_pts[i];
+    const double* xArray = m->knot_x + (size_t)i * (size_t)m->max_knots;
+    const float xvar = (float)(m->pars[i]);                    /* :54 */
+    m->ParamValues[i] = xvar;
+    if (nPoints == 0) continue;
+    short segment = 0;
+    short kHigh = (short)(nPoints - 1);
+    const short PreviousSegment = m->CurrSegment[i];
+    if (xvar <= xArray[0]) segment = 0;
+    else if (xvar >= xArray[nPoints - 1]) segment = kHigh;
+    else if (xArray[PreviousSegment + 1] > xvar && xvar >= xArray[PreviousSegment]) segment = PreviousSegment;
+    else {
+      short kHalf = 0;
+      while (kHigh - segment > 1) {
+        kHalf = (short)((segment + kHigh) / 2);
+        if (xvar > xArray[kHalf]) segment = kHalf; else kHigh = kHalf;
+      }
+    }
+    if (segment >= nPoints - 1 && nPoints > 1) segment = (short)(nPoints - 2);
+    m->CurrSegment[i] = segment;
+    m->SplineSegments[i] = segment;
+  }
+}
+/* BinnedSplineHandler::Evaluate (Splines/BinnedSplineHandler.cpp:295-341), default build */
+M3O_API void m3o_binnedd_evaluate(BinnedSplineHandlerD* h) {
+  find_spline_segment_d(h);
+  const int64_t n = h->n_unique;
+  #pragma omp parallel for simd if (g_multithread)
+  for (int64_t iCoeff = 0; iCoeff < n; ++iCoeff) {
+    const int iSpline = h->uniquecoeffindices[iCoeff];
+    const short uniqueIndex = (short)h->uniquesplinevec_Monolith[iSpline];
+    const short currentsegment = (short)h->SplineSegments[uniqueIndex];
+    const int segCoeff = h->coeffindexvec[iSpline] + currentsegment;
+    const int coeffOffset = segCoeff * nCoeff;
+    const double y = h->manycoeff_arr[coeffOffset + 0], b = h->manycoeff_arr[coeffOffset + 1];
+    const double c = h->manycoeff_arr[coeffOffset + 2], d = h->manycoeff_arr[coeffOffset + 3];
+    const double xvar = h->pars[uniqueIndex];                                  /* :327 un-narrowed */
+    const double dx = xvar - h->xcoeff_arr[segCoeff];
+    double weight = fma(dx, fma(dx, fma(dx, d, c), b), y);
+    if (weight < 0) weight = 0.;
+    h->weightvec_Monolith[iSpline] = weight;
+  }
+}
+M3O_API const double* m3o_binnedd_weights(const BinnedSplineHandlerD* b) { return b->weightvec_Monolith; }
+M3O_API const short* m3o_binnedd_segments(const BinnedSplineHandlerD* b) { return b->SplineSegments; }
+
 /* ============================================================================================
  * Samples: EventInfo (Samples/FarDetectorCoreInfoStruct.h:82-126) + SampleHandlerFD state
  * ========================================================================================== */
@@ -464,6 +554,10 @@ typedef struct {
   int UpdateW2;      /* LikelihoodOptions:UpdateW2 (Samples/SampleHandlerFD.cpp:64) */
   SMonolith* SplineHandler;
   struct BinnedSplineHandler_* BinnedHandler;   /* the other SplineBase implementation (either/or) */
+  /* default build (M3::float_t = double) of the binned path: per-event pointer vectors in double */
+  struct BinnedSplineHandlerD_* BinnedHandlerD;
+  const double*** tw_d;   /* [event] -> std::vector<const M3::float_t*> total_weight_pointers */
+  int* n_tw_d;
 } SampleHandlerFD;
 
 
@@ -585,6 +679,7 @@ M3O_API void m3o_sample_destroy(SampleHandlerFD* s) {
     free(s->MCSamples[e].KinVar); free(s->MCSamples[e].NomBin);
   }
   free(s->MCSamples);
+  if (s->tw_d) { for (unsigned int e = 0; e < s->nEvents; ++e) free((void*)s->tw_d[e]); free((void*)s->tw_d); free(s->n_tw_d); }
   for (int i = 0; i < s->nSamples; ++i)
   {
     for (int d = 0; d < s->SampleBinning[i].nDim; ++d) { free(s->SampleBinning[i].BinEdges[d]); free(s->SampleBinning[i].BinLookup[d]); }
@@ -774,6 +869,80 @@ M3O_API void m3o_fill_only(SampleHandlerFD* s) {
   ResetHistograms(s);
   if (g_multithread) FillArray_MP(s); else FillArray(s);
   if (!s->UpdateW2) s->FirstTimeW2 = 0;
+}
+
+
+/* Default-build wiring: total_weight_pointers are const double* -- oscillation weight, the binned-spline weights
+ * (BinnedSplineHandler::retPointer), the extra weight, in that order (see m3o_sample_set_events_binned). */
+M3O_API void m3o_sample_set_events_binned_d(SampleHandlerFD* s, const int* sample_id, const double* kin,
+                                            int n_norm_per_event, const short* norm_idx, const double* norm_base,
+                                            const double* osc_base, struct BinnedSplineHandlerD_* binned,
+                                            const uint32_t* n_per_event, const int* spline_index, const double* static_w) {
+  m3o_sample_set_events(s, sample_id, kin, n_norm_per_event, norm_idx, norm_base, NULL, NULL, NULL, NULL);
+  s->BinnedHandlerD = binned;
+  s->tw_d = (const double***)calloc((size_t)s->nEvents, sizeof(double**));
+  s->n_tw_d = (int*)calloc((size_t)s->nEvents, sizeof(int));
+  uint64_t off = 0;
+  for (unsigned int e = 0; e < s->nEvents; ++e) {
+    const int n_b = (int)n_per_event[e];
+    const double** tw = (const double**)malloc(sizeof(double*) * (size_t)(n_b + 2));
+    int nt = 0;
+    if (osc_base) tw[nt++] = &osc_base[e];
+    for (int j = 0; j < n_b; ++j) tw[nt++] = &binned->weightvec_Monolith[spline_index[off + (uint64_t)j]];
+    if (static_w) tw[nt++] = &static_w[e];
+    s->tw_d[e] = tw; s->n_tw_d[e] = nt;
+    off += (uint64_t)n_b;
+  }
+}
+
+/* SampleHandlerFD::CalcWeightTotal (Samples/SampleHandlerFD.cpp:568-594) with M3::float_t = double */
+static inline double CalcWeightTotal_d(const SampleHandlerFD* s, unsigned int e, int simd) {
+  const EventInfo* MCEvent = &s->MCSamples[e];
+  double TotalWeight = 1.0;
+  if (simd) {
+    #pragma omp simd reduction(*:TotalWeight)
+    for (int iParam = 0; iParam < MCEvent->n_norm; ++iParam) TotalWeight *= (double)(*(MCEvent->norm_pointers[iParam]));
+    #pragma omp simd reduction(*:TotalWeight)
+    for (int iWeight = 0; iWeight < s->n_tw_d[e]; ++iWeight) TotalWeight *= *(s->tw_d[e][iWeight]);
+  } else {
+    for (int iParam = 0; iParam < MCEvent->n_norm; ++iParam) TotalWeight *= (double)(*(MCEvent->norm_pointers[iParam]));
+    for (int iWeight = 0; iWeight < s->n_tw_d[e]; ++iWeight) TotalWeight *= *(s->tw_d[e][iWeight]);
+  }
+  return TotalWeight;
+}
+
+/* SampleHandlerFD::Reweight, default build, binned splines */
+M3O_API void m3o_reweight_d(SampleHandlerFD* s) {
+  ResetHistograms(s);
+  if (s->BinnedHandlerD) m3o_binnedd_evaluate(s->BinnedHandlerD);
+  const int FirstTimeW2 = s->FirstTimeW2;
+  if (g_multithread) {
+    const int TotalBins = s->TotalBins;
+    double* MC = s->SampleHandlerFD_array; double* W2 = s->SampleHandlerFD_array_w2;
+    #pragma omp parallel for reduction(+:MC[:TotalBins], W2[:TotalBins])
+    for (unsigned int iEvent = 0; iEvent < s->nEvents; ++iEvent) {
+      const EventInfo* MCEvent = &s->MCSamples[iEvent];
+      const double totalweight = CalcWeightTotal_d(s, iEvent, 1);
+      if (totalweight <= 0.) continue;
+      const int GlobalBin = FindGlobalBin(s, MCEvent->NominalSample, MCEvent->KinVar, MCEvent->NomBin, MCEvent->n_dim);
+      if (GlobalBin > UnderOverFlowBin) { MC[GlobalBin] += totalweight; if (FirstTimeW2) W2[GlobalBin] += totalweight * totalweight; }
+    }
+  } else {
+    for (unsigned int iEvent = 0; iEvent < s->nEvents; ++iEvent) {
+      const EventInfo* MCEvent = &s->MCSamples[iEvent];
+      const double totalweight = CalcWeightTotal_d(s, iEvent, 0);
+      if (totalweight <= 0.) continue;
+      const int GlobalBin = FindGlobalBin(s, MCEvent->NominalSample, MCEvent->KinVar, MCEvent->NomBin, MCEvent->n_dim);
+      if (GlobalBin > UnderOverFlowBin) {
+        s->SampleHandlerFD_array[GlobalBin] += totalweight;
+        if (FirstTimeW2) s->SampleHandlerFD_array_w2[GlobalBin] += totalweight * totalweight;
+      }
+    }
+  }
+  if (!s->UpdateW2) s->FirstTimeW2 = 0;
+}
+M3O_API void m3o_event_weights_d(const SampleHandlerFD* s, double* out) {
+  for (unsigned int e = 0; e < s->nEvents; ++e) out[e] = CalcWeightTotal_d(s, e, 0);
 }
 
 /* SampleHandlerBase::GetPoissonLLH (Samples/SampleHandlerBase.cpp:17-31) */

@@ -76,3 +76,45 @@ def test_binned_rejects_inconsistent_input():
     with pytest.raises(lib.M3BError):       # events first
         h.upload_event_binned_splines(np.zeros(4, np.uint32), np.zeros(0, np.int32))
     h.close()
+
+
+def test_binned_spline_path_default_double_build(oracle_build):
+    """The reference's DEFAULT build (M3::float_t = double): double coefficients / weights / osc / static weights,
+    std::fma, the parameter read un-narrowed by the evaluation but narrowed to float by FindSplineSegment."""
+    w = B.CFG4_SMALL
+    exact = oracle_build == "serial"
+    bsh, osh, od = O.build_binned_from_workload(w, update_w2=True, f64=True)
+    gsh, gd = handlers.build_binned_from_workload(w, update_w2=True, keep_event_weights=True, f64=True)
+    np.testing.assert_array_equal(gsh.GetEventBins(), osh.event_bins())
+    data = None
+    for i, step in enumerate((-1, 0, 1, -2, 2, -3, -4, 3)):
+        sp, nm = B.proposal(w, step)
+        sp = sp + 1e-9 * (i + 1)            # not representable in float: the eval must use the double value
+        bsh.set_params(sp); osh.norm_vals[:] = nm
+        gd["pars"][:] = sp; gd["norm"][:] = nm
+        osc = B.make_osc(w, i, f64=True)
+        osh.osc_w[:] = osc; gd["osc"][:] = osc; gsh.OscillatorEvaluated()
+        osh.Reweight(); gsh.Reweight()
+        if data is None:
+            data = np.random.default_rng(3).poisson(osh.mc).astype(np.float64)
+            osh.AddData(data); gsh.AddData(data)
+            osh.Reweight(); gsh.Reweight()
+        o, g = osh.GetLikelihood(), gsh.GetLikelihood()
+        seg, _ = gsh.SplineHandler.FindSplineSegment()
+        np.testing.assert_array_equal(seg, bsh.segments)
+        wv = gsh.SplineHandler.weightvec_Monolith
+        assert wv.dtype == np.float64
+        np.testing.assert_array_equal(wv, bsh.weights)            # same fma nesting in double: bit-exact
+        sw, tw = gsh.GetEventWeight()
+        if exact:
+            np.testing.assert_array_equal(tw, osh.event_weights())
+        else:
+            np.testing.assert_allclose(tw, osh.event_weights(), rtol=1e-13, atol=0)
+        np.testing.assert_allclose(gsh.GetMCArray(), osh.mc, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(gsh.GetW2Array(), osh.w2, rtol=1e-12, atol=1e-12)
+        assert g == pytest.approx(o, rel=1e-10, abs=1e-9)
+    # and the double build really differs from the float build at the 1e-8 level (so the test can tell them apart)
+    fsh, fd = handlers.build_binned_from_workload(w, update_w2=True)
+    fd["pars"][:] = gd["pars"]; fd["norm"][:] = gd["norm"]
+    fsh.Reweight(); fsh.GetLikelihood()
+    assert not np.array_equal(fsh.SplineHandler.weightvec_Monolith.astype(np.float64), gsh.SplineHandler.weightvec_Monolith)
