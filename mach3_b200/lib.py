@@ -90,7 +90,14 @@ def bind_to_gpu_cpus(device=0):
 
 
 def _p(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def addr(a):
+    """Integer address of a C-contiguous array (for Handle.step_addr: callers that, like a C++ host, already hold
+    pointers and must not pay ctypes' per-call pointer extraction).  The array must stay alive."""
+    assert a.flags.c_contiguous
+    return a.ctypes.data
 
 
 def _c(a, dtype):
@@ -112,6 +119,10 @@ class Handle:
         self.n_bins = 0
         self.n_events = 0
         self.n_params = 0
+        self._tot = C.c_double(0)
+        self._tot_ref = C.byref(self._tot)
+        self.L.m3b_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.m3b_llh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 
     def _ck(self, rc):
         if rc != OK:
@@ -268,6 +279,19 @@ class Handle:
         ps = np.zeros((n_sets, max(self.n_samples, 1)), np.float64) if per_sample else None
         self._ck(self.L.m3b_step_batch(self.h, C.c_int32(n_sets), _p(sp), _p(nm), _p(osc_w), _p(tot), _p(ps)))
         return (tot, ps[:, :self.n_samples]) if per_sample else tot
+
+    def step_addr(self, spline_pars_addr, norm_pars_addr=0, osc_w_addr=0):
+        """m3b_step on raw addresses (float64 spline pars, float64 norm pars, float32 osc weights or 0)."""
+        rc = self.L.m3b_step(self.h, spline_pars_addr or None, norm_pars_addr or None, osc_w_addr or None)
+        if rc != OK:
+            self._ck(rc)
+
+    def llh_fast(self):
+        """m3b_llh total only, no allocation."""
+        rc = self.L.m3b_llh(self.h, self._tot_ref, None)
+        if rc != OK:
+            self._ck(rc)
+        return self._tot.value
 
     def step_segments(self, param_values, segments, norm_pars=None, osc_w=None):
         pv, sg, nm = _c(param_values, np.float32), _c(segments, np.int16), _c(norm_pars, np.float64)
