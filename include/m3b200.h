@@ -235,9 +235,12 @@ M3B_API int m3b_read_event_bins(m3b_handle* h, int32_t* bins);
  * m3b_hist_device_ptr     device address of {mc[n_bins], w2[n_bins]} (contiguous, 2*n_bins doubles)
  *                         so the caller can all-reduce it in place (NCCL through torch.distributed)
  * m3b_llh_from_hist       enqueue the LLH reduction over the (now global) histogram
- * m3b_peer_*              the library's own exchange over NVLink peer memory: every rank pushes its
- *                         partial histogram into each peer's inbox from inside the fill kernel's
- *                         last block; the LLH kernel waits for the N arrivals and sums in rank order. */
+ * m3b_peer_*, m3b_step_peer  the library's own exchange over NVLink peer memory, fused with the likelihood: every
+ *                         rank's partial histogram lives in a buffer exported through CUDA IPC (m3b_peer_export gives
+ *                         the 64-byte handle, m3b_peer_import maps a peer's); the fill kernel publishes an epoch flag,
+ *                         the exchange+likelihood kernel on every rank pulls all partials over NVLink, sums them in
+ *                         rank order (bit-identical totals on all ranks) and reduces -lnL in the same launch.  The
+ *                         wait for the peers' flags is bounded: a dead peer gives M3B_ERR_PEER, never a hang.          */
 M3B_API int m3b_step_fill(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w);
 M3B_API int m3b_hist_device_ptr(m3b_handle* h, void** dev_ptr, int32_t* n_bins, int32_t* w2_live);
 M3B_API int m3b_llh_from_hist(m3b_handle* h);

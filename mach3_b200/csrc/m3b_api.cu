@@ -802,7 +802,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     // written to d_hw[cur] by the pull kernel
     REQUIRE(h->peer_world > 0, M3B_ERR_STATE, "m3b_step_peer: call m3b_peer_export/import first");
     ++h->peer_epoch;
-    double* part = h->d_inbox[h->peer_epoch & 1];
+    double* part = h->d_partial[h->peer_epoch & 1];
     CK(cudaMemsetAsync(part, 0, sizeof(double) * h->n_bins * (w2_live ? 2 : 1), h->stream));
     if (w2_live) h->d_w2_frozen = w2;
   } else if (mode != kWeightsOnly) {
@@ -844,7 +844,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     if (next_live && (h->d_hw[other] + h->n_bins) != h->d_w2_frozen) { a.w2_next = h->d_hw[other] + h->n_bins; h->w2_zero[other] = true; }
   }
   if (mode == kPeer) {
-    double* part = h->d_inbox[h->peer_epoch & 1];
+    double* part = h->d_partial[h->peer_epoch & 1];
     a.hist = part; a.w2 = w2_live ? part + h->n_bins : nullptr;
     a.peer_world = h->peer_world; a.peer_rank = h->peer_rank; a.peer_epoch = h->peer_epoch;
     a.peer_flag_own = h->d_flags[0];
@@ -873,7 +873,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     l.data = h->d_data; l.n_bins = h->n_bins; l.n_samples = h->n_samples;
     l.test_stat = h->test_stat; l.llh_dev = h->d_llh; l.llh_host = h->h_llh_dev;
     l.peer_world = h->peer_world; l.epoch = h->peer_epoch;
-    for (int r = 0; r < h->peer_world; ++r) { l.peer_hist[r] = h->peer_inbox[par][r]; l.peer_flag[r] = h->peer_flag[0][r]; }
+    for (int r = 0; r < h->peer_world; ++r) { l.peer_hist[r] = h->peer_partial[par][r]; l.peer_flag[r] = h->peer_flag[0][r]; }
     l.hist_out = mc; l.w2_out = w2; l.w2_live = w2_live ? 1 : 0; l.status = h->d_status;
     l.w2 = h->d_w2_frozen;
     l.partial = h->d_llh_partial; l.ticket = h->d_llh_ticket;
@@ -1116,14 +1116,14 @@ M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ip
   REQUIRE(h->n_bins > 0, M3B_ERR_STATE, "m3b_peer_export: upload the binning first");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
   CK(cudaSetDevice(h->device));
-  if (!h->d_inbox[0]) {
+  if (!h->d_partial[0]) {
     // one exported allocation: [2 parities][mc[n_bins] | w2[n_bins]] then this rank's epoch flag
     const size_t part_d = static_cast<size_t>(2) * h->n_bins;
     const size_t total_d = 2 * part_d + 16;
     double* base = nullptr;
     CK(dev_alloc(h, &base, total_d));
     CK(cudaMemset(base, 0, total_d * sizeof(double)));
-    h->d_inbox[0] = base; h->d_inbox[1] = base + part_d;
+    h->d_partial[0] = base; h->d_partial[1] = base + part_d;
     h->d_flags[0] = reinterpret_cast<unsigned int*>(base + 2 * part_d);
     h->d_flags[1] = h->d_flags[0];
     CK(dev_alloc(h, &h->d_llh_partial, static_cast<size_t>(kLlhPullMaxBlocks) * std::max(1, h->n_samples)));
@@ -1131,9 +1131,9 @@ M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ip
     CK(cudaMemset(h->d_llh_ticket, 0, sizeof(unsigned int)));
   }
   h->peer_world = world; h->peer_rank = rank;
-  for (int par = 0; par < 2; ++par) { h->peer_inbox[par][rank] = h->d_inbox[par]; h->peer_flag[par][rank] = h->d_flags[par]; }
+  for (int par = 0; par < 2; ++par) { h->peer_partial[par][rank] = h->d_partial[par]; h->peer_flag[par][rank] = h->d_flags[par]; }
   cudaIpcMemHandle_t mh;
-  CK(cudaIpcGetMemHandle(&mh, h->d_inbox[0]));
+  CK(cudaIpcGetMemHandle(&mh, h->d_partial[0]));
   memcpy(ipc_handle_64B, &mh, 64);
   return M3B_OK;
 }
@@ -1150,7 +1150,7 @@ M3B_API int m3b_peer_import(m3b_handle* h, int32_t peer_rank, const void* ipc_ha
   h->ipc_opened.push_back(p);
   double* base = static_cast<double*>(p);
   const size_t part_d = static_cast<size_t>(2) * h->n_bins;
-  h->peer_inbox[0][peer_rank] = base; h->peer_inbox[1][peer_rank] = base + part_d;
+  h->peer_partial[0][peer_rank] = base; h->peer_partial[1][peer_rank] = base + part_d;
   h->peer_flag[0][peer_rank] = reinterpret_cast<unsigned int*>(base + 2 * part_d);
   h->peer_flag[1][peer_rank] = h->peer_flag[0][peer_rank];
   return M3B_OK;

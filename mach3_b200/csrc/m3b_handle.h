@@ -122,9 +122,9 @@ struct m3b_handle {
 
   // ---- peer exchange
   int peer_world = 0, peer_rank = 0;
-  double* d_inbox[2] = {nullptr, nullptr};       // own inboxes (two epochs' parity), [world*2*n_bins]
+  double* d_partial[2] = {nullptr, nullptr};     // this rank's exported partial histograms (two epochs' parity), {mc,w2}[n_bins]
   unsigned int* d_flags[2] = {nullptr, nullptr}; // [world]
-  double* peer_inbox[2][8] = {};
+  double* peer_partial[2][8] = {};
   unsigned int* peer_flag[2][8] = {};
   unsigned int peer_epoch = 0;
   double* d_llh_partial = nullptr; unsigned int* d_llh_ticket = nullptr;
