@@ -411,3 +411,43 @@ def test_llh_scan_matches_the_reference_loop(oracle_build):
     # handle at the central values with one Reweight: same cached-segment history on both sides
     mono.set_params(c_sp); osh.norm_vals[:] = c_nm; osh.Reweight()
     assert gsh.GetLikelihood() == pytest.approx(osh.GetLikelihood(), rel=1e-9 if _exact() else LLH_RTOL)
+
+
+def test_fill_only_then_llh_from_hist_equals_fused(oracle_build):
+    """The multi-GPU building blocks on one GPU: m3b_step_fill + m3b_llh_from_hist (what every rank runs around the
+    exchange) give the fused step's histogram and -lnL; the histogram device pointer is stable across steps."""
+    from mach3_b200 import sharding
+    w = synth.SPARSE.scaled(12_000)
+    mono, osh, od = O.build_from_workload(w, update_w2=True)
+    fused, fd = handlers.build_from_workload(w, update_w2=True)
+    split, sd = handlers.build_from_workload(w, update_w2=True, fused_llh=False)
+    sh = sharding.ShardedSampleHandler(split.handle, None)
+    split.handle.upload_osc(sd["osc"])           # the sharded wrapper takes the weights per call; keep step 0's on the device
+    ptr0 = None
+    for step in (-1, 0, 1, 2):
+        sp, nm = synth.proposal(w, step)
+        mono.set_params(sp); osh.norm_vals[:] = nm
+        fd["pars"][:] = sp; fd["norm"][:] = nm
+        osh.Reweight(); fused.Reweight()
+        if step == -1:
+            data = np.random.default_rng(4).poisson(osh.mc).astype(np.float64)
+            osh.AddData(data); fused.AddData(data); split.AddData(data)
+            osh.Reweight(); fused.Reweight()
+        sh.Reweight(sp, nm)
+        ptr, nb, live = split.handle.hist_device_ptr()
+        assert nb == w.n_bins and live == 1 and (ptr0 is None or ptr == ptr0)
+        ptr0 = ptr
+        assert sh.GetLikelihood() == pytest.approx(fused.GetLikelihood(), rel=1e-12)
+        np.testing.assert_allclose(split.GetMCArray(), fused.GetMCArray(), rtol=1e-12, atol=1e-12)
+        assert sh.GetLikelihood() == pytest.approx(osh.GetLikelihood(), rel=1e-10 if _exact() else LLH_RTOL, abs=1e-9)
+
+
+def test_block_trace_reports_every_block():
+    w = synth.CFG1.scaled(50_000)
+    gsh, gd = handlers.build_from_workload(w)
+    gsh.Reweight(); gsh.GetLikelihood()
+    gsh.handle.block_trace(read=False)
+    gsh.Reweight(); gsh.GetLikelihood()
+    tr = gsh.handle.block_trace()
+    assert tr.shape == (gsh.handle.info().grid_blocks, 8)
+    assert (tr[:, 6] > tr[:, 0]).all() and int(tr[:, 7].sum()) == -(-w.n_events // 256)     # every 256-event unit exactly once
