@@ -163,7 +163,14 @@ class SampleHandlerB200 : public FDBase {
                             max_norm ? norm_idx.data() : nullptr, bases.n_norm, any_osc ? 1 : 0,
                             any_osc ? osc_idx.data() : nullptr, n_osc_dev_, static_w.data()),
           "m3b_upload_events");
-    if (any_osc) osc_stage_.assign(static_cast<size_t>(n_osc_dev_), 1.0f);
+    if (any_osc) {
+      // staging copy of the oscillator's weight array in pinned + mapped memory from the library: the fill kernel
+      // streams it over PCIe itself (zero-copy), no separate H2D pass
+      void* p = nullptr;
+      check(m3b_alloc_host(h_, sizeof(float) * static_cast<size_t>(n_osc_dev_), &p), "m3b_alloc_host");
+      osc_stage_ = static_cast<float*>(p);
+      std::fill(osc_stage_, osc_stage_ + n_osc_dev_, 1.0f);
+    }
     check(m3b_upload_data(h_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_upload_data");
     ready_ = true;
   }
@@ -178,8 +185,9 @@ class SampleHandlerB200 : public FDBase {
     for (size_t p = 0; p < spline_ptrs_.size(); ++p) spline_vals_[p] = *spline_ptrs_[p];
     const float* osc = nullptr;
     if (n_osc_dev_ > 0) {
-      std::copy(bases_.osc_base, bases_.osc_base + bases_.n_osc, osc_stage_.begin());
-      osc = osc_stage_.data();
+      check(m3b_synchronize(h_), "m3b_synchronize");       // the previous step may still be reading the staging array
+      std::copy(bases_.osc_base, bases_.osc_base + bases_.n_osc, osc_stage_);
+      osc = osc_stage_;
     }
     check(m3b_step(h_, spline_vals_.empty() ? nullptr : spline_vals_.data(), bases_.norm_base, osc), "m3b_step");
     host_arrays_stale_ = true;
@@ -221,7 +229,7 @@ class SampleHandlerB200 : public FDBase {
   PointerBases bases_{};
   std::vector<const double*> spline_ptrs_;
   std::vector<double> spline_vals_;
-  std::vector<float> osc_stage_;
+  float* osc_stage_ = nullptr;             // m3b_alloc_host; freed with the handle
 };
 
 }  // namespace m3b200

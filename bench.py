@@ -214,9 +214,13 @@ def main_b200(args):
                     ev["static_w"])
     del ev
     n_osc_bufs = 4
-    osc_bufs = [synth.make_osc(w, k, e0, e1) for k in range(n_osc_bufs)]
-    for b in osc_bufs:
-        h.register_host_buffer(b)          # the caller's persistent osc array: pinned once
+    # the caller's persistent oscillation-weight arrays live in pinned + mapped host memory from the library
+    # (m3b_alloc_host; registering malloc'ed numpy memory gave less than half the PCIe rate on this pool)
+    osc_bufs = []
+    for k in range(n_osc_bufs):
+        b = h.alloc_host(n_local, np.float32)
+        b[:] = synth.make_osc(w, k, e0, e1)
+        osc_bufs.append(b)
     h.upload_osc(osc_bufs[0])
     t_setup = time.perf_counter() - t_setup
 

@@ -58,6 +58,7 @@ M3B_API void m3b_destroy(m3b_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : h->registered) cudaHostUnregister(p);
+  for (void* p : h->host_allocs) cudaFreeHost(p);
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   for (int i = 0; i < m3b_handle::kRing; ++i) {
@@ -557,6 +558,25 @@ M3B_API int m3b_register_host_buffer(m3b_handle* h, void* ptr, uint64_t bytes) {
   CK(cudaSetDevice(h->device));
   CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
   h->registered.push_back(ptr);
+  return M3B_OK;
+}
+
+M3B_API int m3b_alloc_host(m3b_handle* h, uint64_t bytes, void** ptr) {
+  REQUIRE(h && ptr && bytes, M3B_ERR_INVALID, "m3b_alloc_host: bad argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaHostAlloc(ptr, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  h->host_allocs.push_back(*ptr);
+  return M3B_OK;
+}
+
+M3B_API int m3b_free_host(m3b_handle* h, void* ptr) {
+  REQUIRE(h && ptr, M3B_ERR_INVALID, "m3b_free_host: bad argument");
+  auto it = std::find(h->host_allocs.begin(), h->host_allocs.end(), ptr);
+  REQUIRE(it != h->host_allocs.end(), M3B_ERR_INVALID, "m3b_free_host: not allocated by m3b_alloc_host on this handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaFreeHost(ptr));
+  h->host_allocs.erase(it);
   return M3B_OK;
 }
 

@@ -131,6 +131,7 @@ struct m3b_handle {
   int32_t* d_status = nullptr;
   std::vector<void*> ipc_opened;
   std::vector<void*> registered;
+  std::vector<void*> host_allocs;        // m3b_alloc_host
 
   // ---- BinnedSplineHandler path (m3b_binned.cu)
   bool binned = false;

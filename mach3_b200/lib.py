@@ -23,7 +23,7 @@ EXPORTS = (
     "m3b_upload_binned_splines", "m3b_upload_event_binned_splines", "m3b_read_binned_weights",
     "m3b_upload_binned_splines_f64", "m3b_upload_event_weights_f64", "m3b_upload_osc_f64", "m3b_read_binned_weights_f64",
     "m3b_read_event_weights_f64",
-    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer",
+    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
     "m3b_set_test_statistic", "m3b_reset_w2",
     "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
@@ -252,6 +252,14 @@ class Handle:
 
     def register_host_buffer(self, arr):
         self._ck(self.L.m3b_register_host_buffer(self.h, _p(arr), C.c_uint64(arr.nbytes)))
+
+    def alloc_host(self, n, dtype=np.float32):
+        """numpy array over pinned + mapped host memory owned by the handle (valid until close())."""
+        dt = np.dtype(dtype)
+        p = C.c_void_p()
+        self._ck(self.L.m3b_alloc_host(self.h, C.c_uint64(int(n) * dt.itemsize), C.byref(p)))
+        buf = (C.c_char * (int(n) * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=int(n))
 
     def set_test_statistic(self, ts):
         self._ck(self.L.m3b_set_test_statistic(self.h, C.c_int32(ts)))
