@@ -849,6 +849,10 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   a.osc_host = osc_zc; a.osc_store = h->d_osc;
   if (h->use_tma) {
     a.tile_counter = h->d_tile_counter; a.n_stages = h->tma_stages; a.tma = h->tma;
+    // queued fused steps overlap (programmatic dependent launch) unless something reads/writes per-event outputs or
+    // brackets the kernel with timing events
+    static const bool pdl_off = [] { const char* z = getenv("M3B_PDL"); return z && z[0] == '0'; }();
+    a.pdl = (!pdl_off && mode == kFused && h->hist_in_smem && !h->timing && !h->d_evt_spline_w && !osc_zc && !h->d_trace) ? 1 : 0;
     const char* ge = getenv("M3B_GUARD_X2");
     a.guard_x2 = ge && atoi(ge) > 0 ? atoi(ge) : 6;
   }

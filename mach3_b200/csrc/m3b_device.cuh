@@ -220,10 +220,16 @@ static __device__ void block_llh(const double* __restrict__ hist, const double* 
 // Every thread of the block must call it.  `scratch` = n_samples*32 doubles of shared memory that
 // no longer hold live data.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void finish_block(const FillArgs& a, const double* s_hist, const double* s_w2,
                                              double* scratch, int* s_last) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const bool w2_live = a.w2 != nullptr;
+  // queued steps (programmatic dependent launch): the histogram buffers, the ticket and the scheduler counter were
+  // last written by the previous step's final block -- make sure that launch has completed before touching them
+  if (a.pdl) grid_dependency_wait();
   if (a.fuse_llh) {
     // the last block will need data[] (and a frozen w2[]) which the coefficient stream has pushed out
     // of L2 by now: every block pulls its slice back in while it flushes

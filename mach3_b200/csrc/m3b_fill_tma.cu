@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
   float* s_osc = reinterpret_cast<float*>(smem + L.off_osc);
 
   if (tid == 0) trace_mark(a, 0);
+  // let the next queued step's blocks take over SMs as ours retire (it waits before touching anything we write)
+  if (a.pdl) grid_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerWarps); }
     mbar_init(&step_bar, 1);
@@ -163,13 +165,14 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
     unsigned long long n_units = 0;
     const bool expanded = a.step.n_sigs_x > 0;
     const int32_t* rowx = reinterpret_cast<const int32_t*>(st + a.step.off_rowx);
-    bool fresh = true;
+    bool fresh = true, pdl_waited = false;
     while (true) {
       if (fresh) { fresh = false; if (u >= unit_end) break; }
       else if (u >= u_end) {
         // guided grab: one atomicAdd (never retries, no CAS storms); the size comes from the
         // work left as of this producer's previous grab
         unsigned int c = 0; int want = 0;
+        if (a.pdl && !pdl_waited) { grid_dependency_wait(); pdl_waited = true; }    // the counter was re-armed by the previous step's last block
         if (lane == 0) {
           const unsigned int done = static_units + seen;
           const unsigned int left = unit_begin + done < unit_end ? unit_end - unit_begin - done : 0u;
@@ -393,6 +396,15 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
 
 cudaError_t launch_fill_tma(const FillArgs& a, int grid, int smem, cudaStream_t s) {
   if (a.T % kUnit != 0 || a.T / kUnit > kMaxG || (a.T / kUnit & (a.T / kUnit - 1)) != 0) return cudaErrorInvalidValue;
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kUnit + 32); cfg.dynamicSmemBytes = static_cast<size_t>(smem); cfg.stream = s;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fill_tma_kernel, a);
+  }
   fill_tma_kernel<<<grid, kUnit + 32, smem, s>>>(a);
   return cudaGetLastError();
 }

@@ -130,6 +130,9 @@ struct FillArgs {
   unsigned int* ticket;
   unsigned int* tile_counter;  // dynamic tile scheduler of the TMA kernel (nullptr: static interleave)
   int32_t n_stages;            // TMA kernel: stages of the shared-memory coefficient ring
+  int32_t pdl;                 // TMA kernel launched with programmatic stream serialization: the next step's ramp may
+                               // overlap this step's tail; everything the previous launch wrote is touched only after
+                               // griddepcontrol.wait
   int32_t guard_x2;            // TMA kernel: whole tile rows are grabbed while more than guard_x2/2 * grid * g units are left
   double* llh_dev;             // [1+n_samples]
   double* llh_host;            // mapped pinned mirror (nullptr = none)
