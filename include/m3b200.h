@@ -174,6 +174,11 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
                               int32_t n_norm_per_event, const int16_t* norm_idx, int32_t n_norm_values,
                               int32_t use_osc, const int32_t* osc_idx, int64_t n_osc_values,
                               const float* static_w);
+/* m3b_update_kinematics: functional ("shift") parameters (Samples/SampleHandlerFD.cpp:545-564, ApplyShifts) call
+ *   arbitrary std::functions per event, so they stay on the host; the caller hands over the shifted kinematic
+ *   variables (same layout as m3b_upload_events' kin) and the events are re-binned on the device.  Needs
+ *   M3B_FLAG_KEEP_KINEMATICS.  Asynchronous; takes effect for the following steps.                             */
+M3B_API int m3b_update_kinematics(m3b_handle* h, const double* kin);
 /* SampleHandlerFD::AddData (Samples/SampleHandlerFD.cpp:955-1044), array form */
 M3B_API int m3b_upload_data(m3b_handle* h, const double* data, int32_t n_bins);
 /* oscillation weights computed elsewhere (NuOscillator) and already valid for the next steps    */

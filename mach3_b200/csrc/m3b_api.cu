@@ -492,7 +492,7 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
     ba.grid_start = h->d_grid_start; ba.grid_idx = h->d_grid_idx;
     CK(launch_bins(ba, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (keep) { h->d_sample_id = d_sid; h->d_kin = d_kin; } else { cudaFree(d_sid); cudaFree(d_kin); }
+    if (keep) { h->d_sample_id = d_sid; h->d_kin = d_kin; h->kin_dims = max_dim; } else { cudaFree(d_sid); cudaFree(d_kin); }
   }
   // norm bindings, transposed to [slot][event] and padded
   h->norm_slots = norm_idx ? n_norm_per_event : 0;
@@ -533,6 +533,25 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
     CK(dev_alloc(h, &h->d_evt_total_w, static_cast<size_t>(EP)));
   }
   h->launch_ready = false;
+  return M3B_OK;
+}
+
+// Functional ("shift") parameters (Samples/SampleHandlerFD.cpp:545-564) call arbitrary std::functions per event, so they
+// stay on the host: the caller applies its shifts to the kinematic variables and hands the shifted values over; the
+// events are re-binned on the device with the same FindGlobalBin semantics.  Asynchronous on the handle's stream.
+M3B_API int m3b_update_kinematics(m3b_handle* h, const double* kin) {
+  REQUIRE(h && kin, M3B_ERR_INVALID, "m3b_update_kinematics: null argument");
+  REQUIRE(h->d_kin && h->n_events > 0, M3B_ERR_STATE, "m3b_update_kinematics: create the handle with M3B_FLAG_KEEP_KINEMATICS and upload the events first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_kin, kin, sizeof(double) * h->n_events * h->kin_dims, cudaMemcpyHostToDevice, h->stream));
+  BinArgs ba{};
+  ba.n_events = h->n_events; ba.e_pad = h->e_pad; ba.sample_id = h->d_sample_id; ba.kin = h->d_kin; ba.n_samples = h->n_samples;
+  ba.n_dim = h->d_ndim; ba.nbins = h->d_nbins; ba.edge_off = h->d_edge_off; ba.stride = h->d_stride;
+  ba.global_off = h->d_goff; ba.edges = h->d_edges; ba.bin = h->d_bin;
+  ba.uniform = h->d_uniform; ba.box_off = h->d_box_off; ba.grid_off = h->d_grid_off; ba.boxes = h->d_boxes;
+  ba.grid_start = h->d_grid_start; ba.grid_idx = h->d_grid_idx;
+  CK(launch_bins(ba, h->stream));
+  ++h->launches;
   return M3B_OK;
 }
 

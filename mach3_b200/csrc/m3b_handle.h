@@ -78,6 +78,7 @@ struct m3b_handle {
   int16_t* d_norm_idx = nullptr;
   int norm_slots = 0, n_norm_values = 0;
   double* d_kin = nullptr;
+  int kin_dims = 0;
   int32_t* d_sample_id = nullptr;
   float *d_evt_spline_w = nullptr, *d_evt_total_w = nullptr;
   bool evt_weights_valid = false;

@@ -23,7 +23,7 @@ EXPORTS = (
     "m3b_upload_binned_splines", "m3b_upload_event_binned_splines", "m3b_read_binned_weights",
     "m3b_upload_binned_splines_f64", "m3b_upload_event_weights_f64", "m3b_upload_osc_f64", "m3b_read_binned_weights_f64",
     "m3b_read_event_weights_f64",
-    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
+    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_update_kinematics", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
     "m3b_set_test_statistic", "m3b_reset_w2",
     "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
@@ -241,6 +241,12 @@ class Handle:
         self._ck(self.L.m3b_upload_events(self.h, C.c_int64(sid.size), _p(sid), _p(k), C.c_int32(n_norm_per_event),
                                           _p(ni), C.c_int32(n_norm_values), C.c_int32(int(use_osc)), _p(oi),
                                           C.c_int64(n_osc_values), _p(sw)))
+
+    def update_kinematics(self, kin):
+        """Shifted kinematic variables (functional parameters applied on the host): re-bins on the device."""
+        k = _c(kin, np.float64)
+        self._keep_kin = k
+        self._ck(self.L.m3b_update_kinematics(self.h, _p(k)))
 
     def upload_data(self, data):
         d = _c(data, np.float64)

@@ -451,3 +451,35 @@ def test_block_trace_reports_every_block():
     tr = gsh.handle.block_trace()
     assert tr.shape == (gsh.handle.info().grid_blocks, 8)
     assert (tr[:, 6] > tr[:, 0]).all() and int(tr[:, 7].sum()) == -(-w.n_events // 256)     # every 256-event unit exactly once
+
+
+def test_functional_shifts_applied_on_the_host_rebin_on_the_device():
+    """Functional (kinematic-shift) parameters stay on the host (SampleHandlerFD.cpp:545-564): the shifted KinVar are
+    handed over with m3b_update_kinematics and re-binned with FindGlobalBin semantics; oracle = the same shifted values."""
+    O.set_multithread(False)
+    w = synth.SPARSE.scaled(15_000)
+    typ, npts, cx = synth.param_layout(w)
+    spl, ev = synth.make_splines(w), synth.make_events(w)
+    h = lib.Handle(update_w2=True, flags=lib.FLAG_KEEP_KINEMATICS | lib.FLAG_KEEP_EVENT_WEIGHTS)
+    h.upload_spline_monolith(w.n_params, w.n_knots, cx, npts, spl)
+    h.upload_binning(synth.bin_edges(w))
+    h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0, ev["static_w"])
+    osc = synth.make_osc(w, 0)
+    h.upload_osc(osc)
+    rng = np.random.default_rng(3)
+    for step in range(3):
+        kin = ev["kin"] * (1.0 + 0.05 * rng.normal(size=ev["kin"].size))      # an energy-scale-like shift per event
+        mono = O.SMonolith(w.n_params, w.n_knots, cx, npts, spl)
+        osh = O.SampleHandlerFD(w.n_events, synth.bin_edges(w), w.test_statistic, True)
+        norm = np.ones(w.n_norm_params)
+        osh.set_events(ev["sample_id"], kin, ev["norm_idx"], w.n_norm_per_event, norm, osc, mono, ev["static_w"])
+        sp, nm = synth.proposal(w, step)
+        mono.set_params(sp); osh.norm_vals[:] = nm
+        osh.Reweight()
+        h.update_kinematics(kin)
+        h.step(sp, nm)
+        h.llh()
+        np.testing.assert_array_equal(h.read_event_bins(), osh.event_bins())
+        np.testing.assert_allclose(h.read_hist()[0], osh.mc, rtol=1e-12, atol=1e-12)
+    h.close()
+    O.set_multithread(True)
