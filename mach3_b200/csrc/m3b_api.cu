@@ -781,7 +781,8 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   if (!h->use_tma) osc_zc = nullptr;
 
   // per-step table {segment, dx, value, norm}
-  const bool inline_step = h->step.bytes <= kStepInlineMax && !getenv("M3B_NO_INLINE_STEP");
+  static const bool no_inline_env = getenv("M3B_NO_INLINE_STEP") != nullptr;
+  const bool inline_step = h->step.bytes <= kStepInlineMax && !no_inline_env;
   FillArgs a{};
   const int slot = h->ring;
   unsigned char* st = a.step_inline;
@@ -872,8 +873,8 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     // brackets the kernel with timing events
     static const bool pdl_off = [] { const char* z = getenv("M3B_PDL"); return z && z[0] == '0'; }();
     a.pdl = (!pdl_off && mode == kFused && h->hist_in_smem && !h->timing && !h->d_evt_spline_w && !osc_zc && !h->d_trace) ? 1 : 0;
-    const char* ge = getenv("M3B_GUARD_X2");
-    a.guard_x2 = ge && atoi(ge) > 0 ? atoi(ge) : 6;
+    static const int guard_env = [] { const char* ge = getenv("M3B_GUARD_X2"); return ge && atoi(ge) > 0 ? atoi(ge) : 6; }();
+    a.guard_x2 = guard_env;
   }
   a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->llh_host_override ? h->llh_host_override : h->h_llh_dev;
   a.evt_spline_w = h->d_evt_spline_w; a.evt_total_w = h->d_evt_total_w;

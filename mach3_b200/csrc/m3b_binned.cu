@@ -201,7 +201,7 @@ static int upload_binned_impl(m3b_handle* h, int32_t n_params, int32_t max_knots
   REQUIRE(n_unique >= 0 && (n_unique == 0 || (uniquecoeffindices && manycoeff_arr && xcoeff_arr)), M3B_ERR_INVALID, "m3b_upload_binned_splines: null coefficient arrays");
   CK(cudaSetDevice(h->device));
   h->P = n_params; h->Kmax = max_knots;
-  if (F64) { h->coeff_x_d.assign(knot_x, knot_x + static_cast<size_t>(n_params) * max_knots); h->f64 = true; }
+  if constexpr (F64) { h->coeff_x_d.assign(knot_x, knot_x + static_cast<size_t>(n_params) * max_knots); h->f64 = true; }
   else h->coeff_x.assign(knot_x, knot_x + static_cast<size_t>(n_params) * max_knots);
   h->n_pts.assign(n_pts, n_pts + n_params);
   h->nseg.resize(n_params);
@@ -255,16 +255,16 @@ static int upload_binned_impl(m3b_handle* h, int32_t n_params, int32_t max_knots
   for (int p = 0; p < n_params; ++p)
     for (int64_t k0 = 0; k0 < npad[p]; k0 += kBTileSplines)
       tiles.push_back(BTile{coef_base[p], static_cast<int32_t>(npad[p]), p, static_cast<int32_t>(k0), static_cast<int32_t>(out_base[p] + k0)});
-  if (F64) {
-    CK(dev_upload(h, &h->d_bcoef_d, reinterpret_cast<const std::vector<double>&>(coef)));
-    CK(dev_upload(h, &h->d_bx_d, reinterpret_cast<const std::vector<double>&>(xs)));
+  if constexpr (F64) {
+    CK(dev_upload(h, &h->d_bcoef_d, coef));
+    CK(dev_upload(h, &h->d_bx_d, xs));
     CK(dev_alloc(h, &h->d_bw_d, static_cast<size_t>(n_act_pad)));
   } else {
     float4* dc = nullptr;
     CK(dev_alloc(h, &dc, static_cast<size_t>(n_coef_dev)));
     CK(cudaMemcpy(dc, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
     h->d_bcoef = dc;
-    CK(dev_upload(h, &h->d_bx, reinterpret_cast<const std::vector<float>&>(xs)));
+    CK(dev_upload(h, &h->d_bx, xs));
     CK(dev_alloc(h, &h->d_bw, static_cast<size_t>(n_act_pad)));
   }
   CK(dev_upload(h, &h->d_btiles, tiles));
