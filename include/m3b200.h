@@ -109,6 +109,15 @@ M3B_API int m3b_upload_spline_monolith(m3b_handle* h, int32_t n_params, int32_t 
                                        const uint32_t* nParamPerEvent_tf1, const int16_t* paramNo_tf1,
                                        const float* coeff_tf1);
 
+/* FastSplineInfo::xPts in the default build's M3::float_t = double (Splines/SplineStructs.h:21-44).  The monolith
+ * arrays only carry the knots as floats (coeff_x); SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-111)
+ * compares the float-narrowed parameter against xPts, which hold the splines' double knots when SMonolith was
+ * built in-process (Splines/SplineMonolith.cpp:393-404) and float-rounded ones when it was reloaded from a spline
+ * file (Splines/SplineBase.cpp:166-190) or in a _LOW_MEMORY_STRUCTS_ build.  The two differ only when a proposed
+ * value lands between a knot and its float rounding.  Default: coeff_x.  x_pts[n_params*max_knots] (rows padded,
+ * only n_pts[p] entries of row p are read); NULL restores the default.  dx still uses coeff_x, as the reference. */
+M3B_API int m3b_set_spline_knots_f64(m3b_handle* h, const double* x_pts);
+
 /* ---- binned splines --------------------------------------------------------------------------
  * The other SplineBase implementation, BinnedSplineHandler (Splines/BinnedSplineHandler.h:110-135,
  * Evaluate/CalcSplineWeights .cpp:295-341), _LOW_MEMORY_STRUCTS_ build (M3::float_t = float).  Either this

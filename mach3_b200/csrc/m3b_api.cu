@@ -159,7 +159,10 @@ static int append_chunk(m3b_handle* h, int64_t n, const uint32_t* cnt_c, const i
   for (uint64_t s = 0; s < tot_c; ++s) {
     const int p = paramNo[s];
     REQUIRE(p >= 0 && p < P, M3B_ERR_INVALID, "m3b_splines_append: paramNo_arr out of range");
-    const uint64_t nk = (s + 1 < tot_c ? knot_off[s + 1] : total_knots) - knot_off[s];
+    uint64_t nk = (s + 1 < tot_c ? knot_off[s + 1] : total_knots) - knot_off[s];
+    // the last used response: SMonolith sizes coeff_many from ScanMasterSpline's count, which includes the one-knot
+    // splines PrepareForGPU then skips (Splines/SplineMonolith.cpp:370,151), so unused knots may follow it
+    if (s + 1 == tot_c && nk > static_cast<uint64_t>(h->n_pts[p]) && knot_off[s] <= total_knots) nk = static_cast<uint64_t>(h->n_pts[p]);
     if (nk != static_cast<uint64_t>(h->n_pts[p])) {
       char b[256];
       snprintf(b, sizeof b, "m3b_splines_append: response %llu of parameter %d has %llu knots, parameter has %d",
@@ -644,7 +647,16 @@ static void find_segments_t(m3b_handle* h, const double* pars, const K* knots) {
 }  // extern "C++"
 static void find_segments(m3b_handle* h, const double* pars) {
   if (h->f64) find_segments_t(h, pars, h->coeff_x_d.data());
+  else if (!h->knots_d.empty()) find_segments_t(h, pars, h->knots_d.data());
   else find_segments_t(h, pars, h->coeff_x.data());
+}
+
+M3B_API int m3b_set_spline_knots_f64(m3b_handle* h, const double* x_pts) {
+  REQUIRE(h, M3B_ERR_INVALID, "m3b_set_spline_knots_f64: null handle");
+  REQUIRE(h->P > 0 && !h->binned, M3B_ERR_STATE, "m3b_set_spline_knots_f64: upload the spline monolith first");
+  if (!x_pts) { h->knots_d.clear(); return M3B_OK; }
+  h->knots_d.assign(x_pts, x_pts + static_cast<size_t>(h->P) * h->Kmax);
+  return M3B_OK;
 }
 
 M3B_API int m3b_find_segments(m3b_handle* h, const double* spline_pars, int16_t* segments, float* param_values) {

@@ -28,6 +28,7 @@ struct m3b_handle {
   // ---- spline parameters (FastSplineInfo, Splines/SplineStructs.h:21-44)
   int P = 0, Kmax = 0;
   std::vector<float> coeff_x;
+  std::vector<double> knots_d;   // optional FastSplineInfo::xPts in double (m3b_set_spline_knots_f64); empty: coeff_x
   std::vector<int16_t> n_pts;
   std::vector<int16_t> curr_segment;     // FastSplineInfo::CurrSegment
   std::vector<int16_t> segments;         // SplineBase::SplineSegments

@@ -25,7 +25,7 @@ EXPORTS = (
     "m3b_read_event_weights_f64",
     "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_update_kinematics", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
     "m3b_set_test_statistic", "m3b_reset_w2",
-    "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_synchronize",
+    "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_set_spline_knots_f64", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
     "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
     "m3b_get_info", "m3b_set_timing", "m3b_kernel_time", "m3b_block_trace",
@@ -333,6 +333,10 @@ class Handle:
         val = np.zeros(self.n_params, np.float32)
         self._ck(self.L.m3b_find_segments(self.h, _p(sp), _p(seg), _p(val)))
         return seg, val
+
+    def set_spline_knots_f64(self, x_pts):
+        """FastSplineInfo::xPts as doubles ([n_params, max_knots]); None restores the float knots of coeff_x."""
+        self._ck(self.L.m3b_set_spline_knots_f64(self.h, None if x_pts is None else _p(_c(x_pts, np.float64))))
 
     def synchronize(self):
         self._ck(self.L.m3b_synchronize(self.h))

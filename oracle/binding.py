@@ -100,6 +100,11 @@ class SMonolith:
     def Evaluate(self):
         lib().m3o_evaluate(self.h)
 
+    def set_knots_f64(self, x_pts):
+        """FastSplineInfo::xPts in double (the default build with splines built in-process); None: float knots."""
+        self._knots_d = None if x_pts is None else np.ascontiguousarray(x_pts, np.float64)
+        lib().m3o_set_knots_f64(self.h, None if x_pts is None else _p(self._knots_d))
+
     def set_curr_segment(self, p, seg):
         lib().m3o_set_curr_segment(self.h, C.c_int(p), C.c_int(seg))
 

@@ -59,6 +59,9 @@ enum TestStatistic { kPoisson, kBarlowBeeston, kIceCube, kPearson, kDembinskiAbd
 typedef struct {
   short nPts;
   const float* xPts;              /* knot positions (first spline seen for the parameter) */
+  const double* xPts_d;           /* the same in M3::float_t = double (default build, splines built in-process:
+                                     Splines/SplineMonolith.cpp:393-404); NULL: the float ones (values reloaded
+                                     from a spline file, Splines/SplineBase.cpp:166-190, or _LOW_MEMORY_STRUCTS_) */
   int   n_x;                      /* xPts.size() */
   short CurrSegment;
   const double* splineParsPointer;
@@ -147,10 +150,12 @@ M3O_API void m3o_set_spline_pointers(SMonolith* m, const double* base) {
 }
 
 /* SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-109) */
+#define XARR(k) (xd ? xd[k] : (double)xf[k])      /* float xvar against M3::float_t knots: the comparison is in double */
 M3O_API void m3o_find_spline_segment(SMonolith* m) {
   for (short i = 0; i < m->nParams; ++i) {
     const short nPoints = m->SplineInfoArray[i].nPts;
-    const float* xArray = m->SplineInfoArray[i].xPts;
+    const float* xf = m->SplineInfoArray[i].xPts;
+    const double* xd = m->SplineInfoArray[i].xPts_d;
 
     /* :54-55 the variation is narrowed to float, stored for every parameter */
     const float xvar = (float)(*m->SplineInfoArray[i].splineParsPointer);
@@ -163,17 +168,17 @@ M3O_API void m3o_find_spline_segment(SMonolith* m) {
     short kHigh = (short)(nPoints - 1);
     const short PreviousSegment = m->SplineInfoArray[i].CurrSegment;
 
-    if (xvar <= xArray[0]) {                                   /* :69 */
+    if (xvar <= XARR(0)) {                                   /* :69 */
       segment = 0;
-    } else if (xvar >= xArray[nPoints - 1]) {                  /* :72 */
+    } else if (xvar >= XARR(nPoints - 1)) {                  /* :72 */
       segment = kHigh;
-    } else if (xArray[PreviousSegment + 1] > xvar && xvar >= xArray[PreviousSegment]) { /* :76 */
+    } else if (XARR(PreviousSegment + 1) > xvar && xvar >= XARR(PreviousSegment)) { /* :76 */
       segment = PreviousSegment;
     } else {                                                   /* :79-95 binary search */
       short kHalf = 0;
       while (kHigh - segment > 1) {
         kHalf = (short)((segment + kHigh) / 2);
-        if (xvar > xArray[kHalf]) segment = kHalf;
+        if (xvar > XARR(kHalf)) segment = kHalf;
         else kHigh = kHalf;
       }
     }
@@ -182,6 +187,12 @@ M3O_API void m3o_find_spline_segment(SMonolith* m) {
     m->SplineInfoArray[i].CurrSegment = segment;               /* :102-103 */
     m->SplineSegments[i] = (short)m->SplineInfoArray[i].CurrSegment;
   }
+}
+#undef XARR
+
+/* knots as doubles (the reference's default build when the monolith is built in-process); xPts[nParams*max_knots] */
+M3O_API void m3o_set_knots_f64(SMonolith* m, const double* xPts) {
+  for (short i = 0; i < m->nParams; ++i) m->SplineInfoArray[i].xPts_d = xPts ? xPts + (size_t)i * (size_t)m->_max_knots : NULL;
 }
 
 /* SMonolith::CalcSplineWeights (Splines/SplineMonolith.cpp:727-788), serial build */

@@ -1,3 +1,3 @@
-// stand-in for ROOT's TMatrixDSym.h (ROOT is not installed in this image): deliberately empty.
-// The reference code compiled through oracle/ref_host uses nothing from it.
+// stand-in for ROOT's TMatrixDSym.h (ROOT is not installed in this image): compile-only declarations, see root_fwd.h.
 #pragma once
+#include "root_fwd.h"

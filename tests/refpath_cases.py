@@ -1,0 +1,97 @@
+"""Seeded inputs for the reference-host-path parity tests (tests/test_reference_path.py) and the script that makes
+their golden vectors (tests/golden/make_ref_host_path.py).  Per-event response functions in the shape MaCh3 hands to
+SMonolith's constructor (std::vector<std::vector<TResponseFunction_red*>>, Splines/SplineMonolith.cpp:36-49):
+TSpline3_red knots {x, y, b, c, d} and TF1_red {a, b}.  numpy's PCG64 streams are stable across versions."""
+import numpy as np
+
+
+def _knots(p, k, representable):
+    if representable:                     # multiples of 1/4: exact in float, the usual sigma grids
+        return (np.arange(k) - (k - 1) / 2.0) * (0.5 if k > 3 else 1.0)
+    lo, hi = -1.3 - 0.1 * p, 1.7 + 0.07 * p
+    return np.linspace(lo, hi, k)         # plain decimals: NOT exact in float
+
+
+def make_case(name):
+    """-> dict(type[P], npts[E,P], vals[sum,5], pars[T,P])"""
+    if name == "mixed":
+        E, P, n_tf1, cover, seed, flat = 600, 14, 4, 0.6, 11, False
+        K = [2, 3, 5, 7, 9, 4, 6, 8, 3, 5]
+    elif name == "flat":
+        E, P, n_tf1, cover, seed, flat = 400, 9, 2, 0.5, 12, True
+        K = [5, 3, 7, 4, 6, 2, 9]
+    elif name == "dense2":
+        E, P, n_tf1, cover, seed, flat = 300, 3, 0, 1.0, 13, False
+        K = [2, 2, 2]
+    else:
+        raise KeyError(name)
+    rng = np.random.default_rng(seed)
+    n_spl = P - n_tf1
+    typ = np.array([0] * n_spl + [1] * n_tf1, np.int32)
+    x_of = [_knots(p, K[p], representable=(p % 2 == 0)) for p in range(n_spl)]
+    dead = 3 if flat else -1                                   # a parameter no event responds to
+    npts = np.zeros((E, P), np.int32)
+    rows = []
+    for e in range(E):
+        for p in range(P):
+            has = (e == 0 or rng.random() < cover) and p != dead
+            if flat and e > 0 and e % 7 == 0:
+                has = False                                    # events without any response
+            if not has:
+                continue
+            if typ[p]:
+                npts[e, p] = 2
+                a, b = rng.normal(0.0, 0.05), 1.0 + rng.normal(0.0, 0.02)
+                rows.append(np.array([[0, a, 0, 0, 0], [0, b, 0, 0, 0]], np.float64))
+            elif flat and e > 0 and rng.random() < 0.15:
+                npts[e, p] = 1                                 # a one-knot ("flat") spline: skipped at :151
+                rows.append(np.array([[x_of[p][0], 1.0, 0, 0, 0]], np.float64))
+            else:
+                k = K[p]
+                npts[e, p] = k
+                r = np.zeros((k, 5))
+                r[:, 0] = x_of[p]
+                r[:, 1] = 1.0 + 0.15 * rng.normal(size=k)
+                r[:, 2] = 0.10 * rng.normal(size=k)
+                r[:, 3] = 0.05 * rng.normal(size=k)
+                r[:, 4] = 0.02 * rng.normal(size=k)
+                rows.append(r)
+    vals = np.concatenate(rows, 0)
+
+    # the proposals: a random walk (exercises the cached-segment shortcut) interleaved with boundary cases
+    T = 40
+    pars = np.zeros((T, P))
+    walk = np.zeros(P)
+    for t in range(1, T):
+        walk = walk + rng.normal(0.0, 0.6, P)
+        walk = np.clip(walk, -4.5, 4.5)
+        pars[t] = walk
+    def knot(p, k):
+        return x_of[p][min(k, len(x_of[p]) - 1)] if p < n_spl else 0.3
+    for p in range(P):
+        pars[5, p] = knot(p, 0)                                             # exactly the first knot
+        pars[9, p] = knot(p, 99)                                            # exactly the last knot
+        pars[13, p] = knot(p, 1)                                            # an interior knot (as a double)
+        pars[17, p] = float(np.float32(knot(p, 1)))                         # ... its float rounding
+        pars[21, p] = float(np.nextafter(np.float32(knot(p, 1)), np.float32(9)))    # one float ulp above
+        pars[25, p] = float(np.nextafter(np.float32(knot(p, 1)), np.float32(-9)))   # one float ulp below
+        pars[29, p] = -10.0 if p % 2 else 10.0                              # far outside the knots
+        pars[33, p] = knot(p, 2) + 1e-12                                    # a double hair above a knot
+    return dict(type=typ, npts=npts, vals=vals, pars=pars)
+
+
+CASES = ("mixed", "flat", "dense2")
+
+
+def stat_inputs():
+    """(data, mc, w2) triples for SampleHandlerBase::GetTestStatLLH: the branches around data == 0, mc == 0,
+    M3::_LOW_MC_BOUND_ (1e-5), w2 == 0, and ordinary bins.  128 = 2 x 64 so that the device test can give every
+    triple its own one-bin sample."""
+    rng = np.random.default_rng(5)
+    special = [(d, m) for d in (0.0, 1e-6, 1e-5, 2e-5, 1.0, 7.0, 250.0) for m in (0.0, 1e-7, 1e-5, 3e-5, 0.5, 7.0, 260.0)]
+    ns, nr = len(special), 128 - len(special)
+    data = np.array([s[0] for s in special] + list(rng.poisson(rng.uniform(0.1, 40.0, nr)).astype(float)))
+    mc = np.array([s[1] for s in special] + list(rng.uniform(0.05, 45.0, nr)))
+    w2 = np.concatenate([np.where(np.arange(ns) % 3 == 0, 0.0, mc[:ns] * rng.uniform(0.001, 0.5, ns)),
+                         mc[ns:] * rng.uniform(0.001, 0.2, nr)])
+    return data, mc, w2

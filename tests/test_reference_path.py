@@ -1,0 +1,196 @@
+"""Pins the HOST side of the path and the test statistics to the REFERENCE'S OWN CODE, run in this container:
+Splines/SplineMonolith.cpp (SMonolith: ScanMasterSpline, PrepareForGPU, CPU Evaluate = FindSplineSegment +
+CalcSplineWeights + CalcTotalEventWeight), Splines/SplineBase.cpp (FindSplineSegment) and
+Samples/SampleHandlerBase.cpp (GetTestStatLLH, GetPoissonLLH) were compiled from /root/reference where they lie
+(oracle/ref_host: stand-ins only for the absent ROOT/spdlog/yaml-cpp headers) and driven on the seeded inputs of
+tests/refpath_cases.py; the outputs are committed as tests/golden/ref_host_path.npz
+(generator: tests/golden/make_ref_host_path.py).
+  * CPU: the oracle, fed the monolith arrays THE REFERENCE BUILT, reproduces its segments, float parameter values
+    and per-event weights bit for bit over 40 proposals per case (history-dependent segment cache included), and
+    its five test statistics;
+  * live: where oracle/_ref/libm3ref_path.so exists the reference is re-run and must reproduce the vectors;
+  * GPU: libm3b200, fed the same arrays through m3b_upload_spline_monolith, gives the reference's segments and
+    per-event weights, and its device test statistics the reference's per-bin values."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refpath_cases as RC  # noqa: E402
+from oracle import binding as O
+from oracle import ref_path_binding as RP
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_host_path.npz")
+ARR = ("coeff_x", "coeff_many", "nKnots_arr", "paramNo_arr", "nParamPerEvent", "nParamPerEvent_tf1", "paramNo_tf1",
+       "coeff_tf1", "n_pts", "x_pts_f64")
+BOUNDARY_STEPS = (5, 9, 13, 17, 21, 25, 33)       # proposals placed on / one ulp off a knot (refpath_cases.make_case)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _arrays(g, name):
+    a = {k: g[f"{name}/arr/{k}"] for k in ARR}
+    a["n_events"] = int(g[f"{name}/sizes"][0])
+    return a
+
+
+def _oracle_monolith(g, name, double_knots=True):
+    a = _arrays(g, name)
+    P, K = int(g[f"{name}/sizes"][1]), int(g[f"{name}/sizes"][2])
+    m = O.SMonolith(P, K, a["coeff_x"], a["n_pts"], a)
+    if double_knots:
+        m.set_knots_f64(a["x_pts_f64"])
+    return m, a
+
+
+def _digest(c):
+    h = hashlib.sha256()
+    for k in ("type", "npts", "vals", "pars"):
+        h.update(np.ascontiguousarray(c[k]).tobytes())
+    return np.frombuffer(h.digest(), np.uint8)
+
+
+@pytest.mark.parametrize("name", RC.CASES)
+def test_inputs_are_the_ones_the_vectors_were_made_from(gold, name):
+    np.testing.assert_array_equal(_digest(RC.make_case(name)), gold[f"{name}/input_sha256"])
+
+
+@pytest.mark.parametrize("name", RC.CASES)
+def test_oracle_host_path_matches_reference_vectors(gold, name):
+    O.set_multithread(False)                       # the serial build: strict left-to-right float product
+    m, _ = _oracle_monolith(gold, name)
+    pars = RC.make_case(name)["pars"]
+    for t in range(pars.shape[0]):
+        m.set_params(pars[t])
+        m.Evaluate()
+        np.testing.assert_array_equal(m.segments, gold[f"{name}/segments"][t], err_msg=f"segments, step {t}")
+        np.testing.assert_array_equal(m.param_values, gold[f"{name}/param_values"][t])
+        np.testing.assert_array_equal(m.total_weights.view(np.uint32), gold[f"{name}/weights"][t].view(np.uint32),
+                                      err_msg=f"weights, step {t}")
+
+
+@pytest.mark.parametrize("name", RC.CASES)
+def test_float_knots_differ_from_double_knots_only_at_knot_boundaries(gold, name):
+    """coeff_x carries the knots as floats; FindSplineSegment compares against FastSplineInfo::xPts, doubles when the
+    monolith was built in-process.  With float knots (a monolith reloaded from file, or _LOW_MEMORY_STRUCTS_) the
+    segments can differ only where a proposal sits within a float ulp of a knot that is not exact in float."""
+    m, a = _oracle_monolith(gold, name, double_knots=False)
+    P, K = int(gold[f"{name}/sizes"][1]), int(gold[f"{name}/sizes"][2])
+    x = a["x_pts_f64"].reshape(P, K)
+    exact = np.array([np.array_equal(x[p], x[p].astype(np.float32).astype(np.float64)) for p in range(P)])
+    pars = RC.make_case(name)["pars"]
+    for t in range(pars.shape[0]):
+        m.set_params(pars[t])
+        m.FindSplineSegment()
+        diff = m.segments != gold[f"{name}/segments"][t]
+        assert not diff[exact].any()
+        if t not in BOUNDARY_STEPS:
+            assert not diff.any(), (t, np.nonzero(diff)[0])
+
+
+def test_oracle_test_statistics_match_reference(gold):
+    d, mc, w2 = gold["stat/data"], gold["stat/mc"], gold["stat/w2"]
+    d2, mc2, w22 = RC.stat_inputs()
+    np.testing.assert_array_equal(d, d2); np.testing.assert_array_equal(mc, mc2); np.testing.assert_array_equal(w2, w22)
+    for kind in range(5):
+        got = np.array([O.test_stat_llh(kind, d[i], mc[i], w2[i]) for i in range(d.size)])
+        np.testing.assert_allclose(got, gold[f"stat/llh{kind}"], rtol=1e-14, atol=1e-300, err_msg=f"test statistic {kind}")
+    np.testing.assert_array_equal(gold["stat/low_mc_bound"], [1e-5])
+    # kPoisson is GetPoissonLLH except that it guards data == 0 differently: both were recorded
+    assert np.isfinite(gold["stat/poisson"]).all()
+
+
+@pytest.mark.skipif(not RP.available(), reason="oracle/_ref/libm3ref_path.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", RC.CASES)
+def test_reference_rerun_reproduces_the_vectors(gold, name):
+    c = RC.make_case(name)
+    m = RP.RefSMonolith(c["type"], c["npts"], c["vals"])
+    try:
+        got = m.arrays()
+        for k in ARR:
+            np.testing.assert_array_equal(got[k], gold[f"{name}/arr/{k}"], err_msg=k)
+        for t in range(c["pars"].shape[0]):
+            w, s, v = m.evaluate(c["pars"][t])
+            np.testing.assert_array_equal(s, gold[f"{name}/segments"][t])
+            np.testing.assert_array_equal(v, gold[f"{name}/param_values"][t])
+            np.testing.assert_array_equal(w.view(np.uint32), gold[f"{name}/weights"][t].view(np.uint32))
+    finally:
+        m.close()
+
+
+@pytest.mark.skipif(not RP.available(), reason="oracle/_ref/libm3ref_path.so not built (needs /root/reference at build time)")
+def test_reference_rerun_reproduces_the_test_statistics(gold):
+    for kind in range(5):
+        v, thrown = RP.test_stat(kind, gold["stat/data"], gold["stat/mc"], gold["stat/w2"])
+        assert thrown == 0
+        np.testing.assert_array_equal(v, gold[f"stat/llh{kind}"])
+
+
+# ---- device -----------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", RC.CASES)
+def test_device_segments_and_weights_match_reference_host(gold, name):
+    """m3b_upload_spline_monolith consumes the arrays SMonolith::PrepareForGPU built (unused tail entries, padded
+    coeff_x rows, parameters without any spline included); per step the segments equal the reference's and the
+    per-event spline weight equals SMonolith::Evaluate's cpu_total_weights: same fmaf chain, same product order."""
+    from mach3_b200 import lib as L
+    a = _arrays(gold, name)
+    E, P, K = (int(v) for v in gold[f"{name}/sizes"][:3])
+    h = L.Handle(flags=L.FLAG_KEEP_EVENT_WEIGHTS)
+    h.upload_binning([[np.array([0.0, 1.0])]])
+    h.upload_spline_monolith(P, K, a["coeff_x"], a["n_pts"], a)
+    h.set_spline_knots_f64(a["x_pts_f64"])
+    h.upload_events(np.zeros(E, np.int32), np.full(E, 0.5))
+    pars = RC.make_case(name)["pars"]
+    worst = 0.0
+    for t in range(pars.shape[0]):
+        seg, val = h.find_segments(pars[t])
+        np.testing.assert_array_equal(seg, gold[f"{name}/segments"][t], err_msg=f"segments, step {t}")
+        np.testing.assert_array_equal(val, gold[f"{name}/param_values"][t])
+        h.step(pars[t])
+        h.llh()
+        sw, tw = h.read_event_weights()
+        ref = gold[f"{name}/weights"][t]
+        worst = max(worst, float(np.max(np.abs(sw - ref) / np.maximum(np.abs(ref), 1e-30))))
+        np.testing.assert_array_equal(sw.view(np.uint32), ref.view(np.uint32), err_msg=f"weights, step {t}")
+    assert worst <= 1e-5            # north_star's bound; the assertion above is the stronger, bit-exact one
+    h.close()
+
+
+@pytest.mark.gpu
+def test_device_test_statistics_match_reference(gold):
+    """Every (data, mc, w2) triple gets a one-bin sample of its own: the device's per-sample -lnL is the reference's
+    GetTestStatLLH of that bin.  The histogram is written straight into the device buffer (the multi-GPU entry point,
+    m3b_hist_device_ptr + m3b_llh_from_hist), so the statistics are tested on exactly the reference's inputs."""
+    import torch
+    from mach3_b200 import lib as L
+    from mach3_b200.sharding import _DevArray
+    d, mc, w2 = gold["stat/data"], gold["stat/mc"], gold["stat/w2"]
+    NS = 64
+    for kind in range(5):
+        h = L.Handle(test_statistic=kind, update_w2=True, flags=L.FLAG_NO_FUSED_LLH)
+        h.upload_binning([[np.array([0.0, 1.0])] for _ in range(NS)])
+        h.upload_events(np.arange(NS, dtype=np.int32), np.full(NS, 0.5))
+        for b in range(d.size // NS):
+            sl = slice(b * NS, (b + 1) * NS)
+            h.upload_data(d[sl])
+            h.step(np.zeros(0), mode="fill")
+            h.synchronize()
+            ptr, nb, live = h.hist_device_ptr()
+            assert nb == NS and live == 1
+            hist = torch.as_tensor(_DevArray(ptr, 2 * nb), device="cuda:0")
+            hist.copy_(torch.from_numpy(np.concatenate([mc[sl], w2[sl]])))
+            torch.cuda.synchronize()
+            h.llh_from_hist()
+            tot, per = h.llh(per_sample=True)
+            ref = gold[f"stat/llh{kind}"][sl]
+            # device log / lgamma are a few ulp off glibc's; north_star's bound on -lnL is 1e-6 relative
+            np.testing.assert_allclose(per, ref, rtol=1e-10, atol=1e-13, err_msg=f"test statistic {kind}, batch {b}")
+            assert tot == pytest.approx(ref.sum(), rel=1e-10)
+        h.close()
