@@ -61,9 +61,15 @@ def test_inputs_are_the_ones_the_vectors_were_made_from(gold, name):
     np.testing.assert_array_equal(_digest(RC.make_case(name)), gold[f"{name}/input_sha256"])
 
 
-@pytest.mark.parametrize("name", RC.CASES)
-def test_oracle_host_path_matches_reference_vectors(gold, name):
+@pytest.fixture
+def serial_oracle():
     O.set_multithread(False)                       # the serial build: strict left-to-right float product
+    yield
+    O.set_multithread(True)
+
+
+@pytest.mark.parametrize("name", RC.CASES)
+def test_oracle_host_path_matches_reference_vectors(gold, name, serial_oracle):
     m, _ = _oracle_monolith(gold, name)
     pars = RC.make_case(name)["pars"]
     for t in range(pars.shape[0]):
