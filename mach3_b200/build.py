@@ -89,7 +89,7 @@ def build_reference_gpu(force=False, verbose=False):
     # the reference's own (header-only) binning code behind a C ABI: pins the oracle's FindBin / non-uniform binning
     hmk = os.path.join(ORACLE, "ref_host", "Makefile")
     if os.path.exists(hmk):
-        _run(["make", "-C", os.path.dirname(hmk), "-B" if force else "-s"], verbose)
+        _run(["make", "-j4", "-C", os.path.dirname(hmk), "-B" if force else "-s"], verbose)
     # the drop-in SMonolithGPU adapter, compiled against the reference's own header + the same harness
     amk = os.path.join(ROOT, "adapters", "Makefile")
     if os.path.exists(amk):

@@ -136,8 +136,10 @@ class SampleHandlerFD:
     """Far-detector sample handler whose Reweight/GetLikelihood run as one fused device pass."""
 
     def __init__(self, edges, test_statistic=_lib.POISSON, update_w2=False, device=0, tile_events=0,
-                 keep_event_weights=False, fused_llh=True):
-        flags = (_lib.FLAG_KEEP_EVENT_WEIGHTS if keep_event_weights else 0) | (0 if fused_llh else _lib.FLAG_NO_FUSED_LLH)
+                 keep_event_weights=False, fused_llh=True, keep_kinematics=False):
+        """keep_kinematics: needed for handle.update_kinematics (functional shifts applied on the host)."""
+        flags = ((_lib.FLAG_KEEP_EVENT_WEIGHTS if keep_event_weights else 0) | (0 if fused_llh else _lib.FLAG_NO_FUSED_LLH)
+                 | (_lib.FLAG_KEEP_KINEMATICS if keep_kinematics else 0))
         self.handle = _lib.Handle(device=device, test_statistic=test_statistic, update_w2=update_w2,
                                   tile_events=tile_events, flags=flags)
         self.handle.upload_binning(edges)

@@ -12,16 +12,15 @@
  * load this library, and only as the checker or the timed CPU baseline.  The product
  * (mach3_b200/) never links, imports or calls it.
  *
- * PARITY PIN STATUS: the reference ships no tests, fixtures or golden vectors for this path
- *  and its host code cannot be built here (needs ROOT, yaml-cpp, spdlog).  The
- * spline-evaluation part (CalcSplineWeights + CalcTotalEventWeight) is pinned against the
- * reference's OWN CUDA kernels (Splines/gpuSplineUtils.cu compiled from /root/reference into
- * oracle/_ref, run on a B200; vectors committed under tests/golden/).  The binning part (FindBin,
- * bin-migration look-up, strides, InitNonUniform, InitialiseGridMapping, IsEventInside) is pinned against the
- * reference's OWN header Samples/SampleStructs.h compiled into oracle/_ref/libm3ref_host.so (oracle/ref_host,
- * vectors tests/golden/ref_host_binning.npz).  FindSplineSegment, CalcWeightTotal, FillArray, the test
- * statistics and BinnedSplineHandler::CalcSplineWeights are "parity unpinned": checked only against
- * known-answer tests derived from the formulas.
+ * PARITY PIN STATUS: pinned.  The reference ships no tests, fixtures or golden vectors for this path
+ *  and its own build system cannot run here, but its translation units of the path
+ * (Splines/SplineMonolith.cpp, SplineBase.cpp, BinnedSplineHandler.cpp, Samples/SampleHandlerFD.cpp,
+ * SampleHandlerBase.cpp, BinningHandler.cpp; Samples/SampleStructs.h; Splines/gpuSplineUtils.cu) compile from
+ * /root/reference with compile-only stand-ins for the absent ROOT / spdlog / yaml-cpp headers
+ * (oracle/ref_host, oracle/ref_gpu -> oracle/_ref/).  Their outputs on seeded inputs are committed under
+ * tests/golden/ (ref_host_path.npz, ref_host_fd.npz, ref_host_binning.npz, ref_gpu_weights.npz) with the
+ * generating scripts; this file reproduces them bit for bit in the serial build, in both M3::float_t builds
+ * (tests/test_reference_path.py, test_reference_host.py, test_reference_gpu.py).
  *
  * The data layout deliberately mirrors the reference (AoS {y,b,c,d} knots, {count,start}
  * CSR, one heap-allocated pointer vector per event) so that timing it is a fair stand-in

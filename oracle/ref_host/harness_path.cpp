@@ -168,3 +168,239 @@ REFP_API void refp_poisson(int n, const double* data, const double* mc, double* 
   for (int i = 0; i < n; ++i) out[i] = s.GetPoissonLLH(data[i], mc[i]);
 }
 REFP_API double refp_low_mc_bound() { return M3::_LOW_MC_BOUND_; }
+
+// ==================================================================================================================
+// SampleHandlerFD (Samples/SampleHandlerFD.cpp), BinningHandler (Samples/BinningHandler.cpp) and
+// BinnedSplineHandler (Splines/BinnedSplineHandler.cpp): the per-step part of the path run by THE REFERENCE'S CODE
+//   Reweight :316-343 -> ResetHistograms :442, SplineHandler->Evaluate(), FillArray :352-386
+//                        (ApplyShifts, IsEventSelected, CalcWeightTotal :568-596, BinningHandler::FindGlobalBin :257-291,
+//                        the `<= 0` skip, the W2 freeze FirstTimeW2/UpdateW2)
+//   GetLikelihood :1284-1300, GetSampleLikelihood :1262-1281, FindNominalBinAndEdges :858-887, SetSplinePointers
+//   :1196-1259 (monolith arm, _LOW_MEMORY_STRUCTS_ build), BinnedSplineHandler::Evaluate/CalcSplineWeights :295-341.
+// What a MaCh3 experiment supplies through YAML, ROOT files and its SampleHandlerFD subclass -- binning, events,
+// which parameters and weights every event points at -- is filled into the reference's own structures directly
+// (-fno-access-control); nothing of the configuration-time code is run.
+// ==================================================================================================================
+#include "Samples/SampleHandlerFD.h"
+#include "Splines/BinnedSplineHandler.h"
+
+// ---- link-time stand-ins for the four reference functions whose translation units need yaml-cpp / NuOscillator at
+//      run time (Manager.cpp, MaCh3Modes.cpp, OscillationHandler.cpp).  None is reached by the code driven here,
+//      except the Manager constructor, which SampleHandlerFD's constructor calls to read its YAML: here it reads nothing.
+Manager::Manager(std::string const& filename) { FileName = filename; }
+Manager::~Manager() {}
+std::string MaCh3Modes::GetMaCh3ModeName(const int) const { m3stub::no_root("MaCh3Modes"); }
+std::string MaCh3Modes::GetSplineSuffixFromMaCh3Mode(const int) { m3stub::no_root("MaCh3Modes"); }
+void OscillationHandler::Evaluate() { m3stub::no_root("OscillationHandler"); }
+const M3::float_t* OscillationHandler::GetNuOscillatorPointers(const int, const int, const int, const int, const FLOAT_T, const FLOAT_T) { m3stub::no_root("OscillationHandler"); }
+
+namespace {
+struct FD final : SampleHandlerFD {
+  std::vector<double> kin;          // [event][4]: what KinVar points at
+  std::vector<double> norm;         // what norm_pointers point at (ParameterHandler::_fPropVal)
+  std::vector<M3::float_t> pool;    // what total_weight_pointers point at (oscillation weights, extra weights)
+  Mono* mono = nullptr;             // spline parameters live with the spline handler
+  std::vector<double>* binned_pars = nullptr;
+  FD() : SampleHandlerFD("ref_host", nullptr, nullptr) {}
+  void CleanMemoryBeforeFit() override {}
+  void AddAdditionalWeightPointers() override {}
+  void SetupSplines() override {}
+  void Init() override {}
+  int SetupExperimentMC() override { return 0; }
+  void SetupFDMC() override {}
+  void RegisterFunctionalParameters() override {}
+  double ReturnKinematicParameter(std::string, int) override { return 0.0; }
+  double ReturnKinematicParameter(int, int) override { return 0.0; }
+  const double* GetPointerToKinematicParameter(std::string name, int iEvent) override { return &kin[size_t(iEvent) * 4 + size_t(name[1] - '0')]; }
+  const double* GetPointerToKinematicParameter(double, int) override { return nullptr; }
+};
+
+struct Binned final : BinnedSplineHandler {
+  std::vector<double> pars;
+  static ParameterHandlerGeneric* fake_xsec() { static ParameterHandlerGeneric x; return &x; }
+  // only stored by the constructor (Splines/BinnedSplineHandler.cpp:14-32), never dereferenced by Evaluate
+  static MaCh3Modes* fake_modes() { static long long blob[64]; return reinterpret_cast<MaCh3Modes*>(blob); }
+  Binned() : BinnedSplineHandler(fake_xsec(), fake_modes()) {}
+  std::vector<std::string> GetTokensFromSplineName(std::string) override { return {}; }
+};
+}  // namespace
+
+// samples: n_dim[s]; uniform[s]; uniform: nbins[4*s+d] + edges concatenated; non-uniform: nbins[4*s] boxes of n_dim {lo,hi}
+REFP_API void* refp_fd_create(int n_samples, const int* n_dim, const int* uniform, const int* nbins, const double* edges,
+                              int test_statistic, int update_w2) {
+  FD* fd = nullptr;
+  try {
+    fd = new FD();
+    fd->nSamples = M3::int_t(n_samples);
+    fd->SampleDetails.resize(n_samples);
+    const double* ep = edges;
+    for (int s = 0; s < n_samples; ++s) {
+      fd->SampleDetails[s].nDimensions = n_dim[s];
+      fd->SampleDetails[s].SampleTitle = "s" + std::to_string(s);
+      for (int d = 0; d < n_dim[s]; ++d) fd->SampleDetails[s].VarStr.push_back("v" + std::to_string(d));
+      SampleBinningInfo info;
+      if (uniform[s]) {
+        std::vector<std::vector<double>> e(n_dim[s]);
+        for (int d = 0; d < n_dim[s]; ++d) { e[d].assign(ep, ep + nbins[4 * s + d] + 1); ep += nbins[4 * s + d] + 1; }
+        info.InitUniform(e);
+      } else {
+        const int nb = nbins[4 * s];
+        std::vector<std::vector<std::vector<double>>> in(nb, std::vector<std::vector<double>>(n_dim[s], std::vector<double>(2)));
+        for (int b = 0; b < nb; ++b)
+          for (int d = 0; d < n_dim[s]; ++d) { in[b][d][0] = ep[0]; in[b][d][1] = ep[1]; ep += 2; }
+        info.InitNonUniform(in);
+      }
+      fd->Binning->SampleBinning.emplace_back(info);
+    }
+    fd->Binning->SetGlobalBinNumbers();
+    const int nb = fd->Binning->GetNBins();
+    fd->SampleHandlerFD_array.assign(nb, 0.0);
+    fd->SampleHandlerFD_array_w2.assign(nb, 0.0);
+    fd->SampleHandlerFD_data.assign(nb, 0.0);
+    fd->Selection.resize(n_samples);
+    fd->StoredSelection.resize(n_samples);
+    fd->SetTestStatistic(static_cast<TestStatistic>(test_statistic));
+    fd->UpdateW2 = update_w2 != 0;
+    fd->FirstTimeW2 = true;
+  } catch (...) { delete fd; return nullptr; }
+  return fd;
+}
+REFP_API void refp_fd_destroy(void* p) { delete static_cast<FD*>(p); }
+REFP_API int refp_fd_nbins(void* p) { return static_cast<FD*>(p)->Binning->GetNBins(); }
+REFP_API int refp_float_t_bytes() { return int(sizeof(M3::float_t)); }
+
+// The spline handler moves into the sample handler (std::unique_ptr<SplineBase> SplineHandler), as in
+// SampleHandlerFD::SetupSplines of an experiment.
+REFP_API void refp_fd_attach_monolith(void* p, void* mono) {
+  FD* fd = static_cast<FD*>(p);
+  fd->mono = static_cast<Mono*>(mono);
+  fd->SplineHandler.reset(fd->mono->m);
+  fd->mono->m = nullptr;                 // owned by the sample handler from here on
+}
+
+// BinnedSplineHandler with its monolith arrays handed over as they stand after FillSampleArray / TransferToMonolith.
+REFP_API void* refp_fd_attach_binned(void* p, int P, int max_knots, const double* knot_x, const int16_t* n_pts,
+                                     int64_t n_slots, const int* uniquesplinevec, const int* coeffindexvec,
+                                     int64_t n_unique, const int* uniquecoeffindices, int64_t n_coeff,
+                                     const double* manycoeff, const double* xcoeff) {
+  FD* fd = static_cast<FD*>(p);
+  Binned* b = new Binned();
+  b->nParams = short(P);
+  b->SplineSegments = new short int[P]();
+  b->ParamValues = new float[P]();
+  b->pars.assign(P, 0.0);
+  b->SplineInfoArray.resize(P);
+  for (int i = 0; i < P; ++i) {
+    b->SplineInfoArray[i].nPts = M3::int_t(n_pts[i]);
+    b->SplineInfoArray[i].xPts.assign(n_pts[i] > 0 ? size_t(n_pts[i]) : 0, M3::float_t(0));
+    for (int k = 0; k < n_pts[i]; ++k) b->SplineInfoArray[i].xPts[k] = M3::float_t(knot_x[size_t(i) * max_knots + k]);
+    b->SplineInfoArray[i].CurrSegment = 0;
+    b->SplineInfoArray[i].splineParsPointer = &b->pars[i];
+  }
+  b->uniquesplinevec_Monolith.assign(uniquesplinevec, uniquesplinevec + n_slots);
+  b->coeffindexvec.assign(coeffindexvec, coeffindexvec + n_slots);
+  b->uniquecoeffindices.assign(uniquecoeffindices, uniquecoeffindices + n_unique);
+  b->weightvec_Monolith.assign(size_t(n_slots), M3::float_t(1));        // flat slots stay 1 (.cpp:672)
+  b->xcoeff_arr = new M3::float_t[size_t(n_coeff)];
+  b->manycoeff_arr = new M3::float_t[size_t(n_coeff) * 4];
+  for (int64_t i = 0; i < n_coeff; ++i) b->xcoeff_arr[i] = M3::float_t(xcoeff[i]);
+  for (int64_t i = 0; i < n_coeff * 4; ++i) b->manycoeff_arr[i] = M3::float_t(manycoeff[i]);
+  fd->binned_pars = &b->pars;
+  fd->SplineHandler.reset(b);
+  return b;
+}
+
+// Events.  Weight pointers are pushed in the reference's order (SampleHandlerFD::Initialise :169-202):
+//   w_before (oscillation weight; SetupOscParameters) -> spline weights (SetSplinePointers) -> w_after (extras).
+// w_before / w_after: [n_events * n_*] indices into the M3::float_t pool, -1 = none.
+// monolith: the reference's own SetSplinePointers() wires SMonolith::retPointer(event) (_LOW_MEMORY_STRUCTS_ only);
+// binned: slot indices per event (CSR binned_start[n_events+1], binned_slot[]) -> &weightvec_Monolith[slot].
+REFP_API int refp_fd_set_events(void* p, int n_events, const int* sample_id, const double* kin /* [n_events][4] */,
+                                int n_norm_per_event, const int16_t* norm_idx, int n_norm_values,
+                                int n_before, const int* w_before, int n_after, const int* w_after, int n_pool,
+                                const int64_t* binned_start, const int* binned_slot) {
+  FD* fd = static_cast<FD*>(p);
+  try {
+    fd->nEvents = unsigned(n_events);
+    fd->kin.assign(kin, kin + size_t(n_events) * 4);
+    fd->norm.assign(size_t(n_norm_values > 0 ? n_norm_values : 1), 1.0);
+    fd->pool.assign(size_t(n_pool > 0 ? n_pool : 1), M3::float_t(1));
+    fd->MCSamples = std::vector<EventInfo>(size_t(n_events));
+    fd->funcParsGrid.assign(size_t(n_events), {});
+    for (int e = 0; e < n_events; ++e) {
+      EventInfo& ev = fd->MCSamples[e];
+      ev.NominalSample = sample_id[e];
+      for (int k = 0; k < n_norm_per_event; ++k) {
+        const int16_t i = norm_idx[size_t(e) * n_norm_per_event + k];
+        if (i >= 0) ev.norm_pointers.push_back(&fd->norm[i]);
+      }
+      for (int k = 0; k < n_before; ++k) {
+        const int i = w_before[size_t(e) * n_before + k];
+        if (i >= 0) ev.total_weight_pointers.push_back(&fd->pool[i]);
+      }
+    }
+    fd->FindNominalBinAndEdges();                             // the reference's own (KinVar pointers, NomBin)
+    if (fd->mono) {
+      fd->SetSplinePointers();                                // the reference's own; throws in the double build
+    } else if (binned_start) {
+      Binned* b = static_cast<Binned*>(fd->SplineHandler.get());
+      for (int e = 0; e < n_events; ++e)
+        for (int64_t k = binned_start[e]; k < binned_start[e + 1]; ++k)
+          fd->MCSamples[e].total_weight_pointers.push_back(&b->weightvec_Monolith[binned_slot[k]]);
+    }
+    for (int e = 0; e < n_events; ++e)
+      for (int k = 0; k < n_after; ++k) {
+        const int i = w_after[size_t(e) * n_after + k];
+        if (i >= 0) fd->MCSamples[e].total_weight_pointers.push_back(&fd->pool[i]);
+      }
+  } catch (...) { return 1; }
+  return 0;
+}
+
+REFP_API void refp_fd_set_data(void* p, const double* data) {
+  FD* fd = static_cast<FD*>(p);
+  std::copy(data, data + fd->SampleHandlerFD_data.size(), fd->SampleHandlerFD_data.begin());
+}
+// shifted kinematics (what functional parameters write): same storage, the nominal bins stay
+REFP_API void refp_fd_set_kin(void* p, const double* kin) {
+  FD* fd = static_cast<FD*>(p);
+  std::copy(kin, kin + fd->kin.size(), fd->kin.begin());
+}
+REFP_API void refp_fd_set_test_statistic(void* p, int kind) { static_cast<FD*>(p)->SetTestStatistic(static_cast<TestStatistic>(kind)); }
+
+// one step: the values every pointer looks at, then SampleHandlerFD::Reweight()
+REFP_API int refp_fd_reweight(void* p, const double* spline_pars, const double* norm, const double* pool) {
+  FD* fd = static_cast<FD*>(p);
+  if (spline_pars && fd->mono) for (size_t i = 0; i < fd->mono->pars.size(); ++i) fd->mono->pars[i] = spline_pars[i];
+  if (spline_pars && fd->binned_pars) for (size_t i = 0; i < fd->binned_pars->size(); ++i) (*fd->binned_pars)[i] = spline_pars[i];
+  if (norm) std::copy(norm, norm + fd->norm.size(), fd->norm.begin());
+  if (pool) for (size_t i = 0; i < fd->pool.size(); ++i) fd->pool[i] = M3::float_t(pool[i]);
+  try { fd->Reweight(); } catch (...) { return 1; }
+  return 0;
+}
+REFP_API double refp_fd_llh(void* p) { return static_cast<FD*>(p)->GetLikelihood(); }
+REFP_API double refp_fd_sample_llh(void* p, int s) { return static_cast<FD*>(p)->GetSampleLikelihood(s); }
+REFP_API void refp_fd_read(void* p, double* mc, double* w2) {
+  FD* fd = static_cast<FD*>(p);
+  std::copy(fd->SampleHandlerFD_array.begin(), fd->SampleHandlerFD_array.end(), mc);
+  std::copy(fd->SampleHandlerFD_array_w2.begin(), fd->SampleHandlerFD_array_w2.end(), w2);
+}
+// per event: CalcWeightTotal and FindGlobalBin as FillArray calls them
+REFP_API void refp_fd_events(void* p, double* weight, int* bin) {
+  FD* fd = static_cast<FD*>(p);
+  for (unsigned e = 0; e < fd->nEvents; ++e) {
+    const EventInfo* ev = &fd->MCSamples[e];
+    if (weight) weight[e] = double(fd->CalcWeightTotal(ev));
+    if (bin) bin[e] = fd->Binning->FindGlobalBin(ev->NominalSample, ev->KinVar, ev->NomBin);
+  }
+}
+REFP_API int64_t refp_fd_binned_weights(void* p, double* out) {
+  Binned* b = dynamic_cast<Binned*>(static_cast<FD*>(p)->SplineHandler.get());
+  if (!b) return -1;
+  if (out) for (size_t i = 0; i < b->weightvec_Monolith.size(); ++i) out[i] = double(b->weightvec_Monolith[i]);
+  return int64_t(b->weightvec_Monolith.size());
+}
+REFP_API void refp_fd_segments(void* p, int16_t* out) {
+  SplineBase* s = static_cast<FD*>(p)->SplineHandler.get();
+  if (s) std::memcpy(out, s->SplineSegments, size_t(s->nParams) * sizeof(short));
+}

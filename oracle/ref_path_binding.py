@@ -12,18 +12,43 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libm3ref_path.so")
-_L = None
+LIB_PATH = os.path.join(_HERE, "_ref", "libm3ref_path.so")          # default build: M3::float_t = double
+LIB_PATH_LM = os.path.join(_HERE, "_ref", "libm3ref_path_lm.so")    # -D_LOW_MEMORY_STRUCTS_: M3::float_t = float
+_LIBS = {}
 
 
 def available():
-    return os.path.exists(LIB_PATH)
+    return os.path.exists(LIB_PATH) and os.path.exists(LIB_PATH_LM)
 
 
-def lib():
-    global _L
-    if _L is None:
-        L = C.CDLL(LIB_PATH)
+def lib(build="double"):
+    """build: "double" (the reference's default) or "float" (_LOW_MEMORY_STRUCTS_)."""
+    if build not in _LIBS:
+        L = C.CDLL(LIB_PATH if build == "double" else LIB_PATH_LM)
+        assert L.refp_float_t_bytes() == (8 if build == "double" else 4)
+        L.refp_fd_create.restype = C.c_void_p
+        L.refp_fd_create.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int]
+        L.refp_fd_destroy.argtypes = [C.c_void_p]
+        L.refp_fd_nbins.argtypes = [C.c_void_p]
+        L.refp_fd_attach_monolith.argtypes = [C.c_void_p, C.c_void_p]
+        L.refp_fd_attach_binned.restype = C.c_void_p
+        L.refp_fd_attach_binned.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.refp_fd_set_events.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.refp_fd_set_data.argtypes = [C.c_void_p, C.c_void_p]
+        L.refp_fd_set_kin.argtypes = [C.c_void_p, C.c_void_p]
+        L.refp_fd_set_test_statistic.argtypes = [C.c_void_p, C.c_int]
+        L.refp_fd_reweight.argtypes = [C.c_void_p] * 4
+        L.refp_fd_llh.restype = C.c_double
+        L.refp_fd_llh.argtypes = [C.c_void_p]
+        L.refp_fd_sample_llh.restype = C.c_double
+        L.refp_fd_sample_llh.argtypes = [C.c_void_p, C.c_int]
+        L.refp_fd_read.argtypes = [C.c_void_p] * 3
+        L.refp_fd_events.argtypes = [C.c_void_p] * 3
+        L.refp_fd_binned_weights.restype = C.c_int64
+        L.refp_fd_binned_weights.argtypes = [C.c_void_p, C.c_void_p]
+        L.refp_fd_segments.argtypes = [C.c_void_p, C.c_void_p]
         L.refp_mono_create.restype = C.c_void_p
         L.refp_mono_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refp_mono_destroy.argtypes = [C.c_void_p]
@@ -34,8 +59,8 @@ def lib():
         L.refp_test_stat.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4
         L.refp_poisson.argtypes = [C.c_int] + [C.c_void_p] * 3
         L.refp_low_mc_bound.restype = C.c_double
-        _L = L
-    return _L
+        _LIBS[build] = L
+    return _LIBS[build]
 
 
 def _p(a):
@@ -53,8 +78,8 @@ class RefSMonolith:
     type[P]: 0 TSpline3_red, 1 TF1_red.  npts[n_events, P]: knots (0: the event has no response to the parameter).
     vals[total_knots, 5] = {x, y, b, c, d} per knot in (event, parameter, knot) order; TF1: column 1 = coefficient."""
 
-    def __init__(self, type_, npts, vals):
-        L = lib()
+    def __init__(self, type_, npts, vals, build="double"):
+        L = self.L = lib(build)
         self.type = np.ascontiguousarray(type_, np.int32)
         npts = np.ascontiguousarray(npts, np.int32)
         vals = np.ascontiguousarray(vals, np.float64)
@@ -71,7 +96,7 @@ class RefSMonolith:
     def arrays(self):
         """The monolith arrays exactly as SMonolith::PrepareForGPU left them (the arguments of
         SMonolithGPU::CopyToGPU_SplineMonolith, and of m3b_upload_spline_monolith)."""
-        L = lib()
+        L = self.L
         out = {}
         for which, (name, dt) in enumerate(_ARRAYS):
             n = L.refp_mono_array(self.h, which, None)
@@ -87,13 +112,134 @@ class RefSMonolith:
         w = np.zeros(self.NEvents, np.float32)
         seg = np.zeros(self.nParams, np.int16)
         val = np.zeros(self.nParams, np.float32)
-        if lib().refp_mono_evaluate(self.h, _p(pars), _p(w), _p(seg), _p(val)):
+        if self.L.refp_mono_evaluate(self.h, _p(pars), _p(w), _p(seg), _p(val)):
             raise RuntimeError("the reference threw in SMonolith::Evaluate")
         return w, seg, val
 
     def close(self):
         if self.h:
-            lib().refp_mono_destroy(self.h)
+            self.L.refp_mono_destroy(self.h)
+            self.h = None
+
+
+class RefSampleHandlerFD:
+    """The reference's SampleHandlerFD (+ BinningHandler) filled directly with a binning, events and their pointers;
+    Reweight() / GetLikelihood() are the reference's own.  edges: list over samples -- a list over dims of edge arrays
+    (uniform) or an array [n_boxes, n_dim, 2] (non-uniform).  build "float" is the only one in which SMonolith can be
+    attached (Samples/SampleHandlerFD.cpp:1244-1254)."""
+
+    def __init__(self, edges, test_statistic=0, update_w2=False, build="double"):
+        self.L = lib(build)
+        self.build = build
+        ns = len(edges)
+        ndim, uniform, nbins, flat = np.zeros(ns, np.int32), np.ones(ns, np.int32), np.zeros(ns * 4, np.int32), []
+        for s_, dims in enumerate(edges):
+            if isinstance(dims, np.ndarray) and dims.ndim == 3:
+                uniform[s_], ndim[s_], nbins[4 * s_] = 0, dims.shape[1], dims.shape[0]
+                flat.append(np.asarray(dims, np.float64).reshape(-1))
+                continue
+            ndim[s_] = len(dims)
+            for d, e in enumerate(dims):
+                nbins[4 * s_ + d] = len(e) - 1
+                flat.append(np.asarray(e, np.float64))
+        flat = np.ascontiguousarray(np.concatenate(flat))
+        self.ndim = ndim
+        self.h = self.L.refp_fd_create(ns, _p(ndim), _p(uniform), _p(nbins), _p(flat), int(test_statistic), int(update_w2))
+        if not self.h:
+            raise RuntimeError("the reference rejected this binning (MaCh3Exception)")
+        self.n_samples = ns
+        self.n_bins = self.L.refp_fd_nbins(self.h)
+        self.mono = None
+
+    def attach_monolith(self, mono: RefSMonolith):
+        assert self.build == "float" and mono.L is self.L
+        self.L.refp_fd_attach_monolith(self.h, mono.h)
+        self.mono = mono          # its SMonolith now belongs to the sample handler
+
+    def attach_binned(self, spl):
+        """spl: the dict of mach3_b200.synth.binned.make_binned_splines (the reference's monolith arrays)."""
+        k = [np.ascontiguousarray(spl["knot_x"], np.float64), np.ascontiguousarray(spl["n_pts"], np.int16),
+             np.ascontiguousarray(spl["uniquesplinevec_Monolith"], np.int32), np.ascontiguousarray(spl["coeffindexvec"], np.int32),
+             np.ascontiguousarray(spl["uniquecoeffindices"], np.int32), np.ascontiguousarray(spl["manycoeff_arr"], np.float64),
+             np.ascontiguousarray(spl["xcoeff_arr"], np.float64)]
+        self.n_slots = k[2].size
+        self.n_params = int(spl["n_params"])
+        self.L.refp_fd_attach_binned(self.h, self.n_params, int(spl["max_knots"]), _p(k[0]), _p(k[1]), k[2].size, _p(k[2]),
+                                     _p(k[3]), k[4].size, _p(k[4]), k[6].size, _p(k[5]), _p(k[6]))
+
+    def set_events(self, sample_id, kin, norm_idx=None, n_norm_per_event=0, n_norm_values=0, w_before=None, w_after=None,
+                   n_pool=0, binned_n_per_event=None, binned_slot=None):
+        """kin: [max_dim, n_events] (the layout of m3b_upload_events); w_before / w_after: [n_events, k] pool indices."""
+        sid = np.ascontiguousarray(sample_id, np.int32)
+        E = self.n_events = sid.size
+        kin = np.asarray(kin, np.float64).reshape(-1, E)
+        k4 = np.zeros((E, 4), np.float64)
+        k4[:, :kin.shape[0]] = kin.T
+        ni = None if norm_idx is None else np.ascontiguousarray(norm_idx, np.int16)
+        wb = None if w_before is None else np.ascontiguousarray(np.asarray(w_before, np.int32).reshape(E, -1))
+        wa = None if w_after is None else np.ascontiguousarray(np.asarray(w_after, np.int32).reshape(E, -1))
+        bs = bi = None
+        if binned_n_per_event is not None:
+            bs = np.zeros(E + 1, np.int64)
+            bs[1:] = np.cumsum(np.asarray(binned_n_per_event, np.int64))
+            bi = np.ascontiguousarray(binned_slot, np.int32)
+        self._keep = (sid, k4, ni, wb, wa, bs, bi)
+        rc = self.L.refp_fd_set_events(self.h, E, _p(sid), _p(k4), int(n_norm_per_event if ni is not None else 0),
+                                       None if ni is None else _p(ni), int(n_norm_values),
+                                       0 if wb is None else wb.shape[1], None if wb is None else _p(wb),
+                                       0 if wa is None else wa.shape[1], None if wa is None else _p(wa), int(n_pool),
+                                       None if bs is None else _p(bs), None if bi is None else _p(bi))
+        if rc:
+            raise RuntimeError("the reference threw while wiring the events")
+
+    def set_kin(self, kin):
+        kin = np.asarray(kin, np.float64).reshape(-1, self.n_events)
+        k4 = np.zeros((self.n_events, 4), np.float64)
+        k4[:, :kin.shape[0]] = kin.T
+        self.L.refp_fd_set_kin(self.h, _p(k4))
+
+    def set_data(self, data):
+        d = np.ascontiguousarray(data, np.float64)
+        assert d.size == self.n_bins
+        self.L.refp_fd_set_data(self.h, _p(d))
+
+    def set_test_statistic(self, kind):
+        self.L.refp_fd_set_test_statistic(self.h, int(kind))
+
+    def reweight(self, spline_pars=None, norm=None, pool=None):
+        a = [None if v is None else np.ascontiguousarray(v, np.float64) for v in (spline_pars, norm, pool)]
+        if self.L.refp_fd_reweight(self.h, *[None if v is None else _p(v) for v in a]):
+            raise RuntimeError("the reference threw in SampleHandlerFD::Reweight")
+
+    def llh(self):
+        return self.L.refp_fd_llh(self.h)
+
+    def sample_llh(self):
+        return np.array([self.L.refp_fd_sample_llh(self.h, s_) for s_ in range(self.n_samples)])
+
+    def hist(self):
+        mc, w2 = np.zeros(self.n_bins), np.zeros(self.n_bins)
+        self.L.refp_fd_read(self.h, _p(mc), _p(w2))
+        return mc, w2
+
+    def events(self):
+        w, b = np.zeros(self.n_events), np.zeros(self.n_events, np.int32)
+        self.L.refp_fd_events(self.h, _p(w), _p(b))
+        return w, b
+
+    def binned_weights(self):
+        out = np.zeros(self.n_slots)
+        self.L.refp_fd_binned_weights(self.h, _p(out))
+        return out
+
+    def segments(self, n_params):
+        out = np.zeros(n_params, np.int16)
+        self.L.refp_fd_segments(self.h, _p(out))
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.refp_fd_destroy(self.h)
             self.h = None
 
 

@@ -95,3 +95,48 @@ def stat_inputs():
     w2 = np.concatenate([np.where(np.arange(ns) % 3 == 0, 0.0, mc[:ns] * rng.uniform(0.001, 0.5, ns)),
                          mc[ns:] * rng.uniform(0.001, 0.2, nr)])
     return data, mc, w2
+
+
+# ---- the full per-step path: SampleHandlerFD::Reweight + GetLikelihood over the "mixed" monolith --------------------
+FD_STEPS = 12
+N_NORM = 6
+NPE = 3
+
+
+def fd_edges():
+    """Three samples: 1-D uniform, 2-D uniform, 2-D non-uniform boxes (with a gap and an overlap-free L shape)."""
+    boxes = np.array([[[0.0, 1.0], [0.0, 1.0]], [[1.0, 2.5], [0.0, 0.5]], [[1.0, 2.5], [0.5, 1.0]],
+                      [[0.0, 0.7], [1.0, 2.0]], [[0.7, 2.5], [1.0, 2.0]], [[2.7, 3.0], [0.0, 2.0]]])
+    return [[np.linspace(0.0, 3.0, 13)], [np.array([0.0, 0.4, 0.9, 1.5, 2.2, 3.0]), np.linspace(0.0, 2.0, 5)], boxes]
+
+
+def fd_case():
+    """Events for make_case("mixed"): sample, kinematics (some outside every bin, some on edges), up to NPE norm
+    pointers, an oscillation weight and a static weight per event (a few zero / negative: the `<= 0` skip),
+    FD_STEPS proposals, and one set of shifted kinematics (what functional parameters would write)."""
+    c = make_case("mixed")
+    E = c["npts"].shape[0]
+    rng = np.random.default_rng(21)
+    sample_id = rng.integers(0, 3, E).astype(np.int32)
+    kin = np.zeros((2, E))
+    kin[0] = rng.uniform(-0.2, 3.2, E)
+    kin[1] = rng.uniform(-0.1, 2.1, E)
+    on_edge = rng.integers(0, E, 40)
+    kin[0, on_edge] = np.linspace(0.0, 3.0, 13)[rng.integers(0, 13, 40)]
+    norm_idx = rng.integers(-1, N_NORM, (E, NPE)).astype(np.int16)
+    static_w = rng.uniform(0.5, 1.5, E).astype(np.float32)
+    static_w[rng.integers(0, E, 9)] = 0.0
+    static_w[rng.integers(0, E, 5)] = -0.3
+    osc = rng.random((FD_STEPS, E)).astype(np.float32)
+    norm = np.clip(rng.normal(1.0, 0.1, (FD_STEPS, N_NORM)), 0.5, 1.5)
+    kin_shift = kin + rng.normal(0.0, 0.08, kin.shape)
+    return dict(mono=c, sample_id=sample_id, kin=kin, kin_shift=kin_shift, norm_idx=norm_idx, static_w=static_w,
+                osc=osc, norm=norm, pars=c["pars"][[0, 1, 2, 5, 9, 13, 17, 21, 25, 29, 33, 38]])
+
+
+def binned_workload():
+    from mach3_b200.synth import binned as B
+    return B.CFG4_SMALL.scaled(n_events=4000, n_grid=150)
+
+
+BINNED_STEPS = (-1, 0, 1, 2, -2, -3, -4, 3)

@@ -200,3 +200,149 @@ def test_device_test_statistics_match_reference(gold):
             np.testing.assert_allclose(per, ref, rtol=1e-10, atol=1e-13, err_msg=f"test statistic {kind}, batch {b}")
             assert tot == pytest.approx(ref.sum(), rel=1e-10)
         h.close()
+
+
+# =====================================================================================================================
+# The full per-step path against the reference's own SampleHandlerFD::Reweight / GetLikelihood
+# (tests/golden/ref_host_fd.npz, generator tests/golden/make_ref_host_fd.py; both reference builds)
+# =====================================================================================================================
+GOLD_FD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_host_fd.npz")
+BARLOW_BEESTON = 1
+
+
+@pytest.fixture(scope="module")
+def gold_fd():
+    return np.load(GOLD_FD)
+
+
+@pytest.mark.parametrize("update_w2", [False, True])
+def test_oracle_full_path_matches_reference_sample_handler(gold, gold_fd, update_w2, serial_oracle):
+    """Monolith + SampleHandlerFD, _LOW_MEMORY_STRUCTS_ build (the only one that wires SMonolith in): per-event
+    CalcWeightTotal, FindGlobalBin (three binnings, events outside / on edges, shifted kinematics with stale nominal
+    bins), the `<= 0` skip, the W2 freeze and Barlow-Beeston -lnL, step by step."""
+    tag = f"mono_w2{int(update_w2)}"
+    f = RC.fd_case()
+    E = f["sample_id"].size
+    mono, a = _oracle_monolith(gold, "mixed", double_knots=False)       # float build: FastSplineInfo::xPts are floats
+    sh = O.SampleHandlerFD(E, RC.fd_edges(), BARLOW_BEESTON, update_w2)
+    assert sh.n_bins == int(gold_fd[f"{tag}/n_bins"][0])
+    norm, osc = np.ones(RC.N_NORM), np.ones(E, np.float32)
+    sh.set_events(f["sample_id"], f["kin"].reshape(-1).copy(), f["norm_idx"].reshape(-1), RC.NPE, norm, osc, mono, f["static_w"])
+    for t in range(RC.FD_STEPS):
+        if t == 8:
+            sh._keep[1][:] = f["kin_shift"].reshape(-1)           # the KinVar pointers look into this array
+        mono.set_params(f["pars"][t]); sh.norm_vals[:] = f["norm"][t]; sh.osc_w[:] = f["osc"][t]
+        sh.Reweight()
+        if t == 0:
+            sh.AddData(gold_fd[f"{tag}/data"])
+        np.testing.assert_array_equal(mono.segments, gold_fd[f"{tag}/segments"][t])
+        np.testing.assert_array_equal(sh.event_bins(), gold_fd[f"{tag}/event_bin"][t], err_msg=f"bins, step {t}")
+        np.testing.assert_array_equal(sh.event_weights().view(np.uint32), gold_fd[f"{tag}/event_w"][t].view(np.uint32),
+                                      err_msg=f"event weights, step {t}")
+        np.testing.assert_array_equal(sh.mc, gold_fd[f"{tag}/mc"][t], err_msg=f"mc, step {t}")          # same summation order
+        np.testing.assert_array_equal(sh.w2, gold_fd[f"{tag}/w2"][t], err_msg=f"w2, step {t}")
+        assert sh.GetLikelihood() == pytest.approx(float(gold_fd[f"{tag}/llh"][t]), rel=1e-14)
+        got = np.array([sh.GetSampleLikelihood(s) for s in range(3)])
+        np.testing.assert_allclose(got, gold_fd[f"{tag}/sample_llh"][t], rtol=1e-14)
+
+
+@pytest.mark.parametrize("build", ["float", "double"])
+def test_oracle_binned_path_matches_reference_sample_handler(gold_fd, build, serial_oracle):
+    """BinnedSplineHandler::Evaluate (segments, weightvec_Monolith incl. the clamp at 0) + SampleHandlerFD in both
+    reference builds: M3::float_t = float and the default double."""
+    from mach3_b200.synth import binned as B
+    tag = f"binned_{build}"
+    w = RC.binned_workload()
+    f64 = build == "double"
+    b, sh, d = O.build_binned_from_workload(w, update_w2=True, test_statistic=BARLOW_BEESTON, f64=f64)
+    for i, step in enumerate(RC.BINNED_STEPS):
+        sp, nm = B.proposal(w, step)
+        b.set_params(sp); sh.norm_vals[:] = nm; sh.osc_w[:] = B.make_osc(w, max(step, 0), f64=f64)
+        sh.Reweight()
+        if i == 0:
+            sh.AddData(gold_fd[f"{tag}/data"])
+        np.testing.assert_array_equal(b.segments, gold_fd[f"{tag}/segments"][i])
+        np.testing.assert_array_equal(b.weights, gold_fd[f"{tag}/slot_w"][i], err_msg=f"weightvec_Monolith, step {step}")
+        np.testing.assert_array_equal(sh.event_weights(), gold_fd[f"{tag}/event_w"][i], err_msg=f"event weights, step {step}")
+        np.testing.assert_array_equal(sh.mc, gold_fd[f"{tag}/mc"][i])
+        np.testing.assert_array_equal(sh.w2, gold_fd[f"{tag}/w2"][i])
+        assert sh.GetLikelihood() == pytest.approx(float(gold_fd[f"{tag}/llh"][i]), rel=1e-14)
+
+
+@pytest.mark.skipif(not RP.available(), reason="oracle/_ref/libm3ref_path*.so not built (needs /root/reference at build time)")
+def test_reference_rerun_reproduces_the_sample_handler_vectors(gold_fd):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_ref_host_fd as G
+    out = {}
+    G.run_monolith(out, False); G.run_monolith(out, True); G.run_binned(out, "float"); G.run_binned(out, "double")
+    assert set(out) == set(gold_fd.files)
+    for k, v in out.items():
+        np.testing.assert_array_equal(np.asarray(v), gold_fd[k], err_msg=k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("update_w2", [False, True])
+def test_device_full_path_matches_reference_sample_handler(gold, gold_fd, update_w2):
+    """libm3b200's fused step against the reference's SampleHandlerFD::Reweight + GetLikelihood: bins and per-event
+    weights bit for bit, histograms to 1e-12 (f64 atomics reorder the sum), -lnL to 1e-10."""
+    from mach3_b200 import handlers
+    tag = f"mono_w2{int(update_w2)}"
+    f = RC.fd_case()
+    E = f["sample_id"].size
+    a = _arrays(gold, "mixed")
+    P, K = int(gold["mixed/sizes"][1]), int(gold["mixed/sizes"][2])
+    sh = handlers.SampleHandlerFD(RC.fd_edges(), BARLOW_BEESTON, update_w2, keep_event_weights=True, keep_kinematics=True)
+    sh.SetupSplines(P, K, a["coeff_x"], a["n_pts"], a)               # float build: the float knots of coeff_x
+    pars, norm, osc = np.zeros(P), np.ones(RC.N_NORM), np.ones(E, np.float32)
+    sh.SetupEvents(f["sample_id"], f["kin"].reshape(-1), f["norm_idx"].reshape(-1), RC.NPE, norm, osc, None, f["static_w"])
+    sh.SetSplinePointers(pars)
+    assert sh.n_bins == int(gold_fd[f"{tag}/n_bins"][0])
+    for t in range(RC.FD_STEPS):
+        if t == 8:
+            sh.handle.update_kinematics(f["kin_shift"].reshape(-1))
+        pars[:] = f["pars"][t]; norm[:] = f["norm"][t]; osc[:] = f["osc"][t]
+        sh.OscillatorEvaluated()
+        sh.Reweight()
+        if t == 0:
+            sh.GetLikelihood()
+            sh.AddData(gold_fd[f"{tag}/data"])
+        llh = sh.GetLikelihood()
+        np.testing.assert_array_equal(sh.handle.read_event_bins(), gold_fd[f"{tag}/event_bin"][t], err_msg=f"bins, step {t}")
+        sw, tw = sh.handle.read_event_weights()
+        ref_w = gold_fd[f"{tag}/event_w"][t]
+        live = ref_w > 0                                        # skipped events: the device leaves w <= 0 as computed
+        np.testing.assert_array_equal(tw[live].view(np.uint32), ref_w[live].view(np.uint32), err_msg=f"event weights, step {t}")
+        mc, w2 = sh.handle.read_hist()
+        np.testing.assert_allclose(mc, gold_fd[f"{tag}/mc"][t], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(w2, gold_fd[f"{tag}/w2"][t], rtol=1e-12, atol=1e-13)
+        if t > 0:
+            assert llh == pytest.approx(float(gold_fd[f"{tag}/llh"][t]), rel=1e-10)
+            per = sh.handle.llh(per_sample=True)[1]
+            np.testing.assert_allclose(per, gold_fd[f"{tag}/sample_llh"][t], rtol=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("build", ["float", "double"])
+def test_device_binned_path_matches_reference_sample_handler(gold_fd, build):
+    from mach3_b200 import handlers
+    from mach3_b200.synth import binned as B
+    tag = f"binned_{build}"
+    w = RC.binned_workload()
+    f64 = build == "double"
+    sh, d = handlers.build_binned_from_workload(w, update_w2=True, test_statistic=BARLOW_BEESTON, keep_event_weights=True, f64=f64)
+    for i, step in enumerate(RC.BINNED_STEPS):
+        sp, nm = B.proposal(w, step)
+        d["pars"][:] = sp; d["norm"][:] = nm; d["osc"][:] = B.make_osc(w, max(step, 0), f64=f64)
+        sh.OscillatorEvaluated()
+        sh.Reweight()
+        if i == 0:
+            sh.GetLikelihood()
+            sh.AddData(gold_fd[f"{tag}/data"])
+        llh = sh.GetLikelihood()
+        np.testing.assert_array_equal(np.asarray(sh.SplineHandler.weightvec_Monolith), gold_fd[f"{tag}/slot_w"][i],
+                                      err_msg=f"weightvec_Monolith, step {step}")
+        mc, w2 = sh.handle.read_hist()
+        np.testing.assert_allclose(mc, gold_fd[f"{tag}/mc"][i], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(w2, gold_fd[f"{tag}/w2"][i], rtol=1e-12, atol=1e-13)
+        if i > 0:
+            assert llh == pytest.approx(float(gold_fd[f"{tag}/llh"][i]), rel=1e-10)
