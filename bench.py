@@ -107,57 +107,91 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle's restatement of the reference's MULTITHREAD CPU path
-# (the reference itself cannot be built here: ROOT/yaml-cpp/spdlog are absent)
+# reference arm / cpu baseline.  kind "reference": the reference's OWN CPU implementation of the path --
+# Splines/SplineMonolith.cpp, SplineBase.cpp, Samples/SampleHandlerFD.cpp, SampleHandlerBase.cpp, BinningHandler.cpp
+# compiled from /root/reference with its release flags + MULTITHREAD + _LOW_MEMORY_STRUCTS_ into
+# oracle/_ref/libm3ref_path_lm_mt.so (oracle/ref_host/Makefile; built in the container that has the reference, it
+# travels to the GPU box).  kind "port": the oracle's restatement, when that library is absent.
 # ---------------------------------------------------------------------------------------------
 def cpu_path(w, n_sample, steps, warmup, budget_s=None):
     """Times SampleHandlerFD::Reweight (FindSplineSegment + CalcSplineWeights + CalcTotalEventWeight
     + FillArray_MP) + GetLikelihood on a bounded sample of workload `w`, DragRace style
-    (Fitters/FitterBase.cpp:461-520).  Returns (events/s, ms/step, laps, cores, llh)."""
+    (Fitters/FitterBase.cpp:461-520).  Returns (events/s, ms/step, laps, cores, llh, sample workload, kind)."""
     from mach3_b200 import synth
-    from oracle import binding as O          # the checker, here as the timed CPU baseline
-    O.set_multithread(True)
+    from oracle import ref_path_binding as RP     # the checker's reference build, here as the timed CPU baseline
     ws = w.scaled(min(n_sample, w.n_events))
-    mono, sh, d = O.build_from_workload(ws)
-    sp, nm = synth.proposal(ws, -1)
-    mono.set_params(sp); sh.norm_vals[:] = nm
-    sh.Reweight()
-    sh.AddData(np.random.default_rng(ws.seed).poisson(sh.mc).astype(np.float64))
+    if RP.available_mt():
+        kind = "reference"
+        typ, npts, cx = synth.param_layout(ws)
+        spl, ev = synth.make_splines(ws), synth.make_events(ws)
+        mono = RP.RefSMonolith.from_arrays(ws.n_params, ws.n_knots, cx, npts, typ, spl, build="float_mt")
+        fd = RP.RefSampleHandlerFD(synth.bin_edges(ws), ws.test_statistic, False, build="float_mt")
+        fd.attach_monolith(mono)
+        E = ws.n_events
+        idx = np.arange(E, dtype=np.int32)
+        fd.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"] if ws.n_norm_per_event else None, ws.n_norm_per_event,
+                      ws.n_norm_params, w_before=idx, w_after=E + idx, n_pool=2 * E)
+        pool = np.concatenate([synth.make_osc(ws, 0), ev["static_w"]]).astype(np.float64)
+        cores = RP.num_threads("float_mt")
+
+        def step(k, first=False):
+            sp, nm = synth.proposal(ws, k)
+            t0 = time.perf_counter()
+            fd.reweight(sp, nm, pool if first else None)      # the weights the pointers look at change only once here
+            llh = fd.llh()
+            return time.perf_counter() - t0, llh
+        step(-1, first=True)
+        fd.set_data(np.random.default_rng(ws.seed).poisson(fd.hist()[0]).astype(np.float64))
+    else:
+        kind = "port"
+        from oracle import binding as O
+        O.set_multithread(True)
+        mono, sh, d = O.build_from_workload(ws)
+        cores = O.num_threads()
+
+        def step(k, first=False):
+            sp, nm = synth.proposal(ws, k)
+            mono.set_params(sp); sh.norm_vals[:] = nm
+            t0 = time.perf_counter()
+            sh.Reweight()
+            llh = sh.GetLikelihood()
+            return time.perf_counter() - t0, llh
+        step(-1)
+        sh.AddData(np.random.default_rng(ws.seed).poisson(sh.mc).astype(np.float64))
     for k in range(max(warmup, 1)):
-        sp, nm = synth.proposal(ws, k)
-        mono.set_params(sp); sh.norm_vals[:] = nm
-        sh.Reweight(); llh = sh.GetLikelihood()
-    t_all, laps = 0.0, 0
+        step(k)
+    t_all, laps, llh = 0.0, 0, 0.0
     for k in range(steps):
-        sp, nm = synth.proposal(ws, warmup + k)
-        mono.set_params(sp); sh.norm_vals[:] = nm
-        t0 = time.perf_counter()
-        sh.Reweight()
-        llh = sh.GetLikelihood()
-        t_all += time.perf_counter() - t0
+        dt, llh = step(warmup + k)
+        t_all += dt
         laps += 1
         if budget_s is not None and t_all > budget_s and laps >= 3:
             break
     ms = 1e3 * t_all / laps
-    return ws.n_events / (ms * 1e-3), ms, laps, O.num_threads(), llh, ws
+    return ws.n_events / (ms * 1e-3), ms, laps, cores, llh, ws, kind
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses all host threads (before libgomp initialises)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from mach3_b200 import build
     build.build_synth(); build.build_oracle()
     w = pick_workload(args)
-    evs, ms, laps, cores, llh, ws = cpu_path(w, args.cpu_sample_events, args.steps, min(args.warmup, 3), budget_s=120.0)
-    sample = (f"{ws.n_events} events of the {w.n_events}-event workload, {laps} timed steps, OpenMP {cores} threads, "
-              "oracle port of the reference's MULTITHREAD CPU path (flags -O3 -fopenmp -flto, no -march)")
+    evs, ms, laps, cores, llh, ws, kind = cpu_path(w, args.cpu_sample_events, args.steps, min(args.warmup, 3), budget_s=120.0)
+    what = ("the reference's own SampleHandlerFD::Reweight + GetLikelihood over its SMonolith (compiled from the reference "
+            "sources: release flags -O3 -flto, MULTITHREAD, _LOW_MEMORY_STRUCTS_, no -march)" if kind == "reference" else
+            "oracle port of the reference's MULTITHREAD CPU path (flags -O3 -fopenmp -flto, no -march)")
+    sample = f"{ws.n_events} events of the {w.n_events}-event workload, {laps} timed steps, OpenMP {cores} threads, {what}"
     line = {"impl": "reference", "metric": "reweighted events/s per MCMC step (reweight+fill+LLH)", "value": evs,
             "unit": "events/s", "n_gpus": args.gpus, "steps": laps, "warmup": min(args.warmup, 3), "ms_per_step": ms,
             "llh_evals_per_s": 1e3 / ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
             "config": {"workload": w.name, "sample": sample},
-            "cpu_baseline": {"value": evs, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": evs, "unit": "events/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": evs, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -362,10 +396,12 @@ def main_b200(args):
             "llh": {"last_value_step": llh_last, "last_e2e_step": llh_e2e, "after_warmup": llh_w},
         }
         if world == 1 and not args.no_cpu_baseline:
-            evs, ms, laps, cores, _, ws = cpu_path(w, args.cpu_sample_events, 100, 2, budget_s=15.0)
-            line["cpu_baseline"] = {"value": evs, "unit": "events/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+            evs, ms, laps, cores, _, ws, kind = cpu_path(w, args.cpu_sample_events, 100, 2, budget_s=15.0)
+            line["cpu_baseline"] = {"value": evs, "unit": "events/s", "cores": cores, "kind": kind, "ms_per_step": ms,
                                     "sample": f"{ws.n_events} events of the same workload, {laps} DragRace laps of "
-                                              f"Reweight+GetLikelihood, OpenMP {cores} threads"}
+                                              f"Reweight+GetLikelihood, OpenMP {cores} threads"
+                                              + (" (the reference's own sources, oracle/_ref/libm3ref_path_lm_mt.so)"
+                                                 if kind == "reference" else " (oracle port)")}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -97,6 +97,61 @@ REFP_API void* refp_mono_create(int n_events, int P, const int* type, const int*
   h->m->setSplinePointers(ptrs);
   return h;
 }
+// The same SMonolith, for workloads too large to hand over as one heap object per response (the bench's CPU
+// baseline: millions of responses).  A one-event monolith goes through the reference's constructor, then its
+// members are replaced by the monolith arrays as PrepareForGPU would have left them (the layout the tests above
+// verify against the constructor's own output).  Evaluate() is the reference's, on the reference's layout.
+REFP_API void* refp_mono_create_from_arrays(int P, int max_knots, const float* coeff_x, const int16_t* n_pts, const int8_t* type,
+                                            int64_t n_events, const uint32_t* nParamPerEvent, const int16_t* paramNo_arr,
+                                            const uint64_t* nKnots_arr, uint64_t total_knots, const float* coeff_many,
+                                            const uint32_t* nParamPerEvent_tf1, const int16_t* paramNo_tf1, const float* coeff_tf1) {
+  std::vector<std::vector<TResponseFunction_red*>> master(1, std::vector<TResponseFunction_red*>(P, nullptr));
+  std::vector<RespFuncType> types(P);
+  M3::float_t X[2] = {0, 1}, Y[2] = {1, 1}, z[3] = {0, 0, 0};
+  M3::float_t* rows[2] = {z, z};
+  for (int p = 0; p < P; ++p) {
+    types[p] = type[p] ? kTF1_red : kTSpline3_red;
+    if (type[p]) { TF1_red* f = new TF1_red(); f->SetSize(2); f->SetParameter(0, 0); f->SetParameter(1, 1); master[0][p] = f; }
+    else master[0][p] = new TSpline3_red(X, Y, 2, rows);
+  }
+  Mono* h = new Mono();
+  try { h->m = new SMonolith(master, types, false); } catch (...) { delete h; return nullptr; }
+  SMonolith* m = h->m;
+  uint64_t ns = 0, nl = 0;
+  for (int64_t e = 0; e < n_events; ++e) { ns += nParamPerEvent[2 * e]; nl += nParamPerEvent_tf1[2 * e]; }
+  m->NEvents = unsigned(n_events); m->_max_knots = short(max_knots);
+  m->NSplines_valid = unsigned(ns); m->NTF1_valid = unsigned(nl); m->nKnots = unsigned(total_knots); m->nTF1coeff = unsigned(nl * 2);
+  m->cpu_spline_handler->coeff_x.assign(coeff_x, coeff_x + size_t(P) * max_knots);
+  m->cpu_spline_handler->coeff_many.assign(coeff_many, coeff_many + total_knots * 4);
+  m->cpu_spline_handler->nKnots_arr.resize(ns);
+  for (uint64_t i = 0; i < ns; ++i) m->cpu_spline_handler->nKnots_arr[i] = unsigned(nKnots_arr[i]);
+  m->cpu_spline_handler->paramNo_arr.assign(paramNo_arr, paramNo_arr + ns);
+  m->cpu_nParamPerEvent.assign(nParamPerEvent, nParamPerEvent + 2 * n_events);
+  m->cpu_nParamPerEvent_tf1.assign(nParamPerEvent_tf1, nParamPerEvent_tf1 + 2 * n_events);
+  m->cpu_paramNo_TF1_arr.assign(paramNo_tf1, paramNo_tf1 + nl);
+  m->cpu_coeff_TF1_many.assign(coeff_tf1, coeff_tf1 + nl * 2);
+  for (int p = 0; p < P; ++p) {
+    m->SplineInfoArray[p].nPts = M3::int_t(n_pts[p]);
+    m->SplineInfoArray[p].xPts.assign(n_pts[p] > 0 ? size_t(n_pts[p]) : 0, M3::float_t(0));
+    for (int k = 0; k < n_pts[p]; ++k) m->SplineInfoArray[p].xPts[k] = M3::float_t(coeff_x[size_t(p) * max_knots + k]);
+    m->SplineInfoArray[p].CurrSegment = 0;
+  }
+  delete[] m->cpu_total_weights; delete[] m->cpu_weights_spline_var; delete[] m->cpu_weights_tf1_var;
+  m->cpu_total_weights = new float[size_t(n_events) + 1]();
+  m->cpu_weights_spline_var = new float[ns + 1]();
+  m->cpu_weights_tf1_var = new float[nl + 1]();
+  h->pars.assign(P, 0.0);
+  std::vector<const double*> ptrs(P);
+  for (int p = 0; p < P; ++p) ptrs[p] = &h->pars[p];
+  m->setSplinePointers(ptrs);
+  return h;
+}
+#ifdef MULTITHREAD
+#include <omp.h>
+REFP_API int refp_num_threads() { return omp_get_max_threads(); }     // the reference's MULTITHREAD build
+#else
+REFP_API int refp_num_threads() { return 1; }
+#endif
 REFP_API void refp_mono_destroy(void* p) { Mono* h = static_cast<Mono*>(p); delete h->m; delete h; }
 
 // sizes: {NEvents, nParams, _max_knots, NSplines_valid, NTF1_valid, nKnots, nTF1coeff}

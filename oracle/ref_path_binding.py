@@ -14,6 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libm3ref_path.so")          # default build: M3::float_t = double
 LIB_PATH_LM = os.path.join(_HERE, "_ref", "libm3ref_path_lm.so")    # -D_LOW_MEMORY_STRUCTS_: M3::float_t = float
+LIB_PATH_LM_MT = os.path.join(_HERE, "_ref", "libm3ref_path_lm_mt.so")   # ... with the release flags + MULTITHREAD
+_PATHS = {"double": LIB_PATH, "float": LIB_PATH_LM, "float_mt": LIB_PATH_LM_MT}
 _LIBS = {}
 
 
@@ -22,10 +24,14 @@ def available():
 
 
 def lib(build="double"):
-    """build: "double" (the reference's default) or "float" (_LOW_MEMORY_STRUCTS_)."""
+    """build: "double" (the reference's default), "float" (_LOW_MEMORY_STRUCTS_), or "float_mt" (the float build with
+    the reference's release flags and MULTITHREAD: the one `bench.py --impl reference` times)."""
     if build not in _LIBS:
-        L = C.CDLL(LIB_PATH if build == "double" else LIB_PATH_LM)
+        L = C.CDLL(_PATHS[build])
         assert L.refp_float_t_bytes() == (8 if build == "double" else 4)
+        L.refp_mono_create_from_arrays.restype = C.c_void_p
+        L.refp_mono_create_from_arrays.argtypes = ([C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
+                                                   + [C.c_uint64] + [C.c_void_p] * 4)
         L.refp_fd_create.restype = C.c_void_p
         L.refp_fd_create.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int]
         L.refp_fd_destroy.argtypes = [C.c_void_p]
@@ -93,6 +99,29 @@ class RefSMonolith:
         (self.NEvents, self.nParams, self.max_knots, self.NSplines_valid, self.NTF1_valid, self.nKnots,
          self.nTF1coeff) = (int(v) for v in s)
 
+    @classmethod
+    def from_arrays(cls, n_params, max_knots, coeff_x, n_pts, type_, spl, build="float"):
+        """SMonolith over monolith arrays that already have the reference's layout (mach3_b200.synth.make_splines):
+        for workloads too large to hand over as one object per response."""
+        self = cls.__new__(cls)
+        L = self.L = lib(build)
+        k = [np.ascontiguousarray(coeff_x, np.float32), np.ascontiguousarray(n_pts, np.int16), np.ascontiguousarray(type_, np.int8),
+             np.ascontiguousarray(spl["nParamPerEvent"], np.uint32), np.ascontiguousarray(spl["paramNo_arr"], np.int16),
+             np.ascontiguousarray(spl["nKnots_arr"], np.uint64), np.ascontiguousarray(spl["coeff_many"], np.float32),
+             np.ascontiguousarray(spl["nParamPerEvent_tf1"], np.uint32), np.ascontiguousarray(spl["paramNo_tf1"], np.int16),
+             np.ascontiguousarray(spl["coeff_tf1"], np.float32)]
+        n_events = k[3].size // 2
+        self.h = L.refp_mono_create_from_arrays(int(n_params), int(max_knots), _p(k[0]), _p(k[1]), _p(k[2]), n_events, _p(k[3]),
+                                                _p(k[4]), _p(k[5]), k[6].size // 4, _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9]))
+        if not self.h:
+            raise RuntimeError("the reference threw while building the monolith")
+        s = np.zeros(7, np.int64)
+        L.refp_mono_sizes(self.h, _p(s))
+        (self.NEvents, self.nParams, self.max_knots, self.NSplines_valid, self.NTF1_valid, self.nKnots,
+         self.nTF1coeff) = (int(v) for v in s)
+        self.n_events, self.n_params = self.NEvents, self.nParams
+        return self
+
     def arrays(self):
         """The monolith arrays exactly as SMonolith::PrepareForGPU left them (the arguments of
         SMonolithGPU::CopyToGPU_SplineMonolith, and of m3b_upload_spline_monolith)."""
@@ -152,7 +181,7 @@ class RefSampleHandlerFD:
         self.mono = None
 
     def attach_monolith(self, mono: RefSMonolith):
-        assert self.build == "float" and mono.L is self.L
+        assert self.build in ("float", "float_mt") and mono.L is self.L
         self.L.refp_fd_attach_monolith(self.h, mono.h)
         self.mono = mono          # its SMonolith now belongs to the sample handler
 
@@ -255,6 +284,14 @@ def poisson(data, mc):
     out = np.zeros(data.size)
     lib().refp_poisson(data.size, _p(data), _p(mc), _p(out))
     return out
+
+
+def num_threads(build="float_mt"):
+    return lib(build).refp_num_threads()
+
+
+def available_mt():
+    return os.path.exists(LIB_PATH_LM_MT)
 
 
 def low_mc_bound():

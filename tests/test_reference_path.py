@@ -346,3 +346,54 @@ def test_device_binned_path_matches_reference_sample_handler(gold_fd, build):
         np.testing.assert_allclose(w2, gold_fd[f"{tag}/w2"][i], rtol=1e-12, atol=1e-13)
         if i > 0:
             assert llh == pytest.approx(float(gold_fd[f"{tag}/llh"][i]), rel=1e-10)
+
+
+@pytest.mark.skipif(not RP.available(), reason="oracle/_ref/libm3ref_path*.so not built (needs /root/reference at build time)")
+def test_array_fed_reference_monolith_equals_the_constructed_one(gold):
+    """bench.py's CPU baseline hands the reference's SMonolith its arrays directly (millions of responses would not
+    fit as heap objects): same Evaluate() results as the monolith the reference's constructor builds."""
+    c = RC.make_case("mixed")
+    a = _arrays(gold, "mixed")
+    P, K = int(gold["mixed/sizes"][1]), int(gold["mixed/sizes"][2])
+    spl = dict(a); spl["nKnots_arr"] = a["nKnots_arr"].astype(np.uint64)
+    m0 = RP.RefSMonolith(c["type"], c["npts"], c["vals"], build="float")
+    m1 = RP.RefSMonolith.from_arrays(P, K, a["coeff_x"], a["n_pts"], c["type"].astype(np.int8), spl, build="float")
+    try:
+        for t in range(0, 40, 3):
+            w0, s0, v0 = m0.evaluate(c["pars"][t])
+            w1, s1, v1 = m1.evaluate(c["pars"][t])
+            np.testing.assert_array_equal(s0, s1)
+            np.testing.assert_array_equal(w0.view(np.uint32), w1.view(np.uint32))
+    finally:
+        m0.close(); m1.close()
+
+
+@pytest.mark.skipif(not RP.available_mt(), reason="oracle/_ref/libm3ref_path_lm_mt.so not built")
+def test_reference_release_build_agrees_with_the_oracle_multithread_path():
+    """The library bench.py times as cpu_baseline kind "reference" (release flags, MULTITHREAD) against the oracle's
+    MULTITHREAD arm on a cfg2 sample: reassociated float products and sums, so 1e-6 on -lnL (north_star's bound)."""
+    from mach3_b200 import synth
+    w = synth.CFG2.scaled(20_000)
+    typ, npts, cx = synth.param_layout(w)
+    spl, ev = synth.make_splines(w), synth.make_events(w)
+    mono = RP.RefSMonolith.from_arrays(w.n_params, w.n_knots, cx, npts, typ, spl, build="float_mt")
+    fd = RP.RefSampleHandlerFD(synth.bin_edges(w), w.test_statistic, False, build="float_mt")
+    fd.attach_monolith(mono)
+    E = w.n_events
+    idx = np.arange(E, dtype=np.int32)
+    fd.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, w_before=idx, w_after=E + idx, n_pool=2 * E)
+    pool = np.concatenate([synth.make_osc(w, 0), ev["static_w"]]).astype(np.float64)
+    O.set_multithread(True)
+    omono, osh, od = O.build_from_workload(w)
+    data = None
+    for step in (-1, 0, 1):
+        sp, nm = synth.proposal(w, step)
+        fd.reweight(sp, nm, pool)
+        omono.set_params(sp); osh.norm_vals[:] = nm
+        osh.Reweight()
+        if data is None:
+            data = np.random.default_rng(1).poisson(osh.mc).astype(np.float64)
+            fd.set_data(data); osh.AddData(data)
+        np.testing.assert_allclose(fd.hist()[0], osh.mc, rtol=1e-6, atol=1e-9)
+        assert fd.llh() == pytest.approx(osh.GetLikelihood(), rel=1e-6, abs=1e-9)
+    fd.close()
