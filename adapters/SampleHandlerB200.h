@@ -23,7 +23,8 @@
 //     EventInfo::KinVar[d]                 -> kin[d][e] = *ptr  (bins are found on the device; functional
 //                                             "shift" parameters, :545-564, are NOT supported by this adapter)
 //     EventInfo::NominalSample             -> sample_id
-//     BinningHandler (GetNDim/GetBinEdges) -> m3b_upload_binning            (uniform binning only)
+//     BinningHandler (GetNDim/GetBinEdges/ -> m3b_upload_binning_ex         (uniform and non-uniform samples)
+//       IsUniform/GetNonUniformBins)
 //     SplineMonoStruct + SMonolith arrays  -> m3b_upload_spline_monolith    (pass them through SetMonolith())
 //
 // Per step Reweight() = [Oscillator->Evaluate()] + ONE m3b_step call: FindSplineSegment (host, the
@@ -95,22 +96,32 @@ class SampleHandlerB200 : public FDBase {
                                        mono.coeff_many, mono.nParamPerEvent_tf1, mono.paramNo_tf1, mono.coeff_tf1),
             "m3b_upload_spline_monolith");
 
-    // --- binning (BinningHandler: uniform arm, Samples/BinningHandler.cpp:257-277)
+    // --- binning (BinningHandler, Samples/BinningHandler.cpp:257-291): uniform samples hand over their axis edges,
+    //     non-uniform ones (Samples/SampleStructs.h:468-528) their boxes (BinInfo::Extent); the library rebuilds the
+    //     mega-bin grid exactly as InitialiseGridMapping does
     const int nS = static_cast<int>(this->GetNsamples());
-    std::vector<int32_t> ndim(nS), nbins(static_cast<size_t>(nS) * 4, 0);
+    std::vector<int32_t> ndim(nS), uniform(nS, 1), nbins(static_cast<size_t>(nS) * 4, 0);
     std::vector<double> edges;
     int max_dim = 0;
     for (int s = 0; s < nS; ++s) {
       ndim[s] = this->GetBinningHandler()->GetNDim(s);
       if (ndim[s] < 1 || ndim[s] > 4) throw std::runtime_error("SampleHandlerB200: 1..4 binning dimensions per sample");
       max_dim = ndim[s] > max_dim ? ndim[s] : max_dim;
-      for (int d = 0; d < ndim[s]; ++d) {
-        const std::vector<double> e = this->GetBinningHandler()->GetBinEdges(s, d);
-        nbins[static_cast<size_t>(s) * 4 + d] = static_cast<int32_t>(e.size()) - 1;
-        edges.insert(edges.end(), e.begin(), e.end());
+      if (this->GetBinningHandler()->IsUniform(s)) {
+        for (int d = 0; d < ndim[s]; ++d) {
+          const std::vector<double> e = this->GetBinningHandler()->GetBinEdges(s, d);
+          nbins[static_cast<size_t>(s) * 4 + d] = static_cast<int32_t>(e.size()) - 1;
+          edges.insert(edges.end(), e.begin(), e.end());
+        }
+      } else {
+        uniform[s] = 0;
+        const auto boxes = this->GetBinningHandler()->GetNonUniformBins(s);
+        nbins[static_cast<size_t>(s) * 4] = static_cast<int32_t>(boxes.size());
+        for (const auto& b : boxes)
+          for (int d = 0; d < ndim[s]; ++d) { edges.push_back(b.Extent[d][0]); edges.push_back(b.Extent[d][1]); }
       }
     }
-    check(m3b_upload_binning(h_, nS, ndim.data(), nbins.data(), edges.data()), "m3b_upload_binning");
+    check(m3b_upload_binning_ex(h_, nS, ndim.data(), uniform.data(), nbins.data(), edges.data()), "m3b_upload_binning_ex");
     n_bins_ = this->GetBinningHandler()->GetNBins();
 
     // --- events: pointers -> indices

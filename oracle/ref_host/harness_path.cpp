@@ -250,7 +250,7 @@ void OscillationHandler::Evaluate() { m3stub::no_root("OscillationHandler"); }
 const M3::float_t* OscillationHandler::GetNuOscillatorPointers(const int, const int, const int, const int, const FLOAT_T, const FLOAT_T) { m3stub::no_root("OscillationHandler"); }
 
 namespace {
-struct FD final : SampleHandlerFD {
+struct FD : SampleHandlerFD {
   std::vector<double> kin;          // [event][4]: what KinVar points at
   std::vector<double> norm;         // what norm_pointers point at (ParameterHandler::_fPropVal)
   std::vector<M3::float_t> pool;    // what total_weight_pointers point at (oscillation weights, extra weights)
@@ -270,6 +270,17 @@ struct FD final : SampleHandlerFD {
   const double* GetPointerToKinematicParameter(double, int) override { return nullptr; }
 };
 
+#ifdef M3B_WITH_ADAPTER
+}  // namespace
+// The drop-in adapter (adapters/SampleHandlerB200.h) instantiated over the REAL SampleHandlerFD class hierarchy:
+// the fitters' three virtuals then run on the B200 through libm3b200's C ABI.
+#include "SampleHandlerB200.h"
+namespace {
+using FDType = m3b200::SampleHandlerB200<FD>;
+#else
+using FDType = FD;
+#endif
+
 struct Binned final : BinnedSplineHandler {
   std::vector<double> pars;
   static ParameterHandlerGeneric* fake_xsec() { static ParameterHandlerGeneric x; return &x; }
@@ -285,7 +296,7 @@ REFP_API void* refp_fd_create(int n_samples, const int* n_dim, const int* unifor
                               int test_statistic, int update_w2) {
   FD* fd = nullptr;
   try {
-    fd = new FD();
+    fd = new FDType();
     fd->nSamples = M3::int_t(n_samples);
     fd->SampleDetails.resize(n_samples);
     const double* ep = edges;
@@ -458,4 +469,54 @@ REFP_API int64_t refp_fd_binned_weights(void* p, double* out) {
 REFP_API void refp_fd_segments(void* p, int16_t* out) {
   SplineBase* s = static_cast<FD*>(p)->SplineHandler.get();
   if (s) std::memcpy(out, s->SplineSegments, size_t(s->nParams) * sizeof(short));
+}
+
+// ---- the adapter over the real class (only in the build that links libm3b200: libm3ref_path_lm_b200.so) ----------
+REFP_API int refp_fd_move_to_b200(void* p, int device) {
+#ifdef M3B_WITH_ADAPTER
+  FD* fd = static_cast<FD*>(p);
+  FDType* b = static_cast<FDType*>(fd);
+  SMonolith* m = dynamic_cast<SMonolith*>(fd->SplineHandler.get());
+  m3b200::MonolithArrays a;
+  std::vector<int16_t> n_pts;
+  if (m) {
+    n_pts.resize(size_t(m->nParams));
+    for (int i = 0; i < m->nParams; ++i) {
+      n_pts[i] = int16_t(m->SplineInfoArray[i].xPts.empty() ? 0 : m->SplineInfoArray[i].nPts);
+      a.spline_par_pointers.push_back(m->SplineInfoArray[i].splineParsPointer);
+    }
+    a.n_params = m->nParams; a.max_knots = m->_max_knots;
+    a.coeff_x = m->cpu_spline_handler->coeff_x.data(); a.n_pts = n_pts.data();
+    a.nParamPerEvent = m->cpu_nParamPerEvent.data(); a.paramNo_arr = m->cpu_spline_handler->paramNo_arr.data();
+    a.nKnots_arr = m->cpu_spline_handler->nKnots_arr.data(); a.total_knots = uint32_t(m->cpu_spline_handler->coeff_many.size() / 4);
+    a.coeff_many = m->cpu_spline_handler->coeff_many.data(); a.nParamPerEvent_tf1 = m->cpu_nParamPerEvent_tf1.data();
+    a.paramNo_tf1 = m->cpu_paramNo_TF1_arr.data(); a.coeff_tf1 = m->cpu_coeff_TF1_many.data();
+    a.cpu_total_weights = m->cpu_total_weights;
+  }
+  m3b200::PointerBases pb;
+  pb.norm_base = fd->norm.data(); pb.n_norm = int(fd->norm.size());
+  pb.osc_base = fd->pool.data(); pb.n_osc = int64_t(fd->nEvents);       // pool = [osc per event | extra weights]
+  pb.zero = &M3::Zero; pb.unity = &M3::Unity;
+  try { b->MoveToB200(a, pb, device); } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+  return 0;
+#else
+  (void)p; (void)device;
+  return -1;
+#endif
+}
+REFP_API int refp_fd_data_changed(void* p) {
+#ifdef M3B_WITH_ADAPTER
+  try { static_cast<FDType*>(static_cast<FD*>(p))->DataChanged(); } catch (...) { return 1; }
+  return 0;
+#else
+  (void)p; return -1;
+#endif
+}
+REFP_API int refp_fd_sync_host_arrays(void* p) {
+#ifdef M3B_WITH_ADAPTER
+  try { static_cast<FDType*>(static_cast<FD*>(p))->SyncHostArrays(); } catch (...) { return 1; }
+  return 0;
+#else
+  (void)p; return -1;
+#endif
 }

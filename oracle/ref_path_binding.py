@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libm3ref_path.so")          # default build: M3::float_t = double
 LIB_PATH_LM = os.path.join(_HERE, "_ref", "libm3ref_path_lm.so")    # -D_LOW_MEMORY_STRUCTS_: M3::float_t = float
 LIB_PATH_LM_MT = os.path.join(_HERE, "_ref", "libm3ref_path_lm_mt.so")   # ... with the release flags + MULTITHREAD
-_PATHS = {"double": LIB_PATH, "float": LIB_PATH_LM, "float_mt": LIB_PATH_LM_MT}
+LIB_PATH_LM_B200 = os.path.join(_HERE, "_ref", "libm3ref_path_lm_b200.so")   # ... with adapters/SampleHandlerB200.h over the real class
+_PATHS = {"double": LIB_PATH, "float": LIB_PATH_LM, "float_mt": LIB_PATH_LM_MT, "float_b200": LIB_PATH_LM_B200}
 _LIBS = {}
 
 
@@ -55,6 +56,9 @@ def lib(build="double"):
         L.refp_fd_binned_weights.restype = C.c_int64
         L.refp_fd_binned_weights.argtypes = [C.c_void_p, C.c_void_p]
         L.refp_fd_segments.argtypes = [C.c_void_p, C.c_void_p]
+        L.refp_fd_move_to_b200.argtypes = [C.c_void_p, C.c_int]
+        L.refp_fd_data_changed.argtypes = [C.c_void_p]
+        L.refp_fd_sync_host_arrays.argtypes = [C.c_void_p]
         L.refp_mono_create.restype = C.c_void_p
         L.refp_mono_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refp_mono_destroy.argtypes = [C.c_void_p]
@@ -181,7 +185,7 @@ class RefSampleHandlerFD:
         self.mono = None
 
     def attach_monolith(self, mono: RefSMonolith):
-        assert self.build in ("float", "float_mt") and mono.L is self.L
+        assert self.build in ("float", "float_mt", "float_b200") and mono.L is self.L
         self.L.refp_fd_attach_monolith(self.h, mono.h)
         self.mono = mono          # its SMonolith now belongs to the sample handler
 
@@ -256,6 +260,19 @@ class RefSampleHandlerFD:
         self.L.refp_fd_events(self.h, _p(w), _p(b))
         return w, b
 
+    # -- only in build "float_b200": the object is an m3b200::SampleHandlerB200<FD> over the reference's class
+    def move_to_b200(self, device=0):
+        if self.L.refp_fd_move_to_b200(self.h, int(device)):
+            raise RuntimeError("SampleHandlerB200::MoveToB200 failed")
+
+    def data_changed(self):
+        if self.L.refp_fd_data_changed(self.h):
+            raise RuntimeError("SampleHandlerB200::DataChanged failed")
+
+    def sync_host_arrays(self):
+        if self.L.refp_fd_sync_host_arrays(self.h):
+            raise RuntimeError("SampleHandlerB200::SyncHostArrays failed")
+
     def binned_weights(self):
         out = np.zeros(self.n_slots)
         self.L.refp_fd_binned_weights(self.h, _p(out))
@@ -288,6 +305,10 @@ def poisson(data, mc):
 
 def num_threads(build="float_mt"):
     return lib(build).refp_num_threads()
+
+
+def available_b200():
+    return os.path.exists(LIB_PATH_LM_B200)
 
 
 def available_mt():

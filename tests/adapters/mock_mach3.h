@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <array>
 #include <vector>
 
 namespace M3 {
@@ -44,6 +45,11 @@ class BinningHandler {
   }
   int GetNDim(const int s) const { return int(edges[s].size()); }
   std::vector<double> GetBinEdges(const int s, const int d) const { return edges[s].at(d); }
+  // the mock only does uniform binning (the real class, with non-uniform samples, is exercised through
+  // oracle/_ref/libm3ref_path_lm_b200.so: tests/test_adapter_gpu.py)
+  bool IsUniform(const int) const { return true; }
+  struct BinInfo { std::vector<std::array<double, 2>> Extent; };
+  std::vector<BinInfo> GetNonUniformBins(const int) const { return {}; }
   int GetNBins() const { return total; }
   int GetSampleStartBin(const int s) const { return offset[s]; }
   int GetSampleEndBin(const int s) const { return s + 1 < int(offset.size()) ? offset[s + 1] : total; }

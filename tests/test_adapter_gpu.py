@@ -51,3 +51,47 @@ def test_sample_handler_adapter_runs_the_fitters_call_surface(args):
         pytest.skip("oracle/_ref/adapter_test not built")
     r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "ADAPTER OK" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.gpu
+def test_adapter_over_the_reference_real_sample_handler_class():
+    """adapters/SampleHandlerB200.h instantiated over the reference's REAL SampleHandlerFD (compiled from
+    /root/reference, oracle/ref_host) and linked with libm3b200: after MoveToB200() the fitters' calls --
+    Reweight(), GetLikelihood(), GetSampleLikelihood() -- run on the B200 and return what the reference's own CPU
+    implementation returned for the same object (tests/golden/ref_host_fd.npz), W2 frozen and live."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import refpath_cases as RC
+    from oracle import ref_path_binding as RP
+    if not RP.available_b200():
+        pytest.skip("oracle/_ref/libm3ref_path_lm_b200.so not built (needs /root/reference at build time)")
+    gold = np.load(os.path.join(here, "golden", "ref_host_fd.npz"))
+    for update_w2 in (False, True):
+        tag = f"mono_w2{int(update_w2)}"
+        f = RC.fd_case()
+        c = f["mono"]
+        E = f["sample_id"].size
+        m = RP.RefSMonolith(c["type"], c["npts"], c["vals"], build="float_b200")
+        fd = RP.RefSampleHandlerFD(RC.fd_edges(), 1, update_w2, build="float_b200")
+        fd.attach_monolith(m)
+        idx = np.arange(E, dtype=np.int32)
+        fd.set_events(f["sample_id"], f["kin"], f["norm_idx"], RC.NPE, RC.N_NORM, w_before=idx, w_after=E + idx, n_pool=2 * E)
+        # step 0 on the reference's CPU path (before MoveToB200 the adapter forwards to the base class) ...
+        pool = np.concatenate([f["osc"][0], f["static_w"]]).astype(np.float64)
+        fd.reweight(f["pars"][0], f["norm"][0], pool)
+        np.testing.assert_array_equal(fd.hist()[0], gold[f"{tag}/mc"][0])
+        fd.set_data(gold[f"{tag}/data"])
+        # ... then the same object moves to the B200 and replays the chain from its first step
+        fd.move_to_b200(0)
+        for t in range(8):                                   # (steps 8+ shift the kinematics: not supported by the adapter)
+            pool = np.concatenate([f["osc"][t], f["static_w"]]).astype(np.float64)
+            fd.reweight(f["pars"][t], f["norm"][t], pool)
+            assert fd.llh() == pytest.approx(float(gold[f"{tag}/llh"][t]), rel=1e-10)
+            np.testing.assert_allclose(fd.sample_llh(), gold[f"{tag}/sample_llh"][t], rtol=1e-10)
+            fd.sync_host_arrays()
+            mc, w2 = fd.hist()
+            np.testing.assert_allclose(mc, gold[f"{tag}/mc"][t], rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(w2, gold[f"{tag}/w2"][t], rtol=1e-12, atol=1e-13)
+        fd.close()
