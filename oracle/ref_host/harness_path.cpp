@@ -166,6 +166,7 @@ REFP_API void refp_mono_sizes(void* p, int64_t* out) {
 //        returns the element count; copies when out != nullptr
 REFP_API int64_t refp_mono_array(void* p, int which, void* out) {
   SMonolith* m = static_cast<Mono*>(p)->m;
+  if (!m->cpu_spline_handler) return -1;      // MaCh3_CUDA build: handed to the GPU class and freed (SplineMonolith.cpp:305-311)
   auto give = [&](const void* src, size_t n, size_t sz) -> int64_t { if (out && n) std::memcpy(out, src, n * sz); return int64_t(n); };
   switch (which) {
     case 0: return give(m->cpu_spline_handler->coeff_x.data(), m->cpu_spline_handler->coeff_x.size(), 4);
@@ -200,7 +201,7 @@ REFP_API int refp_mono_evaluate(void* p, const double* pars, float* weights, int
   Mono* h = static_cast<Mono*>(p);
   SMonolith* m = h->m;
   for (size_t i = 0; i < h->pars.size(); ++i) h->pars[i] = pars[i];
-  try { m->Evaluate(); } catch (...) { return 1; }
+  try { m->Evaluate(); m->SynchroniseMemTransfer(); } catch (...) { return 1; }     // the fence is a no-op in the CPU build
   if (weights) std::memcpy(weights, m->cpu_total_weights, size_t(m->NEvents) * sizeof(float));
   if (segments) std::memcpy(segments, m->SplineSegments, size_t(m->nParams) * sizeof(short));
   if (param_values) std::memcpy(param_values, m->ParamValues, size_t(m->nParams) * sizeof(float));

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libm3ref_path.so")          # default bu
 LIB_PATH_LM = os.path.join(_HERE, "_ref", "libm3ref_path_lm.so")    # -D_LOW_MEMORY_STRUCTS_: M3::float_t = float
 LIB_PATH_LM_MT = os.path.join(_HERE, "_ref", "libm3ref_path_lm_mt.so")   # ... with the release flags + MULTITHREAD
 LIB_PATH_LM_B200 = os.path.join(_HERE, "_ref", "libm3ref_path_lm_b200.so")   # ... with adapters/SampleHandlerB200.h over the real class
-_PATHS = {"double": LIB_PATH, "float": LIB_PATH_LM, "float_mt": LIB_PATH_LM_MT, "float_b200": LIB_PATH_LM_B200}
+LIB_PATH_LM_CUDA = os.path.join(_HERE, "_ref", "libm3ref_path_lm_cuda.so")   # ... MaCh3_CUDA build, adapters/SMonolithGPU_m3b200.cu
+_PATHS = {"float_cuda": LIB_PATH_LM_CUDA, "double": LIB_PATH, "float": LIB_PATH_LM, "float_mt": LIB_PATH_LM_MT, "float_b200": LIB_PATH_LM_B200}
 _LIBS = {}
 
 
@@ -185,7 +186,7 @@ class RefSampleHandlerFD:
         self.mono = None
 
     def attach_monolith(self, mono: RefSMonolith):
-        assert self.build in ("float", "float_mt", "float_b200") and mono.L is self.L
+        assert self.build in ("float", "float_mt", "float_b200", "float_cuda") and mono.L is self.L
         self.L.refp_fd_attach_monolith(self.h, mono.h)
         self.mono = mono          # its SMonolith now belongs to the sample handler
 
@@ -305,6 +306,10 @@ def poisson(data, mc):
 
 def num_threads(build="float_mt"):
     return lib(build).refp_num_threads()
+
+
+def available_cuda():
+    return os.path.exists(LIB_PATH_LM_CUDA)
 
 
 def available_b200():

@@ -95,3 +95,54 @@ def test_adapter_over_the_reference_real_sample_handler_class():
             np.testing.assert_allclose(mc, gold[f"{tag}/mc"][t], rtol=1e-12, atol=1e-13)
             np.testing.assert_allclose(w2, gold[f"{tag}/w2"][t], rtol=1e-12, atol=1e-13)
         fd.close()
+
+
+@pytest.mark.gpu
+def test_reference_smonolith_cuda_build_drives_the_drop_in_smonolithgpu():
+    """Level 1 of INTEGRATION.md for real: the reference's SMonolith compiled with MaCh3_CUDA (from
+    /root/reference/Splines/SplineMonolith.cpp) and linked with adapters/SMonolithGPU_m3b200.cu in place of the
+    reference's gpuSplineUtils.cu.  Its constructor (MoveToGPU) and Evaluate() go through the reference's own
+    SMonolithGPU interface into libm3b200; the per-event weights equal, bit for bit, what the same class computes in
+    its CPU build (tests/golden/ref_host_path.npz), and SampleHandlerFD on top gives the reference's histograms."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import refpath_cases as RC
+    from oracle import ref_path_binding as RP
+    if not RP.available_cuda():
+        pytest.skip("oracle/_ref/libm3ref_path_lm_cuda.so not built (needs /root/reference at build time)")
+    gold = np.load(os.path.join(here, "golden", "ref_host_path.npz"))
+    for name in RC.CASES:
+        c = RC.make_case(name)
+        m = RP.RefSMonolith(c["type"], c["npts"], c["vals"], build="float_cuda")
+        # float build: FastSplineInfo::xPts are floats, so segments can differ from the double-build vectors within a
+        # float ulp of a knot (tests/test_reference_path.py); compare the steps where they agree
+        for t in range(c["pars"].shape[0]):
+            w, s, v = m.evaluate(c["pars"][t])
+            np.testing.assert_array_equal(v, gold[f"{name}/param_values"][t])
+            if np.array_equal(s, gold[f"{name}/segments"][t]):
+                np.testing.assert_array_equal(w.view(np.uint32), gold[f"{name}/weights"][t].view(np.uint32), err_msg=f"{name} step {t}")
+            else:
+                assert t in (5, 9, 13, 17, 21, 25, 33)
+        m.close()
+    # and the full sample handler on top of the GPU-built monolith: the reference's FillArray reads the weights the
+    # drop-in class copied back into cpu_total_weights
+    gfd = np.load(os.path.join(here, "golden", "ref_host_fd.npz"))
+    f = RC.fd_case()
+    c = f["mono"]
+    E = f["sample_id"].size
+    m = RP.RefSMonolith(c["type"], c["npts"], c["vals"], build="float_cuda")
+    fd = RP.RefSampleHandlerFD(RC.fd_edges(), 1, True, build="float_cuda")
+    fd.attach_monolith(m)
+    idx = np.arange(E, dtype=np.int32)
+    fd.set_events(f["sample_id"], f["kin"], f["norm_idx"], RC.NPE, RC.N_NORM, w_before=idx, w_after=E + idx, n_pool=2 * E)
+    for t in range(8):
+        pool = np.concatenate([f["osc"][t], f["static_w"]]).astype(np.float64)
+        fd.reweight(f["pars"][t], f["norm"][t], pool)
+        if t == 0:
+            fd.set_data(gfd["mono_w21/data"])
+        mc, w2 = fd.hist()
+        np.testing.assert_array_equal(mc, gfd["mono_w21/mc"][t])          # same weights, same serial FillArray
+        assert fd.llh() == pytest.approx(float(gfd["mono_w21/llh"][t]), rel=1e-14)
+    fd.close()
