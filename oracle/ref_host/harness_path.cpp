@@ -17,6 +17,9 @@
 // m3b_upload_spline_monolith.
 #include "Splines/SplineMonolith.h"
 #include "Samples/SampleHandlerBase.h"
+#ifdef MaCh3_CUDA
+#include "Splines/gpuSplineUtils.cuh"
+#endif
 
 #include <cstdint>
 #include <cstring>
@@ -119,6 +122,16 @@ REFP_API void* refp_mono_create_from_arrays(int P, int max_knots, const float* c
   SMonolith* m = h->m;
   uint64_t ns = 0, nl = 0;
   for (int64_t e = 0; e < n_events; ++e) { ns += nParamPerEvent[2 * e]; nl += nParamPerEvent_tf1[2 * e]; }
+#ifdef MaCh3_CUDA
+  // the one-event monolith already moved to the GPU and freed its host arrays (SplineMonolith.cpp:254-313): release
+  // it the way the destructor does (:621-626) and start again from empty host structures
+  m->gpu_spline_handler->CleanupGPU_SplineMonolith(m->cpu_total_weights);
+  m->gpu_spline_handler->CleanupGPU_Segments(m->SplineSegments, m->ParamValues);
+  delete m->gpu_spline_handler;
+  m->gpu_spline_handler = nullptr;
+  m->cpu_total_weights = nullptr; m->SplineSegments = nullptr; m->ParamValues = nullptr;
+  m->cpu_spline_handler = new SplineMonoStruct();
+#endif
   m->NEvents = unsigned(n_events); m->_max_knots = short(max_knots);
   m->NSplines_valid = unsigned(ns); m->NTF1_valid = unsigned(nl); m->nKnots = unsigned(total_knots); m->nTF1coeff = unsigned(nl * 2);
   m->cpu_spline_handler->coeff_x.assign(coeff_x, coeff_x + size_t(P) * max_knots);
@@ -136,10 +149,18 @@ REFP_API void* refp_mono_create_from_arrays(int P, int max_knots, const float* c
     for (int k = 0; k < n_pts[p]; ++k) m->SplineInfoArray[p].xPts[k] = M3::float_t(coeff_x[size_t(p) * max_knots + k]);
     m->SplineInfoArray[p].CurrSegment = 0;
   }
+#ifdef MaCh3_CUDA
+  // what PrepareForGPU does before MoveToGPU in this build (:81-95): pinned segment / value arrays, then the move
+  m->gpu_spline_handler->InitGPU_Segments(&m->SplineSegments);       // static-like: do not touch `this` (called on nullptr, :82)
+  m->gpu_spline_handler->InitGPU_Vals(&m->ParamValues);
+  for (int p = 0; p < P; ++p) { m->SplineSegments[p] = 0; m->ParamValues[p] = -999; }
+  m->MoveToGPU();
+#else
   delete[] m->cpu_total_weights; delete[] m->cpu_weights_spline_var; delete[] m->cpu_weights_tf1_var;
   m->cpu_total_weights = new float[size_t(n_events) + 1]();
   m->cpu_weights_spline_var = new float[ns + 1]();
   m->cpu_weights_tf1_var = new float[nl + 1]();
+#endif
   h->pars.assign(P, 0.0);
   std::vector<const double*> ptrs(P);
   for (int p = 0; p < P; ++p) ptrs[p] = &h->pars[p];

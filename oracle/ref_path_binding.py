@@ -29,7 +29,10 @@ def lib(build="double"):
     """build: "double" (the reference's default), "float" (_LOW_MEMORY_STRUCTS_), or "float_mt" (the float build with
     the reference's release flags and MULTITHREAD: the one `bench.py --impl reference` times)."""
     if build not in _LIBS:
-        L = C.CDLL(_PATHS[build])
+        # "float_refcuda_P<n>": the whole incumbent -- MaCh3_CUDA build with the reference's own kernels for n parameters
+        path = (os.path.join(_HERE, "_ref", f"libm3ref_path_lm_refcuda_{build.split('_')[-1]}.so")
+                if build.startswith("float_refcuda_") else _PATHS[build])
+        L = C.CDLL(path)
         assert L.refp_float_t_bytes() == (8 if build == "double" else 4)
         L.refp_mono_create_from_arrays.restype = C.c_void_p
         L.refp_mono_create_from_arrays.argtypes = ([C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
@@ -186,7 +189,7 @@ class RefSampleHandlerFD:
         self.mono = None
 
     def attach_monolith(self, mono: RefSMonolith):
-        assert self.build in ("float", "float_mt", "float_b200", "float_cuda") and mono.L is self.L
+        assert self.build.startswith("float") and mono.L is self.L
         self.L.refp_fd_attach_monolith(self.h, mono.h)
         self.mono = mono          # its SMonolith now belongs to the sample handler
 
@@ -306,6 +309,10 @@ def poisson(data, mc):
 
 def num_threads(build="float_mt"):
     return lib(build).refp_num_threads()
+
+
+def available_refcuda(n_params):
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libm3ref_path_lm_refcuda_P{n_params}.so"))
 
 
 def available_cuda():
