@@ -227,6 +227,11 @@ M3B_API int m3b_llh(m3b_handle* h, double* total, double* per_sample /* [n_sampl
  *   llh_per_sample[n_sets*n_samples] or NULL.  osc_w (or NULL) applies to the whole batch.                 */
 M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars,
                            const float* osc_w, double* llh_total, double* llh_per_sample);
+/* m3b_step_batch_hist: the same, and every set's MC histogram comes back too: mc[n_sets*n_bins] (what
+ *   PredictiveThrower writes per toy after samples[i]->Reweight(), Fitters/PredictiveThrower.cpp:507-563).      */
+M3B_API int m3b_step_batch_hist(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars,
+                                const float* osc_w, double* llh_total, double* llh_per_sample /* or NULL */,
+                                double* mc);
 /* m3b_eval_weights = SMonolithGPU::RunGPU_SplineMonolith exactly (Splines/gpuSplineUtils.cu:444-512):
  *   evaluate all responses, multiply per event, and enqueue the copy of the per-event totals into the
  *   caller's host array (cpu_total_weights, pinned by InitGPU_SplineMonolith :139) -- asynchronous until

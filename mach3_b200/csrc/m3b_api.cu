@@ -1032,8 +1032,8 @@ M3B_API int m3b_eval_weights(m3b_handle* h, const float* param_values, const int
 // vectors against the same events.  Sets are evaluated in order with the reference's sequential semantics
 // (cached segments of SplineBase::FindSplineSegment, W2 freeze), all launches are enqueued back to back and
 // the host synchronises ONCE; every set's -lnL lands in its own slot of a mapped host array.
-M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars,
-                           const float* osc_w, double* llh_total, double* llh_per_sample) {
+static int step_batch_impl(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars,
+                           const float* osc_w, double* llh_total, double* llh_per_sample, double* mc_out) {
   REQUIRE(h && llh_total, M3B_ERR_INVALID, "m3b_step_batch: null argument");
   REQUIRE(n_sets > 0, M3B_ERR_INVALID, "m3b_step_batch: n_sets must be positive");
   REQUIRE(h->peer_world == 0 && !(h->cfg.flags & M3B_FLAG_NO_FUSED_LLH), M3B_ERR_STATE, "m3b_step_batch: single-GPU fused handles only");
@@ -1059,6 +1059,14 @@ M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_p
                        i0 == 0 ? osc_w : nullptr, h->h_batch_dev + slot * i0, &done);
     if (rc != M3B_OK) return rc;
     if (!done) break;
+    if (mc_out) {
+      // the chunk's histograms live as [bin][256 sets]; the next chunk reuses the buffer
+      std::vector<double> tmp(static_cast<size_t>(h->n_bins) * 256);
+      CK(cudaMemcpyAsync(tmp.data(), h->bt_hist, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      for (int32_t k = 0; k < n; ++k)
+        for (int b = 0; b < h->n_bins; ++b) mc_out[static_cast<size_t>(i0 + k) * h->n_bins + b] = tmp[static_cast<size_t>(b) * 256 + k];
+    }
     i0 += n;
   }
   for (int32_t i = i0; i < n_sets && rc == M3B_OK; ++i) {
@@ -1066,6 +1074,9 @@ M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_p
     rc = step_common(h, h->P > 0 ? spline_pars + static_cast<size_t>(i) * h->P : nullptr,
                      h->n_norm_values > 0 ? norm_pars + static_cast<size_t>(i) * h->n_norm_values : nullptr,
                      (i == 0 && i0 == 0) ? osc_w : nullptr, kFused);
+    if (rc == M3B_OK && mc_out)     // stream-ordered after this set's step, before the next one reuses the other buffer
+      CK(cudaMemcpyAsync(mc_out + static_cast<size_t>(i) * h->n_bins, h->d_hw[h->cur], sizeof(double) * h->n_bins,
+                         cudaMemcpyDeviceToHost, h->stream));
   }
   h->llh_host_override = nullptr;
   if (rc != M3B_OK) return rc;
@@ -1077,6 +1088,17 @@ M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_p
   // m3b_llh after a batch returns the last set's value
   for (size_t k = 0; k < slot; ++k) h->h_llh[k] = h->h_batch[slot * (n_sets - 1) + k];
   return M3B_OK;
+}
+
+M3B_API int m3b_step_batch(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars,
+                           const float* osc_w, double* llh_total, double* llh_per_sample) {
+  return step_batch_impl(h, n_sets, spline_pars, norm_pars, osc_w, llh_total, llh_per_sample, nullptr);
+}
+
+M3B_API int m3b_step_batch_hist(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars,
+                                const float* osc_w, double* llh_total, double* llh_per_sample, double* mc) {
+  REQUIRE(mc, M3B_ERR_INVALID, "m3b_step_batch_hist: null histogram output");
+  return step_batch_impl(h, n_sets, spline_pars, norm_pars, osc_w, llh_total, llh_per_sample, mc);
 }
 
 M3B_API int m3b_step_fill(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w) {

@@ -7,6 +7,10 @@ rows serves the whole loop.
                    samples[i]->Reweight(); samples[i]->GetLikelihood() (+ GetSampleLikelihood when split by sample).
                    Returns what the reference writes into hScanSam / hScanSamSplit: 2 x (-lnL).
 
+    ProduceToys    the sample side of PredictiveThrower::ProduceToys (Fitters/PredictiveThrower.cpp:507-563): for every
+                   thrown parameter set samples[i]->Reweight() and the MC histogram of every sample (what WriteToy
+                   stores); here all throws go through one m3b_step_batch_hist call.
+
 Only the sample-likelihood part is computed here; the systematic (prior) terms of the scan come from the
 ParameterHandler and are out of scope.
 """
@@ -44,3 +48,20 @@ def RunLLHScan(sample, central_spline_pars, central_norm_pars=None, spline_range
     h.step(c_sp, c_nm)
     h.llh()
     return out
+
+
+def ProduceToys(sample, spline_par_throws, norm_par_throws=None, chunk=256):
+    """`sample`: mach3_b200.handlers.SampleHandlerFD.  spline_par_throws[n_toys, n_params] / norm_par_throws[n_toys, n_norm]:
+    the parameter sets PredictiveThrower draws from the posterior chain (or from the prior).  Returns
+    (mc[n_toys, n_bins], llh[n_toys]): each toy's MC prediction in global-bin order (slice it per sample with the
+    binning's sample offsets) and the sample -lnL of that throw against the loaded data.  Sequential semantics: the
+    result equals looping Reweight() over the throws."""
+    h = sample.handle
+    sp = np.ascontiguousarray(spline_par_throws, np.float64)
+    nm = None if norm_par_throws is None else np.ascontiguousarray(norm_par_throws, np.float64)
+    n = sp.shape[0]
+    mcs, llhs = [], []
+    for i0 in range(0, n, chunk):
+        tot, mc = h.step_batch_hist(sp[i0:i0 + chunk], None if nm is None else nm[i0:i0 + chunk])
+        mcs.append(mc); llhs.append(tot)
+    return np.concatenate(mcs, 0), np.concatenate(llhs)

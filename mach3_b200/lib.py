@@ -25,7 +25,7 @@ EXPORTS = (
     "m3b_read_event_weights_f64",
     "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_update_kinematics", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
     "m3b_set_test_statistic", "m3b_reset_w2",
-    "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_set_spline_knots_f64", "m3b_synchronize",
+    "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_step_batch_hist", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_set_spline_knots_f64", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
     "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
     "m3b_get_info", "m3b_set_timing", "m3b_kernel_time", "m3b_block_trace",
@@ -293,6 +293,16 @@ class Handle:
         ps = np.zeros((n_sets, max(self.n_samples, 1)), np.float64) if per_sample else None
         self._ck(self.L.m3b_step_batch(self.h, C.c_int32(n_sets), _p(sp), _p(nm), _p(osc_w), _p(tot), _p(ps)))
         return (tot, ps[:, :self.n_samples]) if per_sample else tot
+
+    def step_batch_hist(self, spline_pars, norm_pars=None, osc_w=None):
+        """Like step_batch, and every set's MC histogram comes back: (-lnL[n_sets], mc[n_sets, n_bins])."""
+        sp = _c(spline_pars, np.float64)
+        n_sets = sp.shape[0] if sp is not None else np.asarray(norm_pars).shape[0]
+        nm = _c(norm_pars, np.float64)
+        tot = np.zeros(n_sets, np.float64)
+        mc = np.zeros((n_sets, self.n_bins), np.float64)
+        self._ck(self.L.m3b_step_batch_hist(self.h, C.c_int32(n_sets), _p(sp), _p(nm), _p(osc_w), _p(tot), None, _p(mc)))
+        return tot, mc
 
     def step_addr(self, spline_pars_addr, norm_pars_addr=0, osc_w_addr=0):
         """m3b_step on raw addresses (float64 spline pars, float64 norm pars, float32 osc weights or 0)."""

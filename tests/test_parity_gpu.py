@@ -413,6 +413,32 @@ def test_llh_scan_matches_the_reference_loop(oracle_build):
     assert gsh.GetLikelihood() == pytest.approx(osh.GetLikelihood(), rel=1e-9 if _exact() else LLH_RTOL)
 
 
+@pytest.mark.parametrize("update_w2", [False, True])
+def test_predictive_toys_match_the_reference_loop(oracle_build, update_w2):
+    """PredictiveThrower's toy loop (set a thrown parameter set, Reweight, keep every sample's MC histogram;
+    Fitters/PredictiveThrower.cpp:507-563) through m3b_step_batch_hist: frozen W2 goes through the batched kernel
+    (one pass over the coefficient rows for all throws), live W2 through the sequential path; both return each
+    throw's histogram and -lnL as the oracle's loop computes them."""
+    from mach3_b200 import fitters
+    w = synth.SPARSE.scaled(20_000)
+    mono, osh, od = O.build_from_workload(w, update_w2=update_w2)
+    gsh, gd = handlers.build_from_workload(w, update_w2=update_w2)
+    _set(w, -1, mono, osh, gsh, gd)
+    osh.Reweight(); gsh.Reweight(); gsh.GetLikelihood()
+    data = np.random.default_rng(13).poisson(osh.mc).astype(np.float64)
+    osh.AddData(data); gsh.AddData(data)
+    n_toys = 37
+    throws = [synth.proposal(w, 100 + k) for k in range(n_toys)]
+    sps = np.stack([t[0] for t in throws]); nms = np.stack([t[1] for t in throws])
+    mc, llh = fitters.ProduceToys(gsh, sps, nms)
+    assert mc.shape == (n_toys, w.n_bins) and llh.shape == (n_toys,)
+    for k in range(n_toys):
+        mono.set_params(sps[k]); osh.norm_vals[:] = nms[k]
+        osh.Reweight()
+        np.testing.assert_allclose(mc[k], osh.mc, rtol=1e-12 if _exact() else 1e-6, atol=1e-12, err_msg=f"toy {k}")
+        assert llh[k] == pytest.approx(osh.GetLikelihood(), rel=1e-9 if _exact() else LLH_RTOL, abs=1e-9)
+
+
 def test_fill_only_then_llh_from_hist_equals_fused(oracle_build):
     """The multi-GPU building blocks on one GPU: m3b_step_fill + m3b_llh_from_hist (what every rank runs around the
     exchange) give the fused step's histogram and -lnL; the histogram device pointer is stable across steps."""
