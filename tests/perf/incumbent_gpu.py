@@ -1,14 +1,15 @@
 """The incumbent: MaCh3's own CUDA spline kernels (Splines/gpuSplineUtils.cu built into oracle/_ref, driven like
 SMonolith::Evaluate + SynchroniseMemTransfer) on BASELINE config 2, next to the drop-in adapter (same call sequence on
 libm3b200) and the fused step.  The reference's GPU path stops at per-event spline weights (n_events x 4 B copied to the
-host every step); fill and likelihood then run on the CPU.    python scripts/incumbent_gpu.py [n_events]"""
+host every step); fill and likelihood then run on the CPU.    python tests/perf/incumbent_gpu.py [n_events]
+(lives under tests/ because it drives oracle/: test infrastructure, never the product)"""
 import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from mach3_b200 import handlers, lib, synth          # noqa: E402
 from oracle import binding as O                        # noqa: E402
 from oracle import ref_gpu_binding as R                # noqa: E402
