@@ -9,9 +9,10 @@
 // TEST INFRASTRUCTURE (part of oracle/).  The reference header is compiled where it lies (-I/root/reference);
 // ROOT, spdlog, yaml-cpp and NuOscillator are absent from this image, so oracle/ref_host/stubs/ provides empty
 // stand-ins for their headers (none of their functionality is used by the code exercised here).  The ten lines
-// of BinningHandler::FindGlobalBin (Samples/BinningHandler.cpp:257-291; that file cannot be compiled without
-// ROOT) are driven here on the reference's structures: FindBin per dimension, Strides, then for non-uniform
-// binning BinGridMapping[mega] in order with Bins[b].IsEventInside().
+// of BinningHandler::FindGlobalBin (Samples/BinningHandler.cpp:257-291) are re-stated here on the reference's
+// structures: FindBin per dimension, Strides, then for non-uniform binning BinGridMapping[mega] in order with
+// Bins[b].IsEventInside().  (harness_path.cpp compiles Samples/BinningHandler.cpp itself and runs the REAL
+// FindGlobalBin; tests/test_reference_host.py checks that both give the same bins.)
 #include "Samples/SampleStructs.h"
 
 #include <cstdint>

@@ -77,3 +77,23 @@ def test_device_bins_match_reference_vectors(name):
     h.upload_events(np.zeros(kin.shape[1], np.int32), np.ascontiguousarray(kin).reshape(-1))
     np.testing.assert_array_equal(h.read_event_bins(), g[f"{name}/bin_true"])
     h.close()
+
+
+from oracle import ref_path_binding as RP   # noqa: E402
+
+
+@pytest.mark.skipif(not RP.available(), reason="oracle/_ref/libm3ref_path.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", CASES)
+def test_real_binninghandler_findglobalbin_reproduces_the_vectors(name):
+    """The vectors above were made with the ten glue lines of BinningHandler::FindGlobalBin re-stated in the harness
+    (Samples/BinningHandler.cpp could not be compiled then).  It compiles now (oracle/ref_host/harness_path.cpp):
+    the reference's REAL BinningHandler::FindGlobalBin, with the nominal bins from its own FindNominalBinAndEdges,
+    gives the same bin ids on the same edge-heavy inputs."""
+    g = np.load(GOLD)
+    spec = _spec(g, name)
+    kin = g[f"{name}/kin"]
+    fd = RP.RefSampleHandlerFD([spec], 0, False, build="double")
+    fd.set_events(np.zeros(kin.shape[1], np.int32), kin)
+    _, bins = fd.events()
+    np.testing.assert_array_equal(bins, g[f"{name}/bin_true"])
+    fd.close()
