@@ -395,6 +395,16 @@ def main_b200(args):
             "gpu_launches": int(launches), "clocks": clk,
             "llh": {"last_value_step": llh_last, "last_e2e_step": llh_e2e, "after_warmup": llh_w},
         }
+        if world > 1:
+            # the driver's N=1 run is cfg2 (BASELINE configs[1]); the same-workload single-GPU point of THIS strong-scaling
+            # curve was measured once and committed (python bench.py --workload cfg3 on one B200: all events resident)
+            try:
+                one = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_cfg3_1gpu.json")))
+                if one["config"]["events"] == E and one["config"]["responses_per_event"] == w.n_params:
+                    line["same_workload_on_one_gpu"] = {"value": one["value"], "ms_per_step": one["ms_per_step"], "unit": "events/s",
+                                                        "source": "profiles/r01_bench_cfg3_1gpu.json (committed measurement, not this run)"}
+            except Exception:
+                pass
         if world == 1 and not args.no_cpu_baseline:
             evs, ms, laps, cores, _, ws, kind = cpu_path(w, args.cpu_sample_events, 100, 2, budget_s=15.0)
             line["cpu_baseline"] = {"value": evs, "unit": "events/s", "cores": cores, "kind": kind, "ms_per_step": ms,
