@@ -4,11 +4,13 @@
 //     Evaluate :712-723 -> SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-111),
 //                          CalcSplineWeights :727-789, CalcTotalEventWeight :792-832
 //   SampleHandlerBase::GetTestStatLLH / GetPoissonLLH (Samples/SampleHandlerBase.cpp:17-193)
-// Those three translation units are compiled WHERE THEY LIE under /root/reference (see Makefile); nothing of
-// them is copied.  ROOT, spdlog and yaml-cpp are absent from this image: stubs/ holds compile-only stand-ins
-// (root_fwd.h) and shadows of three reference headers that exist only to pull those libraries in
-// (Manager/Manager.h, Manager/MaCh3Modes.h, Samples/HistogramUtils.h, Parameters/ParameterHandlerGeneric.h).
-// The code exercised here never calls into them: responses are handed over as the reference's own reduced
+// (the second half of this file adds SampleHandlerFD, BinningHandler and BinnedSplineHandler).  The reference's
+// translation units are compiled WHERE THEY LIE under /root/reference (see Makefile); nothing of them is copied.
+// ROOT, spdlog, yaml-cpp and NuOscillator are absent from this image: stubs/ holds compile-only stand-ins for their
+// headers (root_fwd.h, yaml-cpp/yaml.h, spdlog/spdlog.h: permissive classes that abort if ever called) and ONE shadow
+// of a reference header, Parameters/ParameterHandlerGeneric.h, whose real version needs ROOT's matrix classes; all
+// other reference headers (Manager.h, YamlHelper.h, MaCh3Modes.h, HistogramUtils.h, ...) are the reference's own.
+// The code exercised here never calls into the stand-ins: responses are handed over as the reference's own reduced
 // objects, TSpline3_red(X, Y, N, P) (Splines/SplineStructs.h:285) and TF1_red + SetSize/SetParameter (:215-234).
 //
 // TEST INFRASTRUCTURE (part of oracle/): pins the oracle's restatement of the host path to the reference itself
