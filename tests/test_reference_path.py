@@ -397,3 +397,65 @@ def test_reference_release_build_agrees_with_the_oracle_multithread_path():
         np.testing.assert_allclose(fd.hist()[0], osh.mc, rtol=1e-6, atol=1e-9)
         assert fd.llh() == pytest.approx(osh.GetLikelihood(), rel=1e-6, abs=1e-9)
     fd.close()
+
+
+# =====================================================================================================================
+# BASELINE config 1 at full size (the reference's own CPU-runnable case) against the reference's own code
+# =====================================================================================================================
+GOLD_CFG1 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_host_baseline.npz")
+CFG1_STEPS = (-1, 0, 1, 2, 3, -2, -3, 4)
+BASELINE_SHAPES = ("cfg1", "cfg2s", "cfg3s")
+
+
+def _shape(name):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_ref_host_baseline as G
+    return G, G.workloads()[name]
+
+
+@pytest.mark.parametrize("name", BASELINE_SHAPES)
+def test_oracle_baseline_shapes_match_reference(name, serial_oracle):
+    """cfg1 at full size, cfg2 / cfg3 shapes on samples: the oracle against the reference's own Reweight +
+    GetLikelihood, histogram bit for bit."""
+    from mach3_b200 import synth
+    g = np.load(GOLD_CFG1)
+    _, w = _shape(name)
+    mono, sh, d = O.build_from_workload(w)
+    for i, step in enumerate(CFG1_STEPS):
+        sp, nm = synth.proposal(w, step)
+        mono.set_params(sp); sh.norm_vals[:] = nm
+        sh.Reweight()
+        if i == 0:
+            sh.AddData(g[f"{name}/data"])
+        np.testing.assert_array_equal(sh.mc, g[f"{name}/mc"][i], err_msg=f"step {step}")
+        assert sh.GetLikelihood() == pytest.approx(float(g[f"{name}/llh"][i]), rel=1e-14)
+
+
+@pytest.mark.skipif(not RP.available(), reason="oracle/_ref/libm3ref_path_lm.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", BASELINE_SHAPES)
+def test_reference_rerun_reproduces_baseline_shapes(name):
+    G, w = _shape(name)
+    out, g = G.run(w), np.load(GOLD_CFG1)
+    for k in ("data", "mc", "llh"):
+        np.testing.assert_array_equal(out[k], g[f"{name}/{k}"], err_msg=k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", BASELINE_SHAPES)
+def test_device_baseline_shapes_match_reference(name):
+    """The fused step against the reference's own Reweight + GetLikelihood on BASELINE's shapes (config 1 at full
+    size).  Bars of north_star: -lnL within 1e-6 relative (asserted: 1e-10), histogram 1e-12."""
+    from mach3_b200 import handlers, synth
+    g = np.load(GOLD_CFG1)
+    _, w = _shape(name)
+    sh, d = handlers.build_from_workload(w)
+    for i, step in enumerate(CFG1_STEPS):
+        sp, nm = synth.proposal(w, step)
+        d["pars"][:] = sp; d["norm"][:] = nm
+        sh.Reweight()
+        if i == 0:
+            sh.GetLikelihood(); sh.AddData(g[f"{name}/data"])
+        llh = sh.GetLikelihood()
+        np.testing.assert_allclose(sh.handle.read_hist()[0], g[f"{name}/mc"][i], rtol=1e-12, atol=1e-12, err_msg=f"step {step}")
+        if i > 0:
+            assert llh == pytest.approx(float(g[f"{name}/llh"][i]), rel=1e-10)
