@@ -459,3 +459,41 @@ def test_device_baseline_shapes_match_reference(name):
         np.testing.assert_allclose(sh.handle.read_hist()[0], g[f"{name}/mc"][i], rtol=1e-12, atol=1e-12, err_msg=f"step {step}")
         if i > 0:
             assert llh == pytest.approx(float(g[f"{name}/llh"][i]), rel=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not RP.available_mt(), reason="oracle/_ref/libm3ref_path_lm_mt.so not built (needs /root/reference at build time)")
+def test_full_size_cfg2_against_the_reference_itself():
+    """BASELINE config 2 at FULL size (1M events x 50 responses, 900 bins), live: the reference's own multithreaded
+    SampleHandlerFD::Reweight + GetLikelihood (release build of its sources, on the box's host cores) next to the fused
+    B200 step, same proposals.  north_star's bar on -lnL: 1e-6 relative (the MULTITHREAD build reassociates float
+    products and double sums, so not bit-exact)."""
+    from mach3_b200 import handlers, synth
+    w = synth.CFG2
+    typ, npts, cx = synth.param_layout(w)
+    spl, ev = synth.make_splines(w), synth.make_events(w)
+    mono = RP.RefSMonolith.from_arrays(w.n_params, w.n_knots, cx, npts, typ, spl, build="float_mt")
+    fd = RP.RefSampleHandlerFD(synth.bin_edges(w), w.test_statistic, False, build="float_mt")
+    fd.attach_monolith(mono)
+    E = w.n_events
+    idx = np.arange(E, dtype=np.int32)
+    fd.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, w_before=idx, w_after=E + idx, n_pool=2 * E)
+    del spl
+    pool = np.concatenate([synth.make_osc(w, 0), ev["static_w"]]).astype(np.float64)
+    gsh, gd = handlers.build_from_workload(w)
+    worst = 0.0
+    for i, step in enumerate((-1, 0, 1, 2, 3)):
+        sp, nm = synth.proposal(w, step)
+        fd.reweight(sp, nm, pool if i == 0 else None)
+        gd["pars"][:] = sp; gd["norm"][:] = nm
+        gsh.Reweight()
+        if i == 0:
+            data = np.random.default_rng(w.seed).poisson(fd.hist()[0]).astype(np.float64)
+            fd.set_data(data); gsh.GetLikelihood(); gsh.AddData(data)
+        r, g = fd.llh(), gsh.GetLikelihood()
+        np.testing.assert_allclose(gsh.handle.read_hist()[0], fd.hist()[0], rtol=1e-6, atol=1e-9)
+        if i > 0:
+            worst = max(worst, abs(g - r) / abs(r))
+            assert abs(g - r) <= 1e-6 * abs(r), (step, g, r)
+    print(f"full-size cfg2: worst relative -lnL difference to the reference {worst:.2e}")
+    fd.close()
