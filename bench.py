@@ -120,7 +120,14 @@ def cpu_path(w, n_sample, steps, warmup, budget_s=None):
     from mach3_b200 import synth
     from oracle import ref_path_binding as RP     # the checker's reference build, here as the timed CPU baseline
     ws = w.scaled(min(n_sample, w.n_events))
-    if RP.available_mt():
+    use_ref = RP.available_mt()
+    if use_ref:
+        try:
+            RP.lib("float_mt")
+        except OSError as e:                      # the prebuilt library does not load on this box: time the port
+            print(f"bench.py: {e}; falling back to the oracle port for the CPU baseline", file=sys.stderr)
+            use_ref = False
+    if use_ref:
         kind = "reference"
         typ, npts, cx = synth.param_layout(ws)
         spl, ev = synth.make_splines(ws), synth.make_events(ws)
