@@ -11,6 +11,13 @@ rows serves the whole loop.
                    thrown parameter set samples[i]->Reweight() and the MC histogram of every sample (what WriteToy
                    stores); here all throws go through one m3b_step_batch_hist call.
 
+    EvaluateDelayedStages
+                   DelayedMR2T2::DoStep (Fitters/DelayedMR2T2.cpp:110-157) proposes up to max_rejections+1 stage
+                   points per step, each needing samples[i]->Reweight() + GetLikelihood() before the accept test.
+                   The stage proposals do not depend on the earlier stages' likelihoods (only on the random draws
+                   and the decaying step scale), so a fitter can draw them up front and evaluate them speculatively
+                   in one batch; it then walks the stages in order and stops at the first accepted one.
+
 Only the sample-likelihood part is computed here; the systematic (prior) terms of the scan come from the
 ParameterHandler and are out of scope.
 """
@@ -65,3 +72,15 @@ def ProduceToys(sample, spline_par_throws, norm_par_throws=None, chunk=256):
         tot, mc = h.step_batch_hist(sp[i0:i0 + chunk], None if nm is None else nm[i0:i0 + chunk])
         mcs.append(mc); llhs.append(tot)
     return np.concatenate(mcs, 0), np.concatenate(llhs)
+
+
+def EvaluateDelayedStages(sample, stage_spline_pars, stage_norm_pars=None):
+    """`sample`: mach3_b200.handlers.SampleHandlerFD.  stage_spline_pars[n_stages, n_params] /
+    stage_norm_pars[n_stages, n_norm]: the stage proposals of one delayed-rejection step, in stage order.  Returns
+    -lnL[n_stages] (sample part of logLProp for every stage), evaluated with the reference's sequential semantics in
+    stage order.  Difference to the reference loop: stages after the accepted one are evaluated too, so the cached
+    spline segment (Splines/SplineBase.cpp:76) may sit elsewhere afterwards -- it only matters for a later proposal
+    exactly on a knot."""
+    sp = np.ascontiguousarray(stage_spline_pars, np.float64)
+    nm = None if stage_norm_pars is None else np.ascontiguousarray(stage_norm_pars, np.float64)
+    return sample.handle.step_batch(sp, nm)

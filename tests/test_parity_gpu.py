@@ -439,6 +439,32 @@ def test_predictive_toys_match_the_reference_loop(oracle_build, update_w2):
         assert llh[k] == pytest.approx(osh.GetLikelihood(), rel=1e-9 if _exact() else LLH_RTOL, abs=1e-9)
 
 
+def test_delayed_rejection_stages_match_the_reference_loop(oracle_build):
+    """DelayedMR2T2's stage loop (Fitters/DelayedMR2T2.cpp:110-157): stage proposals with a decaying step scale around
+    the current point, each Reweight + GetLikelihood on the oracle; the speculative batch gives the same -lnL per stage."""
+    from mach3_b200 import fitters
+    w = synth.SPARSE.scaled(20_000)
+    mono, osh, od = O.build_from_workload(w)
+    gsh, gd = handlers.build_from_workload(w)
+    _set(w, -1, mono, osh, gsh, gd)
+    osh.Reweight(); gsh.Reweight(); gsh.GetLikelihood()
+    data = np.random.default_rng(14).poisson(osh.mc).astype(np.float64)
+    osh.AddData(data); gsh.AddData(data)
+    rng = np.random.default_rng(15)
+    cur_sp, cur_nm = synth.proposal(w, 7)
+    for step in range(3):
+        scale, sps, nms = 1.0, [], []
+        for stage in range(4):                                   # max_rejections = 3, decay_rate = 0.5
+            sps.append(cur_sp + scale * 0.4 * rng.normal(size=cur_sp.size)); nms.append(cur_nm + scale * 0.05 * rng.normal(size=cur_nm.size))
+            scale *= 0.5
+        got = fitters.EvaluateDelayedStages(gsh, np.stack(sps), np.stack(nms))
+        for stage in range(4):
+            mono.set_params(sps[stage]); osh.norm_vals[:] = nms[stage]
+            osh.Reweight()
+            assert got[stage] == pytest.approx(osh.GetLikelihood(), rel=1e-9 if _exact() else LLH_RTOL, abs=1e-9)
+        cur_sp, cur_nm = sps[int(np.argmin(got))], nms[int(np.argmin(got))]
+
+
 def test_fill_only_then_llh_from_hist_equals_fused(oracle_build):
     """The multi-GPU building blocks on one GPU: m3b_step_fill + m3b_llh_from_hist (what every rank runs around the
     exchange) give the fused step's histogram and -lnL; the histogram device pointer is stable across steps."""
