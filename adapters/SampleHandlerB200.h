@@ -19,10 +19,14 @@
 //           inside SMonolith::cpu_total_weights       the event's spline weight: produced on the device, dropped
 //           inside the oscillator's weight array      osc_idx = ptr - base          (SampleHandlerFD.cpp:1108-1122)
 //           &M3::Zero / &M3::Unity                    static factor 0 / 1           (:1128-1131)
-//           anything else                             read now, folded into the event's static weight
+//           inside PointerBases::constant_weight_ranges   read now, folded into the event's static weight
+//           anything else                             ERROR (a weight the device copy would never see change)
 //     EventInfo::KinVar[d]                 -> kin[d][e] = *ptr  (bins are found on the device; functional
-//                                             "shift" parameters, :545-564, are NOT supported by this adapter)
+//                                             "shift" parameters, :545-564, and CalcWeightFunc overrides, :428, are
+//                                             NOT supported by this adapter: it throws if funcParsGrid is non-empty)
 //     EventInfo::NominalSample             -> sample_id
+//     StoredSelection (KinematicCut lists, -> m3b_upload_selection: IsEventSelected (:281-294) runs on the device; the
+//       Samples/SampleHandlerFD.h:364-371)    cut variables are read once through ReturnKinematicParameter(var, event)
 //     BinningHandler (GetNDim/GetBinEdges/ -> m3b_upload_binning_ex         (uniform and non-uniform samples)
 //       IsUniform/GetNonUniformBins)
 //     SplineMonoStruct + SMonolith arrays  -> m3b_upload_spline_monolith    (pass them through SetMonolith())
@@ -69,6 +73,10 @@ struct PointerBases {
   const float* osc_base = nullptr;    int64_t n_osc = 0;     // the oscillator's weight array (may be null)
   const float* zero = nullptr;                               // &M3::Zero
   const float* unity = nullptr;                              // &M3::Unity
+  // Address ranges of experiment-specific weights (AddAdditionalWeightPointers) that never change during a fit, e.g. a
+  // per-event flux or POT weight array: {first, one-past-last}.  A weight pointer that is none of the above and lies
+  // in none of these ranges is an ERROR (it might be rewritten every step, which the device copy would not see).
+  std::vector<std::pair<const float*, const float*>> constant_weight_ranges;
 };
 
 template <class FDBase>
@@ -85,6 +93,10 @@ class SampleHandlerB200 : public FDBase {
     cfg.update_w2 = this->UpdateW2 ? 1 : 0;
     check(m3b_create(&cfg, &h_), "m3b_create");
     const int64_t E = static_cast<int64_t>(this->GetNEvents());
+    // functional ("shift") parameters rewrite the kinematics through std::functions every step (ApplyShifts,
+    // Samples/SampleHandlerFD.cpp:545-564): not something a constant device table can follow -- refuse, loudly
+    for (const auto& shifts : this->funcParsGrid)
+      if (!shifts.empty()) throw std::runtime_error("SampleHandlerB200: functional (shift) parameters are not supported by this adapter");
     bases_ = bases;
     spline_ptrs_ = mono.spline_par_pointers;
     spline_vals_.assign(spline_ptrs_.size(), 0.0);
@@ -153,7 +165,12 @@ class SampleHandlerB200 : public FDBase {
         } else if (p == bases.zero) {
           static_w[e] = 0.0f;                 // NC event with flavour change (SampleHandlerFD.cpp:1128-1131)
         } else if (p != bases.unity) {
-          static_w[e] *= static_cast<float>(*p);    // experiment-specific constant weight
+          bool constant = false;
+          for (const auto& r : bases.constant_weight_ranges) constant |= (p >= r.first && p < r.second);
+          if (!constant)
+            throw std::runtime_error("SampleHandlerB200: event " + std::to_string(e) + " has a weight pointer that is neither the "
+                                     "oscillation array, the spline monolith, M3::Zero/Unity nor inside PointerBases::constant_weight_ranges");
+          static_w[e] *= static_cast<float>(*p);    // experiment-specific constant weight, folded once
         }
       }
       any_osc |= has_osc;
@@ -181,6 +198,26 @@ class SampleHandlerB200 : public FDBase {
       check(m3b_alloc_host(h_, sizeof(float) * static_cast<size_t>(n_osc_dev_), &p), "m3b_alloc_host");
       osc_stage_ = static_cast<float*>(p);
       std::fill(osc_stage_, osc_stage_ + n_osc_dev_, 1.0f);
+    }
+    // --- selection cuts (Samples/SampleHandlerFD.cpp:281-294): one table row per distinct ParamToCutOnIt, filled
+    //     through the experiment's own ReturnKinematicParameter; without functional shifts the values are constants
+    {
+      std::vector<int32_t> cut_sample, cut_var, distinct;
+      std::vector<double> lo, hi;
+      for (int s = 0; s < nS && s < static_cast<int>(this->StoredSelection.size()); ++s)
+        for (const auto& c : this->StoredSelection[static_cast<size_t>(s)]) {
+          size_t v = 0;
+          while (v < distinct.size() && distinct[v] != c.ParamToCutOnIt) ++v;
+          if (v == distinct.size()) distinct.push_back(c.ParamToCutOnIt);
+          cut_sample.push_back(s); cut_var.push_back(static_cast<int32_t>(v)); lo.push_back(c.LowerBound); hi.push_back(c.UpperBound);
+        }
+      if (!cut_sample.empty()) {
+        std::vector<double> values(distinct.size() * static_cast<size_t>(E));
+        for (size_t v = 0; v < distinct.size(); ++v)
+          for (int64_t e = 0; e < E; ++e) values[v * static_cast<size_t>(E) + e] = this->ReturnKinematicParameter(distinct[v], static_cast<int>(e));
+        check(m3b_upload_selection(h_, static_cast<int32_t>(cut_sample.size()), cut_sample.data(), cut_var.data(), lo.data(), hi.data(),
+                                   static_cast<int32_t>(distinct.size()), values.data()), "m3b_upload_selection");
+      }
     }
     check(m3b_upload_data(h_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_upload_data");
     ready_ = true;

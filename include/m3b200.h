@@ -59,14 +59,15 @@ typedef enum {
 enum {
   M3B_FLAG_KEEP_EVENT_WEIGHTS = 1, /* write per-event spline + total weights every step (+8 B/event)   */
   M3B_FLAG_KEEP_KINEMATICS    = 2, /* keep kinematic variables on the device so bins can be recomputed */
-  M3B_FLAG_NO_FUSED_LLH       = 4  /* never fuse the LLH into the fill kernel (multi-GPU callers)      */
+  M3B_FLAG_NO_FUSED_LLH       = 4, /* never fuse the LLH into the fill kernel (multi-GPU callers)      */
+  M3B_FLAG_NO_BATCH_KERNEL    = 8  /* m3b_step_batch always runs sequential single-set launches         */
 };
 
 typedef struct {
   int32_t device;          /* CUDA ordinal                                                          */
   int32_t test_statistic;  /* m3b_test_statistic; LikelihoodOptions:TestStatistic (Manager.cpp:98-127)*/
   int32_t update_w2;       /* LikelihoodOptions:UpdateW2 (Samples/SampleHandlerFD.cpp:64)            */
-  int32_t tile_events;     /* events per tile row of the device layout: 0 (auto: 512 below 1.5M events, else 1024), 128..1024 */
+  int32_t tile_events;     /* events per tile row of the device layout: 0 (auto: 512 below 1.5M events, else 1024), 256, 512, 1024 */
   int32_t flags;           /* M3B_FLAG_*                                                            */
   int32_t reserved[11];
 } m3b_config;
@@ -188,6 +189,25 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
  *   variables (same layout as m3b_upload_events' kin) and the events are re-binned on the device.  Needs
  *   M3B_FLAG_KEEP_KINEMATICS.  Asynchronous; takes effect for the following steps.                             */
 M3B_API int m3b_update_kinematics(m3b_handle* h, const double* kin);
+/* m3b_upload_selection: SampleHandlerFD::IsEventSelected (Samples/SampleHandlerFD.cpp:281-294), applied to every
+ *   event before its weight is formed (FillArray :361, FillArray_MP :424): the per-sample lists of KinematicCut
+ *   {ParamToCutOnIt, LowerBound, UpperBound} (Samples/SampleStructs.h:149-157; StoredSelection, filled at
+ *   SampleHandlerFD.cpp:162 and copied into Selection at the top of every fill, :355/:393).  An event of sample s is
+ *   dropped when, for any cut k of that sample, Val < lower[k] || Val >= upper[k] (so Val == lower passes, Val ==
+ *   upper fails, NaN passes -- the reference's comparison).  Val = ReturnKinematicParameter(ParamToCutOnIt, event)
+ *   is experiment code, so the caller evaluates it once per distinct cut variable and hands the table over:
+ *     cut_sample[n_cuts], cut_var[n_cuts], lower[n_cuts], upper[n_cuts]      cuts in StoredSelection order
+ *     values[v*n_events + e], v < n_vars                                      the v-th cut variable of event e
+ *   cut_var[k] >= 0 indexes `values`; cut_var[k] = -1-d means "the event's d-th binning variable" (kin of
+ *   m3b_upload_events; needs M3B_FLAG_KEEP_KINEMATICS) and follows m3b_update_kinematics automatically.
+ *   After m3b_upload_events; replaces any earlier selection (n_cuts = 0 removes it).  Dropped events keep their
+ *   FindGlobalBin result in m3b_read_event_bins but never reach the histogram; m3b_read_event_selected gives the mask.
+ * m3b_update_selection_values: the cut variables after functional shifts (ApplyShifts runs before IsEventSelected,
+ *   SampleHandlerFD.cpp:359-361): same layout as `values`; the selection is re-evaluated on the device.          */
+M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* cut_sample, const int32_t* cut_var,
+                                 const double* lower, const double* upper, int32_t n_vars, const double* values);
+M3B_API int m3b_update_selection_values(m3b_handle* h, const double* values);
+M3B_API int m3b_read_event_selected(m3b_handle* h, uint8_t* selected /* [n_events] 1 = passes every cut */);
 /* SampleHandlerFD::AddData (Samples/SampleHandlerFD.cpp:955-1044), array form */
 M3B_API int m3b_upload_data(m3b_handle* h, const double* data, int32_t n_bins);
 /* oscillation weights computed elsewhere (NuOscillator) and already valid for the next steps    */

@@ -65,8 +65,11 @@ def build_cuda(force=False, verbose=False):
         cmd = [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                "-ccbin", GXX, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", out, *srcs,
                "-Xptxas", "-v", "-lcudart"]
+        if os.environ.get("M3B_BUILD_EXPERIMENTS"):      # A/B builds only: legacy kernel variants + M3B_* environment knobs
+            cmd.insert(1, "-DM3B_EXPERIMENTS")
         log = _run(cmd, verbose)
-        with open(os.path.join(PKG, "ptxas.log"), "w") as f:
+        os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)          # git-ignored; registers / spills per kernel
+        with open(os.path.join(ROOT, "build", "ptxas.log"), "w") as f:
             f.write(log)
     return out
 

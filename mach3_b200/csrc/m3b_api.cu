@@ -7,6 +7,17 @@
 static thread_local std::string g_last_error;
 std::string& m3b_last_error_slot() { return g_last_error; }
 
+// Tuning knobs read from the environment exist only in -DM3B_EXPERIMENTS builds (A/B measurements); the product
+// library takes its configuration from m3b_config alone.
+static inline const char* experiment_env(const char* name) {
+#ifdef M3B_EXPERIMENTS
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 extern "C" {
 
 M3B_API int m3b_abi_version(void) { return 1; }
@@ -29,8 +40,8 @@ M3B_API int m3b_create(const m3b_config* cfg, m3b_handle** out) {
     return fail(nullptr, M3B_ERR_NODEVICE, std::string("m3b_create: device '") + prop.name +
                                                "' is not sm_100 (kernels are built for sm_100a only)");
   const int T = cfg->tile_events == 0 ? 1024 : cfg->tile_events;
-  if (T != 128 && T != 256 && T != 512 && T != 1024)
-    return fail(nullptr, M3B_ERR_INVALID, "m3b_create: tile_events must be 128, 256, 512 or 1024");
+  if (T != 256 && T != 512 && T != 1024)
+    return fail(nullptr, M3B_ERR_INVALID, "m3b_create: tile_events must be 0 (auto), 256, 512 or 1024");
   h = new m3b_handle();
   h->cfg = *cfg;
   h->device = cfg->device;
@@ -321,11 +332,25 @@ M3B_API int m3b_upload_spline_monolith(m3b_handle* h, int32_t n_params, int32_t 
 // ------------------------------------------------------------------------------------------------
 // binning, events, data
 // ------------------------------------------------------------------------------------------------
+static int upload_binning_body(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* uniform,
+                               const int32_t* nbins, const double* edges);
+// a rejected upload leaves the handle as it was (no half-initialised binning)
 static int upload_binning_impl(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* uniform,
                                const int32_t* nbins, const double* edges) {
   REQUIRE(h, M3B_ERR_INVALID, "null handle");
   REQUIRE(n_samples > 0 && n_samples <= 64 && n_dim && nbins && edges, M3B_ERR_INVALID, "m3b_upload_binning: bad argument (1..64 samples)");
   REQUIRE(h->n_samples == 0, M3B_ERR_STATE, "m3b_upload_binning: binning already uploaded");
+  const int rc = upload_binning_body(h, n_samples, n_dim, uniform, nbins, edges);
+  if (rc != M3B_OK) {
+    h->n_samples = 0; h->n_bins = 0;
+    h->b_ndim.clear(); h->b_nbins.clear(); h->b_edge_off.clear(); h->b_stride.clear(); h->b_goff.clear(); h->sample_start.clear();
+    h->b_edges.clear(); h->b_uniform.clear(); h->b_box_off.clear(); h->b_grid_off.clear(); h->b_grid_start.clear();
+    h->b_grid_idx.clear(); h->b_boxes.clear();
+  }
+  return rc;
+}
+static int upload_binning_body(m3b_handle* h, int32_t n_samples, const int32_t* n_dim, const int32_t* uniform,
+                               const int32_t* nbins, const double* edges) {
   CK(cudaSetDevice(h->device));
   h->n_samples = n_samples;
   h->b_ndim.assign(n_dim, n_dim + n_samples);
@@ -483,8 +508,9 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
   {
     int32_t* d_sid = nullptr; double* d_kin = nullptr;
     const bool keep = (h->cfg.flags & M3B_FLAG_KEEP_KINEMATICS) != 0;
-    if (keep) { CK(dev_alloc(h, &d_sid, static_cast<size_t>(E))); CK(dev_alloc(h, &d_kin, static_cast<size_t>(E) * max_dim)); }
-    else { CK(cudaMalloc(&d_sid, sizeof(int32_t) * E)); CK(cudaMalloc(&d_kin, sizeof(double) * E * max_dim)); }
+    CK(dev_alloc(h, &d_sid, static_cast<size_t>(E)));          // kept: a later m3b_upload_selection needs the samples
+    if (keep) CK(dev_alloc(h, &d_kin, static_cast<size_t>(E) * max_dim));
+    else CK(cudaMalloc(&d_kin, sizeof(double) * E * max_dim));
     CK(cudaMemcpyAsync(d_sid, sample_id, sizeof(int32_t) * E, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_kin, kin, sizeof(double) * E * max_dim, cudaMemcpyHostToDevice, h->stream));
     BinArgs ba{};
@@ -495,7 +521,9 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
     ba.grid_start = h->d_grid_start; ba.grid_idx = h->d_grid_idx;
     CK(launch_bins(ba, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (keep) { h->d_sample_id = d_sid; h->d_kin = d_kin; h->kin_dims = max_dim; } else { cudaFree(d_sid); cudaFree(d_kin); }
+    h->d_sample_id = d_sid; h->kin_dims = max_dim;
+    if (keep) h->d_kin = d_kin; else cudaFree(d_kin);
+    h->d_bin_raw = h->d_bin;
   }
   // norm bindings, transposed to [slot][event] and padded
   h->norm_slots = norm_idx ? n_norm_per_event : 0;
@@ -539,6 +567,87 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
   return M3B_OK;
 }
 
+// SampleHandlerFD::IsEventSelected (Samples/SampleHandlerFD.cpp:281-294) over the uploaded cuts: bin[] = bin_raw[] or -1
+static int run_selection(m3b_handle* h) {
+  if (h->n_cuts == 0) return M3B_OK;
+  SelectArgs sa{};
+  sa.n_events = h->n_events; sa.e_pad = h->e_pad; sa.sample_id = h->d_sample_id;
+  sa.cut_start = h->d_cut_start; sa.cut_var = h->d_cut_var; sa.lower = h->d_cut_lo; sa.upper = h->d_cut_hi;
+  sa.values = h->d_sel_vals; sa.kin = h->d_kin; sa.bin_raw = h->d_bin_raw; sa.bin = h->d_bin; sa.selected = h->d_selected;
+  CK(launch_select(sa, h->stream));
+  ++h->launches;
+  return M3B_OK;
+}
+
+M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* cut_sample, const int32_t* cut_var,
+                                 const double* lower, const double* upper, int32_t n_vars, const double* values) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  REQUIRE(h->n_events > 0 && h->d_sample_id, M3B_ERR_STATE, "m3b_upload_selection: upload the events first");
+  REQUIRE(n_cuts >= 0 && n_vars >= 0, M3B_ERR_INVALID, "m3b_upload_selection: negative count");
+  REQUIRE(n_cuts == 0 || (cut_sample && cut_var && lower && upper), M3B_ERR_INVALID, "m3b_upload_selection: null cut arrays");
+  REQUIRE(n_vars == 0 || values, M3B_ERR_INVALID, "m3b_upload_selection: null cut-variable table");
+  bool uses_kin = false;
+  for (int k = 0; k < n_cuts; ++k) {
+    REQUIRE(cut_sample[k] >= 0 && cut_sample[k] < h->n_samples, M3B_ERR_INVALID, "m3b_upload_selection: cut_sample out of range");
+    REQUIRE(cut_var[k] < n_vars && cut_var[k] >= -h->kin_dims, M3B_ERR_INVALID, "m3b_upload_selection: cut_var out of range");
+    uses_kin |= cut_var[k] < 0;
+  }
+  REQUIRE(!uses_kin || h->d_kin, M3B_ERR_STATE, "m3b_upload_selection: cuts on binning variables (cut_var < 0) need M3B_FLAG_KEEP_KINEMATICS");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (n_cuts == 0) {                        // selection removed: every event is back in
+    if (h->d_bin_raw != h->d_bin) CK(cudaMemcpy(h->d_bin, h->d_bin_raw, sizeof(int32_t) * h->e_pad, cudaMemcpyDeviceToDevice));
+    if (h->d_selected) CK(cudaMemset(h->d_selected, 1, static_cast<size_t>(h->e_pad)));
+    h->n_cuts = 0;
+    return M3B_OK;
+  }
+  // cuts grouped by sample, StoredSelection order kept inside a sample (the first failing cut decides; any order gives
+  // the same answer, but the order of evaluation is the reference's)
+  std::vector<int32_t> start(static_cast<size_t>(h->n_samples) + 1, 0), var(n_cuts);
+  std::vector<double> lo(n_cuts), hi(n_cuts);
+  for (int k = 0; k < n_cuts; ++k) ++start[cut_sample[k] + 1];
+  for (int s = 0; s < h->n_samples; ++s) start[s + 1] += start[s];
+  std::vector<int32_t> fill(start.begin(), start.end() - 1);
+  for (int k = 0; k < n_cuts; ++k) { const int j = fill[cut_sample[k]]++; var[j] = cut_var[k]; lo[j] = lower[k]; hi[j] = upper[k]; }
+  if (h->d_bin_raw == h->d_bin) {           // first selection on this handle: keep FindGlobalBin's answer aside
+    CK(dev_alloc(h, &h->d_bin_raw, static_cast<size_t>(h->e_pad)));
+    CK(cudaMemcpy(h->d_bin_raw, h->d_bin, sizeof(int32_t) * h->e_pad, cudaMemcpyDeviceToDevice));
+    CK(dev_alloc(h, &h->d_selected, static_cast<size_t>(h->e_pad)));
+    CK(cudaMemset(h->d_selected, 0, static_cast<size_t>(h->e_pad)));
+  }
+  CK(dev_upload(h, &h->d_cut_start, start));
+  CK(dev_upload(h, &h->d_cut_var, var));
+  CK(dev_upload(h, &h->d_cut_lo, lo));
+  CK(dev_upload(h, &h->d_cut_hi, hi));
+  if (n_vars > 0) {
+    if (n_vars != h->n_sel_vars) CK(dev_alloc(h, &h->d_sel_vals, static_cast<size_t>(n_vars) * h->n_events));
+    CK(cudaMemcpy(h->d_sel_vals, values, sizeof(double) * n_vars * h->n_events, cudaMemcpyHostToDevice));
+  }
+  h->n_cuts = n_cuts; h->n_sel_vars = n_vars; h->sel_uses_kin = uses_kin;
+  int rc = run_selection(h);
+  if (rc != M3B_OK) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return M3B_OK;
+}
+
+M3B_API int m3b_update_selection_values(m3b_handle* h, const double* values) {
+  REQUIRE(h && values, M3B_ERR_INVALID, "m3b_update_selection_values: null argument");
+  REQUIRE(h->n_cuts > 0 && h->n_sel_vars > 0, M3B_ERR_STATE, "m3b_update_selection_values: no selection with cut variables uploaded");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_sel_vals, values, sizeof(double) * h->n_sel_vars * h->n_events, cudaMemcpyHostToDevice, h->stream));
+  return run_selection(h);
+}
+
+M3B_API int m3b_read_event_selected(m3b_handle* h, uint8_t* selected) {
+  REQUIRE(h && selected, M3B_ERR_INVALID, "m3b_read_event_selected: null argument");
+  REQUIRE(h->n_events > 0, M3B_ERR_STATE, "m3b_read_event_selected: no events");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (!h->d_selected) { memset(selected, 1, static_cast<size_t>(h->n_events)); return M3B_OK; }
+  CK(cudaMemcpy(selected, h->d_selected, static_cast<size_t>(h->n_events), cudaMemcpyDeviceToHost));
+  return M3B_OK;
+}
+
 // Functional ("shift") parameters (Samples/SampleHandlerFD.cpp:545-564) call arbitrary std::functions per event, so they
 // stay on the host: the caller applies its shifts to the kinematic variables and hands the shifted values over; the
 // events are re-binned on the device with the same FindGlobalBin semantics.  Asynchronous on the handle's stream.
@@ -550,12 +659,12 @@ M3B_API int m3b_update_kinematics(m3b_handle* h, const double* kin) {
   BinArgs ba{};
   ba.n_events = h->n_events; ba.e_pad = h->e_pad; ba.sample_id = h->d_sample_id; ba.kin = h->d_kin; ba.n_samples = h->n_samples;
   ba.n_dim = h->d_ndim; ba.nbins = h->d_nbins; ba.edge_off = h->d_edge_off; ba.stride = h->d_stride;
-  ba.global_off = h->d_goff; ba.edges = h->d_edges; ba.bin = h->d_bin;
+  ba.global_off = h->d_goff; ba.edges = h->d_edges; ba.bin = h->d_bin_raw;
   ba.uniform = h->d_uniform; ba.box_off = h->d_box_off; ba.grid_off = h->d_grid_off; ba.boxes = h->d_boxes;
   ba.grid_start = h->d_grid_start; ba.grid_idx = h->d_grid_idx;
   CK(launch_bins(ba, h->stream));
   ++h->launches;
-  return M3B_OK;
+  return run_selection(h);       // ApplyShifts runs before IsEventSelected (Samples/SampleHandlerFD.cpp:359-361)
 }
 
 M3B_API int m3b_upload_data(m3b_handle* h, const double* data, int32_t n_bins) {
@@ -700,10 +809,11 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
   if (!h->launch_ready || h->launch_w2_live != w2_live) {
     FillArgs a{};
     a.step = h->step; a.max_nc = h->max_nc; a.max_nl = h->max_nl; a.n_bins = h->n_bins; a.n_samples = h->n_samples;
-    // kernel choice: M3B_VARIANT=tma (default) | 0..5 (LDG register-streaming variants, m3b_kernels.cu)
+    h->use_tma = !h->binned;
+#ifdef M3B_EXPERIMENTS   // M3B_VARIANT=0..5: the register-streaming predecessor (m3b_kernels.cu), A/B only
     const char* v = getenv("M3B_VARIANT");
-    h->use_tma = h->T % 256 == 0 && !h->binned;
-    if (v && v[0] >= '0' && v[0] <= '9') { h->use_tma = false; h->variant = atoi(v); }
+    if (v && v[0] >= '0' && v[0] <= '9' && !h->binned) { h->use_tma = false; h->variant = atoi(v); }
+#endif
     if (h->binned) {
       // BinnedSplineHandler path: evaluate the non-flat splines, then gather/fill (m3b_binned.cu)
       int smem = binned_fill_smem_bytes(a, true, w2_live);
@@ -720,12 +830,11 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
       h->launch_w2_live = w2_live;
       return M3B_OK;
     }
-    REQUIRE(h->use_tma || h->T <= 512, M3B_ERR_INVALID, "step: the register-streaming kernel variants need tile_events <= 512");
     const int llh_scratch = h->n_samples * 32 * 8;
     if (h->use_tma) {
       // ring of 32 KB stages in whatever shared memory the fixed tables (and the privatised
       // histogram, if it fits next to >= 3 stages) leave of the 227 KB opt-in limit
-      const char* be = getenv("M3B_TMA_BLOCKS_PER_SM");
+      const char* be = experiment_env("M3B_TMA_BLOCKS_PER_SM");
       const int want_bps = be && atoi(be) > 1 ? atoi(be) : 1;
       const int budget = (232448 - 1024 * want_bps) / want_bps - 1024;     // static barriers + per-block reserve
       auto stages_for = [&](bool hist) {
@@ -735,7 +844,7 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
       h->hist_in_smem = true;
       int ns = stages_for(true);
       if (ns < 3) { h->hist_in_smem = false; ns = stages_for(false); }
-      const char* se = getenv("M3B_TMA_STAGES");
+      const char* se = experiment_env("M3B_TMA_STAGES");
       if (se && atoi(se) > 0) ns = std::min(ns, atoi(se));
       REQUIRE(ns >= 2, M3B_ERR_NOMEM, "step: per-step tables leave no room for the coefficient ring in shared memory");
       h->tma_stages = ns;
@@ -749,6 +858,7 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
       const int64_t units = h->n_tiles * (h->T / 256);
       h->grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(std::min(bps, want_bps)) * h->sm_count));
     }
+#ifdef M3B_EXPERIMENTS
     if (!h->use_tma) {
       int smem = fill_smem_bytes(a, true, w2_live);
       h->hist_in_smem = smem <= 200 * 1024;
@@ -762,6 +872,7 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
       const char* g = getenv("M3B_GRID_BLOCKS_PER_SM");
       if (g && atoi(g) > 0) h->grid = static_cast<int>(std::min<int64_t>(h->n_tiles, static_cast<int64_t>(std::min(atoi(g), bps)) * h->sm_count));
     }
+#endif
     h->launch_ready = true;
     h->launch_w2_live = w2_live;
   }
@@ -778,9 +889,9 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   // Oscillation weights handed over in pinned (registered) host memory are not copied: the TMA
   // kernel's producers stream them over PCIe while the coefficients stream from HBM.
   const float* osc_zc = nullptr;
-  if (osc_w && h->use_osc && !h->d_osc_idx && h->T % 256 == 0) {
+  if (osc_w && h->use_osc && !h->d_osc_idx) {
     // asked every step (about a microsecond): the caller may have re-registered or re-allocated the array
-    static const bool zc_off = [] { const char* z = getenv("M3B_OSC_ZEROCOPY"); return z && z[0] == '0'; }();
+    static const bool zc_off = [] { const char* z = experiment_env("M3B_OSC_ZEROCOPY"); return z && z[0] == '0'; }();
     cudaPointerAttributes at{};
     if (!zc_off && cudaPointerGetAttributes(&at, osc_w) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
         (reinterpret_cast<uintptr_t>(at.devicePointer) & 15) == 0)
@@ -793,7 +904,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   if (!h->use_tma) osc_zc = nullptr;
 
   // per-step table {segment, dx, value, norm}
-  static const bool no_inline_env = getenv("M3B_NO_INLINE_STEP") != nullptr;
+  static const bool no_inline_env = experiment_env("M3B_NO_INLINE_STEP") != nullptr;
   const bool inline_step = h->step.bytes <= kStepInlineMax && !no_inline_env;
   FillArgs a{};
   const int slot = h->ring;
@@ -883,9 +994,9 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     a.tile_counter = h->d_tile_counter; a.n_stages = h->tma_stages; a.tma = h->tma;
     // queued fused steps overlap (programmatic dependent launch) unless something reads/writes per-event outputs or
     // brackets the kernel with timing events
-    static const bool pdl_off = [] { const char* z = getenv("M3B_PDL"); return z && z[0] == '0'; }();
+    static const bool pdl_off = [] { const char* z = experiment_env("M3B_PDL"); return z && z[0] == '0'; }();
     a.pdl = (!pdl_off && mode == kFused && h->hist_in_smem && !h->timing && !h->d_evt_spline_w && !osc_zc && !h->d_trace) ? 1 : 0;
-    static const int guard_env = [] { const char* ge = getenv("M3B_GUARD_X2"); return ge && atoi(ge) > 0 ? atoi(ge) : 6; }();
+    static const int guard_env = [] { const char* ge = experiment_env("M3B_GUARD_X2"); return ge && atoi(ge) > 0 ? atoi(ge) : 6; }();
     a.guard_x2 = guard_env;
   }
   a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->llh_host_override ? h->llh_host_override : h->h_llh_dev;
@@ -920,7 +1031,9 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     if (h->n_btiles > 0) { CK(launch_binned_eval(a, h->binned_eval_grid, h->stream)); ++h->launches; }
     CK(launch_binned_fill(a, h->grid, h->smem, h->stream));
   } else if (h->use_tma) CK(launch_fill_tma(a, h->grid, h->smem, h->stream));
+#ifdef M3B_EXPERIMENTS
   else CK(launch_fill(a, h->variant, h->grid, h->smem, h->stream));
+#endif
   if (h->timing) { CK(cudaEventRecord(h->tev[h->tev_used + 1], h->stream)); h->tev_used += 2; }
   ++h->launches;
   if (mode == kPeer) {
@@ -998,6 +1111,7 @@ static int ensure_standalone_events(m3b_handle* h) {
   h->e_pad = h->n_tiles * T;
   CK(dev_alloc(h, &h->d_bin, static_cast<size_t>(h->e_pad)));
   CK(cudaMemset(h->d_bin, 0xFF, sizeof(int32_t) * h->e_pad));       // bin -1: nothing is ever filled
+  h->d_bin_raw = h->d_bin;
   if (!h->d_evt_spline_w) {
     CK(dev_alloc(h, &h->d_evt_spline_w, static_cast<size_t>(h->e_pad)));
     CK(dev_alloc(h, &h->d_evt_total_w, static_cast<size_t>(h->e_pad)));
@@ -1038,12 +1152,14 @@ static int step_batch_impl(m3b_handle* h, int32_t n_sets, const double* spline_p
   REQUIRE(n_sets > 0, M3B_ERR_INVALID, "m3b_step_batch: n_sets must be positive");
   REQUIRE(h->peer_world == 0 && !(h->cfg.flags & M3B_FLAG_NO_FUSED_LLH), M3B_ERR_STATE, "m3b_step_batch: single-GPU fused handles only");
   REQUIRE(h->n_bins > 0, M3B_ERR_STATE, "m3b_step_batch: upload binning and events first");
+  REQUIRE(h->P == 0 || spline_pars, M3B_ERR_INVALID, "m3b_step_batch: spline_pars is NULL");
+  REQUIRE(h->n_norm_values == 0 || norm_pars, M3B_ERR_INVALID, "m3b_step_batch: norm_pars is NULL but events carry norm pointers");
   CK(cudaSetDevice(h->device));
   const size_t slot = static_cast<size_t>(1 + h->n_samples);
   if (h->batch_cap < static_cast<size_t>(n_sets)) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_batch) cudaFreeHost(h->h_batch);
-  for (void* p : {h->bt_dx, h->bt_rowoff, h->bt_val, h->bt_rowlist, h->bt_norm, h->bt_sigs, h->bt_hist, h->bt_llh, h->bt_slot}) if (p) cudaFree(p);
+    h->h_batch = nullptr; h->batch_cap = 0;      // (the kernel's own staging buffers are sized by m3b_batch_try)
     CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_batch), sizeof(double) * slot * n_sets, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_batch_dev), h->h_batch, 0));
     h->batch_cap = static_cast<size_t>(n_sets);
@@ -1170,7 +1286,8 @@ M3B_API int m3b_read_event_bins(m3b_handle* h, int32_t* bins) {
   REQUIRE(h && bins, M3B_ERR_INVALID, "m3b_read_event_bins: null argument");
   REQUIRE(h->n_events > 0, M3B_ERR_STATE, "m3b_read_event_bins: no events");
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpy(bins, h->d_bin, sizeof(int32_t) * h->n_events, cudaMemcpyDeviceToHost));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(bins, h->d_bin_raw, sizeof(int32_t) * h->n_events, cudaMemcpyDeviceToHost));
   return M3B_OK;
 }
 
@@ -1270,7 +1387,7 @@ M3B_API int m3b_block_trace(m3b_handle* h, uint64_t* out, int32_t* grid) {
     CK(cudaStreamSynchronize(h->stream));
     REQUIRE(h->grid <= 4096, M3B_ERR_INVALID, "m3b_block_trace: grid too large");
     CK(cudaMemcpy(out, h->d_trace, sizeof(unsigned long long) * 8 * h->grid, cudaMemcpyDeviceToHost));
-    if (getenv("M3B_TRACE_LAST")) {
+    if (experiment_env("M3B_TRACE_LAST")) {
       unsigned long long last[2];
       CK(cudaMemcpy(last, h->d_trace + 8 * 4000, sizeof last, cudaMemcpyDeviceToHost));
       unsigned long long t0 = ~0ull;

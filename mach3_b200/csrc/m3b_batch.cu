@@ -255,7 +255,7 @@ int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, cons
                   double* host_slots_dev, int* done) {
   *done = 0;
   if (h->binned || !h->splines_done || h->first_time_w2 || h->cfg.update_w2 || n_sets > kBSets || h->T % kBT != 0) return M3B_OK;
-  if (getenv("M3B_NO_BATCH_KERNEL")) return M3B_OK;
+  if (h->cfg.flags & M3B_FLAG_NO_BATCH_KERNEL) return M3B_OK;
   if (h->tiles_dirty || !h->d_tiles) return M3B_OK;     // first step has not run yet
   CK(cudaSetDevice(h->device));
   if (h->Kmax > 64) return M3B_OK;

@@ -70,7 +70,14 @@ struct m3b_handle {
 
   // ---- events
   int64_t n_events = 0, e_pad = 0, n_tiles = 0;
-  int32_t* d_bin = nullptr;
+  int32_t* d_bin = nullptr;              // what the fill kernels read (bin_raw, or -1 for events the selection drops)
+  int32_t* d_bin_raw = nullptr;          // FindGlobalBin per event; == d_bin while no selection is uploaded
+  // selection (SampleHandlerFD::IsEventSelected): cuts CSR by sample + the caller's cut-variable table
+  int n_cuts = 0, n_sel_vars = 0;
+  bool sel_uses_kin = false;
+  int32_t *d_cut_start = nullptr, *d_cut_var = nullptr;
+  double *d_cut_lo = nullptr, *d_cut_hi = nullptr, *d_sel_vals = nullptr;
+  uint8_t* d_selected = nullptr;
   int32_t* d_osc_idx = nullptr;
   float* d_osc = nullptr;
   int64_t n_osc = 0;

@@ -199,6 +199,20 @@ struct BinArgs {
   const int32_t* grid_idx;
 };
 
+// SampleHandlerFD::IsEventSelected on the device (m3b_upload_selection)
+struct SelectArgs {
+  int64_t n_events, e_pad;
+  const int32_t* sample_id;
+  const int32_t* cut_start;    // [n_samples+1] CSR over the cut arrays below
+  const int32_t* cut_var;      // >= 0: row of `values`; -1-d: row d of `kin`
+  const double* lower; const double* upper;
+  const double* values;        // [v * n_events + e]
+  const double* kin;           // [d * n_events + e] (may be null when no cut refers to it)
+  const int32_t* bin_raw;      // FindGlobalBin per event
+  int32_t* bin;                // what the fill kernels read: bin_raw, or -1 for a rejected event
+  uint8_t* selected;
+};
+
 struct RetileArgs {
   int64_t n;                   // events in chunk
   int64_t tile0_event;         // chunk's first event is the first lane of a tile
@@ -226,6 +240,7 @@ cudaError_t launch_llh(const LlhArgs& a, cudaStream_t s);
 cudaError_t launch_llh_pull(const LlhArgs& a, int blocks, cudaStream_t s);
 constexpr int kLlhPullMaxBlocks = 32;
 cudaError_t launch_bins(const BinArgs& a, cudaStream_t s);
+cudaError_t launch_select(const SelectArgs& a, cudaStream_t s);
 cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s);
 cudaError_t fill_occupancy(int T, int variant, int smem_bytes, int* blocks_per_sm);
 cudaError_t fill_set_smem(int T, int variant, int smem_bytes);

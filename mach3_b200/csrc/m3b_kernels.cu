@@ -1,14 +1,7 @@
 // m3b_kernels.cu -- hand-written sm_100a kernels of the MaCh3 per-step likelihood hot path.
 //
-//   fill_kernel   fused   SMonolith::CalcSplineWeights + CalcTotalEventWeight
-//                         (Splines/SplineMonolith.cpp:727-830)
-//                       + SampleHandlerFD::CalcWeightTotal + FillArray_MP
-//                         (Samples/SampleHandlerFD.cpp:390-448, 568-594)
-//                       + SampleHandlerFD::GetLikelihood / SampleHandlerBase::GetTestStatLLH
-//                         (Samples/SampleHandlerFD.cpp:1284-1300, Samples/SampleHandlerBase.cpp:17-192)
-//                 one launch per MCMC step: HBM-bound coefficient stream -> registers -> per-event
-//                 product -> shared-memory privatised histogram -> global f64 reduction -> the last
-//                 block to finish reduces the likelihood (block-then-grid) and returns one scalar.
+//   (the fused per-step kernel itself is fill_tma_kernel, m3b_fill_tma.cu; its register-streaming
+//    predecessor fill_kernel<> below is compiled only with -DM3B_EXPERIMENTS)
 //   llh_kernel    the likelihood reduction alone (after a multi-GPU histogram exchange)
 //   bin_kernel    BinningHandler::FindGlobalBin (Samples/BinningHandler.cpp:257-277) per event
 //   retile_*      AoS reference monolith -> tiled SoA device layout (setup time)
@@ -18,6 +11,7 @@
 
 namespace m3b {
 
+#ifdef M3B_EXPERIMENTS   // the first design (register-streaming loads), kept out of the product build: A/B experiments only
 // ------------------------------------------------------------------------------------------------
 // the fused per-step kernel
 // ------------------------------------------------------------------------------------------------
@@ -178,6 +172,8 @@ cudaError_t fill_occupancy(int T, int variant, int smem, int* bps) {
   return cudaSuccess;
 }
 
+#endif  // M3B_EXPERIMENTS
+
 // ------------------------------------------------------------------------------------------------
 // likelihood alone (after an external all-reduce of the histogram)
 // ------------------------------------------------------------------------------------------------
@@ -323,6 +319,32 @@ cudaError_t launch_bins(const BinArgs& a, cudaStream_t s) {
   const int threads = 256;
   const int64_t blocks = (a.e_pad + threads - 1) / threads;
   bin_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// SampleHandlerFD::IsEventSelected (Samples/SampleHandlerFD.cpp:281-294): the event fails on the first cut of its
+// sample with Val < LowerBound || Val >= UpperBound.  A rejected event never reaches CalcWeightTotal or the
+// histogram (:361, :424): the fill kernels see bin -1 for it.
+// ------------------------------------------------------------------------------------------------
+__global__ void select_kernel(const __grid_constant__ SelectArgs a) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= a.e_pad) return;
+  if (e >= a.n_events) { a.bin[e] = -1; return; }
+  const int s = a.sample_id[e];
+  bool ok = true;
+  for (int k = a.cut_start[s]; k < a.cut_start[s + 1] && ok; ++k) {
+    const int v = a.cut_var[k];
+    const double val = v >= 0 ? a.values[static_cast<int64_t>(v) * a.n_events + e]
+                              : a.kin[static_cast<int64_t>(-1 - v) * a.n_events + e];
+    if ((val < a.lower[k]) || (val >= a.upper[k])) ok = false;
+  }
+  a.selected[e] = ok ? 1 : 0;
+  a.bin[e] = ok ? a.bin_raw[e] : -1;
+}
+cudaError_t launch_select(const SelectArgs& a, cudaStream_t s) {
+  const int threads = 256;
+  select_kernel<<<static_cast<unsigned>((a.e_pad + threads - 1) / threads), threads, 0, s>>>(a);
   return cudaGetLastError();
 }
 

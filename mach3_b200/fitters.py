@@ -78,9 +78,19 @@ def EvaluateDelayedStages(sample, stage_spline_pars, stage_norm_pars=None):
     """`sample`: mach3_b200.handlers.SampleHandlerFD.  stage_spline_pars[n_stages, n_params] /
     stage_norm_pars[n_stages, n_norm]: the stage proposals of one delayed-rejection step, in stage order.  Returns
     -lnL[n_stages] (sample part of logLProp for every stage), evaluated with the reference's sequential semantics in
-    stage order.  Difference to the reference loop: stages after the accepted one are evaluated too, so the cached
-    spline segment (Splines/SplineBase.cpp:76) may sit elsewhere afterwards -- it only matters for a later proposal
-    exactly on a knot."""
+    stage order.
+
+    This is a speculative evaluator, NOT a re-implementation of DelayedMR2T2::DoStep (Fitters/DelayedMR2T2.cpp:110-157);
+    the caller that pre-draws the stages must reproduce the reference's rules itself:
+      * stage i+1 is proposed around stage i's proposal (the AcceptStep "leapfrog", :124-127), with the step scale
+        multiplied by DecayRate only when stage i was actually evaluated and rejected (:152-153) -- a stage that is out
+        of bounds or has logLProp > MinLogLikelihood `continue`s WITHOUT the decay (:129-131);
+      * the reference interleaves its random draws (ProposeStep, IsStepAccepted, ProbabilisticDelay) stage by stage;
+        drawing all proposals first changes the order in which the RNG stream is consumed, so a chain built on this
+        helper is statistically equivalent to, but not step-for-step identical with, the reference's chain;
+      * stages after the accepted one are evaluated too, so the cached spline segment (Splines/SplineBase.cpp:76) may
+        sit elsewhere afterwards -- it only matters for a later proposal exactly on a knot.
+    The C++ form with these rules built in is adapters/BatchFitters.h (DelayedStages)."""
     sp = np.ascontiguousarray(stage_spline_pars, np.float64)
     nm = None if stage_norm_pars is None else np.ascontiguousarray(stage_norm_pars, np.float64)
     return sample.handle.step_batch(sp, nm)

@@ -136,10 +136,10 @@ class SampleHandlerFD:
     """Far-detector sample handler whose Reweight/GetLikelihood run as one fused device pass."""
 
     def __init__(self, edges, test_statistic=_lib.POISSON, update_w2=False, device=0, tile_events=0,
-                 keep_event_weights=False, fused_llh=True, keep_kinematics=False):
+                 keep_event_weights=False, fused_llh=True, keep_kinematics=False, batch_kernel=True):
         """keep_kinematics: needed for handle.update_kinematics (functional shifts applied on the host)."""
         flags = ((_lib.FLAG_KEEP_EVENT_WEIGHTS if keep_event_weights else 0) | (0 if fused_llh else _lib.FLAG_NO_FUSED_LLH)
-                 | (_lib.FLAG_KEEP_KINEMATICS if keep_kinematics else 0))
+                 | (_lib.FLAG_KEEP_KINEMATICS if keep_kinematics else 0) | (0 if batch_kernel else _lib.FLAG_NO_BATCH_KERNEL))
         self.handle = _lib.Handle(device=device, test_statistic=test_statistic, update_w2=update_w2,
                                   tile_events=tile_events, flags=flags)
         self.handle.upload_binning(edges)
@@ -178,6 +178,11 @@ class SampleHandlerFD:
                                   0 if norm_pars is None else norm_pars.size, osc_w is not None, osc_idx,
                                   0 if osc_w is None else osc_w.size, static_w)
         self._osc_dirty = osc_w is not None
+
+    def SetSelection(self, cuts, values=None):
+        """StoredSelection (Samples/SampleHandlerFD.cpp:162): cuts = [(sample, var, lower, upper), ...];
+        values[n_vars, n_events] = ReturnKinematicParameter(var, event) for the cut variables."""
+        self.handle.upload_selection(cuts, values)
 
     def SetSplinePointers(self, spline_pars_array):
         self._spline_pars = spline_pars_array
@@ -234,7 +239,7 @@ class SampleHandlerFD:
 
 
 def build_from_workload(w, e0=0, e1=None, with_osc=True, update_w2=False, test_statistic=None, device=0,
-                        tile_events=0, keep_event_weights=False, chunk_events=None, fused_llh=True):
+                        tile_events=0, keep_event_weights=False, chunk_events=None, fused_llh=True, batch_kernel=True):
     """B200 SampleHandlerFD + SMonolith wired on a synthetic workload (mirror of the oracle's helper)."""
     from . import synth
     e1 = w.n_events if e1 is None else e1
@@ -242,7 +247,7 @@ def build_from_workload(w, e0=0, e1=None, with_osc=True, update_w2=False, test_s
     spl = synth.make_splines(w, e0, e1)
     ev = synth.make_events(w, e0, e1)
     sh = SampleHandlerFD(synth.bin_edges(w), w.test_statistic if test_statistic is None else test_statistic,
-                         update_w2, device, tile_events, keep_event_weights, fused_llh)
+                         update_w2, device, tile_events, keep_event_weights, fused_llh, batch_kernel=batch_kernel)
     sh.SetupSplines(w.n_params, w.n_knots, cx, npts, spl, chunk_events=chunk_events)
     pars = np.zeros(w.n_params, np.float64)
     norm = np.ones(max(w.n_norm_params, 1), np.float64)[:w.n_norm_params]

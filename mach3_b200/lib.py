@@ -15,6 +15,7 @@ POISSON, BARLOW_BEESTON, ICECUBE, PEARSON, DEMBINSKI_ABDELMOTTELEB = range(5)
 FLAG_KEEP_EVENT_WEIGHTS = 1
 FLAG_KEEP_KINEMATICS = 2
 FLAG_NO_FUSED_LLH = 4
+FLAG_NO_BATCH_KERNEL = 8
 
 #: every symbol include/m3b200.h declares
 EXPORTS = (
@@ -23,7 +24,7 @@ EXPORTS = (
     "m3b_upload_binned_splines", "m3b_upload_event_binned_splines", "m3b_read_binned_weights",
     "m3b_upload_binned_splines_f64", "m3b_upload_event_weights_f64", "m3b_upload_osc_f64", "m3b_read_binned_weights_f64",
     "m3b_read_event_weights_f64",
-    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_update_kinematics", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
+    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_update_kinematics", "m3b_upload_selection", "m3b_update_selection_values", "m3b_read_event_selected", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
     "m3b_set_test_statistic", "m3b_reset_w2",
     "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_step_batch_hist", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_set_spline_knots_f64", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
@@ -247,6 +248,26 @@ class Handle:
         k = _c(kin, np.float64)
         self._keep_kin = k
         self._ck(self.L.m3b_update_kinematics(self.h, _p(k)))
+
+    def upload_selection(self, cuts, values=None):
+        """SampleHandlerFD::IsEventSelected: cuts = [(sample, var, lower, upper), ...] in StoredSelection order;
+        values[n_vars, n_events] = the cut variables (var >= 0 indexes its rows; var = -1-d: binning variable d)."""
+        n = len(cuts)
+        cs = np.array([c[0] for c in cuts], np.int32); cv = np.array([c[1] for c in cuts], np.int32)
+        lo = np.array([c[2] for c in cuts], np.float64); hi = np.array([c[3] for c in cuts], np.float64)
+        v = None if values is None else np.ascontiguousarray(np.asarray(values, np.float64).reshape(-1, self.n_events))
+        self._ck(self.L.m3b_upload_selection(self.h, C.c_int32(n), _p(cs), _p(cv), _p(lo), _p(hi),
+                                             C.c_int32(0 if v is None else v.shape[0]), _p(v)))
+
+    def update_selection_values(self, values):
+        v = np.ascontiguousarray(np.asarray(values, np.float64).reshape(-1, self.n_events))
+        self._keep_sel = v
+        self._ck(self.L.m3b_update_selection_values(self.h, _p(v)))
+
+    def read_event_selected(self):
+        out = np.zeros(self.n_events, np.uint8)
+        self._ck(self.L.m3b_read_event_selected(self.h, _p(out)))
+        return out.astype(bool)
 
     def upload_data(self, data):
         d = _c(data, np.float64)

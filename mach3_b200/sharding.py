@@ -42,7 +42,9 @@ class ShardedSampleHandler:
 
     `handle` is a lib.Handle created with FLAG_NO_FUSED_LLH that holds this rank's shard (splines,
     events, full binning, full data histogram).  `dist` is an initialised torch.distributed module
-    (or None for world 1)."""
+    (or None for world 1).  With the NCCL exchange the handle is put on torch's current CUDA stream of
+    `device` (the stream the all-reduce is issued on): fill -> all-reduce -> likelihood are then stream-ordered;
+    callers must keep that stream current while they call Reweight()."""
 
     def __init__(self, handle, dist=None, exchange="nccl", device=None):
         self.h = handle
@@ -81,6 +83,9 @@ class ShardedSampleHandler:
                 pass
             elif exchange == "nccl":
                 import torch
+                # the all-reduce runs on torch's current stream; the library's fill and likelihood launches must be
+                # ordered with it, so the handle is moved onto that stream (it owns a private non-blocking one by default)
+                handle.set_stream(torch.cuda.current_stream(device).cuda_stream)
                 ptr, nb, _ = handle.hist_device_ptr()
                 self._hist = torch.as_tensor(_DevArray(ptr, 2 * nb), device=device)
             else:

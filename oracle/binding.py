@@ -290,6 +290,20 @@ class SampleHandlerFD:
     def FillOnly(self):
         lib().m3o_fill_only(self.h)
 
+    def SetSelection(self, cuts, values):
+        """StoredSelection: cuts = [(sample, var, lower, upper), ...]; values[n_vars, n_events] (kept alive, may be
+        rewritten in place: shifted cut variables) = ReturnKinematicParameter(var, event)."""
+        cs = np.array([c[0] for c in cuts], np.int32); cv = np.array([c[1] for c in cuts], np.int32)
+        lo = np.array([c[2] for c in cuts], np.float64); hi = np.array([c[3] for c in cuts], np.float64)
+        self.cut_values = np.ascontiguousarray(np.asarray(values, np.float64).reshape(-1, self.n_events))
+        assert cv.size == 0 or (cv.min() >= 0 and cv.max() < self.cut_values.shape[0])
+        lib().m3o_sample_set_selection(self.h, C.c_int(len(cuts)), _p(cs), _p(cv), _p(lo), _p(hi), _p(self.cut_values))
+
+    def event_selected(self):
+        out = np.zeros(self.n_events, np.uint8)
+        lib().m3o_event_selected(self.h, _p(out))
+        return out.astype(bool)
+
     def GetLikelihood(self):
         return lib().m3o_get_likelihood(self.h)
 

@@ -542,6 +542,11 @@ M3O_API const short* m3o_binnedd_segments(const BinnedSplineHandlerD* b) { retur
 /* ============================================================================================
  * Samples: EventInfo (Samples/FarDetectorCoreInfoStruct.h:82-126) + SampleHandlerFD state
  * ========================================================================================== */
+typedef struct {          /* Samples/SampleStructs.h:149-157 */
+  int ParamToCutOnIt;
+  double LowerBound, UpperBound;
+} KinematicCut;
+
 typedef struct {
   const double** norm_pointers;         int n_norm;      /* std::vector<const double*>        */
   const float**  total_weight_pointers; int n_tw;        /* std::vector<const M3::float_t*>   */
@@ -568,6 +573,11 @@ typedef struct {
   struct BinnedSplineHandlerD_* BinnedHandlerD;
   const double*** tw_d;   /* [event] -> std::vector<const M3::float_t*> total_weight_pointers */
   int* n_tw_d;
+  /* std::vector<std::vector<KinematicCut>> StoredSelection / Selection (Samples/SampleHandlerFD.h:364-371), flattened:
+   * cuts of sample s are Selection[SelStart[s] .. SelStart[s+1]).  ReturnKinematicParameter(var, event) -- pure
+   * virtual in the reference, experiment code -- is a table look-up here: CutValues[var*nEvents + event]. */
+  int* SelStart; KinematicCut* StoredSelection; KinematicCut* Selection; int nCuts;
+  const double* CutValues;
 } SampleHandlerFD;
 
 
@@ -697,6 +707,7 @@ M3O_API void m3o_sample_destroy(SampleHandlerFD* s) {
   }
   free(s->SampleBinning);
   free(s->SampleHandlerFD_array); free(s->SampleHandlerFD_array_w2); free(s->SampleHandlerFD_data);
+  free(s->SelStart); free(s->StoredSelection); free(s->Selection);
   free(s);
 }
 
@@ -775,6 +786,43 @@ M3O_API void m3o_sample_set_events_binned(SampleHandlerFD* s, const int* sample_
   }
 }
 
+/* StoredSelection as the experiment's YAML fills it (Samples/SampleHandlerFD.cpp:140-165): n_cuts cuts
+ * {sample, ParamToCutOnIt, LowerBound, UpperBound}, kept in the given order inside each sample.  values[var*nEvents+e]
+ * stands in for ReturnKinematicParameter(var, e); the caller owns it (and may rewrite it: functional shifts). */
+M3O_API void m3o_sample_set_selection(SampleHandlerFD* s, int n_cuts, const int* cut_sample, const int* cut_var,
+                                      const double* lower, const double* upper, const double* values) {
+  free(s->SelStart); free(s->StoredSelection); free(s->Selection);
+  s->SelStart = (int*)calloc((size_t)s->nSamples + 1, sizeof(int));
+  s->StoredSelection = (KinematicCut*)calloc((size_t)(n_cuts > 0 ? n_cuts : 1), sizeof(KinematicCut));
+  s->Selection = (KinematicCut*)calloc((size_t)(n_cuts > 0 ? n_cuts : 1), sizeof(KinematicCut));
+  for (int k = 0; k < n_cuts; ++k) ++s->SelStart[cut_sample[k] + 1];
+  for (int i = 0; i < s->nSamples; ++i) s->SelStart[i + 1] += s->SelStart[i];
+  int* fill = (int*)malloc(sizeof(int) * (size_t)s->nSamples);
+  for (int i = 0; i < s->nSamples; ++i) fill[i] = s->SelStart[i];
+  for (int k = 0; k < n_cuts; ++k) {
+    KinematicCut* c = &s->StoredSelection[fill[cut_sample[k]]++];
+    c->ParamToCutOnIt = cut_var[k]; c->LowerBound = lower[k]; c->UpperBound = upper[k];
+  }
+  free(fill);
+  s->nCuts = n_cuts;
+  s->CutValues = values;
+}
+
+/* SampleHandlerFD::IsEventSelected (Samples/SampleHandlerFD.cpp:281-294) */
+static inline int IsEventSelected(const SampleHandlerFD* s, const int iSample, const unsigned int iEvent) {
+  if (!s->SelStart) return 1;
+  for (int iSelection = s->SelStart[iSample]; iSelection < s->SelStart[iSample + 1]; ++iSelection) {
+    const KinematicCut* Cut = &s->Selection[iSelection];
+    const double Val = s->CutValues[(size_t)Cut->ParamToCutOnIt * s->nEvents + iEvent];   /* ReturnKinematicParameter */
+    if ((Val < Cut->LowerBound) || (Val >= Cut->UpperBound)) return 0;
+  }
+  return 1;
+}
+M3O_API void m3o_event_selected(const SampleHandlerFD* s, unsigned char* out) {
+  if (s->SelStart) memcpy(s->Selection, s->StoredSelection, sizeof(KinematicCut) * (size_t)s->nCuts);
+  for (unsigned int e = 0; e < s->nEvents; ++e) out[e] = (unsigned char)IsEventSelected(s, s->MCSamples[e].NominalSample, e);
+}
+
 /* SampleHandlerFD::CalcWeightTotal (Samples/SampleHandlerFD.cpp:568-594) */
 static inline float CalcWeightTotal(const EventInfo* restrict MCEvent) {
   float TotalWeight = 1.0;
@@ -830,9 +878,11 @@ static void ResetHistograms(SampleHandlerFD* s) {
   if (s->FirstTimeW2) for (int i = 0; i < s->TotalBins; ++i) s->SampleHandlerFD_array_w2[i] = 0.0;
 }
 
-/* SampleHandlerFD::FillArray_MP (Samples/SampleHandlerFD.cpp:390-448); no functional shifts,
- * no selection cuts, no CalcWeightFunc (defaults, Samples/SampleHandlerFD.h:241,289) */
+/* SampleHandlerFD::FillArray_MP (Samples/SampleHandlerFD.cpp:390-448); functional shifts are the caller's (it
+ * rewrites the kinematic / cut-variable arrays the pointers look at), no CalcWeightFunc (default: does nothing,
+ * Samples/SampleHandlerFD.h:241,289) */
 static void FillArray_MP(SampleHandlerFD* s) {
+  if (s->SelStart) memcpy(s->Selection, s->StoredSelection, sizeof(KinematicCut) * (size_t)s->nCuts);   /* Selection = StoredSelection, :393 */
   const int TotalBins = s->TotalBins;
   const unsigned int NumberOfEvents = s->nEvents;
   double* MC_Array_for_reduction = s->SampleHandlerFD_array;
@@ -841,6 +891,7 @@ static void FillArray_MP(SampleHandlerFD* s) {
   #pragma omp parallel for reduction(+:MC_Array_for_reduction[:TotalBins], W2_array_for_reduction[:TotalBins])
   for (unsigned int iEvent = 0; iEvent < NumberOfEvents; ++iEvent) {
     const EventInfo* restrict MCEvent = &s->MCSamples[iEvent];
+    if (!IsEventSelected(s, MCEvent->NominalSample, iEvent)) continue;                    /* :424 */
     const float totalweight = CalcWeightTotal(MCEvent);
     if (totalweight <= 0.) continue;                                                      /* :432 */
     const int GlobalBin = FindGlobalBin(s, MCEvent->NominalSample, MCEvent->KinVar, MCEvent->NomBin, MCEvent->n_dim);
@@ -853,8 +904,10 @@ static void FillArray_MP(SampleHandlerFD* s) {
 
 /* SampleHandlerFD::FillArray (Samples/SampleHandlerFD.cpp:352-383), the serial build's fill */
 static void FillArray(SampleHandlerFD* s) {
+  if (s->SelStart) memcpy(s->Selection, s->StoredSelection, sizeof(KinematicCut) * (size_t)s->nCuts);   /* :355 */
   for (unsigned int iEvent = 0; iEvent < s->nEvents; iEvent++) {
     const EventInfo* restrict MCEvent = &s->MCSamples[iEvent];
+    if (!IsEventSelected(s, MCEvent->NominalSample, iEvent)) continue;                    /* :361 */
     const float totalweight = CalcWeightTotal_serial(MCEvent);
     if (totalweight <= 0.) continue;
     const int GlobalBin = FindGlobalBin(s, MCEvent->NominalSample, MCEvent->KinVar, MCEvent->NomBin, MCEvent->n_dim);
@@ -925,6 +978,7 @@ static inline double CalcWeightTotal_d(const SampleHandlerFD* s, unsigned int e,
 M3O_API void m3o_reweight_d(SampleHandlerFD* s) {
   ResetHistograms(s);
   if (s->BinnedHandlerD) m3o_binnedd_evaluate(s->BinnedHandlerD);
+  if (s->SelStart) memcpy(s->Selection, s->StoredSelection, sizeof(KinematicCut) * (size_t)s->nCuts);
   const int FirstTimeW2 = s->FirstTimeW2;
   if (g_multithread) {
     const int TotalBins = s->TotalBins;
@@ -932,6 +986,7 @@ M3O_API void m3o_reweight_d(SampleHandlerFD* s) {
     #pragma omp parallel for reduction(+:MC[:TotalBins], W2[:TotalBins])
     for (unsigned int iEvent = 0; iEvent < s->nEvents; ++iEvent) {
       const EventInfo* MCEvent = &s->MCSamples[iEvent];
+      if (!IsEventSelected(s, MCEvent->NominalSample, iEvent)) continue;
       const double totalweight = CalcWeightTotal_d(s, iEvent, 1);
       if (totalweight <= 0.) continue;
       const int GlobalBin = FindGlobalBin(s, MCEvent->NominalSample, MCEvent->KinVar, MCEvent->NomBin, MCEvent->n_dim);
@@ -940,6 +995,7 @@ M3O_API void m3o_reweight_d(SampleHandlerFD* s) {
   } else {
     for (unsigned int iEvent = 0; iEvent < s->nEvents; ++iEvent) {
       const EventInfo* MCEvent = &s->MCSamples[iEvent];
+      if (!IsEventSelected(s, MCEvent->NominalSample, iEvent)) continue;
       const double totalweight = CalcWeightTotal_d(s, iEvent, 0);
       if (totalweight <= 0.) continue;
       const int GlobalBin = FindGlobalBin(s, MCEvent->NominalSample, MCEvent->KinVar, MCEvent->NomBin, MCEvent->n_dim);

@@ -289,7 +289,9 @@ struct FD : SampleHandlerFD {
   void SetupFDMC() override {}
   void RegisterFunctionalParameters() override {}
   double ReturnKinematicParameter(std::string, int) override { return 0.0; }
-  double ReturnKinematicParameter(int, int) override { return 0.0; }
+  // the experiment's kinematic-variable look-up: variable v of the event = column v of its row in `kin` (columns past
+  // the sample's binning dimensions are free for variables that are only cut on)
+  double ReturnKinematicParameter(int var, int iEvent) override { return kin[size_t(iEvent) * 4 + size_t(var)]; }
   const double* GetPointerToKinematicParameter(std::string name, int iEvent) override { return &kin[size_t(iEvent) * 4 + size_t(name[1] - '0')]; }
   const double* GetPointerToKinematicParameter(double, int) override { return nullptr; }
 };
@@ -447,6 +449,25 @@ REFP_API int refp_fd_set_events(void* p, int n_events, const int* sample_id, con
   return 0;
 }
 
+// StoredSelection, as SampleHandlerFD::ReadConfig leaves it (Samples/SampleHandlerFD.cpp:140-165): per sample a list of
+// KinematicCut {ParamToCutOnIt, LowerBound, UpperBound}.  FillArray[_MP] copies it into Selection at every fill and
+// IsEventSelected (:281-294) applies it through ReturnKinematicParameter(ParamToCutOnIt, event).
+REFP_API void refp_fd_set_selection(void* p, int n_cuts, const int* cut_sample, const int* cut_var, const double* lower, const double* upper) {
+  FD* fd = static_cast<FD*>(p);
+  for (auto& s : fd->StoredSelection) s.clear();
+  for (int k = 0; k < n_cuts; ++k) {
+    KinematicCut c;
+    c.ParamToCutOnIt = cut_var[k]; c.LowerBound = lower[k]; c.UpperBound = upper[k];
+    fd->StoredSelection[size_t(cut_sample[k])].emplace_back(c);
+  }
+  fd->Selection = fd->StoredSelection;
+}
+REFP_API void refp_fd_selected(void* p, unsigned char* out) {
+  FD* fd = static_cast<FD*>(p);
+  fd->Selection = fd->StoredSelection;
+  for (unsigned e = 0; e < fd->nEvents; ++e) out[e] = fd->IsEventSelected(fd->MCSamples[e].NominalSample, int(e)) ? 1 : 0;
+}
+
 REFP_API void refp_fd_set_data(void* p, const double* data) {
   FD* fd = static_cast<FD*>(p);
   std::copy(data, data + fd->SampleHandlerFD_data.size(), fd->SampleHandlerFD_data.begin());
@@ -521,6 +542,7 @@ REFP_API int refp_fd_move_to_b200(void* p, int device) {
   pb.norm_base = fd->norm.data(); pb.n_norm = int(fd->norm.size());
   pb.osc_base = fd->pool.data(); pb.n_osc = int64_t(fd->nEvents);       // pool = [osc per event | extra weights]
   pb.zero = &M3::Zero; pb.unity = &M3::Unity;
+  pb.constant_weight_ranges.push_back({fd->pool.data() + fd->nEvents, fd->pool.data() + fd->pool.size()});   // the extras
   try { b->MoveToB200(a, pb, device); } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
   return 0;
 #else

@@ -235,6 +235,18 @@ class RefSampleHandlerFD:
         k4[:, :kin.shape[0]] = kin.T
         self.L.refp_fd_set_kin(self.h, _p(k4))
 
+    def set_selection(self, cuts):
+        """StoredSelection: cuts = [(sample, var, lower, upper), ...]; var = column of the event's kinematic row
+        (FD::ReturnKinematicParameter in oracle/ref_host/harness_path.cpp)."""
+        cs = np.array([c[0] for c in cuts], np.int32); cv = np.array([c[1] for c in cuts], np.int32)
+        lo = np.array([c[2] for c in cuts], np.float64); hi = np.array([c[3] for c in cuts], np.float64)
+        self.L.refp_fd_set_selection(self.h, len(cuts), _p(cs), _p(cv), _p(lo), _p(hi))
+
+    def selected(self):
+        out = np.zeros(self.n_events, np.uint8)
+        self.L.refp_fd_selected(self.h, _p(out))
+        return out.astype(bool)
+
     def set_data(self, data):
         d = np.ascontiguousarray(data, np.float64)
         assert d.size == self.n_bins

@@ -71,6 +71,19 @@ class ExperimentFD : public SampleHandlerFD {
       ev.total_weight_pointers.push_back(Mono->retPointer(int(e)));               // :1248
       ev.total_weight_pointers.push_back(&static_w[e]);                           // AddAdditionalWeightPointers
     }
+    // selection cuts (StoredSelection, SampleHandlerFD.cpp:140-165): sample 0 on its first binning variable, sample 1 on
+    // a variable that is only cut on (ReturnKinematicParameter(7, e)), sample 2 none
+    StoredSelection.resize(size_t(c.n_samples));
+    cut_only.resize(E);
+    for (int64_t e = 0; e < E; ++e) cut_only[e] = double((e * 2654435761u) % 1000) / 1000.0;
+    { KinematicCut k; k.ParamToCutOnIt = 0; k.LowerBound = 0.2; k.UpperBound = 2.5; StoredSelection[0].push_back(k); }
+    if (c.n_samples > 1) {
+      KinematicCut k; k.ParamToCutOnIt = 7; k.LowerBound = 0.125; k.UpperBound = 0.875; StoredSelection[1].push_back(k);
+      KinematicCut k2; k2.ParamToCutOnIt = 1; k2.LowerBound = 0.1; k2.UpperBound = 3.0; StoredSelection[1].push_back(k2);
+    }
+  }
+  double ReturnKinematicParameter(int var, int e) override {
+    return var == 7 ? cut_only[size_t(e)] : kin[size_t(var) * nEvents + size_t(e)];
   }
   void SetData(const std::vector<double>& d) { SampleHandlerFD_data = d; }
   const std::vector<double>& MC() const { return SampleHandlerFD_array; }
@@ -89,12 +102,13 @@ class ExperimentFD : public SampleHandlerFD {
     b.norm_base = W.norms.data(); b.n_norm = int(W.norms.size());
     b.osc_base = Oscillator->weights.data(); b.n_osc = int64_t(Oscillator->weights.size());
     b.zero = &M3::Zero; b.unity = &M3::Unity;
+    b.constant_weight_ranges.push_back({static_w.data(), static_w.data() + static_w.size()});
     return b;
   }
  protected:
   Workload& W;
   SMonolith* Mono = nullptr;
-  std::vector<int32_t> sample_id; std::vector<double> kin; std::vector<int16_t> norm_idx; std::vector<float> static_w;
+  std::vector<int32_t> sample_id; std::vector<double> kin, cut_only; std::vector<int16_t> norm_idx; std::vector<float> static_w;
   template <class T> friend class m3b200::SampleHandlerB200;
 };
 

@@ -25,6 +25,12 @@ constexpr double _LOW_MC_BOUND_ = .00001;
 
 enum TestStatistic { kPoisson = 0, kBarlowBeeston = 1, kIceCube = 2, kPearson = 3, kDembinskiAbdelmotteleb = 4 };
 
+struct KinematicCut {          // Samples/SampleStructs.h:149-157
+  int ParamToCutOnIt = -999;
+  double LowerBound = -999, UpperBound = -999;
+};
+struct FunctionalShifter {};
+
 struct EventInfo {
   std::vector<const double*> norm_pointers;
   std::vector<const M3::float_t*> total_weight_pointers;
@@ -175,8 +181,10 @@ class SampleHandlerFD : public SampleHandlerBase {
     if (FirstTimeW2) std::fill(SampleHandlerFD_array_w2.begin(), SampleHandlerFD_array_w2.end(), 0.);
     if (Oscillator) Oscillator->Evaluate();
     if (SplineHandler) SplineHandler->Evaluate();
+    Selection = StoredSelection;                           // :355
     for (unsigned int e = 0; e < GetNEvents(); ++e) {
       const EventInfo& ev = MCSamples[e];
+      if (!IsEventSelected(ev.NominalSample, int(e))) continue;          // :361
       M3::float_t w = 1.0f;                                // CalcWeightTotal :568-594
       for (const double* p : ev.norm_pointers) w *= static_cast<M3::float_t>(*p);
       for (const M3::float_t* p : ev.total_weight_pointers) w *= *p;
@@ -197,7 +205,18 @@ class SampleHandlerFD : public SampleHandlerBase {
       l += GetTestStatLLH(SampleHandlerFD_data[b], SampleHandlerFD_array[b], SampleHandlerFD_array_w2[b]);
     return l;
   }
+  virtual double ReturnKinematicParameter(int, int) { return 0.0; }     // pure virtual in the reference (SampleHandlerFD.h:293)
+  bool IsEventSelected(const int iSample, const int iEvent) {           // Samples/SampleHandlerFD.cpp:281-294
+    if (size_t(iSample) >= Selection.size()) return true;
+    for (const auto& Cut : Selection[size_t(iSample)]) {
+      const double Val = ReturnKinematicParameter(Cut.ParamToCutOnIt, iEvent);
+      if ((Val < Cut.LowerBound) || (Val >= Cut.UpperBound)) return false;
+    }
+    return true;
+  }
  protected:
+  std::vector<std::vector<KinematicCut>> StoredSelection, Selection;
+  std::vector<std::vector<FunctionalShifter*>> funcParsGrid;
   std::unique_ptr<SplineBase> SplineHandler;
   std::shared_ptr<OscillationHandler> Oscillator;
   std::unique_ptr<BinningHandler> Binning;

@@ -140,3 +140,33 @@ def binned_workload():
 
 
 BINNED_STEPS = (-1, 0, 1, 2, -2, -3, -4, 3)
+
+
+# ---- selection cuts: SampleHandlerFD::IsEventSelected (Samples/SampleHandlerFD.cpp:281-294) over fd_case() -----------
+SEL_STEPS = 6
+SEL_SHIFT_AT = 4
+
+
+def selection_case():
+    """StoredSelection for the three samples of fd_edges() and the kinematic table the cuts read.  kin4[v, e]: rows 0/1
+    are the binning variables of fd_case(), rows 2/3 exist only to be cut on.  Cuts (sample, variable, lower, upper):
+    sample 0 on its binning variable and on variable 2; sample 1 on variable 3, which holds values EXACTLY on both
+    bounds (lower passes, upper fails); sample 2 on its second binning variable and variable 2.  kin4_shift: every row
+    moved (what functional parameters write before IsEventSelected runs, :359-361)."""
+    f = fd_case()
+    E = f["sample_id"].size
+    rng = np.random.default_rng(41)
+    kin4 = np.zeros((4, E))
+    kin4[:2] = f["kin"]
+    kin4[2] = rng.uniform(0.0, 2.0, E)
+    kin4[3] = rng.uniform(0.0, 1.0, E)
+    on_lo, on_hi = rng.integers(0, E, 25), rng.integers(0, E, 25)
+    kin4[3, on_lo] = 0.25
+    kin4[3, on_hi] = 0.75
+    kin4[3, rng.integers(0, E, 3)] = np.nan                  # NaN fails neither comparison: the reference selects it
+    cuts = [(0, 0, 0.5, 2.4), (0, 2, 0.1, 1.8), (1, 3, 0.25, 0.75), (2, 1, 0.2, 1.9), (2, 2, 0.3, 2.0)]
+    kin4_shift = kin4.copy()
+    kin4_shift[:2] = f["kin_shift"]
+    kin4_shift[2] = kin4[2] + rng.normal(0.0, 0.1, E)
+    kin4_shift[3] = np.where(np.isnan(kin4[3]), np.nan, np.clip(kin4[3] + rng.normal(0.0, 0.05, E), 0.0, 1.0))
+    return dict(kin4=kin4, kin4_shift=kin4_shift, cuts=cuts)
