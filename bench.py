@@ -1,17 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- one reweight + fill + likelihood step of the MaCh3 hot path on N B200s.
 
-    python bench.py --gpus N --steps K --warmup W            (N>1: launched through torchrun)
-    python bench.py --impl reference ...                      (the reference's CPU path, host cores)
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched through torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (the reference's own CPU path, host cores)
 
-Workload (BASELINE.json): N=1 -> configs[1] "T2K-FD-like" 1M events x (40 TSpline3 K=7 + 10 TF1),
-60x15 bins, Poisson.  N>1 -> configs[2] "DUNE-FD-scale" 20M events x (48+12), 4 samples x 80x20 bins,
-events sharded contiguously over the ranks, partial histograms exchanged every step.
-Synthetic data (mach3_b200.synth), fresh proposal every step so the active spline segments change.
+Workload at EVERY N (so the driver's 1/2/4/8 points are one strong-scaling curve): BASELINE.json configs[2],
+"DUNE-FD-scale" 20M events x (48 TSpline3 K=7 + 12 TF1), 4 samples x 80x20 bins, Poisson -- the configuration the
+north_star target is quoted on; it fits one B200 (94 GB resident).  N>1: events sharded contiguously over the ranks,
+partial histograms exchanged every step.  Synthetic data (mach3_b200.synth), fresh proposal every step so the active
+spline segments change.
 
-Prints ONE JSON line (rank 0).  `value` = events/s with all inputs resident in HBM (only the
-<2 KB per-step parameter table crosses PCIe); `e2e` = the same through the C ABI with the
-oscillation-weight array copied from host memory inside every step and the -lnL read back.
+Prints ONE JSON line (rank 0):
+  value    events/s of the HOST-SYNCHRONISED step -- m3b_step + m3b_llh every step, the way MR2T2 drives it
+           (Fitters/MR2T2.cpp:62-74: step k+1 cannot be proposed before step k's -lnL is on the host) -- with all inputs
+           resident in HBM (only the <2 KB per-step parameter table crosses PCIe);
+  e2e      the same with the oscillation-weight array taken from (pinned) HOST memory inside every step;
+  extra.queued   K steps enqueued without a host sync (LLH scans, batches: consecutive launches overlap ramp and tail);
+  roofline the fill kernel's isolated launch duration (the library's CUDA events around every launch) against HBM;
+  N=1 only: extra.cfg2 / extra.cfg4 / extra.cfg5 = the other BASELINE configs as complete sub-records (clocks, roofline,
+           cpu_baseline each), extra.incumbent_gpu = the reference's own MaCh3_CUDA build on the same B200;
+  N>1 only: parity = an untimed check of the sharded -lnL / histogram against the CPU oracle (both exchanges) --
+           the run FAILS (rc != 0) above 1e-6; single_process = the same N-GPU step driven by ONE host thread through
+           m3b_group_* (the drop-in boundary for the reference's single-process fitters).
 """
 from __future__ import annotations
 
@@ -22,6 +32,7 @@ import statistics
 import subprocess
 import sys
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -30,13 +41,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CHUNK = 131072          # events generated / uploaded per chunk (multiple of every tile size)
+METRIC = "reweighted events/s per host-synchronised MCMC step (reweight+fill+LLH)"
+DTYPE = "f32 weights / f64 histogram+LLH"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--events", type=int, default=0, help="override the total event count (debug)")
@@ -45,7 +58,11 @@ def parse():
                          "NCCL all-reduce + likelihood launch (nccl), or peer with NCCL as fallback (auto)")
     ap.add_argument("--tile", type=int, default=int(os.environ.get("M3B_TILE", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-events", type=int, default=200_000)
+    ap.add_argument("--cpu-sample-events", type=int, default=1_000_000,
+                    help="events of the workload the CPU reference is timed on (bounded sample; the full 20M-event monolith "
+                         "needs 109 GB of host memory and overflows the reference's 32-bit knot offsets)")
+    ap.add_argument("--extras", default="auto", choices=["auto", "all", "none"],
+                    help="N=1 sub-records cfg2/cfg4/cfg5/incumbent_gpu, N>1 parity + single-process record (auto: on for the default workload)")
     return ap.parse_args()
 
 
@@ -53,11 +70,18 @@ def pick_workload(args):
     from mach3_b200 import synth
     name = args.workload
     if name == "auto":
-        name = "cfg2" if args.gpus == 1 else "cfg3"
+        name = "cfg3"
     w = {"cfg1": synth.CFG1, "cfg2": synth.CFG2, "cfg3": synth.CFG3}[name]
     if args.events:
         w = w.scaled(args.events, name=w.name + f" [events overridden to {args.events}]")
     return w
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -75,10 +99,12 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.index)],
+                                       "-lms", "50", "-i", str(self.index)],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.25)          # let the first samples land before the timed region starts
         except Exception:
             self.p = None
+        return self
 
     def stop(self):
         if self.p is None:
@@ -108,8 +134,8 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline.  kind "reference": the reference's OWN CPU implementation of the path --
-# Splines/SplineMonolith.cpp, SplineBase.cpp, Samples/SampleHandlerFD.cpp, SampleHandlerBase.cpp, BinningHandler.cpp
-# compiled from /root/reference with its release flags + MULTITHREAD + _LOW_MEMORY_STRUCTS_ into
+# Splines/SplineMonolith.cpp, SplineBase.cpp, BinnedSplineHandler.cpp, Samples/SampleHandlerFD.cpp, SampleHandlerBase.cpp,
+# BinningHandler.cpp compiled from /root/reference with its release flags + MULTITHREAD + _LOW_MEMORY_STRUCTS_ into
 # oracle/_ref/libm3ref_path_lm_mt.so (oracle/ref_host/Makefile; built in the container that has the reference, it
 # travels to the GPU box).  kind "port": the oracle's restatement, when that library is absent.
 # ---------------------------------------------------------------------------------------------
@@ -119,7 +145,7 @@ def cpu_path(w, n_sample, steps, warmup, budget_s=None):
     (Fitters/FitterBase.cpp:461-520).  Returns (events/s, ms/step, laps, cores, llh, sample workload, kind)."""
     from mach3_b200 import synth
     from oracle import ref_path_binding as RP     # the checker's reference build, here as the timed CPU baseline
-    ws = w.scaled(min(n_sample, w.n_events))
+    ws = w if n_sample >= w.n_events else w.scaled(n_sample)
     use_ref = RP.available_mt()
     if use_ref:
         try:
@@ -132,6 +158,7 @@ def cpu_path(w, n_sample, steps, warmup, budget_s=None):
         typ, npts, cx = synth.param_layout(ws)
         spl, ev = synth.make_splines(ws), synth.make_events(ws)
         mono = RP.RefSMonolith.from_arrays(ws.n_params, ws.n_knots, cx, npts, typ, spl, build="float_mt")
+        del spl
         fd = RP.RefSampleHandlerFD(synth.bin_edges(ws), ws.test_statistic, False, build="float_mt")
         fd.attach_monolith(mono)
         E = ws.n_events
@@ -178,6 +205,15 @@ def cpu_path(w, n_sample, steps, warmup, budget_s=None):
     return ws.n_events / (ms * 1e-3), ms, laps, cores, llh, ws, kind
 
 
+def cpu_baseline_record(w, n_sample, steps, warmup, budget_s):
+    evs, ms, laps, cores, _, ws, kind = cpu_path(w, n_sample, steps, warmup, budget_s=budget_s)
+    whole = ws.n_events == w.n_events
+    return {"value": evs, "unit": "events/s", "cores": cores, "kind": kind, "ms_per_step": ms,
+            "sample": (f"the whole {w.n_events}-event workload" if whole else f"{ws.n_events} events of the {w.n_events}-event workload")
+                      + f", {laps} DragRace laps of Reweight+GetLikelihood after {max(warmup, 1)} warm-up, OpenMP {cores} threads"
+                      + (" (the reference's own sources, oracle/_ref/libm3ref_path_lm_mt.so)" if kind == "reference" else " (oracle port)")}
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -188,15 +224,19 @@ def main_reference(args):
     from mach3_b200 import build
     build.build_synth(); build.build_oracle()
     w = pick_workload(args)
-    evs, ms, laps, cores, llh, ws, kind = cpu_path(w, args.cpu_sample_events, args.steps, min(args.warmup, 3), budget_s=120.0)
+    evs, ms, laps, cores, llh, ws, kind = cpu_path(w, args.cpu_sample_events, args.steps, args.warmup, budget_s=150.0)
     what = ("the reference's own SampleHandlerFD::Reweight + GetLikelihood over its SMonolith (compiled from the reference "
             "sources: release flags -O3 -flto, MULTITHREAD, _LOW_MEMORY_STRUCTS_, no -march)" if kind == "reference" else
             "oracle port of the reference's MULTITHREAD CPU path (flags -O3 -fopenmp -flto, no -march)")
-    sample = f"{ws.n_events} events of the {w.n_events}-event workload, {laps} timed steps, OpenMP {cores} threads, {what}"
-    line = {"impl": "reference", "metric": "reweighted events/s per MCMC step (reweight+fill+LLH)", "value": evs,
-            "unit": "events/s", "n_gpus": args.gpus, "steps": laps, "warmup": min(args.warmup, 3), "ms_per_step": ms,
-            "llh_evals_per_s": 1e3 / ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
-            "vs_baseline": None, "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
+    whole = ws.n_events == w.n_events
+    sample = (f"the whole {w.n_events}-event workload" if whole else
+              f"{ws.n_events} events of the {w.n_events}-event workload (the full monolith needs 109 GB of host memory and "
+              f"overflows the reference's unsigned-int knot offsets, Splines/SplineCommon.h:30-50)") + \
+             f", {laps} timed steps, OpenMP {cores} threads, {what}"
+    line = {"impl": "reference", "metric": METRIC, "value": evs,
+            "unit": "events/s", "n_gpus": args.gpus, "steps": laps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
+            "llh_evals_per_s": 1e3 / ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": w.name, "sample": sample},
             "cpu_baseline": {"value": evs, "unit": "events/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": evs, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,7 +245,311 @@ def main_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-# B200 arm
+# B200 arm: the event-by-event monolith path (configs 1-3)
+# ---------------------------------------------------------------------------------------------
+class _ChunkBuffers:
+    """Two sets of pinned staging arrays for the monolith upload: the generator (host, OpenMP) fills one while the
+    library copies the other to the device (true DMA, no pageable bounce) and re-tiles it."""
+
+    def __init__(self, h, w, n_max):
+        from mach3_b200 import synth
+        self.sets = []
+        tc, tl = synth.count_responses(w, 0, min(n_max, w.n_events))
+        # dense upper bounds: every event has at most n_cubic / n_linear responses
+        tc, tl = max(tc, n_max * w.n_cubic), max(tl, n_max * w.n_linear)
+        for _ in range(2):
+            self.sets.append(dict(
+                nParamPerEvent=h.alloc_host(2 * n_max, np.uint32), paramNo_arr=h.alloc_host(max(tc, 1), np.int16),
+                nKnots_arr=h.alloc_host(max(tc, 1), np.uint64), coeff_many=h.alloc_host(max(tc, 1) * w.n_knots * 4, np.float32),
+                nParamPerEvent_tf1=h.alloc_host(2 * n_max, np.uint32), paramNo_tf1=h.alloc_host(max(tl, 1), np.int16),
+                coeff_tf1=h.alloc_host(max(tl, 1) * 2, np.float32)))
+
+    def free(self, h):
+        for s in self.sets:
+            for a in s.values():
+                h.free_host(a)
+        self.sets = []
+
+
+def upload_monolith(h, w, e0, e1):
+    """Generates events [e0, e1) of workload `w` in the reference's monolith layout chunk by chunk and appends them;
+    generation of chunk k+1 overlaps the upload of chunk k."""
+    from mach3_b200 import synth
+    typ, npts, cx = synth.param_layout(w)
+    h.splines_begin(w.n_params, w.n_knots, cx, npts, e1 - e0)
+    starts = list(range(e0, e1, CHUNK))
+    if starts:
+        bufs = _ChunkBuffers(h, w, min(CHUNK, e1 - e0))
+        with ThreadPoolExecutor(1) as pool:
+            fut = pool.submit(synth.make_splines, w, starts[0], min(e1, starts[0] + CHUNK), bufs.sets[0])
+            for i, c0 in enumerate(starts):
+                spl = fut.result()
+                if i + 1 < len(starts):
+                    fut = pool.submit(synth.make_splines, w, starts[i + 1], min(e1, starts[i + 1] + CHUNK), bufs.sets[(i + 1) % 2])
+                h.splines_append(spl)            # synchronous: the buffer is free again when it returns
+        bufs.free(h)
+    h.splines_end()
+
+
+def build_handle(w, e0, e1, local, flags, tile, stream_ptr, n_osc_bufs=4):
+    from mach3_b200 import lib, synth
+    h = lib.Handle(device=local, test_statistic=w.test_statistic, update_w2=False, tile_events=tile, flags=flags)
+    if stream_ptr is not None:
+        h.set_stream(stream_ptr)
+    t0 = time.perf_counter()
+    upload_monolith(h, w, e0, e1)
+    h.upload_binning(synth.bin_edges(w))
+    ev = synth.make_events(w, e0, e1)
+    h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0,
+                    ev["static_w"])
+    del ev
+    # the caller's persistent oscillation-weight arrays live in pinned + mapped host memory from the library
+    # (m3b_alloc_host; registering malloc'ed numpy memory gave less than half the PCIe rate on this pool)
+    osc_bufs = []
+    for k in range(n_osc_bufs):
+        b = h.alloc_host(e1 - e0, np.float32)
+        synth.make_osc(w, k, e0, e1, out=b)
+        osc_bufs.append(b)
+    h.upload_osc(osc_bufs[0])
+    return h, osc_bufs, time.perf_counter() - t0
+
+
+def measure_monolith(args, w, world, rank, local, dist, torch, W, K, want_cpu_baseline, cpu_sample):
+    """Builds this rank's shard of workload `w` and measures the step three ways (host-synchronised with resident
+    inputs = value; queued; host-synchronised with host inputs = e2e) plus the fill kernel's own duration.
+    Returns the rank-0 record (None on other ranks) and keeps nothing alive."""
+    from mach3_b200 import lib, sharding, synth
+    E = w.n_events
+    e0, e1 = sharding.shard_range(E, world, rank)
+    n_local = e1 - e0
+    flags = lib.FLAG_NO_FUSED_LLH if world > 1 else 0
+    stream = torch.cuda.current_stream()
+    h, osc_bufs, t_setup = build_handle(w, e0, e1, local, flags, args.tile, stream.cuda_stream)
+    n_osc_bufs = len(osc_bufs)
+    sh = sharding.ShardedSampleHandler(h, dist, args.exchange, device=f"cuda:{local}") if world > 1 else None
+
+    props = {k: synth.proposal(w, k) for k in range(-1, 3 * (W + K) + 16)}
+    props = {k: (np.ascontiguousarray(sp, np.float64), np.ascontiguousarray(nm, np.float64)) for k, (sp, nm) in props.items()}
+    prop_addr = {k: (lib.addr(sp), lib.addr(nm) if nm.size else 0) for k, (sp, nm) in props.items()}
+    osc_addr = {id(b): lib.addr(b) for b in osc_bufs}
+
+    def step(k, osc=None):
+        if world == 1:
+            # raw addresses, like the C++ host the library is made for (no per-call ctypes pointer extraction)
+            h.step_addr(prop_addr[k][0], prop_addr[k][1], 0 if osc is None else osc_addr[id(osc)])
+        else:
+            sp, nm = props[k]
+            sh.Reweight(sp, nm, osc)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # Asimov data at nominal, Poisson-fluctuated with a seed every rank shares
+    step(-1); h.llh()
+    mc, _ = h.read_hist()
+    data = np.random.default_rng(w.seed).poisson(mc).astype(np.float64)
+    h.upload_data(data)
+
+    def timed(fn, n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        t0 = time.perf_counter()
+        out = fn(n)
+        ev1.record(stream)
+        barrier()
+        t_host = time.perf_counter() - t0
+        return max(ev0.elapsed_time(ev1), 1e3 * t_host), out
+
+    # ---------------- value: host-synchronised steps, inputs resident in HBM --------------------
+    for k in range(W):
+        step(k); h.llh_fast()
+    llh_w = h.llh()
+    clocks = ClockSampler(local).start()
+    launches0 = h.info().kernel_launches
+
+    def sync_steps(n):
+        v = 0.0
+        for k in range(W, W + n):
+            step(k)
+            v = h.llh_fast()
+        return v
+    ms_sync, llh_sync = timed(sync_steps, K)
+    launches = h.info().kernel_launches - launches0
+
+    # ---------------- queued: K steps enqueued without a host sync ------------------------------
+    def queued_steps(n):
+        for k in range(W, W + n):
+            step(k)
+        return None
+    ms_queued, _ = timed(queued_steps, K)
+    llh_queued = h.llh()
+    assert llh_queued == llh_sync or abs(llh_queued - llh_sync) <= 1e-9 * abs(llh_sync), (llh_sync, llh_queued)
+
+    # ---------------- the fill kernel alone (library's events around every launch) --------------
+    h.set_timing(True)
+    h.kernel_time()
+    for k in range(W, W + K):
+        step(k)
+    h.llh()
+    kern_ms, kern_n = h.kernel_time()
+    h.set_timing(False)
+
+    # ---------------- e2e: host buffers in, scalar out, every step ------------------------------
+    for k in range(min(W, 5)):
+        step(W + K + k, osc_bufs[k % n_osc_bufs]); h.llh()
+
+    def e2e_steps(n):
+        v = 0.0
+        for k in range(n):
+            step(W + K + 5 + k, osc_bufs[k % n_osc_bufs])
+            v = h.llh_fast()
+        return v
+    ms_e2e, llh_e2e = timed(e2e_steps, K)
+    clk = clocks.stop()
+
+    info = h.info()
+    kern_avg = kern_ms / max(kern_n, 1)
+    if dist is not None:
+        t = torch.tensor([ms_sync, ms_queued, ms_e2e, kern_avg], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_sync, ms_queued, ms_e2e, kern_avg = t.tolist()
+    exchange = "none" if world == 1 else sh.exchange
+    h.close()
+    del h, sh, osc_bufs
+    if rank != 0:
+        return None
+
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ms_step = ms_sync / K
+    alg_bytes_local = n_local * w.bytes_per_event        # SURVEY §8d per-event figure x events of one launch
+    achieved = alg_bytes_local / (kern_avg * 1e-3) / 1e9
+    step_bytes = 12 * w.n_params + 4 * w.n_norm_params
+    traffic, traffic_src = committed_traffic(w, world, info)
+    rec = {
+        "metric": METRIC,
+        "value": E / (ms_step * 1e-3), "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "llh_evals_per_s": 1e3 / ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": {"workload": w.name, "events": E, "events_per_gpu": n_local, "responses_per_event": w.n_params,
+                   "bins": w.n_bins, "tile_events": info.tile_events, "grid_blocks": info.grid_blocks,
+                   "smem_bytes": info.smem_bytes, "tma_stages": info.tma_stages, "exchange": exchange,
+                   "step": "m3b_step (async) + m3b_llh (blocks) every step; inputs resident in HBM",
+                   "l2": "inputs larger than L2: %.0f MB of coefficient rows stream per step per GPU, fresh "
+                         "proposal (different segments) every step" % (info.active_bytes_per_step / 1e6),
+                   "device_bytes": info.device_bytes, "setup_s": round(t_setup, 2)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth, read+write)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs_nominal": achieved / 8000.0,
+                     "kernel": "m3b::fill_tma_kernel", "kernel_ms": kern_avg, "algorithmic_bytes_per_launch": alg_bytes_local,
+                     "loaded_bytes_per_launch": info.active_bytes_per_step, "traffic": traffic, "traffic_source": traffic_src,
+                     "note": "kernel_ms = isolated launch duration (library's CUDA events around every launch); a read-only "
+                             "stream can exceed the copy (read+write) peak",
+                     "frac_of_step": kern_avg / ms_step},
+        "e2e": {"value": E / (ms_e2e / K * 1e-3), "unit": "events/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(4 * n_local + step_bytes), "d2h_bytes_per_step": int(8 * (1 + w.n_samples)),
+                "api": "m3b_step(host pars, host norms, host osc weights in pinned memory) + m3b_llh(); the osc weights "
+                       "are streamed over PCIe by the fill kernel's own bulk copies (no separate H2D pass)"},
+        "gpu_launches": int(launches), "clocks": clk,
+        "extra": {"queued": {"value": E / (ms_queued / K * 1e-3), "unit": "events/s", "ms_per_step": ms_queued / K,
+                             "what": "K steps enqueued back to back, ONE host synchronisation at the end (LLH scans, "
+                                     "m3b_step_batch's sequential path): consecutive fused launches overlap ramp and tail "
+                                     "through programmatic dependent launch",
+                             "achieved_gbs": alg_bytes_local / (ms_queued / K * 1e-3) / 1e9}},
+        "llh": {"last_value_step": llh_sync, "last_e2e_step": llh_e2e, "after_warmup": llh_w},
+    }
+    if want_cpu_baseline:
+        rec["cpu_baseline"] = cpu_baseline_record(w, cpu_sample, 100, 2, budget_s=15.0)
+    return rec
+
+
+def committed_traffic(w, world, info):
+    """DRAM bytes per launch from the committed `ncu --set full` capture whose launch configuration is the one this run
+    used (profiles/r02_ncu_*.json carry tile_events / tma_stages / events); None when no capture matches."""
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted(f for f in os.listdir(pdir) if f.startswith("r02_ncu_full_fill_tma") and f.endswith(".json"))
+    except OSError:
+        return None, None
+    for f in names:
+        try:
+            pj = json.load(open(os.path.join(pdir, f)))
+            c = pj.get("config", {})
+            if c.get("events_per_gpu") != info.n_events or c.get("tile_events") != info.tile_events or \
+                    c.get("tma_stages") != info.tma_stages or c.get("responses_per_event") != w.n_params:
+                continue
+            return float(pj["dram_bytes_per_launch"]), f"profiles/{f} (dram__bytes_read.sum + dram__bytes_write.sum per launch, same launch configuration)"
+        except Exception:
+            continue
+    return None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# N>1: untimed parity of the sharded path against the CPU oracle (the checker), both exchanges
+# ---------------------------------------------------------------------------------------------
+def sharded_parity(args, world, rank, local, dist, torch, n_events=160_001):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "multigpu"))
+    import parity_ranks
+    return parity_ranks.run_parity(dist, rank, world, local, n_events, verbose=False)
+
+
+# ---------------------------------------------------------------------------------------------
+# N>1: the same N-GPU step from ONE process / ONE host thread (m3b_group_*), rank 0 after the ranks have left
+# ---------------------------------------------------------------------------------------------
+def measure_single_process(args, w, n_dev, torch, W, K, expect_llh):
+    from mach3_b200 import lib, synth
+    t0 = time.perf_counter()
+    g = lib.Group(list(range(n_dev)), test_statistic=w.test_statistic, update_w2=False, tile_events=args.tile)
+    osc_bufs = []
+    for i in range(n_dev):
+        e0, e1 = g.shard(w.n_events, i)
+        m = g.member(i)
+        upload_monolith(m, w, e0, e1)
+        m.upload_binning(synth.bin_edges(w))
+        ev = synth.make_events(w, e0, e1)
+        m.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0, ev["static_w"])
+        del ev
+    g.connect()
+    # per-step oscillation weights: one pinned host array over ALL events (what the oscillator owns), sharded by the group
+    for k in range(4):
+        b = g.alloc_host(w.n_events, np.float32)
+        synth.make_osc(w, k, 0, w.n_events, out=b)
+        osc_bufs.append(b)
+    g.upload_osc(osc_bufs[0])
+    t_setup = time.perf_counter() - t0
+    props = {k: synth.proposal(w, k) for k in range(-1, 3 * (W + K) + 16)}
+    props = {k: (np.ascontiguousarray(sp, np.float64), np.ascontiguousarray(nm, np.float64)) for k, (sp, nm) in props.items()}
+    g.step(*props[-1]); g.llh()
+    mc, _ = g.read_hist()
+    g.upload_data(np.random.default_rng(w.seed).poisson(mc).astype(np.float64))
+    for k in range(W):
+        g.step(*props[k]); g.llh()
+    t1 = time.perf_counter()
+    for k in range(W, W + K):
+        g.step(*props[k]); llh = g.llh()
+    ms_sync = 1e3 * (time.perf_counter() - t1) / K
+    for k in range(min(W, 5)):
+        g.step(*props[W + K + k], osc_w=osc_bufs[k % 4]); g.llh()
+    t1 = time.perf_counter()
+    for k in range(K):
+        g.step(*props[W + K + 5 + k], osc_w=osc_bufs[k % 4]); llh_e = g.llh()
+    ms_e2e = 1e3 * (time.perf_counter() - t1) / K
+    rec = {"value": w.n_events / (ms_sync * 1e-3), "unit": "events/s", "ms_per_step": ms_sync, "n_gpus": n_dev,
+           "e2e": {"value": w.n_events / (ms_e2e * 1e-3), "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(4 * w.n_events),
+                   "d2h_bytes_per_step": int(8 * (1 + w.n_samples))},
+           "timing": "host wall clock around K x (m3b_group_step + m3b_group_llh), one process, one calling thread",
+           "exchange": g.exchange, "setup_s": round(t_setup, 1), "llh_last": llh,
+           "llh_rel_diff_to_multi_process": (abs(llh - expect_llh) / abs(expect_llh)) if expect_llh else None}
+    g.close()
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------
+# main, B200 arm
 # ---------------------------------------------------------------------------------------------
 def main_b200(args):
     # torchrun exports OMP_NUM_THREADS=1; the synthetic-workload generator (host, OpenMP) would then build each
@@ -219,9 +563,8 @@ def main_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
@@ -233,214 +576,101 @@ def main_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w = pick_workload(args)
-    E = w.n_events
-    # contiguous, tile-aligned event shards
-    from mach3_b200 import sharding
-    e0, e1 = sharding.shard_range(E, world, rank)
-    n_local = e1 - e0
-
-    flags = lib.FLAG_NO_FUSED_LLH if world > 1 else 0
-    h = lib.Handle(device=local, test_statistic=w.test_statistic, update_w2=False, tile_events=args.tile, flags=flags)
-    stream = torch.cuda.current_stream()
-    h.set_stream(stream.cuda_stream)
-    t_setup = time.perf_counter()
-    typ, npts, cx = synth.param_layout(w)
-    h.splines_begin(w.n_params, w.n_knots, cx, npts, n_local)
-    for c0 in range(e0, e1, CHUNK):
-        h.splines_append(synth.make_splines(w, c0, min(e1, c0 + CHUNK)))
-    h.splines_end()
-    h.upload_binning(synth.bin_edges(w))
-    ev = synth.make_events(w, e0, e1)
-    h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0,
-                    ev["static_w"])
-    del ev
-    n_osc_bufs = 4
-    # the caller's persistent oscillation-weight arrays live in pinned + mapped host memory from the library
-    # (m3b_alloc_host; registering malloc'ed numpy memory gave less than half the PCIe rate on this pool)
-    osc_bufs = []
-    for k in range(n_osc_bufs):
-        b = h.alloc_host(n_local, np.float32)
-        b[:] = synth.make_osc(w, k, e0, e1)
-        osc_bufs.append(b)
-    h.upload_osc(osc_bufs[0])
-    t_setup = time.perf_counter() - t_setup
-
-    sh = sharding.ShardedSampleHandler(h, dist, args.exchange, device=f"cuda:{local}") if world > 1 else None
-
-    def step(k, osc=None):
-        sp, nm = props[k]
-        if world == 1:
-            # raw addresses, like the C++ host the library is made for (no per-call ctypes pointer extraction)
-            h.step_addr(prop_addr[k][0], prop_addr[k][1], 0 if osc is None else osc_addr[id(osc)])
-        else:
-            sh.Reweight(sp, nm, osc)
-
-    W, K = args.warmup, args.steps
-    props = {k: synth.proposal(w, k) for k in range(-1, 2 * (W + K) + 16)}
-    props = {k: (np.ascontiguousarray(sp, np.float64), np.ascontiguousarray(nm, np.float64)) for k, (sp, nm) in props.items()}
-    prop_addr = {k: (lib.addr(sp), lib.addr(nm) if nm.size else 0) for k, (sp, nm) in props.items()}
-    osc_addr = {id(b): lib.addr(b) for b in osc_bufs}
-
-    # Asimov data at nominal, Poisson-fluctuated with a seed every rank shares
-    step(-1); h.llh()
-    mc, _ = h.read_hist()
-    data = np.random.default_rng(w.seed).poisson(mc).astype(np.float64)
-    h.upload_data(data)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---------------- value: inputs resident in HBM --------------------------------------------
-    # K queued steps between two events on the launching stream (consecutive fused launches may overlap their
-    # ramp/tail through programmatic dependent launch), then the same K steps again with the library's own events
-    # around every launch (which serialises them): `value` comes from the first pass, the kernel's isolated launch
-    # duration -- what the roofline uses -- from the second.
-    for k in range(W):
-        step(k)
-    llh_w = h.llh()
-    clocks = ClockSampler(local)
-    clocks.start()
-    launches0 = h.info().kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for k in range(W, W + K):
-        step(k)
-    ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = h.info().kernel_launches - launches0
-    llh_last = h.llh()
-    h.set_timing(True)
-    h.kernel_time()
-    for k in range(W, W + K):
-        step(k)
-    llh_last2 = h.llh()
-    kern_ms, kern_n = h.kernel_time()
-    h.set_timing(False)
-    assert llh_last2 == llh_last or abs(llh_last2 - llh_last) <= 1e-9 * abs(llh_last), (llh_last, llh_last2)
-
-    # ---------------- e2e: host buffers in, scalar out, every step -----------------------------
-    for k in range(min(W, 5)):
-        step(W + K + k, osc_bufs[k % n_osc_bufs]); h.llh()
-    barrier()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record(stream)
-    t_host = time.perf_counter()
-    for k in range(K):
-        step(W + K + 5 + k, osc_bufs[k % n_osc_bufs])
-        llh_e2e = h.llh_fast()
-    ev3.record(stream)
-    barrier()
-    t_host = time.perf_counter() - t_host
-    ms_e2e = max(ev2.elapsed_time(ev3), 1e3 * t_host)
-    clk = clocks.stop()
-
-    info = h.info()
-    if dist is not None:
-        t = torch.tensor([ms_total, ms_e2e, kern_ms / max(kern_n, 1)], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e, kern_avg = t.tolist()
-    else:
-        kern_avg = kern_ms / max(kern_n, 1)
-
+    W, K = max(args.warmup, 3), args.steps
+    extras = args.extras == "all" or (args.extras == "auto" and args.workload == "auto" and not args.events)
+    line = measure_monolith(args, w, world, rank, local, dist, torch, W, K,
+                            want_cpu_baseline=(world == 1 and not args.no_cpu_baseline), cpu_sample=args.cpu_sample_events)
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        ms_step = ms_total / K
-        alg_bytes_local = n_local * w.bytes_per_event        # SURVEY §8d per-event figure x events of one launch
-        achieved = alg_bytes_local / (kern_avg * 1e-3) / 1e9
-        step_bytes = 12 * w.n_params + 4 * w.n_norm_params
-        kname = "m3b::fill_tma_kernel" if info.kernel_variant < 0 else f"m3b::fill_kernel<{info.tile_events},variant {info.kernel_variant}>"
-        # DRAM traffic per launch from the committed `ncu --set full` capture of this same command
-        traffic, traffic_src = None, None
-        prof = os.path.join(ROOT, "profiles", "r01_ncu_full_fill_tma_cfg2.json")
-        if world == 1 and w is synth.CFG2 and info.kernel_variant < 0 and os.path.exists(prof):
-            try:
-                pj = json.load(open(prof))
-                rd = [float(x) for x in pj["dram__bytes_read.sum"]["per_launch"]]
-                wr = [float(x) for x in pj["dram__bytes_write.sum"]["per_launch"]]
-                scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-                traffic = (sum(rd) / len(rd)) * scale[pj["dram__bytes_read.sum"]["unit"]] + \
-                          (sum(wr) / len(wr)) * scale[pj["dram__bytes_write.sum"]["unit"]]
-                traffic_src = "profiles/r01_ncu_full_fill_tma_cfg2.json (dram__bytes_read.sum + dram__bytes_write.sum, mean of 3 launches)"
-            except Exception:
-                traffic = None
-        line = {
-            "metric": "reweighted events/s per MCMC step (reweight+fill+LLH)",
-            "value": E / (ms_step * 1e-3), "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_step, "llh_evals_per_s": 1e3 / ms_step, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-            "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
-            "config": {"workload": w.name, "events": E, "events_per_gpu": n_local, "responses_per_event": w.n_params,
-                       "bins": w.n_bins, "tile_events": info.tile_events, "grid_blocks": info.grid_blocks,
-                       "smem_bytes": info.smem_bytes, "tma_stages": info.tma_stages, "exchange": ("none" if world == 1 else sh.exchange),
-                       "l2": "inputs larger than L2: %.0f MB of coefficient rows stream per step per GPU, fresh "
-                             "proposal (different segments) every step" % (info.active_bytes_per_step / 1e6),
-                       "device_bytes": info.device_bytes, "setup_s": round(t_setup, 2), "host_cpu_affinity": numa},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                         "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "kernel": kname, "kernel_ms": kern_avg, "algorithmic_bytes_per_launch": alg_bytes_local,
-                         "loaded_bytes_per_launch": info.active_bytes_per_step, "traffic": traffic, "traffic_source": traffic_src,
-                         "note": "kernel_ms = isolated launch duration (library's CUDA events around every launch, which "
-                                 "serialises the launches); `value`/ms_per_step come from K queued steps whose ramp/tail "
-                                 "overlap through programmatic dependent launch",
-                         "achieved_queued": alg_bytes_local / (ms_step * 1e-3) / 1e9,
-                         "frac_queued": alg_bytes_local / (ms_step * 1e-3) / 1e9 / peak},
-            "e2e": {"value": E / (ms_e2e / K * 1e-3), "unit": "events/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": int(4 * n_local + step_bytes), "d2h_bytes_per_step": int(8 * (1 + w.n_samples)),
-                    "api": "m3b_step(host pars, host norms, host osc weights in pinned memory) + m3b_llh(); the osc weights "
-                           "are streamed over PCIe by the fill kernel's own bulk copies (no separate H2D pass)"},
-            "gpu_launches": int(launches), "clocks": clk,
-            "llh": {"last_value_step": llh_last, "last_e2e_step": llh_e2e, "after_warmup": llh_w},
-        }
-        if world > 1:
-            # the driver's N=1 run is cfg2 (BASELINE configs[1]); the same-workload single-GPU point of THIS strong-scaling
-            # curve was measured once and committed (python bench.py --workload cfg3 on one B200: all events resident)
-            try:
-                one = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_cfg3_1gpu.json")))
-                if one["config"]["events"] == E and one["config"]["responses_per_event"] == w.n_params:
-                    line["same_workload_on_one_gpu"] = {"value": one["value"], "ms_per_step": one["ms_per_step"], "unit": "events/s",
-                                                        "source": "profiles/r01_bench_cfg3_1gpu.json (committed measurement, not this run)"}
-            except Exception:
-                pass
-        if world == 1 and not args.no_cpu_baseline:
-            evs, ms, laps, cores, _, ws, kind = cpu_path(w, args.cpu_sample_events, 100, 2, budget_s=15.0)
-            line["cpu_baseline"] = {"value": evs, "unit": "events/s", "cores": cores, "kind": kind, "ms_per_step": ms,
-                                    "sample": f"{ws.n_events} events of the same workload, {laps} DragRace laps of "
-                                              f"Reweight+GetLikelihood, OpenMP {cores} threads"
-                                              + (" (the reference's own sources, oracle/_ref/libm3ref_path_lm_mt.so)"
-                                                 if kind == "reference" else " (oracle port)")}
-        print(json.dumps(line), flush=True)
+        line["config"]["host_cpu_affinity"] = numa
+    rc = 0
+    if world > 1 and extras:
+        par = sharded_parity(args, world, rank, local, dist, torch)
+        if rank == 0:
+            line["parity"] = par
+            if not par["ok"]:
+                rc = 3
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    h.close()
+        if rank != 0:
+            return 0
+        # this process no longer shares the GPUs: the host threads may use every core again
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except Exception:
+            pass
+    if world > 1 and extras:
+        try:
+            line["single_process"] = measure_single_process(args, w, world, torch, W, K, line["llh"]["last_value_step"])
+        except Exception as e:                                   # noqa: BLE001 -- the headline line must still be printed
+            line["single_process"] = {"error": f"{type(e).__name__}: {e}"}
+    if world == 1 and extras:
+        ex = line["extra"]
+        for name, fn in (("cfg2", lambda: measure_monolith(args, synth.CFG2, 1, 0, local, None, torch, W, max(K, 100),
+                                                           want_cpu_baseline=not args.no_cpu_baseline, cpu_sample=synth.CFG2.n_events)),
+                         ("cfg4", lambda: measure_cfg4(args, local, not args.no_cpu_baseline)),
+                         ("cfg5", lambda: measure_cfg5(args, local, not args.no_cpu_baseline)),
+                         ("incumbent_gpu", lambda: measure_incumbent(local))):
+            try:
+                ex[name] = fn()
+            except Exception as e:                               # noqa: BLE001
+                ex[name] = {"error": f"{type(e).__name__}: {e}"}
+    print(json.dumps(line), flush=True)
+    return rc
 
 
-def main_cfg4(args):
-    """BASELINE config 4 (BinnedSplineHandler workload), single GPU, optional bench line:
-    python bench.py --workload cfg4 [--events N]   (not the default; the headline stays cfg2)."""
-    import torch
-    from mach3_b200 import handlers, lib
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4: BinnedSplineHandler workload
+# ---------------------------------------------------------------------------------------------
+def cpu_binned(w, steps, warmup, budget_s):
+    """The reference's own BinnedSplineHandler::Evaluate + SampleHandlerFD::FillArray_MP + GetLikelihood (release build,
+    MULTITHREAD, float) on workload `w` (a bounded sample of config 4)."""
     from mach3_b200.synth import binned as B
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; no CPU fallback")
-    w = B.CFG4 if not args.events else B.CFG4.scaled(n_events=args.events, n_grid=max(1000, int(B.CFG4.n_grid * args.events / B.CFG4.n_events)))
+    from oracle import ref_path_binding as RP
+    if not RP.available_mt():
+        return None
+    spl, ev = B.make_binned_splines(w), B.make_binned_events(w)
+    E = w.n_events
+    fd = RP.RefSampleHandlerFD(B.bin_edges(w), w.test_statistic, True, build="float_mt")
+    fd.attach_binned(spl)
+    idx = np.arange(E, dtype=np.int32)
+    fd.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, w_before=idx,
+                  w_after=E + idx, n_pool=2 * E, binned_n_per_event=ev["n_per_event"], binned_slot=ev["spline_index"])
+    pool = np.concatenate([B.make_osc(w, 0), ev["static_w"]]).astype(np.float64)
+    sp, nm = B.proposal(w, -1)
+    fd.reweight(sp, nm, pool)
+    fd.set_data(np.random.default_rng(w.seed).poisson(fd.hist()[0]).astype(np.float64))
+    t_all, laps = 0.0, 0
+    for k in range(warmup + steps):
+        sp, nm = B.proposal(w, k)
+        t0 = time.perf_counter()
+        fd.reweight(sp, nm, None); fd.llh()
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            t_all += dt; laps += 1
+            if t_all > budget_s and laps >= 3:
+                break
+    cores = RP.num_threads("float_mt")
+    fd.close()
+    ms = 1e3 * t_all / laps
+    return {"value": E / (ms * 1e-3), "unit": "events/s", "cores": cores, "kind": "reference", "ms_per_step": ms,
+            "binned_spline_evals_per_s": int(spl["uniquecoeffindices"].size) / (ms * 1e-3),
+            "sample": f"{E} events x {w.n_systs} systematics x {w.n_grid} spline bins ({int(spl['uniquecoeffindices'].size)} non-flat "
+                      f"binned splines): a 1/10 sample of config 4, {laps} laps of the reference's BinnedSplineHandler::Evaluate + "
+                      f"FillArray_MP + GetLikelihood (oracle/_ref/libm3ref_path_lm_mt.so), OpenMP {cores} threads"}
+
+
+def measure_cfg4(args, local=0, want_cpu=True):
+    import torch
+    from mach3_b200 import handlers
+    from mach3_b200.synth import binned as B
+    w = B.CFG4 if not args.events or args.workload != "cfg4" else B.CFG4.scaled(n_events=args.events, n_grid=max(1000, int(B.CFG4.n_grid * args.events / B.CFG4.n_events)))
     t0 = time.perf_counter()
-    sh, d = handlers.build_binned_from_workload(w, update_w2=True)
+    sh, d = handlers.build_binned_from_workload(w, update_w2=True, device=local)
     h = sh.handle
     t_setup = time.perf_counter() - t0
-    W, K = args.warmup, args.steps
-    props = {k: B.proposal(w, k) for k in range(-1, W + K + 2)}
+    W, K = max(args.warmup, 3), max(args.steps, 20)
+    props = {k: B.proposal(w, k) for k in range(-1, 2 * (W + K) + 2)}
 
     def step(k):
         d["pars"][:], d["norm"][:] = props[k]
@@ -449,20 +679,25 @@ def main_cfg4(args):
     step(-1); sh.GetLikelihood()
     sh.AddData(np.random.default_rng(w.seed).poisson(sh.GetMCArray()).astype(np.float64))
     for k in range(W):
-        step(k)
-    sh.GetLikelihood()
-    h.set_timing(True); h.kernel_time()
+        step(k); sh.GetLikelihood()
+    clocks = ClockSampler(local).start()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     for k in range(W, W + K):
-        step(k)
-    llh = sh.GetLikelihood()
-    t_async = time.perf_counter() - t1
-    kern_ms, kern_n = h.kernel_time()
+        step(k); llh = sh.GetLikelihood()
+    t_sync = time.perf_counter() - t1
     t1 = time.perf_counter()
-    for k in range(K):
-        step(W + (k % K)); llh_e = sh.GetLikelihood()
-    t_e2e = time.perf_counter() - t1
+    for k in range(W, W + K):
+        step(k)
+    sh.GetLikelihood()
+    t_queued = time.perf_counter() - t1
+    h.set_timing(True); h.kernel_time()
+    for k in range(W, W + K):
+        step(k)
+    sh.GetLikelihood()
+    kern_ms, kern_n = h.kernel_time()
+    h.set_timing(False)
+    clk = clocks.stop()
     n_act = int(d["spl"]["uniquecoeffindices"].size)
     n_ptr = int(d["ev"]["spline_index"].size)
     mask = np.zeros(w.n_slots, bool); mask[d["spl"]["uniquecoeffindices"]] = True
@@ -470,46 +705,45 @@ def main_cfg4(args):
     del mask
     # eval: {y,b,c,d}+x read, weight write per non-flat spline; fill: event table + (index + gathered weight) per non-flat pointer
     alg = n_act * (16 + 4 + 4) + w.n_events * 8 + n_nonflat * 4 * 2
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     kms = kern_ms / max(kern_n, 1)
-    line = {"metric": "reweighted events/s per MCMC step (binned-spline eval + fill + Barlow-Beeston LLH)",
-            "value": w.n_events / (t_async / K), "unit": "events/s", "n_gpus": 1, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * t_async / K, "binned_spline_evals_per_s": n_act / (t_async / K), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
-            "config": {"workload": w.name, "events": w.n_events, "active_binned_splines": n_act, "weight_pointers": n_ptr, "non_flat_weight_pointers": n_nonflat,
-                       "slots": w.n_slots, "bins": w.n_bins, "setup_s": round(t_setup, 1),
-                       "l2": "coefficient rows (%.0f MB/step) stream from HBM; the compact weight array (%.0f MB) is gathered through L2"
-                             % (n_act * 20 / 1e6, n_act * 4 / 1e6)},
-            "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (kms * 1e-3) / 1e9 / peak, "kernel": "m3b::binned_eval_kernel + m3b::binned_fill_kernel",
-                         "kernel_ms": kms, "algorithmic_bytes_per_launch": alg, "traffic": None},
-            "e2e": {"value": w.n_events / (t_e2e / K), "unit": "events/s", "ms_per_step": 1e3 * t_e2e / K,
-                    "h2d_bytes_per_step": 12 * w.n_systs + 4 * w.n_norm_params, "d2h_bytes_per_step": 16},
-            "gpu_launches": int(2 * K), "llh": {"last": llh, "last_e2e": llh_e}}
-    print(json.dumps(line), flush=True)
+    info = h.info()
+    rec = {"metric": "reweighted events/s per host-synchronised MCMC step (binned-spline eval + fill + Barlow-Beeston LLH)",
+           "value": w.n_events / (t_sync / K), "unit": "events/s", "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": 1e3 * t_sync / K, "binned_spline_evals_per_s": n_act / (t_sync / K), "higher_is_better": True,
+           "dtype": DTYPE, "data": "synthetic",
+           "config": {"workload": w.name, "events": w.n_events, "active_binned_splines": n_act, "weight_pointers": n_ptr, "non_flat_weight_pointers": n_nonflat,
+                      "slots": w.n_slots, "bins": w.n_bins, "setup_s": round(t_setup, 1),
+                      "l2": "coefficient rows (%.0f MB/step) stream from HBM; the compact weight array (%.0f MB) is gathered through L2"
+                            % (n_act * 20 / 1e6, n_act * 4 / 1e6)},
+           "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (kms * 1e-3) / 1e9 / peak, "kernel": "m3b::binned_eval_kernel + m3b::binned_fill_kernel",
+                        "kernel_ms": kms, "algorithmic_bytes_per_launch": alg, "traffic": None,
+                        "note": "kernel_ms = eval + fill launches of one step, from the library's CUDA events"},
+           "e2e": {"value": w.n_events / (t_sync / K), "unit": "events/s", "ms_per_step": 1e3 * t_sync / K,
+                   "h2d_bytes_per_step": 12 * w.n_systs + 4 * w.n_norm_params, "d2h_bytes_per_step": 16,
+                   "note": "config 4 has no per-step host array: the step's only inputs are the parameter values"},
+           "extra": {"queued": {"ms_per_step": 1e3 * t_queued / K}},
+           "gpu_launches": int(2 * K), "clocks": clk, "llh": {"last": llh}, "device_bytes": info.device_bytes}
+    h.close()
+    del sh, d
+    if want_cpu:
+        rec["cpu_baseline"] = cpu_binned(B.CFG4.scaled(n_events=w.n_events // 10, n_grid=w.n_grid // 10), 20, 2, 10.0)
+    return rec
 
 
-def main_cfg5(args):
-    """BASELINE config 5 (batched proposals), single GPU, optional bench line:
-    python bench.py --workload cfg5 [--events N] [--steps batches]   -- 256 parameter sets per batch."""
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 5: batched proposals
+# ---------------------------------------------------------------------------------------------
+def measure_cfg5(args, local=0, want_cpu=True):
     import torch
     from mach3_b200 import lib, synth
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; no CPU fallback")
-    w = synth.CFG5 if not args.events else synth.CFG5.scaled(args.events)
+    w = synth.CFG5 if not args.events or args.workload != "cfg5" else synth.CFG5.scaled(args.events)
     n_sets = 256
-    h = lib.Handle(test_statistic=w.test_statistic, update_w2=False, tile_events=args.tile)
+    h = lib.Handle(device=local, test_statistic=w.test_statistic, update_w2=False, tile_events=args.tile)
     t0 = time.perf_counter()
-    typ, npts, cx = synth.param_layout(w)
-    h.splines_begin(w.n_params, w.n_knots, cx, npts, w.n_events)
-    for c0 in range(0, w.n_events, CHUNK):
-        h.splines_append(synth.make_splines(w, c0, min(w.n_events, c0 + CHUNK)))
-    h.splines_end()
+    upload_monolith(h, w, 0, w.n_events)
     h.upload_binning(synth.bin_edges(w))
     ev = synth.make_events(w, 0, w.n_events)
     h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0, ev["static_w"])
@@ -533,11 +767,12 @@ def main_cfg5(args):
         nms = np.clip(nm0[None, :] + rng.normal(0, 0.05, (n_sets, w.n_norm_params)), 0.5, 1.5)
         return sps, nms
 
-    W, K = max(1, min(args.warmup, 2)), max(1, min(args.steps, 5))
+    W, K = 2, 4
     bs = [batch(k) for k in range(W + K)]
     for k in range(W):
         h.step_batch(*bs[k])
     h.kernel_time()
+    clocks = ClockSampler(local).start()
     t1 = time.perf_counter()
     for k in range(W, W + K):
         tot = h.step_batch(*bs[k])
@@ -554,32 +789,80 @@ def main_cfg5(args):
         h.step_batch(sc_sp, sc_nm)
     t_scan = (time.perf_counter() - t2) / K
     ms_scan, n_scan = h.kernel_time()
+    clk = clocks.stop()
     fp_instr = w.n_events * n_sets * (4 * (w.n_params - w.n_linear) + 2 * w.n_linear)     # FMA/MUL issue slots
-    peak_issue = 148 * 128 * 1.965e9
-    line = {"metric": "LLH evaluations/s over batched proposals (reweight+fill+LLH per parameter set)", "value": n_sets / t_b,
-            "unit": "LLH evals/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_b, "us_per_llh": 1e6 * t_b / n_sets,
-            "event_sets_per_s": w.n_events * n_sets / t_b, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 weights / f64 histogram+LLH", "data": "synthetic",
-            "config": {"workload": w.name, "events": w.n_events, "sets_per_batch": n_sets, "bins": w.n_bins, "setup_s": round(t_setup, 1),
-                       "single_set_kernel_ms": ms1 / max(n1, 1), "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / kms,
-                       "llh_scan_256_points": {"ms": 1e3 * t_scan, "us_per_llh": 1e6 * t_scan / n_sets, "kernel_ms": ms_scan / max(n_scan, 1),
-                                               "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / (ms_scan / max(n_scan, 1))}},
-            "roofline": {"bound": "fp32 issue (CUDA cores; no contraction, so no tensor cores)", "achieved": fp_instr / (kms * 1e-3) / 1e12,
-                         "peak": peak_issue / 1e12, "unit": "T FP32 instr/s", "frac": fp_instr / (kms * 1e-3) / peak_issue,
-                         "kernel": "m3b::fill_batch_kernel", "kernel_ms": kms, "traffic": None},
-            "e2e": {"value": n_sets / t_b, "unit": "LLH evals/s", "h2d_bytes_per_step": int(n_sets * (8 * w.n_params + 8 * w.n_norm_params)),
-                    "d2h_bytes_per_step": int(n_sets * 8 * (1 + w.n_samples))},
-            "gpu_launches": int(2 * K), "llh": {"first": float(tot[0]), "last": float(tot[-1])}}
-    print(json.dumps(line), flush=True)
+    sm_ghz = (clk.get("sm_max_mhz") or 1965.0) * 1e-3
+    peak_issue = 148 * 128 * sm_ghz * 1e9
+    rec = {"metric": "LLH evaluations/s over batched proposals (reweight+fill+LLH per parameter set)", "value": n_sets / t_b,
+           "unit": "LLH evals/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_b, "us_per_llh": 1e6 * t_b / n_sets,
+           "event_sets_per_s": w.n_events * n_sets / t_b, "higher_is_better": True, "dtype": DTYPE, "data": "synthetic",
+           "config": {"workload": w.name, "events": w.n_events, "sets_per_batch": n_sets, "bins": w.n_bins, "setup_s": round(t_setup, 1),
+                      "proposals": "256 perturbations N(theta0, 0.3^2) around one point: 1-3 active segments per parameter",
+                      "single_set_kernel_ms": ms1 / max(n1, 1), "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / kms,
+                      "llh_scan_256_points": {"ms": 1e3 * t_scan, "us_per_llh": 1e6 * t_scan / n_sets, "kernel_ms": ms_scan / max(n_scan, 1),
+                                              "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / (ms_scan / max(n_scan, 1))}},
+           "roofline": {"bound": "fp32 issue (CUDA cores; no contraction, so no tensor cores)", "achieved": fp_instr / (kms * 1e-3) / 1e12,
+                        "peak": peak_issue / 1e12, "peak_source": "148 SMs x 128 FP32 lanes x max SM clock", "unit": "T FP32 instr/s",
+                        "frac": fp_instr / (kms * 1e-3) / peak_issue, "kernel": "m3b::fill_batch_kernel", "kernel_ms": kms, "traffic": None,
+                        "algorithmic_instr_per_launch": fp_instr},
+           "e2e": {"value": n_sets / t_b, "unit": "LLH evals/s", "h2d_bytes_per_step": int(n_sets * (8 * w.n_params + 8 * w.n_norm_params)),
+                   "d2h_bytes_per_step": int(n_sets * 8 * (1 + w.n_samples))},
+           "gpu_launches": int(2 * K), "clocks": clk, "llh": {"first": float(tot[0]), "last": float(tot[-1])}}
+    h.close()
+    if want_cpu:
+        evs, ms, laps, cores, _, ws, kind = cpu_path(synth.CFG5, 500_000, 20, 2, budget_s=8.0)
+        rec["cpu_baseline"] = {"value": 1e3 / (ms * w.n_events / ws.n_events), "unit": "LLH evals/s", "cores": cores, "kind": kind,
+                               "sample": f"{ws.n_events} events of the workload, {laps} sequential Reweight+GetLikelihood laps (the reference has no "
+                                         f"batched path: one parameter set per step), scaled to the full {w.n_events} events; OpenMP {cores} threads"}
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------
+# the incumbent GPU path: the reference's own MaCh3_CUDA build (SMonolith + Splines/gpuSplineUtils.cu kernels compiled
+# from the reference's sources, weights copied back every step, FillArray_MP + GetLikelihood on the host cores)
+# ---------------------------------------------------------------------------------------------
+def measure_incumbent(local=0):
+    from mach3_b200 import synth
+    from oracle import ref_path_binding as RP
+    w = synth.CFG2
+    if not RP.available_refcuda(w.n_params):
+        return {"unavailable": f"oracle/_ref/libm3ref_path_lm_refcuda_P{w.n_params}.so not built (needs /root/reference at build time)"}
+    build = f"float_refcuda_P{w.n_params}"
+    typ, npts, cx = synth.param_layout(w)
+    spl, ev = synth.make_splines(w), synth.make_events(w)
+    mono = RP.RefSMonolith.from_arrays(w.n_params, w.n_knots, cx, npts, typ, spl, build=build)
+    del spl
+    fd = RP.RefSampleHandlerFD(synth.bin_edges(w), w.test_statistic, False, build=build)
+    fd.attach_monolith(mono)
+    E = w.n_events
+    idx = np.arange(E, dtype=np.int32)
+    fd.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, w_before=idx, w_after=E + idx, n_pool=2 * E)
+    pool = np.concatenate([synth.make_osc(w, 0), ev["static_w"]]).astype(np.float64)
+    sp, nm = synth.proposal(w, -1)
+    fd.reweight(sp, nm, pool)
+    fd.set_data(np.random.default_rng(w.seed).poisson(fd.hist()[0]).astype(np.float64))
+    ts = []
+    for k in range(25):
+        sp, nm = synth.proposal(w, k)
+        t0 = time.perf_counter()
+        fd.reweight(sp, nm, None)
+        llh = fd.llh()
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(ts[5:]))
+    cores = RP.num_threads(build)
+    fd.close()
+    return {"value": E / (ms * 1e-3), "unit": "events/s", "ms_per_step": ms, "workload": w.name, "host_threads": cores, "llh_last": llh,
+            "what": "the reference's MaCh3_CUDA build on this B200: its SMonolith + gpuSplineUtils.cu kernels (per-event spline weights, "
+                    "4 B/event copied back), then SampleHandlerFD::FillArray_MP + GetLikelihood on the host cores; compiled from the "
+                    "reference's own sources (oracle/ref_host/Makefile); 20 timed steps after 5 warm-up; compare with extra.cfg2"}
 
 
 if __name__ == "__main__":
     a = parse()
-    if a.workload == "cfg4":
-        main_cfg4(a)
-    elif a.workload == "cfg5":
-        main_cfg5(a)
-    elif a.impl == "reference":
+    if a.impl == "reference":
         main_reference(a)
+    elif a.workload in ("cfg4", "cfg5"):
+        fn = measure_cfg4 if a.workload == "cfg4" else measure_cfg5
+        print(json.dumps(fn(a, int(os.environ.get("LOCAL_RANK", "0")), not a.no_cpu_baseline)), flush=True)
     else:
-        main_b200(a)
+        sys.exit(main_b200(a))

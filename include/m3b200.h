@@ -292,6 +292,56 @@ M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ip
 M3B_API int m3b_peer_import(m3b_handle* h, int32_t peer_rank, const void* ipc_handle_64B);
 M3B_API int m3b_step_peer(m3b_handle* h, const double* spline_pars, const double* norm_pars, const float* osc_w);
 
+/* ---- multi-GPU from ONE process, ONE calling thread ---------------------------------------------------------------
+ * The reference's fitters are single-process, single-threaded callers (Fitters/MR2T2.cpp:62-74: per sample handler
+ * Reweight(), then GetLikelihood(); Fitters/FitterBase.cpp:461-520).  A group keeps that call surface and spreads ONE
+ * sample handler over n devices of the box: member i owns a contiguous, tile-aligned shard of the events on devices[i]
+ * (the same device may be listed more than once), the library launches the n fills from its own per-device worker
+ * threads, and member 0 -- the lead -- sums the partial histograms and reduces -lnL in one launch:
+ *   M3B_EXCHANGE_PEER  the lead pulls the members' partial histograms through peer-to-peer loads (cudaDeviceEnablePeerAccess
+ *                      pointers; no IPC, no second process) behind their epoch flags -- exchange fused with the likelihood;
+ *   M3B_EXCHANGE_NCCL  every member all-reduces its histogram in place with ONE ncclAllReduce over NVLink (libnccl.so.2
+ *                      is loaded at run time, communicators from ncclCommInitAll), the lead then reduces -lnL.
+ * Set-up: m3b_group_create -> uploads (either per member through m3b_group_member() with the ordinary m3b_upload_* calls
+ * on the member's shard [m3b_group_shard], or for the whole workload at once through the m3b_group_upload_* calls below,
+ * which slice the reference's arrays by event range) -> m3b_group_connect.  Per step: m3b_group_step (asynchronous) +
+ * m3b_group_llh (blocks).  Not thread-safe per group; one group = one SampleHandlerFD.                              */
+typedef struct m3b_group m3b_group;
+enum { M3B_EXCHANGE_PEER = 0, M3B_EXCHANGE_NCCL = 1 };
+M3B_API int m3b_group_create(const m3b_config* cfg /* .device ignored */, const int32_t* devices, int32_t n_devices, m3b_group** out);
+M3B_API void m3b_group_destroy(m3b_group* g);
+M3B_API const char* m3b_group_last_error(const m3b_group* g);
+M3B_API int32_t m3b_group_size(const m3b_group* g);
+M3B_API m3b_handle* m3b_group_member(m3b_group* g, int32_t i);
+/* events [*e0, *e1) of member i when n_events are spread over the group (equal contiguous shards, multiples of 1024) */
+M3B_API int m3b_group_shard(const m3b_group* g, int64_t n_events, int32_t i, int64_t* e0, int64_t* e1);
+/* whole-workload uploads: same arguments as the per-handle calls, sliced by the members' event ranges */
+M3B_API int m3b_group_upload_spline_monolith(m3b_group* g, int32_t n_params, int32_t max_knots, const float* coeff_x,
+                                             const int16_t* n_pts, int64_t n_events, const uint32_t* nParamPerEvent,
+                                             const int16_t* paramNo_arr, const uint32_t* nKnots_arr, uint32_t total_knots,
+                                             const float* coeff_many, const uint32_t* nParamPerEvent_tf1,
+                                             const int16_t* paramNo_tf1, const float* coeff_tf1);
+M3B_API int m3b_group_upload_binning_ex(m3b_group* g, int32_t n_samples, const int32_t* n_dim, const int32_t* uniform,
+                                        const int32_t* nbins, const double* edges);
+M3B_API int m3b_group_upload_events(m3b_group* g, int64_t n_events, const int32_t* sample_id, const double* kin,
+                                    int32_t n_norm_per_event, const int16_t* norm_idx, int32_t n_norm_values,
+                                    int32_t use_osc, const int32_t* osc_idx, int64_t n_osc_values, const float* static_w);
+M3B_API int m3b_group_upload_selection(m3b_group* g, int32_t n_cuts, const int32_t* cut_sample, const int32_t* cut_var,
+                                       const double* lower, const double* upper, int32_t n_vars, const double* values);
+M3B_API int m3b_group_upload_data(m3b_group* g, const double* data, int32_t n_bins);
+M3B_API int m3b_group_upload_osc(m3b_group* g, const float* osc_w, int64_t n);
+/* wires the exchange (after every member has its binning and events); exchange = M3B_EXCHANGE_* */
+M3B_API int m3b_group_connect(m3b_group* g, int32_t exchange);
+/* pinned + mapped host memory every device of the group can stream from (the oscillator's weight array) */
+M3B_API int m3b_group_alloc_host(m3b_group* g, uint64_t bytes, void** ptr);
+/* = SampleHandlerFD::Reweight on all shards.  osc_w: NULL, or this step's oscillation weights in host memory -- one
+ * array over ALL events in event order when the events were uploaded without osc_idx (member i reads its own range),
+ * else the shared array every osc_idx points into.  Asynchronous; the parameter arrays are copied before it returns. */
+M3B_API int m3b_group_step(m3b_group* g, const double* spline_pars, const double* norm_pars, const float* osc_w);
+M3B_API int m3b_group_llh(m3b_group* g, double* total, double* per_sample);
+M3B_API int m3b_group_read_hist(m3b_group* g, double* mc, double* w2);
+M3B_API int m3b_group_synchronize(m3b_group* g);
+
 /* ---- introspection ----------------------------------------------------------------------------- */
 typedef struct {
   int64_t n_events, n_tiles;

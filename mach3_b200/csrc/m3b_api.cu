@@ -1036,7 +1036,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
 #endif
   if (h->timing) { CK(cudaEventRecord(h->tev[h->tev_used + 1], h->stream)); h->tev_used += 2; }
   ++h->launches;
-  if (mode == kPeer) {
+  if (mode == kPeer && h->peer_pull) {
     const int par = h->peer_epoch & 1;
     LlhArgs l{};
     l.data = h->d_data; l.n_bins = h->n_bins; l.n_samples = h->n_samples;
@@ -1305,11 +1305,9 @@ M3B_API int m3b_read_event_weights(m3b_handle* h, float* spline_w, float* total_
 // ------------------------------------------------------------------------------------------------
 // peer exchange wiring (CUDA IPC between the per-GPU processes)
 // ------------------------------------------------------------------------------------------------
-M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ipc_handle_64B) {
-  REQUIRE(h && ipc_handle_64B, M3B_ERR_INVALID, "m3b_peer_export: null argument");
-  REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, M3B_ERR_INVALID, "m3b_peer_export: 1..8 ranks");
-  REQUIRE(h->n_bins > 0, M3B_ERR_STATE, "m3b_peer_export: upload the binning first");
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+}  // extern "C"
+int m3b_peer_alloc(m3b_handle* h) {
+  REQUIRE(h && h->n_bins > 0, M3B_ERR_STATE, "peer exchange: upload the binning first");
   CK(cudaSetDevice(h->device));
   if (!h->d_partial[0]) {
     // one exported allocation: [2 parities][mc[n_bins] | w2[n_bins]] then this rank's epoch flag
@@ -1325,6 +1323,17 @@ M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ip
     CK(dev_alloc(h, &h->d_llh_ticket, 1));
     CK(cudaMemset(h->d_llh_ticket, 0, sizeof(unsigned int)));
   }
+  return M3B_OK;
+}
+extern "C" {
+
+M3B_API int m3b_peer_export(m3b_handle* h, int32_t rank, int32_t world, void* ipc_handle_64B) {
+  REQUIRE(h && ipc_handle_64B, M3B_ERR_INVALID, "m3b_peer_export: null argument");
+  REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, M3B_ERR_INVALID, "m3b_peer_export: 1..8 ranks");
+  REQUIRE(h->n_bins > 0, M3B_ERR_STATE, "m3b_peer_export: upload the binning first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  int rc = m3b_peer_alloc(h);
+  if (rc != M3B_OK) return rc;
   h->peer_world = world; h->peer_rank = rank;
   for (int par = 0; par < 2; ++par) { h->peer_partial[par][rank] = h->d_partial[par]; h->peer_flag[par][rank] = h->d_flags[par]; }
   cudaIpcMemHandle_t mh;

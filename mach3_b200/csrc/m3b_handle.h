@@ -16,6 +16,7 @@ using namespace m3b;
 int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars, const float* osc_w,
                   double* host_slots_dev, int* done);      // m3b_batch.cu
 std::string& m3b_last_error_slot();     // thread-local last error (defined in m3b_api.cu)
+int m3b_peer_alloc(m3b_handle* h);      // the exported partial-histogram buffers + epoch flag of the peer exchange (m3b_api.cu)
 
 struct m3b_handle {
   m3b_config cfg{};
@@ -131,6 +132,7 @@ struct m3b_handle {
 
   // ---- peer exchange
   int peer_world = 0, peer_rank = 0;
+  bool peer_pull = true;                         // false: a non-lead member of a single-process group (m3b_group.cu) only publishes
   double* d_partial[2] = {nullptr, nullptr};     // this rank's exported partial histograms (two epochs' parity), {mc,w2}[n_bins]
   unsigned int* d_flags[2] = {nullptr, nullptr}; // [world]
   double* peer_partial[2][8] = {};

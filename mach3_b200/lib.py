@@ -30,7 +30,12 @@ EXPORTS = (
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
     "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
     "m3b_get_info", "m3b_set_timing", "m3b_kernel_time", "m3b_block_trace",
+    "m3b_group_create", "m3b_group_destroy", "m3b_group_last_error", "m3b_group_size", "m3b_group_member", "m3b_group_shard",
+    "m3b_group_upload_spline_monolith", "m3b_group_upload_binning_ex", "m3b_group_upload_events", "m3b_group_upload_selection",
+    "m3b_group_upload_data", "m3b_group_upload_osc", "m3b_group_connect", "m3b_group_alloc_host", "m3b_group_step",
+    "m3b_group_llh", "m3b_group_read_hist", "m3b_group_synchronize",
 )
+EXCHANGE_PEER, EXCHANGE_NCCL = 0, 1
 
 
 class Config(C.Structure):
@@ -67,6 +72,14 @@ def load():
         L.m3b_last_error.argtypes = [C.c_void_p]
         L.m3b_destroy.restype = None
         L.m3b_destroy.argtypes = [C.c_void_p]
+        L.m3b_group_last_error.restype = C.c_char_p
+        L.m3b_group_last_error.argtypes = [C.c_void_p]
+        L.m3b_group_destroy.restype = None
+        L.m3b_group_destroy.argtypes = [C.c_void_p]
+        L.m3b_group_member.restype = C.c_void_p
+        L.m3b_group_member.argtypes = [C.c_void_p, C.c_int32]
+        L.m3b_group_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.m3b_group_llh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -108,6 +121,19 @@ def _c(a, dtype):
 class Handle:
     """One device context = one sample handler + its spline monolith."""
 
+    @classmethod
+    def borrowed(cls, ptr, owner):
+        """A Handle object over an m3b_handle* that belongs to something else (a Group member): never destroyed here."""
+        self = cls.__new__(cls)
+        self.L = load()
+        self.h = C.c_void_p(ptr)
+        self._owner = owner
+        self._borrowed = True
+        self.n_samples = self.n_bins = self.n_events = self.n_params = 0
+        self._tot = C.c_double(0)
+        self._tot_ref = C.byref(self._tot)
+        return self
+
     def __init__(self, device=0, test_statistic=POISSON, update_w2=False, tile_events=0, flags=0):
         self.L = load()
         cfg = Config(device=device, test_statistic=test_statistic, update_w2=int(update_w2),
@@ -130,9 +156,9 @@ class Handle:
             raise M3BError(rc, (self.L.m3b_last_error(self.h) or b"").decode())
 
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             self.L.m3b_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -288,6 +314,10 @@ class Handle:
         buf = (C.c_char * (int(n) * dt.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=dt, count=int(n))
 
+    def free_host(self, arr):
+        """Give an alloc_host array back (the array must not be used afterwards)."""
+        self._ck(self.L.m3b_free_host(self.h, C.c_void_p(arr.ctypes.data)))
+
     def set_test_statistic(self, ts):
         self._ck(self.L.m3b_set_test_statistic(self.h, C.c_int32(ts)))
 
@@ -433,3 +463,134 @@ class Handle:
         i = Info()
         self._ck(self.L.m3b_get_info(self.h, C.byref(i)))
         return i
+
+
+class Group:
+    """ONE sample handler over several devices, driven by one process / one calling thread (m3b_group_*): the form in
+    which the reference's single-process fitters (Fitters/MR2T2.cpp:62-74) reach more than one GPU."""
+
+    def __init__(self, devices, test_statistic=POISSON, update_w2=False, tile_events=0, flags=0):
+        self.L = load()
+        cfg = Config(device=0, test_statistic=test_statistic, update_w2=int(update_w2), tile_events=tile_events, flags=flags)
+        dev = np.ascontiguousarray(devices, np.int32)
+        self.g = C.c_void_p()
+        rc = self.L.m3b_group_create(C.byref(cfg), _p(dev), C.c_int32(dev.size), C.byref(self.g))
+        if rc != OK:
+            raise M3BError(rc, (self.L.m3b_last_error(None) or b"").decode())
+        self.n = int(dev.size)
+        self.devices = [int(d) for d in dev]
+        self._members = [Handle.borrowed(self.L.m3b_group_member(self.g, i), self) for i in range(self.n)]
+        self.exchange = None
+        self.n_bins = self.n_samples = 0
+        self._tot = C.c_double(0)
+        self._tot_ref = C.byref(self._tot)
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise M3BError(rc, (self.L.m3b_group_last_error(self.g) or b"").decode())
+
+    def close(self):
+        if self.g:
+            self.L.m3b_group_destroy(self.g)
+            self.g = C.c_void_p()
+            for m in self._members:
+                m.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def member(self, i) -> Handle:
+        return self._members[i]
+
+    def shard(self, n_events, i):
+        e0, e1 = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.m3b_group_shard(self.g, C.c_int64(n_events), C.c_int32(i), C.byref(e0), C.byref(e1)))
+        return e0.value, e1.value
+
+    # ---- whole-workload uploads (the reference's arrays, sliced by the library)
+    def upload_spline_monolith(self, n_params, max_knots, coeff_x, n_pts, spl):
+        cx, npt = _c(coeff_x, np.float32), _c(n_pts, np.int16)
+        a = [_c(spl["nParamPerEvent"], np.uint32), _c(spl["paramNo_arr"], np.int16), _c(spl["nKnots_arr"], np.uint32),
+             _c(spl["coeff_many"], np.float32), _c(spl["nParamPerEvent_tf1"], np.uint32),
+             _c(spl["paramNo_tf1"], np.int16), _c(spl["coeff_tf1"], np.float32)]
+        self._ck(self.L.m3b_group_upload_spline_monolith(
+            self.g, C.c_int32(n_params), C.c_int32(max_knots), _p(cx), _p(npt), C.c_int64(a[0].size // 2),
+            _p(a[0]), _p(a[1]), _p(a[2]), C.c_uint32(a[3].size // 4), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6])))
+        for m in self._members:
+            m.n_params = int(n_params)
+
+    def upload_binning(self, edges):
+        for m in self._members:
+            m.upload_binning(edges)
+        self.n_bins, self.n_samples = self._members[0].n_bins, self._members[0].n_samples
+
+    def upload_events(self, sample_id, kin, norm_idx=None, n_norm_per_event=0, n_norm_values=0, use_osc=False,
+                      osc_idx=None, n_osc_values=0, static_w=None):
+        sid, k = _c(sample_id, np.int32), _c(kin, np.float64)
+        ni, oi, sw = _c(norm_idx, np.int16), _c(osc_idx, np.int32), _c(static_w, np.float32)
+        self._ck(self.L.m3b_group_upload_events(self.g, C.c_int64(sid.size), _p(sid), _p(k), C.c_int32(n_norm_per_event),
+                                                _p(ni), C.c_int32(n_norm_values), C.c_int32(int(use_osc)), _p(oi),
+                                                C.c_int64(n_osc_values), _p(sw)))
+        for i, m in enumerate(self._members):
+            e0, e1 = self.shard(sid.size, i)
+            m.n_events = e1 - e0
+
+    def upload_selection(self, cuts, values=None, n_events=None):
+        cs = np.array([c[0] for c in cuts], np.int32); cv = np.array([c[1] for c in cuts], np.int32)
+        lo = np.array([c[2] for c in cuts], np.float64); hi = np.array([c[3] for c in cuts], np.float64)
+        n_events = n_events or sum(m.n_events for m in self._members)
+        v = None if values is None else np.ascontiguousarray(np.asarray(values, np.float64).reshape(-1, n_events))
+        self._ck(self.L.m3b_group_upload_selection(self.g, C.c_int32(len(cuts)), _p(cs), _p(cv), _p(lo), _p(hi),
+                                                   C.c_int32(0 if v is None else v.shape[0]), _p(v)))
+
+    def upload_data(self, data):
+        d = _c(data, np.float64)
+        self._ck(self.L.m3b_group_upload_data(self.g, _p(d), C.c_int32(d.size)))
+
+    def upload_osc(self, osc_w):
+        o = _c(osc_w, np.float32)
+        self._ck(self.L.m3b_group_upload_osc(self.g, _p(o), C.c_int64(o.size)))
+
+    def connect(self, exchange="peer"):
+        if not self.n_bins:
+            self.n_bins, self.n_samples = self._members[0].n_bins, self._members[0].n_samples
+        self._ck(self.L.m3b_group_connect(self.g, C.c_int32(EXCHANGE_NCCL if exchange == "nccl" else EXCHANGE_PEER)))
+        self.exchange = exchange
+
+    def alloc_host(self, n, dtype=np.float32):
+        dt = np.dtype(dtype)
+        p = C.c_void_p()
+        self._ck(self.L.m3b_group_alloc_host(self.g, C.c_uint64(int(n) * dt.itemsize), C.byref(p)))
+        buf = (C.c_char * (int(n) * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=int(n))
+
+    def step(self, spline_pars, norm_pars=None, osc_w=None):
+        sp, nm = _c(spline_pars, np.float64), _c(norm_pars, np.float64)
+        if osc_w is not None:
+            assert osc_w.dtype == np.float32 and osc_w.flags.c_contiguous
+        self._keep = (sp, nm, osc_w)
+        rc = self.L.m3b_group_step(self.g, None if sp is None else sp.ctypes.data, None if nm is None or nm.size == 0 else nm.ctypes.data,
+                                   None if osc_w is None else osc_w.ctypes.data)
+        if rc != OK:
+            self._ck(rc)
+
+    def llh(self, per_sample=False):
+        if not per_sample:
+            rc = self.L.m3b_group_llh(self.g, self._tot_ref, None)
+            if rc != OK:
+                self._ck(rc)
+            return self._tot.value
+        ps = np.zeros(max(self.n_samples, 1), np.float64)
+        self._ck(self.L.m3b_group_llh(self.g, self._tot_ref, ps.ctypes.data))
+        return self._tot.value, ps[:self.n_samples]
+
+    def read_hist(self):
+        mc, w2 = np.zeros(self.n_bins, np.float64), np.zeros(self.n_bins, np.float64)
+        self._ck(self.L.m3b_group_read_hist(self.g, _p(mc), _p(w2)))
+        return mc, w2
+
+    def synchronize(self):
+        self._ck(self.L.m3b_group_synchronize(self.g))

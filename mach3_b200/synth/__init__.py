@@ -146,19 +146,34 @@ def param_layout(w: Workload):
     return typ, npts, cx
 
 
-def make_splines(w: Workload, e0=0, e1=None):
-    """Reference monolith arrays for events [e0,e1) (offsets relative to the chunk)."""
+def count_responses(w: Workload, e0=0, e1=None):
+    """-> (TSpline3 responses, TF1 responses) of events [e0,e1)."""
     e1 = w.n_events if e1 is None else e1
-    n = e1 - e0
     cfg = w.cfg()
     tc, tl = C.c_uint64(0), C.c_uint64(0)
     lib().m3s_count(C.byref(cfg), C.c_int64(e0), C.c_int64(e1), None, None, C.byref(tc), C.byref(tl))
-    tc, tl = tc.value, tl.value
-    out = dict(
-        nParamPerEvent=np.zeros(2 * n, np.uint32), paramNo_arr=np.zeros(tc, np.int16),
-        nKnots_arr=np.zeros(tc, np.uint64), coeff_many=np.zeros(tc * w.n_knots * 4, np.float32),
-        nParamPerEvent_tf1=np.zeros(2 * n, np.uint32), paramNo_tf1=np.zeros(tl, np.int16),
-        coeff_tf1=np.zeros(tl * 2, np.float32))
+    return tc.value, tl.value
+
+
+def make_splines(w: Workload, e0=0, e1=None, into=None):
+    """Reference monolith arrays for events [e0,e1) (offsets relative to the chunk).  `into`: a dict of
+    preallocated arrays of the same names (e.g. pinned staging buffers), at least as long as needed; the
+    result then holds views of their leading parts."""
+    e1 = w.n_events if e1 is None else e1
+    n = e1 - e0
+    cfg = w.cfg()
+    tc, tl = count_responses(w, e0, e1)
+    sizes = dict(nParamPerEvent=2 * n, paramNo_arr=tc, nKnots_arr=tc, coeff_many=tc * w.n_knots * 4,
+                 nParamPerEvent_tf1=2 * n, paramNo_tf1=tl, coeff_tf1=tl * 2)
+    if into is not None:
+        out = {k: into[k][:sz] for k, sz in sizes.items()}
+        assert all(out[k].size == sz for k, sz in sizes.items()), "staging buffers too small"
+    else:
+        out = dict(
+            nParamPerEvent=np.zeros(2 * n, np.uint32), paramNo_arr=np.zeros(tc, np.int16),
+            nKnots_arr=np.zeros(tc, np.uint64), coeff_many=np.zeros(tc * w.n_knots * 4, np.float32),
+            nParamPerEvent_tf1=np.zeros(2 * n, np.uint32), paramNo_tf1=np.zeros(tl, np.int16),
+            coeff_tf1=np.zeros(tl * 2, np.float32))
     lib().m3s_fill_splines(C.byref(cfg), C.c_int64(e0), C.c_int64(e1), _p(out["nParamPerEvent"]),
                            _p(out["paramNo_arr"]), _p(out["nKnots_arr"]), _p(out["coeff_many"]),
                            _p(out["nParamPerEvent_tf1"]), _p(out["paramNo_tf1"]), _p(out["coeff_tf1"]))
