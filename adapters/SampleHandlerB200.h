@@ -17,6 +17,8 @@
 //     EventInfo::norm_pointers[j]          -> norm_idx = ptr - <base of ParameterHandlerBase::_fPropVal>
 //     EventInfo::total_weight_pointers[k]  -> classified by address:
 //           inside SMonolith::cpu_total_weights       the event's spline weight: produced on the device, dropped
+//           inside BinnedSplineHandler::              slot index = ptr - weightvec_Monolith.data(): the binned arm
+//             weightvec_Monolith                      (SetSplinePointers, Samples/SampleHandlerFD.cpp:1196-1242)
 //           inside the oscillator's weight array      osc_idx = ptr - base          (SampleHandlerFD.cpp:1108-1122)
 //           &M3::Zero / &M3::Unity                    static factor 0 / 1           (:1128-1131)
 //           inside PointerBases::constant_weight_ranges   read now, folded into the event's static weight
@@ -29,12 +31,23 @@
 //       Samples/SampleHandlerFD.h:364-371)    cut variables are read once through ReturnKinematicParameter(var, event)
 //     BinningHandler (GetNDim/GetBinEdges/ -> m3b_upload_binning_ex         (uniform and non-uniform samples)
 //       IsUniform/GetNonUniformBins)
-//     SplineMonoStruct + SMonolith arrays  -> m3b_upload_spline_monolith    (pass them through SetMonolith())
+//     SplineMonoStruct + SMonolith arrays  -> m3b_upload_spline_monolith    (MonolithArrays)
+//     BinnedSplineHandler arrays           -> m3b_upload_binned_splines + m3b_upload_event_binned_splines (BinnedArrays)
 //
-// Per step Reweight() = [Oscillator->Evaluate()] + ONE m3b_step call: FindSplineSegment (host, the
-// reference's own history-dependent rule) -> fused evaluate/product/fill/-lnL kernel.  Nothing but
-// the -lnL scalar comes back; SampleHandlerFD_array / _array_w2 are refreshed lazily by SyncHostArrays()
-// (call it before GetMCArray()/PrintRates()/plotting).
+// Devices: MoveToB200(..., {d}) puts the whole sample on one B200 (one fused launch per step);
+// MoveToB200(..., {0,1,...,7}) spreads the events over several B200s of the box through m3b_group_* -- still ONE
+// process and ONE calling thread, the fitters do not change.
+//
+// Per step Reweight() = [Oscillator->Evaluate()] + ONE m3b_step / m3b_group_step call: FindSplineSegment (host, the
+// reference's own history-dependent rule) -> fused evaluate/product/fill/-lnL kernel.  The oscillation weights:
+//     * the oscillator's array is REGISTERED with CUDA once (PointerBases::register_osc_array, default) and handed to
+//       the library as it stands: the fill kernel streams it over PCIe (events in array order) or the library issues
+//       one DMA copy (indexed events) -- no host-side copy, no per-step synchronisation;
+//     * if the registration is refused, or register_osc_array is false, the array is copied into a pinned staging
+//       buffer every step (the pre-round-2 behaviour: ~0.1 ms per MB on one host thread).
+// Nothing but the -lnL scalar comes back; SampleHandlerFD_array / _array_w2 are refreshed lazily by SyncHostArrays()
+// (call it before GetMCArray()/PrintRates()/plotting).  Before MoveToB200() every virtual forwards to the reference's
+// own CPU implementation (FDBase::Reweight etc. -- e.g. for the Asimov pass of a set-up that moves later).
 //
 // The template keeps this header compilable against the real MaCh3 (needs ROOT; not available in this
 // repository's build image) and against the mock in tests/adapters/mock_mach3.h, which the repository's
@@ -42,6 +55,7 @@
 #pragma once
 #include "m3b200.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -68,6 +82,24 @@ struct MonolithArrays {               // Splines/SplineCommon.h:30-50, Splines/S
   const float* cpu_total_weights = nullptr;   // SMonolith::cpu_total_weights (address range only; never read)
 };
 
+// The other SplineBase implementation (Splines/BinnedSplineHandler.h:110-135), _LOW_MEMORY_STRUCTS_ build
+// (M3::float_t = float): its monolith arrays as they stand after TransferToMonolith.
+struct BinnedArrays {
+  int n_params = 0, max_knots = 0;
+  const float* knot_x = nullptr;              // FastSplineInfo::xPts per parameter, rows padded to max_knots
+  const int16_t* n_pts = nullptr;             // FastSplineInfo::nPts                [n_params]
+  int64_t n_slots = 0;                        // weightvec_Monolith.size()
+  const int32_t* uniquesplinevec_Monolith = nullptr;   // [n_slots]
+  const int32_t* coeffindexvec = nullptr;              // [n_slots]
+  int64_t n_unique = 0;
+  const int32_t* uniquecoeffindices = nullptr;         // [n_unique]
+  int64_t n_coeff = 0;
+  const float* manycoeff_arr = nullptr;       // [n_coeff*4]
+  const float* xcoeff_arr = nullptr;          // [n_coeff]
+  std::vector<const double*> spline_par_pointers;      // FastSplineInfo::splineParsPointer per parameter
+  const float* weightvec_Monolith = nullptr;  // address range of the slots (never read)
+};
+
 struct PointerBases {
   const double* norm_base = nullptr;  int n_norm = 0;        // ParameterHandlerBase::_fPropVal.data(), size
   const float* osc_base = nullptr;    int64_t n_osc = 0;     // the oscillator's weight array (may be null)
@@ -77,36 +109,46 @@ struct PointerBases {
   // per-event flux or POT weight array: {first, one-past-last}.  A weight pointer that is none of the above and lies
   // in none of these ranges is an ERROR (it might be rewritten every step, which the device copy would not see).
   std::vector<std::pair<const float*, const float*>> constant_weight_ranges;
+  // page-lock the oscillator's weight array where it lies (cudaHostRegister) so the device reads it without a host copy
+  bool register_osc_array = true;
 };
 
 template <class FDBase>
 class SampleHandlerB200 : public FDBase {
  public:
   using FDBase::FDBase;
-  ~SampleHandlerB200() override { if (h_) m3b_destroy(h_); }
+  ~SampleHandlerB200() override {
+    if (g_) m3b_group_destroy(g_);
+    else if (h_) m3b_destroy(h_);
+  }
 
   // Call once after the base class finished Initialise() (events, binning, splines, pointers wired).
-  void MoveToB200(const MonolithArrays& mono, const PointerBases& bases, int cuda_device = 0) {
+  // Exactly one of mono.n_params / binned.n_params may be non-zero (SampleHandlerFD holds one SplineBase).
+  void MoveToB200(const MonolithArrays& mono, const PointerBases& bases, const std::vector<int>& cuda_devices = {0},
+                  const BinnedArrays& binned = BinnedArrays()) {
+    if (cuda_devices.empty() || cuda_devices.size() > 8) throw std::runtime_error("SampleHandlerB200: 1..8 devices");
+    if (mono.n_params > 0 && binned.n_params > 0) throw std::runtime_error("SampleHandlerB200: monolith OR binned splines, not both");
+    if (binned.n_params > 0 && cuda_devices.size() > 1) throw std::runtime_error("SampleHandlerB200: the binned-spline arm runs on one device");
     m3b_config cfg{};
-    cfg.device = cuda_device;
+    cfg.device = cuda_devices[0];
     cfg.test_statistic = static_cast<int32_t>(this->fTestStatistic);   // enum TestStatistic == m3b_test_statistic
     cfg.update_w2 = this->UpdateW2 ? 1 : 0;
-    check(m3b_create(&cfg, &h_), "m3b_create");
+    if (cuda_devices.size() == 1) {
+      check(m3b_create(&cfg, &h_), "m3b_create");
+    } else {
+      std::vector<int32_t> dev(cuda_devices.begin(), cuda_devices.end());
+      if (m3b_group_create(&cfg, dev.data(), static_cast<int32_t>(dev.size()), &g_) != M3B_OK)
+        throw std::runtime_error(std::string("SampleHandlerB200: m3b_group_create: ") + m3b_last_error(nullptr));
+      h_ = m3b_group_member(g_, 0);
+    }
     const int64_t E = static_cast<int64_t>(this->GetNEvents());
     // functional ("shift") parameters rewrite the kinematics through std::functions every step (ApplyShifts,
     // Samples/SampleHandlerFD.cpp:545-564): not something a constant device table can follow -- refuse, loudly
     for (const auto& shifts : this->funcParsGrid)
       if (!shifts.empty()) throw std::runtime_error("SampleHandlerB200: functional (shift) parameters are not supported by this adapter");
     bases_ = bases;
-    spline_ptrs_ = mono.spline_par_pointers;
+    spline_ptrs_ = mono.n_params > 0 ? mono.spline_par_pointers : binned.spline_par_pointers;
     spline_vals_.assign(spline_ptrs_.size(), 0.0);
-
-    // --- spline monolith: the reference's arrays, as they are
-    if (mono.n_params > 0)
-      check(m3b_upload_spline_monolith(h_, mono.n_params, mono.max_knots, mono.coeff_x, mono.n_pts, E,
-                                       mono.nParamPerEvent, mono.paramNo_arr, mono.nKnots_arr, mono.total_knots,
-                                       mono.coeff_many, mono.nParamPerEvent_tf1, mono.paramNo_tf1, mono.coeff_tf1),
-            "m3b_upload_spline_monolith");
 
     // --- binning (BinningHandler, Samples/BinningHandler.cpp:257-291): uniform samples hand over their axis edges,
     //     non-uniform ones (Samples/SampleStructs.h:468-528) their boxes (BinInfo::Extent); the library rebuilds the
@@ -133,18 +175,35 @@ class SampleHandlerB200 : public FDBase {
           for (int d = 0; d < ndim[s]; ++d) { edges.push_back(b.Extent[d][0]); edges.push_back(b.Extent[d][1]); }
       }
     }
-    check(m3b_upload_binning_ex(h_, nS, ndim.data(), uniform.data(), nbins.data(), edges.data()), "m3b_upload_binning_ex");
+    if (g_) gcheck(m3b_group_upload_binning_ex(g_, nS, ndim.data(), uniform.data(), nbins.data(), edges.data()), "m3b_group_upload_binning_ex");
+    else check(m3b_upload_binning_ex(h_, nS, ndim.data(), uniform.data(), nbins.data(), edges.data()), "m3b_upload_binning_ex");
     n_bins_ = this->GetBinningHandler()->GetNBins();
+
+    // --- the spline handler's arrays, as they are
+    if (mono.n_params > 0) {
+      if (g_) gcheck(m3b_group_upload_spline_monolith(g_, mono.n_params, mono.max_knots, mono.coeff_x, mono.n_pts, E, mono.nParamPerEvent,
+                                                      mono.paramNo_arr, mono.nKnots_arr, mono.total_knots, mono.coeff_many,
+                                                      mono.nParamPerEvent_tf1, mono.paramNo_tf1, mono.coeff_tf1), "m3b_group_upload_spline_monolith");
+      else check(m3b_upload_spline_monolith(h_, mono.n_params, mono.max_knots, mono.coeff_x, mono.n_pts, E, mono.nParamPerEvent,
+                                            mono.paramNo_arr, mono.nKnots_arr, mono.total_knots, mono.coeff_many,
+                                            mono.nParamPerEvent_tf1, mono.paramNo_tf1, mono.coeff_tf1), "m3b_upload_spline_monolith");
+    } else if (binned.n_params > 0) {
+      check(m3b_upload_binned_splines(h_, binned.n_params, binned.max_knots, binned.knot_x, binned.n_pts, binned.n_slots,
+                                      binned.uniquesplinevec_Monolith, binned.coeffindexvec, binned.n_unique, binned.uniquecoeffindices,
+                                      binned.n_coeff, binned.manycoeff_arr, binned.xcoeff_arr), "m3b_upload_binned_splines");
+    }
 
     // --- events: pointers -> indices
     size_t max_norm = 0;
     for (int64_t e = 0; e < E; ++e) max_norm = std::max(max_norm, this->MCSamples[e].norm_pointers.size());
     if (max_norm > 16) throw std::runtime_error("SampleHandlerB200: more than 16 norm pointers on one event");
-    std::vector<int32_t> sample_id(E), osc_idx(E, 0);
+    std::vector<int32_t> sample_id(E), osc_idx(E, -1);
     std::vector<double> kin(static_cast<size_t>(max_dim) * E, 0.0);
     std::vector<int16_t> norm_idx(static_cast<size_t>(max_norm) * E, -1);
     std::vector<float> static_w(E, 1.0f);
-    bool any_osc = false, all_osc = true;
+    std::vector<uint32_t> n_binned(binned.n_params > 0 ? E : 0, 0);
+    std::vector<int32_t> binned_slot;
+    bool any_osc = false, identity = true;
     for (int64_t e = 0; e < E; ++e) {
       const auto& ev = this->MCSamples[e];
       sample_id[e] = ev.NominalSample;
@@ -154,14 +213,16 @@ class SampleHandlerB200 : public FDBase {
         if (off < 0 || off >= bases.n_norm) throw std::runtime_error("SampleHandlerB200: norm pointer outside the parameter array");
         norm_idx[e * max_norm + j] = static_cast<int16_t>(off);
       }
-      bool has_osc = false;
       for (const auto* p : ev.total_weight_pointers) {
         if (mono.cpu_total_weights && p >= mono.cpu_total_weights && p < mono.cpu_total_weights + E) {
           if (p - mono.cpu_total_weights != e) throw std::runtime_error("SampleHandlerB200: event points at another event's spline weight");
+        } else if (binned.weightvec_Monolith && p >= binned.weightvec_Monolith && p < binned.weightvec_Monolith + binned.n_slots) {
+          binned_slot.push_back(static_cast<int32_t>(p - binned.weightvec_Monolith));      // pointer order kept (:1236-1242)
+          ++n_binned[e];
         } else if (bases.osc_base && p >= bases.osc_base && p < bases.osc_base + bases.n_osc) {
-          if (has_osc) throw std::runtime_error("SampleHandlerB200: two oscillation weights on one event");
+          if (osc_idx[e] >= 0) throw std::runtime_error("SampleHandlerB200: two oscillation weights on one event");
           osc_idx[e] = static_cast<int32_t>(p - bases.osc_base);
-          has_osc = true;
+          any_osc = true;
         } else if (p == bases.zero) {
           static_w[e] = 0.0f;                 // NC event with flavour change (SampleHandlerFD.cpp:1128-1131)
         } else if (p != bases.unity) {
@@ -169,35 +230,34 @@ class SampleHandlerB200 : public FDBase {
           for (const auto& r : bases.constant_weight_ranges) constant |= (p >= r.first && p < r.second);
           if (!constant)
             throw std::runtime_error("SampleHandlerB200: event " + std::to_string(e) + " has a weight pointer that is neither the "
-                                     "oscillation array, the spline monolith, M3::Zero/Unity nor inside PointerBases::constant_weight_ranges");
+                                     "oscillation array, the spline handler, M3::Zero/Unity nor inside PointerBases::constant_weight_ranges");
           static_w[e] *= static_cast<float>(*p);    // experiment-specific constant weight, folded once
         }
       }
-      any_osc |= has_osc;
-      all_osc &= has_osc;
+      identity &= (osc_idx[e] == e);
     }
-    if (any_osc && !all_osc) {
-      // events without an oscillation weight read a slot that always holds 1.0f
-      extra_unity_slot_ = true;
-      for (int64_t e = 0; e < E; ++e) {
-        bool has = false;
-        for (const auto* p : this->MCSamples[e].total_weight_pointers)
-          has |= (bases.osc_base && p >= bases.osc_base && p < bases.osc_base + bases.n_osc);
-        if (!has) osc_idx[e] = static_cast<int32_t>(bases.n_osc);
-      }
-    }
-    n_osc_dev_ = any_osc ? bases.n_osc + (extra_unity_slot_ ? 1 : 0) : 0;
-    check(m3b_upload_events(h_, E, sample_id.data(), kin.data(), static_cast<int32_t>(max_norm),
-                            max_norm ? norm_idx.data() : nullptr, bases.n_norm, any_osc ? 1 : 0,
-                            any_osc ? osc_idx.data() : nullptr, n_osc_dev_, static_w.data()),
-          "m3b_upload_events");
+    // events in the oscillator array's own order (one weight per event): no index table, the kernel streams the array
+    osc_direct_ = any_osc && identity && bases.n_osc == E;
+    n_osc_dev_ = any_osc ? bases.n_osc : 0;
+    const int32_t* oi = (any_osc && !osc_direct_) ? osc_idx.data() : nullptr;       // -1 entries: no oscillation weight (reads 1.0)
+    if (g_) gcheck(m3b_group_upload_events(g_, E, sample_id.data(), kin.data(), static_cast<int32_t>(max_norm), max_norm ? norm_idx.data() : nullptr,
+                                           bases.n_norm, any_osc ? 1 : 0, oi, n_osc_dev_, static_w.data()), "m3b_group_upload_events");
+    else check(m3b_upload_events(h_, E, sample_id.data(), kin.data(), static_cast<int32_t>(max_norm), max_norm ? norm_idx.data() : nullptr,
+                                 bases.n_norm, any_osc ? 1 : 0, oi, n_osc_dev_, static_w.data()), "m3b_upload_events");
+    if (binned.n_params > 0)
+      check(m3b_upload_event_binned_splines(h_, E, n_binned.data(), binned_slot.data()), "m3b_upload_event_binned_splines");
     if (any_osc) {
-      // staging copy of the oscillator's weight array in pinned + mapped memory from the library: the fill kernel
-      // streams it over PCIe itself (zero-copy), no separate H2D pass
-      void* p = nullptr;
-      check(m3b_alloc_host(h_, sizeof(float) * static_cast<size_t>(n_osc_dev_), &p), "m3b_alloc_host");
-      osc_stage_ = static_cast<float*>(p);
-      std::fill(osc_stage_, osc_stage_ + n_osc_dev_, 1.0f);
+      // the oscillator's array, page-locked where it lies; else a pinned staging copy refreshed every step
+      if (bases.register_osc_array &&
+          m3b_register_host_buffer(h_, const_cast<float*>(bases.osc_base), sizeof(float) * static_cast<uint64_t>(bases.n_osc)) == M3B_OK) {
+        osc_registered_ = true;
+      } else {
+        void* p = nullptr;
+        if (g_) gcheck(m3b_group_alloc_host(g_, sizeof(float) * static_cast<size_t>(n_osc_dev_), &p), "m3b_group_alloc_host");
+        else check(m3b_alloc_host(h_, sizeof(float) * static_cast<size_t>(n_osc_dev_), &p), "m3b_alloc_host");
+        osc_stage_ = static_cast<float*>(p);
+        std::fill(osc_stage_, osc_stage_ + n_osc_dev_, 1.0f);
+      }
     }
     // --- selection cuts (Samples/SampleHandlerFD.cpp:281-294): one table row per distinct ParamToCutOnIt, filled
     //     through the experiment's own ReturnKinematicParameter; without functional shifts the values are constants
@@ -215,29 +275,48 @@ class SampleHandlerB200 : public FDBase {
         std::vector<double> values(distinct.size() * static_cast<size_t>(E));
         for (size_t v = 0; v < distinct.size(); ++v)
           for (int64_t e = 0; e < E; ++e) values[v * static_cast<size_t>(E) + e] = this->ReturnKinematicParameter(distinct[v], static_cast<int>(e));
-        check(m3b_upload_selection(h_, static_cast<int32_t>(cut_sample.size()), cut_sample.data(), cut_var.data(), lo.data(), hi.data(),
-                                   static_cast<int32_t>(distinct.size()), values.data()), "m3b_upload_selection");
+        const int32_t nc = static_cast<int32_t>(cut_sample.size()), nv = static_cast<int32_t>(distinct.size());
+        if (g_) gcheck(m3b_group_upload_selection(g_, nc, cut_sample.data(), cut_var.data(), lo.data(), hi.data(), nv, values.data()), "m3b_group_upload_selection");
+        else check(m3b_upload_selection(h_, nc, cut_sample.data(), cut_var.data(), lo.data(), hi.data(), nv, values.data()), "m3b_upload_selection");
       }
     }
-    check(m3b_upload_data(h_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_upload_data");
+    if (g_) {
+      gcheck(m3b_group_upload_data(g_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_group_upload_data");
+      gcheck(m3b_group_connect(g_, M3B_EXCHANGE_PEER), "m3b_group_connect");
+    } else {
+      check(m3b_upload_data(h_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_upload_data");
+    }
     ready_ = true;
   }
+  // (pre-round-2 signature)
+  void MoveToB200(const MonolithArrays& mono, const PointerBases& bases, int cuda_device) { MoveToB200(mono, bases, std::vector<int>{cuda_device}); }
 
   // SampleHandlerFD::AddData (Samples/SampleHandlerFD.cpp:955-1044) changed SampleHandlerFD_data
-  void DataChanged() { check(m3b_upload_data(h_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_upload_data"); }
+  void DataChanged() {
+    if (g_) gcheck(m3b_group_upload_data(g_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_group_upload_data");
+    else check(m3b_upload_data(h_, this->SampleHandlerFD_data.data(), n_bins_), "m3b_upload_data");
+  }
 
   // ---- the three virtuals the fitters call -------------------------------------------------------
   void Reweight() override {
-    if (!ready_) { FDBase::Reweight(); return; }           // before MoveToB200: the reference's own path
+    if (!ready_) { FDBase::Reweight(); return; }           // before MoveToB200: the reference's own CPU path
     if (this->Oscillator) this->Oscillator->Evaluate();    // NuOscillator stays where it is (input array)
     for (size_t p = 0; p < spline_ptrs_.size(); ++p) spline_vals_[p] = *spline_ptrs_[p];
     const float* osc = nullptr;
     if (n_osc_dev_ > 0) {
-      check(m3b_synchronize(h_), "m3b_synchronize");       // the previous step may still be reading the staging array
-      std::copy(bases_.osc_base, bases_.osc_base + bases_.n_osc, osc_stage_);
-      osc = osc_stage_;
+      if (osc_registered_) {
+        osc = bases_.osc_base;                              // read by the device where it lies; the caller's next
+                                                            // Evaluate() comes after GetLikelihood(), which synchronises
+      } else {
+        if (g_) gcheck(m3b_group_synchronize(g_), "m3b_group_synchronize");
+        else check(m3b_synchronize(h_), "m3b_synchronize"); // the previous step may still be reading the staging array
+        std::copy(bases_.osc_base, bases_.osc_base + bases_.n_osc, osc_stage_);
+        osc = osc_stage_;
+      }
     }
-    check(m3b_step(h_, spline_vals_.empty() ? nullptr : spline_vals_.data(), bases_.norm_base, osc), "m3b_step");
+    const double* sp = spline_vals_.empty() ? nullptr : spline_vals_.data();
+    if (g_) gcheck(m3b_group_step(g_, sp, bases_.norm_base, osc), "m3b_group_step");
+    else check(m3b_step(h_, sp, bases_.norm_base, osc), "m3b_step");
     host_arrays_stale_ = true;
     if (!this->UpdateW2) this->FirstTimeW2 = false;        // Samples/SampleHandlerFD.cpp:342
   }
@@ -245,7 +324,8 @@ class SampleHandlerB200 : public FDBase {
   double GetLikelihood() const override {
     if (!ready_) return FDBase::GetLikelihood();
     double total = 0;
-    check(m3b_llh(h_, &total, nullptr), "m3b_llh");
+    if (g_) gcheck(m3b_group_llh(g_, &total, nullptr), "m3b_group_llh");
+    else check(m3b_llh(h_, &total, nullptr), "m3b_llh");
     return total;
   }
 
@@ -253,31 +333,39 @@ class SampleHandlerB200 : public FDBase {
     if (!ready_) return FDBase::GetSampleLikelihood(isample);
     std::vector<double> per(static_cast<size_t>(const_cast<SampleHandlerB200*>(this)->GetNsamples()));
     double total = 0;
-    check(m3b_llh(h_, &total, per.data()), "m3b_llh");
+    if (g_) gcheck(m3b_group_llh(g_, &total, per.data()), "m3b_group_llh");
+    else check(m3b_llh(h_, &total, per.data()), "m3b_llh");
     return per.at(static_cast<size_t>(isample));
   }
 
   // Lazy host mirrors of SampleHandlerFD_array / _array_w2 (Samples/SampleHandlerFD.h:337-341).
   void SyncHostArrays() {
     if (!ready_ || !host_arrays_stale_) return;
-    check(m3b_read_hist(h_, this->SampleHandlerFD_array.data(), this->SampleHandlerFD_array_w2.data()), "m3b_read_hist");
+    if (g_) gcheck(m3b_group_read_hist(g_, this->SampleHandlerFD_array.data(), this->SampleHandlerFD_array_w2.data()), "m3b_group_read_hist");
+    else check(m3b_read_hist(h_, this->SampleHandlerFD_array.data(), this->SampleHandlerFD_array_w2.data()), "m3b_read_hist");
     host_arrays_stale_ = false;
   }
 
-  m3b_handle* handle() const { return h_; }
+  m3b_handle* handle() const { return h_; }         // the (lead) device handle
+  m3b_group* group() const { return g_; }           // non-null when the sample is spread over several devices
+  bool OscillatorArrayRegistered() const { return osc_registered_; }
 
  private:
   void check(int rc, const char* what) const {
     if (rc != M3B_OK) throw std::runtime_error(std::string("SampleHandlerB200: ") + what + ": " + m3b_last_error(h_));
   }
+  void gcheck(int rc, const char* what) const {
+    if (rc != M3B_OK) throw std::runtime_error(std::string("SampleHandlerB200: ") + what + ": " + m3b_group_last_error(g_));
+  }
   m3b_handle* h_ = nullptr;
-  bool ready_ = false, host_arrays_stale_ = false, extra_unity_slot_ = false;
+  m3b_group* g_ = nullptr;
+  bool ready_ = false, host_arrays_stale_ = false, osc_direct_ = false, osc_registered_ = false;
   int n_bins_ = 0;
   int64_t n_osc_dev_ = 0;
   PointerBases bases_{};
   std::vector<const double*> spline_ptrs_;
   std::vector<double> spline_vals_;
-  float* osc_stage_ = nullptr;             // m3b_alloc_host; freed with the handle
+  float* osc_stage_ = nullptr;             // pinned staging copy (only when the oscillator's array could not be registered)
 };
 
 }  // namespace m3b200

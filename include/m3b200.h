@@ -166,7 +166,8 @@ M3B_API int m3b_read_event_weights_f64(m3b_handle* h, double* spline_w, double* 
  *   norm_idx[e*npe+j]     index into the per-step norm value array (EventInfo::norm_pointers as
  *                         offsets from ParameterHandlerBase::_fPropVal), <0 = none
  *   osc_idx[E]            index into the per-step oscillation weight array (osc_w_pointer as an
- *                         offset), NULL = event e reads osc[e]; use_osc=0: no osc weight at all
+ *                         offset; -1 = this event has none, e.g. &M3::Unity for NC events), NULL = event e reads
+ *                         osc[e]; use_osc=0: no osc weight at all
  *   static_w[E]           product of the event's constant extra weights, NULL = none
  * Events must come in the same order as the spline monolith's events.                              */
 M3B_API int m3b_upload_binning(m3b_handle* h, int32_t n_samples, const int32_t* n_dim,

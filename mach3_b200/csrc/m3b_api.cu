@@ -545,7 +545,7 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
     if (osc_idx) {
       std::vector<int32_t> oi(static_cast<size_t>(EP), 0);
       for (int64_t e = 0; e < E; ++e) {
-        REQUIRE(osc_idx[e] >= 0 && osc_idx[e] < n_osc_values, M3B_ERR_INVALID, "m3b_upload_events: osc_idx out of range");
+        REQUIRE(osc_idx[e] >= -1 && osc_idx[e] < n_osc_values, M3B_ERR_INVALID, "m3b_upload_events: osc_idx out of range");
         oi[e] = osc_idx[e];
       }
       CK(dev_upload(h, &h->d_osc_idx, oi));
@@ -687,7 +687,7 @@ M3B_API int m3b_upload_osc(m3b_handle* h, const float* osc_w, int64_t n) {
 M3B_API int m3b_register_host_buffer(m3b_handle* h, void* ptr, uint64_t bytes) {
   REQUIRE(h && ptr && bytes, M3B_ERR_INVALID, "m3b_register_host_buffer: bad argument");
   CK(cudaSetDevice(h->device));
-  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   h->registered.push_back(ptr);
   return M3B_OK;
 }

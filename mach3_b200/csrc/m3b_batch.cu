@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kCT + 32, 1) fill_batch_kernel(const __grid_co
       float w_osc = 1.f, w_static = 1.f;
       if (a.osc) {
         const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[ev]) : (ev < a.n_events ? ev : 0);
-        w_osc = a.osc[oi];
+        w_osc = oi >= 0 ? a.osc[oi] : 1.f;
       }
       if (a.static_w) w_static = a.static_w[ev];
       int ni[4] = {-1, -1, -1, -1};

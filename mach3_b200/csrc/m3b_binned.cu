@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) binned_fill_kernel(const __grid_constant_
     R w_osc = 1, w_static = 1;
     if (oscp) {
       const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
-      w_osc = oscp[oi];
+      w_osc = oi >= 0 ? oscp[oi] : R(1);
     }
     if (statp) w_static = statp[e];
     // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kUnit + 32, 1) fill_tma_kernel(const __grid_co
             w_osc[q] = 1.f; w_static[q] = 1.f;
             if (a.osc && !a.osc_host) {
               const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
-              w_osc[q] = a.osc[oi];
+              w_osc[q] = oi >= 0 ? a.osc[oi] : 1.f;          // osc_idx -1: the event carries no oscillation weight
             }
             if (a.static_w) w_static[q] = a.static_w[e];
             w_spl[q] = 1.0f;

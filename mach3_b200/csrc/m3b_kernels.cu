@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) fill_kernel(const __grid_consta
     float w_osc = 1.f, w_static = 1.f;
     if (a.osc) {
       const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
-      w_osc = a.osc[oi];
+      w_osc = oi >= 0 ? a.osc[oi] : 1.f;
     }
     if (a.static_w) w_static = a.static_w[e];
     // CalcWeightTotal, first factor: norms (double -> float on the host), reference order

@@ -23,7 +23,9 @@
 #include "Splines/gpuSplineUtils.cuh"
 #endif
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -309,6 +311,7 @@ using FDType = FD;
 
 struct Binned final : BinnedSplineHandler {
   std::vector<double> pars;
+  int64_t n_coeff_keep = 0;          // length of xcoeff_arr / manycoeff_arr (in knots)
   static ParameterHandlerGeneric* fake_xsec() { static ParameterHandlerGeneric x; return &x; }
   // only stored by the constructor (Splines/BinnedSplineHandler.cpp:14-32), never dereferenced by Evaluate
   static MaCh3Modes* fake_modes() { static long long blob[64]; return reinterpret_cast<MaCh3Modes*>(blob); }
@@ -393,6 +396,7 @@ REFP_API void* refp_fd_attach_binned(void* p, int P, int max_knots, const double
   b->coeffindexvec.assign(coeffindexvec, coeffindexvec + n_slots);
   b->uniquecoeffindices.assign(uniquecoeffindices, uniquecoeffindices + n_unique);
   b->weightvec_Monolith.assign(size_t(n_slots), M3::float_t(1));        // flat slots stay 1 (.cpp:672)
+  b->n_coeff_keep = n_coeff;
   b->xcoeff_arr = new M3::float_t[size_t(n_coeff)];
   b->manycoeff_arr = new M3::float_t[size_t(n_coeff) * 4];
   for (int64_t i = 0; i < n_coeff; ++i) b->xcoeff_arr[i] = M3::float_t(xcoeff[i]);
@@ -517,7 +521,10 @@ REFP_API void refp_fd_segments(void* p, int16_t* out) {
 }
 
 // ---- the adapter over the real class (only in the build that links libm3b200: libm3ref_path_lm_b200.so) ----------
-REFP_API int refp_fd_move_to_b200(void* p, int device) {
+REFP_API int refp_fd_move_to_b200_ex(void* p, int n_devices, const int* devices);
+REFP_API int refp_fd_move_to_b200(void* p, int device) { return refp_fd_move_to_b200_ex(p, 1, &device); }
+// devices: one entry = the whole sample on that B200; several = m3b_group_* (one process, one calling thread)
+REFP_API int refp_fd_move_to_b200_ex(void* p, int n_devices, const int* devices) {
 #ifdef M3B_WITH_ADAPTER
   FD* fd = static_cast<FD*>(p);
   FDType* b = static_cast<FDType*>(fd);
@@ -543,10 +550,34 @@ REFP_API int refp_fd_move_to_b200(void* p, int device) {
   pb.osc_base = fd->pool.data(); pb.n_osc = int64_t(fd->nEvents);       // pool = [osc per event | extra weights]
   pb.zero = &M3::Zero; pb.unity = &M3::Unity;
   pb.constant_weight_ranges.push_back({fd->pool.data() + fd->nEvents, fd->pool.data() + fd->pool.size()});   // the extras
-  try { b->MoveToB200(a, pb, device); } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+  // the binned arm (Samples/SampleHandlerFD.cpp:1196-1242): BinnedSplineHandler's monolith arrays as they stand
+  m3b200::BinnedArrays ba;
+  std::vector<float> knot_x; std::vector<int16_t> bn_pts;
+  std::vector<int32_t> usv, civ, uci;
+#ifdef _LOW_MEMORY_STRUCTS_
+  if (Binned* bs = dynamic_cast<Binned*>(fd->SplineHandler.get())) {
+    int K = 0;
+    for (int i = 0; i < bs->nParams; ++i) K = std::max(K, int(bs->SplineInfoArray[i].nPts));
+    knot_x.assign(size_t(bs->nParams) * K, 0.f); bn_pts.resize(size_t(bs->nParams));
+    for (int i = 0; i < bs->nParams; ++i) {
+      bn_pts[i] = int16_t(bs->SplineInfoArray[i].nPts);
+      for (int k = 0; k < bn_pts[i]; ++k) knot_x[size_t(i) * K + k] = bs->SplineInfoArray[i].xPts[k];
+      ba.spline_par_pointers.push_back(bs->SplineInfoArray[i].splineParsPointer);
+    }
+    usv.assign(bs->uniquesplinevec_Monolith.begin(), bs->uniquesplinevec_Monolith.end());
+    civ.assign(bs->coeffindexvec.begin(), bs->coeffindexvec.end());
+    uci.assign(bs->uniquecoeffindices.begin(), bs->uniquecoeffindices.end());
+    ba.n_params = bs->nParams; ba.max_knots = K; ba.knot_x = knot_x.data(); ba.n_pts = bn_pts.data();
+    ba.n_slots = int64_t(bs->weightvec_Monolith.size()); ba.uniquesplinevec_Monolith = usv.data(); ba.coeffindexvec = civ.data();
+    ba.n_unique = int64_t(uci.size()); ba.uniquecoeffindices = uci.data(); ba.n_coeff = bs->n_coeff_keep;
+    ba.manycoeff_arr = bs->manycoeff_arr; ba.xcoeff_arr = bs->xcoeff_arr; ba.weightvec_Monolith = bs->weightvec_Monolith.data();
+  }
+#endif
+  try { b->MoveToB200(a, pb, std::vector<int>(devices, devices + n_devices), ba); }
+  catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
   return 0;
 #else
-  (void)p; (void)device;
+  (void)p; (void)n_devices; (void)devices;
   return -1;
 #endif
 }

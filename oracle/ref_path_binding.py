@@ -278,7 +278,9 @@ class RefSampleHandlerFD:
 
     # -- only in build "float_b200": the object is an m3b200::SampleHandlerB200<FD> over the reference's class
     def move_to_b200(self, device=0):
-        if self.L.refp_fd_move_to_b200(self.h, int(device)):
+        """device: one ordinal, or a list of ordinals (the sample is then spread over them through m3b_group_*)."""
+        dev = np.ascontiguousarray([device] if np.isscalar(device) else list(device), np.int32)
+        if self.L.refp_fd_move_to_b200_ex(self.h, int(dev.size), _p(dev)):
             raise RuntimeError("SampleHandlerB200::MoveToB200 failed")
 
     def data_changed(self):

@@ -3,14 +3,19 @@
 // pointer vectors into the parameter array, the oscillator's weight array and the monolith's
 // cpu_total_weights), then two instances run the same proposals: one through the mock's scalar CPU path,
 // one through SampleHandlerB200 -> libm3b200 on the B200.  -lnL must agree to 1e-6 relative
-// (north_star), histograms to 1e-9.    usage: adapter_test [n_events] [barlow]
+// (north_star), histograms to 1e-9.    usage: adapter_test [n_events] [barlow|poisson] [n_members] [time]
+// n_members > 1: the adapter spreads the sample over that many group members (devices 0..n-1 modulo the GPUs present;
+// m3b_group_*: still one process, one calling thread).  "time": prints the adapter's real per-step cost
+// (Oscillator->Evaluate() + Reweight() + GetLikelihood(), host wall clock) for the registered-array and the staging route.
 #include "mock_mach3.h"
 #include "SampleHandlerB200.h"
 #include "m3b_synth.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cuda_runtime_api.h>
 #include <random>
 
 struct Workload {
@@ -124,9 +129,17 @@ int main(int argc, char** argv) {
   m3s_param_layout(&c, w.type.data(), w.n_pts.data(), w.coeff_x.data());
   w.pars.assign(c.n_params, 0.); w.norms.assign(c.n_norm_params, 1.);
 
+  const int n_members = argc > 3 ? atoi(argv[3]) : 1;
+  const bool timing = argc > 4 && !strcmp(argv[4], "time");
+  int n_gpus = 1;
+  cudaGetDeviceCount(&n_gpus);
+  std::vector<int> devices;
+  for (int i = 0; i < n_members; ++i) devices.push_back(i % (n_gpus > 0 ? n_gpus : 1));
   ExperimentFD cpu(w, barlow, barlow);
   m3b200::SampleHandlerB200<ExperimentFD> gpu(w, barlow, barlow);
-  gpu.MoveToB200(gpu.Arrays(), gpu.Bases(), 0);
+  gpu.MoveToB200(gpu.Arrays(), gpu.Bases(), devices);
+  printf("adapter on %d member(s), %d GPU(s) present, oscillator array %s\n", n_members, n_gpus,
+         gpu.OscillatorArrayRegistered() ? "registered in place" : "staged");
 
   SampleHandlerBase* handlers[2] = {&cpu, &gpu};       // the fitters only see the base-class virtuals
   m3s_proposal(&c, -1, w.pars.data(), w.norms.data());
@@ -154,6 +167,25 @@ int main(int argc, char** argv) {
     ok &= good;
     printf("step %2d: -lnL cpu %.9f  b200 %.9f  rel %.2e  hist %.1e  w2 %.1e  sum(per-sample) %.9f  %s\n", step, l[0], l[1], rel, dmax, dw2, ls,
            good ? "OK" : "FAIL");
+  }
+  if (timing) {
+    // the adapter's real step cost, as a fitter pays it: Reweight() (incl. Oscillator->Evaluate()) + GetLikelihood()
+    for (int route = 0; route < 2; ++route) {
+      m3b200::SampleHandlerB200<ExperimentFD> t(w, barlow, barlow);
+      m3b200::PointerBases pb = t.Bases();
+      pb.register_osc_array = route == 0;
+      t.MoveToB200(t.Arrays(), pb, devices);
+      t.SetData(data); t.DataChanged();
+      for (int k = 0; k < 10; ++k) { m3s_proposal(&c, k, w.pars.data(), w.norms.data()); t.Reweight(); t.GetLikelihood(); }
+      const auto t0 = std::chrono::steady_clock::now();
+      const int K = 200;
+      double l = 0;
+      for (int k = 0; k < K; ++k) { m3s_proposal(&c, k % 16, w.pars.data(), w.norms.data()); t.Reweight(); l = t.GetLikelihood(); }
+      const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / K;
+      printf("adapter step cost (%s): %.1f us per Reweight+GetLikelihood, %lld events, -lnL %.6f\n",
+             t.OscillatorArrayRegistered() ? "oscillator array registered, read in place" : "oscillator array copied to a pinned staging buffer every step",
+             us, (long long)E, l);
+    }
   }
   printf(ok ? "ADAPTER OK\n" : "ADAPTER FAILED\n");
   return ok ? 0 : 1;

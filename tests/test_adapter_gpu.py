@@ -40,11 +40,13 @@ def test_smonolithgpu_adapter_is_a_drop_in(wl, n):
         ref.close()
 
 
-@pytest.mark.parametrize("args", [["30011"], ["20000", "barlow"]])
+@pytest.mark.parametrize("args", [["30011"], ["20000", "barlow"], ["30011", "poisson", "3"], ["9000", "barlow", "8"]])
 def test_sample_handler_adapter_runs_the_fitters_call_surface(args):
     """adapters/SampleHandlerB200.h compiled against the mock MaCh3 (tests/adapters/mock_mach3.h): a C++
     program calls Reweight()/GetLikelihood()/GetSampleLikelihood() through SampleHandlerBase pointers on
-    a CPU instance and on the B200 adapter wired from the same EventInfo pointer soup."""
+    a CPU instance and on the B200 adapter wired from the same EventInfo pointer soup.  A third argument n > 1 spreads
+    the sample over n group members (m3b_group_*: one process, one calling thread; devices 0..n-1 modulo the GPUs of
+    the box) -- the 8-GPU step from the single-process boundary."""
     import subprocess
     exe = os.path.join(os.path.dirname(R.adapter_path()), "adapter_test")
     if not os.path.exists(exe):
@@ -54,7 +56,8 @@ def test_sample_handler_adapter_runs_the_fitters_call_surface(args):
 
 
 @pytest.mark.gpu
-def test_adapter_over_the_reference_real_sample_handler_class():
+@pytest.mark.parametrize("n_members", [1, 2])
+def test_adapter_over_the_reference_real_sample_handler_class(n_members):
     """adapters/SampleHandlerB200.h instantiated over the reference's REAL SampleHandlerFD (compiled from
     /root/reference, oracle/ref_host) and linked with libm3b200: after MoveToB200() the fitters' calls --
     Reweight(), GetLikelihood(), GetSampleLikelihood() -- run on the B200 and return what the reference's own CPU
@@ -84,7 +87,8 @@ def test_adapter_over_the_reference_real_sample_handler_class():
         np.testing.assert_array_equal(fd.hist()[0], gold[f"{tag}/mc"][0])
         fd.set_data(gold[f"{tag}/data"])
         # ... then the same object moves to the B200 and replays the chain from its first step
-        fd.move_to_b200(0)
+        import torch
+        fd.move_to_b200(0 if n_members == 1 else [i % torch.cuda.device_count() for i in range(n_members)])
         for t in range(8):                                   # (steps 8+ shift the kinematics: not supported by the adapter)
             pool = np.concatenate([f["osc"][t], f["static_w"]]).astype(np.float64)
             fd.reweight(f["pars"][t], f["norm"][t], pool)
@@ -95,6 +99,45 @@ def test_adapter_over_the_reference_real_sample_handler_class():
             np.testing.assert_allclose(mc, gold[f"{tag}/mc"][t], rtol=1e-12, atol=1e-13)
             np.testing.assert_allclose(w2, gold[f"{tag}/w2"][t], rtol=1e-12, atol=1e-13)
         fd.close()
+
+
+@pytest.mark.gpu
+def test_adapter_binned_arm_over_the_reference_real_classes():
+    """The binned arm of SetSplinePointers (Samples/SampleHandlerFD.cpp:1196-1242): the reference's REAL
+    BinnedSplineHandler + SampleHandlerFD (float build) wired by the reference's harness; MoveToB200 turns every
+    `&weightvec_Monolith[slot]` pointer into a slot index and the step runs on the B200 (binned_eval_kernel +
+    binned_fill_kernel).  -lnL and histograms against the reference's own CPU results (tests/golden/ref_host_fd.npz)."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import refpath_cases as RC
+    from mach3_b200.synth import binned as B
+    from oracle import ref_path_binding as RP
+    if not RP.available_b200():
+        pytest.skip("oracle/_ref/libm3ref_path_lm_b200.so not built (needs /root/reference at build time)")
+    gold = np.load(os.path.join(here, "golden", "ref_host_fd.npz"))
+    tag = "binned_float"
+    w = RC.binned_workload()
+    spl, ev = B.make_binned_splines(w), B.make_binned_events(w)
+    E = w.n_events
+    fd = RP.RefSampleHandlerFD(B.bin_edges(w), 1, True, build="float_b200")
+    fd.attach_binned(spl)
+    idx = np.arange(E, dtype=np.int32)
+    fd.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, w_before=idx,
+                  w_after=E + idx, n_pool=2 * E, binned_n_per_event=ev["n_per_event"], binned_slot=ev["spline_index"])
+    fd.set_data(gold[f"{tag}/data"])
+    fd.move_to_b200(0)
+    for i, step in enumerate(RC.BINNED_STEPS):
+        sp, nm = B.proposal(w, step)
+        pool = np.concatenate([B.make_osc(w, max(step, 0)), ev["static_w"]]).astype(np.float64)
+        fd.reweight(sp, nm, pool)
+        assert fd.llh() == pytest.approx(float(gold[f"{tag}/llh"][i]), rel=1e-10), step
+        fd.sync_host_arrays()
+        mc, w2 = fd.hist()
+        np.testing.assert_allclose(mc, gold[f"{tag}/mc"][i], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(w2, gold[f"{tag}/w2"][i], rtol=1e-12, atol=1e-13)
+    fd.close()
 
 
 @pytest.mark.gpu
