@@ -346,6 +346,41 @@ class SampleHandlerB200 : public FDBase {
     host_arrays_stale_ = false;
   }
 
+  // ---- batched proposals (m3b_step_batch: ONE pass over the coefficient rows for up to 256 parameter sets) ----------
+  // The caller moves the parameters to proposal j exactly as it would before Reweight() (cov->SetParProp, ThrowParameters,
+  // ProposeStep ...) and calls CaptureProposal(): the values behind this sample's spline and normalisation pointers are
+  // recorded, nothing is evaluated.  EvaluateCaptured() then returns -lnL of every captured proposal -- the same numbers,
+  // in the same order, as Reweight() + GetLikelihood() called proposal by proposal (sequential semantics: cached spline
+  // segments, frozen W2).  The oscillation weights are those of the last Reweight().  adapters/BatchFitters.h builds
+  // RunLLHScan, the PredictiveThrower toy loop and DelayedMR2T2's stages on these three calls.
+  void BeginBatch() { batch_sp_.clear(); batch_nm_.clear(); batch_n_ = 0; }
+  void CaptureProposal() {
+    for (const double* p : spline_ptrs_) batch_sp_.push_back(*p);
+    batch_nm_.insert(batch_nm_.end(), bases_.norm_base, bases_.norm_base + bases_.n_norm);
+    ++batch_n_;
+  }
+  int CapturedProposals() const { return batch_n_; }
+  // llh[n]; per_sample (optional) [n * GetNsamples()]; mc (optional) [n * n_bins]: every proposal's MC histogram
+  std::vector<double> EvaluateCaptured(std::vector<double>* per_sample = nullptr, std::vector<double>* mc = nullptr) {
+    if (!ready_) throw std::runtime_error("SampleHandlerB200::EvaluateCaptured: call MoveToB200 first");
+    if (g_) throw std::runtime_error("SampleHandlerB200::EvaluateCaptured: batched proposals run on one device (MoveToB200 with a single device)");
+    std::vector<double> llh(static_cast<size_t>(batch_n_), 0.0);
+    if (batch_n_ == 0) return llh;
+    const int nS = static_cast<int>(this->GetNsamples());
+    if (per_sample) per_sample->assign(static_cast<size_t>(batch_n_) * nS, 0.0);
+    const double* sp = batch_sp_.empty() ? nullptr : batch_sp_.data();
+    const double* nm = batch_nm_.empty() ? nullptr : batch_nm_.data();
+    if (mc) {
+      mc->assign(static_cast<size_t>(batch_n_) * n_bins_, 0.0);
+      check(m3b_step_batch_hist(h_, batch_n_, sp, nm, nullptr, llh.data(), per_sample ? per_sample->data() : nullptr, mc->data()), "m3b_step_batch_hist");
+    } else {
+      check(m3b_step_batch(h_, batch_n_, sp, nm, nullptr, llh.data(), per_sample ? per_sample->data() : nullptr), "m3b_step_batch");
+    }
+    host_arrays_stale_ = true;
+    BeginBatch();
+    return llh;
+  }
+
   m3b_handle* handle() const { return h_; }         // the (lead) device handle
   m3b_group* group() const { return g_; }           // non-null when the sample is spread over several devices
   bool OscillatorArrayRegistered() const { return osc_registered_; }
@@ -365,6 +400,8 @@ class SampleHandlerB200 : public FDBase {
   PointerBases bases_{};
   std::vector<const double*> spline_ptrs_;
   std::vector<double> spline_vals_;
+  std::vector<double> batch_sp_, batch_nm_;     // captured proposals, row-major
+  int batch_n_ = 0;
   float* osc_stage_ = nullptr;             // pinned staging copy (only when the oscillator's array could not be registered)
 };
 

@@ -110,6 +110,25 @@ M3B_API int m3b_upload_spline_monolith(m3b_handle* h, int32_t n_params, int32_t 
                                        const uint32_t* nParamPerEvent_tf1, const int16_t* paramNo_tf1,
                                        const float* coeff_tf1);
 
+/* ---- the monolith on disk, without ROOT -----------------------------------------------------------------------
+ * The reference caches a built SMonolith in a ROOT file (SMonolith::PrepareSplineFile / LoadSplineFile,
+ * Splines/SplineMonolith.cpp:454-614; FastSplineInfo directory, Splines/SplineBase.cpp:139-191).  The same arrays as ONE
+ * flat little-endian file ("M3BMONO1": header with the scalars of the "Settings" tree, then named, 64-byte aligned
+ * sections carrying the reference's member names -- layout in mach3_b200/csrc/m3b_file.cu):
+ * m3b_write_monolith_file   the writer a MaCh3 maintainer calls next to PrepareSplineFile (adapters/M3BMonolithFile.h);
+ *                           x_pts_f64 (FastSplineInfo::xPts as doubles, rows padded to max_knots) may be NULL; needs no GPU
+ * m3b_monolith_file_info    the header scalars (needs no GPU)
+ * m3b_upload_from_file      = LoadSplineFile + MoveToGPU: streams the file to the device in chunks of chunk_events events
+ *                           (0 = 131072) so host memory stays bounded however large the monolith is
+ * m3b_group_upload_from_file every member of a single-process group reads its own event range                        */
+M3B_API int m3b_write_monolith_file(const char* path, int32_t n_params, int32_t max_knots, const float* coeff_x,
+                                    const int16_t* n_pts, const double* x_pts_f64, int64_t n_events,
+                                    const uint32_t* nParamPerEvent, const int16_t* paramNo_arr, const uint32_t* nKnots_arr,
+                                    uint32_t total_knots, const float* coeff_many, const uint32_t* nParamPerEvent_tf1,
+                                    const int16_t* paramNo_tf1, const float* coeff_tf1);
+M3B_API int m3b_monolith_file_info(const char* path, int64_t* n_events, int32_t* n_params, int32_t* max_knots, uint64_t* total_knots);
+M3B_API int m3b_upload_from_file(m3b_handle* h, const char* path, int64_t chunk_events);
+
 /* FastSplineInfo::xPts in the default build's M3::float_t = double (Splines/SplineStructs.h:21-44).  The monolith
  * arrays only carry the knots as floats (coeff_x); SplineBase::FindSplineSegment (Splines/SplineBase.cpp:44-111)
  * compares the float-narrowed parameter against xPts, which hold the splines' double knots when SMonolith was
@@ -322,6 +341,7 @@ M3B_API int m3b_group_upload_spline_monolith(m3b_group* g, int32_t n_params, int
                                              const int16_t* paramNo_arr, const uint32_t* nKnots_arr, uint32_t total_knots,
                                              const float* coeff_many, const uint32_t* nParamPerEvent_tf1,
                                              const int16_t* paramNo_tf1, const float* coeff_tf1);
+M3B_API int m3b_group_upload_from_file(m3b_group* g, const char* path, int64_t chunk_events);
 M3B_API int m3b_group_upload_binning_ex(m3b_group* g, int32_t n_samples, const int32_t* n_dim, const int32_t* uniform,
                                         const int32_t* nbins, const double* edges);
 M3B_API int m3b_group_upload_events(m3b_group* g, int64_t n_events, const int32_t* sample_id, const double* kin,

@@ -34,6 +34,7 @@ EXPORTS = (
     "m3b_group_upload_spline_monolith", "m3b_group_upload_binning_ex", "m3b_group_upload_events", "m3b_group_upload_selection",
     "m3b_group_upload_data", "m3b_group_upload_osc", "m3b_group_connect", "m3b_group_alloc_host", "m3b_group_step",
     "m3b_group_llh", "m3b_group_read_hist", "m3b_group_synchronize",
+    "m3b_write_monolith_file", "m3b_monolith_file_info", "m3b_upload_from_file", "m3b_group_upload_from_file",
 )
 EXCHANGE_PEER, EXCHANGE_NCCL = 0, 1
 
@@ -118,6 +119,31 @@ def _c(a, dtype):
     return None if a is None else np.ascontiguousarray(a, dtype)
 
 
+def write_monolith_file(path, n_params, max_knots, coeff_x, n_pts, spl, x_pts_f64=None):
+    """The ROOT-free spline-monolith cache file (m3b_write_monolith_file); needs no GPU."""
+    L = load()
+    cx, npt = _c(coeff_x, np.float32), _c(n_pts, np.int16)
+    xp = _c(x_pts_f64, np.float64)
+    a = [_c(spl["nParamPerEvent"], np.uint32), _c(spl["paramNo_arr"], np.int16), _c(spl["nKnots_arr"], np.uint32),
+         _c(spl["coeff_many"], np.float32), _c(spl["nParamPerEvent_tf1"], np.uint32),
+         _c(spl["paramNo_tf1"], np.int16), _c(spl["coeff_tf1"], np.float32)]
+    rc = L.m3b_write_monolith_file(os.fsencode(path), C.c_int32(n_params), C.c_int32(max_knots), _p(cx), _p(npt), _p(xp),
+                                   C.c_int64(a[0].size // 2), _p(a[0]), _p(a[1]), _p(a[2]), C.c_uint32(a[3].size // 4), _p(a[3]),
+                                   _p(a[4]), _p(a[5]), _p(a[6]))
+    if rc != OK:
+        raise M3BError(rc, (L.m3b_last_error(None) or b"").decode())
+
+
+def monolith_file_info(path):
+    """-> dict(n_events, n_params, max_knots, total_knots) of an M3BMONO1 file; needs no GPU."""
+    L = load()
+    ne, npar, mk, tk = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.c_uint64(0)
+    rc = L.m3b_monolith_file_info(os.fsencode(path), C.byref(ne), C.byref(npar), C.byref(mk), C.byref(tk))
+    if rc != OK:
+        raise M3BError(rc, (L.m3b_last_error(None) or b"").decode())
+    return dict(n_events=ne.value, n_params=npar.value, max_knots=mk.value, total_knots=tk.value)
+
+
 class Handle:
     """One device context = one sample handler + its spline monolith."""
 
@@ -197,6 +223,11 @@ class Handle:
         self._ck(self.L.m3b_upload_spline_monolith(
             self.h, C.c_int32(n_params), C.c_int32(max_knots), _p(cx), _p(npt), C.c_int64(a[0].size // 2),
             _p(a[0]), _p(a[1]), _p(a[2]), C.c_uint32(a[3].size // 4), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6])))
+
+    def upload_from_file(self, path, chunk_events=0):
+        """SMonolith::LoadSplineFile + MoveToGPU from the ROOT-free cache file, streamed in chunks."""
+        self._ck(self.L.m3b_upload_from_file(self.h, os.fsencode(path), C.c_int64(chunk_events)))
+        self.n_params = monolith_file_info(path)["n_params"]
 
     # ---- binning / events / data
     def upload_binned_splines(self, spl, f64=False):
@@ -521,6 +552,11 @@ class Group:
             _p(a[0]), _p(a[1]), _p(a[2]), C.c_uint32(a[3].size // 4), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6])))
         for m in self._members:
             m.n_params = int(n_params)
+
+    def upload_from_file(self, path, chunk_events=0):
+        self._ck(self.L.m3b_group_upload_from_file(self.g, os.fsencode(path), C.c_int64(chunk_events)))
+        for m in self._members:
+            m.n_params = monolith_file_info(path)["n_params"]
 
     def upload_binning(self, edges):
         for m in self._members:
