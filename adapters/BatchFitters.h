@@ -93,7 +93,8 @@ std::vector<std::vector<double>> ThrowToysBatched(const std::vector<Sample*>& sa
 //                       previous rejected one).
 //   prior_llh(i)        sum of systematics[s]->GetLikelihood() for stage i's proposal (host; captured by the caller when
 //                       proposing)
-//   accept(p), delay()  IsStepAccepted(accProb) and ProbabilisticDelay() -- the reference's own random draws.
+//   accept(i, p), delay(i)  IsStepAccepted(accProb) and "go on delaying" (= !ProbabilisticDelay()'s break, :148-150) for
+//                       stage i -- the reference's own random draws.
 // RNG order: all proposals are drawn before the first accept/delay draw, whereas the reference interleaves them stage by
 // stage: the chain is statistically equivalent to, not draw-for-draw identical with, the reference's.
 struct DelayedResult {
@@ -107,7 +108,7 @@ struct DelayedResult {
 template <class Sample>
 DelayedResult DelayedStagesBatched(const std::vector<Sample*>& samples, int max_rejections, double logLCurr,
                                    const std::function<bool(int, bool)>& propose, const std::function<double(int)>& prior_llh,
-                                   const std::function<bool(double)>& accept, const std::function<bool()>& delay,
+                                   const std::function<bool(int, double)>& accept, const std::function<bool(int)>& delay,
                                    bool delay_on_oob_only = false, double large_logl = 1234567890.0) {
   const int n = max_rejections + 1;
   std::vector<char> oob(n, 0);
@@ -146,9 +147,9 @@ DelayedResult DelayedStagesBatched(const std::vector<Sample*>& samples, int max_
       else accProb = std::min(num / den, 1.0);
       is_delayed = true;
     }
-    if (accept(accProb)) { r.accepted_stage = i; r.accepted_delayed = is_delayed; break; }
+    if (accept(i, accProb)) { r.accepted_stage = i; r.accepted_delayed = is_delayed; break; }
     if (delay_on_oob_only) break;                       // :141-145 (not out of bounds here)
-    if (!delay()) break;                                // :148-150
+    if (!delay(i)) break;                               // :148-150
     MinLogLikelihood = logLProp;                        // :153
   }
   return r;

@@ -9,6 +9,7 @@
 // (Oscillator->Evaluate() + Reweight() + GetLikelihood(), host wall clock) for the registered-array and the staging route.
 #include "mock_mach3.h"
 #include "SampleHandlerB200.h"
+#include "BatchFitters.h"
 #include "m3b_synth.h"
 
 #include <chrono>
@@ -91,6 +92,7 @@ class ExperimentFD : public SampleHandlerFD {
     return var == 7 ? cut_only[size_t(e)] : kin[size_t(var) * nEvents + size_t(e)];
   }
   void SetData(const std::vector<double>& d) { SampleHandlerFD_data = d; }
+  void FreezeOscillator() { Oscillator->per_step.clear(); }
   const std::vector<double>& MC() const { return SampleHandlerFD_array; }
   const std::vector<double>& W2() const { return SampleHandlerFD_array_w2; }
   m3b200::MonolithArrays Arrays() const {
@@ -116,6 +118,122 @@ class ExperimentFD : public SampleHandlerFD {
   std::vector<int32_t> sample_id; std::vector<double> kin, cut_only; std::vector<int16_t> norm_idx; std::vector<float> static_w;
   template <class T> friend class m3b200::SampleHandlerB200;
 };
+
+// adapters/BatchFitters.h against the reference's sequential loops run on the mock's CPU path: FitterBase::RunLLHScan's
+// inner loop (Fitters/FitterBase.cpp:742-798), PredictiveThrower's toy loop (Fitters/PredictiveThrower.cpp:507-563) and
+// DelayedMR2T2::DoStep (Fitters/DelayedMR2T2.cpp:110-157) with the same pre-drawn proposals and accept/delay draws.
+static bool batch_consumers(Workload& w, ExperimentFD& cpu, m3b200::SampleHandlerB200<ExperimentFD>& gpu) {
+  using B200 = m3b200::SampleHandlerB200<ExperimentFD>;
+  const m3s_config& c = w.c;
+  bool ok = true;
+  // a batch is evaluated with the oscillation weights of the last Reweight(): hold the oscillator still on both sides
+  cpu.FreezeOscillator(); gpu.FreezeOscillator();
+  std::vector<B200*> samples = {&gpu};
+  // ---- RunLLHScan: parameter 3 over 100 points, central values from proposal 2
+  m3s_proposal(&c, 2, w.pars.data(), w.norms.data());
+  const std::vector<double> pars0 = w.pars;
+  const int n_points = 100, ipar = 3;
+  auto point = [&](int j) { w.pars = pars0; w.pars[ipar] = -2.9 + 5.8 * (j + 0.5) / n_points; };
+  std::vector<std::vector<double>> split;
+  const auto scan = m3b200::LLHScanBatched<B200>(samples, n_points, point, &split);
+  double worst = 0, worst_split = 0;
+  for (int j = 0; j < n_points; ++j) {
+    point(j);
+    cpu.Reweight();
+    const double l = cpu.GetLikelihood();
+    worst = std::max(worst, std::fabs(scan[0][j] - l) / std::max(1e-300, std::fabs(l)));
+    double ls = 0;
+    for (int s = 0; s < c.n_samples; ++s) ls += split[0][size_t(j) * c.n_samples + s];
+    worst_split = std::max(worst_split, std::fabs(ls - scan[0][j]) / std::max(1e-300, std::fabs(l)));
+  }
+  printf("LLHScanBatched: %d points, worst rel diff to the sequential loop %.2e, per-sample sums %.1e  %s\n", n_points, worst, worst_split,
+         worst <= 1e-6 && worst_split <= 1e-9 ? "OK" : "FAIL");
+  ok &= worst <= 1e-6 && worst_split <= 1e-9;
+  // ---- PredictiveThrower: 40 toys, each toy's MC histogram and -lnL
+  const int n_toys = 40;
+  auto toy = [&](int i) { m3s_proposal(&c, 100 + i, w.pars.data(), w.norms.data()); };
+  std::vector<std::vector<double>> toy_llh;
+  const auto mc = m3b200::ThrowToysBatched<B200>(samples, n_toys, toy, &toy_llh, 16);
+  const size_t nb = cpu.MC().size();
+  double worst_mc = 0, worst_l = 0;
+  for (int i = 0; i < n_toys; ++i) {
+    toy(i);
+    cpu.Reweight();
+    for (size_t b = 0; b < nb; ++b) worst_mc = std::max(worst_mc, std::fabs(mc[0][size_t(i) * nb + b] - cpu.MC()[b]) / std::max(1.0, std::fabs(cpu.MC()[b])));
+    const double l = cpu.GetLikelihood();
+    worst_l = std::max(worst_l, std::fabs(toy_llh[0][i] - l) / std::max(1e-300, std::fabs(l)));
+  }
+  printf("ThrowToysBatched: %d toys, worst histogram diff %.1e, worst -lnL rel diff %.2e  %s\n", n_toys, worst_mc, worst_l,
+         worst_mc <= 1e-9 && worst_l <= 1e-6 ? "OK" : "FAIL");
+  ok &= worst_mc <= 1e-9 && worst_l <= 1e-6;
+  // ---- DelayedMR2T2::DoStep: 60 steps, 3 allowed rejections, against the reference's loop run stage by stage on the CPU
+  //      instance with the SAME pre-drawn unit proposals, accept draws and delay draws
+  {
+    std::mt19937_64 rng(99);
+    std::normal_distribution<double> gaus(0, 1);
+    std::uniform_real_distribution<double> uni(0, 1);
+    const int max_rej = 3; const double decay_rate = 0.3, large = 1234567890.0, delay_probability = 0.8;
+    int agree = 0, accepted = 0, delayed = 0, redo = 0, n_steps = 60;
+    std::vector<double> curr = pars0;
+    w.pars = curr; cpu.Reweight();
+    double logLCurr = cpu.GetLikelihood();
+    double worst_stage = 0;
+    for (int step = 0; step < n_steps; ++step) {
+      std::vector<std::vector<double>> unit(max_rej + 1, std::vector<double>(curr.size()));
+      std::vector<double> u_acc(max_rej + 1), u_del(max_rej + 1);
+      for (int i = 0; i <= max_rej; ++i) { for (double& x : unit[i]) x = gaus(rng); u_acc[i] = uni(rng); u_del[i] = uni(rng); }
+      // the proposal rule both runs share: centred on the previous stage's proposal (the AcceptStep "leapfrog",
+      // :124-127), scale multiplied by decay_rate when the previous stage was evaluated and rejected (:152)
+      std::vector<double> centre; double scale = 0; std::vector<std::vector<double>> props(max_rej + 1);
+      auto propose = [&](int i, bool decay) {
+        if (i == 0) { centre = curr; scale = 0.12; }
+        if (decay) scale *= decay_rate;
+        std::vector<double> p(curr.size());
+        bool oob = false;
+        for (size_t k = 0; k < p.size(); ++k) { p[k] = centre[k] + scale * unit[i][k]; oob |= std::fabs(p[k]) > 2.9; }
+        centre = p; props[i] = p; w.pars = p;
+        return oob;
+      };
+      // (1) the reference's loop, stage by stage, on the CPU instance
+      int acc_ref = -1; double MinLL = large, ll_ref = 0; bool decay = false;
+      std::vector<double> llh_ref(max_rej + 1, 0.0);
+      for (int i = 0; i <= max_rej; ++i) {
+        const bool oob = propose(i, decay);
+        decay = false;
+        double logLProp = large;
+        if (!oob) { cpu.Reweight(); logLProp = cpu.GetLikelihood(); llh_ref[i] = logLProp; }
+        if (oob || logLProp > MinLL) continue;
+        double accProb;
+        if (i == 0) accProb = std::min(1.0, std::exp(logLCurr - logLProp));
+        else {
+          const double num = std::max(0.0, std::exp(MinLL - logLProp) - 1.0), den = std::exp(MinLL - logLCurr) - 1.0;
+          accProb = den <= 0.0 ? 1.0 : ((std::isinf(num) || std::isinf(den)) ? std::min(1.0, std::exp(logLCurr - logLProp)) : std::min(num / den, 1.0));
+        }
+        if (!(u_acc[i] > accProb)) { acc_ref = i; ll_ref = logLProp; break; }       // MCMCBase::IsStepAccepted
+        if (u_del[i] > delay_probability) break;                                      // ProbabilisticDelay() == false: stop delaying
+        decay = true; MinLL = logLProp;
+      }
+      const std::vector<std::vector<double>> props_ref = props;
+      // (2) the batched form: all stages proposed first, one device pass, then the same decisions
+      const auto r = m3b200::DelayedStagesBatched<B200>(samples, max_rej, logLCurr, propose, [](int) { return 0.0; },
+                                                        [&](int i, double pacc) { return !(u_acc[i] > pacc); },
+                                                        [&](int i) { return !(u_del[i] > delay_probability); });
+      if (r.redo_from >= 0) { ++redo; }            // (the sequential re-proposal of the tail is the caller's: count, do not compare)
+      else {
+        agree += (r.accepted_stage == acc_ref);
+        for (int i = 0; i < r.stages_used; ++i)
+          if (llh_ref[i] != 0.0 && props[i] == props_ref[i])
+            worst_stage = std::max(worst_stage, std::fabs(r.stage_llh[i] - llh_ref[i]) / std::max(1e-300, std::fabs(llh_ref[i])));
+      }
+      if (acc_ref >= 0) { curr = props_ref[acc_ref]; logLCurr = ll_ref; ++accepted; delayed += acc_ref > 0; }
+    }
+    const bool good = agree + redo == n_steps && worst_stage <= 1e-6 && accepted > 0;
+    printf("DelayedStagesBatched: %d steps, %d accepted (%d after a delay), decisions agree with the stage-by-stage loop in %d, "
+           "%d needed a sequential tail, worst stage -lnL rel diff %.2e  %s\n", n_steps, accepted, delayed, agree, redo, worst_stage, good ? "OK" : "FAIL");
+    ok &= good;
+  }
+  return ok;
+}
 
 int main(int argc, char** argv) {
   const int64_t E = argc > 1 ? atoll(argv[1]) : 30011;
@@ -168,6 +286,7 @@ int main(int argc, char** argv) {
     printf("step %2d: -lnL cpu %.9f  b200 %.9f  rel %.2e  hist %.1e  w2 %.1e  sum(per-sample) %.9f  %s\n", step, l[0], l[1], rel, dmax, dw2, ls,
            good ? "OK" : "FAIL");
   }
+  if (argc > 4 && !strcmp(argv[4], "batch")) ok &= batch_consumers(w, cpu, gpu);
   if (timing) {
     // the adapter's real step cost, as a fitter pays it: Reweight() (incl. Oscillator->Evaluate()) + GetLikelihood()
     for (int route = 0; route < 2; ++route) {

@@ -40,13 +40,16 @@ def test_smonolithgpu_adapter_is_a_drop_in(wl, n):
         ref.close()
 
 
-@pytest.mark.parametrize("args", [["30011"], ["20000", "barlow"], ["30011", "poisson", "3"], ["9000", "barlow", "8"]])
+@pytest.mark.parametrize("args", [["30011"], ["20000", "barlow"], ["30011", "poisson", "3"], ["9000", "barlow", "8"],
+                                  ["20000", "poisson", "1", "batch"], ["8000", "barlow", "1", "batch"]])
 def test_sample_handler_adapter_runs_the_fitters_call_surface(args):
     """adapters/SampleHandlerB200.h compiled against the mock MaCh3 (tests/adapters/mock_mach3.h): a C++
     program calls Reweight()/GetLikelihood()/GetSampleLikelihood() through SampleHandlerBase pointers on
     a CPU instance and on the B200 adapter wired from the same EventInfo pointer soup.  A third argument n > 1 spreads
     the sample over n group members (m3b_group_*: one process, one calling thread; devices 0..n-1 modulo the GPUs of
-    the box) -- the 8-GPU step from the single-process boundary."""
+    the box) -- the 8-GPU step from the single-process boundary.  "batch": adapters/BatchFitters.h (RunLLHScan,
+    PredictiveThrower's toy loop, DelayedMR2T2's stages on m3b_step_batch) against the sequential loops on the CPU
+    instance."""
     import subprocess
     exe = os.path.join(os.path.dirname(R.adapter_path()), "adapter_test")
     if not os.path.exists(exe):
