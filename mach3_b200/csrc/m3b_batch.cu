@@ -256,6 +256,10 @@ int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, cons
   *done = 0;
   if (h->binned || !h->splines_done || h->first_time_w2 || h->cfg.update_w2 || n_sets > kBSets || h->T % kBT != 0) return M3B_OK;
   if (h->cfg.flags & M3B_FLAG_NO_BATCH_KERNEL) return M3B_OK;
+  if (!(h->cfg.flags & M3B_FLAG_BATCH_KERNEL_V1)) {      // the second-generation kernel first (m3b_batch2.cuh)
+    const int rc2 = m3b_batch2_try(h, n_sets, spline_pars, norm_pars, osc_w, host_slots_dev, done);
+    if (rc2 != M3B_OK || *done) return rc2;
+  }
   if (h->tiles_dirty || !h->d_tiles) return M3B_OK;     // first step has not run yet
   CK(cudaSetDevice(h->device));
   if (h->Kmax > 64) return M3B_OK;
@@ -328,8 +332,10 @@ int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, cons
   auto grow = [&](void** p, size_t& cap, size_t bytes) -> cudaError_t {
     if (cap >= bytes && *p) return cudaSuccess;
     if (*p) cudaFree(*p);
-    cap = bytes + bytes / 4 + 256;
-    return cudaMalloc(p, cap);
+    *p = nullptr; cap = 0;
+    const cudaError_t e = cudaMalloc(p, bytes + bytes / 4 + 256);
+    if (e == cudaSuccess) cap = bytes + bytes / 4 + 256;
+    return e;
   };
   const size_t slot = static_cast<size_t>(1 + h->n_samples);
   CK(grow(&h->bt_dx, h->bt_dx_cap, t_dx.size() * 4 + 16));
@@ -388,3 +394,5 @@ int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, cons
   *done = 1;
   return M3B_OK;
 }
+
+#include "m3b_batch2.cuh"

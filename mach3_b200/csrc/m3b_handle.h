@@ -15,6 +15,8 @@ using namespace m3b;
 
 int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars, const float* osc_w,
                   double* host_slots_dev, int* done);      // m3b_batch.cu
+int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, const double* norm_pars, const float* osc_w,
+                   double* host_slots_dev, int* done);     // m3b_batch2.cuh (same translation unit)
 std::string& m3b_last_error_slot();     // thread-local last error (defined in m3b_api.cu)
 int m3b_peer_alloc(m3b_handle* h);      // the exported partial-histogram buffers + epoch flag of the peer exchange (m3b_api.cu)
 
@@ -164,9 +166,9 @@ struct m3b_handle {
   double* llh_host_override = nullptr;
   // staging of the batched kernel (m3b_batch.cu), grown on demand
   void *bt_dx = nullptr, *bt_rowoff = nullptr, *bt_val = nullptr, *bt_rowlist = nullptr, *bt_norm = nullptr, *bt_sigs = nullptr,
-       *bt_hist = nullptr, *bt_llh = nullptr, *bt_slot = nullptr;
+       *bt_hist = nullptr, *bt_llh = nullptr, *bt_slot = nullptr, *bt_group = nullptr;
   size_t bt_dx_cap = 0, bt_rowoff_cap = 0, bt_val_cap = 0, bt_rowlist_cap = 0, bt_norm_cap = 0, bt_sigs_cap = 0, bt_hist_cap = 0,
-         bt_llh_cap = 0, bt_slot_cap = 0;
+         bt_llh_cap = 0, bt_slot_cap = 0, bt_group_cap = 0;
 
   uint64_t steps = 0, launches = 0;
 

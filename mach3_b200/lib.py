@@ -16,6 +16,7 @@ FLAG_KEEP_EVENT_WEIGHTS = 1
 FLAG_KEEP_KINEMATICS = 2
 FLAG_NO_FUSED_LLH = 4
 FLAG_NO_BATCH_KERNEL = 8
+FLAG_BATCH_KERNEL_V1 = 16
 
 #: every symbol include/m3b200.h declares
 EXPORTS = (

@@ -1,0 +1,11 @@
+#!/bin/bash
+# keeps asking for a GPU slot until the call is actually served (exit code 3 = pod busy, nothing charged)
+# usage: scripts/gpurun_retry.sh <timeout_s> <command...>
+T=$1; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout $T -- "$@"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3
