@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(256) binned_fill_kernel(const __grid_constant_
 
   for (int64_t wt = static_cast<int64_t>(blockIdx.x) * 8 + warp; wt < a.n_wtiles; wt += static_cast<int64_t>(gridDim.x) * 8) {
     const WTile d = a.wtiles[wt];
-    const int64_t e = wt * 32 + lane;
+    // events are processed in the order of their spline-grid cell (a.perm, built at upload): the 32 lanes of a warp --
+    // and the 8 warps of the block -- then gather from the same few sectors of every parameter's weight row
+    const int64_t e = a.perm ? static_cast<int64_t>(a.perm[wt * 32 + lane]) : wt * 32 + lane;
     const int bin = a.bin[e];
     R w_osc = 1, w_static = 1;
     if (oscp) {
@@ -270,6 +272,7 @@ static int upload_binned_impl(m3b_handle* h, int32_t n_params, int32_t max_knots
   CK(dev_upload(h, &h->d_btiles, tiles));
   h->n_btiles = static_cast<int32_t>(tiles.size());
   h->b_n_slots = n_slots; h->b_n_act = n_unique; h->b_n_act_pad = n_act_pad;
+  h->b_out_base = out_base; h->b_count.assign(count.begin() + 1, count.end());
   h->binned = true;
   h->launch_ready = false;
   return M3B_OK;
@@ -302,37 +305,55 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
   CK(cudaSetDevice(h->device));
   const int64_t n_wt = h->e_pad / 32;
   std::vector<WTile> wt(static_cast<size_t>(n_wt));
-  // first pass: non-flat pointers per event, ELL width per 32 events
+  // first pass: non-flat pointers per event, and where in its parameter's weight row the event's first one sits
   std::vector<uint32_t> keep(static_cast<size_t>(n_events), 0);
+  std::vector<uint64_t> first(static_cast<size_t>(n_events) + 1, 0);
+  std::vector<float> cell(static_cast<size_t>(n_events), 2.f);      // position of the event's spline-grid cell, 0..1 (2: no non-flat pointer)
   uint64_t off = 0;
   for (int64_t e = 0; e < n_events; ++e) {
     uint32_t k = 0;
+    first[e] = off;
     for (uint32_t j = 0; j < n_per_event[e]; ++j) {
       const int32_t s = spline_index[off + j];
       REQUIRE(s >= 0 && s < h->b_n_slots, M3B_ERR_INVALID, "m3b_upload_event_binned_splines: spline_index out of range");
-      if (h->b_slot2compact[s] >= 0) ++k;        // flat splines hold exactly 1.0f: multiplying by them changes nothing
+      const int32_t c = h->b_slot2compact[s];
+      if (c < 0) continue;                       // flat splines hold exactly 1.0f: multiplying by them changes nothing
+      if (k == 0) {
+        // compact indices are grouped by parameter and ascend with the slot inside a parameter, i.e. with the spline-grid
+        // cell (Splines/BinnedSplineHandler.h:110: [..][syst][mode][var1][var2][var3]); the rank inside the parameter's
+        // row, as a fraction, is comparable between events whose first non-flat pointer belongs to different parameters
+        const int p = h->b_param_of_compact_row(c);
+        cell[e] = static_cast<float>(static_cast<double>(c - h->b_out_base[p]) / static_cast<double>(std::max<int64_t>(1, h->b_count[p])));
+      }
+      ++k;
     }
     keep[e] = k;
     off += n_per_event[e];
   }
+  first[n_events] = off;
+  // processing order: events sorted by cell (stable).  Only the ORDER in which the fill kernel walks the events changes;
+  // every per-event array stays indexed by the caller's event number.
+  std::vector<int32_t> perm(static_cast<size_t>(h->e_pad));
+  for (int64_t e = 0; e < h->e_pad; ++e) perm[e] = static_cast<int32_t>(e);
+  std::stable_sort(perm.begin(), perm.begin() + n_events, [&](int32_t x, int32_t y) { return cell[x] < cell[y]; });
   int64_t total = 0;
   for (int64_t t = 0; t < n_wt; ++t) {
     uint32_t mx = 0;
-    for (int64_t e = t * 32; e < std::min<int64_t>(n_events, t * 32 + 32); ++e) mx = std::max(mx, keep[e]);
+    for (int64_t v = t * 32; v < std::min<int64_t>(n_events, t * 32 + 32); ++v) mx = std::max(mx, keep[perm[v]]);
     wt[t].off = total; wt[t].max_n = static_cast<int32_t>(mx); wt[t].pad = 0;
     total += static_cast<int64_t>(mx) * 32;
   }
   std::vector<int32_t> ell(static_cast<size_t>(std::max<int64_t>(total, 1)), -1);
-  off = 0;
-  for (int64_t e = 0; e < n_events; ++e) {
-    const WTile& d = wt[e / 32];
+  for (int64_t v = 0; v < n_events; ++v) {
+    const int64_t e = perm[v];
+    const WTile& d = wt[v / 32];
     int64_t k = 0;
-    for (uint32_t j = 0; j < n_per_event[e]; ++j) {
-      const int32_t c = h->b_slot2compact[spline_index[off + j]];
-      if (c >= 0) ell[d.off + (k++) * 32 + (e & 31)] = c;       // pointer order kept: the product is sequential
+    for (uint64_t j = first[e]; j < first[e + 1]; ++j) {
+      const int32_t c = h->b_slot2compact[spline_index[j]];
+      if (c >= 0) ell[d.off + (k++) * 32 + (v & 31)] = c;       // pointer order kept: the product is sequential
     }
-    off += n_per_event[e];
   }
+  CK(dev_upload(h, &h->d_perm, perm));
   if (h->f64) {
     // default build: osc / static weights and the per-event outputs are M3::float_t = double.  Until the caller
     // supplies doubles (m3b_upload_event_weights_f64 / m3b_upload_osc_f64) the float uploads are widened (exact).

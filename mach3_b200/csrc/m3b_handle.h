@@ -156,6 +156,11 @@ struct m3b_handle {
   int64_t b_n_slots = 0, b_n_act = 0, b_n_act_pad = 0, n_wtiles = 0;
   int32_t n_btiles = 0;
   std::vector<int32_t> b_slot2compact, b_compact2slot;
+  std::vector<int64_t> b_out_base, b_count;      // per parameter: first compact index of its (padded) weight row / non-flat splines in it
+  int b_param_of_compact_row(int64_t c) const {  // parameter whose weight row holds compact index c
+    return static_cast<int>(std::upper_bound(b_out_base.begin(), b_out_base.end(), c) - b_out_base.begin()) - 1;
+  }
+  int32_t* d_perm = nullptr;                     // order in which the binned fill kernel walks the events (sorted by spline-grid cell)
   float4* d_bcoef = nullptr; float* d_bx = nullptr; float* d_bw = nullptr;
   BTile* d_btiles = nullptr; WTile* d_wtiles = nullptr; int32_t* d_ell = nullptr;
   uint64_t b_gather_per_step = 0;

@@ -150,6 +150,7 @@ struct FillArgs {
   const double* osc_d; const double* static_d;
   double* evt_spline_d; double* evt_total_d;
   const int32_t* ell; const WTile* wtiles; int64_t n_wtiles;
+  const int32_t* perm;         // binned fill: event handled by (warp tile, lane), nullptr = identity
   // optional per-block timeline (m3b_block_trace): 8 x u64 globaltimer ns per block
   unsigned long long* trace;
   alignas(16) unsigned char step_inline[kStepInlineMax];
