@@ -48,7 +48,9 @@ typedef enum {
                          /* identical knots per parameter, Splines/SplineMonolith.cpp:102-104)     */
   M3B_ERR_NOMEM = 5,
   M3B_ERR_NODEVICE = 6,  /* no sm_100 device: the product path has no CPU fallback                 */
-  M3B_ERR_PEER = 7       /* peer (multi-GPU) exchange failed or timed out                          */
+  M3B_ERR_PEER = 7,      /* peer (multi-GPU) exchange failed or timed out                          */
+  M3B_ERR_MATH = 8       /* a test statistic hit a case in which the reference throws MaCh3Exception  */
+                         /* (Barlow-Beeston negative discriminant, Samples/SampleHandlerBase.cpp:64-67) */
 } m3b_status;
 
 /* Samples/SampleStructs.h:105-112 (same numeric values as enum TestStatistic) */

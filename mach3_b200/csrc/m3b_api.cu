@@ -999,7 +999,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     static const int guard_env = [] { const char* ge = experiment_env("M3B_GUARD_X2"); return ge && atoi(ge) > 0 ? atoi(ge) : 6; }();
     a.guard_x2 = guard_env;
   }
-  a.ticket = h->d_ticket; a.llh_dev = h->d_llh; a.llh_host = h->llh_host_override ? h->llh_host_override : h->h_llh_dev;
+  a.ticket = h->d_ticket; a.status = h->d_status; a.llh_dev = h->d_llh; a.llh_host = h->llh_host_override ? h->llh_host_override : h->h_llh_dev;
   a.evt_spline_w = h->d_evt_spline_w; a.evt_total_w = h->d_evt_total_w;
   a.trace = h->d_trace;
   if (mode == kFused) {
@@ -1197,6 +1197,15 @@ static int step_batch_impl(m3b_handle* h, int32_t n_sets, const double* spline_p
   h->llh_host_override = nullptr;
   if (rc != M3B_OK) return rc;
   CK(cudaStreamSynchronize(h->stream));
+  bool any_nan = false;
+  for (int32_t i = 0; i < n_sets; ++i) any_nan |= h->h_batch[slot * i] != h->h_batch[slot * i];
+  if (any_nan) {
+    int32_t st = 0;
+    CK(cudaMemcpy(&st, h->d_status, sizeof st, cudaMemcpyDeviceToHost));
+    if (st != 0) CK(cudaMemset(h->d_status, 0, sizeof st));
+    if (st & 2) return fail(h, M3B_ERR_MATH, "m3b_step_batch: negative square root in the Barlow-Beeston coefficient (the reference throws "
+                                             "MaCh3Exception here, Samples/SampleHandlerBase.cpp:64-67)");
+  }
   for (int32_t i = 0; i < n_sets; ++i) {
     llh_total[i] = h->h_batch[slot * i];
     if (llh_per_sample) for (int s = 0; s < h->n_samples; ++s) llh_per_sample[static_cast<size_t>(i) * h->n_samples + s] = h->h_batch[slot * i + 1 + s];
@@ -1259,10 +1268,13 @@ M3B_API int m3b_llh(m3b_handle* h, double* total, double* per_sample) {
   REQUIRE(h->steps > 0, M3B_ERR_STATE, "m3b_llh: no step yet");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  if (h->peer_world > 0 && h->h_llh[0] != h->h_llh[0]) {     // NaN: look at the exchange status
+  if (h->h_llh[0] != h->h_llh[0]) {     // NaN: an exchange time-out, or a case in which the reference throws?
     int32_t st = 0;
     CK(cudaMemcpy(&st, h->d_status, sizeof st, cudaMemcpyDeviceToHost));
-    if (st != 0) return fail(h, M3B_ERR_PEER, "m3b_llh: peer histogram exchange timed out");
+    if (st != 0) CK(cudaMemset(h->d_status, 0, sizeof st));
+    if (st & 1) return fail(h, M3B_ERR_PEER, "m3b_llh: peer histogram exchange timed out");
+    if (st & 2) return fail(h, M3B_ERR_MATH, "m3b_llh: negative square root in the Barlow-Beeston coefficient (the reference throws "
+                                             "MaCh3Exception here, Samples/SampleHandlerBase.cpp:64-67)");
   }
   *total = h->h_llh[0];
   if (per_sample) for (int s = 0; s < h->n_samples; ++s) per_sample[s] = h->h_llh[1 + s];

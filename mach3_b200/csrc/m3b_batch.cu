@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(kCT + 32, 1) fill_batch_kernel(const __grid_co
 // the mapped host array; also un-transposes the LAST set's histogram into `last_out` (the handle's current one)
 __global__ void __launch_bounds__(256) llh_batch_kernel(const double* hist, const double* w2, const double* data,
                                                         const int32_t* sample_start, int n_bins, int n_samples, int test_stat,
-                                                        double* llh_dev, double* llh_host, double* last_out) {
+                                                        double* llh_dev, double* llh_host, double* last_out, int32_t* status) {
   __shared__ double s_part[kMaxSamples * 8];
+  bool thrown = false;
   const int set = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double* col = hist + set;
   for (int s = 0; s < n_samples; ++s) {
@@ -224,11 +225,12 @@ __global__ void __launch_bounds__(256) llh_batch_kernel(const double* hist, cons
     for (int b = b0 + tid; b < b1; b += 256) {
       const double mc = col[static_cast<int64_t>(b) * kBSets];
       if (set == static_cast<int>(gridDim.x) - 1) last_out[b] = mc;
-      acc += test_stat_llh(test_stat, data[b], mc, w2 ? w2[b] : 0.);
+      acc += test_stat_llh(test_stat, data[b], mc, w2 ? w2[b] : 0., thrown);
     }
     acc = warp_sum(acc);
     if (lane == 0) s_part[s * 8 + warp] = acc;
   }
+  if (thrown) atomicOr(status, kStatusMathError);
   __syncthreads();
   if (tid < n_samples) {
     double tot = 0.;
@@ -384,7 +386,7 @@ int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, cons
   const int nxt = h->cur ^ 1;       // leave the handle as after the last set's step: its histogram becomes the current one
   llh_batch_kernel<<<n_sets, 256, 0, h->stream>>>(static_cast<const double*>(h->bt_hist), h->d_w2_frozen, h->d_data, h->d_sample_start,
                                                   h->n_bins, h->n_samples, h->test_stat, static_cast<double*>(h->bt_llh), host_slots_dev,
-                                                  h->d_hw[nxt]);
+                                                  h->d_hw[nxt], h->d_status);
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(h->d_tile_counter, 0, sizeof(unsigned int), h->stream));
   h->mc_zero[nxt] = false;

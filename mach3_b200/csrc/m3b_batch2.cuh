@@ -430,7 +430,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   const int nxt = h->cur ^ 1;       // leave the handle as after the last set's step: its histogram becomes the current one
   llh_batch_kernel<<<n_sets, 256, 0, h->stream>>>(static_cast<const double*>(h->bt_hist), h->d_w2_frozen, h->d_data, h->d_sample_start,
                                                   h->n_bins, h->n_samples, h->test_stat, static_cast<double*>(h->bt_llh), host_slots_dev,
-                                                  h->d_hw[nxt]);
+                                                  h->d_hw[nxt], h->d_status);
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(h->d_tile_counter, 0, sizeof(unsigned int), h->stream));
   h->mc_zero[nxt] = false;

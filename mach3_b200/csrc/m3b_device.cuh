@@ -90,7 +90,10 @@ __device__ __forceinline__ double poisson_llh(double data, double mc) {      // 
   return (mc - data + data * log(data / mc));
 }
 
-static __device__ double test_stat_llh(int ts, double data, double mc, double w2) {
+// `thrown` is set where the reference throws MaCh3Exception instead of returning a number (the Barlow-Beeston negative
+// discriminant, :64-67); the kernels collect it in the handle's status word and m3b_llh turns it into M3B_ERR_MATH.
+constexpr int kStatusPeerTimeout = 1, kStatusMathError = 2;
+static __device__ double test_stat_llh(int ts, double data, double mc, double w2, bool& thrown) {
   switch (ts) {
     case 1: {   // kBarlowBeeston :46-88
       double newmc = mc;
@@ -102,7 +105,7 @@ static __device__ double test_stat_llh(int ts, double data, double mc, double w2
       const double fractional2 = fractional * fractional;
       const double temp = newmc * fractional2 - 1;
       const double temp2 = temp * temp + 4 * data * fractional2;
-      if (temp2 < 0) return nan("");          // the reference throws here
+      if (temp2 < 0) { thrown = true; return nan(""); }          // the reference throws here
       const double beta = (-1 * temp + sqrt(temp2)) / 2.;
       double stat = mc * beta;
       if (data > 0) {
@@ -168,8 +171,9 @@ constexpr int kMaxSamples = 64;
 
 static __device__ void block_llh(const double* __restrict__ hist, const double* __restrict__ w2,
                           const double* __restrict__ data, const int32_t* __restrict__ sample_start,
-                          int n_samples, int ts, double* llh_dev, double* llh_host, double* scratch) {
+                          int n_samples, int ts, double* llh_dev, double* llh_host, double* scratch, int32_t* status) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  bool thrown = false;
   for (int s = 0; s < n_samples; ++s) {
     const int b0 = sample_start[s], b1 = sample_start[s + 1];
     double acc = 0.;
@@ -188,11 +192,12 @@ static __device__ void block_llh(const double* __restrict__ hist, const double* 
       }
       #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (b + k * NT < b1) acc += test_stat_llh(ts, d[k], m[k], v[k]);
+        if (b + k * NT < b1) acc += test_stat_llh(ts, d[k], m[k], v[k], thrown);
     }
     acc = warp_sum(acc);
     if (lane == 0) scratch[s * 32 + warp] = acc;
   }
+  if (thrown && status) atomicOr(status, kStatusMathError);
   __syncthreads();
   if (threadIdx.x < n_samples) {
     double tot = 0.;
@@ -281,7 +286,7 @@ __device__ __forceinline__ void finish_block(const FillArgs& a, const double* s_
   if (!a.fuse_llh) { if (tid == 0) *a.ticket = 0u; return; }
 
   if (tid == 0 && a.trace) a.trace[8 * 4000 + 0] = globaltimer_ns();      // last block: ticket won
-  block_llh(a.hist, a.w2_frozen, a.data, a.sample_start_inline, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, scratch);
+  block_llh(a.hist, a.w2_frozen, a.data, a.sample_start_inline, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, scratch, a.status);
   if (tid == 0 && a.trace) a.trace[8 * 4000 + 1] = globaltimer_ns();      // last block: -lnL written
   // prepare the next step: zero its histogram(s), re-arm the ticket
   if (a.hist_next) for (int i = tid; i < a.n_bins; i += NT) a.hist_next[i] = 0.;

@@ -128,6 +128,7 @@ struct FillArgs {
   const int32_t* sample_start; // [n_samples+1] global bin offsets
   int32_t sample_start_inline[65];   // the same, in the kernel parameters (saves the last block a DRAM round trip)
   unsigned int* ticket;
+  int32_t* status;             // handle's status word: bit 1 = a test statistic hit a case where the reference throws
   unsigned int* tile_counter;  // dynamic tile scheduler of the TMA kernel (nullptr: static interleave)
   int32_t n_stages;            // TMA kernel: stages of the shared-memory coefficient ring
   int32_t pdl;                 // TMA kernel launched with programmatic stream serialization: the next step's ramp may

@@ -179,7 +179,7 @@ cudaError_t fill_occupancy(int T, int variant, int smem, int* bps) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) llh_kernel(const __grid_constant__ LlhArgs a) {
   __shared__ double s_part[kMaxSamples * 32];
-  block_llh(a.hist, a.w2, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, s_part);
+  block_llh(a.hist, a.w2, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, s_part, a.status);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -208,11 +208,12 @@ __global__ void __launch_bounds__(512) llh_pull_kernel(const __grid_constant__ L
   }
   __syncthreads();
   if (!s_ok) {
-    if (tid == 0 && blockIdx.x == 0) { *a.status = 1; a.llh_dev[0] = nan(""); if (a.llh_host) a.llh_host[0] = nan(""); }
+    if (tid == 0 && blockIdx.x == 0) { atomicOr(a.status, kStatusPeerTimeout); a.llh_dev[0] = nan(""); if (a.llh_host) a.llh_host[0] = nan(""); }
     return;
   }
   const int per = (a.n_bins + gridDim.x - 1) / gridDim.x;
   const int b0 = blockIdx.x * per, b1 = min(a.n_bins, b0 + per);
+  bool thrown = false;
   for (int s = 0; s < a.n_samples; ++s) {
     const int lo = max(b0, a.sample_start_inline[s]), hi = min(b1, a.sample_start_inline[s + 1]);
     double acc = 0.;
@@ -226,11 +227,12 @@ __global__ void __launch_bounds__(512) llh_pull_kernel(const __grid_constant__ L
       } else if (a.w2) {
         w2 = a.w2[b];
       }
-      acc += test_stat_llh(a.test_stat, a.data[b], mc, w2);
+      acc += test_stat_llh(a.test_stat, a.data[b], mc, w2, thrown);
     }
     acc = warp_sum(acc);
     if (lane == 0) s_part[s * 16 + warp] = acc;
   }
+  if (thrown) atomicOr(a.status, kStatusMathError);
   __syncthreads();
   if (tid < a.n_samples) {
     double tot = 0.;

@@ -556,3 +556,30 @@ def test_batch_size_grows_on_one_handle(oracle_build):
                 osh.norm_vals[:] = nms[i]
             osh.Reweight()
             assert tot[i] == pytest.approx(osh.GetLikelihood(), rel=LLH_RTOL, abs=1e-9), (n_sets, i)
+
+
+def test_barlow_beeston_negative_discriminant_is_an_error_like_the_reference_throw(oracle_build):
+    """SampleHandlerBase::GetTestStatLLH throws MaCh3Exception when the Barlow-Beeston discriminant is negative
+    (Samples/SampleHandlerBase.cpp:64-67; only reachable with a negative data bin).  The device flags it and m3b_llh /
+    m3b_step_batch return M3B_ERR_MATH instead of handing a NaN to the fitter; the handle stays usable."""
+    w = synth.CFG1.scaled(6_000)
+    gsh, gd = handlers.build_from_workload(w, test_statistic=lib.BARLOW_BEESTON)
+    sp, nm = synth.proposal(w, 0)
+    gd["pars"][:] = sp; gd["norm"][:] = nm
+    gsh.Reweight(); gsh.GetLikelihood()
+    mc = gsh.GetMCArray()
+    good = np.random.default_rng(4).poisson(mc).astype(np.float64)
+    bad = good.copy()
+    b = int(np.argmax(mc))
+    bad[b] = -50.0 * max(mc[b], 1.0)            # temp^2 + 4*data*f^2 < 0
+    gsh.AddData(bad)
+    gsh.Reweight()
+    with pytest.raises(lib.M3BError) as ei:
+        gsh.GetLikelihood()
+    assert ei.value.code == 8 and "Barlow-Beeston" in str(ei.value)
+    with pytest.raises(lib.M3BError) as ei:
+        gsh.handle.step_batch(np.stack([sp, sp]), np.stack([nm, nm]) if w.n_norm_params else None)
+    assert ei.value.code == 8
+    gsh.AddData(good)
+    gsh.Reweight()
+    assert np.isfinite(gsh.GetLikelihood())
