@@ -183,7 +183,8 @@ M3B_API int m3b_read_event_weights_f64(m3b_handle* h, double* spline_w, double* 
  *   edges concatenated sample-major, dim-major.  Global bin = sum bin_d*stride_d + GlobalOffset.
  * m3b_upload_events: what SampleHandlerFD::Initialise wires per event (SampleHandlerFD.cpp:169-202)
  *   sample_id[E]          EventInfo::NominalSample
- *   kin[d*E+e]            *EventInfo::KinVar[d]   (bins are found on the device with
+ *   kin[d*E+e]            *EventInfo::KinVar[d], d < the largest dimensionality among the samples of the binning (rows a
+ *                         lower-dimensional sample does not use are ignored; bins are found on the device with
  *                         FindGlobalBin semantics, BinningHandler.cpp:257-277 -> SampleStructs.h:577-613)
  *   norm_idx[e*npe+j]     index into the per-step norm value array (EventInfo::norm_pointers as
  *                         offsets from ParameterHandlerBase::_fPropVal), <0 = none
@@ -231,6 +232,23 @@ M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* c
                                  const double* lower, const double* upper, int32_t n_vars, const double* values);
 M3B_API int m3b_update_selection_values(m3b_handle* h, const double* values);
 M3B_API int m3b_read_event_selected(m3b_handle* h, uint8_t* selected /* [n_events] 1 = passes every cut */);
+/* m3b_upload_linear_shifts / m3b_set_shift_pars: functional ("shift") parameters ON THE DEVICE.
+ *   SampleHandlerFD::ApplyShifts (Samples/SampleHandlerFD.cpp:545-564) runs, for every event and every step,
+ *   ResetShifts(event) -> (*funcPtr)(valuePtr, event) for each FunctionalShifter of funcParsGrid[event], in order ->
+ *   FinaliseShifts(event), before IsEventSelected and FindGlobalBin see the event.  The std::functions are experiment
+ *   code; the family covered here is the linear one,  x_t += (*valuePtr) * c  with a per-event constant c (energy-scale,
+ *   bias and resolution shifts are of this form: c = the energy deposit the parameter scales).  Per event, in
+ *   funcParsGrid order: n_per_event[e] entries {shift_par (index into the per-step shift-parameter array), target, coef};
+ *   target t < n_dims: the event's t-th binning variable; t >= n_dims: row t - n_dims of the selection's cut-variable
+ *   table (m3b_upload_selection, which must come first if cut variables are shifted).  Arithmetic: double, one
+ *   multiplication and one addition per entry, each rounded (what `x += par * c` compiles to without FMA contraction),
+ *   starting from the nominal values every step: bit-identical shifted variables, hence bit-identical bins and cuts.
+ *   Needs M3B_FLAG_KEEP_KINEMATICS.  m3b_set_shift_pars is asynchronous and takes effect for the following steps
+ *   (bins and selection are recomputed on the device: no per-event data crosses PCIe).
+ *   Shifts that are not of this form stay with the caller: m3b_update_kinematics / m3b_update_selection_values.   */
+M3B_API int m3b_upload_linear_shifts(m3b_handle* h, int32_t n_shift_pars, int64_t n_events, const uint32_t* n_per_event,
+                                     const int32_t* shift_par, const int32_t* target, const double* coef);
+M3B_API int m3b_set_shift_pars(m3b_handle* h, const double* values /* [n_shift_pars] */);
 /* SampleHandlerFD::AddData (Samples/SampleHandlerFD.cpp:955-1044), array form */
 M3B_API int m3b_upload_data(m3b_handle* h, const double* data, int32_t n_bins);
 /* oscillation weights computed elsewhere (NuOscillator) and already valid for the next steps    */
@@ -352,6 +370,9 @@ M3B_API int m3b_group_upload_events(m3b_group* g, int64_t n_events, const int32_
                                     int32_t use_osc, const int32_t* osc_idx, int64_t n_osc_values, const float* static_w);
 M3B_API int m3b_group_upload_selection(m3b_group* g, int32_t n_cuts, const int32_t* cut_sample, const int32_t* cut_var,
                                        const double* lower, const double* upper, int32_t n_vars, const double* values);
+M3B_API int m3b_group_upload_linear_shifts(m3b_group* g, int32_t n_shift_pars, int64_t n_events, const uint32_t* n_per_event,
+                                           const int32_t* shift_par, const int32_t* target, const double* coef);
+M3B_API int m3b_group_set_shift_pars(m3b_group* g, const double* values);
 M3B_API int m3b_group_upload_data(m3b_group* g, const double* data, int32_t n_bins);
 M3B_API int m3b_group_upload_osc(m3b_group* g, const float* osc_w, int64_t n);
 /* wires the exchange (after every member has its binning and events); exchange = M3B_EXCHANGE_* */

@@ -498,11 +498,10 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
   h->n_tiles = (n_events + T - 1) / T;
   h->e_pad = h->n_tiles * T;
   const int64_t E = n_events, EP = h->e_pad;
-  int max_dim = 0;
-  for (int64_t e = 0; e < E; ++e) {
+  int max_dim = 0;                 // rows of kin: the largest dimensionality of ANY sample of the binning
+  for (int s = 0; s < h->n_samples; ++s) max_dim = std::max(max_dim, h->b_ndim[s]);
+  for (int64_t e = 0; e < E; ++e)
     REQUIRE(sample_id[e] >= 0 && sample_id[e] < h->n_samples, M3B_ERR_INVALID, "m3b_upload_events: sample_id out of range");
-    max_dim = std::max(max_dim, h->b_ndim[sample_id[e]]);
-  }
   // bins on the device
   CK(dev_alloc(h, &h->d_bin, static_cast<size_t>(EP)));
   {
@@ -623,6 +622,8 @@ M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* c
     if (n_vars != h->n_sel_vars) CK(dev_alloc(h, &h->d_sel_vals, static_cast<size_t>(n_vars) * h->n_events));
     CK(cudaMemcpy(h->d_sel_vals, values, sizeof(double) * n_vars * h->n_events, cudaMemcpyHostToDevice));
   }
+  REQUIRE(!h->d_sh_start || n_vars == h->n_sel_vars, M3B_ERR_STATE, "m3b_upload_selection: upload the selection before m3b_upload_linear_shifts");
+  if (h->d_sel_vals_nom && n_vars > 0) CK(cudaMemcpy(h->d_sel_vals_nom, h->d_sel_vals, sizeof(double) * n_vars * h->n_events, cudaMemcpyDeviceToDevice));
   h->n_cuts = n_cuts; h->n_sel_vars = n_vars; h->sel_uses_kin = uses_kin;
   int rc = run_selection(h);
   if (rc != M3B_OK) return rc;
@@ -648,14 +649,7 @@ M3B_API int m3b_read_event_selected(m3b_handle* h, uint8_t* selected) {
   return M3B_OK;
 }
 
-// Functional ("shift") parameters (Samples/SampleHandlerFD.cpp:545-564) call arbitrary std::functions per event, so they
-// stay on the host: the caller applies its shifts to the kinematic variables and hands the shifted values over; the
-// events are re-binned on the device with the same FindGlobalBin semantics.  Asynchronous on the handle's stream.
-M3B_API int m3b_update_kinematics(m3b_handle* h, const double* kin) {
-  REQUIRE(h && kin, M3B_ERR_INVALID, "m3b_update_kinematics: null argument");
-  REQUIRE(h->d_kin && h->n_events > 0, M3B_ERR_STATE, "m3b_update_kinematics: create the handle with M3B_FLAG_KEEP_KINEMATICS and upload the events first");
-  CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(h->d_kin, kin, sizeof(double) * h->n_events * h->kin_dims, cudaMemcpyHostToDevice, h->stream));
+static int rebin(m3b_handle* h) {
   BinArgs ba{};
   ba.n_events = h->n_events; ba.e_pad = h->e_pad; ba.sample_id = h->d_sample_id; ba.kin = h->d_kin; ba.n_samples = h->n_samples;
   ba.n_dim = h->d_ndim; ba.nbins = h->d_nbins; ba.edge_off = h->d_edge_off; ba.stride = h->d_stride;
@@ -665,6 +659,71 @@ M3B_API int m3b_update_kinematics(m3b_handle* h, const double* kin) {
   CK(launch_bins(ba, h->stream));
   ++h->launches;
   return run_selection(h);       // ApplyShifts runs before IsEventSelected (Samples/SampleHandlerFD.cpp:359-361)
+}
+
+M3B_API int m3b_upload_linear_shifts(m3b_handle* h, int32_t n_shift_pars, int64_t n_events, const uint32_t* n_per_event,
+                                     const int32_t* shift_par, const int32_t* target, const double* coef) {
+  REQUIRE(h && n_per_event, M3B_ERR_INVALID, "m3b_upload_linear_shifts: null argument");
+  REQUIRE(h->n_events > 0 && n_events == h->n_events, M3B_ERR_STATE, "m3b_upload_linear_shifts: upload the events first (same count)");
+  REQUIRE(h->d_kin, M3B_ERR_STATE, "m3b_upload_linear_shifts: create the handle with M3B_FLAG_KEEP_KINEMATICS");
+  REQUIRE(n_shift_pars > 0 && n_shift_pars <= 4096, M3B_ERR_INVALID, "m3b_upload_linear_shifts: 1..4096 shift parameters");
+  REQUIRE(!h->d_sh_start, M3B_ERR_STATE, "m3b_upload_linear_shifts: already uploaded");
+  std::vector<int64_t> start(static_cast<size_t>(n_events) + 1, 0);
+  for (int64_t e = 0; e < n_events; ++e) start[e + 1] = start[e] + n_per_event[e];
+  const int64_t total = start[n_events];
+  REQUIRE(total == 0 || (shift_par && target && coef), M3B_ERR_INVALID, "m3b_upload_linear_shifts: null entry arrays");
+  for (int64_t k = 0; k < total; ++k) {
+    REQUIRE(shift_par[k] >= 0 && shift_par[k] < n_shift_pars, M3B_ERR_INVALID, "m3b_upload_linear_shifts: shift_par out of range");
+    REQUIRE(target[k] >= 0 && target[k] < h->kin_dims + h->n_sel_vars, M3B_ERR_INVALID,
+            "m3b_upload_linear_shifts: target out of range (binning variables, then the selection's cut variables)");
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(dev_upload(h, &h->d_sh_start, start));
+  CK(dev_alloc(h, &h->d_sh_par, static_cast<size_t>(total)));
+  CK(dev_alloc(h, &h->d_sh_target, static_cast<size_t>(total)));
+  CK(dev_alloc(h, &h->d_sh_coef, static_cast<size_t>(total)));
+  if (total > 0) {
+    CK(cudaMemcpy(h->d_sh_par, shift_par, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_sh_target, target, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_sh_coef, coef, sizeof(double) * total, cudaMemcpyHostToDevice));
+  }
+  // the nominal values every step starts from (ResetShifts)
+  CK(dev_alloc(h, &h->d_kin_nom, static_cast<size_t>(h->n_events) * h->kin_dims));
+  CK(cudaMemcpy(h->d_kin_nom, h->d_kin, sizeof(double) * h->n_events * h->kin_dims, cudaMemcpyDeviceToDevice));
+  if (h->n_sel_vars > 0) {
+    CK(dev_alloc(h, &h->d_sel_vals_nom, static_cast<size_t>(h->n_events) * h->n_sel_vars));
+    CK(cudaMemcpy(h->d_sel_vals_nom, h->d_sel_vals, sizeof(double) * h->n_events * h->n_sel_vars, cudaMemcpyDeviceToDevice));
+  }
+  CK(dev_alloc(h, &h->d_shift_theta, static_cast<size_t>(n_shift_pars)));
+  CK(cudaMemset(h->d_shift_theta, 0, sizeof(double) * n_shift_pars));
+  h->n_shift_pars = n_shift_pars;
+  return M3B_OK;
+}
+
+M3B_API int m3b_set_shift_pars(m3b_handle* h, const double* values) {
+  REQUIRE(h && values, M3B_ERR_INVALID, "m3b_set_shift_pars: null argument");
+  REQUIRE(h->n_shift_pars > 0, M3B_ERR_STATE, "m3b_set_shift_pars: call m3b_upload_linear_shifts first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_shift_theta, values, sizeof(double) * h->n_shift_pars, cudaMemcpyHostToDevice, h->stream));
+  ShiftArgs sa{};
+  sa.n_events = h->n_events; sa.n_dims = h->kin_dims; sa.n_sel_vars = h->d_sel_vals_nom ? h->n_sel_vars : 0;
+  sa.kin_nom = h->d_kin_nom; sa.kin = h->d_kin; sa.sel_nom = h->d_sel_vals_nom; sa.sel = h->d_sel_vals;
+  sa.start = h->d_sh_start; sa.par = h->d_sh_par; sa.target = h->d_sh_target; sa.coef = h->d_sh_coef; sa.theta = h->d_shift_theta;
+  CK(launch_shift(sa, h->stream));
+  ++h->launches;
+  return rebin(h);
+}
+
+// Functional ("shift") parameters (Samples/SampleHandlerFD.cpp:545-564) call arbitrary std::functions per event, so they
+// stay on the host: the caller applies its shifts to the kinematic variables and hands the shifted values over; the
+// events are re-binned on the device with the same FindGlobalBin semantics.  Asynchronous on the handle's stream.
+M3B_API int m3b_update_kinematics(m3b_handle* h, const double* kin) {
+  REQUIRE(h && kin, M3B_ERR_INVALID, "m3b_update_kinematics: null argument");
+  REQUIRE(h->d_kin && h->n_events > 0, M3B_ERR_STATE, "m3b_update_kinematics: create the handle with M3B_FLAG_KEEP_KINEMATICS and upload the events first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_kin, kin, sizeof(double) * h->n_events * h->kin_dims, cudaMemcpyHostToDevice, h->stream));
+  return rebin(h);
 }
 
 M3B_API int m3b_upload_data(m3b_handle* h, const double* data, int32_t n_bins) {

@@ -269,6 +269,29 @@ M3B_API int m3b_group_upload_selection(m3b_group* g, int32_t n_cuts, const int32
   return M3B_OK;
 }
 
+M3B_API int m3b_group_upload_linear_shifts(m3b_group* g, int32_t n_shift_pars, int64_t n_events, const uint32_t* n_per_event,
+                                           const int32_t* shift_par, const int32_t* target, const double* coef) {
+  GREQUIRE(g && n_per_event, M3B_ERR_INVALID, "m3b_group_upload_linear_shifts: null argument");
+  int64_t e0 = 0, k0 = 0;
+  for (m3b_handle* h : g->members) {
+    const int64_t n = h->n_events;
+    if (n == 0) continue;
+    GREQUIRE(e0 + n <= n_events, M3B_ERR_INVALID, "m3b_group_upload_linear_shifts: event count differs from the members'");
+    int64_t k1 = k0;
+    for (int64_t e = e0; e < e0 + n; ++e) k1 += n_per_event[e];
+    GMEMBER(m3b_upload_linear_shifts(h, n_shift_pars, n, n_per_event + e0, shift_par ? shift_par + k0 : nullptr, target ? target + k0 : nullptr,
+                                     coef ? coef + k0 : nullptr));
+    e0 += n; k0 = k1;
+  }
+  return M3B_OK;
+}
+
+M3B_API int m3b_group_set_shift_pars(m3b_group* g, const double* values) {
+  GREQUIRE(g && values, M3B_ERR_INVALID, "m3b_group_set_shift_pars: null argument");
+  for (m3b_handle* h : g->members) if (h->n_events > 0) GMEMBER(m3b_set_shift_pars(h, values));
+  return M3B_OK;
+}
+
 M3B_API int m3b_group_upload_data(m3b_group* g, const double* data, int32_t n_bins) {
   GREQUIRE(g, M3B_ERR_INVALID, "null group");
   for (m3b_handle* h : g->members) GMEMBER(m3b_upload_data(h, data, n_bins));

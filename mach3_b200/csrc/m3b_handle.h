@@ -81,6 +81,11 @@ struct m3b_handle {
   int32_t *d_cut_start = nullptr, *d_cut_var = nullptr;
   double *d_cut_lo = nullptr, *d_cut_hi = nullptr, *d_sel_vals = nullptr;
   uint8_t* d_selected = nullptr;
+  // linear functional shifts (SampleHandlerFD::ApplyShifts on the device): nominal copies + per-event entry lists
+  int n_shift_pars = 0;
+  double *d_kin_nom = nullptr, *d_sel_vals_nom = nullptr, *d_shift_theta = nullptr, *d_sh_coef = nullptr;
+  int64_t* d_sh_start = nullptr;
+  int32_t *d_sh_par = nullptr, *d_sh_target = nullptr;
   int32_t* d_osc_idx = nullptr;
   float* d_osc = nullptr;
   int64_t n_osc = 0;

@@ -215,6 +215,17 @@ struct SelectArgs {
   uint8_t* selected;
 };
 
+// SampleHandlerFD::ApplyShifts for linear functional parameters (m3b_upload_linear_shifts)
+struct ShiftArgs {
+  int64_t n_events;
+  int32_t n_dims, n_sel_vars;
+  const double* kin_nom; double* kin;              // [d * n_events + e]
+  const double* sel_nom; double* sel;              // [v * n_events + e]  (may be null)
+  const int64_t* start;                            // [n_events + 1] CSR over the entries below
+  const int32_t* par; const int32_t* target; const double* coef;
+  const double* theta;                             // [n_shift_pars] this step's parameter values
+};
+
 struct RetileArgs {
   int64_t n;                   // events in chunk
   int64_t tile0_event;         // chunk's first event is the first lane of a tile
@@ -243,6 +254,7 @@ cudaError_t launch_llh_pull(const LlhArgs& a, int blocks, cudaStream_t s);
 constexpr int kLlhPullMaxBlocks = 32;
 cudaError_t launch_bins(const BinArgs& a, cudaStream_t s);
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t s);
+cudaError_t launch_shift(const ShiftArgs& a, cudaStream_t s);
 cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s);
 cudaError_t fill_occupancy(int T, int variant, int smem_bytes, int* blocks_per_sm);
 cudaError_t fill_set_smem(int T, int variant, int smem_bytes);

@@ -351,6 +351,39 @@ cudaError_t launch_select(const SelectArgs& a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// SampleHandlerFD::ApplyShifts (Samples/SampleHandlerFD.cpp:545-564) for linear shifts: ResetShifts (back to the nominal
+// values), then x_t += theta * c for the event's entries in funcParsGrid order.  __dmul_rn / __dadd_rn: two roundings,
+// no FMA contraction -- the arithmetic of the host code the reference compiles for its functional parameters.
+// ------------------------------------------------------------------------------------------------
+__global__ void shift_kernel(const __grid_constant__ ShiftArgs a) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= a.n_events) return;
+  const int64_t k0 = a.start[e], k1 = a.start[e + 1];
+  double x[kMaxDim];
+  #pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) x[d] = d < a.n_dims ? a.kin_nom[static_cast<int64_t>(d) * a.n_events + e] : 0.;
+  for (int v = 0; v < a.n_sel_vars; ++v) a.sel[static_cast<int64_t>(v) * a.n_events + e] = a.sel_nom[static_cast<int64_t>(v) * a.n_events + e];
+  for (int64_t k = k0; k < k1; ++k) {
+    const int t = a.target[k];
+    const double delta = __dmul_rn(a.theta[a.par[k]], a.coef[k]);
+    if (t < a.n_dims) {
+      #pragma unroll
+      for (int d = 0; d < kMaxDim; ++d) if (d == t) x[d] = __dadd_rn(x[d], delta);
+    } else {
+      double* p = a.sel + static_cast<int64_t>(t - a.n_dims) * a.n_events + e;
+      *p = __dadd_rn(*p, delta);
+    }
+  }
+  #pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) if (d < a.n_dims) a.kin[static_cast<int64_t>(d) * a.n_events + e] = x[d];
+}
+cudaError_t launch_shift(const ShiftArgs& a, cudaStream_t s) {
+  const int threads = 256;
+  shift_kernel<<<static_cast<unsigned>((a.n_events + threads - 1) / threads), threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // setup: AoS monolith -> tiled SoA.  identity rows first ({1,0,0,0} / {0,1}: a response that
 // multiplies by exactly 1.0f), then every event scatters its own responses.
 // ------------------------------------------------------------------------------------------------

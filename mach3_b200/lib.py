@@ -25,7 +25,8 @@ EXPORTS = (
     "m3b_upload_binned_splines", "m3b_upload_event_binned_splines", "m3b_read_binned_weights",
     "m3b_upload_binned_splines_f64", "m3b_upload_event_weights_f64", "m3b_upload_osc_f64", "m3b_read_binned_weights_f64",
     "m3b_read_event_weights_f64",
-    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_update_kinematics", "m3b_upload_selection", "m3b_update_selection_values", "m3b_read_event_selected", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
+    "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_update_kinematics", "m3b_upload_selection", "m3b_update_selection_values", "m3b_read_event_selected",
+    "m3b_upload_linear_shifts", "m3b_set_shift_pars", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
     "m3b_set_test_statistic", "m3b_reset_w2",
     "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_step_batch_hist", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_set_spline_knots_f64", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
@@ -36,6 +37,7 @@ EXPORTS = (
     "m3b_group_upload_data", "m3b_group_upload_osc", "m3b_group_connect", "m3b_group_alloc_host", "m3b_group_step",
     "m3b_group_llh", "m3b_group_read_hist", "m3b_group_synchronize",
     "m3b_write_monolith_file", "m3b_monolith_file_info", "m3b_upload_from_file", "m3b_group_upload_from_file",
+    "m3b_group_upload_linear_shifts", "m3b_group_set_shift_pars",
 )
 EXCHANGE_PEER, EXCHANGE_NCCL = 0, 1
 
@@ -327,6 +329,17 @@ class Handle:
         self._ck(self.L.m3b_read_event_selected(self.h, _p(out)))
         return out.astype(bool)
 
+    def upload_linear_shifts(self, n_shift_pars, n_per_event, shift_par, target, coef):
+        """SampleHandlerFD::ApplyShifts for linear functional parameters: per event (funcParsGrid order) entries
+        {shift_par, target, coef}: x_target += value[shift_par] * coef."""
+        npe, sp, tg, cf = _c(n_per_event, np.uint32), _c(shift_par, np.int32), _c(target, np.int32), _c(coef, np.float64)
+        self._ck(self.L.m3b_upload_linear_shifts(self.h, C.c_int32(n_shift_pars), C.c_int64(npe.size), _p(npe), _p(sp), _p(tg), _p(cf)))
+
+    def set_shift_pars(self, values):
+        v = _c(values, np.float64)
+        self._keep_shift = v
+        self._ck(self.L.m3b_set_shift_pars(self.h, _p(v)))
+
     def upload_data(self, data):
         d = _c(data, np.float64)
         self._ck(self.L.m3b_upload_data(self.h, _p(d), C.c_int32(d.size)))
@@ -582,6 +595,14 @@ class Group:
         v = None if values is None else np.ascontiguousarray(np.asarray(values, np.float64).reshape(-1, n_events))
         self._ck(self.L.m3b_group_upload_selection(self.g, C.c_int32(len(cuts)), _p(cs), _p(cv), _p(lo), _p(hi),
                                                    C.c_int32(0 if v is None else v.shape[0]), _p(v)))
+
+    def upload_linear_shifts(self, n_shift_pars, n_per_event, shift_par, target, coef):
+        npe, sp, tg, cf = _c(n_per_event, np.uint32), _c(shift_par, np.int32), _c(target, np.int32), _c(coef, np.float64)
+        self._ck(self.L.m3b_group_upload_linear_shifts(self.g, C.c_int32(n_shift_pars), C.c_int64(npe.size), _p(npe), _p(sp), _p(tg), _p(cf)))
+
+    def set_shift_pars(self, values):
+        v = _c(values, np.float64)
+        self._ck(self.L.m3b_group_set_shift_pars(self.g, _p(v)))
 
     def upload_data(self, data):
         d = _c(data, np.float64)

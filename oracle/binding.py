@@ -299,6 +299,20 @@ class SampleHandlerFD:
         assert cv.size == 0 or (cv.min() >= 0 and cv.max() < self.cut_values.shape[0])
         lib().m3o_sample_set_selection(self.h, C.c_int(len(cuts)), _p(cs), _p(cv), _p(lo), _p(hi), _p(self.cut_values))
 
+    def SetLinearShifts(self, n_per_event, shift_par, target, coef, values):
+        """funcParsGrid for linear functional parameters (SampleHandlerFD::ApplyShifts): per event, in order, entries
+        {shift_par, target, coef}; `values` is the live parameter array the FunctionalShifters' valuePtr look into.
+        Targets < (kinematic rows) shift the live kinematic array handed to set_events, the rest the cut-variable table."""
+        npe = np.ascontiguousarray(n_per_event, np.uint32); sp = np.ascontiguousarray(shift_par, np.int32)
+        tg = np.ascontiguousarray(target, np.int32); cf = np.ascontiguousarray(coef, np.float64)
+        self.shift_values = np.ascontiguousarray(values, np.float64)
+        kin = self._keep[1]
+        n_rows = kin.size // self.n_events
+        cv = getattr(self, "cut_values", None)
+        self._keep_shift = (npe, sp, tg, cf)
+        lib().m3o_sample_set_linear_shifts(self.h, _p(npe), _p(sp), _p(tg), _p(cf), _p(self.shift_values), _p(kin), C.c_int(n_rows),
+                                           None if cv is None else _p(cv), C.c_int(0 if cv is None else cv.shape[0]))
+
     def event_selected(self):
         out = np.zeros(self.n_events, np.uint8)
         lib().m3o_event_selected(self.h, _p(out))

@@ -578,6 +578,12 @@ typedef struct {
    * virtual in the reference, experiment code -- is a table look-up here: CutValues[var*nEvents + event]. */
   int* SelStart; KinematicCut* StoredSelection; KinematicCut* Selection; int nCuts;
   const double* CutValues;
+  /* std::vector<std::vector<FunctionalShifter*>> funcParsGrid (Samples/SampleHandlerFD.h:257), flattened: the shifters
+   * of event e are entries ShiftStart[e] .. ShiftStart[e+1]); FunctionalShifter = {valuePtr, funcPtr}
+   * (Samples/SampleStructs.h:161-168).  The functions are experiment code; the ones restated here are the linear family
+   * x_target += (*valuePtr) * coef.  ResetShifts() restores the nominal values kept in KinNominal / CutNominal. */
+  int64_t* ShiftStart; int* ShiftPar; int* ShiftTarget; double* ShiftCoef; const double* ShiftValues;
+  double* KinShifted; double* KinNominal; int nKinRows; double* CutShifted; double* CutNominal; int nCutRows;
 } SampleHandlerFD;
 
 
@@ -708,6 +714,7 @@ M3O_API void m3o_sample_destroy(SampleHandlerFD* s) {
   free(s->SampleBinning);
   free(s->SampleHandlerFD_array); free(s->SampleHandlerFD_array_w2); free(s->SampleHandlerFD_data);
   free(s->SelStart); free(s->StoredSelection); free(s->Selection);
+  free(s->ShiftStart); free(s->ShiftPar); free(s->ShiftTarget); free(s->ShiftCoef); free(s->KinNominal); free(s->CutNominal);
   free(s);
 }
 
@@ -823,6 +830,51 @@ M3O_API void m3o_event_selected(const SampleHandlerFD* s, unsigned char* out) {
   for (unsigned int e = 0; e < s->nEvents; ++e) out[e] = (unsigned char)IsEventSelected(s, s->MCSamples[e].NominalSample, e);
 }
 
+/* funcParsGrid for linear shifts.  kin[n_kin_rows*nEvents] is the live array the KinVar pointers look into (the one
+ * handed to m3o_sample_set_events), cut_values the live table of m3o_sample_set_selection (or NULL); both are read now
+ * as the nominal values.  Entry k of event e: *values[par[k]] * coef[k] is added to target[k] (< n_kin_rows: that
+ * kinematic row; else cut-variable row target - n_kin_rows). */
+M3O_API void m3o_sample_set_linear_shifts(SampleHandlerFD* s, const uint32_t* n_per_event, const int* par, const int* target,
+                                          const double* coef, const double* values, double* kin, int n_kin_rows,
+                                          double* cut_values, int n_cut_rows) {
+  free(s->ShiftStart); free(s->ShiftPar); free(s->ShiftTarget); free(s->ShiftCoef); free(s->KinNominal); free(s->CutNominal);
+  s->ShiftStart = (int64_t*)calloc((size_t)s->nEvents + 1, sizeof(int64_t));
+  for (unsigned int e = 0; e < s->nEvents; ++e) s->ShiftStart[e + 1] = s->ShiftStart[e] + n_per_event[e];
+  const int64_t tot = s->ShiftStart[s->nEvents];
+  s->ShiftPar = (int*)malloc(sizeof(int) * (size_t)(tot > 0 ? tot : 1));
+  s->ShiftTarget = (int*)malloc(sizeof(int) * (size_t)(tot > 0 ? tot : 1));
+  s->ShiftCoef = (double*)malloc(sizeof(double) * (size_t)(tot > 0 ? tot : 1));
+  memcpy(s->ShiftPar, par, sizeof(int) * (size_t)tot); memcpy(s->ShiftTarget, target, sizeof(int) * (size_t)tot);
+  memcpy(s->ShiftCoef, coef, sizeof(double) * (size_t)tot);
+  s->ShiftValues = values;
+  s->KinShifted = kin; s->nKinRows = n_kin_rows;
+  s->KinNominal = (double*)malloc(sizeof(double) * (size_t)n_kin_rows * s->nEvents);
+  memcpy(s->KinNominal, kin, sizeof(double) * (size_t)n_kin_rows * s->nEvents);
+  s->CutShifted = cut_values; s->nCutRows = cut_values ? n_cut_rows : 0;
+  s->CutNominal = NULL;
+  if (cut_values) {
+    s->CutNominal = (double*)malloc(sizeof(double) * (size_t)n_cut_rows * s->nEvents);
+    memcpy(s->CutNominal, cut_values, sizeof(double) * (size_t)n_cut_rows * s->nEvents);
+  }
+}
+
+/* SampleHandlerFD::ApplyShifts (Samples/SampleHandlerFD.cpp:545-564) */
+static inline void ApplyShifts(SampleHandlerFD* s, const unsigned int iEvent) {
+  if (!s->ShiftStart) return;
+  const int64_t k0 = s->ShiftStart[iEvent], nShifts = s->ShiftStart[iEvent + 1] - k0;
+  if (nShifts == 0) return;                                       /* :549-552: nothing to reset either */
+  /* ResetShifts(iEvent): back to the nominal values */
+  for (int d = 0; d < s->nKinRows; ++d) s->KinShifted[(size_t)d * s->nEvents + iEvent] = s->KinNominal[(size_t)d * s->nEvents + iEvent];
+  for (int v = 0; v < s->nCutRows; ++v) s->CutShifted[(size_t)v * s->nEvents + iEvent] = s->CutNominal[(size_t)v * s->nEvents + iEvent];
+  for (int64_t iShift = 0; iShift < nShifts; ++iShift) {           /* (*fp->funcPtr)(fp->valuePtr, iEvent) */
+    const int t = s->ShiftTarget[k0 + iShift];
+    double* x = t < s->nKinRows ? &s->KinShifted[(size_t)t * s->nEvents + iEvent] : &s->CutShifted[(size_t)(t - s->nKinRows) * s->nEvents + iEvent];
+    const double delta = s->ShiftValues[s->ShiftPar[k0 + iShift]] * s->ShiftCoef[k0 + iShift];
+    *x = *x + delta;
+  }
+  /* FinaliseShifts(iEvent): nothing to do for this family */
+}
+
 /* SampleHandlerFD::CalcWeightTotal (Samples/SampleHandlerFD.cpp:568-594) */
 static inline float CalcWeightTotal(const EventInfo* restrict MCEvent) {
   float TotalWeight = 1.0;
@@ -890,6 +942,7 @@ static void FillArray_MP(SampleHandlerFD* s) {
   const int FirstTimeW2 = s->FirstTimeW2;
   #pragma omp parallel for reduction(+:MC_Array_for_reduction[:TotalBins], W2_array_for_reduction[:TotalBins])
   for (unsigned int iEvent = 0; iEvent < NumberOfEvents; ++iEvent) {
+    ApplyShifts(s, iEvent);                                                               /* :420 */
     const EventInfo* restrict MCEvent = &s->MCSamples[iEvent];
     if (!IsEventSelected(s, MCEvent->NominalSample, iEvent)) continue;                    /* :424 */
     const float totalweight = CalcWeightTotal(MCEvent);
@@ -906,6 +959,7 @@ static void FillArray_MP(SampleHandlerFD* s) {
 static void FillArray(SampleHandlerFD* s) {
   if (s->SelStart) memcpy(s->Selection, s->StoredSelection, sizeof(KinematicCut) * (size_t)s->nCuts);   /* :355 */
   for (unsigned int iEvent = 0; iEvent < s->nEvents; iEvent++) {
+    ApplyShifts(s, iEvent);                                                               /* :358 */
     const EventInfo* restrict MCEvent = &s->MCSamples[iEvent];
     if (!IsEventSelected(s, MCEvent->NominalSample, iEvent)) continue;                    /* :361 */
     const float totalweight = CalcWeightTotal_serial(MCEvent);

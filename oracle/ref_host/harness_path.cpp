@@ -278,6 +278,16 @@ const M3::float_t* OscillationHandler::GetNuOscillatorPointers(const int, const 
 namespace {
 struct FD : SampleHandlerFD {
   std::vector<double> kin;          // [event][4]: what KinVar points at
+  // functional ("shift") parameters of the linear family: parameter s adds (*valuePtr) * shift_coef[s][event] to column
+  // shift_target[s] of the event's kinematic row; the reference's own ApplyShifts (Samples/SampleHandlerFD.cpp:545-564)
+  // drives them through funcParsGrid / FunctionalShifter / ResetShifts
+  std::vector<double> kin_nom, shift_pars;
+  std::vector<int> shift_target;
+  std::vector<std::vector<double>> shift_coef;
+  std::vector<FuncParFuncType> shift_funcs;
+  void ResetShifts(const int iEvent) override {
+    for (int d = 0; d < 4; ++d) kin[size_t(iEvent) * 4 + size_t(d)] = kin_nom[size_t(iEvent) * 4 + size_t(d)];
+  }
   std::vector<double> norm;         // what norm_pointers point at (ParameterHandler::_fPropVal)
   std::vector<M3::float_t> pool;    // what total_weight_pointers point at (oscillation weights, extra weights)
   Mono* mono = nullptr;             // spline parameters live with the spline handler
@@ -470,6 +480,41 @@ REFP_API void refp_fd_selected(void* p, unsigned char* out) {
   FD* fd = static_cast<FD*>(p);
   fd->Selection = fd->StoredSelection;
   for (unsigned e = 0; e < fd->nEvents; ++e) out[e] = fd->IsEventSelected(fd->MCSamples[e].NominalSample, int(e)) ? 1 : 0;
+}
+
+// Functional parameters: n_pars shifters; shifter s applies to the events with a finite coef[s*n_events + e] (NaN = the
+// event is not in its funcParsGrid list) and adds (*valuePtr) * coef to kinematic column target[s].  Wired the way
+// SampleHandlerFD::SetupFunctionalParameters leaves it (:470-540): funcParsMap[s] = {valuePtr, funcPtr}, funcParsGrid[e] =
+// the shifters of event e in parameter order.  Call after refp_fd_set_events (the nominal kinematics are read now).
+REFP_API void refp_fd_set_linear_shifts(void* p, int n_pars, const int* target, const double* coef) {
+  FD* fd = static_cast<FD*>(p);
+  const size_t E = fd->nEvents;
+  fd->kin_nom = fd->kin;
+  fd->shift_pars.assign(size_t(n_pars), 0.0);
+  fd->shift_target.assign(target, target + n_pars);
+  fd->shift_coef.assign(size_t(n_pars), std::vector<double>(E));
+  fd->shift_funcs.resize(size_t(n_pars));
+  fd->funcParsMap.resize(size_t(n_pars));
+  for (int s = 0; s < n_pars; ++s) {
+    std::copy(coef + size_t(s) * E, coef + size_t(s + 1) * E, fd->shift_coef[size_t(s)].begin());
+    fd->shift_funcs[size_t(s)] = [fd, s](const double* par, std::size_t iEvent) {
+      fd->kin[iEvent * 4 + size_t(fd->shift_target[size_t(s)])] += (*par) * fd->shift_coef[size_t(s)][iEvent];
+    };
+    fd->funcParsMap[size_t(s)].valuePtr = &fd->shift_pars[size_t(s)];
+    fd->funcParsMap[size_t(s)].funcPtr = &fd->shift_funcs[size_t(s)];
+  }
+  fd->funcParsGrid.assign(E, {});
+  for (size_t e = 0; e < E; ++e)
+    for (int s = 0; s < n_pars; ++s)
+      if (fd->shift_coef[size_t(s)][e] == fd->shift_coef[size_t(s)][e]) fd->funcParsGrid[e].push_back(&fd->funcParsMap[size_t(s)]);
+}
+REFP_API void refp_fd_set_shift_pars(void* p, const double* vals) {
+  FD* fd = static_cast<FD*>(p);
+  std::copy(vals, vals + fd->shift_pars.size(), fd->shift_pars.begin());
+}
+REFP_API void refp_fd_get_kin(void* p, double* out) {
+  FD* fd = static_cast<FD*>(p);
+  std::copy(fd->kin.begin(), fd->kin.end(), out);
 }
 
 REFP_API void refp_fd_set_data(void* p, const double* data) {

@@ -242,6 +242,25 @@ class RefSampleHandlerFD:
         lo = np.array([c[2] for c in cuts], np.float64); hi = np.array([c[3] for c in cuts], np.float64)
         self.L.refp_fd_set_selection(self.h, len(cuts), _p(cs), _p(cv), _p(lo), _p(hi))
 
+    def set_linear_shifts(self, target, coef):
+        """target[n_pars]: kinematic column each functional parameter shifts; coef[n_pars, n_events]: its per-event
+        coefficient, NaN = the event is not in the parameter's funcParsGrid list."""
+        tg = np.ascontiguousarray(target, np.int32)
+        cf = np.ascontiguousarray(np.asarray(coef, np.float64).reshape(tg.size, self.n_events))
+        self.n_shift_pars = tg.size
+        self.L.refp_fd_set_linear_shifts(self.h, int(tg.size), _p(tg), _p(cf))
+
+    def set_shift_pars(self, vals):
+        v = np.ascontiguousarray(vals, np.float64)
+        assert v.size == self.n_shift_pars
+        self.L.refp_fd_set_shift_pars(self.h, _p(v))
+
+    def kin(self):
+        """The live kinematic rows [n_events, 4] (after the last Reweight: shifted)."""
+        out = np.zeros((self.n_events, 4), np.float64)
+        self.L.refp_fd_get_kin(self.h, _p(out))
+        return out
+
     def selected(self):
         out = np.zeros(self.n_events, np.uint8)
         self.L.refp_fd_selected(self.h, _p(out))

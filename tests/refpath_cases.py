@@ -170,3 +170,49 @@ def selection_case():
     kin4_shift[2] = kin4[2] + rng.normal(0.0, 0.1, E)
     kin4_shift[3] = np.where(np.isnan(kin4[3]), np.nan, np.clip(kin4[3] + rng.normal(0.0, 0.05, E), 0.0, 1.0))
     return dict(kin4=kin4, kin4_shift=kin4_shift, cuts=cuts)
+
+
+# ---- functional ("shift") parameters: SampleHandlerFD::ApplyShifts (Samples/SampleHandlerFD.cpp:545-564) ---------------
+SHIFT_STEPS = 6
+N_SHIFT = 3
+
+
+def shift_case():
+    """Three linear functional parameters on the events of selection_case(): parameter 0 scales the first binning
+    variable (coef = the variable itself: an energy-scale shift), parameter 1 adds a per-event offset to the second
+    binning variable for ~60 % of the events, parameter 2 moves cut-only variable 2 (so events cross the selection
+    bounds).  coef[s, e] NaN = the event is not in the parameter's funcParsGrid list.  values[t, s]: the parameter values
+    per step (step 0: all zero = nominal)."""
+    sel = selection_case()
+    E = sel["kin4"].shape[1]
+    rng = np.random.default_rng(51)
+    coef = np.full((N_SHIFT, E), np.nan)
+    coef[0] = sel["kin4"][0]
+    on1 = rng.random(E) < 0.6
+    coef[1, on1] = rng.normal(0.0, 0.5, int(on1.sum()))
+    on2 = rng.random(E) < 0.5
+    coef[2, on2] = rng.uniform(0.2, 1.0, int(on2.sum()))
+    target = np.array([0, 1, 2], np.int32)
+    values = rng.normal(0.0, 0.08, (SHIFT_STEPS, N_SHIFT))
+    values[0] = 0.0
+    values[3, 2] = 0.9                      # a large move of the cut variable
+    return dict(target=target, coef=coef, values=values)
+
+
+def shift_entries(sh, n_kin_rows=2, mirror_cut_rows=True):
+    """The coefficient matrix of shift_case() as per-event entry lists (the layout of m3b_upload_linear_shifts and of the
+    oracle): n_per_event[E], shift_par[], target[], coef[] in parameter order.  Kinematic column c of the reference
+    harness is binning row c (c < n_kin_rows) AND row c of the 4-row cut-variable table the selection tests use, so a
+    shift of a binning variable is entered twice (target c and target n_kin_rows + c) when mirror_cut_rows."""
+    n_pars, E = sh["coef"].shape
+    npe, par, tgt, cf = np.zeros(E, np.uint32), [], [], []
+    for e in range(E):
+        for s in range(n_pars):
+            c = sh["coef"][s, e]
+            if np.isnan(c):
+                continue
+            col = int(sh["target"][s])
+            targets = [col, n_kin_rows + col] if (col < n_kin_rows and mirror_cut_rows) else [col if col < n_kin_rows else n_kin_rows + col]
+            for t in targets:
+                par.append(s); tgt.append(t); cf.append(c); npe[e] += 1
+    return npe, np.array(par, np.int32), np.array(tgt, np.int32), np.array(cf, np.float64)
