@@ -374,7 +374,7 @@ int m3b_batch_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, cons
   a.bin = h->d_bin; a.osc = h->use_osc ? h->d_osc : nullptr; a.osc_idx = h->d_osc_idx; a.static_w = h->d_static;
   a.norm_idx = h->d_norm_idx; a.norm_slots = h->norm_slots; a.e_pad = h->e_pad; a.n_events = h->n_events;
   a.hist = static_cast<double*>(h->bt_hist); a.n_bins = h->n_bins; a.counter = h->d_tile_counter;
-  CK(cudaFuncSetAttribute(fill_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(allow_max_dynamic_smem(fill_batch_kernel));
   const int grid = static_cast<int>(std::min<int64_t>(a.n_units, h->sm_count));
   if (h->timing) {
     if (h->tev_used + 2 > h->tev.size()) for (int i = 0; i < 2; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->tev.push_back(e); }

@@ -176,10 +176,10 @@ cudaError_t launch_binned_fill(const FillArgs& a, int grid, int smem, cudaStream
   return cudaGetLastError();
 }
 cudaError_t binned_fill_set_smem(int smem) {
-  const int cap = smem > 48 * 1024 ? smem : 48 * 1024;
-  cudaError_t e = cudaFuncSetAttribute(binned_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  (void)smem;
+  cudaError_t e = allow_max_dynamic_smem(binned_fill_kernel<false>);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(binned_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  return allow_max_dynamic_smem(binned_fill_kernel<true>);
 }
 cudaError_t binned_fill_occupancy(int smem, int* bps) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel<true>, 256, smem);

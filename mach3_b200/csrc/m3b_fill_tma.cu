@@ -409,7 +409,8 @@ cudaError_t launch_fill_tma(const FillArgs& a, int grid, int smem, cudaStream_t 
   return cudaGetLastError();
 }
 cudaError_t fill_tma_set_smem(int smem) {
-  return cudaFuncSetAttribute(fill_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  (void)smem;
+  return allow_max_dynamic_smem(fill_tma_kernel);
 }
 cudaError_t fill_tma_occupancy(int smem, int* bps) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, fill_tma_kernel, kUnit + 32, smem);

@@ -247,6 +247,21 @@ struct RetileArgs {
   float2* lin_pool;
 };
 
+// Opt-in dynamic shared memory of a kernel: always raised to the LARGEST size the device allows for it, never to the
+// size one handle happens to need.  The attribute is per function and per device, i.e. shared by every handle (and every
+// worker thread of a group) on that device: setting it per handle would let a later, smaller handle pull it below what an
+// earlier one launches with.
+template <class Kernel>
+inline cudaError_t allow_max_dynamic_smem(Kernel k) {
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, k);
+  if (e != cudaSuccess) return e;
+  int dev = 0, optin = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - static_cast<int>(fa.sharedSizeBytes));
+}
+
 // launchers (m3b_kernels.cu)
 cudaError_t launch_fill(const FillArgs& a, int variant, int grid, int smem_bytes, cudaStream_t s);
 cudaError_t launch_llh(const LlhArgs& a, cudaStream_t s);

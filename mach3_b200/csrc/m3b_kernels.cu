@@ -163,8 +163,8 @@ cudaError_t launch_fill(const FillArgs& a, int variant, int grid, int smem, cuda
   return cudaGetLastError();
 }
 cudaError_t fill_set_smem(int T, int variant, int smem) {
-  const int cap = smem > 48 * 1024 ? smem : 48 * 1024;
-  M3B_FOR_TILE(T, variant, return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, cap))
+  (void)smem;
+  M3B_FOR_TILE(T, variant, return allow_max_dynamic_smem(k))
   return cudaSuccess;
 }
 cudaError_t fill_occupancy(int T, int variant, int smem, int* bps) {

@@ -129,6 +129,10 @@ def test_adapter_binned_arm_over_the_reference_real_classes():
     idx = np.arange(E, dtype=np.int32)
     fd.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, w_before=idx,
                   w_after=E + idx, n_pool=2 * E, binned_n_per_event=ev["n_per_event"], binned_slot=ev["spline_index"])
+    # one step on the reference's CPU path first (the adapter forwards to the base class before MoveToB200): the weight
+    # pool -- the constant extra weights the adapter folds into the events' static weights -- holds its values from here on
+    sp, nm = B.proposal(w, RC.BINNED_STEPS[0])
+    fd.reweight(sp, nm, np.concatenate([B.make_osc(w, max(RC.BINNED_STEPS[0], 0)), ev["static_w"]]).astype(np.float64))
     fd.set_data(gold[f"{tag}/data"])
     fd.move_to_b200(0)
     for i, step in enumerate(RC.BINNED_STEPS):

@@ -110,12 +110,16 @@ def test_group_equals_single_handle_and_member_uploads():
         mono.set_params(sp); osh.norm_vals[:] = nm; osh.Reweight()
         od1["pars"][:] = sp; od1["norm"][:] = nm; one.Reweight()
         l1 = one.GetLikelihood()
-        for g in (gw, gm):
+        np.testing.assert_array_equal(one.handle.read_event_selected(), osh.event_selected(), err_msg="single handle: selection mask")
+        np.testing.assert_allclose(one.GetMCArray(), osh.mc, rtol=1e-12, atol=1e-12, err_msg="single handle vs oracle")
+        assert l1 == pytest.approx(osh.GetLikelihood(), rel=1e-10, abs=1e-9)
+        for name, g in (("whole-workload uploads", gw), ("per-member uploads", gm)):
             g.step(sp, nm)
             lg = g.llh()
-            np.testing.assert_allclose(g.read_hist()[0], one.GetMCArray(), rtol=1e-12, atol=1e-12)
-            assert lg == pytest.approx(l1, rel=1e-11, abs=1e-10)
-        assert l1 == pytest.approx(osh.GetLikelihood(), rel=1e-10, abs=1e-9)
+            mask = np.concatenate([g.member(i).read_event_selected() for i in range(g.n) if g.member(i).n_events])
+            np.testing.assert_array_equal(mask, osh.event_selected(), err_msg=f"{name}: selection mask, step {step}")
+            np.testing.assert_allclose(g.read_hist()[0], osh.mc, rtol=1e-12, atol=1e-12, err_msg=f"{name}: histogram, step {step}")
+            assert lg == pytest.approx(l1, rel=1e-11, abs=1e-10), name
     gw.close(); gm.close()
     O.set_multithread(True)
 
