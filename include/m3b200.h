@@ -63,7 +63,9 @@ enum {
   M3B_FLAG_KEEP_KINEMATICS    = 2, /* keep kinematic variables on the device so bins can be recomputed */
   M3B_FLAG_NO_FUSED_LLH       = 4, /* never fuse the LLH into the fill kernel (multi-GPU callers)      */
   M3B_FLAG_NO_BATCH_KERNEL    = 8, /* m3b_step_batch always runs sequential single-set launches         */
-  M3B_FLAG_BATCH_KERNEL_V1    = 16 /* m3b_step_batch uses the first-generation batched kernel (A/B)     */
+  M3B_FLAG_BATCH_KERNEL_V1    = 16, /* m3b_step_batch uses the first-generation batched kernel (A/B)     */
+  M3B_FLAG_NO_SPIN_LLH        = 32  /* m3b_llh waits with cudaStreamSynchronize instead of polling the     */
+                                    /* step's sequence word in mapped host memory                          */
 };
 
 typedef struct {

@@ -77,6 +77,7 @@ M3B_API void m3b_destroy(m3b_handle* h) {
     if (h->step_ev[i]) cudaEventDestroy(h->step_ev[i]);
   }
   if (h->h_llh) cudaFreeHost(h->h_llh);
+  if (h->h_seq) cudaFreeHost(h->h_seq);
   if (h->h_batch) cudaFreeHost(h->h_batch);
   for (void* p : {h->bt_dx, h->bt_rowoff, h->bt_val, h->bt_rowlist, h->bt_norm, h->bt_sigs, h->bt_hist, h->bt_llh, h->bt_slot, h->bt_group}) if (p) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -469,6 +470,9 @@ static int upload_binning_body(m3b_handle* h, int32_t n_samples, const int32_t* 
   CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_llh), sizeof(double) * (1 + n_samples), cudaHostAllocMapped));
   memset(h->h_llh, 0, sizeof(double) * (1 + n_samples));
   CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_llh_dev), h->h_llh, 0));
+  CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_seq), 64, cudaHostAllocMapped));
+  memset(h->h_seq, 0, 64);
+  CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_seq_dev), h->h_seq, 0));
   h->launch_ready = false;
   return M3B_OK;
 }
@@ -1059,6 +1063,11 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     a.guard_x2 = guard_env;
   }
   a.ticket = h->d_ticket; a.status = h->d_status; a.llh_dev = h->d_llh; a.llh_host = h->llh_host_override ? h->llh_host_override : h->h_llh_dev;
+  // the -lnL of this step is announced through the sequence word when it goes to the handle's own mirror
+  const bool announce = !h->llh_host_override && !(h->cfg.flags & M3B_FLAG_NO_SPIN_LLH) && mode != kWeightsOnly;
+  const unsigned long long seq = announce ? ++h->seq_issued : 0ull;
+  a.llh_seq_host = (announce && mode == kFused) ? h->h_seq_dev : nullptr; a.llh_seq = seq;
+  if (mode != kWeightsOnly) h->seq_wait = (announce && (mode == kFused || (mode == kPeer && h->peer_pull))) ? seq : 0ull;
   a.evt_spline_w = h->d_evt_spline_w; a.evt_total_w = h->d_evt_total_w;
   a.trace = h->d_trace;
   if (mode == kFused) {
@@ -1100,6 +1109,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     LlhArgs l{};
     l.data = h->d_data; l.n_bins = h->n_bins; l.n_samples = h->n_samples;
     l.test_stat = h->test_stat; l.llh_dev = h->d_llh; l.llh_host = h->h_llh_dev;
+    l.llh_seq_host = announce ? h->h_seq_dev : nullptr; l.llh_seq = seq;
     l.peer_world = h->peer_world; l.epoch = h->peer_epoch;
     for (int r = 0; r < h->peer_world; ++r) { l.peer_hist[r] = h->peer_partial[par][r]; l.peer_flag[r] = h->peer_flag[0][r]; }
     l.hist_out = mc; l.w2_out = w2; l.w2_live = w2_live ? 1 : 0; l.status = h->d_status;
@@ -1271,6 +1281,7 @@ static int step_batch_impl(m3b_handle* h, int32_t n_sets, const double* spline_p
   }
   // m3b_llh after a batch returns the last set's value
   for (size_t k = 0; k < slot; ++k) h->h_llh[k] = h->h_batch[slot * (n_sets - 1) + k];
+  h->seq_wait = 0;
   return M3B_OK;
 }
 
@@ -1310,6 +1321,7 @@ M3B_API int m3b_llh_from_hist(m3b_handle* h) {
   l.hist = h->d_hw[h->cur]; l.w2 = h->d_w2_frozen; l.data = h->d_data; l.sample_start = h->d_sample_start;
   l.n_bins = h->n_bins; l.n_samples = h->n_samples; l.test_stat = h->test_stat;
   l.llh_dev = h->d_llh; l.llh_host = h->h_llh_dev; l.status = h->d_status;
+  if (!(h->cfg.flags & M3B_FLAG_NO_SPIN_LLH)) { l.llh_seq_host = h->h_seq_dev; l.llh_seq = ++h->seq_issued; h->seq_wait = l.llh_seq; }
   CK(launch_llh(l, h->stream));
   ++h->launches;
   return M3B_OK;
@@ -1325,8 +1337,20 @@ M3B_API int m3b_synchronize(m3b_handle* h) {
 M3B_API int m3b_llh(m3b_handle* h, double* total, double* per_sample) {
   REQUIRE(h && total, M3B_ERR_INVALID, "m3b_llh: null argument");
   REQUIRE(h->steps > 0, M3B_ERR_STATE, "m3b_llh: no step yet");
+  bool seen = false;
+  if (h->seq_wait != 0) {
+    // poll the sequence word the likelihood kernel writes behind -lnL (mapped host memory).  Bounded: after ~2 s fall back
+    // to the stream wait, which also surfaces a device fault.
+    volatile unsigned long long* sq = h->h_seq;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 1;; ++spin) {
+      if (*sq >= h->seq_wait) { seen = true; break; }
+      __builtin_ia32_pause();
+      if ((spin & 0xfffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) break;
+    }
+  }
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  if (!seen) CK(cudaStreamSynchronize(h->stream));
   if (h->h_llh[0] != h->h_llh[0]) {     // NaN: an exchange time-out, or a case in which the reference throws?
     int32_t st = 0;
     CK(cudaMemcpy(&st, h->d_status, sizeof st, cudaMemcpyDeviceToHost));

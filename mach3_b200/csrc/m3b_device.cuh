@@ -171,7 +171,8 @@ constexpr int kMaxSamples = 64;
 
 static __device__ void block_llh(const double* __restrict__ hist, const double* __restrict__ w2,
                           const double* __restrict__ data, const int32_t* __restrict__ sample_start,
-                          int n_samples, int ts, double* llh_dev, double* llh_host, double* scratch, int32_t* status) {
+                          int n_samples, int ts, double* llh_dev, double* llh_host, double* scratch, int32_t* status,
+                          unsigned long long* seq_host = nullptr, unsigned long long seq = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   bool thrown = false;
   for (int s = 0; s < n_samples; ++s) {
@@ -214,7 +215,11 @@ static __device__ void block_llh(const double* __restrict__ hist, const double* 
       if (llh_host) llh_host[1 + s] = v;
     }
     llh_dev[0] = tot;
-    if (llh_host) llh_host[0] = tot;     // mapped host memory; visible to the host when the kernel has completed
+    if (llh_host) llh_host[0] = tot;     // mapped host memory
+    if (llh_host && seq_host) {          // publish: the host polls this word instead of waiting for the kernel to retire
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(seq_host) = seq;
+    }
   }
 }
 
@@ -286,7 +291,8 @@ __device__ __forceinline__ void finish_block(const FillArgs& a, const double* s_
   if (!a.fuse_llh) { if (tid == 0) *a.ticket = 0u; return; }
 
   if (tid == 0 && a.trace) a.trace[8 * 4000 + 0] = globaltimer_ns();      // last block: ticket won
-  block_llh(a.hist, a.w2_frozen, a.data, a.sample_start_inline, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, scratch, a.status);
+  block_llh(a.hist, a.w2_frozen, a.data, a.sample_start_inline, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, scratch, a.status,
+            a.llh_seq_host, a.llh_seq);
   if (tid == 0 && a.trace) a.trace[8 * 4000 + 1] = globaltimer_ns();      // last block: -lnL written
   // prepare the next step: zero its histogram(s), re-arm the ticket
   if (a.hist_next) for (int i = tid; i < a.n_bins; i += NT) a.hist_next[i] = 0.;

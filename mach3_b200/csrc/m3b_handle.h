@@ -5,6 +5,7 @@
 #include "m3b_internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -109,6 +110,10 @@ struct m3b_handle {
   double* d_llh = nullptr;
   double* h_llh = nullptr;                // mapped pinned
   double* h_llh_dev = nullptr;            // device alias of h_llh
+  // the step's sequence word (mapped pinned): the kernel that writes -lnL sets it to seq_issued afterwards; m3b_llh polls
+  // it instead of waiting for the stream (the likelihood kernel's retirement and the driver's wake-up are off the path)
+  unsigned long long* h_seq = nullptr; unsigned long long* h_seq_dev = nullptr;
+  unsigned long long seq_issued = 0, seq_wait = 0;      // seq_wait == 0: the last step published no sequence word
   int test_stat = 0;
   bool first_time_w2 = true;
   bool last_w2_live = false;

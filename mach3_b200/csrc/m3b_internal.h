@@ -137,6 +137,8 @@ struct FillArgs {
   int32_t guard_x2;            // TMA kernel: whole tile rows are grabbed while more than guard_x2/2 * grid * g units are left
   double* llh_dev;             // [1+n_samples]
   double* llh_host;            // mapped pinned mirror (nullptr = none)
+  unsigned long long* llh_seq_host;   // mapped host word: set to llh_seq after llh_host is written (m3b_llh polls it), or nullptr
+  unsigned long long llh_seq;
   // optional per-event outputs
   float* evt_spline_w;
   float* evt_total_w;
@@ -168,6 +170,7 @@ struct LlhArgs {
   const int32_t* sample_start;
   int32_t n_bins, n_samples, test_stat;
   double* llh_dev; double* llh_host;
+  unsigned long long* llh_seq_host; unsigned long long llh_seq;      // see FillArgs
   // peer (pull) mode: every rank reads all ranks' partial histograms over NVLink peer memory, in rank order
   int32_t peer_world; unsigned int epoch;
   const double* peer_hist[8];        // rank r's exported partial {mc[n_bins], w2[n_bins]} of this epoch's parity

@@ -179,7 +179,7 @@ cudaError_t fill_occupancy(int T, int variant, int smem, int* bps) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) llh_kernel(const __grid_constant__ LlhArgs a) {
   __shared__ double s_part[kMaxSamples * 32];
-  block_llh(a.hist, a.w2, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, s_part, a.status);
+  block_llh(a.hist, a.w2, a.data, a.sample_start, a.n_samples, a.test_stat, a.llh_dev, a.llh_host, s_part, a.status, a.llh_seq_host, a.llh_seq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -208,7 +208,11 @@ __global__ void __launch_bounds__(512) llh_pull_kernel(const __grid_constant__ L
   }
   __syncthreads();
   if (!s_ok) {
-    if (tid == 0 && blockIdx.x == 0) { atomicOr(a.status, kStatusPeerTimeout); a.llh_dev[0] = nan(""); if (a.llh_host) a.llh_host[0] = nan(""); }
+    if (tid == 0 && blockIdx.x == 0) {
+      atomicOr(a.status, kStatusPeerTimeout); a.llh_dev[0] = nan("");
+      if (a.llh_host) a.llh_host[0] = nan("");
+      if (a.llh_host && a.llh_seq_host) { __threadfence_system(); *reinterpret_cast<volatile unsigned long long*>(a.llh_seq_host) = a.llh_seq; }
+    }
     return;
   }
   const int per = (a.n_bins + gridDim.x - 1) / gridDim.x;
@@ -260,6 +264,10 @@ __global__ void __launch_bounds__(512) llh_pull_kernel(const __grid_constant__ L
     }
     a.llh_dev[0] = tot;
     if (a.llh_host) a.llh_host[0] = tot;
+    if (a.llh_host && a.llh_seq_host) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(a.llh_seq_host) = a.llh_seq;
+    }
     *a.ticket = 0u;
   }
 }

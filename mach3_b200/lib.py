@@ -17,6 +17,7 @@ FLAG_KEEP_KINEMATICS = 2
 FLAG_NO_FUSED_LLH = 4
 FLAG_NO_BATCH_KERNEL = 8
 FLAG_BATCH_KERNEL_V1 = 16
+FLAG_NO_SPIN_LLH = 32
 
 #: every symbol include/m3b200.h declares
 EXPORTS = (
