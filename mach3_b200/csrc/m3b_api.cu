@@ -53,11 +53,11 @@ M3B_API int m3b_create(const m3b_config* cfg, m3b_handle** out) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   CK(dev_alloc(h, &h->d_ticket, 1));
-  CK(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
+  CK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
   CK(dev_alloc(h, &h->d_tile_counter, 1));
-  CK(cudaMemset(h->d_tile_counter, 0, sizeof(unsigned int)));
+  CK(cudaMemsetAsync(h->d_tile_counter, 0, sizeof(unsigned int), h->stream));
   CK(dev_alloc(h, &h->d_status, 1));
-  CK(cudaMemset(h->d_status, 0, sizeof(int32_t)));
+  CK(cudaMemsetAsync(h->d_status, 0, sizeof(int32_t), h->stream));
   for (int i = 0; i < m3b_handle::kRing; ++i) CK(cudaEventCreateWithFlags(&h->step_ev[i], cudaEventDisableTiming));
   *out = h;
   return M3B_OK;
@@ -459,14 +459,14 @@ static int upload_binning_body(m3b_handle* h, int32_t n_samples, const int32_t* 
   CK(dev_upload(h, &h->d_edges, h->b_edges));
   for (int k = 0; k < 2; ++k) {
     CK(dev_alloc(h, &h->d_hw[k], static_cast<size_t>(2) * h->n_bins));
-    CK(cudaMemset(h->d_hw[k], 0, sizeof(double) * 2 * h->n_bins));
+    CK(cudaMemsetAsync(h->d_hw[k], 0, sizeof(double) * 2 * h->n_bins, h->stream));
     h->mc_zero[k] = h->w2_zero[k] = true;
   }
   h->d_w2_frozen = h->d_hw[0] + h->n_bins;
   CK(dev_alloc(h, &h->d_data, static_cast<size_t>(h->n_bins)));
-  CK(cudaMemset(h->d_data, 0, sizeof(double) * h->n_bins));
+  CK(cudaMemsetAsync(h->d_data, 0, sizeof(double) * h->n_bins, h->stream));
   CK(dev_alloc(h, &h->d_llh, static_cast<size_t>(1 + n_samples)));
-  CK(cudaMemset(h->d_llh, 0, sizeof(double) * (1 + n_samples)));
+  CK(cudaMemsetAsync(h->d_llh, 0, sizeof(double) * (1 + n_samples), h->stream));
   CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_llh), sizeof(double) * (1 + n_samples), cudaHostAllocMapped));
   memset(h->h_llh, 0, sizeof(double) * (1 + n_samples));
   CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->h_llh_dev), h->h_llh, 0));
@@ -555,7 +555,7 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
     }
     CK(dev_alloc(h, &h->d_osc, static_cast<size_t>(h->n_osc)));
     std::vector<float> ones(static_cast<size_t>(h->n_osc), 1.f);
-    CK(cudaMemcpy(h->d_osc, ones.data(), sizeof(float) * h->n_osc, cudaMemcpyHostToDevice));
+    CK(copy_sync(h, h->d_osc, ones.data(), sizeof(float) * h->n_osc, cudaMemcpyHostToDevice));
   }
   if (static_w) {
     std::vector<float> sw(static_cast<size_t>(EP), 1.f);
@@ -599,8 +599,8 @@ M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* c
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   if (n_cuts == 0) {                        // selection removed: every event is back in
-    if (h->d_bin_raw != h->d_bin) CK(cudaMemcpy(h->d_bin, h->d_bin_raw, sizeof(int32_t) * h->e_pad, cudaMemcpyDeviceToDevice));
-    if (h->d_selected) CK(cudaMemset(h->d_selected, 1, static_cast<size_t>(h->e_pad)));
+    if (h->d_bin_raw != h->d_bin) CK(copy_sync(h, h->d_bin, h->d_bin_raw, sizeof(int32_t) * h->e_pad, cudaMemcpyDeviceToDevice));
+    if (h->d_selected) CK(cudaMemsetAsync(h->d_selected, 1, static_cast<size_t>(h->e_pad), h->stream));
     h->n_cuts = 0;
     return M3B_OK;
   }
@@ -614,9 +614,9 @@ M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* c
   for (int k = 0; k < n_cuts; ++k) { const int j = fill[cut_sample[k]]++; var[j] = cut_var[k]; lo[j] = lower[k]; hi[j] = upper[k]; }
   if (h->d_bin_raw == h->d_bin) {           // first selection on this handle: keep FindGlobalBin's answer aside
     CK(dev_alloc(h, &h->d_bin_raw, static_cast<size_t>(h->e_pad)));
-    CK(cudaMemcpy(h->d_bin_raw, h->d_bin, sizeof(int32_t) * h->e_pad, cudaMemcpyDeviceToDevice));
+    CK(copy_sync(h, h->d_bin_raw, h->d_bin, sizeof(int32_t) * h->e_pad, cudaMemcpyDeviceToDevice));
     CK(dev_alloc(h, &h->d_selected, static_cast<size_t>(h->e_pad)));
-    CK(cudaMemset(h->d_selected, 0, static_cast<size_t>(h->e_pad)));
+    CK(cudaMemsetAsync(h->d_selected, 0, static_cast<size_t>(h->e_pad), h->stream));
   }
   CK(dev_upload(h, &h->d_cut_start, start));
   CK(dev_upload(h, &h->d_cut_var, var));
@@ -624,10 +624,10 @@ M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* c
   CK(dev_upload(h, &h->d_cut_hi, hi));
   if (n_vars > 0) {
     if (n_vars != h->n_sel_vars) CK(dev_alloc(h, &h->d_sel_vals, static_cast<size_t>(n_vars) * h->n_events));
-    CK(cudaMemcpy(h->d_sel_vals, values, sizeof(double) * n_vars * h->n_events, cudaMemcpyHostToDevice));
+    CK(copy_sync(h, h->d_sel_vals, values, sizeof(double) * n_vars * h->n_events, cudaMemcpyHostToDevice));
   }
   REQUIRE(!h->d_sh_start || n_vars == h->n_sel_vars, M3B_ERR_STATE, "m3b_upload_selection: upload the selection before m3b_upload_linear_shifts");
-  if (h->d_sel_vals_nom && n_vars > 0) CK(cudaMemcpy(h->d_sel_vals_nom, h->d_sel_vals, sizeof(double) * n_vars * h->n_events, cudaMemcpyDeviceToDevice));
+  if (h->d_sel_vals_nom && n_vars > 0) CK(copy_sync(h, h->d_sel_vals_nom, h->d_sel_vals, sizeof(double) * n_vars * h->n_events, cudaMemcpyDeviceToDevice));
   h->n_cuts = n_cuts; h->n_sel_vars = n_vars; h->sel_uses_kin = uses_kin;
   int rc = run_selection(h);
   if (rc != M3B_OK) return rc;
@@ -688,19 +688,19 @@ M3B_API int m3b_upload_linear_shifts(m3b_handle* h, int32_t n_shift_pars, int64_
   CK(dev_alloc(h, &h->d_sh_target, static_cast<size_t>(total)));
   CK(dev_alloc(h, &h->d_sh_coef, static_cast<size_t>(total)));
   if (total > 0) {
-    CK(cudaMemcpy(h->d_sh_par, shift_par, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_sh_target, target, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_sh_coef, coef, sizeof(double) * total, cudaMemcpyHostToDevice));
+    CK(copy_sync(h, h->d_sh_par, shift_par, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
+    CK(copy_sync(h, h->d_sh_target, target, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
+    CK(copy_sync(h, h->d_sh_coef, coef, sizeof(double) * total, cudaMemcpyHostToDevice));
   }
   // the nominal values every step starts from (ResetShifts)
   CK(dev_alloc(h, &h->d_kin_nom, static_cast<size_t>(h->n_events) * h->kin_dims));
-  CK(cudaMemcpy(h->d_kin_nom, h->d_kin, sizeof(double) * h->n_events * h->kin_dims, cudaMemcpyDeviceToDevice));
+  CK(copy_sync(h, h->d_kin_nom, h->d_kin, sizeof(double) * h->n_events * h->kin_dims, cudaMemcpyDeviceToDevice));
   if (h->n_sel_vars > 0) {
     CK(dev_alloc(h, &h->d_sel_vals_nom, static_cast<size_t>(h->n_events) * h->n_sel_vars));
-    CK(cudaMemcpy(h->d_sel_vals_nom, h->d_sel_vals, sizeof(double) * h->n_events * h->n_sel_vars, cudaMemcpyDeviceToDevice));
+    CK(copy_sync(h, h->d_sel_vals_nom, h->d_sel_vals, sizeof(double) * h->n_events * h->n_sel_vars, cudaMemcpyDeviceToDevice));
   }
   CK(dev_alloc(h, &h->d_shift_theta, static_cast<size_t>(n_shift_pars)));
-  CK(cudaMemset(h->d_shift_theta, 0, sizeof(double) * n_shift_pars));
+  CK(cudaMemsetAsync(h->d_shift_theta, 0, sizeof(double) * n_shift_pars, h->stream));
   h->n_shift_pars = n_shift_pars;
   return M3B_OK;
 }
@@ -1179,7 +1179,7 @@ static int ensure_standalone_events(m3b_handle* h) {
   h->n_tiles = (h->n_events + T - 1) / T;
   h->e_pad = h->n_tiles * T;
   CK(dev_alloc(h, &h->d_bin, static_cast<size_t>(h->e_pad)));
-  CK(cudaMemset(h->d_bin, 0xFF, sizeof(int32_t) * h->e_pad));       // bin -1: nothing is ever filled
+  CK(cudaMemsetAsync(h->d_bin, 0xFF, sizeof(int32_t) * h->e_pad, h->stream));       // bin -1: nothing is ever filled
   h->d_bin_raw = h->d_bin;
   if (!h->d_evt_spline_w) {
     CK(dev_alloc(h, &h->d_evt_spline_w, static_cast<size_t>(h->e_pad)));
@@ -1271,7 +1271,7 @@ static int step_batch_impl(m3b_handle* h, int32_t n_sets, const double* spline_p
   if (any_nan) {
     int32_t st = 0;
     CK(cudaMemcpy(&st, h->d_status, sizeof st, cudaMemcpyDeviceToHost));
-    if (st != 0) CK(cudaMemset(h->d_status, 0, sizeof st));
+    if (st != 0) CK(cudaMemsetAsync(h->d_status, 0, sizeof st, h->stream));
     if (st & 2) return fail(h, M3B_ERR_MATH, "m3b_step_batch: negative square root in the Barlow-Beeston coefficient (the reference throws "
                                              "MaCh3Exception here, Samples/SampleHandlerBase.cpp:64-67)");
   }
@@ -1354,7 +1354,7 @@ M3B_API int m3b_llh(m3b_handle* h, double* total, double* per_sample) {
   if (h->h_llh[0] != h->h_llh[0]) {     // NaN: an exchange time-out, or a case in which the reference throws?
     int32_t st = 0;
     CK(cudaMemcpy(&st, h->d_status, sizeof st, cudaMemcpyDeviceToHost));
-    if (st != 0) CK(cudaMemset(h->d_status, 0, sizeof st));
+    if (st != 0) CK(cudaMemsetAsync(h->d_status, 0, sizeof st, h->stream));
     if (st & 1) return fail(h, M3B_ERR_PEER, "m3b_llh: peer histogram exchange timed out");
     if (st & 2) return fail(h, M3B_ERR_MATH, "m3b_llh: negative square root in the Barlow-Beeston coefficient (the reference throws "
                                              "MaCh3Exception here, Samples/SampleHandlerBase.cpp:64-67)");
@@ -1410,13 +1410,13 @@ int m3b_peer_alloc(m3b_handle* h) {
     const size_t total_d = 2 * part_d + 16;
     double* base = nullptr;
     CK(dev_alloc(h, &base, total_d));
-    CK(cudaMemset(base, 0, total_d * sizeof(double)));
+    CK(cudaMemsetAsync(base, 0, total_d * sizeof(double), h->stream));
     h->d_partial[0] = base; h->d_partial[1] = base + part_d;
     h->d_flags[0] = reinterpret_cast<unsigned int*>(base + 2 * part_d);
     h->d_flags[1] = h->d_flags[0];
     CK(dev_alloc(h, &h->d_llh_partial, static_cast<size_t>(kLlhPullMaxBlocks) * std::max(1, h->n_samples)));
     CK(dev_alloc(h, &h->d_llh_ticket, 1));
-    CK(cudaMemset(h->d_llh_ticket, 0, sizeof(unsigned int)));
+    CK(cudaMemsetAsync(h->d_llh_ticket, 0, sizeof(unsigned int), h->stream));
   }
   return M3B_OK;
 }
@@ -1484,7 +1484,7 @@ M3B_API int m3b_block_trace(m3b_handle* h, uint64_t* out, int32_t* grid) {
   CK(cudaSetDevice(h->device));
   if (!h->d_trace) {
     CK(dev_alloc(h, &h->d_trace, static_cast<size_t>(8) * 4096));
-    CK(cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * 8 * 4096));
+    CK(cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * 8 * 4096, h->stream));
   }
   if (grid) *grid = h->grid;
   if (out) {

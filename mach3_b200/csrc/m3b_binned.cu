@@ -264,7 +264,7 @@ static int upload_binned_impl(m3b_handle* h, int32_t n_params, int32_t max_knots
   } else {
     float4* dc = nullptr;
     CK(dev_alloc(h, &dc, static_cast<size_t>(n_coef_dev)));
-    CK(cudaMemcpy(dc, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
+    CK(copy_sync(h, dc, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
     h->d_bcoef = dc;
     CK(dev_upload(h, &h->d_bx, xs));
     CK(dev_alloc(h, &h->d_bw, static_cast<size_t>(n_act_pad)));
@@ -389,7 +389,7 @@ M3B_API int m3b_upload_event_weights_f64(m3b_handle* h, int64_t n_events, const 
   std::vector<double> sw(static_cast<size_t>(h->e_pad), 1.0);
   std::copy(static_w, static_w + n_events, sw.begin());
   if (!h->d_static_d) CK(dev_alloc(h, &h->d_static_d, sw.size()));
-  CK(cudaMemcpy(h->d_static_d, sw.data(), sizeof(double) * sw.size(), cudaMemcpyHostToDevice));
+  CK(copy_sync(h, h->d_static_d, sw.data(), sizeof(double) * sw.size(), cudaMemcpyHostToDevice));
   return M3B_OK;
 }
 M3B_API int m3b_upload_osc_f64(m3b_handle* h, const double* osc_w, int64_t n) {

@@ -218,11 +218,19 @@ static inline cudaError_t dev_alloc(m3b_handle* h, Tp** p, size_t n) {
   if (e == cudaSuccess) { h->allocs.push_back(*p); h->device_bytes += n * sizeof(Tp); }
   return e;
 }
+// Set-up copies go through the HANDLE'S stream and are waited for: the handle's kernels run on a non-blocking stream,
+// which is not ordered with the legacy default stream a plain cudaMemcpy uses (and a pageable host-to-device cudaMemcpy
+// may return before its DMA has landed, a device-to-device one before it has run at all).
+static inline cudaError_t copy_sync(m3b_handle* h, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+  if (bytes == 0) return cudaSuccess;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, h->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(h->stream);
+}
 template <class Tp>
 static inline cudaError_t dev_upload(m3b_handle* h, Tp** p, const std::vector<Tp>& v) {
   cudaError_t e = dev_alloc(h, p, v.size());
   if (e != cudaSuccess) return e;
-  if (!v.empty()) e = cudaMemcpy(*p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice);
-  return e;
+  return copy_sync(h, *p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice);
 }
 
