@@ -397,6 +397,7 @@ def measure_monolith(args, w, world, rank, local, dist, torch, W, K, want_cpu_ba
     h.llh()
     kern_ms, kern_n = h.kernel_time()
     h.set_timing(False)
+    info_value = h.info()          # launch configuration of the value / roofline passes (the e2e pass adds staging slots)
 
     # ---------------- e2e: host buffers in, scalar out, every step ------------------------------
     for k in range(min(W, 5)):
@@ -429,15 +430,15 @@ def measure_monolith(args, w, world, rank, local, dist, torch, W, K, want_cpu_ba
     alg_bytes_local = n_local * w.bytes_per_event        # SURVEY §8d per-event figure x events of one launch
     achieved = alg_bytes_local / (kern_avg * 1e-3) / 1e9
     step_bytes = 12 * w.n_params + 4 * w.n_norm_params
-    traffic, traffic_src = committed_traffic(w, world, info)
+    traffic, traffic_src = committed_traffic(w, world, info_value)
     rec = {
         "metric": METRIC,
         "value": E / (ms_step * 1e-3), "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "llh_evals_per_s": 1e3 / ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": w.name, "events": E, "events_per_gpu": n_local, "responses_per_event": w.n_params,
-                   "bins": w.n_bins, "tile_events": info.tile_events, "grid_blocks": info.grid_blocks,
-                   "smem_bytes": info.smem_bytes, "tma_stages": info.tma_stages, "exchange": exchange,
+                   "bins": w.n_bins, "tile_events": info_value.tile_events, "grid_blocks": info_value.grid_blocks,
+                   "smem_bytes": info_value.smem_bytes, "tma_stages": info_value.tma_stages, "exchange": exchange,
                    "step": "m3b_step (async) + m3b_llh (blocks) every step; inputs resident in HBM",
                    "l2": "inputs larger than L2: %.0f MB of coefficient rows stream per step per GPU, fresh "
                          "proposal (different segments) every step" % (info.active_bytes_per_step / 1e6),
@@ -452,6 +453,7 @@ def measure_monolith(args, w, world, rank, local, dist, torch, W, K, want_cpu_ba
                      "frac_of_step": kern_avg / ms_step},
         "e2e": {"value": E / (ms_e2e / K * 1e-3), "unit": "events/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(4 * n_local + step_bytes), "d2h_bytes_per_step": int(8 * (1 + w.n_samples)),
+                "smem_bytes": info.smem_bytes, "tma_stages": info.tma_stages,
                 "api": "m3b_step(host pars, host norms, host osc weights in pinned memory) + m3b_llh(); the osc weights "
                        "are streamed over PCIe by the fill kernel's own bulk copies (no separate H2D pass)"},
         "gpu_launches": int(launches), "clocks": clk,
@@ -803,7 +805,7 @@ def measure_cfg5(args, local=0, want_cpu=True):
                                               "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / (ms_scan / max(n_scan, 1))}},
            "roofline": {"bound": "fp32 issue (CUDA cores; no contraction, so no tensor cores)", "achieved": fp_instr / (kms * 1e-3) / 1e12,
                         "peak": peak_issue / 1e12, "peak_source": "148 SMs x 128 FP32 lanes x max SM clock", "unit": "T FP32 instr/s",
-                        "frac": fp_instr / (kms * 1e-3) / peak_issue, "kernel": "m3b::fill_batch_kernel", "kernel_ms": kms, "traffic": None,
+                        "frac": fp_instr / (kms * 1e-3) / peak_issue, "kernel": "m3b::fill_batch2_kernel", "kernel_ms": kms, "traffic": None,
                         "algorithmic_instr_per_launch": fp_instr},
            "e2e": {"value": n_sets / t_b, "unit": "LLH evals/s", "h2d_bytes_per_step": int(n_sets * (8 * w.n_params + 8 * w.n_norm_params)),
                    "d2h_bytes_per_step": int(n_sets * 8 * (1 + w.n_samples))},
@@ -821,7 +823,34 @@ def measure_cfg5(args, local=0, want_cpu=True):
 # the incumbent GPU path: the reference's own MaCh3_CUDA build (SMonolith + Splines/gpuSplineUtils.cu kernels compiled
 # from the reference's sources, weights copied back every step, FillArray_MP + GetLikelihood on the host cores)
 # ---------------------------------------------------------------------------------------------
+class _QuietStdout:
+    """The reference's CUDA code printf()s its allocations: keep the C-level stdout of this process clean (bench.py's
+    contract is ONE JSON line on stdout)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved); os.close(self.null)
+        return False
+
+
 def measure_incumbent(local=0):
+    with _QuietStdout():
+        return _measure_incumbent(local)
+
+
+def _measure_incumbent(local=0):
     from mach3_b200 import synth
     from oracle import ref_path_binding as RP
     w = synth.CFG2

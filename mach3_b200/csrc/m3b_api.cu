@@ -879,12 +879,14 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
 #endif
     if (h->binned) {
       // BinnedSplineHandler path: evaluate the non-flat splines, then gather/fill (m3b_binned.cu)
+      // a privatised histogram only while it is small: beyond 48 KB per block it costs more (resident blocks, L1 left for
+      // the weight gathers) than the global f64 reductions it saves
       int smem = binned_fill_smem_bytes(a, true, w2_live);
-      h->hist_in_smem = smem <= 200 * 1024;
+      h->hist_in_smem = smem <= 48 * 1024;
       if (!h->hist_in_smem) smem = binned_fill_smem_bytes(a, false, w2_live);
       CK(binned_fill_set_smem(smem));
       int bps = 0;
-      CK(binned_fill_occupancy(smem, &bps));
+      CK(binned_fill_occupancy(smem, h->f64, &bps));
       REQUIRE(bps > 0, M3B_ERR_CUDA, "step: binned fill kernel does not fit on an SM");
       h->smem = smem;
       h->grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_wtiles + 7) / 8, static_cast<int64_t>(bps) * h->sm_count)));

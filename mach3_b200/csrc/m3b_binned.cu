@@ -95,7 +95,7 @@ int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
 }
 
 template <bool F64>
-__global__ void __launch_bounds__(256) binned_fill_kernel(const __grid_constant__ FillArgs a) {
+__global__ void __launch_bounds__(256, F64 ? 2 : 4) binned_fill_kernel(const __grid_constant__ FillArgs a) {
   using R = typename std::conditional<F64, double, float>::type;      // M3::float_t of the build
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -117,7 +117,13 @@ __global__ void __launch_bounds__(256) binned_fill_kernel(const __grid_constant_
   const R* oscp = F64 ? reinterpret_cast<const R*>(a.osc_d) : reinterpret_cast<const R*>(a.osc);
   const R* statp = F64 ? reinterpret_cast<const R*>(a.static_d) : reinterpret_cast<const R*>(a.static_w);
 
-  for (int64_t wt = static_cast<int64_t>(blockIdx.x) * 8 + warp; wt < a.n_wtiles; wt += static_cast<int64_t>(gridDim.x) * 8) {
+  // every block owns a CONTIGUOUS run of warp tiles: consecutive iterations of a block then revisit the sectors its
+  // previous iteration pulled into L1 (the events are walked in spline-grid-cell order, so neighbouring tiles gather from
+  // neighbouring weights); a grid-strided walk would jump a whole grid of tiles ahead and find nothing cached
+  const int64_t tiles_per_block = (a.n_wtiles + gridDim.x - 1) / gridDim.x;
+  const int64_t wt_begin = static_cast<int64_t>(blockIdx.x) * tiles_per_block;
+  const int64_t wt_end = wt_begin + tiles_per_block < a.n_wtiles ? wt_begin + tiles_per_block : a.n_wtiles;
+  for (int64_t wt = wt_begin + warp; wt < wt_end; wt += 8) {
     const WTile d = a.wtiles[wt];
     // events are processed in the order of their spline-grid cell (a.perm, built at upload): the 32 lanes of a warp --
     // and the 8 warps of the block -- then gather from the same few sectors of every parameter's weight row
@@ -181,8 +187,9 @@ cudaError_t binned_fill_set_smem(int smem) {
   if (e != cudaSuccess) return e;
   return allow_max_dynamic_smem(binned_fill_kernel<true>);
 }
-cudaError_t binned_fill_occupancy(int smem, int* bps) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel<true>, 256, smem);
+cudaError_t binned_fill_occupancy(int smem, bool f64, int* bps) {
+  return f64 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel<true>, 256, smem)
+             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel<false>, 256, smem);
 }
 
 }  // namespace m3b

@@ -287,7 +287,7 @@ int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
 cudaError_t launch_binned_eval(const FillArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_binned_fill(const FillArgs& a, int grid, int smem_bytes, cudaStream_t s);
 cudaError_t binned_fill_set_smem(int smem_bytes);
-cudaError_t binned_fill_occupancy(int smem_bytes, int* blocks_per_sm);
+cudaError_t binned_fill_occupancy(int smem_bytes, bool f64, int* blocks_per_sm);
 int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
 
 }  // namespace m3b
