@@ -781,6 +781,13 @@ def measure_cfg5(args, local=0, want_cpu=True):
     t_b = (time.perf_counter() - t1) / K
     msb, nb = h.kernel_time()
     kms = msb / max(nb, 1)
+    # the first-generation kernel on the same handle and batches (A/B)
+    h.set_flags(set_mask=lib.FLAG_BATCH_KERNEL_V1)
+    h.step_batch(*bs[0]); h.kernel_time()
+    for k in range(W, W + 2):
+        h.step_batch(*bs[k])
+    ms_v1, n_v1 = h.kernel_time()
+    h.set_flags(clear_mask=lib.FLAG_BATCH_KERNEL_V1)
     # LLH scan of one parameter (FitterBase::RunLLHScan): 256 points, every other parameter fixed -> one segment per slot
     sp0, nm0 = synth.proposal(w, 1)
     sc_sp = np.tile(sp0, (n_sets, 1)); sc_sp[:, 0] = np.linspace(-2.9, 2.9, n_sets)
@@ -801,6 +808,7 @@ def measure_cfg5(args, local=0, want_cpu=True):
            "config": {"workload": w.name, "events": w.n_events, "sets_per_batch": n_sets, "bins": w.n_bins, "setup_s": round(t_setup, 1),
                       "proposals": "256 perturbations N(theta0, 0.3^2) around one point: 1-3 active segments per parameter",
                       "single_set_kernel_ms": ms1 / max(n1, 1), "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / kms,
+                      "first_generation_kernel_ms": ms_v1 / max(n_v1, 1),
                       "llh_scan_256_points": {"ms": 1e3 * t_scan, "us_per_llh": 1e6 * t_scan / n_sets, "kernel_ms": ms_scan / max(n_scan, 1),
                                               "amortisation_vs_single_set": (ms1 / max(n1, 1)) * n_sets / (ms_scan / max(n_scan, 1))}},
            "roofline": {"bound": "fp32 issue (CUDA cores; no contraction, so no tensor cores)", "achieved": fp_instr / (kms * 1e-3) / 1e12,

@@ -263,6 +263,9 @@ M3B_API int m3b_register_host_buffer(m3b_handle* h, void* ptr, uint64_t bytes);
 M3B_API int m3b_alloc_host(m3b_handle* h, uint64_t bytes, void** ptr);
 M3B_API int m3b_free_host(m3b_handle* h, void* ptr);
 M3B_API int m3b_set_test_statistic(m3b_handle* h, int32_t test_statistic);   /* SampleHandlerBase.h:185 */
+/* switch run-time flags of m3b_config::flags on (set_mask) / off (clear_mask): M3B_FLAG_NO_BATCH_KERNEL,
+ * M3B_FLAG_BATCH_KERNEL_V1, M3B_FLAG_NO_SPIN_LLH (the other flags fix allocations at creation and cannot change) */
+M3B_API int m3b_set_flags(m3b_handle* h, int32_t set_mask, int32_t clear_mask);
 M3B_API int m3b_reset_w2(m3b_handle* h);   /* FirstTimeW2 = true again                              */
 
 /* ---- the step --------------------------------------------------------------------------------

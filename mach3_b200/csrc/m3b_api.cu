@@ -781,6 +781,14 @@ M3B_API int m3b_set_test_statistic(m3b_handle* h, int32_t ts) {
   return M3B_OK;
 }
 
+M3B_API int m3b_set_flags(m3b_handle* h, int32_t set_mask, int32_t clear_mask) {
+  REQUIRE(h, M3B_ERR_INVALID, "null handle");
+  constexpr int32_t kRuntime = M3B_FLAG_NO_BATCH_KERNEL | M3B_FLAG_BATCH_KERNEL_V1 | M3B_FLAG_NO_SPIN_LLH;
+  REQUIRE(((set_mask | clear_mask) & ~kRuntime) == 0, M3B_ERR_INVALID, "m3b_set_flags: only the run-time flags can change after creation");
+  h->cfg.flags = (h->cfg.flags | set_mask) & ~clear_mask;
+  return M3B_OK;
+}
+
 M3B_API int m3b_reset_w2(m3b_handle* h) {
   REQUIRE(h, M3B_ERR_INVALID, "null handle");
   h->first_time_w2 = true;

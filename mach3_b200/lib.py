@@ -28,7 +28,7 @@ EXPORTS = (
     "m3b_read_event_weights_f64",
     "m3b_upload_binning", "m3b_upload_binning_ex", "m3b_upload_events", "m3b_update_kinematics", "m3b_upload_selection", "m3b_update_selection_values", "m3b_read_event_selected",
     "m3b_upload_linear_shifts", "m3b_set_shift_pars", "m3b_upload_data", "m3b_upload_osc", "m3b_register_host_buffer", "m3b_alloc_host", "m3b_free_host",
-    "m3b_set_test_statistic", "m3b_reset_w2",
+    "m3b_set_test_statistic", "m3b_set_flags", "m3b_reset_w2",
     "m3b_step", "m3b_step_segments", "m3b_step_batch", "m3b_step_batch_hist", "m3b_llh", "m3b_eval_weights", "m3b_find_segments", "m3b_set_spline_knots_f64", "m3b_synchronize",
     "m3b_read_hist", "m3b_read_event_weights", "m3b_read_event_bins",
     "m3b_step_fill", "m3b_hist_device_ptr", "m3b_llh_from_hist", "m3b_peer_export", "m3b_peer_import", "m3b_step_peer",
@@ -366,6 +366,9 @@ class Handle:
 
     def set_test_statistic(self, ts):
         self._ck(self.L.m3b_set_test_statistic(self.h, C.c_int32(ts)))
+
+    def set_flags(self, set_mask=0, clear_mask=0):
+        self._ck(self.L.m3b_set_flags(self.h, C.c_int32(set_mask), C.c_int32(clear_mask)))
 
     def reset_w2(self):
         self._ck(self.L.m3b_reset_w2(self.h))
