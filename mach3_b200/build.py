@@ -57,7 +57,8 @@ def cuda_sources():
 
 def build_cuda(force=False, verbose=False):
     """libm3b200.so: kernels + C-ABI (include/m3b200.h), hand-written for sm_100a."""
-    out = os.path.join(PKG, "libm3b200.so")
+    exp = bool(os.environ.get("M3B_BUILD_EXPERIMENTS"))
+    out = os.path.join(PKG, "libm3b200_exp.so" if exp else "libm3b200.so")
     srcs = cuda_sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(ROOT, "include", "m3b200.h"))
@@ -65,11 +66,11 @@ def build_cuda(force=False, verbose=False):
         cmd = [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                "-ccbin", GXX, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", out, *srcs,
                "-Xptxas", "-v", "-lcudart"]
-        if os.environ.get("M3B_BUILD_EXPERIMENTS"):      # A/B builds only: legacy kernel variants + M3B_* environment knobs
+        if exp:      # A/B builds only (libm3b200_exp.so): legacy kernel variants + M3B_* environment knobs
             cmd.insert(1, "-DM3B_EXPERIMENTS")
         log = _run(cmd, verbose)
         os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)          # git-ignored; registers / spills per kernel
-        with open(os.path.join(ROOT, "build", "ptxas.log"), "w") as f:
+        with open(os.path.join(ROOT, "build", "ptxas_exp.log" if exp else "ptxas.log"), "w") as f:
             f.write(log)
     return out
 

@@ -887,16 +887,16 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
 #endif
     if (h->binned) {
       // BinnedSplineHandler path: evaluate the non-flat splines, then gather/fill (m3b_binned.cu)
-      // a privatised histogram only while it is small: beyond 48 KB per block it costs more (resident blocks, L1 left for
-      // the weight gathers) than the global f64 reductions it saves
       int smem = binned_fill_smem_bytes(a, true, w2_live);
-      h->hist_in_smem = smem <= 48 * 1024;
+      const char* hm = experiment_env("M3B_BINNED_SMEM_HIST_MAX_KB");
+      h->hist_in_smem = smem <= (hm ? atoi(hm) : 200) * 1024;
       if (!h->hist_in_smem) smem = binned_fill_smem_bytes(a, false, w2_live);
       CK(binned_fill_set_smem(smem));
       int bps = 0;
       CK(binned_fill_occupancy(smem, h->f64, &bps));
       REQUIRE(bps > 0, M3B_ERR_CUDA, "step: binned fill kernel does not fit on an SM");
       h->smem = smem;
+      { const char* mb = experiment_env("M3B_BINNED_MAX_BPS"); if (mb && atoi(mb) > 0) bps = std::min(bps, atoi(mb)); }
       h->grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_wtiles + 7) / 8, static_cast<int64_t>(bps) * h->sm_count)));
       h->binned_eval_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_btiles + 1) / 2, 8ll * h->sm_count)));
       h->launch_ready = true;
@@ -1103,6 +1103,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   if (h->binned) {
     a.btiles = h->d_btiles; a.n_btiles = h->n_btiles; a.bcoef = h->d_bcoef; a.bx = h->d_bx; a.bw = h->d_bw;
     a.ell = h->d_ell; a.wtiles = h->d_wtiles; a.n_wtiles = h->n_wtiles; a.perm = h->d_perm;
+    { const char* gs = experiment_env("M3B_BINNED_GRID_STRIDE"); a.binned_contiguous = gs && gs[0] == '0' ? 1 : 0; }
     a.real_f64 = h->f64 ? 1 : 0;
     a.bcoef_d = h->d_bcoef_d; a.bx_d = h->d_bx_d; a.bw_d = h->d_bw_d; a.osc_d = h->d_osc_d; a.static_d = h->d_static_d;
     a.evt_spline_d = h->d_evt_spline_d; a.evt_total_d = h->d_evt_total_d;

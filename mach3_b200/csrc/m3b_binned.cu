@@ -95,7 +95,7 @@ int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
 }
 
 template <bool F64>
-__global__ void __launch_bounds__(256, F64 ? 2 : 4) binned_fill_kernel(const __grid_constant__ FillArgs a) {
+__global__ void __launch_bounds__(256, 2) binned_fill_kernel(const __grid_constant__ FillArgs a) {
   using R = typename std::conditional<F64, double, float>::type;      // M3::float_t of the build
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -117,13 +117,14 @@ __global__ void __launch_bounds__(256, F64 ? 2 : 4) binned_fill_kernel(const __g
   const R* oscp = F64 ? reinterpret_cast<const R*>(a.osc_d) : reinterpret_cast<const R*>(a.osc);
   const R* statp = F64 ? reinterpret_cast<const R*>(a.static_d) : reinterpret_cast<const R*>(a.static_w);
 
-  // every block owns a CONTIGUOUS run of warp tiles: consecutive iterations of a block then revisit the sectors its
-  // previous iteration pulled into L1 (the events are walked in spline-grid-cell order, so neighbouring tiles gather from
-  // neighbouring weights); a grid-strided walk would jump a whole grid of tiles ahead and find nothing cached
+  // grid-strided walk over the warp tiles (measured against contiguous runs of tiles per block, which would let a block
+  // re-use the L1 lines of its previous iteration: 249 vs 299 us per config-4 step -- the kernel is bound by the number
+  // of distinct lines a gather instruction touches, not by L1 capacity; profiles/r02_binned_fill_ab.txt)
   const int64_t tiles_per_block = (a.n_wtiles + gridDim.x - 1) / gridDim.x;
-  const int64_t wt_begin = static_cast<int64_t>(blockIdx.x) * tiles_per_block;
-  const int64_t wt_end = wt_begin + tiles_per_block < a.n_wtiles ? wt_begin + tiles_per_block : a.n_wtiles;
-  for (int64_t wt = wt_begin + warp; wt < wt_end; wt += 8) {
+  const int64_t wt_begin = a.binned_contiguous ? static_cast<int64_t>(blockIdx.x) * tiles_per_block : static_cast<int64_t>(blockIdx.x) * 8;
+  const int64_t wt_end = a.binned_contiguous ? (wt_begin + tiles_per_block < a.n_wtiles ? wt_begin + tiles_per_block : a.n_wtiles) : a.n_wtiles;
+  const int64_t wt_step = a.binned_contiguous ? 8 : static_cast<int64_t>(gridDim.x) * 8;
+  for (int64_t wt = wt_begin + warp; wt < wt_end; wt += wt_step) {
     const WTile d = a.wtiles[wt];
     // events are processed in the order of their spline-grid cell (a.perm, built at upload): the 32 lanes of a warp --
     // and the 8 warps of the block -- then gather from the same few sectors of every parameter's weight row

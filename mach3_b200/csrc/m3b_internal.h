@@ -154,6 +154,7 @@ struct FillArgs {
   double* evt_spline_d; double* evt_total_d;
   const int32_t* ell; const WTile* wtiles; int64_t n_wtiles;
   const int32_t* perm;         // binned fill: event handled by (warp tile, lane), nullptr = identity
+  int32_t binned_contiguous;   // experiments: 1 = contiguous runs of warp tiles per block instead of the grid-strided walk
   // optional per-block timeline (m3b_block_trace): 8 x u64 globaltimer ns per block
   unsigned long long* trace;
   alignas(16) unsigned char step_inline[kStepInlineMax];

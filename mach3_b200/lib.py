@@ -8,7 +8,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm3b200.so")
+# M3B_LIB: an experiments build of the library (mach3_b200/build.py with M3B_BUILD_EXPERIMENTS=1: legacy kernel variants and
+# M3B_* tuning knobs read from the environment) for A/B measurements; the product library reads no environment
+LIB_PATH = os.environ.get("M3B_LIB") or os.path.join(_HERE, "libm3b200.so")
 
 OK = 0
 POISSON, BARLOW_BEESTON, ICECUBE, PEARSON, DEMBINSKI_ABDELMOTTELEB = range(5)
