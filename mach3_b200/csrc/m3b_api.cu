@@ -1102,7 +1102,7 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   }
   if (h->binned) {
     a.btiles = h->d_btiles; a.n_btiles = h->n_btiles; a.bcoef = h->d_bcoef; a.bx = h->d_bx; a.bw = h->d_bw;
-    a.ell = h->d_ell; a.wtiles = h->d_wtiles; a.n_wtiles = h->n_wtiles; a.perm = h->d_perm; a.bcols = h->d_bcols;
+    a.ell = h->d_ell; a.wtiles = h->d_wtiles; a.n_wtiles = h->n_wtiles; a.perm = h->d_perm;
     { const char* gs = experiment_env("M3B_BINNED_GRID_STRIDE"); a.binned_contiguous = gs && gs[0] == '0' ? 1 : 0; }
     a.real_f64 = h->f64 ? 1 : 0;
     a.bcoef_d = h->d_bcoef_d; a.bx_d = h->d_bx_d; a.bw_d = h->d_bw_d; a.osc_d = h->d_osc_d; a.static_d = h->d_static_d;

@@ -144,29 +144,8 @@ __global__ void __launch_bounds__(256, 2) binned_fill_kernel(const __grid_consta
     }
     w *= w_osc;
     R w_spl = 1;               // product of the binned weights alone (m3b_read_event_weights)
-    if (a.bcols) {
-      // columns layout: one parameter per column, ascending -- the order of every event's own pointers (checked at
-      // upload), so each lane still multiplies ITS weights in ITS pointer order; an absent weight is exactly 1
-      const BCol* cols = a.bcols + d.off;
-      for (int j0 = 0; j0 < d.max_n; j0 += 8) {
-        int idx[8]; R g[8];
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          idx[j] = -1;
-          if (j0 + j < d.max_n) {
-            const int2 bm = __ldcs(reinterpret_cast<const int2*>(cols + j0 + j));       // {base, mask}: one broadcast load
-            const int o = __ldcs(cols[j0 + j].off + lane);
-            if ((static_cast<unsigned>(bm.y) >> lane) & 1u) idx[j] = bm.x + o;
-          }
-        }
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = idx[j] >= 0 ? __ldg(bw + idx[j]) : R(1);
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) if (idx[j] >= 0) { w *= g[j]; w_spl *= g[j]; }
-      }
-    }
     const int32_t* col = a.ell + d.off + lane;
-    for (int j0 = 0; !a.bcols && j0 < d.max_n; j0 += 8) {
+    for (int j0 = 0; j0 < d.max_n; j0 += 8) {
       int idx[8]; R g[8];
       #pragma unroll
       for (int j = 0; j < 8; ++j) idx[j] = (j0 + j < d.max_n) ? __ldcs(col + (j0 + j) * 32) : -1;
@@ -365,69 +344,7 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
   std::vector<int32_t> perm(static_cast<size_t>(h->e_pad));
   for (int64_t e = 0; e < h->e_pad; ++e) perm[e] = static_cast<int32_t>(e);
   std::stable_sort(perm.begin(), perm.begin() + n_events, [&](int32_t x, int32_t y) { return cell[x] < cell[y]; });
-  // ---- columns layout: possible when every event's non-flat pointers ascend strictly in parameter (one weight per
-  //      parameter, in parameter order -- what SetSplinePointers pushes: GetEventSplines walks the systematics in order,
-  //      Samples/SampleHandlerFD.cpp:1205-1242).  A tile's columns are the parameters any of its 32 events points into.
-  bool ascending = true;
-  std::vector<int16_t> first_param(static_cast<size_t>(n_events), 32767);
-  for (int64_t e = 0; e < n_events && ascending; ++e) {
-    int prev = -1;
-    for (uint64_t j = first[e]; j < first[e + 1]; ++j) {
-      const int32_t c = h->b_slot2compact[spline_index[j]];
-      if (c < 0) continue;
-      const int p = h->b_param_of_compact_row(c);
-      if (prev < 0) first_param[e] = static_cast<int16_t>(p);
-      if (p <= prev) { ascending = false; break; }
-      prev = p;
-    }
-  }
-  if (ascending && h->P < 32767) {
-    // events of one neighbourhood of the spline grid (256 consecutive ones in cell order) are walked in the order of
-    // their first parameter: a tile's events then share most of their parameters and the tile needs few columns
-    for (int64_t v0 = 0; v0 < n_events; v0 += 256)
-      std::stable_sort(perm.begin() + v0, perm.begin() + std::min<int64_t>(n_events, v0 + 256),
-                       [&](int32_t x, int32_t y) { return first_param[x] < first_param[y]; });
-    std::vector<BCol> cols;
-    cols.reserve(static_cast<size_t>(off / 16 + n_wt));
-    std::vector<std::vector<std::pair<int32_t, int32_t>>> by_param(static_cast<size_t>(h->P));      // (compact index, lane) per parameter
-    std::vector<int> touched;
-    for (int64_t t = 0; t < n_wt; ++t) {
-      touched.clear();
-      for (int64_t v = t * 32; v < std::min<int64_t>(n_events, t * 32 + 32); ++v) {
-        const int64_t e = perm[v];
-        for (uint64_t j = first[e]; j < first[e + 1]; ++j) {
-          const int32_t c = h->b_slot2compact[spline_index[j]];
-          if (c < 0) continue;
-          const int p = h->b_param_of_compact_row(c);
-          if (by_param[p].empty()) touched.push_back(p);
-          by_param[p].emplace_back(c, static_cast<int32_t>(v & 31));
-        }
-      }
-      std::sort(touched.begin(), touched.end());
-      wt[t].off = static_cast<int64_t>(cols.size()); wt[t].pad = 0;
-      for (int p : touched) {
-        auto& v = by_param[p];
-        std::sort(v.begin(), v.end());
-        size_t i = 0;
-        while (i < v.size()) {             // lanes whose weights lie within 256 elements of the first share one column
-          BCol bc{}; bc.base = v[i].first; bc.mask = 0; memset(bc.off, 0, sizeof bc.off);
-          size_t k = i;
-          for (; k < v.size() && v[k].first - bc.base < 256; ++k) { bc.mask |= 1u << v[k].second; bc.off[v[k].second] = static_cast<uint8_t>(v[k].first - bc.base); }
-          cols.push_back(bc);
-          i = k;
-        }
-        v.clear();
-      }
-      wt[t].max_n = static_cast<int32_t>(cols.size() - static_cast<size_t>(wt[t].off));
-    }
-    if (cols.empty()) cols.push_back(BCol{});
-    CK(dev_upload(h, &h->d_bcols, cols));
-    h->b_gather_per_step = cols.size();
-  }
   int64_t total = 0;
-  if (h->d_bcols) {
-    // (the ELL arrays below are not built)
-  } else
   for (int64_t t = 0; t < n_wt; ++t) {
     uint32_t mx = 0;
     for (int64_t v = t * 32; v < std::min<int64_t>(n_events, t * 32 + 32); ++v) mx = std::max(mx, keep[perm[v]]);
@@ -435,7 +352,7 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
     total += static_cast<int64_t>(mx) * 32;
   }
   std::vector<int32_t> ell(static_cast<size_t>(std::max<int64_t>(total, 1)), -1);
-  for (int64_t v = 0; !h->d_bcols && v < n_events; ++v) {
+  for (int64_t v = 0; v < n_events; ++v) {
     const int64_t e = perm[v];
     const WTile& d = wt[v / 32];
     int64_t k = 0;
@@ -466,7 +383,7 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
   CK(dev_upload(h, &h->d_ell, ell));
   CK(dev_upload(h, &h->d_wtiles, wt));
   h->n_wtiles = n_wt;
-  if (!h->d_bcols) h->b_gather_per_step = static_cast<uint64_t>(total);
+  h->b_gather_per_step = static_cast<uint64_t>(total);
   h->launch_ready = false;
   return M3B_OK;
 }

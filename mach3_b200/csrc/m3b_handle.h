@@ -171,7 +171,6 @@ struct m3b_handle {
     return static_cast<int>(std::upper_bound(b_out_base.begin(), b_out_base.end(), c) - b_out_base.begin()) - 1;
   }
   int32_t* d_perm = nullptr;                     // order in which the binned fill kernel walks the events (sorted by spline-grid cell)
-  BCol* d_bcols = nullptr;                       // columns layout of the events' weight pointers (nullptr: ELL layout)
   float4* d_bcoef = nullptr; float* d_bx = nullptr; float* d_bw = nullptr;
   BTile* d_btiles = nullptr; WTile* d_wtiles = nullptr; int32_t* d_ell = nullptr;
   uint64_t b_gather_per_step = 0;

@@ -80,20 +80,10 @@ struct BTile {                 // 1024 consecutive active splines of one paramet
   int64_t coef_off;            // first element of the parameter's [nseg][n_pad] block
   int32_t n_pad, param, k0, out0;   // row length, parameter, first spline of the tile in the row, first compact weight
 };
-struct WTile {                 // 32 events (consecutive in the kernel's walking order): their binned-spline pointers
-  int64_t off;                 // columns layout: first BCol of the tile.  ELL layout (fallback): ell[off + j*32 + lane] =
-  int32_t max_n, pad;          // compact weight index of the lane's j-th pointer, -1 = none.  max_n = columns / ELL width
+struct WTile {                 // 32 consecutive events: their binned-spline pointers as ELL columns
+  int64_t off;                 // ell[off + j*32 + lane] = compact weight index of the lane's j-th pointer, -1 = none
+  int32_t max_n, pad;
 };
-// One column of a warp tile in the columns layout: ONE spline parameter, the lanes (events) of the tile that point into
-// its weight row, and where.  All 32 lanes of a gather instruction then read the same parameter's row -- and, the events
-// being walked in spline-grid-cell order, neighbouring elements of it: a couple of 128-byte lines per instruction
-// instead of 32 different ones.  Lane l reads bw[base + off[l]] when bit l of mask is set, else multiplies by exactly 1.
-struct BCol {
-  int32_t base;
-  uint32_t mask;
-  uint8_t off[32];
-};
-static_assert(sizeof(BCol) == 40, "BCol is 40 bytes");
 
 // Shared-memory map of the TMA fill kernel (m3b_fill_tma.cu); computed on the host, passed by value.
 //   [step table][dx[max_nc]][lv[max_nl]][row[max_nc]][stage descriptors][hist (+w2)][ring: n_stages x stage_bytes]
@@ -164,7 +154,6 @@ struct FillArgs {
   double* evt_spline_d; double* evt_total_d;
   const int32_t* ell; const WTile* wtiles; int64_t n_wtiles;
   const int32_t* perm;         // binned fill: event handled by (warp tile, lane), nullptr = identity
-  const BCol* bcols;           // binned fill, columns layout (nullptr: ELL layout)
   int32_t binned_contiguous;   // experiments: 1 = contiguous runs of warp tiles per block instead of the grid-strided walk
   // optional per-block timeline (m3b_block_trace): 8 x u64 globaltimer ns per block
   unsigned long long* trace;
