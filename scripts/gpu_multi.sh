@@ -1,12 +1,11 @@
-# usage: bash scripts/gpu_multi2.sh N   (under gpurun --gpus N): parity + default-exchange bench + nccl bench
-N=${1:-8}
-mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 600 $TR --master-port 29511 tests/multigpu/parity_ranks.py > gpurun_out/multi_parity_$N.log 2>&1; echo "parity exit $?" >> gpurun_out/multi_parity_$N.log
-grep "PARITY\|FAIL\|parity exit" gpurun_out/multi_parity_$N.log
-for ex in auto nccl; do
-  timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps ${STEPS:-100} --warmup 10 --exchange $ex > gpurun_out/bench_cfg3_${N}_$ex.json 2> gpurun_out/bench_cfg3_${N}_$ex.err; echo "bench $ex exit $?"
-  grep "^{" gpurun_out/bench_cfg3_${N}_$ex.json | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); print(d['config']['exchange'], 'ms/step', d['ms_per_step'], 'kernel_ms', d['roofline']['kernel_ms'], 'GB/s', d['roofline']['achieved'], 'e2e ms', d['e2e']['ms_per_step'], 'value', d['value'])"
-done
+#!/bin/bash
+# multi-GPU round-trip on N GPUs of one box: the group / sharding tests on distinct devices, the adapter spread over N devices,
+# then the bench line at N (torchrun, one rank per GPU) with its parity check and its single-process record
+N=${1:-2}
+cd $GRAFT_REPO_ROOT
+O=gpurun_out/multi$N; mkdir -p $O
+nvidia-smi -L > $O/smi.txt; nvidia-smi topo -m >> $O/smi.txt 2>&1
+timeout 900 python -m pytest tests/test_group_gpu.py tests/test_multigpu.py tests/test_shifts.py tests/test_monolith_file.py -m gpu -q > $O/pytest.log 2>&1; echo "pytest rc $?" >> $O/pytest.log
+timeout 300 oracle/_ref/adapter_test 1000000 poisson $N time > $O/adapter_${N}members.log 2>&1; echo "rc $?" >> $O/adapter_${N}members.log
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 > $O/bench.json 2> $O/bench.err; echo "rc $?" >> $O/bench.err
+tail -4 $O/pytest.log; tail -5 $O/adapter_${N}members.log; tail -c 1500 $O/bench.json; tail -5 $O/bench.err
