@@ -7,16 +7,6 @@
 static thread_local std::string g_last_error;
 std::string& m3b_last_error_slot() { return g_last_error; }
 
-// Tuning knobs read from the environment exist only in -DM3B_EXPERIMENTS builds (A/B measurements); the product
-// library takes its configuration from m3b_config alone.
-static inline const char* experiment_env(const char* name) {
-#ifdef M3B_EXPERIMENTS
-  return getenv(name);
-#else
-  (void)name;
-  return nullptr;
-#endif
-}
 
 extern "C" {
 
@@ -570,16 +560,24 @@ M3B_API int m3b_upload_events(m3b_handle* h, int64_t n_events, const int32_t* sa
   return M3B_OK;
 }
 
+// the binned fill kernel reads the bins in its own walking order (m3b_upload_event_binned_splines): refresh that copy
+static int refresh_sorted_bins(m3b_handle* h) {
+  if (!h->d_bin_sorted) return M3B_OK;
+  CK(launch_gather(h->d_bin_sorted, h->d_bin, h->d_perm, h->e_pad, 4, h->stream));
+  ++h->launches;
+  return M3B_OK;
+}
+
 // SampleHandlerFD::IsEventSelected (Samples/SampleHandlerFD.cpp:281-294) over the uploaded cuts: bin[] = bin_raw[] or -1
 static int run_selection(m3b_handle* h) {
-  if (h->n_cuts == 0) return M3B_OK;
+  if (h->n_cuts == 0) return refresh_sorted_bins(h);
   SelectArgs sa{};
   sa.n_events = h->n_events; sa.e_pad = h->e_pad; sa.sample_id = h->d_sample_id;
   sa.cut_start = h->d_cut_start; sa.cut_var = h->d_cut_var; sa.lower = h->d_cut_lo; sa.upper = h->d_cut_hi;
   sa.values = h->d_sel_vals; sa.kin = h->d_kin; sa.bin_raw = h->d_bin_raw; sa.bin = h->d_bin; sa.selected = h->d_selected;
   CK(launch_select(sa, h->stream));
   ++h->launches;
-  return M3B_OK;
+  return refresh_sorted_bins(h);
 }
 
 M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* cut_sample, const int32_t* cut_var,
@@ -602,7 +600,7 @@ M3B_API int m3b_upload_selection(m3b_handle* h, int32_t n_cuts, const int32_t* c
     if (h->d_bin_raw != h->d_bin) CK(copy_sync(h, h->d_bin, h->d_bin_raw, sizeof(int32_t) * h->e_pad, cudaMemcpyDeviceToDevice));
     if (h->d_selected) CK(cudaMemsetAsync(h->d_selected, 1, static_cast<size_t>(h->e_pad), h->stream));
     h->n_cuts = 0;
-    return M3B_OK;
+    return refresh_sorted_bins(h);
   }
   // cuts grouped by sample, StoredSelection order kept inside a sample (the first failing cut decides; any order gives
   // the same answer, but the order of evaluation is the reference's)
@@ -891,13 +889,15 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
       const char* hm = experiment_env("M3B_BINNED_SMEM_HIST_MAX_KB");
       h->hist_in_smem = smem <= (hm ? atoi(hm) : 200) * 1024;
       if (!h->hist_in_smem) smem = binned_fill_smem_bytes(a, false, w2_live);
-      CK(binned_fill_set_smem(smem));
+      const char* nt = experiment_env("M3B_BINNED_THREADS");
+      h->binned_threads = nt ? atoi(nt) : 1024;
       int bps = 0;
-      CK(binned_fill_occupancy(smem, h->f64, &bps));
+      CK(binned_fill_prepare(smem, h->f64, h->binned_threads, &bps));
       REQUIRE(bps > 0, M3B_ERR_CUDA, "step: binned fill kernel does not fit on an SM");
       h->smem = smem;
       { const char* mb = experiment_env("M3B_BINNED_MAX_BPS"); if (mb && atoi(mb) > 0) bps = std::min(bps, atoi(mb)); }
-      h->grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_wtiles + 7) / 8, static_cast<int64_t>(bps) * h->sm_count)));
+      const int tpb = h->binned_threads / 32;
+      h->grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_wtiles + tpb - 1) / tpb, static_cast<int64_t>(bps) * h->sm_count)));
       h->binned_eval_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((h->n_btiles + 1) / 2, 8ll * h->sm_count)));
       h->launch_ready = true;
       h->launch_w2_live = w2_live;
@@ -1103,12 +1103,12 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   if (h->binned) {
     a.btiles = h->d_btiles; a.n_btiles = h->n_btiles; a.bcoef = h->d_bcoef; a.bx = h->d_bx; a.bw = h->d_bw;
     a.ell = h->d_ell; a.wtiles = h->d_wtiles; a.n_wtiles = h->n_wtiles; a.perm = h->d_perm;
-    { const char* gs = experiment_env("M3B_BINNED_GRID_STRIDE"); a.binned_contiguous = gs && gs[0] == '0' ? 1 : 0; }
+    a.bin_sorted = h->d_bin_sorted; a.static_sorted = h->d_static_sorted; a.norm_idx_sorted = h->d_norm_idx_sorted; a.osc_idx_sorted = h->d_osc_idx_sorted;
     a.real_f64 = h->f64 ? 1 : 0;
     a.bcoef_d = h->d_bcoef_d; a.bx_d = h->d_bx_d; a.bw_d = h->d_bw_d; a.osc_d = h->d_osc_d; a.static_d = h->d_static_d;
     a.evt_spline_d = h->d_evt_spline_d; a.evt_total_d = h->d_evt_total_d;
     if (h->n_btiles > 0) { CK(launch_binned_eval(a, h->binned_eval_grid, h->stream)); ++h->launches; }
-    CK(launch_binned_fill(a, h->grid, h->smem, h->stream));
+    CK(launch_binned_fill(a, h->grid, h->binned_threads, h->smem, h->stream));
   } else if (h->use_tma) CK(launch_fill_tma(a, h->grid, h->smem, h->stream));
 #ifdef M3B_EXPERIMENTS
   else CK(launch_fill(a, h->variant, h->grid, h->smem, h->stream));

@@ -94,9 +94,43 @@ int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
   return b > llh_scratch ? b : llh_scratch;
 }
 
-template <bool F64>
-__global__ void __launch_bounds__(256, 2) binned_fill_kernel(const __grid_constant__ FillArgs a) {
+// per-event part: CalcWeightTotal's factors other than the binned splines, read either through the walking order (perm)
+// or from the copies already laid out in that order (streaming loads: L1 is for the weight gathers)
+template <class R>
+struct BEvent { int64_t e; int bin; R w_pre, w_static; };
+template <bool F64, class R>
+__device__ __forceinline__ BEvent<R> binned_event(const FillArgs& a, const R* norm, const R* oscp, const R* statp, int64_t v) {
+  BEvent<R> o;
+  o.e = a.perm ? static_cast<int64_t>(__ldcs(a.perm + v)) : v;
+  const bool sorted = a.bin_sorted != nullptr;
+  o.bin = sorted ? __ldcs(a.bin_sorted + v) : a.bin[o.e];
+  R w_osc = 1;
+  if (oscp) {
+    const int64_t oi = a.osc_idx ? static_cast<int64_t>(sorted && a.osc_idx_sorted ? __ldcs(a.osc_idx_sorted + v) : a.osc_idx[o.e]) : (o.e < a.n_events ? o.e : 0);
+    w_osc = oi >= 0 ? oscp[oi] : R(1);
+  }
+  o.w_static = 1;
+  if (statp) o.w_static = sorted ? __ldcs(reinterpret_cast<const R*>(a.static_sorted) + v) : statp[o.e];
+  // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras
+  R w = 1;
+  for (int j = 0; j < a.norm_slots; ++j) {
+    const int i = sorted ? __ldcs(a.norm_idx_sorted + static_cast<int64_t>(j) * a.e_pad + v) : a.norm_idx[static_cast<int64_t>(j) * a.e_pad + o.e];
+    w *= (i >= 0 ? norm[i] : R(1));
+  }
+  o.w_pre = w * w_osc;
+  return o;
+}
+
+// The fill kernel.  One warp = one warp tile of 32 events per iteration, tiles handed out grid-strided, one per warp of the
+// block.  The kernel is bound by memory latency, not by bandwidth (three dependent loads per tile: tile descriptor -> ELL
+// columns -> weights), so (1) it runs as ONE 1024-thread block per SM at 64 registers: 32 warps share one privatised
+// histogram, and whatever shared memory that leaves stays L1 for the gathers (512 x 2 and 256 x 2 were measured slower:
+// profiles/r02_binned_fill_ab.txt); (2) it is software-pipelined: while the weights of tile i are gathered, the event table
+// and the first kBFront ELL columns of tile i+1 and the descriptor of tile i+2 are already in flight.
+template <bool F64, int NT, int kBFront>
+__global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fill_kernel(const __grid_constant__ FillArgs a) {
   using R = typename std::conditional<F64, double, float>::type;      // M3::float_t of the build
+  constexpr int kTiles = NT / 32;                    // warp tiles per block iteration
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_last;
@@ -108,8 +142,8 @@ __global__ void __launch_bounds__(256, 2) binned_fill_kernel(const __grid_consta
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (smem_hist && !a.weights_only) {
-    for (int i = tid; i < a.n_bins; i += 256) s_hist[i] = 0.;
-    if (w2_live) for (int i = tid; i < a.n_bins; i += 256) s_w2[i] = 0.;
+    for (int i = tid; i < a.n_bins; i += NT) s_hist[i] = 0.;
+    if (w2_live) for (int i = tid; i < a.n_bins; i += NT) s_w2[i] = 0.;
   }
   stage_step_table(a, smem, &bar);
   const R* norm = reinterpret_cast<const R*>(smem + (F64 ? a.step.off_norm_d : a.step.off_norm));
@@ -117,59 +151,89 @@ __global__ void __launch_bounds__(256, 2) binned_fill_kernel(const __grid_consta
   const R* oscp = F64 ? reinterpret_cast<const R*>(a.osc_d) : reinterpret_cast<const R*>(a.osc);
   const R* statp = F64 ? reinterpret_cast<const R*>(a.static_d) : reinterpret_cast<const R*>(a.static_w);
 
-  // grid-strided walk over the warp tiles (measured against contiguous runs of tiles per block, which would let a block
-  // re-use the L1 lines of its previous iteration: 249 vs 299 us per config-4 step -- the kernel is bound by the number
-  // of distinct lines a gather instruction touches, not by L1 capacity; profiles/r02_binned_fill_ab.txt)
-  const int64_t tiles_per_block = (a.n_wtiles + gridDim.x - 1) / gridDim.x;
-  const int64_t wt_begin = a.binned_contiguous ? static_cast<int64_t>(blockIdx.x) * tiles_per_block : static_cast<int64_t>(blockIdx.x) * 8;
-  const int64_t wt_end = a.binned_contiguous ? (wt_begin + tiles_per_block < a.n_wtiles ? wt_begin + tiles_per_block : a.n_wtiles) : a.n_wtiles;
-  const int64_t wt_step = a.binned_contiguous ? 8 : static_cast<int64_t>(gridDim.x) * 8;
-  for (int64_t wt = wt_begin + warp; wt < wt_end; wt += wt_step) {
-    const WTile d = a.wtiles[wt];
+  auto load_desc = [&](int64_t t) {                 // max_n = -1: past the end
+    WTile d; d.off = 0; d.max_n = -1; d.pad = 0;
+    if (t < a.n_wtiles) d = a.wtiles[t];
+    return d;
+  };
+  auto load_front = [&](int64_t t, const WTile& d, BEvent<R>& ev, int (&idx)[kBFront]) {
+    if (d.max_n < 0) return;
     // events are processed in the order of their spline-grid cell (a.perm, built at upload): the 32 lanes of a warp --
-    // and the 8 warps of the block -- then gather from the same few sectors of every parameter's weight row
-    const int64_t e = a.perm ? static_cast<int64_t>(a.perm[wt * 32 + lane]) : wt * 32 + lane;
-    const int bin = a.bin[e];
-    R w_osc = 1, w_static = 1;
-    if (oscp) {
-      const int64_t oi = a.osc_idx ? static_cast<int64_t>(a.osc_idx[e]) : (e < a.n_events ? e : 0);
-      w_osc = oi >= 0 ? oscp[oi] : R(1);
-    }
-    if (statp) w_static = statp[e];
-    // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras
-    R w = 1;
-    for (int j = 0; j < a.norm_slots; ++j) {
-      const int i = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + e];
-      w *= (i >= 0 ? norm[i] : R(1));
-    }
-    w *= w_osc;
-    R w_spl = 1;               // product of the binned weights alone (m3b_read_event_weights)
+    // and the warps of the block -- then gather from the same few sectors of every parameter's weight row
+    ev = binned_event<F64, R>(a, norm, oscp, statp, t * 32 + lane);
     const int32_t* col = a.ell + d.off + lane;
-    for (int j0 = 0; j0 < d.max_n; j0 += 8) {
-      int idx[8]; R g[8];
+    #pragma unroll
+    for (int j = 0; j < kBFront; ++j) idx[j] = j < d.max_n ? __ldcs(col + j * 32) : -1;
+  };
+
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kTiles;
+  int64_t wt = static_cast<int64_t>(blockIdx.x) * kTiles + warp;
+  WTile d_nxt = load_desc(wt);
+  BEvent<R> ev_nxt; ev_nxt.e = 0; ev_nxt.bin = -1; ev_nxt.w_pre = 0; ev_nxt.w_static = 0;
+  int idx_nxt[kBFront];
+  #pragma unroll
+  for (int j = 0; j < kBFront; ++j) idx_nxt[j] = -1;
+  load_front(wt, d_nxt, ev_nxt, idx_nxt);
+  WTile d_nxt2 = load_desc(wt + stride);
+  for (; wt < a.n_wtiles; wt += stride) {
+    const WTile d = d_nxt;
+    const BEvent<R> ev = ev_nxt;
+    int idx[kBFront]; R gw[kBFront];
+    #pragma unroll
+    for (int j = 0; j < kBFront; ++j) idx[j] = idx_nxt[j];
+    #pragma unroll
+    for (int j = 0; j < kBFront; ++j) gw[j] = idx[j] >= 0 ? __ldg(bw + idx[j]) : R(1);
+    // next tile's front and the descriptor after it
+    d_nxt = d_nxt2;
+    load_front(wt + stride, d_nxt, ev_nxt, idx_nxt);
+    d_nxt2 = load_desc(wt + 2 * stride);
+    // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras
+    R w = ev.w_pre;
+    R w_spl = 1;               // product of the binned weights alone (m3b_read_event_weights)
+    #pragma unroll
+    for (int j = 0; j < kBFront; ++j) if (idx[j] >= 0) { w *= gw[j]; w_spl *= gw[j]; }
+    const int32_t* col = a.ell + d.off + lane;
+    for (int j0 = kBFront; j0 < d.max_n; j0 += 8) {
+      int ix[8]; R gx[8];
       #pragma unroll
-      for (int j = 0; j < 8; ++j) idx[j] = (j0 + j < d.max_n) ? __ldcs(col + (j0 + j) * 32) : -1;
+      for (int j = 0; j < 8; ++j) ix[j] = (j0 + j < d.max_n) ? __ldcs(col + (j0 + j) * 32) : -1;
       #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = idx[j] >= 0 ? __ldg(bw + idx[j]) : R(1);
+      for (int j = 0; j < 8; ++j) gx[j] = ix[j] >= 0 ? __ldg(bw + ix[j]) : R(1);
       #pragma unroll
-      for (int j = 0; j < 8; ++j) if (idx[j] >= 0) { w *= g[j]; w_spl *= g[j]; }
+      for (int j = 0; j < 8; ++j) if (ix[j] >= 0) { w *= gx[j]; w_spl *= gx[j]; }
     }
-    w *= w_static;
+    w *= ev.w_static;
+    const int64_t e = ev.e;
     if (e < a.n_events) {
       if (F64) { if (a.evt_spline_d) { a.evt_spline_d[e] = w_spl; a.evt_total_d[e] = w; } }
       else if (a.evt_spline_w) { a.evt_spline_w[e] = static_cast<float>(w_spl); a.evt_total_w[e] = static_cast<float>(w); }
     }
-    if (w > R(0) && bin >= 0 && !a.weights_only) {
+    if (w > R(0) && ev.bin >= 0 && !a.weights_only) {
       if (smem_hist) {
-        atomicAdd(s_hist + bin, static_cast<double>(w));
-        if (w2_live) atomicAdd(s_w2 + bin, static_cast<double>(w * w));
+        atomicAdd(s_hist + ev.bin, static_cast<double>(w));
+        if (w2_live) atomicAdd(s_w2 + ev.bin, static_cast<double>(w * w));
       } else {
-        atomicAdd(a.hist + bin, static_cast<double>(w));
-        if (w2_live) atomicAdd(a.w2 + bin, static_cast<double>(w * w));
+        atomicAdd(a.hist + ev.bin, static_cast<double>(w));
+        if (w2_live) atomicAdd(a.w2 + ev.bin, static_cast<double>(w * w));
       }
     }
   }
   finish_block(a, s_hist, s_w2, reinterpret_cast<double*>(smem), &s_last);
+}
+
+template <class T>
+__global__ void gather_kernel(T* dst, const T* src, const int32_t* perm, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[perm[i]];
+}
+// dst[i] = src[perm[i]] for 2-, 4- or 8-byte elements
+cudaError_t launch_gather(void* dst, const void* src, const int32_t* perm, int64_t n, int elem_bytes, cudaStream_t s) {
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8)));
+  if (elem_bytes == 2) gather_kernel<<<grid, 256, 0, s>>>(static_cast<int16_t*>(dst), static_cast<const int16_t*>(src), perm, n);
+  else if (elem_bytes == 4) gather_kernel<<<grid, 256, 0, s>>>(static_cast<int32_t*>(dst), static_cast<const int32_t*>(src), perm, n);
+  else if (elem_bytes == 8) gather_kernel<<<grid, 256, 0, s>>>(static_cast<int64_t*>(dst), static_cast<const int64_t*>(src), perm, n);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_binned_eval(const FillArgs& a, int grid, cudaStream_t s) {
@@ -177,20 +241,23 @@ cudaError_t launch_binned_eval(const FillArgs& a, int grid, cudaStream_t s) {
   else binned_eval_kernel<<<grid, 256, (a.step.bytes + 15) & ~15, s>>>(a);
   return cudaGetLastError();
 }
-cudaError_t launch_binned_fill(const FillArgs& a, int grid, int smem, cudaStream_t s) {
-  if (a.real_f64) binned_fill_kernel<true><<<grid, 256, smem, s>>>(a);
-  else binned_fill_kernel<false><<<grid, 256, smem, s>>>(a);
-  return cudaGetLastError();
+// 1024 threads x 1 block/SM with an 8-column front is the product configuration; 512 x 2 and 256 x 2 (16-column front)
+// remain selectable in the experiments build (M3B_BINNED_THREADS) for the A/B record
+template <class F>
+static cudaError_t with_fill_kernel(bool f64, int nt, F&& f) {
+  if (nt == 512) return f64 ? f(binned_fill_kernel<true, 512, 4>) : f(binned_fill_kernel<false, 512, 8>);
+  if (nt == 256) return f64 ? f(binned_fill_kernel<true, 256, 16>) : f(binned_fill_kernel<false, 256, 16>);
+  return f64 ? f(binned_fill_kernel<true, 1024, 4>) : f(binned_fill_kernel<false, 1024, 8>);
 }
-cudaError_t binned_fill_set_smem(int smem) {
-  (void)smem;
-  cudaError_t e = allow_max_dynamic_smem(binned_fill_kernel<false>);
-  if (e != cudaSuccess) return e;
-  return allow_max_dynamic_smem(binned_fill_kernel<true>);
+cudaError_t launch_binned_fill(const FillArgs& a, int grid, int nt, int smem, cudaStream_t s) {
+  return with_fill_kernel(a.real_f64 != 0, nt, [&](auto* k) { k<<<grid, nt, smem, s>>>(a); return cudaGetLastError(); });
 }
-cudaError_t binned_fill_occupancy(int smem, bool f64, int* bps) {
-  return f64 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel<true>, 256, smem)
-             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, binned_fill_kernel<false>, 256, smem);
+cudaError_t binned_fill_prepare(int smem, bool f64, int nt, int* bps) {
+  return with_fill_kernel(f64, nt, [&](auto* k) {
+    cudaError_t e = allow_max_dynamic_smem(k);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, k, nt, smem);
+  });
 }
 
 }  // namespace m3b
@@ -281,11 +348,47 @@ static int upload_binned_impl(m3b_handle* h, int32_t n_params, int32_t max_knots
   h->n_btiles = static_cast<int32_t>(tiles.size());
   h->b_n_slots = n_slots; h->b_n_act = n_unique; h->b_n_act_pad = n_act_pad;
   h->b_out_base = out_base; h->b_count.assign(count.begin() + 1, count.end());
+  h->b_run_start.clear(); h->b_run_super.clear();
+  for (int64_t s = 0, super = 0; s < n_slots; ++s) {
+    if (s > 0 && uniquesplinevec_Monolith[s] == uniquesplinevec_Monolith[s - 1]) continue;
+    if (s > 0 && uniquesplinevec_Monolith[s] < uniquesplinevec_Monolith[s - 1]) ++super;
+    h->b_run_start.push_back(s); h->b_run_super.push_back(static_cast<int32_t>(super));
+  }
   h->binned = true;
   h->launch_ready = false;
   return M3B_OK;
 }
 
+
+// The event table (bin, static weight, norm indices, oscillation index) once more in the order the fill kernel walks the
+// events, so a warp reads 32 consecutive elements of each instead of 32 sectors.  The caller-indexed arrays stay the
+// masters (rebinning, selection and re-uploads write those); these copies are refreshed from them.
+static int sort_static_weights(m3b_handle* h) {
+  const void* src = h->f64 ? static_cast<const void*>(h->d_static_d) : static_cast<const void*>(h->d_static);
+  if (!src || !h->d_perm) return M3B_OK;
+  const int elem = h->f64 ? 8 : 4;
+  if (!h->d_static_sorted) {
+    unsigned char* p = nullptr;
+    CK(dev_alloc(h, &p, static_cast<size_t>(h->e_pad) * elem));
+    h->d_static_sorted = p;
+  }
+  CK(launch_gather(h->d_static_sorted, src, h->d_perm, h->e_pad, elem, h->stream));
+  return M3B_OK;
+}
+static int sort_event_table(m3b_handle* h) {
+  CK(dev_alloc(h, &h->d_bin_sorted, static_cast<size_t>(h->e_pad)));
+  CK(launch_gather(h->d_bin_sorted, h->d_bin, h->d_perm, h->e_pad, 4, h->stream));
+  if (h->norm_slots > 0) {
+    CK(dev_alloc(h, &h->d_norm_idx_sorted, static_cast<size_t>(h->e_pad) * h->norm_slots));
+    for (int j = 0; j < h->norm_slots; ++j)
+      CK(launch_gather(h->d_norm_idx_sorted + static_cast<int64_t>(j) * h->e_pad, h->d_norm_idx + static_cast<int64_t>(j) * h->e_pad, h->d_perm, h->e_pad, 2, h->stream));
+  }
+  if (h->d_osc_idx) {
+    CK(dev_alloc(h, &h->d_osc_idx_sorted, static_cast<size_t>(h->e_pad)));
+    CK(launch_gather(h->d_osc_idx_sorted, h->d_osc_idx, h->d_perm, h->e_pad, 4, h->stream));
+  }
+  return sort_static_weights(h);
+}
 
 extern "C" {
 
@@ -316,7 +419,13 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
   // first pass: non-flat pointers per event, and where in its parameter's weight row the event's first one sits
   std::vector<uint32_t> keep(static_cast<size_t>(n_events), 0);
   std::vector<uint64_t> first(static_cast<size_t>(n_events) + 1, 0);
-  std::vector<float> cell(static_cast<size_t>(n_events), 2.f);      // position of the event's spline-grid cell, 0..1 (2: no non-flat pointer)
+  // Sort key = the spline-grid cell of the event.  Slots are laid out [sample][osc][syst][mode][var1][var2][var3]
+  // (Splines/BinnedSplineHandler.h:110) and an event's pointers are pushed syst by syst (SampleHandlerFD.cpp:1196-1242), all
+  // into the same (mode, var1, var2, var3) cell of one (sample, osc) super-block: the offset of the event's first pointer
+  // (flat or not) inside its systematic's block IS that cell.  With the events in (super-block, cell) order, the pointers of
+  // neighbouring events sit next to each other in every systematic's weight row.  (Only the walking order -- and so the
+  // speed -- depends on this reading of the layout; the result does not.)
+  std::vector<int64_t> cell(static_cast<size_t>(n_events), INT64_MAX);     // INT64_MAX: no pointer at all
   uint64_t off = 0;
   for (int64_t e = 0; e < n_events; ++e) {
     uint32_t k = 0;
@@ -324,15 +433,12 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
     for (uint32_t j = 0; j < n_per_event[e]; ++j) {
       const int32_t s = spline_index[off + j];
       REQUIRE(s >= 0 && s < h->b_n_slots, M3B_ERR_INVALID, "m3b_upload_event_binned_splines: spline_index out of range");
+      if (j == 0) {
+        const size_t r = static_cast<size_t>(std::upper_bound(h->b_run_start.begin(), h->b_run_start.end(), static_cast<int64_t>(s)) - h->b_run_start.begin()) - 1;
+        cell[e] = (static_cast<int64_t>(h->b_run_super[r]) << 40) | (s - h->b_run_start[r]);
+      }
       const int32_t c = h->b_slot2compact[s];
       if (c < 0) continue;                       // flat splines hold exactly 1.0f: multiplying by them changes nothing
-      if (k == 0) {
-        // compact indices are grouped by parameter and ascend with the slot inside a parameter, i.e. with the spline-grid
-        // cell (Splines/BinnedSplineHandler.h:110: [..][syst][mode][var1][var2][var3]); the rank inside the parameter's
-        // row, as a fraction, is comparable between events whose first non-flat pointer belongs to different parameters
-        const int p = h->b_param_of_compact_row(c);
-        cell[e] = static_cast<float>(static_cast<double>(c - h->b_out_base[p]) / static_cast<double>(std::max<int64_t>(1, h->b_count[p])));
-      }
       ++k;
     }
     keep[e] = k;
@@ -344,6 +450,12 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
   std::vector<int32_t> perm(static_cast<size_t>(h->e_pad));
   for (int64_t e = 0; e < h->e_pad; ++e) perm[e] = static_cast<int32_t>(e);
   std::stable_sort(perm.begin(), perm.begin() + n_events, [&](int32_t x, int32_t y) { return cell[x] < cell[y]; });
+  // inside a span of 8 warp tiles (events that are in flight together anyway and share L1 lines) the order is free: put
+  // events with equally many non-flat pointers into the same warp, so a tile's ELL columns (its longest event) are mostly full
+  constexpr int kBSortSpan = 8;
+  for (int64_t v0 = 0; v0 < n_events; v0 += 32 * kBSortSpan)
+    std::stable_sort(perm.begin() + v0, perm.begin() + std::min<int64_t>(n_events, v0 + 32 * kBSortSpan),
+                     [&](int32_t x, int32_t y) { return keep[x] > keep[y]; });
   int64_t total = 0;
   for (int64_t t = 0; t < n_wt; ++t) {
     uint32_t mx = 0;
@@ -362,6 +474,7 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
     }
   }
   CK(dev_upload(h, &h->d_perm, perm));
+  if (experiment_env("M3B_VERBOSE")) fprintf(stderr, "[m3b] binned ELL entries %lld\n", static_cast<long long>(total));
   if (h->f64) {
     // default build: osc / static weights and the per-event outputs are M3::float_t = double.  Until the caller
     // supplies doubles (m3b_upload_event_weights_f64 / m3b_upload_osc_f64) the float uploads are widened (exact).
@@ -382,6 +495,7 @@ M3B_API int m3b_upload_event_binned_splines(m3b_handle* h, int64_t n_events, con
   }
   CK(dev_upload(h, &h->d_ell, ell));
   CK(dev_upload(h, &h->d_wtiles, wt));
+  if (int rc = sort_event_table(h)) return rc;
   h->n_wtiles = n_wt;
   h->b_gather_per_step = static_cast<uint64_t>(total);
   h->launch_ready = false;
@@ -398,7 +512,7 @@ M3B_API int m3b_upload_event_weights_f64(m3b_handle* h, int64_t n_events, const 
   std::copy(static_w, static_w + n_events, sw.begin());
   if (!h->d_static_d) CK(dev_alloc(h, &h->d_static_d, sw.size()));
   CK(copy_sync(h, h->d_static_d, sw.data(), sizeof(double) * sw.size(), cudaMemcpyHostToDevice));
-  return M3B_OK;
+  return sort_static_weights(h);
 }
 M3B_API int m3b_upload_osc_f64(m3b_handle* h, const double* osc_w, int64_t n) {
   REQUIRE(h && osc_w, M3B_ERR_INVALID, "m3b_upload_osc_f64: null argument");

@@ -21,6 +21,17 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
 std::string& m3b_last_error_slot();     // thread-local last error (defined in m3b_api.cu)
 int m3b_peer_alloc(m3b_handle* h);      // the exported partial-histogram buffers + epoch flag of the peer exchange (m3b_api.cu)
 
+// Tuning knobs read from the environment exist only in -DM3B_EXPERIMENTS builds (A/B measurements); the product
+// library takes its configuration from m3b_config alone.
+static inline const char* experiment_env(const char* name) {
+#ifdef M3B_EXPERIMENTS
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 struct m3b_handle {
   m3b_config cfg{};
   int device = 0;
@@ -170,11 +181,16 @@ struct m3b_handle {
   int b_param_of_compact_row(int64_t c) const {  // parameter whose weight row holds compact index c
     return static_cast<int>(std::upper_bound(b_out_base.begin(), b_out_base.end(), c) - b_out_base.begin()) - 1;
   }
+  // slot layout as the upload found it: maximal runs of consecutive slots belonging to one parameter ("blocks": one
+  // systematic's (mode, var1, var2, var3) grid), and for each the number of times the parameter index went down before it
+  // ("super-block": one (sample, oscillation channel) in the reference's [sample][osc][syst][mode][var1][var2][var3] order)
+  std::vector<int64_t> b_run_start; std::vector<int32_t> b_run_super;
   int32_t* d_perm = nullptr;                     // order in which the binned fill kernel walks the events (sorted by spline-grid cell)
+  int32_t* d_bin_sorted = nullptr; void* d_static_sorted = nullptr; int16_t* d_norm_idx_sorted = nullptr; int32_t* d_osc_idx_sorted = nullptr;   // event table in walking order
   float4* d_bcoef = nullptr; float* d_bx = nullptr; float* d_bw = nullptr;
   BTile* d_btiles = nullptr; WTile* d_wtiles = nullptr; int32_t* d_ell = nullptr;
   uint64_t b_gather_per_step = 0;
-  int binned_eval_grid = 0;
+  int binned_eval_grid = 0, binned_threads = 256;
 
   // ---- batched proposals (m3b_step_batch): one -lnL slot per set in mapped host memory
   double* h_batch = nullptr; double* h_batch_dev = nullptr; size_t batch_cap = 0;

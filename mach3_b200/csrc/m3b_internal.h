@@ -80,8 +80,8 @@ struct BTile {                 // 1024 consecutive active splines of one paramet
   int64_t coef_off;            // first element of the parameter's [nseg][n_pad] block
   int32_t n_pad, param, k0, out0;   // row length, parameter, first spline of the tile in the row, first compact weight
 };
-struct WTile {                 // 32 consecutive events: their binned-spline pointers as ELL columns
-  int64_t off;                 // ell[off + j*32 + lane] = compact weight index of the lane's j-th pointer, -1 = none
+struct WTile {                 // 32 events (consecutive in the kernel's walking order): their binned-spline pointers as ELL columns
+  int64_t off;                 // ell[off + j*32 + lane] = the lane's j-th pointer, = compact weight index, -1 = none
   int32_t max_n, pad;
 };
 
@@ -154,7 +154,9 @@ struct FillArgs {
   double* evt_spline_d; double* evt_total_d;
   const int32_t* ell; const WTile* wtiles; int64_t n_wtiles;
   const int32_t* perm;         // binned fill: event handled by (warp tile, lane), nullptr = identity
-  int32_t binned_contiguous;   // experiments: 1 = contiguous runs of warp tiles per block instead of the grid-strided walk
+  const int32_t* bin_sorted;   // binned fill: event table in walking order (bin, static weight, norm indices), so the
+  const void* static_sorted;   // 32 lanes of a warp read consecutive elements; float or double like static_w / static_d
+  const int16_t* norm_idx_sorted; const int32_t* osc_idx_sorted;
   // optional per-block timeline (m3b_block_trace): 8 x u64 globaltimer ns per block
   unsigned long long* trace;
   alignas(16) unsigned char step_inline[kStepInlineMax];
@@ -286,9 +288,9 @@ cudaError_t fill_tma_occupancy(int smem_bytes, int* blocks_per_sm);
 int fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
 // BinnedSplineHandler path (m3b_binned.cu)
 cudaError_t launch_binned_eval(const FillArgs& a, int grid, cudaStream_t s);
-cudaError_t launch_binned_fill(const FillArgs& a, int grid, int smem_bytes, cudaStream_t s);
-cudaError_t binned_fill_set_smem(int smem_bytes);
-cudaError_t binned_fill_occupancy(int smem_bytes, bool f64, int* blocks_per_sm);
+cudaError_t launch_binned_fill(const FillArgs& a, int grid, int threads, int smem_bytes, cudaStream_t s);
+cudaError_t binned_fill_prepare(int smem_bytes, bool f64, int threads, int* blocks_per_sm);   // opt-in smem + occupancy
 int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live);
+cudaError_t launch_gather(void* dst, const void* src, const int32_t* perm, int64_t n, int elem_bytes, cudaStream_t s);
 
 }  // namespace m3b
