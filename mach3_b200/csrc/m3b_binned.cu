@@ -94,31 +94,34 @@ int binned_fill_smem_bytes(const FillArgs& a, bool hist_in_smem, bool w2_live) {
   return b > llh_scratch ? b : llh_scratch;
 }
 
-// per-event part: CalcWeightTotal's factors other than the binned splines, read either through the walking order (perm)
-// or from the copies already laid out in that order (streaming loads: L1 is for the weight gathers)
+// per-event part: CalcWeightTotal's factors other than the binned splines.  The event table is read from the copies laid
+// out in walking order (sort_event_table; streaming loads: L1 is for the weight gathers) in two phases, so that the
+// prefetch of the next tile only ISSUES loads: binned_event_load = the raw columns, binned_event_weight = what depends on
+// them (norm look-ups in the step table, the oscillation weight gather).
+constexpr int kBNormFront = 4;
 template <class R>
-struct BEvent { int64_t e; int bin; R w_pre, w_static; };
-template <bool F64, class R>
-__device__ __forceinline__ BEvent<R> binned_event(const FillArgs& a, const R* norm, const R* oscp, const R* statp, int64_t v) {
-  BEvent<R> o;
-  o.e = a.perm ? static_cast<int64_t>(__ldcs(a.perm + v)) : v;
-  const bool sorted = a.bin_sorted != nullptr;
-  o.bin = sorted ? __ldcs(a.bin_sorted + v) : a.bin[o.e];
-  R w_osc = 1;
-  if (oscp) {
-    const int64_t oi = a.osc_idx ? static_cast<int64_t>(sorted && a.osc_idx_sorted ? __ldcs(a.osc_idx_sorted + v) : a.osc_idx[o.e]) : (o.e < a.n_events ? o.e : 0);
-    w_osc = oi >= 0 ? oscp[oi] : R(1);
-  }
-  o.w_static = 1;
-  if (statp) o.w_static = sorted ? __ldcs(reinterpret_cast<const R*>(a.static_sorted) + v) : statp[o.e];
+struct BEvent { int32_t e, bin, oi; int16_t ni[kBNormFront]; R w_static; };
+template <class R>
+__device__ __forceinline__ void binned_event_load(const FillArgs& a, int64_t v, BEvent<R>& o) {
+  o.e = __ldcs(a.perm + v);
+  o.bin = __ldcs(a.bin_sorted + v);
+  o.oi = a.osc_idx_sorted ? __ldcs(a.osc_idx_sorted + v) : -1;
+  o.w_static = a.static_sorted ? __ldcs(reinterpret_cast<const R*>(a.static_sorted) + v) : R(1);
+  #pragma unroll
+  for (int j = 0; j < kBNormFront; ++j) o.ni[j] = j < a.norm_slots ? __ldcs(a.norm_idx_sorted + static_cast<int64_t>(j) * a.e_pad + v) : int16_t(-1);
+}
+template <class R>
+__device__ __forceinline__ R binned_event_weight(const FillArgs& a, const R* norm, const R* oscp, int64_t v, const BEvent<R>& o) {
   // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras
+  const R w_osc = (oscp && o.oi >= 0) ? __ldg(oscp + o.oi) : R(1);
   R w = 1;
-  for (int j = 0; j < a.norm_slots; ++j) {
-    const int i = sorted ? __ldcs(a.norm_idx_sorted + static_cast<int64_t>(j) * a.e_pad + v) : a.norm_idx[static_cast<int64_t>(j) * a.e_pad + o.e];
+  #pragma unroll
+  for (int j = 0; j < kBNormFront; ++j) w *= (o.ni[j] >= 0 ? norm[o.ni[j]] : R(1));
+  for (int j = kBNormFront; j < a.norm_slots; ++j) {
+    const int i = __ldcs(a.norm_idx_sorted + static_cast<int64_t>(j) * a.e_pad + v);
     w *= (i >= 0 ? norm[i] : R(1));
   }
-  o.w_pre = w * w_osc;
-  return o;
+  return w * w_osc;
 }
 
 // The fill kernel.  One warp = one warp tile of 32 events per iteration, tiles handed out grid-strided, one per warp of the
@@ -149,7 +152,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
   const R* norm = reinterpret_cast<const R*>(smem + (F64 ? a.step.off_norm_d : a.step.off_norm));
   const R* bw = F64 ? reinterpret_cast<const R*>(a.bw_d) : reinterpret_cast<const R*>(a.bw);
   const R* oscp = F64 ? reinterpret_cast<const R*>(a.osc_d) : reinterpret_cast<const R*>(a.osc);
-  const R* statp = F64 ? reinterpret_cast<const R*>(a.static_d) : reinterpret_cast<const R*>(a.static_w);
 
   auto load_desc = [&](int64_t t) {                 // max_n = -1: past the end
     WTile d; d.off = 0; d.max_n = -1; d.pad = 0;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
     if (d.max_n < 0) return;
     // events are processed in the order of their spline-grid cell (a.perm, built at upload): the 32 lanes of a warp --
     // and the warps of the block -- then gather from the same few sectors of every parameter's weight row
-    ev = binned_event<F64, R>(a, norm, oscp, statp, t * 32 + lane);
+    binned_event_load<R>(a, t * 32 + lane, ev);
     const int32_t* col = a.ell + d.off + lane;
     #pragma unroll
     for (int j = 0; j < kBFront; ++j) idx[j] = j < d.max_n ? __ldcs(col + j * 32) : -1;
@@ -169,7 +171,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kTiles;
   int64_t wt = static_cast<int64_t>(blockIdx.x) * kTiles + warp;
   WTile d_nxt = load_desc(wt);
-  BEvent<R> ev_nxt; ev_nxt.e = 0; ev_nxt.bin = -1; ev_nxt.w_pre = 0; ev_nxt.w_static = 0;
+  BEvent<R> ev_nxt; ev_nxt.e = 0; ev_nxt.bin = -1; ev_nxt.oi = -1; ev_nxt.w_static = 0;
+  #pragma unroll
+  for (int j = 0; j < kBNormFront; ++j) ev_nxt.ni[j] = -1;
   int idx_nxt[kBFront];
   #pragma unroll
   for (int j = 0; j < kBFront; ++j) idx_nxt[j] = -1;
@@ -183,12 +187,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
     for (int j = 0; j < kBFront; ++j) idx[j] = idx_nxt[j];
     #pragma unroll
     for (int j = 0; j < kBFront; ++j) gw[j] = idx[j] >= 0 ? __ldg(bw + idx[j]) : R(1);
+    const R w_pre = binned_event_weight<R>(a, norm, oscp, wt * 32 + lane, ev);
     // next tile's front and the descriptor after it
     d_nxt = d_nxt2;
     load_front(wt + stride, d_nxt, ev_nxt, idx_nxt);
     d_nxt2 = load_desc(wt + 2 * stride);
     // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras
-    R w = ev.w_pre;
+    R w = w_pre;
     R w_spl = 1;               // product of the binned weights alone (m3b_read_event_weights)
     #pragma unroll
     for (int j = 0; j < kBFront; ++j) if (idx[j] >= 0) { w *= gw[j]; w_spl *= gw[j]; }
@@ -383,9 +388,15 @@ static int sort_event_table(m3b_handle* h) {
     for (int j = 0; j < h->norm_slots; ++j)
       CK(launch_gather(h->d_norm_idx_sorted + static_cast<int64_t>(j) * h->e_pad, h->d_norm_idx + static_cast<int64_t>(j) * h->e_pad, h->d_perm, h->e_pad, 2, h->stream));
   }
-  if (h->d_osc_idx) {
+  if (h->use_osc) {
+    // without an index array the oscillation weights are per event: the index is the event itself (padding: none)
     CK(dev_alloc(h, &h->d_osc_idx_sorted, static_cast<size_t>(h->e_pad)));
-    CK(launch_gather(h->d_osc_idx_sorted, h->d_osc_idx, h->d_perm, h->e_pad, 4, h->stream));
+    if (h->d_osc_idx) CK(launch_gather(h->d_osc_idx_sorted, h->d_osc_idx, h->d_perm, h->e_pad, 4, h->stream));
+    else {
+      std::vector<int32_t> oi(static_cast<size_t>(h->e_pad), -1);
+      CK(cudaMemcpy(oi.data(), h->d_perm, sizeof(int32_t) * h->n_events, cudaMemcpyDeviceToHost));
+      CK(copy_sync(h, h->d_osc_idx_sorted, oi.data(), sizeof(int32_t) * oi.size(), cudaMemcpyHostToDevice));
+    }
   }
   return sort_static_weights(h);
 }
