@@ -168,8 +168,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
     for (int j = 0; j < kBFront; ++j) idx[j] = j < d.max_n ? __ldcs(col + j * 32) : -1;
   };
 
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * kTiles;
-  int64_t wt = static_cast<int64_t>(blockIdx.x) * kTiles + warp;
+  // tile of this warp in block iteration `it`: the block takes kTiles consecutive tiles, and the warp-to-tile assignment
+  // rotates with the iteration -- the upload orders the tiles of a span from long to short, and a fixed assignment would
+  // give the same warps the long tiles every time
+  const int64_t n_chunks = (a.n_wtiles + kTiles - 1) / kTiles;
+  auto tile_of = [&](int64_t it) -> int64_t {
+    const int64_t c = blockIdx.x + it * gridDim.x;
+    return c < n_chunks ? c * kTiles + ((warp + static_cast<int>(it)) & (kTiles - 1)) : a.n_wtiles;
+  };
+  int64_t it = 0;
+  int64_t wt = tile_of(0);
   WTile d_nxt = load_desc(wt);
   BEvent<R> ev_nxt; ev_nxt.e = 0; ev_nxt.bin = -1; ev_nxt.oi = -1; ev_nxt.w_static = 0;
   #pragma unroll
@@ -178,8 +186,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
   #pragma unroll
   for (int j = 0; j < kBFront; ++j) idx_nxt[j] = -1;
   load_front(wt, d_nxt, ev_nxt, idx_nxt);
-  WTile d_nxt2 = load_desc(wt + stride);
-  for (; wt < a.n_wtiles; wt += stride) {
+  WTile d_nxt2 = load_desc(tile_of(1));
+  for (; blockIdx.x + it * gridDim.x < n_chunks; ++it, wt = tile_of(it)) {
     const WTile d = d_nxt;
     const BEvent<R> ev = ev_nxt;
     int idx[kBFront]; R gw[kBFront];
@@ -190,8 +198,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
     const R w_pre = binned_event_weight<R>(a, norm, oscp, wt * 32 + lane, ev);
     // next tile's front and the descriptor after it
     d_nxt = d_nxt2;
-    load_front(wt + stride, d_nxt, ev_nxt, idx_nxt);
-    d_nxt2 = load_desc(wt + 2 * stride);
+    load_front(tile_of(it + 1), d_nxt, ev_nxt, idx_nxt);
+    d_nxt2 = load_desc(tile_of(it + 2));
+    if (d.max_n < 0) continue;                         // the last chunk may be short
     // CalcWeightTotal: norms first, then the weight pointers in push order: osc, binned splines, extras
     R w = w_pre;
     R w_spl = 1;               // product of the binned weights alone (m3b_read_event_weights)
