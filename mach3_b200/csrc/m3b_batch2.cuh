@@ -19,6 +19,17 @@
 //                           wavefronts per (slot, warp) instead of 16; the rank branch is warp-uniform and three-way, so
 //                           a set outside the majority segment costs one extra test, not a second polynomial.
 //
+//   packed arithmetic       a lane's two events ride in the two halves of FFMA2 / FMUL2 (sm_100 packed fp32: two independent
+//                           IEEE fmaf per instruction, so the weights stay bit-identical): 3 + 1 instructions per
+//                           (slot, set) for both events.  The packed operands must sit in aligned register pairs, so one
+//                           warp per staged row first re-packs it in shared memory from {y,b,c,d} per event to
+//                           {y0,y1,b0,b1} | {c0,c1,d0,d1} per event PAIR (each lane rewrites only its own two float4: no
+//                           hazard inside the row) and a second mbarrier per stage tells the block the rows are ready
+//                           (packing in registers instead -- four pair moves per row -- was measured slower: 36.1 vs
+//                           31.5 ms on config 5); dx is duplicated into its pair in registers;
+//   a cheap epilogue        the per-(event,set) norm look-ups walk pre-computed shared-memory offsets (absent slots point
+//                           at a 1.0 entry): 8 LDS + 8 FMUL per set instead of an address computation and a branch each.
+//
 // Slots whose sets select more than three distinct segments, and batches on handles without a frozen W2, take the first
 // kernel / the sequential path (m3b_batch_try, m3b_step_batch).
 #pragma once
@@ -31,10 +42,13 @@ constexpr int kB2SW = 16;           // sets per consumer warp
 constexpr int kB2CW = kB2Sets / kB2SW;
 constexpr int kB2CT = kB2CW * 32;
 constexpr int kB2RowF4 = kB2E + 1;  // staged row stride in float4 (+16 B: rows r, r' at one event land in different banks)
-constexpr int kB2StageRows = 32;    // cubic rows per ring stage
-constexpr int kB2Stages = 4;
-constexpr int kB2StageBytes = kB2StageRows * kB2RowF4 * 16;
-constexpr int kB2MaxGroups = 64;
+constexpr int kB2MaxStageRows = 32; // cubic rows per ring stage (the host picks 32, 24 or 16 and 2..4 stages: what fits next to the tables)
+constexpr int kB2MaxStages = 4;
+constexpr int kB2MaxGroups = 96;
+__host__ __device__ inline int batch2_norm_stride(int n_norm) { return (n_norm + 1) | 1; }     // + the 1.0 entry; odd: lanes with different indices hit different banks
+__host__ __device__ inline int batch2_tables_bytes(int max_nc, int max_nl, int n_norm) {
+  return (max_nc * kB2Sets * 4 + max_nc * kB2CW * 4 + max_nl * kB2Sets * 4 + kB2Sets * batch2_norm_stride(n_norm) * 4 + max_nc * 8 + 127) & ~127;
+}
 
 struct Batch2Group { int32_t c0, c1, n_rows, row0; };   // slots [c0,c1) of the signature; rows [row0,row0+n_rows) of its row list
 struct Batch2Sig {
@@ -53,6 +67,7 @@ struct Batch2Args {
   const float* t_dx; const uint32_t* t_code; const float* t_val; const int32_t* t_rowlist; const int32_t* t_slot; const Batch2Group* t_group;
   const float* t_norm;             // [n_norm][256]
   int32_t n_norm, n_sets, max_nc, max_nl;
+  int32_t n_stages, stage_rows;
   const int32_t* bin; const float* osc; const int32_t* osc_idx; const float* static_w;
   const int16_t* norm_idx; int32_t norm_slots; int64_t e_pad, n_events;
   double* hist;                    // [n_bins][256]
@@ -63,12 +78,31 @@ struct Batch2Args {
 __device__ __forceinline__ void mbar_arrive2(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float horner(const float4& k, float dx) { return fmaf(dx, fmaf(dx, fmaf(dx, k.w, k.z), k.y), k.x); }
-
+// Packed fp32 pairs live in 64-bit registers (lo = event lane, hi = event lane + 32).  fma.rn.f32x2 / mul.rn.f32x2 are two
+// independent IEEE operations per instruction, so every weight equals the scalar fmaf path's bit for bit.
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk2_ffma(pk2 a, pk2 b, pk2 c) { pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ pk2 pk2_mul(pk2 a, pk2 b) { pk2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2 pk2_make(float lo, float hi) { pk2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+__device__ __forceinline__ float pk2_lo(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float pk2_hi(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+// one staged row for the lane's two events, as re-packed in shared memory: {y pair, b pair} | {c pair, d pair}, two LDS.128
+struct B2Row { pk2 y, b, c, d; };
+__device__ __forceinline__ B2Row b2_row(const float4* rp) {
+  const ulonglong2 yb = *reinterpret_cast<const ulonglong2*>(rp), cd = *reinterpret_cast<const ulonglong2*>(rp + 32);
+  B2Row k; k.y = yb.x; k.b = yb.y; k.c = cd.x; k.d = cd.y;
+  return k;
+}
+// fmaf(dx, fmaf(dx, fmaf(dx, d, c), b), y)          (Splines/SplineMonolith.cpp:765), both events
+__device__ __forceinline__ pk2 horner2(const B2Row& k, pk2 dx) {
+  return pk2_ffma(dx, pk2_ffma(dx, pk2_ffma(dx, k.d, k.c), k.b), k.y);
+}
 // The producer's state: which unit / slot group goes into the ring next.  The producer role is taken by consumer warp 0
 // (a 17th warp would put five warps on one scheduler's register file and cap every thread at 96 registers; 16 warps get
 // 128): before warp 0 waits for a stage it makes sure that stage has been issued, and it issues further ahead whenever a
-// ring slot is free -- a few dozen instructions per stage next to ~2500 of evaluation.
+// ring slot is free -- a few dozen instructions per stage next to ~2500 of evaluation.  The state lives in shared memory
+// and is loaded into registers only inside pump(): every thread runs the same code, and 20 registers of producer state
+// held across the evaluation loops would be spilled by all 512.
 struct Batch2Producer {
   int stage = 0; uint32_t phase = 1;       // a fresh mbarrier passes a wait on the "previous" phase
   int u = -2, g = 0, n_groups = 0, nl = 0; // u == -2: fetch the next unit
@@ -76,7 +110,6 @@ struct Batch2Producer {
   TileDesc td{};
   int lane0 = 0;
   bool done = false;
-  unsigned issued = 0;
 };
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -87,27 +120,35 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_constant__ Batch2Args a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full_bar[kB2Stages], empty_bar[kB2Stages];
-  __shared__ int4 s_desc[kB2Stages];      // {unit, sig, group (-1: the TF1 group), 0}; unit < 0 = no more work
+  __shared__ __align__(8) uint64_t full_bar[kB2MaxStages], ready_bar[kB2MaxStages], empty_bar[kB2MaxStages];
+  __shared__ int4 s_desc[kB2MaxStages];   // {unit, sig, group (-1: the TF1 group), 0}; unit < 0 = no more work
+  __shared__ Batch2Producer s_pr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // shared-memory map: [dx nc*256 f32][code nc*16 u32][val nl*256 f32][norm 256*nnp f32][slot nc int2][ring]
-  const int nnp = a.n_norm | 1;
+  const int nnp = batch2_norm_stride(a.n_norm);
   float* s_dx = reinterpret_cast<float*>(smem);
   uint32_t* s_code = reinterpret_cast<uint32_t*>(s_dx + a.max_nc * kB2Sets);
   float* s_val = reinterpret_cast<float*>(s_code + a.max_nc * kB2CW);
   float* s_norm = s_val + a.max_nl * kB2Sets;
   int2* s_slot = reinterpret_cast<int2*>(s_norm + kB2Sets * nnp);
-  const int tables_bytes = (a.max_nc * kB2Sets * 4 + a.max_nc * kB2CW * 4 + a.max_nl * kB2Sets * 4 + kB2Sets * nnp * 4 + a.max_nc * 8 + 127) & ~127;
-  unsigned char* ring = smem + tables_bytes;
+  unsigned char* ring = smem + batch2_tables_bytes(a.max_nc, a.max_nl, a.n_norm);
+  const int stage_bytes = a.stage_rows * kB2RowF4 * 16;
+  const int n_stages = a.n_stages;
 
-  if (tid == 0) for (int s = 0; s < kB2Stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kB2CW); }
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], kB2CW); mbar_init(&empty_bar[s], kB2CW); }
+    s_pr = Batch2Producer();
+  }
+  // norm table [set][nnp]; entry n_norm of every set = 1.0 (where absent norm slots point)
   for (int i = tid; i < a.n_norm * kB2Sets; i += kB2CT) s_norm[(i % kB2Sets) * nnp + i / kB2Sets] = a.t_norm[i];
+  for (int i = tid; i < kB2Sets; i += kB2CT) s_norm[i * nnp + a.n_norm] = 1.0f;
   __syncthreads();
 
   // ---------------------------------------------------------------- producer (warp 0 only; all 32 lanes, convergent)
-  Batch2Producer pr;
   // issues ONE stage (a slot group, a TF1 group or the terminal marker); block = wait for the ring slot, else give up
   auto pump = [&](bool block) -> bool {
+    Batch2Producer pr = s_pr;
+    __syncwarp();
     if (pr.done) return false;
     if (pr.u == -2) {
       int u = 0;
@@ -122,10 +163,10 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
       }
     }
     if (!mbar_test(&empty_bar[pr.stage], pr.phase)) {
-      if (!block) return false;
+      if (!block) { if (lane == 0) s_pr = pr; __syncwarp(); return false; }      // (the unit fetched above is kept)
       mbar_wait(&empty_bar[pr.stage], pr.phase);
     }
-    unsigned char* dst = ring + static_cast<size_t>(pr.stage) * kB2StageBytes;
+    unsigned char* dst = ring + static_cast<size_t>(pr.stage) * stage_bytes;
     if (pr.u >= a.n_units) {
       if (lane == 0) { s_desc[pr.stage] = make_int4(-1, 0, 0, 0); mbar_arrive2(&full_bar[pr.stage]); }
       pr.done = true;
@@ -151,9 +192,10 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         bulk_g2s(dst + static_cast<size_t>(l) * kB2E * 8, pr.td.lin + static_cast<int64_t>(l) * a.T + pr.lane0, kB2E * 8u, &full_bar[pr.stage]);
       pr.u = -2;
     }
+    if (++pr.stage == n_stages) { pr.stage = 0; pr.phase ^= 1u; }
     __syncwarp();
-    if (++pr.stage == kB2Stages) { pr.stage = 0; pr.phase ^= 1u; }
-    ++pr.issued;
+    if (lane == 0) s_pr = pr;
+    __syncwarp();
     return true;
   };
 
@@ -162,14 +204,15 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
     const int set0 = warp * kB2SW;
     const bool active = set0 < a.n_sets;                // warps whose sets are all padding only keep the ring moving
     int stage = 0; uint32_t phase = 0; int cur_sig = -1, cur_nl = 0; int64_t off_group = 0;
-    float W0[kB2SW], W1[kB2SW];
+    pk2 W[kB2SW];                                       // running products: lo = event lane, hi = event lane + 32
+    const pk2 one2 = pk2_make(1.0f, 1.0f);
     #pragma unroll
-    for (int q = 0; q < kB2SW; ++q) { W0[q] = 1.0f; W1[q] = 1.0f; }
-    unsigned consumed = 0;
+    for (int q = 0; q < kB2SW; ++q) W[q] = one2;
+    unsigned consumed = 0, issued = 0;
     while (true) {
       if (warp == 0) {
-        while (pr.issued <= consumed && pump(true)) {}                   // the stage about to be waited for must be in flight
-        while (pr.issued < consumed + kB2Stages && pump(false)) {}       // and as many further ones as the ring has room for
+        while (issued <= consumed && pump(true)) ++issued;                    // the stage about to be waited for must be in flight
+        while (issued < consumed + n_stages && pump(false)) ++issued;         // and as many further ones as the ring has room for
       }
       mbar_wait(&full_bar[stage], phase);
       ++consumed;
@@ -185,38 +228,72 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         cur_sig = d.y; off_group = sg.off_group; cur_nl = sg.nl;
         asm volatile("bar.sync 1, %0;" ::"r"(kB2CT) : "memory");
       }
-      const unsigned char* src = ring + static_cast<size_t>(stage) * kB2StageBytes;
+      unsigned char* src = ring + static_cast<size_t>(stage) * stage_bytes;
       if (d.z >= 0) {
-        // ---- a group of TSpline3 slots: fmaf Horner on the set's segment, running products in the reference's slot order
+        // ---- a group of TSpline3 slots
         const Batch2Group gr = a.t_group[off_group + d.z];
+        // re-pack this warp's share of the staged rows for packed arithmetic: lane l owns float4 l and l+32 of a row
+        {
+          float4* all = reinterpret_cast<float4*>(src) + lane;
+          for (int r = warp; r < gr.n_rows; r += kB2CW) {
+            float4* rp = all + r * kB2RowF4;
+            const float4 e0 = rp[0], e1 = rp[32];
+            rp[0] = make_float4(e0.x, e1.x, e0.y, e1.y);
+            rp[32] = make_float4(e0.z, e1.z, e0.w, e1.w);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the ring slot is re-filled by bulk copies later
+          __syncwarp();
+          if (lane == 0) mbar_arrive2(&ready_bar[stage]);
+          mbar_wait(&ready_bar[stage], phase);
+        }
+        // fmaf Horner on the set's segment, running products in the reference's slot order
         const float4* rows = reinterpret_cast<const float4*>(src) + lane;
         for (int c = gr.c0; active && c < gr.c1; ++c) {
           const int2 si = s_slot[c];                    // {first staged row of the slot in this stage, distinct segments}
           const float4* rp = rows + si.x * kB2RowF4;
           const float4* dxv = reinterpret_cast<const float4*>(s_dx + c * kB2Sets + set0);
-          float dx[kB2SW];
-          #pragma unroll
-          for (int j = 0; j < kB2SW / 4; ++j) { const float4 v = dxv[j]; dx[4 * j] = v.x; dx[4 * j + 1] = v.y; dx[4 * j + 2] = v.z; dx[4 * j + 3] = v.w; }
-          const float4 k00 = rp[0], k01 = rp[32];
-          if (si.y == 1) {
+          const B2Row k0 = b2_row(rp);
+          // 2 bits per set, warp-uniform; rank 0 = the slot's most popular segment
+          const uint32_t code = si.y == 1 ? 0u : s_code[c * kB2CW + warp];
+          if (code == 0u) {                             // all 16 sets of this warp on the slot's first row
             #pragma unroll
-            for (int q = 0; q < kB2SW; ++q) { W0[q] *= horner(k00, dx[q]); W1[q] *= horner(k01, dx[q]); }
+            for (int hq = 0; hq < kB2SW; hq += 8) {     // dx in two halves: 16 registers live instead of 32
+              pk2 dx[8];
+              #pragma unroll
+              for (int j = 0; j < 2; ++j) {             // (dx,dx): the same set's dx for both events of the lane
+                const float4 v = dxv[hq / 4 + j];
+                dx[4 * j] = pk2_make(v.x, v.x); dx[4 * j + 1] = pk2_make(v.y, v.y); dx[4 * j + 2] = pk2_make(v.z, v.z); dx[4 * j + 3] = pk2_make(v.w, v.w);
+              }
+              #pragma unroll
+              for (int q = 0; q < 8; ++q) W[hq + q] = pk2_mul(W[hq + q], horner2(k0, dx[q]));
+            }
           } else {
-            const uint32_t code = s_code[c * kB2CW + warp];
-            const float4 k10 = rp[kB2RowF4], k11 = rp[kB2RowF4 + 32];
-            const float4 k20 = rp[(si.y - 1) * kB2RowF4], k21 = rp[(si.y - 1) * kB2RowF4 + 32];
+            // mixed ranks: a warp-uniform branch per set.  (Evaluating both candidate rows and selecting keeps the 16
+            // chains independent but doubles the FMA-pipe work -- FFMA2 halves the issue slots, not the pipe time:
+            // scripts/microbench/ffma2_rate.cu -- and measured slower: 34.8 vs 32.1 ms on config 5.)
+            const B2Row k1 = b2_row(rp + kB2RowF4), k2 = b2_row(rp + (si.y - 1) * kB2RowF4);
             #pragma unroll
-            for (int q = 0; q < kB2SW; ++q) {
-              const uint32_t r = (code >> (2 * q)) & 3u;        // warp-uniform
-              if (r == 0u) { W0[q] *= horner(k00, dx[q]); W1[q] *= horner(k01, dx[q]); }
-              else if (r == 1u) { W0[q] *= horner(k10, dx[q]); W1[q] *= horner(k11, dx[q]); }
-              else { W0[q] *= horner(k20, dx[q]); W1[q] *= horner(k21, dx[q]); }
+            for (int hq = 0; hq < kB2SW; hq += 8) {
+              pk2 dx[8];
+              #pragma unroll
+              for (int j = 0; j < 2; ++j) {             // (dx,dx): the same set's dx for both events of the lane
+                const float4 v = dxv[hq / 4 + j];
+                dx[4 * j] = pk2_make(v.x, v.x); dx[4 * j + 1] = pk2_make(v.y, v.y); dx[4 * j + 2] = pk2_make(v.z, v.z); dx[4 * j + 3] = pk2_make(v.w, v.w);
+              }
+              #pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                pk2 t;
+                if ((code & (3u << (2 * (hq + q)))) == 0u) t = horner2(k0, dx[q]);
+                else if ((code & (2u << (2 * (hq + q)))) == 0u) t = horner2(k1, dx[q]);
+                else t = horner2(k2, dx[q]);
+                W[hq + q] = pk2_mul(W[hq + q], t);
+              }
             }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive2(&empty_bar[stage]);
-        if (++stage == kB2Stages) { stage = 0; phase ^= 1u; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         continue;
       }
       // ---- the unit's last stage: TF1 slots, then CalcWeightTotal + fill for both events and all 16 sets
@@ -230,49 +307,60 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         osc0 = o0 >= 0 ? a.osc[o0] : 1.f; osc1 = o1 >= 0 ? a.osc[o1] : 1.f;
       }
       if (a.static_w) { st0 = a.static_w[ev0]; st1 = a.static_w[ev1]; }
-      int ni0[4] = {-1, -1, -1, -1}, ni1[4] = {-1, -1, -1, -1};
+      // shared-memory offsets of the (at most four: m3b_batch2_try) norm slots' values for set0 (absent: the 1.0 entry)
+      int np0[4], np1[4];
       #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < a.norm_slots) { ni0[j] = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + ev0]; ni1[j] = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + ev1]; }
+      for (int j = 0; j < 4; ++j) {
+        int i0 = -1, i1 = -1;
+        if (j < a.norm_slots) { i0 = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + ev0]; i1 = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + ev1]; }
+        np0[j] = set0 * nnp + (i0 >= 0 ? i0 : a.n_norm);
+        np1[j] = set0 * nnp + (i1 >= 0 ? i1 : a.n_norm);
+      }
+      // every warp arrives on the stage's second barrier once per use, whether or not the stage had rows to re-pack:
+      // its phase must advance in step with the ring's
+      if (lane == 0) mbar_arrive2(&ready_bar[stage]);
       if (active) {
         const float2* lin = reinterpret_cast<const float2*>(src) + lane;
         for (int l = 0; l < cur_nl; ++l) {
           const float2 c0 = lin[l * kB2E], c1 = lin[l * kB2E + 32];
           const float4* vv = reinterpret_cast<const float4*>(s_val + l * kB2Sets + set0);
+          // fmaf(a, x, b) (Splines/SplineMonolith.cpp:800) for both events: a, b packed over the events, x per set
+          const pk2 a2 = pk2_make(c0.x, c1.x), b2 = pk2_make(c0.y, c1.y);
           #pragma unroll
           for (int j = 0; j < kB2SW / 4; ++j) {
             const float4 v = vv[j];
-            W0[4 * j] *= fmaf(c0.x, v.x, c0.y); W1[4 * j] *= fmaf(c1.x, v.x, c1.y);
-            W0[4 * j + 1] *= fmaf(c0.x, v.y, c0.y); W1[4 * j + 1] *= fmaf(c1.x, v.y, c1.y);
-            W0[4 * j + 2] *= fmaf(c0.x, v.z, c0.y); W1[4 * j + 2] *= fmaf(c1.x, v.z, c1.y);
-            W0[4 * j + 3] *= fmaf(c0.x, v.w, c0.y); W1[4 * j + 3] *= fmaf(c1.x, v.w, c1.y);
+            W[4 * j] = pk2_mul(W[4 * j], pk2_ffma(a2, pk2_make(v.x, v.x), b2));
+            W[4 * j + 1] = pk2_mul(W[4 * j + 1], pk2_ffma(a2, pk2_make(v.y, v.y), b2));
+            W[4 * j + 2] = pk2_mul(W[4 * j + 2], pk2_ffma(a2, pk2_make(v.z, v.z), b2));
+            W[4 * j + 3] = pk2_mul(W[4 * j + 3], pk2_ffma(a2, pk2_make(v.w, v.w), b2));
           }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive2(&empty_bar[stage]);
-      if (++stage == kB2Stages) { stage = 0; phase ^= 1u; }
+      if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       if (active) {
         // CalcWeightTotal + fill, per (event, set): norms (reference order), osc, spline, static
+        double* h0 = a.hist + static_cast<int64_t>(bin0 >= 0 ? bin0 : 0) * kB2Sets + set0;
+        double* h1 = a.hist + static_cast<int64_t>(bin1 >= 0 ? bin1 : 0) * kB2Sets + set0;
+        // two passes, so the 16 sets' shared-memory look-ups and products are independent of the atomics' ordering
         #pragma unroll
         for (int q = 0; q < kB2SW; ++q) {
-          const int set = set0 + q;
-          const float* nv = s_norm + set * nnp;
           float w0 = 1.0f, w1 = 1.0f;
           #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < a.norm_slots) { w0 *= (ni0[j] >= 0 ? nv[ni0[j]] : 1.0f); w1 *= (ni1[j] >= 0 ? nv[ni1[j]] : 1.0f); }
-          for (int j = 4; j < a.norm_slots; ++j) {
-            const int i0 = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + ev0], i1 = a.norm_idx[static_cast<int64_t>(j) * a.e_pad + ev1];
-            w0 *= (i0 >= 0 ? nv[i0] : 1.0f); w1 *= (i1 >= 0 ? nv[i1] : 1.0f);
+          for (int j = 0; j < 4; ++j) { w0 *= s_norm[np0[j] + q * nnp]; w1 *= s_norm[np1[j] + q * nnp]; }
+          w0 *= osc0; w0 *= pk2_lo(W[q]); w0 *= st0;
+          w1 *= osc1; w1 *= pk2_hi(W[q]); w1 *= st1;
+          W[q] = pk2_make(w0, w1);
+        }
+        #pragma unroll
+        for (int q = 0; q < kB2SW; ++q) {
+          const float w0 = pk2_lo(W[q]), w1 = pk2_hi(W[q]);
+          if (set0 + q < a.n_sets) {
+            if (w0 > 0.f && bin0 >= 0) atomicAdd(h0 + q, static_cast<double>(w0));
+            if (w1 > 0.f && bin1 >= 0) atomicAdd(h1 + q, static_cast<double>(w1));
           }
-          w0 *= osc0; w0 *= W0[q]; w0 *= st0;
-          w1 *= osc1; w1 *= W1[q]; w1 *= st1;
-          if (set < a.n_sets) {
-            if (w0 > 0.f && bin0 >= 0) atomicAdd(a.hist + static_cast<int64_t>(bin0) * kB2Sets + set, static_cast<double>(w0));
-            if (w1 > 0.f && bin1 >= 0) atomicAdd(a.hist + static_cast<int64_t>(bin1) * kB2Sets + set, static_cast<double>(w1));
-          }
-          W0[q] = 1.0f; W1[q] = 1.0f;
+          W[q] = one2;
         }
       }
     }
@@ -294,7 +382,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   if (h->binned || !h->splines_done || h->first_time_w2 || h->cfg.update_w2 || n_sets > kB2Sets || h->T % kB2E != 0) return M3B_OK;
   if (h->cfg.flags & (M3B_FLAG_NO_BATCH_KERNEL | M3B_FLAG_BATCH_KERNEL_V1)) return M3B_OK;
   if (h->tiles_dirty || !h->d_tiles) return M3B_OK;     // first step has not run yet
-  if (h->Kmax > 64 || h->norm_slots > kMaxNormSlots) return M3B_OK;
+  if (h->Kmax > 64 || h->norm_slots > 4) return M3B_OK;        // more norm parameters per event: first-generation kernel
   CK(cudaSetDevice(h->device));
   const int P = h->P, S = kB2Sets, n_sigs = static_cast<int>(h->sigs.size());
   // 1. segments of every set, in order (SplineBase::FindSplineSegment keeps its cached-segment history); the handle's
@@ -308,7 +396,20 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
     if (rc != M3B_OK) return rc;
   }
   auto decline = [&]() { h->curr_segment = curr_save; h->segments = seg_save; h->param_values = val_save; return M3B_OK; };
-  // 2. per signature and slot: distinct segments -> staged rows (most popular first); per set: dx and its rank
+  // 2. shared-memory budget: the per-set tables + a ring of 2..4 stages of 32, 24 or
+  //    16 rows, whatever fits (more stages first: the ring hides the bulk-copy latency, the row count only sets how many
+  //    slots share one barrier round)
+  const int Nn = h->n_norm_values;
+  const int tables_bytes = batch2_tables_bytes(h->max_nc, h->max_nl, Nn);
+  int n_stages = 0, stage_rows = 0;
+  {
+    const int budget = 232448 - 1024 - tables_bytes;
+    const int cand[][2] = {{4, 32}, {3, 32}, {4, 24}, {3, 24}, {4, 16}, {2, 32}, {3, 16}, {2, 24}, {2, 16}};
+    for (const auto& c : cand)
+      if (c[0] * c[1] * kB2RowF4 * 16 <= budget && h->max_nl * kB2E * 8 <= c[1] * kB2RowF4 * 16) { n_stages = c[0]; stage_rows = c[1]; break; }
+    if (n_stages == 0) return decline();                // too many parameters for the tables: first-generation kernel
+  }
+  // 3. per signature and slot: distinct segments -> staged rows (most popular first); per set: dx and its rank
   std::vector<Batch2Sig> bs(n_sigs);
   std::vector<float> t_dx, t_val; std::vector<uint32_t> t_code; std::vector<int32_t> t_rowlist, t_slot; std::vector<Batch2Group> t_group;
   for (int g = 0; g < n_sigs; ++g) {
@@ -338,7 +439,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
         rank_of[best] = n_rank++; slot_rows.push_back(segbase + best); used[best] = 0;
       }
       if (n_rank > 3) return decline();      // this kernel stages at most three segments per slot
-      if (cur.n_rows + n_rank > kB2StageRows) {          // close the group: its rows fill one ring stage
+      if (cur.n_rows + n_rank > stage_rows) {            // close the group: its rows fill one ring stage
         cur.c1 = c; t_group.push_back(cur);
         cur = Batch2Group{c, c, 0, rows};
       }
@@ -360,16 +461,11 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
       const int p = pool[2 * sd.nc + l];
       for (int s = 0; s < S; ++s) t_val[b.off_val + static_cast<size_t>(l) * S + s] = val[static_cast<size_t>(s < n_sets ? s : n_sets - 1) * P + p];
     }
-    if (sd.nl * kB2E * 8 > kB2StageBytes) return decline();
   }
-  const int Nn = h->n_norm_values;
   std::vector<float> t_norm(static_cast<size_t>(std::max(Nn, 1)) * S, 1.f);
   for (int n = 0; n < Nn; ++n)
     for (int s = 0; s < S; ++s) t_norm[static_cast<size_t>(n) * S + s] = static_cast<float>(norm_pars[static_cast<size_t>(s < n_sets ? s : n_sets - 1) * Nn + n]);
-  // 3. shared-memory budget: tables + the ring
-  const int tables_bytes = (h->max_nc * S * 4 + h->max_nc * kB2CW * 4 + h->max_nl * S * 4 + S * (Nn | 1) * 4 + h->max_nc * 8 + 127) & ~127;
-  const int smem = tables_bytes + kB2Stages * kB2StageBytes;
-  if (smem > 232448 - 1024) return decline();           // too many parameters for the tables: first-generation kernel
+  const int smem = tables_bytes + n_stages * stage_rows * kB2RowF4 * 16;
   // 4. device staging (grown on demand, kept in the handle; shared with the first kernel's buffers)
   auto grow = [&](void** p, size_t& cap, size_t bytes) -> cudaError_t {
     if (cap >= bytes && *p) return cudaSuccess;
@@ -415,6 +511,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   a.t_norm = static_cast<const float*>(h->bt_norm); a.t_slot = static_cast<const int32_t*>(h->bt_slot);
   a.t_group = static_cast<const Batch2Group*>(h->bt_group);
   a.n_norm = Nn; a.n_sets = n_sets; a.max_nc = h->max_nc; a.max_nl = h->max_nl;
+  a.n_stages = n_stages; a.stage_rows = stage_rows;
   a.bin = h->d_bin; a.osc = h->use_osc ? h->d_osc : nullptr; a.osc_idx = h->d_osc_idx; a.static_w = h->d_static;
   a.norm_idx = h->d_norm_idx; a.norm_slots = h->norm_slots; a.e_pad = h->e_pad; a.n_events = h->n_events;
   a.hist = static_cast<double*>(h->bt_hist); a.n_bins = h->n_bins; a.counter = h->d_tile_counter;
