@@ -711,6 +711,14 @@ def measure_cfg4(args, local=0, want_cpu=True):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     kms = kern_ms / max(kern_n, 1)
     info = h.info()
+    traffic, traffic_src = None, None
+    try:      # DRAM bytes of the two launches from the committed ncu captures of this same workload
+        pj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_full_binned_fill_cfg4.json")))
+        if pj.get("config", {}).get("events") == w.n_events:
+            traffic = float(pj["dram_bytes_per_launch"]) + float(pj["eval_kernel"]["dram_bytes_per_launch"])
+            traffic_src = "profiles/r02_ncu_full_binned_fill_cfg4.json (dram__bytes_read.sum + dram__bytes_write.sum: fill launch + eval launch)"
+    except Exception:
+        pass
     rec = {"metric": "reweighted events/s per host-synchronised MCMC step (binned-spline eval + fill + Barlow-Beeston LLH)",
            "value": w.n_events / (t_sync / K), "unit": "events/s", "n_gpus": 1, "steps": K, "warmup": W,
            "ms_per_step": 1e3 * t_sync / K, "binned_spline_evals_per_s": n_act / (t_sync / K), "higher_is_better": True,
@@ -721,7 +729,7 @@ def measure_cfg4(args, local=0, want_cpu=True):
                             % (n_act * 20 / 1e6, n_act * 4 / 1e6)},
            "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": alg / (kms * 1e-3) / 1e9 / peak, "kernel": "m3b::binned_eval_kernel + m3b::binned_fill_kernel",
-                        "kernel_ms": kms, "algorithmic_bytes_per_launch": alg, "traffic": None,
+                        "kernel_ms": kms, "algorithmic_bytes_per_launch": alg, "traffic": traffic, "traffic_source": traffic_src,
                         "note": "kernel_ms = eval + fill launches of one step, from the library's CUDA events"},
            "e2e": {"value": w.n_events / (t_sync / K), "unit": "events/s", "ms_per_step": 1e3 * t_sync / K,
                    "h2d_bytes_per_step": 12 * w.n_systs + 4 * w.n_norm_params, "d2h_bytes_per_step": 16,
