@@ -610,6 +610,7 @@ def main_b200(args):
         ex = line["extra"]
         for name, fn in (("cfg2", lambda: measure_monolith(args, synth.CFG2, 1, 0, local, None, torch, W, max(K, 100),
                                                            want_cpu_baseline=not args.no_cpu_baseline, cpu_sample=synth.CFG2.n_events)),
+                         ("cfg2_e2e_binned_osc", lambda: measure_binned_osc(args, local, W, max(K, 100))),
                          ("cfg4", lambda: measure_cfg4(args, local, not args.no_cpu_baseline)),
                          ("cfg5", lambda: measure_cfg5(args, local, not args.no_cpu_baseline)),
                          ("incumbent_gpu", lambda: measure_incumbent(local))):
@@ -619,6 +620,46 @@ def main_b200(args):
                 ex[name] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
     return rc
+
+
+def measure_binned_osc(args, local, W, K):
+    """e2e with a BINNED oscillator (NuOscillator's binned mode: events index a small table of oscillation weights,
+    SampleHandlerFD's osc pointers then point into that table): config 2, the per-step host input is the table, not one
+    weight per event.  Host-synchronised m3b_step(host pars, host norms, host table) + m3b_llh per step."""
+    from mach3_b200 import lib, synth
+    w = synth.CFG2
+    n_osc = 4096
+    h = lib.Handle(device=local, test_statistic=w.test_statistic, update_w2=False, tile_events=args.tile)
+    upload_monolith(h, w, 0, w.n_events)
+    h.upload_binning(synth.bin_edges(w))
+    ev = synth.make_events(w, 0, w.n_events)
+    osc_idx = ((np.arange(w.n_events, dtype=np.int64) * 2654435761) % n_osc).astype(np.int32)
+    h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, osc_idx, n_osc,
+                    ev["static_w"])
+    del ev
+    rng = np.random.default_rng(11)
+    tabs = []
+    for _ in range(4):
+        t = h.alloc_host(n_osc, np.float32)
+        t[:] = rng.uniform(0.2, 1.0, n_osc).astype(np.float32)
+        tabs.append(t)
+    props = [synth.proposal(w, k) for k in range(W + K + 1)]
+    h.step(*props[0], tabs[0]); h.llh()
+    h.upload_data(np.random.default_rng(w.seed).poisson(h.read_hist()[0]).astype(np.float64))
+    for k in range(W):
+        h.step(*props[k], tabs[k % 4]); h.llh_fast()
+    h.synchronize()
+    t0 = time.perf_counter()
+    for k in range(K):
+        h.step(*props[W + k], tabs[k % 4]); llh = h.llh_fast()
+    dt = (time.perf_counter() - t0) / K
+    for t in tabs:
+        h.free_host(t)
+    h.close()
+    return {"workload": w.name, "osc_table_entries": n_osc, "ms_per_step": 1e3 * dt, "value": w.n_events / dt, "unit": "events/s",
+            "h2d_bytes_per_step": int(4 * n_osc + 12 * w.n_params + 4 * w.n_norm_params), "d2h_bytes_per_step": 16, "llh_last": float(llh),
+            "what": "host-synchronised step with the oscillation weights as a 4096-entry table in host memory (binned "
+                    "oscillator): the per-step host input shrinks from 4 B per event to the table"}
 
 
 # ---------------------------------------------------------------------------------------------
