@@ -890,7 +890,7 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
       h->hist_in_smem = smem <= (hm ? atoi(hm) : 200) * 1024;
       if (!h->hist_in_smem) smem = binned_fill_smem_bytes(a, false, w2_live);
       const char* nt = experiment_env("M3B_BINNED_THREADS");
-      h->binned_threads = nt ? atoi(nt) : 1024;
+      h->binned_threads = (nt && (atoi(nt) == 256 || atoi(nt) == 512)) ? atoi(nt) : 1024;
       int bps = 0;
       CK(binned_fill_prepare(smem, h->f64, h->binned_threads, &bps));
       REQUIRE(bps > 0, M3B_ERR_CUDA, "step: binned fill kernel does not fit on an SM");
@@ -1107,6 +1107,8 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
     a.real_f64 = h->f64 ? 1 : 0;
     a.bcoef_d = h->d_bcoef_d; a.bx_d = h->d_bx_d; a.bw_d = h->d_bw_d; a.osc_d = h->d_osc_d; a.static_d = h->d_static_d;
     a.evt_spline_d = h->d_evt_spline_d; a.evt_total_d = h->d_evt_total_d;
+    // the fill kernel's set-up overlaps the eval kernel's tail (programmatic dependent launch)
+    a.binned_pdl = (h->n_btiles > 0 && !experiment_env("M3B_NO_BINNED_PDL")) ? 1 : 0;
     if (h->n_btiles > 0) { CK(launch_binned_eval(a, h->binned_eval_grid, h->stream)); ++h->launches; }
     CK(launch_binned_fill(a, h->grid, h->binned_threads, h->smem, h->stream));
   } else if (h->use_tma) CK(launch_fill_tma(a, h->grid, h->smem, h->stream));

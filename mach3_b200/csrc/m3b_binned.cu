@@ -21,6 +21,7 @@ constexpr int kBTileSplines = 1024;     // splines per BTile: 4 per thread, so o
 __global__ void __launch_bounds__(256) binned_eval_kernel(const __grid_constant__ FillArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
+  if (a.binned_pdl) grid_launch_dependents();
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   stage_step_table(a, smem, &bar);
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) binned_eval_kernel(const __grid_constant_
 __global__ void __launch_bounds__(256) binned_eval_kernel_f64(const __grid_constant__ FillArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
+  if (a.binned_pdl) grid_launch_dependents();
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   stage_step_table(a, smem, &bar);
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
   for (int j = 0; j < kBFront; ++j) idx_nxt[j] = -1;
   load_front(wt, d_nxt, ev_nxt, idx_nxt);
   WTile d_nxt2 = load_desc(tile_of(1));
+  // everything above is independent of the eval kernel of this step; the weights and the histograms are not
+  if (a.binned_pdl) grid_dependency_wait();
   for (; blockIdx.x + it * gridDim.x < n_chunks; ++it, wt = tile_of(it)) {
     const WTile d = d_nxt;
     const BEvent<R> ev = ev_nxt;
@@ -259,12 +263,27 @@ cudaError_t launch_binned_eval(const FillArgs& a, int grid, cudaStream_t s) {
 // remain selectable in the experiments build (M3B_BINNED_THREADS) for the A/B record
 template <class F>
 static cudaError_t with_fill_kernel(bool f64, int nt, F&& f) {
+#ifdef M3B_EXPERIMENTS
   if (nt == 512) return f64 ? f(binned_fill_kernel<true, 512, 4>) : f(binned_fill_kernel<false, 512, 8>);
   if (nt == 256) return f64 ? f(binned_fill_kernel<true, 256, 16>) : f(binned_fill_kernel<false, 256, 16>);
+#endif
+  (void)nt;
   return f64 ? f(binned_fill_kernel<true, 1024, 4>) : f(binned_fill_kernel<false, 1024, 8>);
 }
 cudaError_t launch_binned_fill(const FillArgs& a, int grid, int nt, int smem, cudaStream_t s) {
-  return with_fill_kernel(a.real_f64 != 0, nt, [&](auto* k) { k<<<grid, nt, smem, s>>>(a); return cudaGetLastError(); });
+  return with_fill_kernel(a.real_f64 != 0, nt, [&](auto* k) {
+    if (a.binned_pdl) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = static_cast<size_t>(smem); cfg.stream = s;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at.val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, k, a);
+    }
+    k<<<grid, nt, smem, s>>>(a);
+    return cudaGetLastError();
+  });
 }
 cudaError_t binned_fill_prepare(int smem, bool f64, int nt, int* bps) {
   return with_fill_kernel(f64, nt, [&](auto* k) {

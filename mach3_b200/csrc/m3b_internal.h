@@ -134,6 +134,9 @@ struct FillArgs {
   int32_t pdl;                 // TMA kernel launched with programmatic stream serialization: the next step's ramp may
                                // overlap this step's tail; everything the previous launch wrote is touched only after
                                // griddepcontrol.wait
+  int32_t binned_pdl;          // binned path: the fill kernel is launched with programmatic stream serialization behind the
+                               // eval kernel -- its set-up and first prefetch overlap the eval kernel's tail, the weights
+                               // are touched only after griddepcontrol.wait
   int32_t guard_x2;            // TMA kernel: whole tile rows are grabbed while more than guard_x2/2 * grid * g units are left
   double* llh_dev;             // [1+n_samples]
   double* llh_host;            // mapped pinned mirror (nullptr = none)

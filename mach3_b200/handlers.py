@@ -259,12 +259,12 @@ def build_from_workload(w, e0=0, e1=None, with_osc=True, update_w2=False, test_s
 
 
 def build_binned_from_workload(w, update_w2=True, test_statistic=None, device=0, keep_event_weights=False, fused_llh=True,
-                               f64=False):
+                               f64=False, spl=None, ev=None):
     """B200 SampleHandlerFD + BinnedSplineHandler wired on a synthetic binned-spline workload
-    (f64: the reference's default build, M3::float_t = double)."""
+    (f64: the reference's default build, M3::float_t = double).  spl / ev: use these arrays instead of generating them."""
     from .synth import binned as B
-    spl = B.make_binned_splines(w, f64=f64)
-    ev = B.make_binned_events(w, f64=f64)
+    spl = B.make_binned_splines(w, f64=f64) if spl is None else spl
+    ev = B.make_binned_events(w, f64=f64) if ev is None else ev
     sh = SampleHandlerFD(B.bin_edges(w), w.test_statistic if test_statistic is None else test_statistic, update_w2, device,
                          0, keep_event_weights, fused_llh)
     sh.SetupBinnedSplines(spl, f64=f64)

@@ -406,12 +406,12 @@ def build_from_workload(w, e0=0, e1=None, with_osc=True, update_w2=False, test_s
     return mono, sh, dict(typ=typ, npts=npts, coeff_x=cx, spl=spl, ev=ev)
 
 
-def build_binned_from_workload(w, update_w2=True, test_statistic=None, with_osc=True, f64=False):
+def build_binned_from_workload(w, update_w2=True, test_statistic=None, with_osc=True, f64=False, spl=None, ev=None):
     """Oracle BinnedSplineHandler + SampleHandlerFD wired on a synthetic binned-spline workload
-    (f64: the reference's default build)."""
+    (f64: the reference's default build).  spl / ev: use these arrays instead of generating them."""
     from mach3_b200.synth import binned as B
-    spl = B.make_binned_splines(w, f64=f64)
-    ev = B.make_binned_events(w, f64=f64)
+    spl = B.make_binned_splines(w, f64=f64) if spl is None else spl
+    ev = B.make_binned_events(w, f64=f64) if ev is None else ev
     sh = SampleHandlerFD(w.n_events, B.bin_edges(w), w.test_statistic if test_statistic is None else test_statistic, update_w2)
     osc = B.make_osc(w, 0, f64=f64) if with_osc else None
     norm_vals = np.ones(w.n_norm_params, np.float64)

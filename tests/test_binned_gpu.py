@@ -63,6 +63,49 @@ def test_binned_spline_path_matches_oracle(oracle_build, ts):
     assert (bsh.weights == 0).any(), "the workload should exercise the negative-weight clamp"
 
 
+def _scrambled(w, mode):
+    """The same physics in a layout the upload's walking-order heuristics were not written for: the result must not care."""
+    spl, ev = B.make_binned_splines(w), B.make_binned_events(w)
+    rng = np.random.default_rng(17)
+    npe = ev["n_per_event"].astype(np.int64)
+    start = np.concatenate(([0], np.cumsum(npe)))
+    si = ev["spline_index"].copy()
+    if mode == "pointer_order":            # every event's pointers shuffled (the product follows the given order) and
+        keep = np.ones(si.size, bool)      # every seventh event has no pointer at all
+        for e in range(w.n_events):
+            a, b = start[e], start[e + 1]
+            if e % 7 == 3:
+                keep[a:b] = False; npe[e] = 0
+            else:
+                si[a:b] = rng.permutation(si[a:b])
+        ev = dict(ev, n_per_event=npe.astype(np.uint32), spline_index=si[keep])
+    else:                                  # the slots themselves in random order: no systematic owns a run of slots
+        perm = rng.permutation(w.n_slots).astype(np.int32)
+        usv = np.empty_like(spl["uniquesplinevec_Monolith"]); usv[perm] = spl["uniquesplinevec_Monolith"]
+        civ = np.empty_like(spl["coeffindexvec"]); civ[perm] = spl["coeffindexvec"]
+        spl = dict(spl, uniquesplinevec_Monolith=usv, coeffindexvec=civ, uniquecoeffindices=perm[spl["uniquecoeffindices"]])
+        ev = dict(ev, spline_index=perm[si])
+    return spl, ev
+
+
+@pytest.mark.parametrize("mode", ["pointer_order", "slot_order"])
+def test_binned_walking_order_does_not_depend_on_the_layout(oracle_build, mode):
+    if oracle_build != "serial":
+        pytest.skip("bit-exact comparison: serial oracle build")
+    w = B.CFG4_SMALL
+    spl, ev = _scrambled(w, mode)
+    bsh, osh, od = O.build_binned_from_workload(w, update_w2=True, spl=spl, ev=ev)
+    gsh, gd = handlers.build_binned_from_workload(w, update_w2=True, keep_event_weights=True, spl=spl, ev=ev)
+    for i, step in enumerate((-1, 0, 1, 2)):
+        _set(w, step, bsh, osh, gsh, gd, osc_step=i)
+        osh.Reweight(); gsh.Reweight()
+        np.testing.assert_array_equal(gsh.SplineHandler.weightvec_Monolith, bsh.weights)
+        sw, tw = gsh.GetEventWeight()
+        np.testing.assert_array_equal(tw, osh.event_weights())
+        np.testing.assert_allclose(gsh.GetMCArray(), osh.mc, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(gsh.GetW2Array(), osh.w2, rtol=1e-12, atol=1e-12)
+
+
 def test_binned_rejects_inconsistent_input():
     w = B.CFG4_SMALL
     spl = B.make_binned_splines(w)
