@@ -68,6 +68,8 @@ struct Batch2Args {
   const float* t_norm;             // [n_norm][256]
   int32_t n_norm, n_sets, max_nc, max_nl;
   int32_t n_stages, stage_rows;
+  int32_t dbg;                     // experiments build only (timing ablations, scripts/batch_ablation.py; results are wrong
+                                   // when set): 1 no atomics, 2 no epilogue, 4 no spline arithmetic, 8 no re-pack / second barrier
   const int32_t* bin; const float* osc; const int32_t* osc_idx; const float* static_w;
   const int16_t* norm_idx; int32_t norm_slots; int64_t e_pad, n_events;
   double* hist;                    // [n_bins][256]
@@ -75,6 +77,11 @@ struct Batch2Args {
   unsigned int* counter;
 };
 
+#ifdef M3B_EXPERIMENTS
+#define B2DBG(bit) ((a.dbg & (bit)) != 0)
+#else
+#define B2DBG(bit) false
+#endif
 __device__ __forceinline__ void mbar_arrive2(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         // ---- a group of TSpline3 slots
         const Batch2Group gr = a.t_group[off_group + d.z];
         // re-pack this warp's share of the staged rows for packed arithmetic: lane l owns float4 l and l+32 of a row
-        {
+        if (!B2DBG(8)) {
           float4* all = reinterpret_cast<float4*>(src) + lane;
           for (int r = warp; r < gr.n_rows; r += kB2CW) {
             float4* rp = all + r * kB2RowF4;
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         }
         // fmaf Horner on the set's segment, running products in the reference's slot order
         const float4* rows = reinterpret_cast<const float4*>(src) + lane;
-        for (int c = gr.c0; active && c < gr.c1; ++c) {
+        for (int c = gr.c0; active && !B2DBG(4) && c < gr.c1; ++c) {
           const int2 si = s_slot[c];                    // {first staged row of the slot in this stage, distinct segments}
           const float4* rp = rows + si.x * kB2RowF4;
           const float4* dxv = reinterpret_cast<const float4*>(s_dx + c * kB2Sets + set0);
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
       }
       // every warp arrives on the stage's second barrier once per use, whether or not the stage had rows to re-pack:
       // its phase must advance in step with the ring's
-      if (lane == 0) mbar_arrive2(&ready_bar[stage]);
+      if (lane == 0 && !B2DBG(8)) mbar_arrive2(&ready_bar[stage]);
       if (active) {
         const float2* lin = reinterpret_cast<const float2*>(src) + lane;
         for (int l = 0; l < cur_nl; ++l) {
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive2(&empty_bar[stage]);
       if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-      if (active) {
+      if (active && !B2DBG(2)) {
         // CalcWeightTotal + fill, per (event, set): norms (reference order), osc, spline, static
         double* h0 = a.hist + static_cast<int64_t>(bin0 >= 0 ? bin0 : 0) * kB2Sets + set0;
         double* h1 = a.hist + static_cast<int64_t>(bin1 >= 0 ? bin1 : 0) * kB2Sets + set0;
@@ -356,11 +363,11 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         #pragma unroll
         for (int q = 0; q < kB2SW; ++q) {
           const float w0 = pk2_lo(W[q]), w1 = pk2_hi(W[q]);
-          if (set0 + q < a.n_sets) {
+          if (set0 + q < a.n_sets && !B2DBG(1)) {
             if (w0 > 0.f && bin0 >= 0) atomicAdd(h0 + q, static_cast<double>(w0));
             if (w1 > 0.f && bin1 >= 0) atomicAdd(h1 + q, static_cast<double>(w1));
           }
-          W[q] = one2;
+          W[q] = B2DBG(1) ? pk2_make(w0 * 0.f + 1.f, w1 * 0.f + 1.f) : one2;
         }
       }
     }
@@ -512,6 +519,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   a.t_group = static_cast<const Batch2Group*>(h->bt_group);
   a.n_norm = Nn; a.n_sets = n_sets; a.max_nc = h->max_nc; a.max_nl = h->max_nl;
   a.n_stages = n_stages; a.stage_rows = stage_rows;
+  { const char* dbg = experiment_env("M3B_BATCH_DBG"); a.dbg = dbg ? atoi(dbg) : 0; }
   a.bin = h->d_bin; a.osc = h->use_osc ? h->d_osc : nullptr; a.osc_idx = h->d_osc_idx; a.static_w = h->d_static;
   a.norm_idx = h->d_norm_idx; a.norm_slots = h->norm_slots; a.e_pad = h->e_pad; a.n_events = h->n_events;
   a.hist = static_cast<double*>(h->bt_hist); a.n_bins = h->n_bins; a.counter = h->d_tile_counter;
