@@ -1025,7 +1025,19 @@ static int enqueue_step(m3b_handle* h, const float* vals, const int16_t* segs, c
   if (osc_w) {
     REQUIRE(h->use_osc, M3B_ERR_INVALID, "step: osc_w given but events were uploaded with use_osc=0");
     REQUIRE(!h->f64, M3B_ERR_INVALID, "step: this handle runs the double build; pass oscillation weights with m3b_upload_osc_f64");
-    if (!osc_zc) CK(cudaMemcpyAsync(h->d_osc, osc_w, sizeof(float) * h->n_osc, cudaMemcpyHostToDevice, h->stream));
+    if (!osc_zc) {
+      // an indexed oscillator table (NuOscillator's binned mode) is small: from mapped host memory it is fetched by a
+      // kernel, which the fill kernel follows without the copy-engine hand-over
+      const float* tab = nullptr;
+      if (h->d_osc_idx && h->n_osc <= 65536) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, osc_w) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+          tab = static_cast<const float*>(at.devicePointer);
+        cudaGetLastError();
+      }
+      if (tab) { CK(launch_table_copy(h->d_osc, tab, h->n_osc, h->stream)); ++h->launches; }
+      else CK(cudaMemcpyAsync(h->d_osc, osc_w, sizeof(float) * h->n_osc, cudaMemcpyHostToDevice, h->stream));
+    }
   }
 
   // fused mode alternates two buffers (the last block zeroes the other one for the next step);

@@ -278,6 +278,7 @@ cudaError_t launch_llh_pull(const LlhArgs& a, int blocks, cudaStream_t s);
 constexpr int kLlhPullMaxBlocks = 32;
 cudaError_t launch_bins(const BinArgs& a, cudaStream_t s);
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t s);
+cudaError_t launch_table_copy(float* dst, const float* src_host_devptr, int64_t n, cudaStream_t s);
 cudaError_t launch_shift(const ShiftArgs& a, cudaStream_t s);
 cudaError_t launch_retile(const RetileArgs& a, int64_t n_identity_cub, int64_t n_identity_lin, cudaStream_t s);
 cudaError_t fill_occupancy(int T, int variant, int smem_bytes, int* blocks_per_sm);

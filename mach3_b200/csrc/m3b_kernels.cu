@@ -352,6 +352,18 @@ __global__ void select_kernel(const __grid_constant__ SelectArgs a) {
   a.selected[e] = ok ? 1 : 0;
   a.bin[e] = ok ? a.bin_raw[e] : -1;
 }
+// A small oscillator table handed over in mapped host memory is fetched by a kernel instead of the copy engine: a DMA
+// transfer followed by a dependent kernel costs ~30 us on the stream, a kernel reading 16 KB over PCIe a few.
+__global__ void table_copy_kernel(float* __restrict__ dst, const float* __restrict__ src_host, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = src_host[i];
+}
+cudaError_t launch_table_copy(float* dst, const float* src_host_devptr, int64_t n, cudaStream_t s) {
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 64)));
+  table_copy_kernel<<<grid, 256, 0, s>>>(dst, src_host_devptr, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t s) {
   const int threads = 256;
   select_kernel<<<static_cast<unsigned>((a.e_pad + threads - 1) / threads), threads, 0, s>>>(a);

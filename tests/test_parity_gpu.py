@@ -583,3 +583,38 @@ def test_barlow_beeston_negative_discriminant_is_an_error_like_the_reference_thr
     gsh.AddData(good)
     gsh.Reweight()
     assert np.isfinite(gsh.GetLikelihood())
+
+
+def test_indexed_oscillation_table(oracle_build):
+    """A binned oscillator: events index a small table of oscillation weights (osc_idx), the table changes every step.
+    Both hand-over routes: a numpy array (copy engine) and the library's mapped host memory (fetched by a kernel)."""
+    w = synth.SPARSE
+    typ, npts, cx = synth.param_layout(w)
+    spl, ev = synth.make_splines(w, 0, w.n_events), synth.make_events(w, 0, w.n_events)
+    rng = np.random.default_rng(23)
+    n_osc = 257
+    osc_idx = rng.integers(0, n_osc, w.n_events).astype(np.int32)
+    tab_o = np.ones(n_osc, np.float32); tab_g = np.ones(n_osc, np.float32)
+    mono = O.SMonolith(w.n_params, w.n_knots, cx, npts, spl)
+    osh = O.SampleHandlerFD(w.n_events, synth.bin_edges(w), w.test_statistic, False)
+    osh.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, np.ones(w.n_norm_params), tab_o, mono,
+                   ev["static_w"], osc_idx=osc_idx)
+    gsh = handlers.SampleHandlerFD(synth.bin_edges(w), w.test_statistic, False, 0, 0, True, True)
+    gsh.SetupSplines(w.n_params, w.n_knots, cx, npts, spl)
+    pars, norm = np.zeros(w.n_params), np.ones(w.n_norm_params)
+    gsh.SetupEvents(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, norm, tab_g, osc_idx, ev["static_w"])
+    gsh.SetSplinePointers(pars)
+    gd = dict(pars=pars, norm=norm)
+    mapped = gsh.handle.alloc_host(n_osc, np.float32)
+    for i, step in enumerate((-1, 0, 1, 2, 3, 4)):
+        sp, nm = synth.proposal(w, step)
+        mono.set_params(sp); osh.norm_vals[:] = nm; gd["pars"][:] = sp; gd["norm"][:] = nm
+        tab = rng.uniform(0.05, 1.3, n_osc).astype(np.float32)
+        osh.osc_w[:] = tab
+        if i % 2 == 0:
+            tab_g[:] = tab; gsh._osc_w = tab_g
+        else:
+            mapped[:] = tab; gsh._osc_w = mapped
+        gsh.OscillatorEvaluated()
+        _check_step(w, mono, osh, gsh)
+    gsh.handle.free_host(mapped)
