@@ -161,3 +161,45 @@ def test_binned_spline_path_default_double_build(oracle_build):
     fd["pars"][:] = gd["pars"]; fd["norm"][:] = gd["norm"]
     fsh.Reweight(); fsh.GetLikelihood()
     assert not np.array_equal(fsh.SplineHandler.weightvec_Monolith.astype(np.float64), gsh.SplineHandler.weightvec_Monolith)
+
+
+def test_full_size_cfg4_properties(oracle_build):
+    """BASELINE config 4 at its full size (2 M events, 100 M spline slots, 20 M non-flat): size-independent properties of
+    the device path -- the histogram IS the f64 sum of the device's own per-event weights over its own bins, and the
+    per-event weight of a random sample of events IS the float product, in the reference's order, of the norm values,
+    the oscillation weight, the event's binned-spline weights as read back from the device, and the static weight."""
+    if oracle_build != "serial":
+        pytest.skip("no oracle involved: run once")
+    w = B.CFG4
+    gsh, gd = handlers.build_binned_from_workload(w, update_w2=True, keep_event_weights=True)
+    ev = gd["ev"]
+    start = np.concatenate(([0], np.cumsum(ev["n_per_event"].astype(np.int64))))
+    norm_idx = ev["norm_idx"].reshape(w.n_events, w.n_norm_per_event)
+    rng = np.random.default_rng(5)
+    sample = rng.choice(w.n_events, 3000, replace=False)
+    bins = gsh.GetEventBins()
+    for step in (0, 1):
+        sp, nm = B.proposal(w, step)
+        gd["pars"][:] = sp; gd["norm"][:] = nm
+        osc = B.make_osc(w, step); gd["osc"][:] = osc; gsh.OscillatorEvaluated()
+        gsh.Reweight()
+        llh = gsh.GetLikelihood()
+        assert np.isfinite(llh)
+        sw, tw = gsh.GetEventWeight()
+        mc, w2 = gsh.GetMCArray(), gsh.GetW2Array()
+        ok = (tw > 0) & (bins >= 0)
+        np.testing.assert_allclose(mc, np.bincount(bins[ok], tw[ok].astype(np.float64), minlength=gsh.n_bins), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(w2, np.bincount(bins[ok], (tw[ok] * tw[ok]).astype(np.float64), minlength=gsh.n_bins), rtol=1e-12, atol=1e-12)
+        wv = gsh.SplineHandler.weightvec_Monolith            # 1.0 for flat slots
+        assert (wv >= 0).all()
+        normf = nm.astype(np.float32)
+        for e in sample:
+            x = np.float32(1)
+            for j in range(w.n_norm_per_event):
+                x = np.float32(x * normf[norm_idx[e, j]])
+            x = np.float32(x * osc[e])
+            s = np.float32(1)
+            for k in ev["spline_index"][start[e]:start[e + 1]]:
+                x = np.float32(x * wv[k]); s = np.float32(s * wv[k])
+            x = np.float32(x * ev["static_w"][e])
+            assert tw[e] == x and sw[e] == s, (e, tw[e], x)
