@@ -19,6 +19,8 @@ Prints ONE JSON line (rank 0):
   roofline the fill kernel's isolated launch duration (the library's CUDA events around every launch) against HBM;
   N=1 only: extra.cfg2 / extra.cfg4 / extra.cfg5 = the other BASELINE configs as complete sub-records (clocks, roofline,
            cpu_baseline each), extra.incumbent_gpu = the reference's own MaCh3_CUDA build on the same B200;
+  N=1 only: extra.cfg2_e2e_binned_osc / N>1: extra.e2e_binned_osc = the e2e step with a binned oscillator (a 4096-entry
+           table of oscillation weights per step instead of one weight per event);
   N>1 only: parity = an untimed check of the sharded -lnL / histogram against the CPU oracle (both exchanges) --
            the run FAILS (rc != 0) above 1e-6; single_process = the same N-GPU step driven by ONE host thread through
            m3b_group_* (the drop-in boundary for the reference's single-process fitters).
@@ -291,7 +293,9 @@ def upload_monolith(h, w, e0, e1):
     h.splines_end()
 
 
-def build_handle(w, e0, e1, local, flags, tile, stream_ptr, n_osc_bufs=4):
+def build_handle(w, e0, e1, local, flags, tile, stream_ptr, n_osc_bufs=4, osc_table=0):
+    """osc_table > 0: a binned oscillator -- the events index a table of that many oscillation weights (global event
+    number hashed, so every shard sees the same table) and the per-step host input is the table."""
     from mach3_b200 import lib, synth
     h = lib.Handle(device=local, test_statistic=w.test_statistic, update_w2=False, tile_events=tile, flags=flags)
     if stream_ptr is not None:
@@ -300,6 +304,19 @@ def build_handle(w, e0, e1, local, flags, tile, stream_ptr, n_osc_bufs=4):
     upload_monolith(h, w, e0, e1)
     h.upload_binning(synth.bin_edges(w))
     ev = synth.make_events(w, e0, e1)
+    if osc_table:
+        osc_idx = ((np.arange(e0, e1, dtype=np.int64) * 2654435761) % osc_table).astype(np.int32)
+        h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, osc_idx, osc_table,
+                        ev["static_w"])
+        del ev, osc_idx
+        rng = np.random.default_rng(11)
+        osc_bufs = []
+        for k in range(n_osc_bufs):
+            b = h.alloc_host(osc_table, np.float32)
+            b[:] = rng.uniform(0.2, 1.0, osc_table).astype(np.float32)
+            osc_bufs.append(b)
+        h.upload_osc(osc_bufs[0])
+        return h, osc_bufs, time.perf_counter() - t0
     h.upload_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, True, None, 0,
                     ev["static_w"])
     del ev
@@ -591,6 +608,12 @@ def main_b200(args):
             line["parity"] = par
             if not par["ok"]:
                 rc = 3
+        try:      # every rank takes part; a failure on any rank must not leave the others in a collective
+            bo = measure_sharded_binned_osc(args, w, world, rank, local, dist, torch, W, K)
+        except Exception as e:                                   # noqa: BLE001
+            bo = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            line["extra"]["e2e_binned_osc"] = bo
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -620,6 +643,42 @@ def main_b200(args):
                 ex[name] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
     return rc
+
+
+def measure_sharded_binned_osc(args, w, world, rank, local, dist, torch, W, K):
+    """N > 1: the e2e step with a binned oscillator (a 4096-entry table per step instead of one weight per event), same
+    sharding and exchange as the headline line; max over ranks.  Every rank calls it."""
+    from mach3_b200 import lib, sharding, synth
+    e0, e1 = sharding.shard_range(w.n_events, world, rank)
+    stream = torch.cuda.current_stream()
+    h, tabs, t_setup = build_handle(w, e0, e1, local, lib.FLAG_NO_FUSED_LLH, args.tile, stream.cuda_stream, osc_table=4096)
+    sh = sharding.ShardedSampleHandler(h, dist, args.exchange, device=f"cuda:{local}")
+    props = [synth.proposal(w, k) for k in range(-1, W + K)]
+    props = [(np.ascontiguousarray(sp, np.float64), np.ascontiguousarray(nm, np.float64)) for sp, nm in props]
+    sh.Reweight(*props[0], tabs[0]); h.llh()
+    mc, _ = h.read_hist()
+    h.upload_data(np.random.default_rng(w.seed).poisson(mc).astype(np.float64))
+    for k in range(W):
+        sh.Reweight(*props[1 + k], tabs[k % 4]); h.llh_fast()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for k in range(K):
+        sh.Reweight(*props[1 + W + k], tabs[k % 4]); llh = h.llh_fast()
+    ev1.record(stream)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
+    t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    exchange = sh.exchange
+    h.close()
+    del h, sh, tabs
+    return {"value": w.n_events / (ms * 1e-3), "unit": "events/s", "ms_per_step": ms, "osc_table_entries": 4096, "exchange": exchange,
+            "h2d_bytes_per_step": int(4 * 4096 + 12 * w.n_params + 4 * w.n_norm_params), "d2h_bytes_per_step": int(8 * (1 + w.n_samples)),
+            "llh_last": float(llh), "setup_s": round(t_setup, 1),
+            "what": "host-synchronised step, oscillation weights as a 4096-entry table in host memory every step (binned oscillator)"}
 
 
 def measure_binned_osc(args, local, W, K):
