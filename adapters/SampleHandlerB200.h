@@ -58,6 +58,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <stdexcept>
+#include <type_traits>
 #include <string>
 #include <utility>
 #include <vector>
@@ -82,11 +83,12 @@ struct MonolithArrays {               // Splines/SplineCommon.h:30-50, Splines/S
   const float* cpu_total_weights = nullptr;   // SMonolith::cpu_total_weights (address range only; never read)
 };
 
-// The other SplineBase implementation (Splines/BinnedSplineHandler.h:110-135), _LOW_MEMORY_STRUCTS_ build
-// (M3::float_t = float): its monolith arrays as they stand after TransferToMonolith.
-struct BinnedArrays {
+// The other SplineBase implementation (Splines/BinnedSplineHandler.h:110-135): its monolith arrays as they stand after
+// TransferToMonolith.  R = M3::float_t of the MaCh3 build: float with _LOW_MEMORY_STRUCTS_, double by default.
+template <class R>
+struct BinnedArraysT {
   int n_params = 0, max_knots = 0;
-  const float* knot_x = nullptr;              // FastSplineInfo::xPts per parameter, rows padded to max_knots
+  const R* knot_x = nullptr;                  // FastSplineInfo::xPts per parameter, rows padded to max_knots
   const int16_t* n_pts = nullptr;             // FastSplineInfo::nPts                [n_params]
   int64_t n_slots = 0;                        // weightvec_Monolith.size()
   const int32_t* uniquesplinevec_Monolith = nullptr;   // [n_slots]
@@ -94,24 +96,30 @@ struct BinnedArrays {
   int64_t n_unique = 0;
   const int32_t* uniquecoeffindices = nullptr;         // [n_unique]
   int64_t n_coeff = 0;
-  const float* manycoeff_arr = nullptr;       // [n_coeff*4]
-  const float* xcoeff_arr = nullptr;          // [n_coeff]
+  const R* manycoeff_arr = nullptr;           // [n_coeff*4]
+  const R* xcoeff_arr = nullptr;              // [n_coeff]
   std::vector<const double*> spline_par_pointers;      // FastSplineInfo::splineParsPointer per parameter
-  const float* weightvec_Monolith = nullptr;  // address range of the slots (never read)
+  const R* weightvec_Monolith = nullptr;      // address range of the slots (never read)
 };
+using BinnedArrays = BinnedArraysT<float>;    // _LOW_MEMORY_STRUCTS_ build
+using BinnedArraysD = BinnedArraysT<double>;  // default build
 
-struct PointerBases {
+template <class R>
+struct PointerBasesT {
   const double* norm_base = nullptr;  int n_norm = 0;        // ParameterHandlerBase::_fPropVal.data(), size
-  const float* osc_base = nullptr;    int64_t n_osc = 0;     // the oscillator's weight array (may be null)
-  const float* zero = nullptr;                               // &M3::Zero
-  const float* unity = nullptr;                              // &M3::Unity
+  const R* osc_base = nullptr;        int64_t n_osc = 0;     // the oscillator's weight array (may be null)
+  const R* zero = nullptr;                                   // &M3::Zero
+  const R* unity = nullptr;                                  // &M3::Unity
   // Address ranges of experiment-specific weights (AddAdditionalWeightPointers) that never change during a fit, e.g. a
   // per-event flux or POT weight array: {first, one-past-last}.  A weight pointer that is none of the above and lies
   // in none of these ranges is an ERROR (it might be rewritten every step, which the device copy would not see).
-  std::vector<std::pair<const float*, const float*>> constant_weight_ranges;
+  std::vector<std::pair<const R*, const R*>> constant_weight_ranges;
   // page-lock the oscillator's weight array where it lies (cudaHostRegister) so the device reads it without a host copy
+  // (float build; the double build's array is copied to the device every step)
   bool register_osc_array = true;
 };
+using PointerBases = PointerBasesT<float>;    // _LOW_MEMORY_STRUCTS_ build
+using PointerBasesD = PointerBasesT<double>;  // default build
 
 template <class FDBase>
 class SampleHandlerB200 : public FDBase {
@@ -124,8 +132,17 @@ class SampleHandlerB200 : public FDBase {
 
   // Call once after the base class finished Initialise() (events, binning, splines, pointers wired).
   // Exactly one of mono.n_params / binned.n_params may be non-zero (SampleHandlerFD holds one SplineBase).
-  void MoveToB200(const MonolithArrays& mono, const PointerBases& bases, const std::vector<int>& cuda_devices = {0},
-                  const BinnedArrays& binned = BinnedArrays()) {
+  // R is the build's M3::float_t (deduced from the arguments): float = the _LOW_MEMORY_STRUCTS_ build, the only one in
+  // which SMonolith is wired into SampleHandlerFD (Samples/SampleHandlerFD.cpp:1244-1254); double = the default build,
+  // BinnedSplineHandler only, weights and products in double like the reference's (m3b_upload_binned_splines_f64).
+  template <class R>
+  void MoveToB200(const MonolithArrays& mono, const PointerBasesT<R>& bases, const std::vector<int>& cuda_devices = {0},
+                  const BinnedArraysT<R>& binned = BinnedArraysT<R>()) {
+    constexpr bool kF64 = std::is_same<R, double>::value;
+    static_assert(kF64 || std::is_same<R, float>::value, "M3::float_t is float or double");
+    using WeightPtr = typename std::decay<decltype(this->MCSamples[0].total_weight_pointers[0])>::type;
+    static_assert(std::is_same<WeightPtr, const R*>::value, "PointerBases / BinnedArrays of the other M3::float_t build");
+    if (kF64 && mono.n_params > 0) throw std::runtime_error("SampleHandlerB200: the spline monolith exists only in the _LOW_MEMORY_STRUCTS_ build");
     if (cuda_devices.empty() || cuda_devices.size() > 8) throw std::runtime_error("SampleHandlerB200: 1..8 devices");
     if (mono.n_params > 0 && binned.n_params > 0) throw std::runtime_error("SampleHandlerB200: monolith OR binned splines, not both");
     if (binned.n_params > 0 && cuda_devices.size() > 1) throw std::runtime_error("SampleHandlerB200: the binned-spline arm runs on one device");
@@ -146,7 +163,7 @@ class SampleHandlerB200 : public FDBase {
     // Samples/SampleHandlerFD.cpp:545-564): not something a constant device table can follow -- refuse, loudly
     for (const auto& shifts : this->funcParsGrid)
       if (!shifts.empty()) throw std::runtime_error("SampleHandlerB200: functional (shift) parameters are not supported by this adapter");
-    bases_ = bases;
+    norm_base_ = bases.norm_base; n_norm_ = bases.n_norm; osc_base_ = bases.osc_base; n_osc_ = bases.n_osc; f64_ = kF64;
     spline_ptrs_ = mono.n_params > 0 ? mono.spline_par_pointers : binned.spline_par_pointers;
     spline_vals_.assign(spline_ptrs_.size(), 0.0);
 
@@ -188,9 +205,7 @@ class SampleHandlerB200 : public FDBase {
                                             mono.paramNo_arr, mono.nKnots_arr, mono.total_knots, mono.coeff_many,
                                             mono.nParamPerEvent_tf1, mono.paramNo_tf1, mono.coeff_tf1), "m3b_upload_spline_monolith");
     } else if (binned.n_params > 0) {
-      check(m3b_upload_binned_splines(h_, binned.n_params, binned.max_knots, binned.knot_x, binned.n_pts, binned.n_slots,
-                                      binned.uniquesplinevec_Monolith, binned.coeffindexvec, binned.n_unique, binned.uniquecoeffindices,
-                                      binned.n_coeff, binned.manycoeff_arr, binned.xcoeff_arr), "m3b_upload_binned_splines");
+      check(upload_binned(binned), kF64 ? "m3b_upload_binned_splines_f64" : "m3b_upload_binned_splines");
     }
 
     // --- events: pointers -> indices
@@ -200,7 +215,7 @@ class SampleHandlerB200 : public FDBase {
     std::vector<int32_t> sample_id(E), osc_idx(E, -1);
     std::vector<double> kin(static_cast<size_t>(max_dim) * E, 0.0);
     std::vector<int16_t> norm_idx(static_cast<size_t>(max_norm) * E, -1);
-    std::vector<float> static_w(E, 1.0f);
+    std::vector<R> static_w(E, R(1));
     std::vector<uint32_t> n_binned(binned.n_params > 0 ? E : 0, 0);
     std::vector<int32_t> binned_slot;
     bool any_osc = false, identity = true;
@@ -214,8 +229,8 @@ class SampleHandlerB200 : public FDBase {
         norm_idx[e * max_norm + j] = static_cast<int16_t>(off);
       }
       for (const auto* p : ev.total_weight_pointers) {
-        if (mono.cpu_total_weights && p >= mono.cpu_total_weights && p < mono.cpu_total_weights + E) {
-          if (p - mono.cpu_total_weights != e) throw std::runtime_error("SampleHandlerB200: event points at another event's spline weight");
+        if (is_monolith_weight(p, mono, E)) {
+          if (monolith_index(p, mono) != e) throw std::runtime_error("SampleHandlerB200: event points at another event's spline weight");
         } else if (binned.weightvec_Monolith && p >= binned.weightvec_Monolith && p < binned.weightvec_Monolith + binned.n_slots) {
           binned_slot.push_back(static_cast<int32_t>(p - binned.weightvec_Monolith));      // pointer order kept (:1236-1242)
           ++n_binned[e];
@@ -224,14 +239,14 @@ class SampleHandlerB200 : public FDBase {
           osc_idx[e] = static_cast<int32_t>(p - bases.osc_base);
           any_osc = true;
         } else if (p == bases.zero) {
-          static_w[e] = 0.0f;                 // NC event with flavour change (SampleHandlerFD.cpp:1128-1131)
+          static_w[e] = R(0);                 // NC event with flavour change (SampleHandlerFD.cpp:1128-1131)
         } else if (p != bases.unity) {
           bool constant = false;
           for (const auto& r : bases.constant_weight_ranges) constant |= (p >= r.first && p < r.second);
           if (!constant)
             throw std::runtime_error("SampleHandlerB200: event " + std::to_string(e) + " has a weight pointer that is neither the "
                                      "oscillation array, the spline handler, M3::Zero/Unity nor inside PointerBases::constant_weight_ranges");
-          static_w[e] *= static_cast<float>(*p);    // experiment-specific constant weight, folded once
+          static_w[e] *= *p;                  // experiment-specific constant weight, folded once
         }
       }
       identity &= (osc_idx[e] == e);
@@ -240,16 +255,18 @@ class SampleHandlerB200 : public FDBase {
     osc_direct_ = any_osc && identity && bases.n_osc == E;
     n_osc_dev_ = any_osc ? bases.n_osc : 0;
     const int32_t* oi = (any_osc && !osc_direct_) ? osc_idx.data() : nullptr;       // -1 entries: no oscillation weight (reads 1.0)
+    // (double build: the float entry point fixes the shapes, the double static weights follow)
     if (g_) gcheck(m3b_group_upload_events(g_, E, sample_id.data(), kin.data(), static_cast<int32_t>(max_norm), max_norm ? norm_idx.data() : nullptr,
-                                           bases.n_norm, any_osc ? 1 : 0, oi, n_osc_dev_, static_w.data()), "m3b_group_upload_events");
+                                           bases.n_norm, any_osc ? 1 : 0, oi, n_osc_dev_, float_or_null(static_w)), "m3b_group_upload_events");
     else check(m3b_upload_events(h_, E, sample_id.data(), kin.data(), static_cast<int32_t>(max_norm), max_norm ? norm_idx.data() : nullptr,
-                                 bases.n_norm, any_osc ? 1 : 0, oi, n_osc_dev_, static_w.data()), "m3b_upload_events");
+                                 bases.n_norm, any_osc ? 1 : 0, oi, n_osc_dev_, float_or_null(static_w)), "m3b_upload_events");
     if (binned.n_params > 0)
       check(m3b_upload_event_binned_splines(h_, E, n_binned.data(), binned_slot.data()), "m3b_upload_event_binned_splines");
-    if (any_osc) {
+    if (kF64) check(upload_static_f64(E, static_w), "m3b_upload_event_weights_f64");
+    if (any_osc && !kF64) {
       // the oscillator's array, page-locked where it lies; else a pinned staging copy refreshed every step
       if (bases.register_osc_array &&
-          m3b_register_host_buffer(h_, const_cast<float*>(bases.osc_base), sizeof(float) * static_cast<uint64_t>(bases.n_osc)) == M3B_OK) {
+          m3b_register_host_buffer(h_, const_cast<void*>(osc_base_), sizeof(float) * static_cast<uint64_t>(bases.n_osc)) == M3B_OK) {
         osc_registered_ = true;
       } else {
         void* p = nullptr;
@@ -289,7 +306,8 @@ class SampleHandlerB200 : public FDBase {
     ready_ = true;
   }
   // (pre-round-2 signature)
-  void MoveToB200(const MonolithArrays& mono, const PointerBases& bases, int cuda_device) { MoveToB200(mono, bases, std::vector<int>{cuda_device}); }
+  template <class R>
+  void MoveToB200(const MonolithArrays& mono, const PointerBasesT<R>& bases, int cuda_device) { MoveToB200(mono, bases, std::vector<int>{cuda_device}); }
 
   // SampleHandlerFD::AddData (Samples/SampleHandlerFD.cpp:955-1044) changed SampleHandlerFD_data
   void DataChanged() {
@@ -303,20 +321,24 @@ class SampleHandlerB200 : public FDBase {
     if (this->Oscillator) this->Oscillator->Evaluate();    // NuOscillator stays where it is (input array)
     for (size_t p = 0; p < spline_ptrs_.size(); ++p) spline_vals_[p] = *spline_ptrs_[p];
     const float* osc = nullptr;
-    if (n_osc_dev_ > 0) {
+    if (n_osc_dev_ > 0 && f64_) {
+      // default build: the oscillator's array is double; copied to the device (the call returns once the source is free)
+      check(m3b_upload_osc_f64(h_, static_cast<const double*>(osc_base_), n_osc_dev_), "m3b_upload_osc_f64");
+    } else if (n_osc_dev_ > 0) {
+      const float* base = static_cast<const float*>(osc_base_);
       if (osc_registered_) {
-        osc = bases_.osc_base;                              // read by the device where it lies; the caller's next
+        osc = base;                                         // read by the device where it lies; the caller's next
                                                             // Evaluate() comes after GetLikelihood(), which synchronises
       } else {
         if (g_) gcheck(m3b_group_synchronize(g_), "m3b_group_synchronize");
         else check(m3b_synchronize(h_), "m3b_synchronize"); // the previous step may still be reading the staging array
-        std::copy(bases_.osc_base, bases_.osc_base + bases_.n_osc, osc_stage_);
+        std::copy(base, base + n_osc_, osc_stage_);
         osc = osc_stage_;
       }
     }
     const double* sp = spline_vals_.empty() ? nullptr : spline_vals_.data();
-    if (g_) gcheck(m3b_group_step(g_, sp, bases_.norm_base, osc), "m3b_group_step");
-    else check(m3b_step(h_, sp, bases_.norm_base, osc), "m3b_step");
+    if (g_) gcheck(m3b_group_step(g_, sp, norm_base_, osc), "m3b_group_step");
+    else check(m3b_step(h_, sp, norm_base_, osc), "m3b_step");
     host_arrays_stale_ = true;
     if (!this->UpdateW2) this->FirstTimeW2 = false;        // Samples/SampleHandlerFD.cpp:342
   }
@@ -356,7 +378,7 @@ class SampleHandlerB200 : public FDBase {
   void BeginBatch() { batch_sp_.clear(); batch_nm_.clear(); batch_n_ = 0; }
   void CaptureProposal() {
     for (const double* p : spline_ptrs_) batch_sp_.push_back(*p);
-    batch_nm_.insert(batch_nm_.end(), bases_.norm_base, bases_.norm_base + bases_.n_norm);
+    batch_nm_.insert(batch_nm_.end(), norm_base_, norm_base_ + n_norm_);
     ++batch_n_;
   }
   int CapturedProposals() const { return batch_n_; }
@@ -392,12 +414,31 @@ class SampleHandlerB200 : public FDBase {
   void gcheck(int rc, const char* what) const {
     if (rc != M3B_OK) throw std::runtime_error(std::string("SampleHandlerB200: ") + what + ": " + m3b_group_last_error(g_));
   }
+  // the two M3::float_t builds differ only in these calls
+  int upload_binned(const BinnedArraysT<float>& b) {
+    return m3b_upload_binned_splines(h_, b.n_params, b.max_knots, b.knot_x, b.n_pts, b.n_slots, b.uniquesplinevec_Monolith, b.coeffindexvec,
+                                     b.n_unique, b.uniquecoeffindices, b.n_coeff, b.manycoeff_arr, b.xcoeff_arr);
+  }
+  int upload_binned(const BinnedArraysT<double>& b) {
+    return m3b_upload_binned_splines_f64(h_, b.n_params, b.max_knots, b.knot_x, b.n_pts, b.n_slots, b.uniquesplinevec_Monolith, b.coeffindexvec,
+                                         b.n_unique, b.uniquecoeffindices, b.n_coeff, b.manycoeff_arr, b.xcoeff_arr);
+  }
+  static const float* float_or_null(const std::vector<float>& w) { return w.data(); }
+  static const float* float_or_null(const std::vector<double>&) { return nullptr; }
+  int upload_static_f64(int64_t, const std::vector<float>&) { return M3B_OK; }
+  int upload_static_f64(int64_t n, const std::vector<double>& w) { return m3b_upload_event_weights_f64(h_, n, w.data()); }
+  static bool is_monolith_weight(const float* p, const MonolithArrays& m, int64_t n) { return m.cpu_total_weights && p >= m.cpu_total_weights && p < m.cpu_total_weights + n; }
+  static bool is_monolith_weight(const double*, const MonolithArrays&, int64_t) { return false; }
+  static int64_t monolith_index(const float* p, const MonolithArrays& m) { return p - m.cpu_total_weights; }
+  static int64_t monolith_index(const double*, const MonolithArrays&) { return -1; }
   m3b_handle* h_ = nullptr;
   m3b_group* g_ = nullptr;
   bool ready_ = false, host_arrays_stale_ = false, osc_direct_ = false, osc_registered_ = false;
   int n_bins_ = 0;
   int64_t n_osc_dev_ = 0;
-  PointerBases bases_{};
+  const double* norm_base_ = nullptr; int n_norm_ = 0;
+  const void* osc_base_ = nullptr; int64_t n_osc_ = 0;      // the oscillator's array (const M3::float_t*)
+  bool f64_ = false;                                         // default build (M3::float_t = double)
   std::vector<const double*> spline_ptrs_;
   std::vector<double> spline_vals_;
   std::vector<double> batch_sp_, batch_nm_;     // captured proposals, row-major

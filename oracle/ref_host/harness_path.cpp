@@ -573,9 +573,10 @@ REFP_API int refp_fd_move_to_b200_ex(void* p, int n_devices, const int* devices)
 #ifdef M3B_WITH_ADAPTER
   FD* fd = static_cast<FD*>(p);
   FDType* b = static_cast<FDType*>(fd);
-  SMonolith* m = dynamic_cast<SMonolith*>(fd->SplineHandler.get());
   m3b200::MonolithArrays a;
   std::vector<int16_t> n_pts;
+#ifdef _LOW_MEMORY_STRUCTS_          // the event-by-event monolith is wired into SampleHandlerFD in this build only
+  SMonolith* m = dynamic_cast<SMonolith*>(fd->SplineHandler.get());
   if (m) {
     n_pts.resize(size_t(m->nParams));
     for (int i = 0; i < m->nParams; ++i) {
@@ -590,20 +591,21 @@ REFP_API int refp_fd_move_to_b200_ex(void* p, int n_devices, const int* devices)
     a.paramNo_tf1 = m->cpu_paramNo_TF1_arr.data(); a.coeff_tf1 = m->cpu_coeff_TF1_many.data();
     a.cpu_total_weights = m->cpu_total_weights;
   }
-  m3b200::PointerBases pb;
+#endif
+  m3b200::PointerBasesT<M3::float_t> pb;
   pb.norm_base = fd->norm.data(); pb.n_norm = int(fd->norm.size());
   pb.osc_base = fd->pool.data(); pb.n_osc = int64_t(fd->nEvents);       // pool = [osc per event | extra weights]
   pb.zero = &M3::Zero; pb.unity = &M3::Unity;
   pb.constant_weight_ranges.push_back({fd->pool.data() + fd->nEvents, fd->pool.data() + fd->pool.size()});   // the extras
   // the binned arm (Samples/SampleHandlerFD.cpp:1196-1242): BinnedSplineHandler's monolith arrays as they stand
-  m3b200::BinnedArrays ba;
-  std::vector<float> knot_x; std::vector<int16_t> bn_pts;
+  // (either M3::float_t build: the adapter's types follow it)
+  m3b200::BinnedArraysT<M3::float_t> ba;
+  std::vector<M3::float_t> knot_x; std::vector<int16_t> bn_pts;
   std::vector<int32_t> usv, civ, uci;
-#ifdef _LOW_MEMORY_STRUCTS_
   if (Binned* bs = dynamic_cast<Binned*>(fd->SplineHandler.get())) {
     int K = 0;
     for (int i = 0; i < bs->nParams; ++i) K = std::max(K, int(bs->SplineInfoArray[i].nPts));
-    knot_x.assign(size_t(bs->nParams) * K, 0.f); bn_pts.resize(size_t(bs->nParams));
+    knot_x.assign(size_t(bs->nParams) * K, M3::float_t(0)); bn_pts.resize(size_t(bs->nParams));
     for (int i = 0; i < bs->nParams; ++i) {
       bn_pts[i] = int16_t(bs->SplineInfoArray[i].nPts);
       for (int k = 0; k < bn_pts[i]; ++k) knot_x[size_t(i) * K + k] = bs->SplineInfoArray[i].xPts[k];
@@ -617,7 +619,6 @@ REFP_API int refp_fd_move_to_b200_ex(void* p, int n_devices, const int* devices)
     ba.n_unique = int64_t(uci.size()); ba.uniquecoeffindices = uci.data(); ba.n_coeff = bs->n_coeff_keep;
     ba.manycoeff_arr = bs->manycoeff_arr; ba.xcoeff_arr = bs->xcoeff_arr; ba.weightvec_Monolith = bs->weightvec_Monolith.data();
   }
-#endif
   try { b->MoveToB200(a, pb, std::vector<int>(devices, devices + n_devices), ba); }
   catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
   return 0;

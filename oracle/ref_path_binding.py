@@ -17,7 +17,9 @@ LIB_PATH_LM = os.path.join(_HERE, "_ref", "libm3ref_path_lm.so")    # -D_LOW_MEM
 LIB_PATH_LM_MT = os.path.join(_HERE, "_ref", "libm3ref_path_lm_mt.so")   # ... with the release flags + MULTITHREAD
 LIB_PATH_LM_B200 = os.path.join(_HERE, "_ref", "libm3ref_path_lm_b200.so")   # ... with adapters/SampleHandlerB200.h over the real class
 LIB_PATH_LM_CUDA = os.path.join(_HERE, "_ref", "libm3ref_path_lm_cuda.so")   # ... MaCh3_CUDA build, adapters/SMonolithGPU_m3b200.cu
-_PATHS = {"float_cuda": LIB_PATH_LM_CUDA, "double": LIB_PATH, "float": LIB_PATH_LM, "float_mt": LIB_PATH_LM_MT, "float_b200": LIB_PATH_LM_B200}
+LIB_PATH_B200 = os.path.join(_HERE, "_ref", "libm3ref_path_b200.so")   # default (double) build with the adapter over the real class
+_PATHS = {"float_cuda": LIB_PATH_LM_CUDA, "double": LIB_PATH, "float": LIB_PATH_LM, "float_mt": LIB_PATH_LM_MT, "float_b200": LIB_PATH_LM_B200,
+          "double_b200": LIB_PATH_B200}
 _LIBS = {}
 
 
@@ -33,7 +35,7 @@ def lib(build="double"):
         path = (os.path.join(_HERE, "_ref", f"libm3ref_path_lm_refcuda_{build.split('_')[-1]}.so")
                 if build.startswith("float_refcuda_") else _PATHS[build])
         L = C.CDLL(path)
-        assert L.refp_float_t_bytes() == (8 if build == "double" else 4)
+        assert L.refp_float_t_bytes() == (8 if build.startswith("double") else 4)
         L.refp_mono_create_from_arrays.restype = C.c_void_p
         L.refp_mono_create_from_arrays.argtypes = ([C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 3
                                                    + [C.c_uint64] + [C.c_void_p] * 4)
@@ -295,7 +297,7 @@ class RefSampleHandlerFD:
         self.L.refp_fd_events(self.h, _p(w), _p(b))
         return w, b
 
-    # -- only in build "float_b200": the object is an m3b200::SampleHandlerB200<FD> over the reference's class
+    # -- only in builds "float_b200" / "double_b200": the object is an m3b200::SampleHandlerB200<FD> over the reference's class
     def move_to_b200(self, device=0):
         """device: one ordinal, or a list of ordinals (the sample is then spread over them through m3b_group_*)."""
         dev = np.ascontiguousarray([device] if np.isscalar(device) else list(device), np.int32)
@@ -352,8 +354,8 @@ def available_cuda():
     return os.path.exists(LIB_PATH_LM_CUDA)
 
 
-def available_b200():
-    return os.path.exists(LIB_PATH_LM_B200)
+def available_b200(build="float_b200"):
+    return os.path.exists(_PATHS[build])
 
 
 def available_mt():

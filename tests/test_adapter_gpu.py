@@ -105,10 +105,12 @@ def test_adapter_over_the_reference_real_sample_handler_class(n_members):
 
 
 @pytest.mark.gpu
-def test_adapter_binned_arm_over_the_reference_real_classes():
+@pytest.mark.parametrize("build", ["float", "double"])
+def test_adapter_binned_arm_over_the_reference_real_classes(build):
     """The binned arm of SetSplinePointers (Samples/SampleHandlerFD.cpp:1196-1242): the reference's REAL
-    BinnedSplineHandler + SampleHandlerFD (float build) wired by the reference's harness; MoveToB200 turns every
-    `&weightvec_Monolith[slot]` pointer into a slot index and the step runs on the B200 (binned_eval_kernel +
+    BinnedSplineHandler + SampleHandlerFD wired by the reference's harness, in BOTH builds of the reference
+    (_LOW_MEMORY_STRUCTS_: M3::float_t = float; default: double -- the adapter's types follow M3::float_t); MoveToB200 turns
+    every `&weightvec_Monolith[slot]` pointer into a slot index and the step runs on the B200 (binned_eval_kernel +
     binned_fill_kernel).  -lnL and histograms against the reference's own CPU results (tests/golden/ref_host_fd.npz)."""
     import os
     import sys
@@ -117,14 +119,15 @@ def test_adapter_binned_arm_over_the_reference_real_classes():
     import refpath_cases as RC
     from mach3_b200.synth import binned as B
     from oracle import ref_path_binding as RP
-    if not RP.available_b200():
-        pytest.skip("oracle/_ref/libm3ref_path_lm_b200.so not built (needs /root/reference at build time)")
+    if not RP.available_b200(f"{build}_b200"):
+        pytest.skip(f"oracle/_ref adapter library of the {build} build not built (needs /root/reference at build time)")
     gold = np.load(os.path.join(here, "golden", "ref_host_fd.npz"))
-    tag = "binned_float"
+    tag = f"binned_{build}"
+    f64 = build == "double"
     w = RC.binned_workload()
-    spl, ev = B.make_binned_splines(w), B.make_binned_events(w)
+    spl, ev = B.make_binned_splines(w, f64=f64), B.make_binned_events(w, f64=f64)
     E = w.n_events
-    fd = RP.RefSampleHandlerFD(B.bin_edges(w), 1, True, build="float_b200")
+    fd = RP.RefSampleHandlerFD(B.bin_edges(w), 1, True, build=f"{build}_b200")
     fd.attach_binned(spl)
     idx = np.arange(E, dtype=np.int32)
     fd.set_events(ev["sample_id"], ev["kin"], ev["norm_idx"], w.n_norm_per_event, w.n_norm_params, w_before=idx,
@@ -132,12 +135,12 @@ def test_adapter_binned_arm_over_the_reference_real_classes():
     # one step on the reference's CPU path first (the adapter forwards to the base class before MoveToB200): the weight
     # pool -- the constant extra weights the adapter folds into the events' static weights -- holds its values from here on
     sp, nm = B.proposal(w, RC.BINNED_STEPS[0])
-    fd.reweight(sp, nm, np.concatenate([B.make_osc(w, max(RC.BINNED_STEPS[0], 0)), ev["static_w"]]).astype(np.float64))
+    fd.reweight(sp, nm, np.concatenate([B.make_osc(w, max(RC.BINNED_STEPS[0], 0), f64=f64), ev["static_w"]]).astype(np.float64))
     fd.set_data(gold[f"{tag}/data"])
     fd.move_to_b200(0)
     for i, step in enumerate(RC.BINNED_STEPS):
         sp, nm = B.proposal(w, step)
-        pool = np.concatenate([B.make_osc(w, max(step, 0)), ev["static_w"]]).astype(np.float64)
+        pool = np.concatenate([B.make_osc(w, max(step, 0), f64=f64), ev["static_w"]]).astype(np.float64)
         fd.reweight(sp, nm, pool)
         assert fd.llh() == pytest.approx(float(gold[f"{tag}/llh"][i]), rel=1e-10), step
         fd.sync_host_arrays()
