@@ -890,7 +890,7 @@ static int prepare_launch(m3b_handle* h, bool w2_live) {
       h->hist_in_smem = smem <= (hm ? atoi(hm) : 200) * 1024;
       if (!h->hist_in_smem) smem = binned_fill_smem_bytes(a, false, w2_live);
       const char* nt = experiment_env("M3B_BINNED_THREADS");
-      h->binned_threads = (nt && (atoi(nt) == 256 || atoi(nt) == 512)) ? atoi(nt) : 1024;
+      h->binned_threads = (nt && (atoi(nt) == 256 || atoi(nt) == 512 || atoi(nt) == 768)) ? atoi(nt) : 1024;
       int bps = 0;
       CK(binned_fill_prepare(smem, h->f64, h->binned_threads, &bps));
       REQUIRE(bps > 0, M3B_ERR_CUDA, "step: binned fill kernel does not fit on an SM");

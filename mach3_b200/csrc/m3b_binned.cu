@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT >= 4 ? 2 : 1024 / NT) binned_fil
   const int64_t n_chunks = (a.n_wtiles + kTiles - 1) / kTiles;
   auto tile_of = [&](int64_t it) -> int64_t {
     const int64_t c = blockIdx.x + it * gridDim.x;
-    return c < n_chunks ? c * kTiles + ((warp + static_cast<int>(it)) & (kTiles - 1)) : a.n_wtiles;
+    return c < n_chunks ? c * kTiles + ((warp + static_cast<int>(it % kTiles)) % kTiles) : a.n_wtiles;
   };
   int64_t it = 0;
   int64_t wt = tile_of(0);
@@ -266,6 +266,7 @@ static cudaError_t with_fill_kernel(bool f64, int nt, F&& f) {
 #ifdef M3B_EXPERIMENTS
   if (nt == 512) return f64 ? f(binned_fill_kernel<true, 512, 4>) : f(binned_fill_kernel<false, 512, 8>);
   if (nt == 256) return f64 ? f(binned_fill_kernel<true, 256, 16>) : f(binned_fill_kernel<false, 256, 16>);
+  if (nt == 768) return f64 ? f(binned_fill_kernel<true, 768, 8>) : f(binned_fill_kernel<false, 768, 16>);
 #endif
   (void)nt;
   return f64 ? f(binned_fill_kernel<true, 1024, 4>) : f(binned_fill_kernel<false, 1024, 8>);
