@@ -69,7 +69,7 @@ M3B_API void m3b_destroy(m3b_handle* h) {
   if (h->h_llh) cudaFreeHost(h->h_llh);
   if (h->h_seq) cudaFreeHost(h->h_seq);
   if (h->h_batch) cudaFreeHost(h->h_batch);
-  for (void* p : {h->bt_dx, h->bt_rowoff, h->bt_val, h->bt_rowlist, h->bt_norm, h->bt_sigs, h->bt_hist, h->bt_llh, h->bt_slot, h->bt_group}) if (p) cudaFree(p);
+  for (void* p : {h->bt_dx, h->bt_rowoff, h->bt_val, h->bt_rowlist, h->bt_norm, h->bt_sigs, h->bt_hist, h->bt_llh, h->bt_slot, h->bt_group, h->bt_rank8}) if (p) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

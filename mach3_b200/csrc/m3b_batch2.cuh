@@ -30,8 +30,12 @@
 //   a cheap epilogue        the per-(event,set) norm look-ups walk pre-computed shared-memory offsets (absent slots point
 //                           at a 1.0 entry): 8 LDS + 8 FMUL per set instead of an address computation and a branch each.
 //
-// Slots whose sets select more than three distinct segments, and batches on handles without a frozen W2, take the first
-// kernel / the sequential path (m3b_batch_try, m3b_step_batch).
+//   uniform and wide slots  a slot at which every set has the same segment and dx (an LLH scan of another parameter) evaluates
+//                           one polynomial and multiplies it into the 16 products; a slot whose sets spread over 4..8
+//                           segments (the scanned parameter) takes its row per set from a rank byte.
+//
+// Slots with more than eight live segments, more than eight wide slots per signature, more than four norm slots, and batches
+// on handles without a frozen W2, take the first kernel / the sequential path (m3b_batch_try, m3b_step_batch).
 #pragma once
 
 namespace m3b {
@@ -45,26 +49,30 @@ constexpr int kB2RowF4 = kB2E + 1;  // staged row stride in float4 (+16 B: rows 
 constexpr int kB2MaxStageRows = 32; // cubic rows per ring stage (the host picks 32, 24 or 16 and 2..4 stages: what fits next to the tables)
 constexpr int kB2MaxStages = 4;
 constexpr int kB2MaxGroups = 96;
+constexpr int kB2MaxRanks = 8;      // staged segments of one slot: up to 3 go through the 2-bit code word, 4..8 ("wide" slots: a
+constexpr int kB2MaxWide = 8;       // parameter scanned over its whole range) through a byte per set, at most kB2MaxWide such slots
 __host__ __device__ inline int batch2_norm_stride(int n_norm) { return (n_norm + 1) | 1; }     // + the 1.0 entry; odd: lanes with different indices hit different banks
 __host__ __device__ inline int batch2_tables_bytes(int max_nc, int max_nl, int n_norm) {
-  return (max_nc * kB2Sets * 4 + max_nc * kB2CW * 4 + max_nl * kB2Sets * 4 + kB2Sets * batch2_norm_stride(n_norm) * 4 + max_nc * 8 + 127) & ~127;
+  return (max_nc * kB2Sets * 4 + max_nc * kB2CW * 4 + max_nl * kB2Sets * 4 + kB2Sets * batch2_norm_stride(n_norm) * 4 + max_nc * 16 + kB2MaxWide * kB2Sets + 127) & ~127;
 }
 
 struct Batch2Group { int32_t c0, c1, n_rows, row0; };   // slots [c0,c1) of the signature; rows [row0,row0+n_rows) of its row list
 struct Batch2Sig {
-  int32_t nc, nl, n_groups, pad;
+  int32_t nc, nl, n_groups, n_wide;
   int64_t off_dx;        // float    [nc][256]
   int64_t off_code;      // uint32   [nc][16]     2 bits per set of the warp: rank of the set's segment among the slot's staged rows
   int64_t off_val;       // float    [nl][256]
   int64_t off_rowlist;   // int32    [rows]       layout row (segbase + segment) of every staged row, slot-major, rank-minor
-  int64_t off_slot;      // int32    [nc][2]      {row offset inside its group's stage, distinct segments}
+  int64_t off_slot;      // int32    [nc][4]      {row offset inside its group's stage, distinct segments, wide index or -1,
+                         //                        1 = every set has the same segment and dx: one polynomial serves all sets}
+  int64_t off_rank8;     // uint8    [n_wide][256] rank of every set's segment, for the slots with more than three
   int64_t off_group;     // Batch2Group [n_groups]
 };
 
 struct Batch2Args {
   const TileDesc* tiles; int32_t n_units, units_per_tile, T;
   const Batch2Sig* sigs;
-  const float* t_dx; const uint32_t* t_code; const float* t_val; const int32_t* t_rowlist; const int32_t* t_slot; const Batch2Group* t_group;
+  const float* t_dx; const uint32_t* t_code; const float* t_val; const int32_t* t_rowlist; const int32_t* t_slot; const Batch2Group* t_group; const uint8_t* t_rank8;
   const float* t_norm;             // [n_norm][256]
   int32_t n_norm, n_sets, max_nc, max_nl;
   int32_t n_stages, stage_rows;
@@ -137,7 +145,8 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
   uint32_t* s_code = reinterpret_cast<uint32_t*>(s_dx + a.max_nc * kB2Sets);
   float* s_val = reinterpret_cast<float*>(s_code + a.max_nc * kB2CW);
   float* s_norm = s_val + a.max_nl * kB2Sets;
-  int2* s_slot = reinterpret_cast<int2*>(s_norm + kB2Sets * nnp);
+  int4* s_slot = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(s_norm + kB2Sets * nnp) + 15) & ~static_cast<uintptr_t>(15));
+  uint8_t* s_rank8 = reinterpret_cast<uint8_t*>(s_slot + a.max_nc);
   unsigned char* ring = smem + batch2_tables_bytes(a.max_nc, a.max_nl, a.n_norm);
   const int stage_bytes = a.stage_rows * kB2RowF4 * 16;
   const int n_stages = a.n_stages;
@@ -231,7 +240,8 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         for (int i = tid; i < sg.nc * kB2Sets; i += kB2CT) s_dx[i] = a.t_dx[sg.off_dx + i];
         for (int i = tid; i < sg.nc * kB2CW; i += kB2CT) s_code[i] = a.t_code[sg.off_code + i];
         for (int i = tid; i < sg.nl * kB2Sets; i += kB2CT) s_val[i] = a.t_val[sg.off_val + i];
-        for (int c = tid; c < sg.nc; c += kB2CT) s_slot[c] = make_int2(a.t_slot[sg.off_slot + 2 * c], a.t_slot[sg.off_slot + 2 * c + 1]);
+        for (int c = tid; c < sg.nc; c += kB2CT) s_slot[c] = reinterpret_cast<const int4*>(a.t_slot + sg.off_slot)[c];
+        for (int i = tid; i < sg.n_wide * (kB2Sets / 4); i += kB2CT) reinterpret_cast<uint32_t*>(s_rank8)[i] = reinterpret_cast<const uint32_t*>(a.t_rank8 + sg.off_rank8)[i];
         cur_sig = d.y; off_group = sg.off_group; cur_nl = sg.nl;
         asm volatile("bar.sync 1, %0;" ::"r"(kB2CT) : "memory");
       }
@@ -256,10 +266,31 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         // fmaf Horner on the set's segment, running products in the reference's slot order
         const float4* rows = reinterpret_cast<const float4*>(src) + lane;
         for (int c = gr.c0; active && !B2DBG(4) && c < gr.c1; ++c) {
-          const int2 si = s_slot[c];                    // {first staged row of the slot in this stage, distinct segments}
+          const int4 si = s_slot[c];                    // {first staged row of the slot in this stage, distinct segments, wide, uniform}
           const float4* rp = rows + si.x * kB2RowF4;
           const float4* dxv = reinterpret_cast<const float4*>(s_dx + c * kB2Sets + set0);
           const B2Row k0 = b2_row(rp);
+          if (si.w) {
+            // every set has this slot's parameter at the same value (an LLH scan of another parameter, sets that differ
+            // in a few parameters only): one polynomial, then the 16 products -- each set's product order is unchanged
+            const float d = *reinterpret_cast<const float*>(dxv);
+            const pk2 t = horner2(k0, pk2_make(d, d));
+            #pragma unroll
+            for (int q = 0; q < kB2SW; ++q) W[q] = pk2_mul(W[q], t);
+            continue;
+          }
+          if (si.y > 3) {
+            // a slot whose sets spread over more than three segments (the scanned parameter): row per set from its rank byte
+            const uint4 rk = *reinterpret_cast<const uint4*>(s_rank8 + si.z * kB2Sets + set0);
+            const uint32_t rw[4] = {rk.x, rk.y, rk.z, rk.w};
+            #pragma unroll
+            for (int q = 0; q < kB2SW; ++q) {
+              const uint32_t r = (rw[q >> 2] >> (8 * (q & 3))) & 0xffu;
+              const float d = reinterpret_cast<const float*>(dxv)[q];
+              W[q] = pk2_mul(W[q], horner2(b2_row(rp + r * kB2RowF4), pk2_make(d, d)));
+            }
+            continue;
+          }
           // 2 bits per set, warp-uniform; rank 0 = the slot's most popular segment
           const uint32_t code = si.y == 1 ? 0u : s_code[c * kB2CW + warp];
           if (code == 0u) {                             // all 16 sets of this warp on the slot's first row
@@ -419,11 +450,13 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   // 3. per signature and slot: distinct segments -> staged rows (most popular first); per set: dx and its rank
   std::vector<Batch2Sig> bs(n_sigs);
   std::vector<float> t_dx, t_val; std::vector<uint32_t> t_code; std::vector<int32_t> t_rowlist, t_slot; std::vector<Batch2Group> t_group;
+  std::vector<uint8_t> t_rank8;
   for (int g = 0; g < n_sigs; ++g) {
     const SigDesc& sd = h->sigs[g];
     const int32_t* pool = h->sig_pool.data() + sd.off;
     Batch2Sig& b = bs[g];
-    b.nc = sd.nc; b.nl = sd.nl; b.pad = 0;
+    b.nc = sd.nc; b.nl = sd.nl; b.n_wide = 0;
+    b.off_rank8 = static_cast<int64_t>(t_rank8.size());
     b.off_dx = static_cast<int64_t>(t_dx.size()); b.off_code = static_cast<int64_t>(t_code.size());
     b.off_val = static_cast<int64_t>(t_val.size()); b.off_rowlist = static_cast<int64_t>(t_rowlist.size());
     b.off_slot = static_cast<int64_t>(t_slot.size()); b.off_group = static_cast<int64_t>(t_group.size());
@@ -445,21 +478,32 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
         if (best < 0) break;
         rank_of[best] = n_rank++; slot_rows.push_back(segbase + best); used[best] = 0;
       }
-      if (n_rank > 3) return decline();      // this kernel stages at most three segments per slot
+      if (n_rank > kB2MaxRanks || n_rank > stage_rows) return decline();
+      int wide = -1;
+      if (n_rank > 3) {                                  // more than the 2-bit code word holds: a rank byte per set
+        if (b.n_wide == kB2MaxWide) return decline();
+        wide = b.n_wide++;
+        t_rank8.resize(t_rank8.size() + S, 0);
+      }
       if (cur.n_rows + n_rank > stage_rows) {            // close the group: its rows fill one ring stage
         cur.c1 = c; t_group.push_back(cur);
         cur = Batch2Group{c, c, 0, rows};
       }
-      t_slot.push_back(cur.n_rows); t_slot.push_back(n_rank);
+      const int slot_row = cur.n_rows;
       for (int32_t r : slot_rows) t_rowlist.push_back(r);
       cur.n_rows += n_rank; rows += n_rank;
+      bool uniform = n_rank == 1;
       for (int s = 0; s < S; ++s) {
         const int ss = s < n_sets ? s : n_sets - 1;           // padding sets repeat the last set (never filled)
         const int sg = seg[static_cast<size_t>(ss) * P + p];
-        t_code[b.off_code + static_cast<size_t>(c) * kB2CW + s / kB2SW] |= static_cast<uint32_t>(rank_of[sg]) << (2 * (s % kB2SW));
+        if (wide >= 0) t_rank8[static_cast<size_t>(b.off_rank8) + static_cast<size_t>(wide) * S + s] = static_cast<uint8_t>(rank_of[sg]);
+        else t_code[b.off_code + static_cast<size_t>(c) * kB2CW + s / kB2SW] |= static_cast<uint32_t>(rank_of[sg]) << (2 * (s % kB2SW));
         // dx = ParamValues[Param] - coeff_x[Param*_max_knots+segment]   (Splines/SplineMonolith.cpp:759), float
-        t_dx[b.off_dx + static_cast<size_t>(c) * S + s] = val[static_cast<size_t>(ss) * P + p] - h->coeff_x[static_cast<size_t>(p) * h->Kmax + sg];
+        const float dxs = val[static_cast<size_t>(ss) * P + p] - h->coeff_x[static_cast<size_t>(p) * h->Kmax + sg];
+        t_dx[b.off_dx + static_cast<size_t>(c) * S + s] = dxs;
+        uniform = uniform && std::memcmp(&dxs, &t_dx[b.off_dx + static_cast<size_t>(c) * S], sizeof(float)) == 0;
       }
+      t_slot.push_back(slot_row); t_slot.push_back(n_rank); t_slot.push_back(wide); t_slot.push_back(uniform ? 1 : 0);
     }
     if (sd.nc > 0) { cur.c1 = sd.nc; t_group.push_back(cur); }
     b.n_groups = static_cast<int32_t>(t_group.size() - static_cast<size_t>(b.off_group));
@@ -489,6 +533,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   CK(grow(&h->bt_val, h->bt_val_cap, t_val.size() * 4 + 16));
   CK(grow(&h->bt_rowlist, h->bt_rowlist_cap, t_rowlist.size() * 4 + 16));
   CK(grow(&h->bt_slot, h->bt_slot_cap, t_slot.size() * 4 + 16));
+  CK(grow(&h->bt_rank8, h->bt_rank8_cap, t_rank8.size() + 256));
   CK(grow(&h->bt_group, h->bt_group_cap, t_group.size() * sizeof(Batch2Group) + 16));
   CK(grow(&h->bt_norm, h->bt_norm_cap, t_norm.size() * 4));
   CK(grow(&h->bt_sigs, h->bt_sigs_cap, bs.size() * sizeof(Batch2Sig)));
@@ -499,6 +544,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   if (!t_val.empty()) CK(cudaMemcpyAsync(h->bt_val, t_val.data(), t_val.size() * 4, cudaMemcpyHostToDevice, h->stream));
   if (!t_rowlist.empty()) CK(cudaMemcpyAsync(h->bt_rowlist, t_rowlist.data(), t_rowlist.size() * 4, cudaMemcpyHostToDevice, h->stream));
   if (!t_slot.empty()) CK(cudaMemcpyAsync(h->bt_slot, t_slot.data(), t_slot.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  if (!t_rank8.empty()) CK(cudaMemcpyAsync(h->bt_rank8, t_rank8.data(), t_rank8.size(), cudaMemcpyHostToDevice, h->stream));
   if (!t_group.empty()) CK(cudaMemcpyAsync(h->bt_group, t_group.data(), t_group.size() * sizeof(Batch2Group), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->bt_norm, t_norm.data(), t_norm.size() * 4, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->bt_sigs, bs.data(), bs.size() * sizeof(Batch2Sig), cudaMemcpyHostToDevice, h->stream));
@@ -516,7 +562,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   a.t_dx = static_cast<const float*>(h->bt_dx); a.t_code = static_cast<const uint32_t*>(h->bt_rowoff);
   a.t_val = static_cast<const float*>(h->bt_val); a.t_rowlist = static_cast<const int32_t*>(h->bt_rowlist);
   a.t_norm = static_cast<const float*>(h->bt_norm); a.t_slot = static_cast<const int32_t*>(h->bt_slot);
-  a.t_group = static_cast<const Batch2Group*>(h->bt_group);
+  a.t_group = static_cast<const Batch2Group*>(h->bt_group); a.t_rank8 = static_cast<const uint8_t*>(h->bt_rank8);
   a.n_norm = Nn; a.n_sets = n_sets; a.max_nc = h->max_nc; a.max_nl = h->max_nl;
   a.n_stages = n_stages; a.stage_rows = stage_rows;
   { const char* dbg = experiment_env("M3B_BATCH_DBG"); a.dbg = dbg ? atoi(dbg) : 0; }

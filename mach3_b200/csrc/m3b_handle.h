@@ -197,9 +197,9 @@ struct m3b_handle {
   double* llh_host_override = nullptr;
   // staging of the batched kernel (m3b_batch.cu), grown on demand
   void *bt_dx = nullptr, *bt_rowoff = nullptr, *bt_val = nullptr, *bt_rowlist = nullptr, *bt_norm = nullptr, *bt_sigs = nullptr,
-       *bt_hist = nullptr, *bt_llh = nullptr, *bt_slot = nullptr, *bt_group = nullptr;
+       *bt_hist = nullptr, *bt_llh = nullptr, *bt_slot = nullptr, *bt_group = nullptr, *bt_rank8 = nullptr;
   size_t bt_dx_cap = 0, bt_rowoff_cap = 0, bt_val_cap = 0, bt_rowlist_cap = 0, bt_norm_cap = 0, bt_sigs_cap = 0, bt_hist_cap = 0,
-         bt_llh_cap = 0, bt_slot_cap = 0, bt_group_cap = 0;
+         bt_llh_cap = 0, bt_slot_cap = 0, bt_group_cap = 0, bt_rank8_cap = 0;
 
   uint64_t steps = 0, launches = 0;
 
