@@ -66,6 +66,7 @@ struct Batch2Sig {
   int64_t off_slot;      // int32    [nc][4]      {row offset inside its group's stage, distinct segments, wide index or -1,
                          //                        1 = every set has the same segment and dx: one polynomial serves all sets}
   int64_t off_rank8;     // uint8    [n_wide][256] rank of every set's segment, for the slots with more than three
+  uint64_t lin_uniform;  // bit l: every set has the same value of TF1 slot l's parameter (l < 64)
   int64_t off_group;     // Batch2Group [n_groups]
 };
 
@@ -76,6 +77,7 @@ struct Batch2Args {
   const float* t_norm;             // [n_norm][256]
   int32_t n_norm, n_sets, max_nc, max_nl;
   int32_t n_stages, stage_rows;
+  int32_t norm_uniform;            // every set has the same normalisation parameters: the norm product is formed once per event
   int32_t dbg;                     // experiments build only (timing ablations, scripts/batch_ablation.py; results are wrong
                                    // when set): 1 no atomics, 2 no epilogue, 4 no spline arithmetic, 8 no re-pack / second barrier
   const int32_t* bin; const float* osc; const int32_t* osc_idx; const float* static_w;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
     // ---------------------------------------------------------------- consumers: lane = 2 events, warp = 16 sets
     const int set0 = warp * kB2SW;
     const bool active = set0 < a.n_sets;                // warps whose sets are all padding only keep the ring moving
-    int stage = 0; uint32_t phase = 0; int cur_sig = -1, cur_nl = 0; int64_t off_group = 0;
+    int stage = 0; uint32_t phase = 0; int cur_sig = -1, cur_nl = 0; int64_t off_group = 0; uint64_t lin_uniform = 0;
     pk2 W[kB2SW];                                       // running products: lo = event lane, hi = event lane + 32
     const pk2 one2 = pk2_make(1.0f, 1.0f);
     #pragma unroll
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         for (int i = tid; i < sg.nl * kB2Sets; i += kB2CT) s_val[i] = a.t_val[sg.off_val + i];
         for (int c = tid; c < sg.nc; c += kB2CT) s_slot[c] = reinterpret_cast<const int4*>(a.t_slot + sg.off_slot)[c];
         for (int i = tid; i < sg.n_wide * (kB2Sets / 4); i += kB2CT) reinterpret_cast<uint32_t*>(s_rank8)[i] = reinterpret_cast<const uint32_t*>(a.t_rank8 + sg.off_rank8)[i];
-        cur_sig = d.y; off_group = sg.off_group; cur_nl = sg.nl;
+        cur_sig = d.y; off_group = sg.off_group; cur_nl = sg.nl; lin_uniform = sg.lin_uniform;
         asm volatile("bar.sync 1, %0;" ::"r"(kB2CT) : "memory");
       }
       unsigned char* src = ring + static_cast<size_t>(stage) * stage_bytes;
@@ -364,6 +366,13 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
           const float4* vv = reinterpret_cast<const float4*>(s_val + l * kB2Sets + set0);
           // fmaf(a, x, b) (Splines/SplineMonolith.cpp:800) for both events: a, b packed over the events, x per set
           const pk2 a2 = pk2_make(c0.x, c1.x), b2 = pk2_make(c0.y, c1.y);
+          if (l < 64 && ((lin_uniform >> l) & 1ull)) {          // same parameter value in every set: one evaluation
+            const float x = *reinterpret_cast<const float*>(vv);
+            const pk2 t = pk2_ffma(a2, pk2_make(x, x), b2);
+            #pragma unroll
+            for (int q = 0; q < kB2SW; ++q) W[q] = pk2_mul(W[q], t);
+            continue;
+          }
           #pragma unroll
           for (int j = 0; j < kB2SW / 4; ++j) {
             const float4 v = vv[j];
@@ -382,14 +391,27 @@ __global__ void __launch_bounds__(kB2CT, 1) fill_batch2_kernel(const __grid_cons
         double* h0 = a.hist + static_cast<int64_t>(bin0 >= 0 ? bin0 : 0) * kB2Sets + set0;
         double* h1 = a.hist + static_cast<int64_t>(bin1 >= 0 ? bin1 : 0) * kB2Sets + set0;
         // two passes, so the 16 sets' shared-memory look-ups and products are independent of the atomics' ordering
-        #pragma unroll
-        for (int q = 0; q < kB2SW; ++q) {
-          float w0 = 1.0f, w1 = 1.0f;
+        if (a.norm_uniform) {                              // the norm product is the same for every set: formed once
+          float wn0 = 1.0f, wn1 = 1.0f;
           #pragma unroll
-          for (int j = 0; j < 4; ++j) { w0 *= s_norm[np0[j] + q * nnp]; w1 *= s_norm[np1[j] + q * nnp]; }
-          w0 *= osc0; w0 *= pk2_lo(W[q]); w0 *= st0;
-          w1 *= osc1; w1 *= pk2_hi(W[q]); w1 *= st1;
-          W[q] = pk2_make(w0, w1);
+          for (int j = 0; j < 4; ++j) { wn0 *= s_norm[np0[j]]; wn1 *= s_norm[np1[j]]; }
+          #pragma unroll
+          for (int q = 0; q < kB2SW; ++q) {
+            float w0 = wn0, w1 = wn1;
+            w0 *= osc0; w0 *= pk2_lo(W[q]); w0 *= st0;
+            w1 *= osc1; w1 *= pk2_hi(W[q]); w1 *= st1;
+            W[q] = pk2_make(w0, w1);
+          }
+        } else {
+          #pragma unroll
+          for (int q = 0; q < kB2SW; ++q) {
+            float w0 = 1.0f, w1 = 1.0f;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) { w0 *= s_norm[np0[j] + q * nnp]; w1 *= s_norm[np1[j] + q * nnp]; }
+            w0 *= osc0; w0 *= pk2_lo(W[q]); w0 *= st0;
+            w1 *= osc1; w1 *= pk2_hi(W[q]); w1 *= st1;
+            W[q] = pk2_make(w0, w1);
+          }
         }
         #pragma unroll
         for (int q = 0; q < kB2SW; ++q) {
@@ -508,14 +530,26 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
     if (sd.nc > 0) { cur.c1 = sd.nc; t_group.push_back(cur); }
     b.n_groups = static_cast<int32_t>(t_group.size() - static_cast<size_t>(b.off_group));
     if (b.n_groups > kB2MaxGroups) return decline();
+    b.lin_uniform = 0;
     for (int l = 0; l < sd.nl; ++l) {
       const int p = pool[2 * sd.nc + l];
-      for (int s = 0; s < S; ++s) t_val[b.off_val + static_cast<size_t>(l) * S + s] = val[static_cast<size_t>(s < n_sets ? s : n_sets - 1) * P + p];
+      bool uniform = true;
+      for (int s = 0; s < S; ++s) {
+        const float v = val[static_cast<size_t>(s < n_sets ? s : n_sets - 1) * P + p];
+        t_val[b.off_val + static_cast<size_t>(l) * S + s] = v;
+        uniform = uniform && std::memcmp(&v, &t_val[b.off_val + static_cast<size_t>(l) * S], sizeof(float)) == 0;
+      }
+      if (uniform && l < 64) b.lin_uniform |= 1ull << l;
     }
   }
   std::vector<float> t_norm(static_cast<size_t>(std::max(Nn, 1)) * S, 1.f);
+  bool norm_uniform = true;
   for (int n = 0; n < Nn; ++n)
-    for (int s = 0; s < S; ++s) t_norm[static_cast<size_t>(n) * S + s] = static_cast<float>(norm_pars[static_cast<size_t>(s < n_sets ? s : n_sets - 1) * Nn + n]);
+    for (int s = 0; s < S; ++s) {
+      const float v = static_cast<float>(norm_pars[static_cast<size_t>(s < n_sets ? s : n_sets - 1) * Nn + n]);
+      t_norm[static_cast<size_t>(n) * S + s] = v;
+      norm_uniform = norm_uniform && std::memcmp(&v, &t_norm[static_cast<size_t>(n) * S], sizeof(float)) == 0;
+    }
   const int smem = tables_bytes + n_stages * stage_rows * kB2RowF4 * 16;
   // 4. device staging (grown on demand, kept in the handle; shared with the first kernel's buffers)
   auto grow = [&](void** p, size_t& cap, size_t bytes) -> cudaError_t {
@@ -564,7 +598,7 @@ int m3b_batch2_try(m3b_handle* h, int32_t n_sets, const double* spline_pars, con
   a.t_norm = static_cast<const float*>(h->bt_norm); a.t_slot = static_cast<const int32_t*>(h->bt_slot);
   a.t_group = static_cast<const Batch2Group*>(h->bt_group); a.t_rank8 = static_cast<const uint8_t*>(h->bt_rank8);
   a.n_norm = Nn; a.n_sets = n_sets; a.max_nc = h->max_nc; a.max_nl = h->max_nl;
-  a.n_stages = n_stages; a.stage_rows = stage_rows;
+  a.n_stages = n_stages; a.stage_rows = stage_rows; a.norm_uniform = norm_uniform ? 1 : 0;
   { const char* dbg = experiment_env("M3B_BATCH_DBG"); a.dbg = dbg ? atoi(dbg) : 0; }
   a.bin = h->d_bin; a.osc = h->use_osc ? h->d_osc : nullptr; a.osc_idx = h->d_osc_idx; a.static_w = h->d_static;
   a.norm_idx = h->d_norm_idx; a.norm_slots = h->norm_slots; a.e_pad = h->e_pad; a.n_events = h->n_events;
